@@ -1,0 +1,42 @@
+"""Shared helpers for tests, the golden generator and bench (seeded synthetic inputs)."""
+import math
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+HRFP_LAYERS = ((64, 64, 1), (64, 64, 1), (64, 128, 2), (128, 256, 2),
+               (256, 128, 1), (128, 64, 1), (64, 64, 2), (64, 64, 2))
+
+
+def make_hrfp_params(seed: int, layers=HRFP_LAYERS):
+    """Frozen HRFP weights with the reference initialiser's distribution (mynn.py:57-74):
+    W ~ N(0, 2/(9 cin)), gamma ~ N(0, 0.5); drawn from numpy PCG64 so every box regenerates them."""
+    rng = np.random.default_rng(seed)
+    ws, gs = [], []
+    for cin, cout, _ in layers:
+        ws.append((rng.standard_normal((cout, cin, 3, 3)) * math.sqrt(2.0 / (9 * cin))).astype(np.float32))
+        gs.append((rng.standard_normal(cout) * 0.5).astype(np.float32))
+    return ws, gs
+
+
+def make_feat(seed: int, shape):
+    """Post-ReLU-like features with channel-varying statistics."""
+    rng = np.random.default_rng(seed)
+    n, c, h, w = shape
+    sig = rng.uniform(0.5, 1.5, size=(1, c, 1, 1))
+    mu = rng.standard_normal((1, c, 1, 1))
+    x = rng.standard_normal(shape) * sig + mu
+    return np.maximum(x, 0).astype(np.float32)
+
+
+def make_draws(seed: int, n: int, c: int):
+    rng = np.random.default_rng(seed)
+    alpha = (1.0 + 0.75 * rng.standard_normal((n, c))).astype(np.float32)
+    eps = (0.75 * rng.standard_normal((n, c))).astype(np.float32)
+    return alpha, eps
