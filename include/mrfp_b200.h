@@ -1,0 +1,119 @@
+/*
+ * mrfp_b200.h — C ABI of libmrfp_b200.so: the MRFP training-time hot path (NP+ and HRFP/HRFP+)
+ * as hand-written sm_100a CUDA kernels.
+ *
+ * The reference (airl-iisc/MRFP) has no FFI layer: its boundary for this path is the
+ * torch.nn.Module surface of `MRFPPlus` (/root/reference/deepv3.py:152-367).  Each entry point below
+ * replaces the ATen/cuDNN op sequence of one reference code span (cited per function); the Python
+ * host (`mrfp_b200/`) binds them with ctypes and wraps them in torch.autograd.Function objects that
+ * are called from a drop-in `MRFPPlus` module.  INTEGRATION.md shows the binding a maintainer of the
+ * reference would add.
+ *
+ * Conventions
+ *   - every data pointer is a DEVICE pointer owned by the caller (PyTorch tensors); the library
+ *     never allocates, frees or retains device memory and performs no host<->device copy;
+ *   - tensors are contiguous fp32 NCHW at the boundary, exactly what the reference passes around;
+ *   - all work is enqueued on `stream` (a cudaStream_t passed as void*); no host synchronisation;
+ *   - return value: 0 success; < 0 invalid argument (nothing was launched, see mrfp_strerror);
+ *     > 0 a cudaError_t raised by a launch / attribute call;
+ *   - re-entrant: no global mutable state except call_once-guarded per-device function attributes,
+ *     safe under nn.DataParallel's per-device host threads and under DDP.
+ */
+#ifndef MRFP_B200_H_
+#define MRFP_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MRFP_OK                 0
+#define MRFP_ERR_NULL_POINTER  (-1)
+#define MRFP_ERR_BAD_SHAPE     (-2)
+#define MRFP_ERR_WORKSPACE     (-3)   /* workspace / saved buffer too small or misaligned */
+#define MRFP_ERR_UNSUPPORTED   (-4)   /* math mode / channel count not built */
+#define MRFP_ERR_BAD_PLAN      (-5)
+#define MRFP_ERR_DRIVER        (-6)   /* cuTensorMapEncodeTiled entry point unavailable / failed */
+
+#define MRFP_MATH_FP32  0   /* CUDA-core direct convolution, fp32 activations (tight parity mode)   */
+#define MRFP_MATH_BF16  2   /* tcgen05 implicit-GEMM convolution, bf16 operands, fp32 accumulation  */
+
+int         mrfp_version(void);
+const char* mrfp_strerror(int rc);
+
+/* ------------------------------------------------------------------------------------------------
+ * NP+  — replaces MRFPPlus.Normalization_Perturbation_Plus, deepv3.py:268-277 (call sites :317-318,
+ * :334-335) and its autograd backward.
+ *
+ *   m[n,c]   = mean_hw x[n,c,:]                                   (:269)
+ *   d[c]     = std_n(m[:,c]) (unbiased);  s[c] = 1.5 d[c]/max_c d  (:272-273)
+ *   beta     = 1 + eps * s                                         (:275)   eps   = torch.normal(0,.75) draw
+ *   out      = alpha*x - alpha*m + beta*m                          (:276)   alpha = torch.normal(1,.75) draw
+ *
+ * The two Gaussian draws are made by the host with torch's RNG (parity with the reference's RNG
+ * stream) and passed in as (N,C) arrays.  One cooperative persistent kernel: phase A plane sums ->
+ * grid barrier -> every CTA derives the (N,C) statistics -> phase B rewrite, re-reading the tail of
+ * phase A from shared memory / L2.  N == 1 gives NaN exactly like torch.std (deepv3.py:272).
+ * ---------------------------------------------------------------------------------------------- */
+size_t mrfp_npplus_ws_bytes(int N, int C, int HW);
+
+int mrfp_npplus_fwd_f32(const float* x,       /* (N,C,HW) */
+                        const float* alpha,   /* (N,C) draw #1 */
+                        const float* eps,     /* (N,C) draw #2 */
+                        float* out,           /* (N,C,HW) */
+                        float* mean,          /* (N,C) out: plane means, saved for backward */
+                        float* beta,          /* (N,C) out (diagnostic; may be NULL) */
+                        void* ws, size_t ws_bytes, int N, int C, int HW, void* stream);
+
+/* gin = alpha*g + dL/dm/HW with the closed-form dL/dm through std and max. */
+int mrfp_npplus_bwd_f32(const float* gout, const float* alpha, const float* eps, const float* mean,
+                        float* gin, void* ws, size_t ws_bytes, int N, int C, int HW, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * HRFP — replaces the chain deepv3.py:320-327 (8 x conv3x3 -> F.interpolate(nearest) -> BatchNorm2d
+ * (train) -> ReLU on the layer types of deepv3.py:221-237), the adds deepv3.py:329-330 and
+ * :356-357, the BN running-stat side effect, and the autograd input-gradient of all of it.
+ * No weight / gamma / beta gradients exist (requires_grad_(False), deepv3.py:221-237).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct mrfp_hrfp_plan mrfp_hrfp_plan_t;   /* opaque host-side geometry + launch plan */
+
+/* N: local batch; cin: channels of xp (64 for ResNet-50); (xh,xw): xp size; (h,w): image size —
+ * sizes follow deepv3.py:320-327: x1.205, x1.2, x1.2, (h/2,w/2), (h/2,w/2), x0.838, x0.798,
+ * (ceil(h/4),ceil(w/4)).  widths[4] = encoder channel counts (64,64,128,256 in the reference). */
+int  mrfp_hrfp_plan_create(mrfp_hrfp_plan_t** plan, int N, int cin, int xh, int xw, int h, int w,
+                           const int* widths, int math_mode);
+void mrfp_hrfp_plan_destroy(mrfp_hrfp_plan_t* plan);
+
+size_t mrfp_hrfp_plan_ws_bytes(const mrfp_hrfp_plan_t* plan);     /* scratch, fwd and bwd */
+size_t mrfp_hrfp_plan_saved_bytes(const mrfp_hrfp_plan_t* plan);  /* fwd -> bwd state       */
+size_t mrfp_hrfp_plan_lut_bytes(const mrfp_hrfp_plan_t* plan);    /* nearest-index tables   */
+/* writes the table blob into HOST memory; the caller uploads it once per plan */
+int    mrfp_hrfp_plan_write_luts(const mrfp_hrfp_plan_t* plan, void* host_dst, size_t bytes);
+/* per stage k (0..7): out[0..5] = cin, cout, dilation, conv_h, conv_w, out_h; out[6] = out_w */
+int    mrfp_hrfp_plan_stage(const mrfp_hrfp_plan_t* plan, int k, int* out7);
+
+/* Forward.  W[k]: (cout,cin,3,3); gamma/beta[k]: (cout); running_mean/var[k]: (cout) updated in
+ * place with `momentum` (unbiased variance) or skipped when the array pointer is NULL.
+ *   ocout      (N,cin,xh,xw)      = OCout (+ x_add when x_add != NULL: deepv3.py:330)
+ *   ocout_dec  (N,widths[3],h/2,w/2) = OCout_dec, or NULL when HRFP+ is off
+ * ocout == NULL runs the encoder half only (decoder output unused when p >= 0.5). */
+int mrfp_hrfp_fwd(const mrfp_hrfp_plan_t* plan, const float* xp,
+                  const float* const* W, const float* const* gamma, const float* const* beta,
+                  float* const* running_mean, float* const* running_var, float momentum, float eps,
+                  const float* x_add, float* ocout, float* ocout_dec,
+                  const void* lut, void* saved, void* ws, void* stream);
+
+/* Input gradient wrt xp.  g_ocout / g_ocout_dec may be NULL (that output unused). */
+int mrfp_hrfp_bwd(const mrfp_hrfp_plan_t* plan, const float* g_ocout, const float* g_ocout_dec,
+                  const float* const* gamma, const void* lut, const void* saved,
+                  float* g_xp, void* ws, void* stream);
+
+/* HRFP+ skip add, deepv3.py:357: out = dec1_up + ocout_dec (both (N,C,H,W) fp32). */
+int mrfp_add_f32(const float* a, const float* b, float* out, size_t n, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MRFP_B200_H_ */

@@ -1,0 +1,69 @@
+"""ctypes binding of libmrfp_b200.so (the C ABI declared in include/mrfp_b200.h).
+
+There is no fallback: if the shared library is missing or a symbol is absent, importing the ops fails
+loudly.  `python -m mrfp_b200.build` (or `__graft_entry__.build()`) produces the library in-tree.
+"""
+import ctypes
+import os
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG, "lib", "libmrfp_b200.so")
+
+c_float_p = ctypes.c_void_p     # device pointers travel as integers (tensor.data_ptr())
+c_void_pp = ctypes.POINTER(ctypes.c_void_p)
+
+# name -> (restype, argtypes); mirrors include/mrfp_b200.h one to one
+SIGNATURES = {
+    "mrfp_version": (ctypes.c_int, []),
+    "mrfp_strerror": (ctypes.c_char_p, [ctypes.c_int]),
+    "mrfp_npplus_ws_bytes": (ctypes.c_size_t, [ctypes.c_int, ctypes.c_int, ctypes.c_int]),
+    "mrfp_npplus_fwd_f32": (ctypes.c_int, [c_float_p, c_float_p, c_float_p, c_float_p, c_float_p, c_float_p,
+                                           ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int, ctypes.c_int,
+                                           ctypes.c_int, ctypes.c_void_p]),
+    "mrfp_npplus_bwd_f32": (ctypes.c_int, [c_float_p, c_float_p, c_float_p, c_float_p, c_float_p,
+                                           ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int, ctypes.c_int,
+                                           ctypes.c_int, ctypes.c_void_p]),
+    "mrfp_hrfp_plan_create": (ctypes.c_int, [c_void_pp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                             ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_int), ctypes.c_int]),
+    "mrfp_hrfp_plan_destroy": (None, [ctypes.c_void_p]),
+    "mrfp_hrfp_plan_ws_bytes": (ctypes.c_size_t, [ctypes.c_void_p]),
+    "mrfp_hrfp_plan_saved_bytes": (ctypes.c_size_t, [ctypes.c_void_p]),
+    "mrfp_hrfp_plan_lut_bytes": (ctypes.c_size_t, [ctypes.c_void_p]),
+    "mrfp_hrfp_plan_write_luts": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t]),
+    "mrfp_hrfp_plan_stage": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.POINTER(ctypes.c_int)]),
+    "mrfp_hrfp_fwd": (ctypes.c_int, [ctypes.c_void_p, c_float_p, c_void_pp, c_void_pp, c_void_pp, c_void_pp,
+                                     c_void_pp, ctypes.c_float, ctypes.c_float, c_float_p, c_float_p, c_float_p,
+                                     ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
+    "mrfp_hrfp_bwd": (ctypes.c_int, [ctypes.c_void_p, c_float_p, c_float_p, c_void_pp, ctypes.c_void_p,
+                                     ctypes.c_void_p, c_float_p, ctypes.c_void_p, ctypes.c_void_p]),
+    "mrfp_add_f32": (ctypes.c_int, [c_float_p, c_float_p, c_float_p, ctypes.c_size_t, ctypes.c_void_p]),
+}
+
+_lib = None
+
+
+class MrfpError(RuntimeError):
+    pass
+
+
+def load():
+    """Loads the library once and binds every declared symbol (raises if any is missing)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.isfile(LIB_PATH):
+        raise MrfpError(f"{LIB_PATH} not found: build it with `python -m mrfp_b200.build` "
+                        "(there is no CPU / PyTorch fallback for the MRFP kernels)")
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)          # AttributeError if the symbol is not exported
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(rc: int, what: str):
+    if rc != 0:
+        msg = load().mrfp_strerror(rc).decode()
+        raise MrfpError(f"{what} failed: rc={rc} ({msg})")
