@@ -3,297 +3,459 @@
 //
 // Both directions are the same memory-bound shape:  y = a[n,c] * x + b[n,c]  where (a, b) depend on the
 // plane sums of x for ALL planes of the local batch (batch std of the plane means + global channel max).
-// One cooperative persistent kernel, one CTA per SM:
-//   phase A  each CTA streams its contiguous range of "units" (a unit = <= 32 KiB slice of one plane = four
-//            128-bit loads per thread), fp32 per-thread partials -> warp-shuffle tree in double -> one partial
-//            per unit; the loads of unit u+1 are issued before the reduction barrier of unit u, and the LAST
-//            units of the range are kept in shared memory (up to 7 x 32 KiB per SM);
+// One cooperative persistent kernel, one CTA per SM, each CTA owning a contiguous range of "units"
+// (a unit = <= 32 KiB slice of one plane):
+//   phase A  a producer thread streams the units into a shared-memory ring with 1-D TMA bulk copies
+//            (cp.async.bulk + mbarrier complete_tx); 16 consumer warps reduce each unit from shared memory
+//            (128-bit LDS, fp32 lane partials, double warp-shuffle tree); the producer folds the 16 warp
+//            partials of a unit when it recycles the slot.  The LAST units of the range stay resident in the
+//            ring (up to 7 x 32 KiB per SM);
 //   barrier  grid-wide (cooperative groups);
-//   stats    every CTA derives d[c], max_c d (and the backward's extra reductions) from the unit partials
-//            (<= N*C*K doubles, L2 resident) and the (a, b) pair of each plane it owns;
-//   phase B  the CTA walks its range BACKWARDS: first the units still in shared memory (no re-read at all),
-//            then the rest, most-recently-read first so the re-read is served from L2 while it lasts;
-//            streaming (evict-first) stores.
+//   stats    every CTA derives d[c], max_c d, arg-max and the backward's extra reductions from the unit
+//            partials (<= N*C*K doubles, L2 resident) and the (a, b) pair of each plane it owns;
+//   phase B  the CTA walks its range BACKWARDS: first the units still resident in shared memory (no re-read
+//            at all), then the rest, most-recently-read first so the re-read is served from L2 while it
+//            lasts; 128-bit streaming (evict-first) stores.
 // HBM traffic therefore sits between 1R+1W (everything cached on chip) and 2R+1W.
+// A register-staged variant of the same algorithm (no TMA; scalar loads) handles planes whose size or base
+// address is not a multiple of 16 bytes.
 #include "common.cuh"
 #include <cooperative_groups.h>
 #include <math.h>
+#include <stdlib.h>
 
 namespace cg = cooperative_groups;
 
 namespace mrfp {
 namespace {
 
-constexpr int kThreads = 512;
-constexpr int kWarps = kThreads / 32;
-constexpr int kUnitBytes = 32 * 1024;  // slice of a plane handled as one unit: kBatch vectors per thread
-constexpr int kBatch = 4;
+constexpr int kConsumers = 512;                 // consumer threads (16 warps)
+constexpr int kWarps = kConsumers / 32;
+constexpr int kBatch = 4;                       // vectors per consumer thread per unit
+constexpr int kUnitVecs = kConsumers * kBatch;  // 2048 float4 = 32 KiB
+constexpr int kMaxSlots = 7;
 
 struct NpGeom {
   int N, C, HW;
   int P;         // planes = N*C
   int K;         // units per plane
-  int Q;         // elements of vector type per unit (last unit of a plane may be shorter)
+  int Q;         // vectors per unit (last unit of a plane may be shorter)
   int HWV;       // HW / VEC
   long long U;   // total units = P*K
-  int cache_units;   // units kept in shared memory per CTA
+  int slots;     // ring slots / resident units per CTA
   int max_local_planes;
+  int grid;      // CTAs (needed to locate per-CTA plane partials)
+  int per_cta;   // 1: ps[b*max_local_planes + j] = CTA b's partial of its j-th plane; 0: ps[u] per unit
+  int keep_units;  // phase-A units per CTA loaded with an L2 evict_last hint (re-read in phase B)
+  long long scratch_off;   // doubles: ps[0..scratch_off) partials, then pm[P], then chan[4*C]
 };
 
-template <int VEC> struct VecT;
-template <> struct VecT<4> {
-  using type = float4;
-  static __device__ __forceinline__ float4 ld(const float4* p) { return ld_stream_f4(p); }
-  static __device__ __forceinline__ void st(float4* p, const float4& v) { st_stream_f4(p, v); }
-  static __device__ __forceinline__ float sum(const float4& v) { return (v.x + v.y) + (v.z + v.w); }
-  static __device__ __forceinline__ float4 fma(const float4& v, float a, float b) {
-    return make_float4(fmaf(a, v.x, b), fmaf(a, v.y, b), fmaf(a, v.z, b), fmaf(a, v.w, b));
-  }
-};
-template <> struct VecT<1> {
-  using type = float;
-  static __device__ __forceinline__ float ld(const float* p) { return ld_stream_f1(p); }
-  static __device__ __forceinline__ void st(float* p, const float& v) { st_stream_f1(p, v); }
-  static __device__ __forceinline__ float sum(const float& v) { return v; }
-  static __device__ __forceinline__ float fma(const float& v, float a, float b) { return fmaf(a, v, b); }
-};
-
-__device__ __forceinline__ double block_sum(double v, double* red /* kWarps */) {
-  v = warp_sum(v);
-  __syncthreads();
-  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
-  __syncthreads();
-  double t = 0;
-#pragma unroll
-  for (int i = 0; i < kWarps; ++i) t += red[i];
-  return t;
-}
-
+// ------------------------------------------------------------------------------------------------------
+// statistics shared by both kernels
+// ------------------------------------------------------------------------------------------------------
 // unit partials are written by other CTAs earlier in this launch: read through L2 (ld.global.cg)
-__device__ __forceinline__ double unit_total(const double* ps, int plane, int K) {
+__device__ __forceinline__ double plane_total(const double* ps, int plane, const NpGeom& g) {
   double s = 0;
-  for (int k = 0; k < K; ++k) s += __ldcg(ps + (long long)plane * K + k);
+  if (g.per_cta) {
+    // CTAs own contiguous unit ranges [U*b/G, U*(b+1)/G): sum the partial of every CTA touching the plane
+    const long long ua = (long long)plane * g.K, ub = ua + g.K - 1;
+    const int b0 = (int)(((ua + 1) * g.grid - 1) / g.U), b1 = (int)(((ub + 1) * g.grid - 1) / g.U);
+    for (int b = b0; b <= b1; ++b) {
+      const int first_plane = (int)((g.U * b / g.grid) / g.K);
+      s += __ldcg(ps + (long long)b * g.max_local_planes + (plane - first_plane));
+    }
+  } else {
+#pragma unroll 4
+    for (int k = 0; k < g.K; ++k) s += __ldcg(ps + (long long)plane * g.K + k);
+  }
   return s;
 }
 
-// per-channel statistics of the plane means over the local batch (deepv3.py:272): mbar, d = unbiased std
-struct ChanStat {
-  double mbar, d, dLds;
-};
-
-template <bool BWD>
-__device__ __forceinline__ ChanStat channel_stat(const double* ps, const float* __restrict__ mean_in,
-                                                 const float* __restrict__ eps, const NpGeom& g, int c) {
-  ChanStat r;
-  const double inv_hw = 1.0 / (double)g.HW;
-  double s = 0;
-  for (int n = 0; n < g.N; ++n) {
-    const int p = n * g.C + c;
-    s += BWD ? (double)mean_in[p] : unit_total(ps, p, g.K) * inv_hw;
-  }
-  r.mbar = s / (double)g.N;
-  double q = 0, l = 0;
-  for (int n = 0; n < g.N; ++n) {
-    const int p = n * g.C + c;
-    const double m = BWD ? (double)mean_in[p] : unit_total(ps, p, g.K) * inv_hw;
-    q += (m - r.mbar) * (m - r.mbar);
-    if (BWD) l += (double)eps[p] * m * unit_total(ps, p, g.K);   // dL/ds[c] = sum_n eps*m*G
-  }
-  r.d = sqrt(q / (double)(g.N - 1));   // N == 1 -> 0/0 -> NaN, as torch.std
-  r.dLds = l;
-  return r;
+__device__ __forceinline__ double group_sum(double v, int width) {   // xor-butterfly inside aligned lane groups
+  for (int o = width >> 1; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
 }
 
-template <int VEC, bool BWD>
-__global__ void __launch_bounds__(kThreads, 1)
-npplus_kernel(const float* __restrict__ x, const float* __restrict__ alpha, const float* __restrict__ eps,
-              const float* __restrict__ mean_in, float* __restrict__ out, float* __restrict__ mean_out,
-              float* __restrict__ beta_out, double* __restrict__ ps, const NpGeom g) {
-  using V = typename VecT<VEC>::type;
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  V* cache = reinterpret_cast<V*>(smem_raw);
-  float2* coef = reinterpret_cast<float2*>(smem_raw + (size_t)g.cache_units * g.Q * sizeof(V));
-  __shared__ double red[kWarps];
-  __shared__ double red2[2][kWarps];
-  __shared__ double s_dmax, s_T;
-  __shared__ int s_cstar;
+struct NpShared {
+  double w_best[kWarps + 1], w_tsum[kWarps + 1];
+  int w_c[kWarps + 1], w_nan[kWarps + 1];
+  double dmax, T;
+  int cstar;
+};
 
-  const V* xv = reinterpret_cast<const V*>(x);
-  V* ov = reinterpret_cast<V*>(out);
+// Stage 1 (grid-parallel, between two grid barriers): per-channel statistics of the plane means over the
+// local batch (deepv3.py:272) and the plane totals, written once to global scratch:
+//   pm[p]      = plane total (sum over HW) of plane p
+//   chan[4c..] = { mbar, d = unbiased std of the plane means, dL/ds (backward only), - }
+template <bool BWD>
+__device__ void np_stage1(const double* ps, const float* __restrict__ mean_in, const float* __restrict__ eps,
+                          const NpGeom& g, double* pm, double* chan, int nthreads) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = nthreads >> 5;
+  const double inv_hw = 1.0 / (double)g.HW;
+  // lanes = (channel sub-group, batch index): group width = pow2 >= N (capped at 32)
+  int gw = 1;
+  while (gw < g.N && gw < 32) gw <<= 1;
+  const int cpw = 32 / gw, sub = lane % gw, cg_i = lane / gw;
+  const int gwarp = blockIdx.x * nwarps + warp, gwarps = gridDim.x * nwarps;
+  for (int cbase = gwarp * cpw; cbase < g.C; cbase += gwarps * cpw) {     // warp-uniform trip count
+    const int c = cbase + cg_i;
+    const bool valid = c < g.C;
+    double s = 0, m0 = 0, G0 = 0;
+    if (valid) {
+      for (int n = sub; n < g.N; n += gw) {
+        const int p = n * g.C + c;
+        const double tot = plane_total(ps, p, g);
+        pm[p] = tot;
+        const double m = BWD ? (double)mean_in[p] : tot * inv_hw;
+        if (n == sub) { m0 = m; G0 = tot; }
+        s += m;
+      }
+    }
+    const double mbar = group_sum(s, gw) / (double)g.N;
+    double q = 0, l = 0;
+    if (valid) {
+      for (int n = sub; n < g.N; n += gw) {
+        const int p = n * g.C + c;
+        double m, G;
+        if (n == sub) { m = m0; G = G0; }
+        else { G = plane_total(ps, p, g); m = BWD ? (double)mean_in[p] : G * inv_hw; }
+        q += (m - mbar) * (m - mbar);
+        if (BWD) l += (double)eps[p] * m * G;                            // dL/ds[c] = sum_n eps*m*G
+      }
+    }
+    const double d = sqrt(group_sum(q, gw) / (double)(g.N - 1));         // N == 1 -> 0/0 -> NaN, as torch.std
+    const double dLds = BWD ? group_sum(l, gw) : 0.0;
+    if (valid && sub == 0) {
+      chan[4 * c + 0] = mbar;
+      chan[4 * c + 1] = d;
+      chan[4 * c + 2] = dLds;
+    }
+  }
+}
+
+// Stage 2 (every CTA): global max / arg-max of d and the backward's cross-channel sum, then
+// coef[j] = (a, b) for the planes pl0..pl1 touched by this CTA (one thread per plane).
+template <bool BWD>
+__device__ void np_stage2(const double* pm, const double* chan, const float* __restrict__ mean_in,
+                          const float* __restrict__ alpha, const float* __restrict__ eps,
+                          float* __restrict__ mean_out, float* __restrict__ beta_out, const NpGeom& g,
+                          long long u0, long long u1, float2* coef, NpShared& sh, int nthreads) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = nthreads >> 5;
+  const double inv_hw = 1.0 / (double)g.HW;
+  // this CTA's planes: issue their loads first so they overlap the block reduction
+  const int pl0 = (int)(u0 / g.K);
+  const int pl1 = (u1 > u0) ? (int)((u1 - 1) / g.K) : pl0 - 1;
+  double best = -1.0, tsum = 0.0;
+  int bestc = 0x7fffffff;
+  bool anynan = false;
+  for (int c = tid; c < g.C; c += nthreads) {
+    const double d = __ldcg(chan + 4 * c + 1);
+    if (d != d) anynan = true;
+    if (d > best) { best = d; bestc = c; }
+    if (BWD) tsum += __ldcg(chan + 4 * c + 2) * d;
+  }
+  // block arg-max (first index wins on ties), NaN-propagating like Tensor.max (deepv3.py:273)
+  for (int o = 16; o > 0; o >>= 1) {
+    const double ob = __shfl_xor_sync(0xffffffffu, best, o);
+    const int oc = __shfl_xor_sync(0xffffffffu, bestc, o);
+    const int on = __shfl_xor_sync(0xffffffffu, (int)anynan, o);
+    tsum += __shfl_xor_sync(0xffffffffu, tsum, o);
+    if (ob > best || (ob == best && oc < bestc)) { best = ob; bestc = oc; }
+    anynan = anynan || (on != 0);
+  }
+  if (lane == 0) { sh.w_best[warp] = best; sh.w_c[warp] = bestc; sh.w_nan[warp] = anynan; sh.w_tsum[warp] = tsum; }
+  __syncthreads();
+  if (tid == 0) {
+    double b = sh.w_best[0], t = sh.w_tsum[0];
+    int bc = sh.w_c[0], nn = sh.w_nan[0];
+    for (int i = 1; i < nwarps; ++i) {
+      if (sh.w_best[i] > b || (sh.w_best[i] == b && sh.w_c[i] < bc)) { b = sh.w_best[i]; bc = sh.w_c[i]; }
+      nn |= sh.w_nan[i];
+      t += sh.w_tsum[i];
+    }
+    sh.dmax = nn ? (double)NAN : b;
+    sh.cstar = bc;
+    sh.T = 1.5 * t / (sh.dmax * sh.dmax);     // sum_c dL/ds[c] * 1.5 * d[c] / dmax^2
+  }
+  __syncthreads();
+  const double dmax = sh.dmax;
+  for (int j = tid; j <= pl1 - pl0; j += nthreads) {
+    const int p = pl0 + j, c = p % g.C;
+    const double tot = __ldcg(pm + p);
+    const double mbar = __ldcg(chan + 4 * c + 0), d = __ldcg(chan + 4 * c + 1);
+    const double a = (double)alpha[p];
+    const double beta = 1.0 + (double)eps[p] * (d / dmax * 1.5);            // deepv3.py:273,275
+    double b;
+    if (!BWD) {
+      const double m = tot * inv_hw;
+      b = (beta - a) * m;                                                   // out = a*x + (beta-a)*m  (:276)
+      if ((long long)p * g.K >= u0) {   // the CTA owning unit 0 of the plane publishes the side outputs
+        mean_out[p] = (float)m;
+        if (beta_out) beta_out[p] = (float)beta;
+      }
+    } else {
+      const double m = (double)mean_in[p];
+      double dLdd = 1.5 / dmax * __ldcg(chan + 4 * c + 2);
+      if (c == sh.cstar) dLdd -= sh.T;
+      // torch's std_backward zero-fills where std == 0
+      const double dd_dm = (d == 0.0) ? 0.0 : (m - mbar) / ((double)(g.N - 1) * d);
+      const double dLdm = (beta - a) * tot + dLdd * dd_dm;
+      b = dLdm * inv_hw;
+    }
+    coef[j] = make_float2((float)a, (float)b);
+  }
+  __syncthreads();
+}
+
+// ------------------------------------------------------------------------------------------------------
+// mbarrier / bulk-copy primitives
+// ------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_load(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar,
+                                          uint64_t policy) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+               ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)), "l"(policy) : "memory");
+}
+
+// ------------------------------------------------------------------------------------------------------
+// TMA-ring kernel (planes and base addresses 16-byte aligned)
+// ------------------------------------------------------------------------------------------------------
+template <bool BWD>
+__global__ void __launch_bounds__(kConsumers + 32, 1)
+npplus_ring_kernel(const float* __restrict__ x, const float* __restrict__ alpha, const float* __restrict__ eps,
+                   const float* __restrict__ mean_in, float* __restrict__ out, float* __restrict__ mean_out,
+                   float* __restrict__ beta_out, double* ps, const NpGeom g, unsigned long long* trace) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int S = g.slots;
+  auto stamp = [&](int i) {
+    if (trace && threadIdx.x == 0) {
+      unsigned long long t;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+      trace[blockIdx.x * 8 + i] = t;
+    }
+  };
+  stamp(0);
+  float4* ring = reinterpret_cast<float4*>(smem_raw);                                   // S x 32 KiB
+  double* wp = reinterpret_cast<double*>(smem_raw + (size_t)S * kUnitVecs * 16);        // [S][kWarps]
+  uint64_t* full = reinterpret_cast<uint64_t*>(wp + S * kWarps);                        // [S]
+  uint64_t* empty = full + S;                                                           // [S]
+  float2* coef = reinterpret_cast<float2*>(empty + S);                                  // [max_local_planes]
+  __shared__ NpShared sh;
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const bool is_producer = warp == kWarps;
+  const long long u0 = g.U * (long long)blockIdx.x / gridDim.x;
+  const long long u1 = g.U * (long long)(blockIdx.x + 1) / gridDim.x;
+  const int nA = (int)(u1 - u0);
+  const int res = nA < S ? nA : S;                       // units resident after phase A
+  const float4* xv = reinterpret_cast<const float4*>(x);
+  float4* ov = reinterpret_cast<float4*>(out);
+
+  auto unit_len = [&](long long u) { return min(g.Q, g.HWV - (int)(u % g.K) * g.Q); };
+  auto unit_off = [&](long long u) { return (u / g.K) * (long long)g.HWV + (u % g.K) * (long long)g.Q; };
+  auto fills_a = [&](int s) { return s < nA ? (nA - s + S - 1) / S : 0; };   // phase-A fills of slot s
+
+  if (tid == 0) {
+    for (int s = 0; s < S; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], kWarps); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  // ---------------- phase A ----------------
+  // the producer folds the warp partials of each finished unit, in unit order, into one partial per plane
+  double run_total = 0;
+  const int pl0 = (int)(u0 / g.K);
+  auto fold = [&](int j) {
+    const int s = j % S;
+    double t = 0;
+#pragma unroll
+    for (int w = 0; w < kWarps; ++w) t += wp[s * kWarps + w];
+    run_total += t;
+    const long long u = u0 + j;
+    if ((int)(u % g.K) == g.K - 1 || j == nA - 1) {      // last unit of the plane, or of this CTA's range
+      ps[(long long)blockIdx.x * g.max_local_planes + ((int)(u / g.K) - pl0)] = run_total;
+      run_total = 0;
+    }
+  };
+  uint64_t pol_keep, pol_stream;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol_keep));
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol_stream));
+  if (is_producer) {
+    if (lane == 0) {
+      for (int j = 0; j < nA; ++j) {
+        const int s = j % S, k = j / S;
+        if (k > 0) {                                   // recycle: all 16 warps released fill k-1 of this slot
+          mbar_wait(&empty[s], (k - 1) & 1);
+          fold(j - S);
+        }
+        const long long u = u0 + j;
+        const uint32_t bytes = (uint32_t)unit_len(u) * 16u;
+        mbar_expect_tx(&full[s], bytes);
+        // units re-read from L2 in phase B are the newest non-resident ones
+        const bool keep = (j < nA - res) && (j >= nA - res - g.keep_units);
+        bulk_load(ring + (size_t)s * kUnitVecs, xv + unit_off(u), bytes, &full[s], keep ? pol_keep : pol_stream);
+      }
+    }
+  } else {
+    for (int j = 0; j < nA; ++j) {
+      const int s = j % S, k = j / S;
+      const int len = unit_len(u0 + j);
+      mbar_wait(&full[s], k & 1);
+      const float4* src = ring + (size_t)s * kUnitVecs;
+      float acc = 0.f;
+#pragma unroll
+      for (int b = 0; b < kBatch; ++b) {
+        const int i = tid + b * kConsumers;
+        if (i < len) { const float4 v = src[i]; acc += (v.x + v.y) + (v.z + v.w); }
+      }
+      const double w = warp_sum((double)acc);
+      if (lane == 0) {
+        wp[s * kWarps + warp] = w;
+        if (j < nA - res) mbar_arrive(&empty[s]);      // resident units are released in phase B
+      }
+    }
+  }
+  __syncthreads();
+  stamp(1);
+  if (is_producer && lane == 0)                        // partials of the resident units
+    for (int j = nA - res; j < nA; ++j) fold(j);
+  __threadfence();
+  cg::this_grid().sync();
+  stamp(2);
+
+  // ---------------- statistics ----------------
+  double* pm = ps + g.scratch_off;
+  double* chan = pm + g.P;
+  np_stage1<BWD>(ps, mean_in, eps, g, pm, chan, kConsumers + 32);
+  __threadfence();
+  cg::this_grid().sync();
+  np_stage2<BWD>(pm, chan, mean_in, alpha, eps, mean_out, beta_out, g, u0, u1, coef, sh, kConsumers + 32);
+  stamp(3);
+
+  // ---------------- phase B: newest units first ----------------
+  if (is_producer) {
+    if (lane == 0) {
+      for (int i = S; i < nA; ++i) {                   // refills (only when nA > S)
+        const int j = nA - 1 - i, s = j % S;
+        const int done = fills_a(s) - 1 + i / S - 1;   // index of the release that frees the slot
+        mbar_wait(&empty[s], done & 1);
+        const long long u = u0 + j;
+        const uint32_t bytes = (uint32_t)unit_len(u) * 16u;
+        mbar_expect_tx(&full[s], bytes);
+        bulk_load(ring + (size_t)s * kUnitVecs, xv + unit_off(u), bytes, &full[s], pol_stream);
+      }
+    }
+  } else {
+    for (int i = 0; i < nA; ++i) {
+      const int j = nA - 1 - i, s = j % S;
+      const long long u = u0 + j;
+      const int len = unit_len(u);
+      if (i >= S) mbar_wait(&full[s], (fills_a(s) + i / S - 1) & 1);
+      const float2 ab = coef[(int)(u / g.K) - pl0];
+      const float4* src = ring + (size_t)s * kUnitVecs;
+      float4 v[kBatch];
+#pragma unroll
+      for (int b = 0; b < kBatch; ++b) {
+        const int idx = tid + b * kConsumers;
+        if (idx < len) {
+          const float4 t = src[idx];
+          v[b] = make_float4(fmaf(ab.x, t.x, ab.y), fmaf(ab.x, t.y, ab.y), fmaf(ab.x, t.z, ab.y), fmaf(ab.x, t.w, ab.y));
+        }
+      }
+      if (i + S < nA) {                                // slot will be refilled: release it
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[s]);
+      }
+      float4* dst = ov + unit_off(u);
+#pragma unroll
+      for (int b = 0; b < kBatch; ++b) {
+        const int idx = tid + b * kConsumers;
+        if (idx < len) st_stream_f4(dst + idx, v[b]);
+      }
+    }
+  }
+  if (trace) { __syncthreads(); stamp(4); }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// register-staged scalar kernel (any HW, any alignment)
+// ------------------------------------------------------------------------------------------------------
+template <bool BWD>
+__global__ void __launch_bounds__(kConsumers, 1)
+npplus_scalar_kernel(const float* __restrict__ x, const float* __restrict__ alpha, const float* __restrict__ eps,
+                     const float* __restrict__ mean_in, float* __restrict__ out, float* __restrict__ mean_out,
+                     float* __restrict__ beta_out, double* ps, const NpGeom g, unsigned long long* /*trace*/) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  float* cache = reinterpret_cast<float*>(smem_raw);                                        // slots x Q floats
+  float2* coef = reinterpret_cast<float2*>(smem_raw + align_up((size_t)g.slots * g.Q * 4, 16));
+  __shared__ NpShared sh;
+  __shared__ double red2[2][kWarps];
+
   const int tid = threadIdx.x;
   const long long u0 = g.U * (long long)blockIdx.x / gridDim.x;
   const long long u1 = g.U * (long long)(blockIdx.x + 1) / gridDim.x;
-  const long long cache_from = u1 - g.cache_units;   // units >= cache_from live in shared memory
-
-  // ---------------- phase A: unit partial sums ----------------
+  const long long cache_from = u1 - g.slots;   // units >= cache_from live in shared memory
   auto unit_len = [&](long long u) { return min(g.Q, g.HWV - (int)(u % g.K) * g.Q); };
   auto unit_off = [&](long long u) { return (u / g.K) * (long long)g.HWV + (u % g.K) * (long long)g.Q; };
-  auto issue = [&](long long u, V (&r)[kBatch]) {
+
+  for (long long u = u0; u < u1; ++u) {
     const int len = unit_len(u);
-    const V* src = xv + unit_off(u);
-#pragma unroll
-    for (int j = 0; j < kBatch; ++j) {
-      const int i = tid + j * kThreads;
-      if (i < len) r[j] = VecT<VEC>::ld(src + i);
+    const float* src = x + unit_off(u);
+    float* keep = (u >= cache_from) ? cache + (size_t)(u - cache_from) * g.Q : nullptr;
+    float acc = 0.f;
+    for (int i = tid; i < len; i += kConsumers) {
+      const float v = ld_stream_f1(src + i);
+      acc += v;
+      if (keep) keep[i] = v;
     }
-  };
-  {
-    V cur[kBatch], nxt[kBatch];
-    if (u0 < u1) issue(u0, cur);
-    for (long long u = u0; u < u1; ++u) {
-      if (u + 1 < u1) issue(u + 1, nxt);          // in flight across the reduction barrier below
-      const int len = unit_len(u);
-      V* keep = (u >= cache_from) ? cache + (size_t)(u - cache_from) * g.Q : nullptr;
-      float acc[kBatch];
+    const double w = warp_sum((double)acc);
+    double* rb = red2[u & 1];
+    if ((tid & 31) == 0) rb[tid >> 5] = w;
+    __syncthreads();
+    if (tid == 0) {
+      double t = 0;
 #pragma unroll
-      for (int j = 0; j < kBatch; ++j) {
-        const int i = tid + j * kThreads;
-        acc[j] = 0.f;
-        if (i < len) {
-          acc[j] = VecT<VEC>::sum(cur[j]);
-          if (keep) keep[i] = cur[j];
-        }
-      }
-      const double w = warp_sum((double)acc[0] + (double)acc[1] + (double)acc[2] + (double)acc[3]);
-      double* rb = red2[u & 1];
-      if ((tid & 31) == 0) rb[tid >> 5] = w;
-      __syncthreads();
-      if (tid == 0) {
-        double t = 0;
-#pragma unroll
-        for (int i = 0; i < kWarps; ++i) t += rb[i];
-        ps[u] = t;
-      }
-#pragma unroll
-      for (int j = 0; j < kBatch; ++j) cur[j] = nxt[j];
+      for (int i = 0; i < kWarps; ++i) t += rb[i];
+      ps[u] = t;
     }
   }
   __threadfence();
   cg::this_grid().sync();
-
-  // ---------------- statistics (every CTA, redundantly; (N,C)-sized) ----------------
-  {
-    double best = -1.0;
-    int bestc = 0x7fffffff;
-    bool anynan = false;
-    for (int c = tid; c < g.C; c += kThreads) {
-      // forward derives the plane means from the unit partials; backward receives the saved means
-      const double d = channel_stat<BWD>(ps, mean_in, eps, g, c).d;
-      if (d != d) anynan = true;
-      if (d > best) { best = d; bestc = c; }
-    }
-    // block arg-max (first index wins on ties), NaN-propagating like Tensor.max (deepv3.py:273)
-    for (int o = 16; o > 0; o >>= 1) {
-      const double ob = __shfl_xor_sync(0xffffffffu, best, o);
-      const int oc = __shfl_xor_sync(0xffffffffu, bestc, o);
-      const bool on = __shfl_xor_sync(0xffffffffu, (int)anynan, o);
-      if (ob > best || (ob == best && oc < bestc)) { best = ob; bestc = oc; }
-      anynan = anynan || on;
-    }
-    __shared__ double w_best[kWarps];
-    __shared__ int w_c[kWarps];
-    __shared__ int w_nan[kWarps];
-    if ((tid & 31) == 0) { w_best[tid >> 5] = best; w_c[tid >> 5] = bestc; w_nan[tid >> 5] = anynan; }
-    __syncthreads();
-    if (tid == 0) {
-      double b = w_best[0]; int bc = w_c[0]; bool nn = w_nan[0];
-      for (int i = 1; i < kWarps; ++i) {
-        if (w_best[i] > b || (w_best[i] == b && w_c[i] < bc)) { b = w_best[i]; bc = w_c[i]; }
-        nn = nn || w_nan[i];
-      }
-      s_dmax = nn ? (double)NAN : b;
-      s_cstar = bc;
-    }
-    __syncthreads();
-    if (BWD) {
-      double t = 0;
-      const double dmax = s_dmax;
-      for (int c = tid; c < g.C; c += kThreads) {
-        const ChanStat cs = channel_stat<true>(ps, mean_in, eps, g, c);
-        t += cs.dLds * 1.5 * cs.d / (dmax * dmax);
-      }
-      const double T = block_sum(t, red);
-      if (tid == 0) s_T = T;
-      __syncthreads();
-    }
-  }
-  // (a, b) of every plane this CTA touches: one warp per plane, lanes over the batch dim
+  double* pm = ps + g.scratch_off;
+  double* chan = pm + g.P;
+  np_stage1<BWD>(ps, mean_in, eps, g, pm, chan, kConsumers);
+  __threadfence();
+  cg::this_grid().sync();
+  np_stage2<BWD>(pm, chan, mean_in, alpha, eps, mean_out, beta_out, g, u0, u1, coef, sh, kConsumers);
   const int pl0 = (int)(u0 / g.K);
-  const int pl1 = (u1 > u0) ? (int)((u1 - 1) / g.K) : pl0 - 1;
-  {
-    const double dmax = s_dmax;
-    const double inv_hw = 1.0 / (double)g.HW;
-    const int lane = tid & 31, warp = tid >> 5;
-    for (int j = warp; j <= pl1 - pl0; j += kWarps) {
-      const int p = pl0 + j, n = p / g.C, c = p % g.C;
-      double s = 0;
-      for (int nn = lane; nn < g.N; nn += 32)
-        s += BWD ? (double)mean_in[nn * g.C + c] : unit_total(ps, nn * g.C + c, g.K) * inv_hw;
-      const double mbar = warp_sum(s) / (double)g.N;
-      double q = 0, l = 0;
-      for (int nn = lane; nn < g.N; nn += 32) {
-        const int pp = nn * g.C + c;
-        const double m = BWD ? (double)mean_in[pp] : unit_total(ps, pp, g.K) * inv_hw;
-        q += (m - mbar) * (m - mbar);
-        if (BWD) l += (double)eps[pp] * m * unit_total(ps, pp, g.K);
-      }
-      const double d = sqrt(warp_sum(q) / (double)(g.N - 1));
-      const double dLds = BWD ? warp_sum(l) : 0.0;
-      if (lane == 0) {
-        const double a = (double)alpha[p];
-        const double beta = 1.0 + (double)eps[p] * (d / dmax * 1.5);            // deepv3.py:273,275
-        double b;
-        if (!BWD) {
-          const double m = unit_total(ps, p, g.K) * inv_hw;
-          b = (beta - a) * m;                                                   // out = a*x + (beta-a)*m  (:276)
-          if ((long long)p * g.K >= u0) {   // the CTA owning unit 0 of the plane publishes the side outputs
-            mean_out[p] = (float)m;
-            if (beta_out) beta_out[p] = (float)beta;
-          }
-        } else {
-          const double m = (double)mean_in[p];
-          const double G = unit_total(ps, p, g.K);
-          double dLdd = 1.5 / dmax * dLds;
-          if (c == s_cstar) dLdd -= s_T;
-          // torch's std_backward zero-fills where std == 0
-          const double dd_dm = (d == 0.0) ? 0.0 : (m - mbar) / ((double)(g.N - 1) * d);
-          const double dLdm = (beta - a) * G + dLdd * dd_dm;
-          b = dLdm * inv_hw;
-        }
-        coef[j] = make_float2((float)a, (float)b);
-      }
-    }
-  }
-  __syncthreads();
-
-  // ---------------- phase B: rewrite, newest units first ----------------
-  {
-    V cur[kBatch], nxt[kBatch];
-    long long u = u1 - 1;
-    for (; u >= u0 && u >= cache_from; --u) {     // still on chip: no re-read
-      const int len = unit_len(u);
-      const float2 ab = coef[(int)(u / g.K) - pl0];
-      const V* keep = cache + (size_t)(u - cache_from) * g.Q;
-      V* dst = ov + unit_off(u);
-#pragma unroll
-      for (int j = 0; j < kBatch; ++j) {
-        const int i = tid + j * kThreads;
-        if (i < len) VecT<VEC>::st(dst + i, VecT<VEC>::fma(keep[i], ab.x, ab.y));
-      }
-    }
-    if (u >= u0) issue(u, cur);
-    for (; u >= u0; --u) {
-      if (u - 1 >= u0) issue(u - 1, nxt);
-      const int len = unit_len(u);
-      const float2 ab = coef[(int)(u / g.K) - pl0];
-      V* dst = ov + unit_off(u);
-#pragma unroll
-      for (int j = 0; j < kBatch; ++j) {
-        const int i = tid + j * kThreads;
-        if (i < len) VecT<VEC>::st(dst + i, VecT<VEC>::fma(cur[j], ab.x, ab.y));
-      }
-#pragma unroll
-      for (int j = 0; j < kBatch; ++j) cur[j] = nxt[j];
+  for (long long u = u1 - 1; u >= u0; --u) {
+    const int len = unit_len(u);
+    const float2 ab = coef[(int)(u / g.K) - pl0];
+    float* dst = out + unit_off(u);
+    if (u >= cache_from) {
+      const float* keep = cache + (size_t)(u - cache_from) * g.Q;
+      for (int i = tid; i < len; i += kConsumers) st_stream_f1(dst + i, fmaf(ab.x, keep[i], ab.y));
+    } else {
+      const float* src = x + unit_off(u);
+      for (int i = tid; i < len; i += kConsumers) st_stream_f1(dst + i, fmaf(ab.x, ld_stream_f1(src + i), ab.y));
     }
   }
 }
@@ -304,40 +466,44 @@ struct NpLaunch {
   size_t smem;
 };
 
-int plan_launch(int N, int C, int HW, int vec, const DeviceInfo& di, NpLaunch* L) {
+void plan_launch(int N, int C, int HW, bool ring, const DeviceInfo& di, NpLaunch* L) {
   NpGeom& g = L->g;
+  const int vec = ring ? 4 : 1;
   g.N = N; g.C = C; g.HW = HW; g.P = N * C;
   g.HWV = HW / vec;
-  const int unit_elems = kThreads * kBatch;                      // vectors per unit (32 KiB for float4)
-  g.Q = g.HWV < unit_elems ? g.HWV : unit_elems;
+  g.Q = g.HWV < kUnitVecs ? g.HWV : kUnitVecs;
   g.K = (g.HWV + g.Q - 1) / g.Q;                                 // last unit of a plane may be shorter
   g.U = (long long)g.P * g.K;
   L->grid = (int)((g.U < di.sm_count) ? g.U : di.sm_count);
   const long long upc = (g.U + L->grid - 1) / L->grid;           // units per CTA (max)
+  const long long min_upc = g.U / L->grid;                       // ... (min)
   g.max_local_planes = (int)(upc / g.K + 2);
   const size_t coef_bytes = align_up((size_t)g.max_local_planes * sizeof(float2), 16);
-  const size_t budget = (size_t)di.max_smem_optin - 1024 /* static smem */ - coef_bytes;
-  const size_t unit_bytes = align_up((size_t)g.Q * 4 * vec, 16);
-  long long cu = (long long)(budget / unit_bytes);
-  if (cu > upc) cu = upc;
-  // every CTA must have at least cache_units units, or the cached window would start before u0
-  const long long min_upc = g.U / L->grid;
-  if (cu > min_upc) cu = min_upc;
-  g.cache_units = (int)cu;
-  L->smem = (size_t)g.cache_units * g.Q * 4 * vec + coef_bytes;
-  return MRFP_OK;
-}
-
-template <int VEC, bool BWD>
-int launch(const float* x, const float* alpha, const float* eps, const float* mean_in, float* out,
-           float* mean_out, float* beta_out, double* ps, const NpLaunch& L, cudaStream_t s) {
-  auto kern = npplus_kernel<VEC, BWD>;
-  MRFP_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.smem));
-  NpGeom g = L.g;
-  void* args[] = {(void*)&x, (void*)&alpha, (void*)&eps, (void*)&mean_in, (void*)&out,
-                  (void*)&mean_out, (void*)&beta_out, (void*)&ps, (void*)&g};
-  MRFP_CUDA_TRY(cudaLaunchCooperativeKernel((void*)kern, dim3(L.grid), dim3(kThreads), args, L.smem, s));
-  return MRFP_OK;
+  const size_t fixed = 1024 /* static smem + alignment slack */ + coef_bytes;
+  g.grid = L->grid;
+  g.per_cta = ring ? 1 : 0;
+  g.scratch_off = ring ? (long long)L->grid * g.max_local_planes : g.U;
+  g.keep_units = 0;
+  if (ring) {
+    const size_t per_slot = (size_t)kUnitVecs * 16 + kWarps * 8 + 16;
+    long long s = (long long)(((size_t)di.max_smem_optin - fixed) / per_slot);
+    if (s > kMaxSlots) s = kMaxSlots;
+    if (s > upc) s = upc;
+    if (s < 1) s = 1;
+    g.slots = (int)s;
+    L->smem = (size_t)g.slots * per_slot + coef_bytes;
+    // L2 share reserved for phase-B re-reads (MRFP_NPPLUS_KEEP_MB overrides; default 64 MiB)
+    static const long long keep_mb = getenv("MRFP_NPPLUS_KEEP_MB") ? atoll(getenv("MRFP_NPPLUS_KEEP_MB")) : 64;
+    long long ku = (keep_mb << 20) / ((long long)L->grid * kUnitVecs * 16);
+    if (ku > upc) ku = upc;
+    g.keep_units = (int)ku;
+  } else {
+    const size_t unit_bytes = (size_t)g.Q * 4;
+    long long s = (long long)(((size_t)di.max_smem_optin - fixed) / unit_bytes);
+    if (s > min_upc) s = min_upc;   // the resident window must not start before u0
+    g.slots = (int)s;
+    L->smem = align_up((size_t)g.slots * unit_bytes, 16) + coef_bytes;
+  }
 }
 
 template <bool BWD>
@@ -349,12 +515,23 @@ int run(const float* x, const float* alpha, const float* eps, const float* mean_
   DeviceInfo di;
   int rc = get_device_info(&di);
   if (rc) return rc;
-  const bool vec4 = (HW % 4 == 0) && (((uintptr_t)x | (uintptr_t)out) & 15) == 0;
+  const bool ring = (HW % 4 == 0) && (((uintptr_t)x | (uintptr_t)out) & 15) == 0;
   NpLaunch L;
-  plan_launch(N, C, HW, vec4 ? 4 : 1, di, &L);
-  cudaStream_t s = (cudaStream_t)stream;
-  return vec4 ? launch<4, BWD>(x, alpha, eps, mean_in, out, mean_out, beta_out, (double*)ws, L, s)
-              : launch<1, BWD>(x, alpha, eps, mean_in, out, mean_out, beta_out, (double*)ws, L, s);
+  plan_launch(N, C, HW, ring, di, &L);
+  NpGeom g = L.g;
+  double* ps = (double*)ws;
+  // debug: MRFP_NPPLUS_TRACE=1 and a workspace with room for grid*8 extra u64 -> per-CTA phase timestamps
+  static const bool want_trace = getenv("MRFP_NPPLUS_TRACE") != nullptr;
+  const size_t base = align_up(mrfp_npplus_ws_bytes(N, C, HW), 8);
+  unsigned long long* trace = nullptr;
+  if (want_trace && ws_bytes >= base + (size_t)L.grid * 64) trace = (unsigned long long*)((char*)ws + base);
+  void* args[] = {(void*)&x, (void*)&alpha, (void*)&eps, (void*)&mean_in, (void*)&out,
+                  (void*)&mean_out, (void*)&beta_out, (void*)&ps, (void*)&g, (void*)&trace};
+  void* kern = ring ? (void*)npplus_ring_kernel<BWD> : (void*)npplus_scalar_kernel<BWD>;
+  MRFP_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.smem));
+  MRFP_CUDA_TRY(cudaLaunchCooperativeKernel(kern, dim3(L.grid), dim3(ring ? kConsumers + 32 : kConsumers), args,
+                                            L.smem, (cudaStream_t)stream));
+  return MRFP_OK;
 }
 
 }  // namespace
@@ -362,9 +539,11 @@ int run(const float* x, const float* alpha, const float* eps, const float* mean_
 
 extern "C" size_t mrfp_npplus_ws_bytes(int N, int C, int HW) {
   if (N <= 0 || C <= 0 || HW <= 0) return 0;
-  // one double per unit; the scalar path has the most units per plane
-  const long long per_plane = ((long long)HW + mrfp::kThreads * mrfp::kBatch - 1) / (mrfp::kThreads * mrfp::kBatch) + 1;
-  return (size_t)((long long)N * C * per_plane * 8);
+  // one double per unit; the scalar path (2048 floats per unit) has the most units per plane
+  const long long per_plane = ((long long)HW + mrfp::kUnitVecs - 1) / mrfp::kUnitVecs + 1;
+  // partials: per unit (scalar path) or per (CTA, local plane) <= planes + 2 per CTA, CTAs <= 1024 (ring path);
+  // then the plane totals pm[P] and the channel statistics chan[4*C]
+  return (size_t)(((long long)N * C * (per_plane + 1) + 4 * 1024 + 4LL * C) * 8);
 }
 
 extern "C" int mrfp_npplus_fwd_f32(const float* x, const float* alpha, const float* eps, float* out, float* mean,
