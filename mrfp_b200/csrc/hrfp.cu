@@ -1,14 +1,665 @@
-// placeholder: real implementation follows
-#include "common.cuh"
-struct mrfp_hrfp_plan { int dummy; };
-extern "C" int mrfp_hrfp_plan_create(mrfp_hrfp_plan_t** plan, int, int, int, int, int, int, const int*, int) { return MRFP_ERR_UNSUPPORTED; }
-extern "C" void mrfp_hrfp_plan_destroy(mrfp_hrfp_plan_t*) {}
-extern "C" size_t mrfp_hrfp_plan_ws_bytes(const mrfp_hrfp_plan_t*) { return 0; }
-extern "C" size_t mrfp_hrfp_plan_saved_bytes(const mrfp_hrfp_plan_t*) { return 0; }
-extern "C" size_t mrfp_hrfp_plan_lut_bytes(const mrfp_hrfp_plan_t*) { return 0; }
-extern "C" int mrfp_hrfp_plan_write_luts(const mrfp_hrfp_plan_t*, void*, size_t) { return MRFP_ERR_UNSUPPORTED; }
-extern "C" int mrfp_hrfp_plan_stage(const mrfp_hrfp_plan_t*, int, int*) { return MRFP_ERR_UNSUPPORTED; }
-extern "C" int mrfp_hrfp_fwd(const mrfp_hrfp_plan_t*, const float*, const float* const*, const float* const*, const float* const*,
-                  float* const*, float* const*, float, float, const float*, float*, float*, const void*, void*, void*, void*) { return MRFP_ERR_UNSUPPORTED; }
-extern "C" int mrfp_hrfp_bwd(const mrfp_hrfp_plan_t*, const float*, const float*, const float* const*, const void*, const void*, float*, void*, void*) { return MRFP_ERR_UNSUPPORTED; }
-extern "C" int mrfp_add_f32(const float*, const float*, float*, size_t, void*) { return MRFP_ERR_UNSUPPORTED; }
+// HRFP chain for sm_100a — replaces /root/reference/deepv3.py:320-330 (+ :355-357) and its autograd backward:
+// 8 x [conv3x3 (frozen random weights, bias 0) -> nearest resample -> BatchNorm2d(train) -> ReLU].
+//
+// Data layout in HBM: activations and conv outputs are NHWC (channels innermost) in the plan's element type
+// (bf16 for the tcgen05 path, fp32 for the CUDA-core parity path); the module boundary stays fp32 NCHW.
+// Per stage k the forward runs
+//   conv            A_k (NHWC, conv resolution) -> Y_k (saved), and in its epilogue the replication-count
+//                   weighted per-channel sum / sum of squares (= BN batch statistics of the RESAMPLED tensor)
+//   bn_finalize     (N,C)-free: mean, invstd, scale, shift, running-stat update (a-8)
+//   bn_relu_resample   Y_k --gather by LUT, scale/shift, ReLU--> A_{k+1}      (one bandwidth pass)
+// so the resampled / normalised / rectified tensors of the reference (4 passes per stage) never exist.
+// Backward per stage: bn_bwd_reduce (sums over replicas) -> bn_bwd_apply (dY at conv resolution) -> dgrad conv
+// (the same conv kernel with rotated, transposed weights).  No weight gradients (deepv3.py:221-237).
+#include "hrfp.cuh"
+#include <math.h>
+#include <string.h>
+#include <new>
+
+namespace mrfp {
+namespace {
+
+// ------------------------------------------------------------------------------------------------------
+// element access: 8 consecutive channels
+// ------------------------------------------------------------------------------------------------------
+template <typename T> struct Elem;
+template <> struct Elem<float> {
+  static __device__ __forceinline__ void load8(const float* p, float (&v)[8]) {
+    const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+  }
+  static __device__ __forceinline__ void store8(float* p, const float (&v)[8]) {
+    *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+    *reinterpret_cast<float4*>(p + 4) = make_float4(v[4], v[5], v[6], v[7]);
+  }
+  static __device__ __forceinline__ float to_float(float x) { return x; }
+  static __device__ __forceinline__ float from_float(float x) { return x; }
+};
+template <> struct Elem<__nv_bfloat16> {
+  static __device__ __forceinline__ void load8(const __nv_bfloat16* p, float (&v)[8]) {
+    const uint4 r = *reinterpret_cast<const uint4*>(p);
+    const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      v[2 * i] = __uint_as_float(w[i] << 16);
+      v[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+    }
+  }
+  static __device__ __forceinline__ void store8(__nv_bfloat16* p, const float (&v)[8]) {
+    uint32_t w[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+      w[i] = *reinterpret_cast<const uint32_t*>(&h);
+    }
+    *reinterpret_cast<uint4*>(p) = make_uint4(w[0], w[1], w[2], w[3]);
+  }
+  static __device__ __forceinline__ float to_float(__nv_bfloat16 x) { return __bfloat162float(x); }
+  static __device__ __forceinline__ __nv_bfloat16 from_float(float x) { return __float2bfloat16_rn(x); }
+};
+
+// ------------------------------------------------------------------------------------------------------
+// layout conversion at the module boundary
+// ------------------------------------------------------------------------------------------------------
+// src fp32 [N][C][HW] -> dst T [N][HW][C]; accumulate adds into dst (gradient of OCout_dec joining the chain)
+template <typename T>
+__global__ void nchw_to_nhwc_kernel(const float* __restrict__ src, T* __restrict__ dst, int C, int HW, int accumulate) {
+  __shared__ float tile[32][33];
+  const int n = blockIdx.z, c0 = blockIdx.y * 32, p0 = blockIdx.x * 32;
+  const float* s = src + (size_t)n * C * HW;
+  T* d = dst + (size_t)n * C * HW;
+  for (int i = threadIdx.y; i < 32; i += 8) {
+    const int c = c0 + i, p = p0 + threadIdx.x;
+    tile[i][threadIdx.x] = (c < C && p < HW) ? s[(size_t)c * HW + p] : 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += 8) {
+    const int p = p0 + i, c = c0 + threadIdx.x;
+    if (p < HW && c < C) {
+      float v = tile[threadIdx.x][i];
+      T* q = d + (size_t)p * C + c;
+      if (accumulate) v += Elem<T>::to_float(*q);
+      *q = Elem<T>::from_float(v);
+    }
+  }
+}
+
+// out fp32 [N][C][OH][OW] = f(Y[n][ih[oh]][iw[ow]][c]) (+ add), f = identity or ReLU(scale*y + shift)
+template <typename T>
+__global__ void nhwc_to_nchw_kernel(const T* __restrict__ y, float* __restrict__ out, const float* __restrict__ add,
+                                    const int* __restrict__ idx_h, const int* __restrict__ idx_w,
+                                    const float* __restrict__ scale, const float* __restrict__ shift,
+                                    int C, int IH, int IW, int OH, int OW) {
+  __shared__ float tile[32][33];
+  const int n = blockIdx.x / OH, oh = blockIdx.x % OH;
+  const int c0 = blockIdx.y * 32, w0 = blockIdx.z * 32;
+  const int sh = idx_h ? idx_h[oh] : oh;
+  const T* row = y + ((size_t)n * IH + sh) * IW * C;
+  for (int i = threadIdx.y; i < 32; i += 8) {
+    const int ow = w0 + i, c = c0 + threadIdx.x;
+    float v = 0.f;
+    if (ow < OW && c < C) {
+      const int sw = idx_w ? idx_w[ow] : ow;
+      v = Elem<T>::to_float(row[(size_t)sw * C + c]);
+      if (scale) v = fmaxf(fmaf(scale[c], v, shift[c]), 0.f);
+    }
+    tile[i][threadIdx.x] = v;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += 8) {
+    const int c = c0 + i, ow = w0 + threadIdx.x;
+    if (c < C && ow < OW) {
+      const size_t o = (((size_t)n * C + c) * OH + oh) * OW + ow;
+      float v = tile[threadIdx.x][i];
+      if (add) v += add[o];
+      out[o] = v;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// forward element-wise pass: A_next[n][oh][ow][c] = ReLU(scale[c] * Y[n][ih[oh]][iw[ow]][c] + shift[c])
+// ------------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256)
+bn_relu_resample_kernel(const T* __restrict__ y, T* __restrict__ a, const int* __restrict__ idx_h,
+                        const int* __restrict__ idx_w, const float* __restrict__ scale,
+                        const float* __restrict__ shift, int N, int C, int IH, int IW, int OH, int OW) {
+  const int cg = C >> 3;
+  const long long total = (long long)N * OH * OW * cg;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % cg) << 3;
+    long long p = i / cg;
+    const int ow = (int)(p % OW); p /= OW;
+    const int oh = (int)(p % OH);
+    const int n = (int)(p / OH);
+    float v[8];
+    Elem<T>::load8(y + (((size_t)n * IH + idx_h[oh]) * IW + idx_w[ow]) * C + c, v);
+    const float4 s0 = *reinterpret_cast<const float4*>(scale + c), s1 = *reinterpret_cast<const float4*>(scale + c + 4);
+    const float4 h0 = *reinterpret_cast<const float4*>(shift + c), h1 = *reinterpret_cast<const float4*>(shift + c + 4);
+    const float sc[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+    const float sf[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = fmaxf(fmaf(sc[j], v[j], sf[j]), 0.f);
+    Elem<T>::store8(a + (size_t)i * 8, v);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// BN statistics finalisation (one block).  acc[0..C) = sum w*y, acc[kMaxC..) = sum w*y^2 over the conv
+// output, w = replication count  ==  plain sums over the resampled tensor.
+// ------------------------------------------------------------------------------------------------------
+__global__ void bn_finalize_kernel(const double* __restrict__ acc, const float* __restrict__ gamma,
+                                   const float* __restrict__ beta, float* __restrict__ running_mean,
+                                   float* __restrict__ running_var, float* __restrict__ stats, int C,
+                                   double count, float momentum, float eps) {
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const double mean = acc[c] / count;
+    double var = acc[kMaxC + c] / count - mean * mean;
+    if (var < 0) var = 0;
+    const double invstd = 1.0 / sqrt(var + (double)eps);
+    const float sc = (float)((double)gamma[c] * invstd);
+    const float b = beta ? beta[c] : 0.f;
+    stats[0 * kMaxC + c] = (float)mean;
+    stats[1 * kMaxC + c] = (float)invstd;
+    stats[2 * kMaxC + c] = sc;
+    stats[3 * kMaxC + c] = (float)((double)b - mean * (double)sc);
+    if (running_mean) running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * (float)mean;
+    if (running_var) running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)(var * (count / (count - 1.0)));
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// CUDA-core direct 3x3 convolution, fp32 NHWC (tight-parity math mode).  w: [9][CIN][COUT].
+// block = 128 threads: lanes = 32 consecutive pixels, warps = 4 groups of 16 output channels (64 per block).
+// ------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+conv3x3_direct_f32_kernel(const float* __restrict__ in, const float* __restrict__ w, float* __restrict__ out,
+                          int N, int H, int W, int CIN, int COUT, int dil, const int* __restrict__ cnt_h,
+                          const int* __restrict__ cnt_w, double* __restrict__ stat_acc) {
+  extern __shared__ float s_w[];   // [CIN][64]
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const long long pix = (long long)blockIdx.x * 32 + lane;
+  const bool valid = pix < (long long)N * H * W;
+  const int x = (int)(pix % W), y = (int)((pix / W) % H), n = (int)(pix / ((long long)W * H));
+  const int cb = blockIdx.y * 64;
+  float acc[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) acc[i] = 0.f;
+  for (int tap = 0; tap < 9; ++tap) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < CIN * 64; i += 128) {
+      const int ci = i >> 6, co = i & 63;
+      s_w[i] = (cb + co < COUT) ? w[((size_t)tap * CIN + ci) * COUT + cb + co] : 0.f;
+    }
+    __syncthreads();
+    const int yy = y + (tap / 3 - 1) * dil, xx = x + (tap % 3 - 1) * dil;
+    if (valid && yy >= 0 && yy < H && xx >= 0 && xx < W) {
+      const float4* ip = reinterpret_cast<const float4*>(in + (((size_t)n * H + yy) * W + xx) * CIN);
+      for (int c4 = 0; c4 < CIN / 4; ++c4) {
+        const float4 v = ip[c4];
+        const float vv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float4* wr = reinterpret_cast<const float4*>(s_w + (c4 * 4 + j) * 64 + warp * 16);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const float4 ww = wr[q];
+            acc[4 * q + 0] = fmaf(vv[j], ww.x, acc[4 * q + 0]);
+            acc[4 * q + 1] = fmaf(vv[j], ww.y, acc[4 * q + 1]);
+            acc[4 * q + 2] = fmaf(vv[j], ww.z, acc[4 * q + 2]);
+            acc[4 * q + 3] = fmaf(vv[j], ww.w, acc[4 * q + 3]);
+          }
+        }
+      }
+    }
+  }
+  const int co0 = cb + warp * 16;
+  if (valid && co0 < COUT) {
+    float4* op = reinterpret_cast<float4*>(out + (size_t)pix * COUT + co0);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) op[q] = make_float4(acc[4 * q], acc[4 * q + 1], acc[4 * q + 2], acc[4 * q + 3]);
+  }
+  if (stat_acc) {
+    const float wgt = valid ? (float)(cnt_h[y] * cnt_w[x]) : 0.f;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const float s1 = warp_sum(wgt * acc[i]);
+      const float s2 = warp_sum(wgt * acc[i] * acc[i]);
+      if (lane == 0 && co0 + i < COUT) {
+        atomicAdd(stat_acc + co0 + i, (double)s1);
+        atomicAdd(stat_acc + kMaxC + co0 + i, (double)s2);
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// weight packing.  W: (cout, cin, 3, 3) fp32 OIHW.
+//   mode 0 (direct fwd)   out[tap][ci][co] = W[co][ci][tap]          fp32
+//   mode 1 (direct dgrad) out[tap][co][ci] = W[co][ci][8-tap]        fp32   (conv input = co, output = ci)
+//   mode 2 (tc fwd)       out[tap][co][ci] = W[co][ci][tap]          bf16   (rows = N, K = ci contiguous)
+//   mode 3 (tc dgrad)     out[tap][ci][co] = W[co][ci][8-tap]        bf16   (rows = N = ci, K = co contiguous)
+// ------------------------------------------------------------------------------------------------------
+__global__ void pack_weights_kernel(const float* __restrict__ W, void* __restrict__ out, int cin, int cout, int mode) {
+  const int total = 9 * cin * cout;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int tap = i / (cin * cout), r = i % (cin * cout);
+    int ci, co;
+    if (mode == 0 || mode == 3) { ci = r / cout; co = r % cout; } else { co = r / cin; ci = r % cin; }
+    const int st = (mode == 1 || mode == 3) ? 8 - tap : tap;
+    const float v = W[((size_t)co * cin + ci) * 9 + st];
+    if (mode < 2) reinterpret_cast<float*>(out)[i] = v;
+    else reinterpret_cast<__nv_bfloat16*>(out)[i] = __float2bfloat16_rn(v);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// backward of [resample -> BN(train) -> ReLU] at one stage, expressed per SOURCE pixel of the conv output:
+//   mask, xhat depend only on Y[src];  SdA = sum of dA over the replicas of src (a contiguous rectangle);
+//   S1 = sum mask*SdA, S2 = sum mask*xhat*SdA  (then M1 = gamma*S1/count, M2 = gamma*S2/count)
+//   dY[src] = invstd * (mask*gamma*SdA - cnt*(M1 + xhat*M2))
+// ------------------------------------------------------------------------------------------------------
+template <typename T, bool APPLY>
+__global__ void __launch_bounds__(256)
+bn_bwd_kernel(const T* __restrict__ dA, const T* __restrict__ y, T* __restrict__ dY, const int* __restrict__ start_h,
+              const int* __restrict__ cnt_h, const int* __restrict__ start_w, const int* __restrict__ cnt_w,
+              const float* __restrict__ stats, const float* __restrict__ gamma, double* __restrict__ acc,
+              int N, int C, int IH, int IW, int OH, int OW, double count) {
+  __shared__ float s_acc[2 * kMaxC];
+  const int cg = C >> 3, ppb = 256 / cg;
+  const int cgi = threadIdx.x % cg, pl = threadIdx.x / cg, c = cgi << 3;
+  if (!APPLY) {
+    for (int i = threadIdx.x; i < 2 * kMaxC; i += 256) s_acc[i] = 0.f;
+    __syncthreads();
+  }
+  float mean[8], invstd[8], scale[8], shift[8], gm[8], m1[8], m2[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    mean[j] = stats[c + j]; invstd[j] = stats[kMaxC + c + j];
+    scale[j] = stats[2 * kMaxC + c + j]; shift[j] = stats[3 * kMaxC + c + j];
+    gm[j] = gamma[c + j];
+    if (APPLY) {
+      m1[j] = (float)((double)gm[j] * acc[c + j] / count);
+      m2[j] = (float)((double)gm[j] * acc[kMaxC + c + j] / count);
+    }
+  }
+  float s1[8], s2[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { s1[j] = 0.f; s2[j] = 0.f; }
+  const long long npix = (long long)N * IH * IW;
+  for (long long p = (long long)blockIdx.x * ppb + pl; p < npix; p += (long long)gridDim.x * ppb) {
+    const int sx = (int)(p % IW), sy = (int)((p / IW) % IH), n = (int)(p / ((long long)IW * IH));
+    const int h0 = start_h[sy], nh = cnt_h[sy], w0 = start_w[sx], nw = cnt_w[sx];
+    float sd[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) sd[j] = 0.f;
+    for (int a = 0; a < nh; ++a)
+      for (int b = 0; b < nw; ++b) {
+        float g[8];
+        Elem<T>::load8(dA + (((size_t)n * OH + h0 + a) * OW + w0 + b) * C + c, g);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) sd[j] += g[j];
+      }
+    float yv[8];
+    Elem<T>::load8(y + (size_t)p * C + c, yv);
+    if (!APPLY) {
+      if (nh * nw > 0) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float z = fmaf(scale[j], yv[j], shift[j]);
+          const float xh = (yv[j] - mean[j]) * invstd[j];
+          const float t = z > 0.f ? sd[j] : 0.f;
+          s1[j] += t;
+          s2[j] += t * xh;
+        }
+      }
+    } else {
+      const float cnt = (float)(nh * nw);
+      float o[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float z = fmaf(scale[j], yv[j], shift[j]);
+        const float xh = (yv[j] - mean[j]) * invstd[j];
+        const float t = z > 0.f ? sd[j] * gm[j] : 0.f;
+        o[j] = invstd[j] * (t - cnt * (m1[j] + xh * m2[j]));
+      }
+      Elem<T>::store8(dY + (size_t)p * C + c, o);
+    }
+  }
+  if (!APPLY) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      atomicAdd(&s_acc[c + j], s1[j]);
+      atomicAdd(&s_acc[kMaxC + c + j], s2[j]);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < C; i += 256) {
+      atomicAdd(acc + i, (double)s_acc[i]);
+      atomicAdd(acc + kMaxC + i, (double)s_acc[kMaxC + i]);
+    }
+  }
+}
+
+__global__ void add_f32_kernel(const float4* __restrict__ a, const float4* __restrict__ b, float4* __restrict__ o,
+                               size_t n4, const float* a1, const float* b1, float* o1, size_t n) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n4; i += stride) {
+    const float4 x = ld_stream_f4(a + i), y = ld_stream_f4(b + i);
+    st_stream_f4(o + i, make_float4(x.x + y.x, x.y + y.y, x.z + y.z, x.w + y.w));
+  }
+  for (size_t i = n4 * 4 + blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += stride) o1[i] = a1[i] + b1[i];
+}
+
+// ------------------------------------------------------------------------------------------------------
+// host: geometry (must be bit-identical to ATen's upsample_nearest2d index rule)
+// ------------------------------------------------------------------------------------------------------
+void make_index(int in, int out, bool has_sf, double sf, int* idx) {
+  const float scale = has_sf ? (float)(1.0 / sf) : ((float)in / (float)out);
+  for (int d = 0; d < out; ++d) {
+    int s = (int)floorf((float)d * scale);
+    idx[d] = s < in - 1 ? s : in - 1;
+  }
+}
+
+int grid_for(long long work_items, int block, int sm_count, int waves = 8) {
+  long long g = (work_items + block - 1) / block;
+  const long long cap = (long long)sm_count * waves;
+  if (g > cap) g = cap;
+  return g < 1 ? 1 : (int)g;
+}
+
+bool pow2_ge8(int c) { return c >= 8 && c <= kMaxC && (c & (c - 1)) == 0; }
+
+template <typename T>
+int hrfp_forward(const mrfp_hrfp_plan* P, const float* xp, const float* const* W, const float* const* gamma,
+                 const float* const* beta, float* const* rmean, float* const* rvar, float momentum, float eps,
+                 const float* x_add, float* ocout, float* ocout_dec, const int* lut, char* saved, char* ws,
+                 cudaStream_t s, const DeviceInfo& di) {
+  double* acc = reinterpret_cast<double*>(ws + P->acc_fwd_off);
+  MRFP_CUDA_TRY(cudaMemsetAsync(acc, 0, (size_t)kHrfpStages * 2 * kMaxC * sizeof(double), s));
+  const int last = ocout ? kHrfpStages : 4;
+  const bool tc = P->mode == MRFP_MATH_BF16;
+  for (int k = 0; k < last; ++k) {
+    const HrfpStage& st = P->st[k];
+    const int nw = 9 * st.cin * st.cout;
+    pack_weights_kernel<<<grid_for(nw, 256, di.sm_count, 2), 256, 0, s>>>(W[k], ws + st.wf_off, st.cin, st.cout, tc ? 2 : 0);
+    pack_weights_kernel<<<grid_for(nw, 256, di.sm_count, 2), 256, 0, s>>>(W[k], saved + st.wb_off, st.cin, st.cout, tc ? 3 : 1);
+  }
+  T* bufA = reinterpret_cast<T*>(ws + P->bufs_off);
+  T* bufB = reinterpret_cast<T*>(ws + P->bufs_off + P->buf_a_bytes);
+  {
+    const int HW = P->xh * P->xw;
+    dim3 g((HW + 31) / 32, (P->cin + 31) / 32, P->N);
+    nchw_to_nhwc_kernel<T><<<g, dim3(32, 8), 0, s>>>(xp, bufA, P->cin, HW, 0);
+  }
+  T* cur = bufA;
+  T* nxt = bufB;
+  for (int k = 0; k < last; ++k) {
+    const HrfpStage& st = P->st[k];
+    T* Y = reinterpret_cast<T*>(saved + st.y_off);
+    double* a = acc + (size_t)k * 2 * kMaxC;
+    if (tc) {
+      int rc = conv3x3_tc_bf16(reinterpret_cast<const __nv_bfloat16*>(cur),
+                               reinterpret_cast<const __nv_bfloat16*>(ws + st.wf_off),
+                               reinterpret_cast<__nv_bfloat16*>(Y), P->N, st.ch, st.cw, st.cin, st.cout, st.dil,
+                               lut + st.cnt_h, lut + st.cnt_w, a, s);
+      if (rc) return rc;
+    } else {
+      dim3 g((unsigned)(((long long)P->N * st.ch * st.cw + 31) / 32), (st.cout + 63) / 64);
+      const size_t smem = (size_t)st.cin * 64 * sizeof(float);
+      MRFP_CUDA_TRY(cudaFuncSetAttribute(conv3x3_direct_f32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      conv3x3_direct_f32_kernel<<<g, 128, smem, s>>>(reinterpret_cast<const float*>(cur),
+                                                     reinterpret_cast<const float*>(ws + st.wf_off),
+                                                     reinterpret_cast<float*>(Y), P->N, st.ch, st.cw, st.cin, st.cout,
+                                                     st.dil, lut + st.cnt_h, lut + st.cnt_w, a);
+    }
+    float* stats = reinterpret_cast<float*>(saved + P->stats_off) + (size_t)k * 4 * kMaxC;
+    const double count = (double)P->N * st.oh * st.ow;
+    bn_finalize_kernel<<<1, 256, 0, s>>>(a, gamma[k], beta ? beta[k] : nullptr, rmean ? rmean[k] : nullptr,
+                                         rvar ? rvar[k] : nullptr, stats, st.cout, count, momentum, eps);
+    if (k == 3 && ocout_dec) {
+      dim3 g(P->N * st.oh, (st.cout + 31) / 32, (st.ow + 31) / 32);
+      nhwc_to_nchw_kernel<T><<<g, dim3(32, 8), 0, s>>>(Y, ocout_dec, nullptr, lut + st.idx_h, lut + st.idx_w,
+                                                        stats + 2 * kMaxC, stats + 3 * kMaxC, st.cout, st.ch, st.cw,
+                                                        st.oh, st.ow);
+    }
+    if (k == kHrfpStages - 1) {
+      dim3 g(P->N * st.oh, (st.cout + 31) / 32, (st.ow + 31) / 32);
+      nhwc_to_nchw_kernel<T><<<g, dim3(32, 8), 0, s>>>(Y, ocout, x_add, lut + st.idx_h, lut + st.idx_w,
+                                                        stats + 2 * kMaxC, stats + 3 * kMaxC, st.cout, st.ch, st.cw,
+                                                        st.oh, st.ow);
+    } else if (k + 1 < last) {
+      const long long items = (long long)P->N * st.oh * st.ow * (st.cout / 8);
+      bn_relu_resample_kernel<T><<<grid_for(items, 256, di.sm_count), 256, 0, s>>>(
+          Y, nxt, lut + st.idx_h, lut + st.idx_w, stats + 2 * kMaxC, stats + 3 * kMaxC, P->N, st.cout, st.ch, st.cw,
+          st.oh, st.ow);
+      T* t = cur; cur = nxt; nxt = t;
+    }
+  }
+  MRFP_CUDA_TRY(cudaGetLastError());
+  return MRFP_OK;
+}
+
+template <typename T>
+int hrfp_backward(const mrfp_hrfp_plan* P, const float* g_ocout, const float* g_ocout_dec, const float* const* gamma,
+                  const int* lut, const char* saved, float* g_xp, char* ws, cudaStream_t s, const DeviceInfo& di) {
+  double* acc = reinterpret_cast<double*>(ws + P->acc_bwd_off);
+  MRFP_CUDA_TRY(cudaMemsetAsync(acc, 0, (size_t)kHrfpStages * 2 * kMaxC * sizeof(double), s));
+  T* g0 = reinterpret_cast<T*>(ws + P->bufs_off);
+  T* g1 = reinterpret_cast<T*>(ws + P->bufs_off + P->buf_g_bytes);
+  T* dY = reinterpret_cast<T*>(ws + P->bufs_off + 2 * P->buf_g_bytes);
+  const bool tc = P->mode == MRFP_MATH_BF16;
+  T* dA = nullptr;    // gradient wrt the stage output A_{k+1}, NHWC at (oh, ow)
+  T* other = g1;
+  for (int k = kHrfpStages - 1; k >= 0; --k) {
+    const HrfpStage& st = P->st[k];
+    const float* gin = (k == kHrfpStages - 1) ? g_ocout : (k == 3 ? g_ocout_dec : nullptr);
+    if (gin) {
+      const int HW = st.oh * st.ow;
+      dim3 g((HW + 31) / 32, (st.cout + 31) / 32, P->N);
+      T* dst = dA ? dA : g0;
+      nchw_to_nhwc_kernel<T><<<g, dim3(32, 8), 0, s>>>(gin, dst, st.cout, HW, dA ? 1 : 0);
+      if (!dA) { dA = g0; other = g1; }
+    }
+    if (!dA) continue;
+    const T* Y = reinterpret_cast<const T*>(saved + st.y_off);
+    const float* stats = reinterpret_cast<const float*>(saved + P->stats_off) + (size_t)k * 4 * kMaxC;
+    double* a = acc + (size_t)k * 2 * kMaxC;
+    const double count = (double)P->N * st.oh * st.ow;
+    const long long npix = (long long)P->N * st.ch * st.cw;
+    const int ppb = 256 / (st.cout / 8);
+    const int grid = grid_for(npix, ppb, di.sm_count, 4);
+    bn_bwd_kernel<T, false><<<grid, 256, 0, s>>>(dA, Y, nullptr, lut + st.start_h, lut + st.cnt_h, lut + st.start_w,
+                                                 lut + st.cnt_w, stats, gamma[k], a, P->N, st.cout, st.ch, st.cw,
+                                                 st.oh, st.ow, count);
+    bn_bwd_kernel<T, true><<<grid, 256, 0, s>>>(dA, Y, dY, lut + st.start_h, lut + st.cnt_h, lut + st.start_w,
+                                                lut + st.cnt_w, stats, gamma[k], a, P->N, st.cout, st.ch, st.cw,
+                                                st.oh, st.ow, count);
+    // dgrad: conv of dY (cout channels) with the rotated / transposed kernel -> dA_prev (cin channels)
+    if (tc) {
+      int rc = conv3x3_tc_bf16(reinterpret_cast<const __nv_bfloat16*>(dY),
+                               reinterpret_cast<const __nv_bfloat16*>(saved + st.wb_off),
+                               reinterpret_cast<__nv_bfloat16*>(other), P->N, st.ch, st.cw, st.cout, st.cin, st.dil,
+                               nullptr, nullptr, nullptr, s);
+      if (rc) return rc;
+    } else {
+      dim3 g((unsigned)((npix + 31) / 32), (st.cin + 63) / 64);
+      const size_t smem = (size_t)st.cout * 64 * sizeof(float);
+      MRFP_CUDA_TRY(cudaFuncSetAttribute(conv3x3_direct_f32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      conv3x3_direct_f32_kernel<<<g, 128, smem, s>>>(reinterpret_cast<const float*>(dY),
+                                                     reinterpret_cast<const float*>(saved + st.wb_off),
+                                                     reinterpret_cast<float*>(other), P->N, st.ch, st.cw, st.cout,
+                                                     st.cin, st.dil, nullptr, nullptr, nullptr);
+    }
+    T* t = dA; dA = other; other = t;
+  }
+  if (!dA) {   // no gradient reached the chain
+    MRFP_CUDA_TRY(cudaMemsetAsync(g_xp, 0, (size_t)P->N * P->cin * P->xh * P->xw * sizeof(float), s));
+    return MRFP_OK;
+  }
+  dim3 g(P->N * P->xh, (P->cin + 31) / 32, (P->xw + 31) / 32);
+  nhwc_to_nchw_kernel<T><<<g, dim3(32, 8), 0, s>>>(dA, g_xp, nullptr, nullptr, nullptr, nullptr, nullptr, P->cin,
+                                                    P->xh, P->xw, P->xh, P->xw);
+  MRFP_CUDA_TRY(cudaGetLastError());
+  return MRFP_OK;
+}
+
+}  // namespace
+}  // namespace mrfp
+
+using namespace mrfp;
+
+extern "C" int mrfp_hrfp_plan_create(mrfp_hrfp_plan_t** out, int N, int cin, int xh, int xw, int h, int w,
+                                     const int* widths, int math_mode) {
+  if (!out) return MRFP_ERR_NULL_POINTER;
+  *out = nullptr;
+  static const int kDefaultWidths[4] = {64, 64, 128, 256};
+  const int* wd = widths ? widths : kDefaultWidths;
+  if (N <= 0 || xh <= 0 || xw <= 0 || h < 4 || w < 4) return MRFP_ERR_BAD_SHAPE;
+  if (math_mode != MRFP_MATH_FP32 && math_mode != MRFP_MATH_BF16) return MRFP_ERR_UNSUPPORTED;
+  if (!pow2_ge8(cin)) return MRFP_ERR_UNSUPPORTED;
+  for (int i = 0; i < 4; ++i)
+    if (!pow2_ge8(wd[i])) return MRFP_ERR_UNSUPPORTED;
+  mrfp_hrfp_plan* P = new (std::nothrow) mrfp_hrfp_plan();
+  if (!P) return MRFP_ERR_WORKSPACE;
+  P->magic = kPlanMagic;
+  P->N = N; P->cin = cin; P->xh = xh; P->xw = xw; P->h = h; P->w = w; P->mode = math_mode;
+  P->esize = math_mode == MRFP_MATH_BF16 ? 2 : 4;
+  // layer table of deepv3.py:221-237, parametrised by the encoder widths
+  const int chans[9] = {cin, wd[0], wd[1], wd[2], wd[3], wd[2], wd[1], wd[0], cin};
+  const int dils[8] = {1, 1, 2, 2, 1, 1, 2, 2};
+  // resample spec of deepv3.py:320-327
+  const double sfs[8] = {1.205, 1.2, 1.2, 0, 0, 0.838, 0.798, 0};
+  const int sz_h[8] = {0, 0, 0, h / 2, h / 2, 0, 0, (h + 3) / 4};
+  const int sz_w[8] = {0, 0, 0, w / 2, w / 2, 0, 0, (w + 3) / 4};
+  int ch = xh, cw = xw;
+  size_t y_bytes = 0, wf_bytes = 0, wb_bytes = 0, max_act = 0, max_g = 0, max_dy = 0;
+  max_act = (size_t)N * xh * xw * cin * P->esize;
+  for (int k = 0; k < kHrfpStages; ++k) {
+    HrfpStage& st = P->st[k];
+    st.cin = chans[k]; st.cout = chans[k + 1]; st.dil = dils[k];
+    st.ch = ch; st.cw = cw;
+    const bool sf = sfs[k] > 0;
+    st.oh = sf ? (int)floor((double)ch * sfs[k]) : sz_h[k];
+    st.ow = sf ? (int)floor((double)cw * sfs[k]) : sz_w[k];
+    if (st.oh <= 0 || st.ow <= 0) { delete P; return MRFP_ERR_BAD_SHAPE; }
+    if (math_mode == MRFP_MATH_BF16 && !conv3x3_tc_supported(st.cin, st.cout)) { delete P; return MRFP_ERR_UNSUPPORTED; }
+    std::vector<int>& L = P->lut;
+    st.idx_h = (int)L.size(); L.resize(L.size() + st.oh); make_index(ch, st.oh, sf, sfs[k], &L[st.idx_h]);
+    st.idx_w = (int)L.size(); L.resize(L.size() + st.ow); make_index(cw, st.ow, sf, sfs[k], &L[st.idx_w]);
+    const int ph = (ch + kTileH - 1) / kTileH * kTileH + kTileH, pw = (cw + kTileW - 1) / kTileW * kTileW + kTileW;
+    st.cnt_h = (int)L.size(); L.resize(L.size() + ph, 0);
+    st.cnt_w = (int)L.size(); L.resize(L.size() + pw, 0);
+    st.start_h = (int)L.size(); L.resize(L.size() + ch, 0);
+    st.start_w = (int)L.size(); L.resize(L.size() + cw, 0);
+    for (int d = st.oh - 1; d >= 0; --d) { const int sidx = L[st.idx_h + d]; L[st.cnt_h + sidx]++; L[st.start_h + sidx] = d; }
+    for (int d = st.ow - 1; d >= 0; --d) { const int sidx = L[st.idx_w + d]; L[st.cnt_w + sidx]++; L[st.start_w + sidx] = d; }
+    st.y_off = y_bytes;
+    y_bytes += align_up((size_t)N * ch * cw * st.cout * P->esize, 256);
+    st.wf_off = wf_bytes; wf_bytes += align_up((size_t)9 * st.cin * st.cout * P->esize, 256);
+    st.wb_off = wb_bytes; wb_bytes += align_up((size_t)9 * st.cin * st.cout * P->esize, 256);
+    const size_t a_next = (size_t)N * st.oh * st.ow * st.cout * P->esize;   // A_{k+1} and dA_{k+1}
+    const size_t dy = (size_t)N * ch * cw * st.cout * P->esize;             // dY_k
+    const size_t da_prev = (size_t)N * ch * cw * st.cin * P->esize;         // dA_k
+    if (a_next > max_act) max_act = a_next;
+    if (a_next > max_g) max_g = a_next;
+    if (da_prev > max_g) max_g = da_prev;
+    if (dy > max_dy) max_dy = dy;
+    ch = st.oh; cw = st.ow;
+  }
+  // saved: [Y_0..Y_7][stats][dgrad weights]
+  P->stats_off = y_bytes;
+  const size_t stats_bytes = align_up((size_t)kHrfpStages * 4 * kMaxC * sizeof(float), 256);
+  for (int k = 0; k < kHrfpStages; ++k) P->st[k].wb_off += y_bytes + stats_bytes;
+  P->saved_bytes = y_bytes + stats_bytes + wb_bytes;
+  // ws: [acc fwd][acc bwd][fwd weights][buffers: fwd A/B ping-pong | bwd g0, g1, dY]
+  const size_t acc_bytes = (size_t)kHrfpStages * 2 * kMaxC * sizeof(double);
+  P->acc_fwd_off = 0;
+  P->acc_bwd_off = acc_bytes;
+  for (int k = 0; k < kHrfpStages; ++k) P->st[k].wf_off += 2 * acc_bytes;
+  P->bufs_off = align_up(2 * acc_bytes + wf_bytes, 1024);
+  P->buf_a_bytes = align_up(max_act, 1024);
+  P->buf_g_bytes = align_up(max_g, 1024);
+  P->buf_dy_bytes = align_up(max_dy, 1024);
+  const size_t fwd = 2 * P->buf_a_bytes, bwd = 2 * P->buf_g_bytes + P->buf_dy_bytes;
+  P->ws_bytes = P->bufs_off + (fwd > bwd ? fwd : bwd);
+  *out = P;
+  return MRFP_OK;
+}
+
+extern "C" void mrfp_hrfp_plan_destroy(mrfp_hrfp_plan_t* P) {
+  if (P && P->magic == kPlanMagic) { P->magic = 0; delete P; }
+}
+extern "C" size_t mrfp_hrfp_plan_ws_bytes(const mrfp_hrfp_plan_t* P) { return (P && P->magic == kPlanMagic) ? P->ws_bytes : 0; }
+extern "C" size_t mrfp_hrfp_plan_saved_bytes(const mrfp_hrfp_plan_t* P) { return (P && P->magic == kPlanMagic) ? P->saved_bytes : 0; }
+extern "C" size_t mrfp_hrfp_plan_lut_bytes(const mrfp_hrfp_plan_t* P) {
+  return (P && P->magic == kPlanMagic) ? P->lut.size() * sizeof(int) : 0;
+}
+extern "C" int mrfp_hrfp_plan_write_luts(const mrfp_hrfp_plan_t* P, void* host_dst, size_t bytes) {
+  if (!P || P->magic != kPlanMagic) return MRFP_ERR_BAD_PLAN;
+  if (!host_dst) return MRFP_ERR_NULL_POINTER;
+  if (bytes < P->lut.size() * sizeof(int)) return MRFP_ERR_WORKSPACE;
+  memcpy(host_dst, P->lut.data(), P->lut.size() * sizeof(int));
+  return MRFP_OK;
+}
+extern "C" int mrfp_hrfp_plan_stage(const mrfp_hrfp_plan_t* P, int k, int* out7) {
+  if (!P || P->magic != kPlanMagic) return MRFP_ERR_BAD_PLAN;
+  if (!out7) return MRFP_ERR_NULL_POINTER;
+  if (k < 0 || k >= kHrfpStages) return MRFP_ERR_BAD_SHAPE;
+  const HrfpStage& st = P->st[k];
+  out7[0] = st.cin; out7[1] = st.cout; out7[2] = st.dil; out7[3] = st.ch; out7[4] = st.cw; out7[5] = st.oh; out7[6] = st.ow;
+  return MRFP_OK;
+}
+
+extern "C" int mrfp_hrfp_fwd(const mrfp_hrfp_plan_t* P, const float* xp, const float* const* W,
+                             const float* const* gamma, const float* const* beta, float* const* running_mean,
+                             float* const* running_var, float momentum, float eps, const float* x_add, float* ocout,
+                             float* ocout_dec, const void* lut, void* saved, void* ws, void* stream) {
+  if (!P || P->magic != kPlanMagic) return MRFP_ERR_BAD_PLAN;
+  if (!xp || !W || !gamma || !lut || !saved || !ws) return MRFP_ERR_NULL_POINTER;
+  if (!ocout && !ocout_dec) return MRFP_ERR_NULL_POINTER;
+  if (((uintptr_t)saved | (uintptr_t)ws | (uintptr_t)lut) & 255) return MRFP_ERR_WORKSPACE;
+  const int last = ocout ? kHrfpStages : 4;
+  for (int k = 0; k < last; ++k)
+    if (!W[k] || !gamma[k]) return MRFP_ERR_NULL_POINTER;
+  DeviceInfo di;
+  int rc = get_device_info(&di);
+  if (rc) return rc;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (P->mode == MRFP_MATH_BF16)
+    return hrfp_forward<__nv_bfloat16>(P, xp, W, gamma, beta, running_mean, running_var, momentum, eps, x_add, ocout,
+                                       ocout_dec, (const int*)lut, (char*)saved, (char*)ws, s, di);
+  return hrfp_forward<float>(P, xp, W, gamma, beta, running_mean, running_var, momentum, eps, x_add, ocout, ocout_dec,
+                             (const int*)lut, (char*)saved, (char*)ws, s, di);
+}
+
+extern "C" int mrfp_hrfp_bwd(const mrfp_hrfp_plan_t* P, const float* g_ocout, const float* g_ocout_dec,
+                             const float* const* gamma, const void* lut, const void* saved, float* g_xp, void* ws,
+                             void* stream) {
+  if (!P || P->magic != kPlanMagic) return MRFP_ERR_BAD_PLAN;
+  if (!gamma || !lut || !saved || !g_xp || !ws) return MRFP_ERR_NULL_POINTER;
+  if (((uintptr_t)saved | (uintptr_t)ws | (uintptr_t)lut) & 255) return MRFP_ERR_WORKSPACE;
+  DeviceInfo di;
+  int rc = get_device_info(&di);
+  if (rc) return rc;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (P->mode == MRFP_MATH_BF16)
+    return hrfp_backward<__nv_bfloat16>(P, g_ocout, g_ocout_dec, gamma, (const int*)lut, (const char*)saved, g_xp,
+                                        (char*)ws, s, di);
+  return hrfp_backward<float>(P, g_ocout, g_ocout_dec, gamma, (const int*)lut, (const char*)saved, g_xp, (char*)ws, s, di);
+}
+
+extern "C" int mrfp_add_f32(const float* a, const float* b, float* out, size_t n, void* stream) {
+  if (!a || !b || !out) return MRFP_ERR_NULL_POINTER;
+  if (n == 0) return MRFP_OK;
+  DeviceInfo di;
+  int rc = get_device_info(&di);
+  if (rc) return rc;
+  const bool al = ((((uintptr_t)a | (uintptr_t)b | (uintptr_t)out) & 15) == 0);
+  const size_t n4 = al ? n / 4 : 0;
+  const int grid = grid_for((long long)(n4 ? n4 : n), 256, di.sm_count, 16);
+  add_f32_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const float4*)a, (const float4*)b, (float4*)out, n4, a, b, out, n);
+  MRFP_CUDA_TRY(cudaGetLastError());
+  return MRFP_OK;
+}

@@ -1,0 +1,52 @@
+// Internal declarations shared by hrfp.cu (plan, element-wise kernels, orchestration) and conv_tc.cu
+// (tcgen05 implicit-GEMM convolution).
+#pragma once
+#include "common.cuh"
+#include <vector>
+
+namespace mrfp {
+
+constexpr int kHrfpStages = 8;
+constexpr int kMaxC = 256;
+constexpr int kTileH = 8;    // tcgen05 conv output tile: 8 rows x 16 cols = 128 pixels = UMMA M
+constexpr int kTileW = 16;
+
+struct HrfpStage {
+  int cin, cout, dil;
+  int ch, cw;      // conv resolution (input and output of the 3x3 conv)
+  int oh, ow;      // resolution after the nearest resample
+  // offsets (in ints) into the LUT blob
+  int idx_h, idx_w;       // dst -> src index, [oh], [ow]
+  int cnt_h, cnt_w;       // replication count of each src row/col, zero-padded to a tile multiple (+1 tile)
+  int start_h, start_w;   // first dst index of each src row/col, [ch], [cw]
+  size_t y_off;           // conv output Y_k in `saved` (bytes)
+  size_t wf_off;          // packed forward weights in ws (bytes)
+  size_t wb_off;          // packed dgrad weights in `saved` (bytes)
+};
+
+}  // namespace mrfp
+
+struct mrfp_hrfp_plan {
+  uint32_t magic;
+  int N, cin, xh, xw, h, w, mode, esize;
+  mrfp::HrfpStage st[mrfp::kHrfpStages];
+  std::vector<int> lut;
+  size_t ws_bytes, saved_bytes;
+  // ws layout
+  size_t acc_fwd_off, acc_bwd_off, bufs_off, buf_a_bytes, buf_g_bytes, buf_dy_bytes;
+  // saved layout
+  size_t stats_off;   // 8 x 4 x kMaxC floats: mean, invstd, scale, shift
+};
+
+namespace mrfp {
+constexpr uint32_t kPlanMagic = 0x4d524650u;   // 'MRFP'
+
+// tcgen05 implicit-GEMM 3x3 convolution, bf16 NHWC in/out, fp32 accumulation in TMEM (conv_tc.cu).
+//   in  [N][H][W][cin], wpack [9][cout][cin] (tap-major, K contiguous), out [N][H][W][cout]
+//   cnt_h / cnt_w: zero-padded replication counts (device) -> per-channel weighted sum / sum of squares of the
+//   fp32 accumulators are added to stat_acc[0..cout) / stat_acc[kMaxC..kMaxC+cout); pass nullptr to skip.
+int conv3x3_tc_bf16(const __nv_bfloat16* in, const __nv_bfloat16* wpack, __nv_bfloat16* out, int N, int H, int W,
+                    int cin, int cout, int dil, const int* cnt_h, const int* cnt_w, double* stat_acc,
+                    cudaStream_t stream);
+bool conv3x3_tc_supported(int cin, int cout);
+}  // namespace mrfp

@@ -1,0 +1,200 @@
+"""HRFP chain (high-resolution feature perturbation) on the sm_100a kernels.
+
+Host-side mirror of /root/reference/deepv3.py:320-330 and :355-357: the 8 frozen conv/BN pairs are
+ordinary `nn.Conv2d` / `nn.BatchNorm2d` modules owned by the caller (same names and state_dict keys
+as the reference); this file only plans the geometry, owns the workspaces and exposes the chain as
+one `torch.autograd.Function` (input gradient only — the weights are frozen, deepv3.py:221-237).
+"""
+import ctypes
+import math
+from typing import Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import _lib
+
+MATH_FP32 = 0
+MATH_BF16 = 2
+DEFAULT_WIDTHS = (64, 64, 128, 256)
+
+
+def _stream_ptr(dev) -> int:
+    return torch.cuda.current_stream(dev).cuda_stream
+
+
+def _ptr_array(tensors: Sequence[Optional[torch.Tensor]]):
+    arr = (ctypes.c_void_p * len(tensors))()
+    for i, t in enumerate(tensors):
+        arr[i] = None if t is None else t.data_ptr()
+    return arr
+
+
+class HrfpPlan:
+    """Geometry + launch plan for one (N, cin, xh, xw, h, w, math_mode); owns LUTs and workspace."""
+
+    def __init__(self, n, cin, xh, xw, h, w, device, math_mode=MATH_BF16, widths=DEFAULT_WIDTHS):
+        lib = _lib.load()
+        self.key = (n, cin, xh, xw, h, w, math_mode, tuple(widths), str(device))
+        self.device = torch.device(device)
+        handle = ctypes.c_void_p()
+        warr = (ctypes.c_int * 4)(*widths)
+        _lib.check(lib.mrfp_hrfp_plan_create(ctypes.byref(handle), n, cin, xh, xw, h, w, warr, math_mode),
+                   "mrfp_hrfp_plan_create")
+        self.handle = handle
+        self.n, self.cin, self.xh, self.xw, self.h, self.w = n, cin, xh, xw, h, w
+        self.math_mode = math_mode
+        self.ws_bytes = lib.mrfp_hrfp_plan_ws_bytes(handle)
+        self.saved_bytes = lib.mrfp_hrfp_plan_saved_bytes(handle)
+        lut_bytes = lib.mrfp_hrfp_plan_lut_bytes(handle)
+        host = np.empty(lut_bytes // 4, dtype=np.int32)
+        _lib.check(lib.mrfp_hrfp_plan_write_luts(handle, host.ctypes.data, lut_bytes), "mrfp_hrfp_plan_write_luts")
+        self.lut = torch.from_numpy(host).to(self.device)
+        self.stages = []
+        for k in range(8):
+            out = (ctypes.c_int * 7)()
+            _lib.check(lib.mrfp_hrfp_plan_stage(handle, k, out), "mrfp_hrfp_plan_stage")
+            self.stages.append(tuple(out))
+        self._ws = None
+
+    def workspace(self) -> torch.Tensor:
+        if self._ws is None:
+            self._ws = torch.empty(self.ws_bytes, dtype=torch.uint8, device=self.device)
+        return self._ws
+
+    @property
+    def dec_shape(self):
+        cin, cout, dil, ch, cw, oh, ow = self.stages[3]
+        return (self.n, cout, oh, ow)
+
+    def __del__(self):
+        try:
+            if getattr(self, "handle", None):
+                _lib.load().mrfp_hrfp_plan_destroy(self.handle)
+                self.handle = None
+        except Exception:
+            pass
+
+
+_PLAN_CACHE = {}
+
+
+def get_plan(n, cin, xh, xw, h, w, device, math_mode=MATH_BF16, widths=DEFAULT_WIDTHS) -> HrfpPlan:
+    key = (n, cin, xh, xw, h, w, math_mode, tuple(widths), str(device))
+    p = _PLAN_CACHE.get(key)
+    if p is None:
+        p = HrfpPlan(n, cin, xh, xw, h, w, device, math_mode, widths)
+        _PLAN_CACHE[key] = p
+    return p
+
+
+class _HrfpFn(torch.autograd.Function):
+    """(xp, x_add) -> (OCout + x_add, OCout_dec).  x_add may be None (returns OCout alone)."""
+
+    @staticmethod
+    def forward(ctx, xp, x_add, plan, weights, gammas, betas, rmeans, rvars, momentum, eps, want_out, want_dec):
+        lib = _lib.load()
+        if not xp.is_cuda or xp.dtype != torch.float32:
+            raise _lib.MrfpError("HRFP kernels need a CUDA fp32 tensor (no CPU fallback)")
+        xp_c = xp.contiguous()
+        dev = xp.device
+        saved = torch.empty(plan.saved_bytes, dtype=torch.uint8, device=dev)
+        ws = plan.workspace()
+        ocout = torch.empty_like(xp_c) if want_out else None
+        ocdec = torch.empty(plan.dec_shape, dtype=torch.float32, device=dev) if want_dec else None
+        xa = x_add.contiguous() if (x_add is not None and want_out) else None
+        wa, ga = _ptr_array(weights), _ptr_array(gammas)
+        ba = _ptr_array(betas) if betas is not None else None
+        rma = _ptr_array(rmeans) if rmeans is not None else None
+        rva = _ptr_array(rvars) if rvars is not None else None
+        with torch.cuda.device(dev):
+            rc = lib.mrfp_hrfp_fwd(plan.handle, xp_c.data_ptr(), wa, ga, ba, rma, rva, momentum, eps,
+                                   None if xa is None else xa.data_ptr(),
+                                   None if ocout is None else ocout.data_ptr(),
+                                   None if ocdec is None else ocdec.data_ptr(),
+                                   plan.lut.data_ptr(), saved.data_ptr(), ws.data_ptr(), _stream_ptr(dev))
+        _lib.check(rc, "mrfp_hrfp_fwd")
+        ctx.plan = plan
+        ctx.saved_buf = saved
+        ctx.gammas = [g for g in gammas]       # keep alive; gamma is read again in backward
+        ctx.has_add = x_add is not None
+        ctx.want_out, ctx.want_dec = want_out, want_dec
+        outs = []
+        if want_out:
+            outs.append(ocout)
+        if want_dec:
+            outs.append(ocdec)
+        return tuple(outs)
+
+    @staticmethod
+    def backward(ctx, *grads):
+        lib = _lib.load()
+        plan = ctx.plan
+        gi = iter(grads)
+        g_out = next(gi) if ctx.want_out else None
+        g_dec = next(gi) if ctx.want_dec else None
+        dev = plan.device
+        g_out_c = g_out.contiguous() if g_out is not None else None
+        g_dec_c = g_dec.contiguous() if g_dec is not None else None
+        g_xp = None
+        if ctx.needs_input_grad[0]:
+            g_xp = torch.empty((plan.n, plan.cin, plan.xh, plan.xw), dtype=torch.float32, device=dev)
+            ga = _ptr_array(ctx.gammas)
+            ws = plan.workspace()
+            with torch.cuda.device(dev):
+                rc = lib.mrfp_hrfp_bwd(plan.handle, None if g_out_c is None else g_out_c.data_ptr(),
+                                       None if g_dec_c is None else g_dec_c.data_ptr(), ga, plan.lut.data_ptr(),
+                                       ctx.saved_buf.data_ptr(), g_xp.data_ptr(), ws.data_ptr(), _stream_ptr(dev))
+            _lib.check(rc, "mrfp_hrfp_bwd")
+        g_add = g_out_c if (ctx.has_add and ctx.needs_input_grad[1]) else None
+        ctx.saved_buf = None
+        return (g_xp, g_add) + (None,) * 10
+
+
+def hrfp_chain(xp, convs, bns, h, w, x_add=None, want_out=True, want_dec=True, math_mode=MATH_BF16,
+               update_running_stats=True):
+    """Runs the chain of deepv3.py:320-327 on `xp` with the caller's 8 conv / 8 BN modules.
+
+    Returns (OCout [+ x_add], OCout_dec) restricted to the requested outputs."""
+    n, cin, xh, xw = xp.shape
+    widths = tuple(c.out_channels for c in convs[:4])
+    plan = get_plan(n, cin, xh, xw, h, w, xp.device, math_mode, widths)
+    weights = [c.weight for c in convs]
+    gammas = [b.weight for b in bns]
+    betas = [b.bias for b in bns]
+    track = update_running_stats and all(b.track_running_stats and b.running_mean is not None for b in bns)
+    rmeans = [b.running_mean for b in bns] if track else None
+    rvars = [b.running_var for b in bns] if track else None
+    momentum = bns[0].momentum if bns[0].momentum is not None else 0.1
+    eps = bns[0].eps
+    outs = _HrfpFn.apply(xp, x_add, plan, weights, gammas, betas, rmeans, rvars, float(momentum), float(eps),
+                         want_out, want_dec)
+    if track:
+        n_run = 8 if want_out else 4
+        for b in bns[:n_run]:
+            b.num_batches_tracked += 1
+    outs = list(outs)
+    out = outs.pop(0) if want_out else None
+    dec = outs.pop(0) if want_dec else None
+    return out, dec
+
+
+def hrfp_plus_add(dec1_up: torch.Tensor, ocout_dec: torch.Tensor) -> torch.Tensor:
+    """deepv3.py:357 — `torch.add(OCout_dec, dec1)` as one streaming kernel (autograd: identity to both)."""
+    return _AddFn.apply(dec1_up, ocout_dec)
+
+
+class _AddFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, a, b):
+        lib = _lib.load()
+        a_c, b_c = a.contiguous(), b.contiguous()
+        out = torch.empty_like(a_c)
+        with torch.cuda.device(a.device):
+            rc = lib.mrfp_add_f32(a_c.data_ptr(), b_c.data_ptr(), out.data_ptr(), a_c.numel(), _stream_ptr(a.device))
+        _lib.check(rc, "mrfp_add_f32")
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        return g, g

@@ -1,0 +1,144 @@
+"""HRFP CUDA chain (through the C ABI) vs the numpy oracle and the reference-generated fixtures."""
+import math
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import mrfp_oracle as O
+from tests.common import GOLDEN, make_hrfp_params, make_feat
+
+pytestmark = pytest.mark.gpu
+
+# tolerances, relative to max|ref| of each tensor
+TOL = {0: dict(fwd=2e-4, bwd=1e-3),        # fp32 CUDA-core path
+       2: dict(fwd=4e-2, bwd=8e-2)}        # bf16 tensor-core path (8 chained bf16 stages)
+
+
+def _modules(ws, gs, device):
+    convs, bns = [], []
+    for (cin, cout, dil), w, g in zip(O.HRFP_LAYERS, ws, gs):
+        c = torch.nn.Conv2d(cin, cout, 3, padding=dil, dilation=dil).to(device).requires_grad_(False)
+        b = torch.nn.BatchNorm2d(cout).to(device).requires_grad_(False)
+        with torch.no_grad():
+            c.weight.copy_(torch.from_numpy(w)); c.bias.zero_()
+            b.weight.copy_(torch.from_numpy(g)); b.bias.zero_()
+        convs.append(c); bns.append(b)
+    return convs, bns
+
+
+def _run(xp_np, ws, gs, h, w, mode, g1=None, g2=None, x_add=None):
+    from mrfp_b200.hrfp import hrfp_chain
+    dev = "cuda"
+    convs, bns = _modules(ws, gs, dev)
+    xp = torch.from_numpy(xp_np).to(dev).requires_grad_(True)
+    xa = None if x_add is None else torch.from_numpy(x_add).to(dev).requires_grad_(True)
+    out, dec = hrfp_chain(xp, convs, bns, h, w, x_add=xa, math_mode=mode)
+    gx = None
+    if g1 is not None or g2 is not None:
+        outs, gr = [], []
+        if g1 is not None:
+            outs.append(out); gr.append(torch.from_numpy(g1).to(dev))
+        if g2 is not None:
+            outs.append(dec); gr.append(torch.from_numpy(g2).to(dev))
+        torch.autograd.backward(outs, gr)
+        gx = xp.grad.cpu().numpy()
+    return out.detach().cpu().numpy(), dec.detach().cpu().numpy(), gx, bns, (None if xa is None else xa.grad)
+
+
+def _relerr(got, ref):
+    ref = np.asarray(ref, dtype=np.float64)
+    return np.abs(got.astype(np.float64) - ref).max() / max(np.abs(ref).max(), 1e-30)
+
+
+@pytest.mark.parametrize("mode", [0, 2])
+@pytest.mark.parametrize("tag", ["sq", "rect"])
+def test_vs_reference_fixture(tag, mode):
+    g = np.load(os.path.join(GOLDEN, "hrfp.npz"))
+    n, h, w, seed = [int(v) for v in g[f"{tag}_meta"]]
+    xh, xw = math.ceil(h / 4), math.ceil(w / 4)
+    ws, gs = make_hrfp_params(seed)
+    xp = make_feat(seed + 50, (n, 64, xh, xw))
+    rng = np.random.default_rng(seed + 70)
+    g1 = rng.standard_normal((n, 64, xh, xw)).astype(np.float32)
+    g2 = rng.standard_normal((n, 256, h // 2, w // 2)).astype(np.float32)
+    out, dec, gx, bns, _ = _run(xp, ws, gs, h, w, mode, g1, g2)
+    t = TOL[mode]
+    assert _relerr(out, g[f"{tag}_ocout"]) <= t["fwd"]
+    assert _relerr(dec, g[f"{tag}_ocout_dec"].astype(np.float32)) <= max(t["fwd"], 2e-3)   # fixture stored as fp16
+    assert _relerr(gx, g[f"{tag}_gx_both"]) <= t["bwd"]
+    for k in range(8):
+        rtol = 1e-4 if mode == 0 else 2e-2
+        assert np.allclose(bns[k].running_mean.cpu().numpy(), g[f"{tag}_rm{k}"], rtol=rtol, atol=rtol)
+        assert np.allclose(bns[k].running_var.cpu().numpy(), g[f"{tag}_rv{k}"], rtol=rtol, atol=rtol)
+        assert int(bns[k].num_batches_tracked) == 1
+
+
+@pytest.mark.parametrize("mode", [0, 2])
+@pytest.mark.parametrize("which", ["out", "dec"])
+def test_single_gradient_paths(which, mode):
+    g = np.load(os.path.join(GOLDEN, "hrfp.npz"))
+    n, h, w, seed = [int(v) for v in g["sq_meta"]]
+    xh, xw = math.ceil(h / 4), math.ceil(w / 4)
+    ws, gs = make_hrfp_params(seed)
+    xp = make_feat(seed + 50, (n, 64, xh, xw))
+    rng = np.random.default_rng(seed + 70)
+    g1 = rng.standard_normal((n, 64, xh, xw)).astype(np.float32)
+    g2 = rng.standard_normal((n, 256, h // 2, w // 2)).astype(np.float32)
+    _, _, gx, _, _ = _run(xp, ws, gs, h, w, mode, g1 if which == "out" else None, g2 if which == "dec" else None)
+    assert _relerr(gx, g[f"sq_gx_{which}"]) <= TOL[mode]["bwd"]
+
+
+@pytest.mark.parametrize("mode", [0, 2])
+def test_vs_oracle_odd_geometry_and_add(mode):
+    n, h, w = 3, 60, 44
+    xh, xw = 15, 11
+    ws, gs = make_hrfp_params(5)
+    xp = make_feat(6, (n, 64, xh, xw))
+    x_add = np.random.default_rng(7).standard_normal((n, 64, xh, xw)).astype(np.float32)
+    rng = np.random.default_rng(8)
+    g1 = rng.standard_normal((n, 64, xh, xw)).astype(np.float32)
+    g2 = rng.standard_normal((n, 256, h // 2, w // 2)).astype(np.float32)
+    out, dec, gx, _, ga = _run(xp, ws, gs, h, w, mode, g1, g2, x_add=x_add)
+    ws64 = [a.astype(np.float64) for a in ws]; gs64 = [a.astype(np.float64) for a in gs]
+    ro, rd, saved = O.hrfp_forward(xp.astype(np.float64), ws64, gs64, h, w)
+    rg = O.hrfp_backward(g1.astype(np.float64), g2.astype(np.float64), ws64, gs64, saved)
+    t = TOL[mode]
+    assert _relerr(out, ro + x_add) <= t["fwd"]
+    assert _relerr(dec, rd) <= t["fwd"]
+    assert _relerr(gx, rg) <= t["bwd"]
+    assert torch.equal(ga.cpu(), torch.from_numpy(g1))        # d(OCout + x)/dx = identity
+
+
+def test_plan_geometry_768():
+    from mrfp_b200.hrfp import HrfpPlan
+    p = HrfpPlan(8, 64, 192, 192, 768, 768, "cuda", 0)
+    sizes = [192] + [s[5] for s in p.stages]
+    assert sizes == [192, 231, 277, 332, 384, 384, 321, 256, 192]
+    assert [s[:3] for s in p.stages] == [tuple(l) for l in O.HRFP_LAYERS]
+    g = np.load(os.path.join(GOLDEN, "lut.npz"))
+    lut = p.lut.cpu().numpy()
+    # the blob starts with idx_h, idx_w of stage 0
+    assert np.array_equal(lut[:231], g["768_h_0"]) and np.array_equal(lut[231:462], g["768_w_0"])
+
+
+def test_plus_add():
+    from mrfp_b200.hrfp import hrfp_plus_add
+    a = torch.randn(2, 8, 12, 14, device="cuda", requires_grad=True)
+    b = torch.randn(2, 8, 12, 14, device="cuda", requires_grad=True)
+    o = hrfp_plus_add(a, b)
+    assert torch.equal(o, a + b)
+    o.sum().backward()
+    assert torch.equal(a.grad, torch.ones_like(a)) and torch.equal(b.grad, torch.ones_like(b))
+
+
+def test_bad_plan_arguments():
+    import ctypes
+    from mrfp_b200 import _lib
+    lib = _lib.load()
+    h = ctypes.c_void_p()
+    assert lib.mrfp_hrfp_plan_create(ctypes.byref(h), 0, 64, 12, 12, 48, 48, None, 0) == -2
+    assert lib.mrfp_hrfp_plan_create(ctypes.byref(h), 2, 60, 12, 12, 48, 48, None, 0) == -4
+    assert lib.mrfp_hrfp_plan_create(ctypes.byref(h), 2, 64, 12, 12, 48, 48, None, 1) == -4
+    assert lib.mrfp_hrfp_plan_ws_bytes(None) == 0
