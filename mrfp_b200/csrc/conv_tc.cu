@@ -1,5 +1,373 @@
+// tcgen05 implicit-GEMM 3x3 convolution for the HRFP chain (sm_100a), bf16 NHWC operands, fp32 accumulation
+// in TMEM.  Replaces the cuDNN fprop / dgrad calls behind nn.Conv2d at /root/reference/deepv3.py:320-327.
+//
+// GEMM view per output tile:  D[128 pixels][COUT] = sum over (tap, 64-channel chunk) A_tap[128][64] * B_tap[COUT][64]^T
+//   * M tile = 8 rows x 16 cols of output pixels (UMMA M = 128, one TMEM lane per pixel)
+//   * A operand: one 4-D TMA box {64 ch, 16, 8, 1} of the NHWC input at the tap's (dy,dx)*dilation offset —
+//     TMA zero-fills the halo / out-of-image part, so padding costs nothing and no im2col buffer exists;
+//     the box lands in shared memory as 128 rows x 128 B with the 128-byte swizzle = canonical K-major UMMA tile
+//   * B operand: 2-D TMA box {64, COUT} of the tap-major packed weights [9*COUT][CIN]
+//   * accumulators: 2 TMEM stages x COUT fp32 columns (epilogue of tile i overlaps the MMAs of tile i+1)
+// Warp roles (192 threads, persistent over tiles): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer
+// (one elected thread), warps 2-5 = epilogue: tcgen05.ld -> replication-count-weighted per-channel sum / sum of
+// squares of the fp32 accumulators (BN batch statistics of the resampled tensor, warp-transposed shuffle
+// reduction) -> bf16 pack into a swizzled staging tile -> TMA store (clips the ragged image edge).
 #include "hrfp.cuh"
+#include <cuda.h>
+#include <mutex>
+
 namespace mrfp {
-bool conv3x3_tc_supported(int, int) { return false; }
-int conv3x3_tc_bf16(const __nv_bfloat16*, const __nv_bfloat16*, __nv_bfloat16*, int, int, int, int, int, int, const int*, const int*, double*, cudaStream_t) { return MRFP_ERR_UNSUPPORTED; }
+namespace {
+
+constexpr int kBlockK = 64;          // channels per k-step = 128 bytes of bf16 = one swizzle row
+constexpr int kUmmaK = 16;
+constexpr int kThreads = 192;
+constexpr int kATileBytes = 128 * 128;          // 128 pixels x 64 ch x 2 B
+constexpr int kStageOutBytes = 128 * 128;       // 128 pixels x 64 ch x 2 B
+
+template <int COUT> struct Cfg {
+  static constexpr int kBTileBytes = COUT * 128;
+  static constexpr int kStages = COUT == 256 ? 4 : (COUT == 128 ? 5 : 6);
+  static constexpr int kOutBufs = COUT == 256 ? 1 : 2;
+  static constexpr int kTmemCols = 2 * COUT < 32 ? 32 : 2 * COUT;   // power of two for COUT in {16..256}
+  static constexpr int kSmemBytes = kStages * (kATileBytes + kBTileBytes) + kOutBufs * kStageOutBytes +
+                                    2 * COUT * 4 + 256 /* barriers */ + 1024 /* alignment slack */;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+               ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+               ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, const void* src, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem]^T, bf16 x bf16 -> fp32, issued by one thread for the CTA
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
+// K-major, 128-byte swizzle, 8-row groups 1024 B apart (cute::UMMA::SmemDescriptor, version 1)
+__device__ __forceinline__ uint64_t make_desc_sw128(uint32_t smem_addr) {
+  return (uint64_t)((smem_addr >> 4) & 0x3FFF) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+
+// transposed butterfly: on return x[0] of lane l = sum over the 32 lanes of their x[l]   (31 shuffles)
+__device__ __forceinline__ float warp_transpose_sum(float (&x)[32], int lane) {
+#pragma unroll
+  for (int s = 16; s >= 1; s >>= 1) {
+    const bool up = (lane & s) != 0;
+#pragma unroll
+    for (int i = 0; i < s; ++i) {
+      const float send = up ? x[i] : x[i + s];
+      const float keep = up ? x[i + s] : x[i];
+      x[i] = keep + __shfl_xor_sync(0xffffffffu, send, s);
+    }
+  }
+  return x[0];
+}
+
+template <int COUT>
+__global__ void __launch_bounds__(kThreads, 1)
+conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constant__ CUtensorMap tmap_w,
+                  const __grid_constant__ CUtensorMap tmap_out, int CIN, int dil, int tiles_h, int tiles_w,
+                  int num_tiles, const int* __restrict__ cnt_h, const int* __restrict__ cnt_w,
+                  double* __restrict__ stat_acc) {
+  using C = Cfg<COUT>;
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  unsigned char* sA = smem;
+  unsigned char* sB = sA + C::kStages * kATileBytes;
+  unsigned char* sOut = sB + C::kStages * C::kBTileBytes;
+  float* s_stats = reinterpret_cast<float*>(sOut + C::kOutBufs * kStageOutBytes);
+  uint64_t* full = reinterpret_cast<uint64_t*>(s_stats + 2 * COUT);
+  uint64_t* empty = full + C::kStages;
+  uint64_t* tmem_full = empty + C::kStages;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nk = 9 * (CIN / kBlockK);       // k-steps per tile
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < C::kStages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  for (int i = threadIdx.x; i < 2 * COUT; i += kThreads) s_stats[i] = 0.f;
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)), "n"(C::kTmemCols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+        const int tw = t % tiles_w, th = (t / tiles_w) % tiles_h, n = t / (tiles_w * tiles_h);
+        const int h0 = th * kTileH, w0 = tw * kTileW;
+        for (int tap = 0; tap < 9; ++tap) {
+          const int dy = (tap / 3 - 1) * dil, dx = (tap % 3 - 1) * dil;
+          for (int kc = 0; kc < CIN / kBlockK; ++kc) {
+            mbar_wait(&empty[stage], phase ^ 1);
+            mbar_expect_tx(&full[stage], kATileBytes + C::kBTileBytes);
+            tma_load_4d(sA + stage * kATileBytes, &tmap_in, &full[stage], kc * kBlockK, w0 + dx, h0 + dy, n);
+            tma_load_2d(sB + stage * C::kBTileBytes, &tmap_w, &full[stage], kc * kBlockK, tap * COUT);
+            if (++stage == C::kStages) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      // instruction descriptor: D=f32, A=B=bf16, both K-major, N=COUT, M=128
+      constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(COUT >> 3) << 17) | ((128u >> 4) << 24);
+      int stage = 0; uint32_t phase = 0;
+      int it = 0;
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+        const int acc = it & 1;
+        mbar_wait(&tmem_empty[acc], ((it >> 1) & 1) ^ 1);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * COUT);
+        for (int ks = 0; ks < nk; ++ks) {
+          mbar_wait(&full[stage], phase);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint64_t da = make_desc_sw128(smem_u32(sA + stage * kATileBytes));
+          const uint64_t db = make_desc_sw128(smem_u32(sB + stage * C::kBTileBytes));
+#pragma unroll
+          for (int k = 0; k < kBlockK / kUmmaK; ++k)   // +32 B per UMMA_K inside the swizzle row
+            umma_bf16(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (ks | k) != 0);
+          umma_commit(&empty[stage]);                  // frees the smem slot when the MMAs have read it
+          if (++stage == C::kStages) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&tmem_full[acc]);                  // accumulator complete
+      }
+    }
+  } else {
+    // ===================== epilogue (warps 2..5) =====================
+    const int q = warp & 3;                     // TMEM lane quarter this warp may access
+    const int r = q * 32 + lane;                // accumulator row = pixel inside the tile
+    const int hl = r / kTileW, wl = r % kTileW;
+    const bool leader = threadIdx.x == 64;      // first epilogue thread issues the TMA stores
+    int it = 0, obuf = 0;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+      const int tw = t % tiles_w, th = (t / tiles_w) % tiles_h, n = t / (tiles_w * tiles_h);
+      const int h0 = th * kTileH, w0 = tw * kTileW;
+      const int acc = it & 1;
+      float wgt = 0.f;
+      if (stat_acc) wgt = (float)(cnt_h[h0 + hl] * cnt_w[w0 + wl]);   // 0 outside the image (zero-padded tables)
+      mbar_wait(&tmem_full[acc], (it >> 1) & 1);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll 1
+      for (int j = 0; j < COUT / 64; ++j) {
+        unsigned char* ob = sOut + obuf * kStageOutBytes;
+        // the TMA store that last read this staging buffer must have drained
+        if (leader) asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(C::kOutBufs - 1) : "memory");
+        epi_bar_sync();
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          uint32_t v[32];
+          tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * COUT + j * 64 + half * 32), v);
+          if (stat_acc) {
+            float x1[32], x2[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              const float f = __uint_as_float(v[i]);
+              x1[i] = wgt * f;
+              x2[i] = x1[i] * f;
+            }
+            const float s1 = warp_transpose_sum(x1, lane);
+            const float s2 = warp_transpose_sum(x2, lane);
+            atomicAdd(&s_stats[j * 64 + half * 32 + lane], s1);
+            atomicAdd(&s_stats[COUT + j * 64 + half * 32 + lane], s2);
+          }
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {          // four 16-byte chunks (8 channels each) per half
+            uint32_t p[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const __nv_bfloat162 h2 = __floats2bfloat162_rn(__uint_as_float(v[c * 8 + 2 * i]), __uint_as_float(v[c * 8 + 2 * i + 1]));
+              p[i] = *reinterpret_cast<const uint32_t*>(&h2);
+            }
+            const int chunk = half * 4 + c;
+            *reinterpret_cast<uint4*>(ob + r * 128 + ((chunk ^ (r & 7)) << 4)) = make_uint4(p[0], p[1], p[2], p[3]);
+          }
+        }
+        if (j == COUT / 64 - 1) {               // all TMEM reads of this accumulator are done
+          asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        epi_bar_sync();
+        if (leader) {
+          tma_store_4d(&tmap_out, ob, j * 64, w0, h0, n);
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+        if (++obuf == C::kOutBufs) obuf = 0;
+      }
+    }
+    if (leader) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    epi_bar_sync();
+    if (stat_acc) {
+      for (int c = threadIdx.x - 64; c < COUT; c += 128) {
+        atomicAdd(stat_acc + c, (double)s_stats[c]);
+        atomicAdd(stat_acc + kMaxC + c, (double)s_stats[COUT + c]);
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(C::kTmemCols) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// host side: tensor maps (driver entry point fetched through the runtime; no link against libcuda)
+// ------------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  });
+  return fn;
+}
+
+int make_map(CUtensorMap* m, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides,
+             const cuuint32_t* box) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return MRFP_ERR_DRIVER;
+  const cuuint32_t ones[4] = {1, 1, 1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), dims, strides, box,
+                  ones, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? MRFP_OK : MRFP_ERR_DRIVER;
+}
+
+template <int COUT>
+int launch(const __nv_bfloat16* in, const __nv_bfloat16* wpack, __nv_bfloat16* out, int N, int H, int W, int cin,
+           int dil, const int* cnt_h, const int* cnt_w, double* stat_acc, cudaStream_t stream) {
+  CUtensorMap m_in, m_w, m_out;
+  {
+    const cuuint64_t dims[4] = {(cuuint64_t)cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+    const cuuint64_t strides[3] = {(cuuint64_t)cin * 2, (cuuint64_t)W * cin * 2, (cuuint64_t)H * W * cin * 2};
+    const cuuint32_t box[4] = {kBlockK, kTileW, kTileH, 1};
+    int rc = make_map(&m_in, in, 4, dims, strides, box);
+    if (rc) return rc;
+  }
+  {
+    const cuuint64_t dims[2] = {(cuuint64_t)cin, (cuuint64_t)9 * COUT};
+    const cuuint64_t strides[1] = {(cuuint64_t)cin * 2};
+    const cuuint32_t box[2] = {kBlockK, COUT};
+    int rc = make_map(&m_w, wpack, 2, dims, strides, box);
+    if (rc) return rc;
+  }
+  {
+    const cuuint64_t dims[4] = {(cuuint64_t)COUT, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+    const cuuint64_t strides[3] = {(cuuint64_t)COUT * 2, (cuuint64_t)W * COUT * 2, (cuuint64_t)H * W * COUT * 2};
+    const cuuint32_t box[4] = {64, kTileW, kTileH, 1};
+    int rc = make_map(&m_out, out, 4, dims, strides, box);
+    if (rc) return rc;
+  }
+  DeviceInfo di;
+  int rc = get_device_info(&di);
+  if (rc) return rc;
+  const int tiles_h = (H + kTileH - 1) / kTileH, tiles_w = (W + kTileW - 1) / kTileW;
+  const int num_tiles = N * tiles_h * tiles_w;
+  const int grid = num_tiles < di.sm_count ? num_tiles : di.sm_count;
+  auto kern = conv3x3_tc_kernel<COUT>;
+  MRFP_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<COUT>::kSmemBytes));
+  kern<<<grid, kThreads, Cfg<COUT>::kSmemBytes, stream>>>(m_in, m_w, m_out, cin, dil, tiles_h, tiles_w, num_tiles, cnt_h,
+                                                           cnt_w, stat_acc);
+  MRFP_CUDA_TRY(cudaGetLastError());
+  return MRFP_OK;
+}
+
+}  // namespace
+
+bool conv3x3_tc_supported(int cin, int cout) {
+  return cin % kBlockK == 0 && cin <= kMaxC && (cout == 64 || cout == 128 || cout == 256);
+}
+
+int conv3x3_tc_bf16(const __nv_bfloat16* in, const __nv_bfloat16* wpack, __nv_bfloat16* out, int N, int H, int W,
+                    int cin, int cout, int dil, const int* cnt_h, const int* cnt_w, double* stat_acc,
+                    cudaStream_t stream) {
+  if (!conv3x3_tc_supported(cin, cout)) return MRFP_ERR_UNSUPPORTED;
+  if (((uintptr_t)in | (uintptr_t)wpack | (uintptr_t)out) & 15) return MRFP_ERR_WORKSPACE;
+  switch (cout) {
+    case 64: return launch<64>(in, wpack, out, N, H, W, cin, dil, cnt_h, cnt_w, stat_acc, stream);
+    case 128: return launch<128>(in, wpack, out, N, H, W, cin, dil, cnt_h, cnt_w, stat_acc, stream);
+    case 256: return launch<256>(in, wpack, out, N, H, W, cin, dil, cnt_h, cnt_w, stat_acc, stream);
+  }
+  return MRFP_ERR_UNSUPPORTED;
+}
+
+}  // namespace mrfp
+
+// test hook (not part of the public header): one tcgen05 convolution on caller-provided bf16 NHWC buffers
+extern "C" int mrfp_debug_conv3x3_bf16(const void* in, const void* wpack, void* out, int N, int H, int W, int cin,
+                                       int cout, int dil, const int* cnt_h, const int* cnt_w, double* stat_acc,
+                                       void* stream) {
+  return mrfp::conv3x3_tc_bf16((const __nv_bfloat16*)in, (const __nv_bfloat16*)wpack, (__nv_bfloat16*)out, N, H, W, cin,
+                               cout, dil, cnt_h, cnt_w, stat_acc, (cudaStream_t)stream);
 }

@@ -1,0 +1,67 @@
+"""tcgen05 implicit-GEMM conv kernel alone (debug hook of the C library) vs torch conv2d on the same bf16 inputs."""
+import ctypes
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+def _conv_tc(x_nchw, w_oihw, dil, cnt_h=None, cnt_w=None):
+    from mrfp_b200 import _lib
+    lib = _lib.load()
+    fn = lib.mrfp_debug_conv3x3_bf16
+    fn.restype = ctypes.c_int
+    fn.argtypes = [ctypes.c_void_p] * 3 + [ctypes.c_int] * 6 + [ctypes.c_void_p] * 4
+    n, cin, h, w = x_nchw.shape
+    cout = w_oihw.shape[0]
+    x = x_nchw.permute(0, 2, 3, 1).contiguous().to(torch.bfloat16)
+    wp = w_oihw.permute(2, 3, 0, 1).reshape(9, cout, cin).contiguous().to(torch.bfloat16)   # [tap][co][ci]
+    out = torch.full((n, h, w, cout), float("nan"), device="cuda", dtype=torch.bfloat16)
+    acc = torch.zeros(2, 256, device="cuda", dtype=torch.float64)
+    st = torch.cuda.current_stream().cuda_stream
+    rc = fn(x.data_ptr(), wp.data_ptr(), out.data_ptr(), n, h, w, cin, cout, dil,
+            None if cnt_h is None else cnt_h.data_ptr(), None if cnt_w is None else cnt_w.data_ptr(),
+            acc.data_ptr() if cnt_h is not None else None, st)
+    assert rc == 0, rc
+    torch.cuda.synchronize()
+    return out.permute(0, 3, 1, 2).float(), acc, x.permute(0, 3, 1, 2).float(), wp.reshape(3, 3, cout, cin).permute(2, 3, 0, 1).float()
+
+
+@pytest.mark.parametrize("cin,cout,dil", [(64, 64, 1), (64, 64, 2), (64, 128, 2), (128, 256, 2), (256, 128, 1), (128, 64, 1)])
+@pytest.mark.parametrize("shape", [(2, 8, 16), (2, 20, 37), (1, 50, 61)])
+def test_conv_matches_torch(cin, cout, dil, shape):
+    n, h, w = shape
+    torch.manual_seed(cin + cout + dil + h)
+    x = torch.relu(torch.randn(n, cin, h, w, device="cuda"))
+    wt = torch.randn(cout, cin, 3, 3, device="cuda") * (2.0 / (9 * cin)) ** 0.5
+    cnt_h = torch.zeros(((h + 7) // 8 + 1) * 8, dtype=torch.int32, device="cuda")
+    cnt_w = torch.zeros(((w + 15) // 16 + 1) * 16, dtype=torch.int32, device="cuda")
+    cnt_h[:h] = torch.randint(0, 3, (h,), device="cuda", dtype=torch.int32)
+    cnt_w[:w] = torch.randint(0, 3, (w,), device="cuda", dtype=torch.int32)
+    got, acc, xb, wb = _conv_tc(x, wt, dil, cnt_h, cnt_w)
+    torch.backends.cudnn.allow_tf32 = False
+    ref = F.conv2d(xb.double(), wb.double(), padding=dil, dilation=dil)
+    assert not torch.isnan(got).any()
+    err = (got.double() - ref).abs().max().item()
+    # bf16 output rounding: half an ulp = 2^-9 relative
+    assert err <= 2 ** -8 * ref.abs().max().item() + 1e-6, err
+    wgt = (cnt_h[:h].double()[:, None] * cnt_w[:w].double()[None, :])[None, None]
+    s1 = (ref * wgt).sum((0, 2, 3)); s2 = (ref * ref * wgt).sum((0, 2, 3))
+    assert torch.allclose(acc[0, :cout], s1, rtol=1e-4, atol=1e-3 * s1.abs().max().item())
+    assert torch.allclose(acc[1, :cout], s2, rtol=1e-4, atol=1e-3 * s2.abs().max().item())
+
+
+def test_conv_without_stats_full_size_linearity():
+    """D1 shape of the reference chain (256->128 @384^2), batch 2: conv(a*x) = a*conv(x) and agreement with cuDNN."""
+    torch.manual_seed(0)
+    x = torch.relu(torch.randn(2, 256, 384, 384, device="cuda"))
+    wt = torch.randn(128, 256, 3, 3, device="cuda") * (2.0 / (9 * 256)) ** 0.5
+    got, _, xb, wb = _conv_tc(x, wt, 1)
+    got2, _, _, _ = _conv_tc(2 * x, wt, 1)
+    assert torch.equal(got2, 2 * got)                 # exact: power-of-two scaling commutes with bf16 rounding
+    torch.backends.cudnn.allow_tf32 = False
+    ref = F.conv2d(xb, wb, padding=1)
+    assert (got - ref).abs().max().item() <= 2 ** -8 * ref.abs().max().item() + 1e-5
