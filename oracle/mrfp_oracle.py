@@ -214,22 +214,35 @@ def resample_bwd(gr: np.ndarray, idx_h: np.ndarray, idx_w: np.ndarray, in_h: int
     return out
 
 
+def round_bf16(x: np.ndarray) -> np.ndarray:
+    """Round-to-nearest-even to bfloat16 precision (returned as float64)."""
+    u = np.ascontiguousarray(x, dtype=np.float32).view(np.uint32)
+    r = ((u >> np.uint32(16)) & np.uint32(1)) + np.uint32(0x7FFF)
+    return ((u + r) & np.uint32(0xFFFF0000)).view(np.float32).astype(np.float64)
+
+
 def hrfp_forward(xp: np.ndarray, weights: Sequence[np.ndarray], gammas: Sequence[np.ndarray],
                  h: int, w: int, betas: Optional[Sequence[np.ndarray]] = None,
                  biases: Optional[Sequence[np.ndarray]] = None,
-                 layers: Sequence[Tuple[int, int, int]] = HRFP_LAYERS):
+                 layers: Sequence[Tuple[int, int, int]] = HRFP_LAYERS, quant=None):
     """deepv3.py:320-327.  Returns (OCout, OCout_dec, saved) with saved = per-stage dict for backward
-    and for the BN running-stat side effect (a-8): batch mean, biased var, element count."""
+    and for the BN running-stat side effect (a-8): batch mean, biased var, element count.
+
+    `quant` (e.g. `round_bf16`) models a reduced-precision STORAGE format: it is applied where the
+    tensor-core CUDA path stores bf16 (stem feature, weights, each conv output, each activation); the
+    arithmetic stays exact and the BN statistics come from the unrounded accumulators, as on the device."""
     stages = hrfp_geometry(h, w, xp.shape[2], xp.shape[3], layers)
-    a = xp
+    q = quant if quant is not None else (lambda t: t)
+    a = q(xp)
     saved = []
     ocout_dec = None
     for k, st in enumerate(stages):
-        y = conv3x3(a, weights[k], st.dil, None if biases is None else biases[k])
-        r = resample(y, st.idx_h, st.idx_w)
-        mu = r.mean((0, 2, 3))
-        var = r.var((0, 2, 3))                                   # biased, used for normalisation
+        y_acc = conv3x3(a, q(weights[k]), st.dil, None if biases is None else biases[k])
+        r_acc = resample(y_acc, st.idx_h, st.idx_w)
+        mu = r_acc.mean((0, 2, 3))
+        var = r_acc.var((0, 2, 3))                               # biased, used for normalisation
         invstd = 1.0 / np.sqrt(var + BN_EPS)
+        r = resample(q(y_acc), st.idx_h, st.idx_w)
         xhat = (r - mu[None, :, None, None]) * invstd[None, :, None, None]
         z = xhat * gammas[k][None, :, None, None]
         if betas is not None:
@@ -237,24 +250,26 @@ def hrfp_forward(xp: np.ndarray, weights: Sequence[np.ndarray], gammas: Sequence
         a_next = np.maximum(z, 0)
         saved.append(dict(stage=st, a_in=a, xhat=xhat, z=z, invstd=invstd, mean=mu, var=var,
                           count=r.shape[0] * r.shape[2] * r.shape[3]))
-        a = a_next
         if k == 3:
-            ocout_dec = a
+            ocout_dec = a_next               # the fp32 NCHW outputs are written unrounded
+        a = q(a_next) if k < len(stages) - 1 else a_next
     return a, ocout_dec, saved
 
 
 def hrfp_backward(g_ocout: Optional[np.ndarray], g_ocout_dec: Optional[np.ndarray],
-                  weights: Sequence[np.ndarray], gammas: Sequence[np.ndarray], saved) -> np.ndarray:
-    """Input gradient (wrt xp) of the chain; no weight / gamma / beta gradients (frozen, deepv3.py:221-237)."""
-    ga = g_ocout
+                  weights: Sequence[np.ndarray], gammas: Sequence[np.ndarray], saved, quant=None) -> np.ndarray:
+    """Input gradient (wrt xp) of the chain; no weight / gamma / beta gradients (frozen, deepv3.py:221-237).
+    `quant`: storage rounding of the incoming gradients, of dY and of each dgrad output (see hrfp_forward)."""
+    q = quant if quant is not None else (lambda t: t)
+    ga = None if g_ocout is None else q(g_ocout)
     for k in range(7, -1, -1):
         sv = saved[k]
         st: HrfpStage = sv["stage"]
         if k == 3:
             if ga is None:
-                ga = g_ocout_dec
+                ga = None if g_ocout_dec is None else q(g_ocout_dec)
             elif g_ocout_dec is not None:
-                ga = ga + g_ocout_dec
+                ga = q(ga + g_ocout_dec)
         if ga is None:
             continue
         dz = ga * (sv["z"] > 0)
@@ -262,8 +277,8 @@ def hrfp_backward(g_ocout: Optional[np.ndarray], g_ocout_dec: Optional[np.ndarra
         m1 = dxh.mean((0, 2, 3))[None, :, None, None]
         m2 = (dxh * sv["xhat"]).mean((0, 2, 3))[None, :, None, None]
         dr = sv["invstd"][None, :, None, None] * (dxh - m1 - sv["xhat"] * m2)
-        dy = resample_bwd(dr, st.idx_h, st.idx_w, st.conv_h, st.conv_w)
-        ga = conv3x3_dgrad(dy, weights[k], st.dil)
+        dy = q(resample_bwd(dr, st.idx_h, st.idx_w, st.conv_h, st.conv_w))
+        ga = q(conv3x3_dgrad(dy, q(weights[k]), st.dil))
     return ga
 
 

@@ -11,9 +11,17 @@ from tests.common import GOLDEN, make_hrfp_params, make_feat
 
 pytestmark = pytest.mark.gpu
 
-# tolerances, relative to max|ref| of each tensor
-TOL = {0: dict(fwd=2e-4, bwd=1e-3),        # fp32 CUDA-core path
-       2: dict(fwd=4e-2, bwd=8e-2)}        # bf16 tensor-core path (8 chained bf16 stages)
+# Tolerances (max |err| / max |ref|).
+#  mode 0 (fp32 CUDA-core path): the reference's fp32 tolerance; measured 3e-6 fwd / 1.4e-6 bwd.
+#  mode 2 (bf16 tcgen05 path): eight chained stages whose activations, conv outputs and gradients are STORED in
+#  bf16.  The numpy oracle with the same storage rounding (oracle.round_bf16) sits 2.0e-2 (fwd) / 1.7e-1 (bwd) from the
+#  fp32 reference on these fixtures — that distance is the format, not the kernels — and the kernels sit at
+#  2.0e-2 / 1.7e-1 as well, and at 8e-3 / 7e-2 from the bf16-storage oracle (rounding-boundary chaos keeps the two
+#  bf16 computations from agreeing better than the rounding noise itself).  The tensor-core conv alone is checked
+#  to one bf16 ulp in tests/test_conv_tc_gpu.py.
+TOL = {0: dict(fwd=2e-4, bwd=1e-3),
+       2: dict(fwd=5e-2, bwd=3e-1)}
+TOL_VS_BF16_ORACLE = dict(fwd=2.5e-2, bwd=1.5e-1)
 
 
 def _modules(ws, gs, device):
@@ -109,6 +117,12 @@ def test_vs_oracle_odd_geometry_and_add(mode):
     assert _relerr(dec, rd) <= t["fwd"]
     assert _relerr(gx, rg) <= t["bwd"]
     assert torch.equal(ga.cpu(), torch.from_numpy(g1))        # d(OCout + x)/dx = identity
+    if mode == 2:      # same computation with the same bf16 storage points
+        qo, qd, qs = O.hrfp_forward(xp.astype(np.float64), ws64, gs64, h, w, quant=O.round_bf16)
+        qg = O.hrfp_backward(g1.astype(np.float64), g2.astype(np.float64), ws64, gs64, qs, quant=O.round_bf16)
+        assert _relerr(out, qo + x_add) <= TOL_VS_BF16_ORACLE["fwd"]
+        assert _relerr(dec, qd) <= TOL_VS_BF16_ORACLE["fwd"]
+        assert _relerr(gx, qg) <= TOL_VS_BF16_ORACLE["bwd"]
 
 
 def test_plan_geometry_768():
