@@ -1,0 +1,348 @@
+#!/usr/bin/env python
+"""Benchmark of the MRFP hot path (BASELINE.json metric) — one JSON line on stdout.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+A "step" is one forward+backward pass of the whole MRFP path over one batch of synthetic stem / layer1
+features at BASELINE config[1] shapes (per GPU: batch 8, 768x768 crop -> 64ch and 256ch @192x192):
+    NP+ call 1 fwd (deepv3.py:318) -> HRFP chain fwd incl. OCout+x (deepv3.py:320-330) -> NP+ call 2 fwd
+    (deepv3.py:335) -> backward of all three with gradients for x, OCout_dec (HRFP+, deepv3.py:357) and the
+    layer1 feature.
+The path shards by batch with no collective: under torchrun every rank runs the same step on
+its own batch-8 shard ("weak" scaling) and `value` is the aggregate images/s.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_PER_GPU, H_IMG, W_IMG = 8, 768, 768
+XH = XW = 192
+HRFP_FLOP_FWD_PER_SAMPLE = 192.70e9        # needed-only MACs x2; dgrad the same
+METRIC = "mrfp_fwd_bwd_throughput"
+UNIT = "img/s"
+CONFIG = {
+    "workload": "mrfp_fwd_bwd: NP+ on (8,64,192,192) and (8,256,192,192) + HRFP/HRFP+ chain 64ch@192^2 -> 256ch@384^2 -> "
+                "64ch@192^2, fwd + input-gradient bwd, per-GPU batch 8 (BASELINE config[1], 768x768 crop)",
+    "per_gpu_batch": N_PER_GPU, "crop": [H_IMG, W_IMG], "hrfp_math": "bf16 tcgen05 (fp32 accumulate)", "np_plus_math": "fp32",
+    "cache": "inputs larger than L2 (302 MB / 1.2 GB tensors per step); the per-kernel roofline launches flush L2 first",
+}
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    return ap.parse_args()
+
+
+# ----------------------------------------------------------------------------------------------------------
+# reference arm / cpu_baseline: the reference's CPU implementation of the path (oracle/torch_port.py)
+# ----------------------------------------------------------------------------------------------------------
+def cpu_reference_run(steps, warmup, batch=2):
+    """Bounded sample: the same step at BASELINE config[0] size (batch 2), all host threads."""
+    import torch
+    from oracle import torch_port as T
+    torch.set_num_threads(os.cpu_count() or 1)
+    torch.manual_seed(1)
+    convs, bns = T.make_layers()
+    g = torch.Generator().manual_seed(0)
+    xp = torch.relu(torch.randn(batch, 64, XH, XW, generator=g))
+    f2 = torch.relu(torch.randn(batch, 256, XH, XW, generator=g))
+    draws = [(1 + 0.75 * torch.randn(batch, c, 1, 1, generator=g), 0.75 * torch.randn(batch, c, 1, 1, generator=g)) for c in (64, 256)]
+    grads = (torch.randn(batch, 64, XH, XW, generator=g), torch.randn(batch, 256, H_IMG // 2, W_IMG // 2, generator=g),
+             torch.randn(batch, 256, XH, XW, generator=g))
+    for _ in range(warmup):
+        T.mrfp_step(convs, bns, xp, f2, draws, grads, H_IMG, W_IMG)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        T.mrfp_step(convs, bns, xp, f2, draws, grads, H_IMG, W_IMG)
+    dt = time.perf_counter() - t0
+    return dict(value=batch * steps / dt, unit=UNIT, cores=torch.get_num_threads(), kind="port",
+                sample=f"same step at batch {batch} (BASELINE config[0] shapes), {steps} timed + {warmup} warm-up passes of "
+                       "oracle/torch_port.py (the reference's torch operators on the host cores); the reference itself is a "
+                       "Python package under /root/reference that does not exist on the GPU box"), dt / steps * 1e3
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps = max(1, min(args.steps, 3))
+    warm = 1 if args.warmup > 0 else 0
+    base, ms = cpu_reference_run(steps, warm)
+    line = {"impl": "reference", "metric": METRIC, "value": base["value"], "unit": UNIT, "n_gpus": args.gpus,
+            "steps": steps, "warmup": warm, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": CONFIG, "cpu_baseline": base,
+            "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+# ----------------------------------------------------------------------------------------------------------
+# our arm
+# ----------------------------------------------------------------------------------------------------------
+class ClockSampler(threading.Thread):
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.stop_flag = index, [], False
+
+    def run(self):
+        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.05)
+
+    def summary(self):
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        sm = sorted(int(r[0]) for r in self.rows if r[0].isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(r[2 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": int(self.rows[0][1]) if self.rows[0][1].isdigit() else None,
+                "reasons": reasons, "samples": len(self.rows)}
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from mrfp_b200 import build, _lib
+    from mrfp_b200 import hrfp as H
+    from mrfp_b200 import npplus as NP
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl ours needs a CUDA device (the MRFP kernels have no CPU fallback)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    if rank == 0:
+        build.build()
+    if world > 1:
+        dist.barrier()
+    lib = _lib.load()
+
+    n = N_PER_GPU
+    torch.manual_seed(1 + rank)
+    from mrfp_b200.model import HRFP_CONVS, init_hrfp_module
+    chans, dils = [64, 64, 64, 128, 256, 128, 64, 64, 64], [1, 1, 2, 2, 1, 1, 2, 2]
+    convs = [torch.nn.Conv2d(chans[k], chans[k + 1], 3, padding=dils[k], dilation=dils[k]).to(dev).requires_grad_(False)
+             for k in range(len(HRFP_CONVS))]
+    bns = [torch.nn.BatchNorm2d(chans[k + 1]).to(dev).requires_grad_(False) for k in range(len(HRFP_CONVS))]
+    for c, b in zip(convs, bns):            # the reference initialiser (network/mynn.py:57-74), random-init weights
+        init_hrfp_module(c); init_hrfp_module(b)
+    sig = 0.5 + torch.rand(1, 256, 1, 1, device=dev)
+    mu = torch.randn(1, 256, 1, 1, device=dev)
+    xp = torch.relu(torch.randn(n, 64, XH, XW, device=dev) * sig[:, :64] + mu[:, :64])
+    f2 = torch.relu(torch.randn(n, 256, XH, XW, device=dev) * sig + mu)
+    draws = [(1 + 0.75 * torch.randn(n, c, 1, 1, device=dev), 0.75 * torch.randn(n, c, 1, 1, device=dev)) for c in (64, 256)]
+    g_x = torch.randn(n, 64, XH, XW, device=dev)
+    g_dec = torch.randn(n, 256, H_IMG // 2, W_IMG // 2, device=dev)
+    g_f2 = torch.randn(n, 256, XH, XW, device=dev)
+
+    def step(xp_, f2_, gx_, gdec_, gf2_):
+        """Public API path: autograd Functions over the C ABI."""
+        a = xp_.detach().requires_grad_(True)
+        b = f2_.detach().requires_grad_(True)
+        x = NP.np_plus_with_draws(a, *draws[0])
+        x, dec = H.hrfp_chain(a, convs, bns, H_IMG, W_IMG, x_add=x, math_mode=H.MATH_BF16)
+        y2 = NP.np_plus_with_draws(b, *draws[1])
+        torch.autograd.backward([x, dec, y2], [gx_, gdec_, gf2_])
+        return x, dec, y2, a.grad, b.grad
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step(xp, f2, g_x, g_dec, g_f2)
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    sync_all()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step(xp, f2, g_x, g_dec, g_f2)
+    e1.record()
+    sync_all()
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    if sampler:
+        sampler.stop_flag = True
+        sampler.join(timeout=2)
+    total_ms = float(ms.item())
+    value = world * n * args.steps / (total_ms * 1e-3)
+
+    # ---- e2e: same step through the same API with HOST (pinned) buffers, copies inside the timed region ----
+    host_in = [t.cpu().pin_memory() for t in (xp, f2, g_x, g_dec, g_f2)]
+    dev_in = [torch.empty_like(t) for t in (xp, f2, g_x, g_dec, g_f2)]
+    outs = step(xp, f2, g_x, g_dec, g_f2)
+    host_out = [torch.empty(o.shape, dtype=o.dtype).pin_memory() for o in outs]
+    h2d = sum(t.numel() * 4 for t in host_in)
+    d2h = sum(t.numel() * 4 for t in host_out)
+
+    def e2e_step():
+        for d, h in zip(dev_in, host_in):
+            d.copy_(h, non_blocking=True)
+        o = step(*dev_in)
+        for h, d in zip(host_out, o):
+            h.copy_(d, non_blocking=True)
+
+    e2e_steps = max(3, min(args.steps, 10))
+    for _ in range(2):
+        e2e_step()
+    sync_all()
+    e0.record()
+    for _ in range(e2e_steps):
+        e2e_step()
+    e1.record()
+    sync_all()
+    ms2 = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
+    e2e_value = world * n * e2e_steps / (float(ms2.item()) * 1e-3)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- per-kernel roofline measurements (rank 0, CUDA events on the launching stream, L2 flushed) ----
+    peaks = {}
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            peaks = json.load(f)
+    except Exception:
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    tf_peak = float(peaks.get("bf16_tflops", 1590.0))
+    tf_sustained = float(peaks.get("bf16_tflops_sustained", tf_peak))
+    peak_src = "measured (MEASURED_PEAKS.json)" if peaks else "fallback (B200_PROFILING.md)"
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    st = torch.cuda.current_stream().cuda_stream
+
+    def time_launch(fn, iters=10):
+        ts = []
+        for i in range(iters + 3):
+            flush.zero_()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(); fn(); b.record(); torch.cuda.synchronize()
+            if i >= 3:
+                ts.append(a.elapsed_time(b))
+        return sum(ts) / len(ts)
+
+    np_rows = {}
+    for name, x_t, (al, ep) in (("npplus_64ch", xp, draws[0]), ("npplus_256ch", f2, draws[1])):
+        nn_, c = x_t.shape[0], x_t.shape[1]
+        out = torch.empty_like(x_t)
+        mean = torch.empty(nn_, c, device=dev); beta = torch.empty(nn_, c, device=dev)
+        al2, ep2 = al.reshape(nn_, c).contiguous(), ep.reshape(nn_, c).contiguous()
+        wsb = lib.mrfp_npplus_ws_bytes(nn_, c, XH * XW)
+        wsp = torch.empty(wsb, dtype=torch.uint8, device=dev)
+        bytes_alg = 2 * x_t.numel() * 4
+        t_f = time_launch(lambda: _lib.check(lib.mrfp_npplus_fwd_f32(x_t.data_ptr(), al2.data_ptr(), ep2.data_ptr(), out.data_ptr(),
+                                                                     mean.data_ptr(), beta.data_ptr(), wsp.data_ptr(), wsb, nn_, c, XH * XW, st), "np fwd"))
+        t_b = time_launch(lambda: _lib.check(lib.mrfp_npplus_bwd_f32(x_t.data_ptr(), al2.data_ptr(), ep2.data_ptr(), mean.data_ptr(),
+                                                                     out.data_ptr(), wsp.data_ptr(), wsb, nn_, c, XH * XW, st), "np bwd"))
+        np_rows[name] = {"fwd_us": t_f * 1e3, "bwd_us": t_b * 1e3, "fwd_gbs": bytes_alg / t_f / 1e6, "bwd_gbs": bytes_alg / t_b / 1e6,
+                         "algorithmic_bytes": bytes_alg}
+    np_bytes = sum(2 * r["algorithmic_bytes"] for r in np_rows.values())
+    np_time = sum(r["fwd_us"] + r["bwd_us"] for r in np_rows.values()) * 1e-6
+    big = np_rows["npplus_256ch"]
+    roof_np = {"kernel": "npplus_ring_kernel<fwd> on (8,256,192,192)", "bound": "hbm", "achieved": big["fwd_gbs"], "peak": hbm_peak,
+               "unit": "GB/s", "frac": big["fwd_gbs"] / hbm_peak, "traffic": None, "peak_source": peak_src,
+               "all_four_np_kernels_gbs": np_bytes / np_time / 1e9, "per_call": np_rows}
+
+    # tcgen05 conv kernels of the chain, forward shapes (debug hook = the same kernel the chain launches)
+    import ctypes
+    fn = lib.mrfp_debug_conv3x3_bf16
+    fn.restype = ctypes.c_int
+    fn.argtypes = [ctypes.c_void_p] * 3 + [ctypes.c_int] * 6 + [ctypes.c_void_p] * 4
+    plan = H.get_plan(n, 64, XH, XW, H_IMG, W_IMG, dev, H.MATH_BF16)
+    conv_rows, conv_time, conv_flop = [], 0.0, 0.0
+    for k, (cin, cout, dil, ch, cw, oh, ow) in enumerate(plan.stages):
+        a_in = torch.randn(n, ch, cw, cin, device=dev).to(torch.bfloat16)
+        wp = (torch.randn(9, cout, cin, device=dev) * (2.0 / (9 * cin)) ** 0.5).to(torch.bfloat16)
+        y = torch.empty(n, ch, cw, cout, device=dev, dtype=torch.bfloat16)
+        t = time_launch(lambda: fn(a_in.data_ptr(), wp.data_ptr(), y.data_ptr(), n, ch, cw, cin, cout, dil, None, None, None, st), 5)
+        fl = 2.0 * n * ch * cw * cout * 9 * cin
+        conv_rows.append({"stage": k, "cin": cin, "cout": cout, "hw": [ch, cw], "us": t * 1e3, "tflops": fl / t / 1e9})
+        conv_time += t; conv_flop += fl
+        del a_in, wp, y
+    top = max(conv_rows, key=lambda r: r["us"])
+    roofline = {"kernel": f"conv3x3_tc_kernel<{top['cout']}> stage {top['stage']} ({top['cin']}->{top['cout']} @{top['hw'][0]}x{top['hw'][1]})",
+                "bound": "tensor", "achieved": top["tflops"], "peak": tf_peak, "unit": "TFLOP/s", "frac": top["tflops"] / tf_peak,
+                "traffic": None, "peak_source": peak_src, "peak_sustained": tf_sustained,
+                "all_conv_fwd_tflops": conv_flop / conv_time / 1e9, "per_stage": conv_rows}
+
+    # chain-level numbers through the public API
+    def t_api(fn_, iters=5):
+        for _ in range(2):
+            fn_()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(iters):
+            fn_()
+        b.record(); torch.cuda.synchronize()
+        return a.elapsed_time(b) / iters
+
+    xr = xp.detach().requires_grad_(True)
+    t_chain_f = t_api(lambda: H.hrfp_chain(xr, convs, bns, H_IMG, W_IMG, math_mode=H.MATH_BF16))
+
+    def chain_fb():
+        xr.grad = None
+        o, d = H.hrfp_chain(xr, convs, bns, H_IMG, W_IMG, math_mode=H.MATH_BF16)
+        torch.autograd.backward([o, d], [g_x, g_dec])
+    t_chain_fb = t_api(chain_fb)
+    hrfp = {"fwd_ms": t_chain_f, "fwd_bwd_ms": t_chain_fb,
+            "fwd_tflops_needed_only": HRFP_FLOP_FWD_PER_SAMPLE * n / t_chain_f / 1e9,
+            "fwd_bwd_tflops_needed_only": 2 * HRFP_FLOP_FWD_PER_SAMPLE * n / t_chain_fb / 1e9}
+
+    base, _ = cpu_reference_run(1, 1) if world == 1 else (None, None)
+
+    # kernels launched per step (ours; memsets excluded): NP+ 2 fwd + 2 bwd; HRFP fwd 16 weight packs + 1 NCHW->NHWC +
+    # 8 conv + 8 BN finalize + 7 BN/ReLU/resample + 2 NHWC->NCHW epilogues; HRFP bwd 2 NCHW->NHWC + 8 x (2 BN-bwd + conv) + 1
+    launches_per_step = 4 + (16 + 1 + 8 + 8 + 7 + 2) + (2 + 24 + 1)
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16 (HRFP tensor-core operands, fp32 accumulate) / f32 (NP+)", "data": "synthetic", "config": CONFIG,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps},
+            "gpu_launches": launches_per_step * args.steps,
+            "roofline": roofline, "roofline_npplus": roof_np, "hrfp_chain": hrfp,
+            "clocks": sampler.summary() if sampler else None}
+    if base is not None:
+        line["cpu_baseline"] = base
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)

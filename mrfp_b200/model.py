@@ -1,0 +1,233 @@
+"""Drop-in `MRFPPlus` — the reference's torch.nn.Module surface for the MRFP hot path.
+
+Mirrors /root/reference/deepv3.py:152-367 (`MRFPPlus`): same constructor arguments, same child-module
+names and state_dict keys (the published MRFP+ checkpoint, README.md:18, loads with `strict=True`),
+same `forward(x, gts=None, training=True)`, same `Normalization_Perturbation_Plus(feat)`, same three
+`random.random()` gates and the same RNG consumption order of the HRFP re-randomisation
+(deepv3.py:290-306 -> network/mynn.py:57-74).  The three MRFP insertion points call the sm_100a
+kernels of libmrfp_b200.so (NP+: npplus.py; HRFP / HRFP+: hrfp.py); the surrounding DeepLabV3+ /
+ResNet-50 host (stem, layer1-4, ASPP, decoder, loss) is plain PyTorch and is NOT accelerated here
+(out of scope).
+
+Differences from the reference, all observable only through the BN buffers of the 8 OC* BatchNorms:
+the reference evaluates the HRFP chain on every forward, even when its result is discarded (eval mode,
+or p >= 0.5 and p3 >= 0.5).  This module skips that dead compute; `strict_buffers=True` restores the
+reference's buffer updates (running_mean / running_var / num_batches_tracked) in training mode.
+"""
+import math
+import random
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import hrfp as _hrfp
+from . import npplus as _npplus
+
+HRFP_CONVS = ("OClayer1", "OClayer2", "OClayer3", "OClayer4",
+              "OCdeclayer1", "OCdeclayer2", "OCdeclayer3", "OCdeclayer4")
+HRFP_BNS = ("OC1_bn", "OC2_bn", "OC3_bn", "OC4_bn", "OC1_decbn", "OC2_decbn", "OC3_decbn", "OC4_decbn")
+
+
+def upsample_bilinear(x, size):
+    """network/mynn.py:114-119."""
+    return F.interpolate(x, size=size, mode="bilinear", align_corners=True)
+
+
+def init_hrfp_module(module: nn.Module):
+    """network/mynn.py:57-74 for one conv or one BN (same torch RNG calls in the same order)."""
+    if isinstance(module, nn.Conv2d):
+        nn.init.kaiming_normal_(module.weight, nonlinearity="relu")
+        if module.bias is not None:
+            module.bias.data.zero_()
+    elif isinstance(module, nn.BatchNorm2d):
+        nn.init.normal_(module.weight, mean=0.0, std=0.5)
+        module.bias.data.zero_()
+
+
+def init_head(*models):
+    """network/mynn.py:37-55 (`initialize_weights`)."""
+    for model in models:
+        for m in model.modules():
+            if isinstance(m, (nn.Conv2d, nn.Linear)):
+                nn.init.kaiming_normal_(m.weight, nonlinearity="relu")
+                if m.bias is not None:
+                    m.bias.data.zero_()
+            elif isinstance(m, nn.BatchNorm2d):
+                m.weight.data.fill_(1)
+                m.bias.data.zero_()
+
+
+class MRFPMixin:
+    """The MRFP layers and insertion points, independent of the trunk (used by MRFPPlus below and usable
+    on other trunks: SURVEY.md §8f-2)."""
+
+    def _build_hrfp(self, in_ch=64, widths=(64, 64, 128, 256)):
+        chans = [in_ch, widths[0], widths[1], widths[2], widths[3], widths[2], widths[1], widths[0], in_ch]
+        dils = [1, 1, 2, 2, 1, 1, 2, 2]
+        for k, (cname, bname) in enumerate(zip(HRFP_CONVS, HRFP_BNS)):      # deepv3.py:221-237
+            conv = nn.Conv2d(chans[k], chans[k + 1], kernel_size=3, stride=1, padding=dils[k], dilation=dils[k])
+            setattr(self, cname, conv.requires_grad_(False))
+            setattr(self, bname, nn.BatchNorm2d(chans[k + 1]).requires_grad_(False))
+        self.reinit_hrfp()                                                  # deepv3.py:239-254
+
+    def hrfp_modules(self):
+        return [getattr(self, n) for n in HRFP_CONVS], [getattr(self, n) for n in HRFP_BNS]
+
+    def reinit_hrfp(self):
+        """deepv3.py:290-306: conv1, bn1, conv2, bn2, ... in module order."""
+        for cname, bname in zip(HRFP_CONVS, HRFP_BNS):
+            init_hrfp_module(getattr(self, cname))
+            init_hrfp_module(getattr(self, bname))
+
+    def Normalization_Perturbation_Plus(self, feat):
+        """deepv3.py:268-277 on the fused NP+ kernels."""
+        return _npplus.normalization_perturbation_plus(feat)
+
+    def mrfp_stem(self, xp, h, w, training, p, p2, p3):
+        """Insertion point 1 (deepv3.py:316-330).  Returns (x, OCout_dec or None)."""
+        x = xp
+        if training and p2 < 0.5:
+            x = self.Normalization_Perturbation_Plus(xp)
+        want_out = training and p < 0.5
+        want_dec = training and p3 < 0.5
+        dec = None
+        if want_out or want_dec:
+            convs, bns = self.hrfp_modules()
+            out, dec = _hrfp.hrfp_chain(xp, convs, bns, h, w, x_add=x if want_out else None,
+                                        want_out=want_out, want_dec=want_dec, math_mode=self.math_mode)
+            if want_out:
+                x = out                                                     # OCout + x  (deepv3.py:330)
+        elif training and self.strict_buffers:
+            convs, bns = self.hrfp_modules()
+            with torch.no_grad():
+                _hrfp.hrfp_chain(xp, convs, bns, h, w, want_out=True, want_dec=False, math_mode=self.math_mode)
+        return x, dec
+
+
+class Bottleneck(nn.Module):
+    """ResNet bottleneck with the optional trailing InstanceNorm of the reference's iw == 4 variant
+    (network/Resnet.py:148-227); plain tensors instead of the reference's [x, w_arr] tuples."""
+    expansion = 4
+
+    def __init__(self, inplanes, planes, stride=1, downsample=None, instance_norm=False):
+        super().__init__()
+        self.conv1 = nn.Conv2d(inplanes, planes, 1, bias=False)
+        self.bn1 = nn.BatchNorm2d(planes)
+        self.conv2 = nn.Conv2d(planes, planes, 3, stride=stride, padding=1, bias=False)
+        self.bn2 = nn.BatchNorm2d(planes)
+        self.conv3 = nn.Conv2d(planes, planes * 4, 1, bias=False)
+        self.bn3 = nn.BatchNorm2d(planes * 4)
+        self.downsample = downsample
+        if instance_norm:
+            self.instance_norm_layer = nn.InstanceNorm2d(planes * 4, affine=True)
+        self.has_in = instance_norm
+        self.relu = nn.ReLU(inplace=True)
+
+    def forward(self, x):
+        out = self.relu(self.bn1(self.conv1(x)))
+        out = self.relu(self.bn2(self.conv2(out)))
+        out = self.bn3(self.conv3(out))
+        out = out + (x if self.downsample is None else self.downsample(x))
+        if self.has_in:
+            out = self.instance_norm_layer(out)
+        return self.relu(out)
+
+
+def _make_layer(inplanes, planes, blocks, stride, in_last):
+    downsample = None
+    if stride != 1 or inplanes != planes * 4:
+        downsample = nn.Sequential(nn.Conv2d(inplanes, planes * 4, 1, stride=stride, bias=False),
+                                   nn.BatchNorm2d(planes * 4))
+    layers = [Bottleneck(inplanes, planes, stride, downsample)]
+    for i in range(1, blocks):
+        layers.append(Bottleneck(planes * 4, planes, instance_norm=in_last and i == blocks - 1))
+    return nn.Sequential(*layers)
+
+
+class ASPP(nn.Module):
+    """deepv3.py:64-126 (output stride 16: rates 6, 12, 18)."""
+
+    def __init__(self, in_dim, reduction_dim=256, rates=(6, 12, 18)):
+        super().__init__()
+        feats = [nn.Sequential(nn.Conv2d(in_dim, reduction_dim, 1, bias=False), nn.BatchNorm2d(reduction_dim),
+                               nn.ReLU(inplace=True))]
+        for r in rates:
+            feats.append(nn.Sequential(nn.Conv2d(in_dim, reduction_dim, 3, dilation=r, padding=r, bias=False),
+                                       nn.BatchNorm2d(reduction_dim), nn.ReLU(inplace=True)))
+        self.features = nn.ModuleList(feats)
+        self.img_pooling = nn.AdaptiveAvgPool2d(1)
+        self.img_conv = nn.Sequential(nn.Conv2d(in_dim, 256, 1, bias=False), nn.BatchNorm2d(256), nn.ReLU(inplace=True))
+
+    def forward(self, x):
+        img = upsample_bilinear(self.img_conv(self.img_pooling(x)), x.shape[2:])
+        return torch.cat([img] + [f(x) for f in self.features], 1)
+
+
+class MRFPPlus(nn.Module, MRFPMixin):
+    """DeepLabV3+ / ResNet-50 (IN at the stem and at the end of layer1, layer2: wt_layer=[0,0,4,4,4,0,0]) with
+    MRFP+ applied while training."""
+
+    def __init__(self, num_classes, trunk="resnet-50", criterion=None, criterion_aux=None, variant="D16",
+                 wt_layer=(0, 0, 4, 4, 4, 0, 0), use_wtloss=False, math_mode=_hrfp.MATH_BF16, strict_buffers=False):
+        super().__init__()
+        if trunk != "resnet-50":
+            raise ValueError("Not a valid network arch")                    # deepv3.py:177-178
+        if tuple(wt_layer) != (0, 0, 4, 4, 4, 0, 0):
+            raise ValueError("only the reference's wt_layer=[0,0,4,4,4,0,0] host is provided")
+        self.criterion, self.criterion_aux = criterion, criterion_aux
+        self.variant, self.wt_layer, self.use_wtloss, self.trunk = variant, list(wt_layer), use_wtloss, trunk
+        self.math_mode, self.strict_buffers = math_mode, strict_buffers
+
+        self.layer0 = nn.Sequential(nn.Conv2d(3, 64, 7, stride=2, padding=3, bias=False),
+                                    nn.InstanceNorm2d(64, affine=True), nn.ReLU(inplace=True),
+                                    nn.MaxPool2d(3, stride=2, padding=1))
+        self.layer1 = _make_layer(64, 64, 3, 1, True)
+        self.layer2 = _make_layer(256, 128, 4, 2, True)
+        self.layer3 = _make_layer(512, 256, 6, 2, False)
+        self.layer4 = _make_layer(1024, 512, 3, 2, False)
+        for m in self.modules():                                            # network/Resnet.py:563-570
+            if isinstance(m, nn.Conv2d):
+                nn.init.kaiming_normal_(m.weight, mode="fan_out", nonlinearity="relu")
+        if variant == "D16":                                                # deepv3.py:184-189
+            for n, m in self.layer4.named_modules():
+                if "conv2" in n:
+                    m.dilation, m.padding, m.stride = (2, 2), (2, 2), (1, 1)
+                elif "downsample.0" in n:
+                    m.stride = (1, 1)
+        self.output_stride = 16
+        self.aspp = ASPP(2048, 256)
+        self.bot_fine = nn.Sequential(nn.Conv2d(256, 48, 1, bias=False), nn.BatchNorm2d(48), nn.ReLU(inplace=True))
+        self.bot_aspp = nn.Sequential(nn.Conv2d(1280, 256, 1, bias=False), nn.BatchNorm2d(256), nn.ReLU(inplace=True))
+        self.final1 = nn.Sequential(nn.Conv2d(304, 256, 3, padding=1, bias=False), nn.BatchNorm2d(256), nn.ReLU(inplace=True),
+                                    nn.Conv2d(256, 256, 3, padding=1, bias=False), nn.BatchNorm2d(256), nn.ReLU(inplace=True))
+        self.final2 = nn.Sequential(nn.Conv2d(256, num_classes, 1, bias=True))
+        self._build_hrfp(64)
+        init_head(self.aspp, self.bot_aspp, self.bot_fine, self.final1, self.final2)
+        self.eps = 1e-5
+        self.whitening = False
+        self.three_input_layer = False
+
+    def forward(self, x, gts=None, training=True):
+        p, p2, p3 = random.random(), random.random(), random.random()       # deepv3.py:281-283
+        h, w = x.shape[2:]
+        if training and p < 0.5:
+            self.reinit_hrfp()                                              # deepv3.py:290-306
+        xp = self.layer0(x)                                                 # deepv3.py:309-316
+        x, ocout_dec = self.mrfp_stem(xp, h, w, training, p, p2, p3)        # deepv3.py:317-330
+        x = self.layer1(x)                                                  # deepv3.py:332
+        if training and p2 < 0.5:
+            x = self.Normalization_Perturbation_Plus(x)                     # deepv3.py:334-335
+        low_level = x
+        x = self.layer4(self.layer3(self.layer2(x)))
+        dec0_up = self.bot_aspp(self.aspp(x))
+        dec0_fine = self.bot_fine(low_level)
+        dec0 = torch.cat([dec0_fine, upsample_bilinear(dec0_up, low_level.shape[2:])], 1)
+        dec1 = self.final1(dec0)
+        if training and p3 < 0.5:                                           # deepv3.py:355-357
+            dec1 = upsample_bilinear(dec1, (int(h / 2), int(w / 2)))
+            dec1 = _hrfp.hrfp_plus_add(dec1, ocout_dec)
+        main_out = upsample_bilinear(self.final2(dec1), (h, w))
+        if training:
+            return self.criterion(main_out, gts)
+        return main_out

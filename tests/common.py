@@ -40,3 +40,29 @@ def make_draws(seed: int, n: int, c: int):
     alpha = (1.0 + 0.75 * rng.standard_normal((n, c))).astype(np.float32)
     eps = (0.75 * rng.standard_normal((n, c))).astype(np.float32)
     return alpha, eps
+
+
+def fill_state_dict(model, seed: int):
+    """Deterministic, name-keyed parameter fill (numpy PCG64) so the reference model in the build container and
+    this repo's model on any box carry identical weights without shipping a 160 MB state_dict."""
+    import zlib
+    import torch
+    sd = model.state_dict()
+    with torch.no_grad():
+        for key, t in sd.items():
+            if not t.dtype.is_floating_point:
+                continue
+            rng = np.random.default_rng([seed, zlib.crc32(key.encode())])
+            shape = tuple(t.shape)
+            if key.endswith("running_var"):
+                v = rng.uniform(0.5, 1.5, shape)
+            elif key.endswith("running_mean"):
+                v = 0.1 * rng.standard_normal(shape)
+            elif t.dim() == 1 and key.endswith("weight"):
+                v = 1.0 + 0.1 * rng.standard_normal(shape)
+            elif t.dim() == 1:
+                v = 0.1 * rng.standard_normal(shape)
+            else:
+                fan_in = int(np.prod(shape[1:]))
+                v = rng.standard_normal(shape) * math.sqrt(2.0 / fan_in)
+            t.copy_(torch.from_numpy(v.astype(np.float32)))

@@ -21,7 +21,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 sys.path.insert(0, ROOT)
 from oracle.ref_shim import load_reference           # noqa: E402
-from tests.common import make_hrfp_params, make_feat, make_draws   # noqa: E402
+from tests.common import make_hrfp_params, make_feat, make_draws, fill_state_dict   # noqa: E402
 
 deepv3 = load_reference()
 torch.set_num_threads(8)
@@ -224,9 +224,59 @@ def gen_rng_order(m):
     print("known_answers.json: draws", len(log), "frozen", frozen, "trainable", train)
 
 
+def gen_full_model(m):
+    """One training forward+backward of the reference MRFPPlus on CPU, all three branches on, every random draw
+    injected: loss and gradient fingerprints for the drop-in module test (tests/test_model.py)."""
+    import deepv3 as ref
+    fill_state_dict(m, 77)
+    m.train()
+    n, hh, ww = 2, 64, 64
+    rng = np.random.default_rng(78)
+    x = torch.from_numpy(rng.uniform(0, 255, (n, 3, hh, ww)).astype(np.float32))
+    gts = torch.from_numpy(rng.integers(0, 19, (n, hh, ww)).astype(np.int64))
+    gts[torch.from_numpy(rng.uniform(size=(n, hh, ww)) < 0.05)] = 255
+    ws, gs = make_hrfp_params(79)
+    a1, e1 = make_draws(80, n, 64)
+    a2, e2 = make_draws(81, n, 256)
+    calls = {"i": 0}
+    orig_init = ref.initialize_weights_kaimingnormal_forOC
+
+    def fake_init(mod):
+        k = calls["i"] // 2
+        with torch.no_grad():
+            if isinstance(mod, torch.nn.Conv2d):
+                mod.weight.copy_(torch.from_numpy(ws[k])); mod.bias.zero_()
+            else:
+                mod.weight.copy_(torch.from_numpy(gs[k])); mod.bias.zero_()
+        calls["i"] += 1
+
+    ref.initialize_weights_kaimingnormal_forOC = fake_init
+    try:
+        random.seed(4)                      # p, p2, p3 all < 0.5
+        draws = [torch.from_numpy(t).reshape(n, -1, 1, 1) for t in (a1, e1, a2, e2)]
+        with InjectNormal(draws):
+            loss = m(x, gts, training=True)
+        loss.backward()
+    finally:
+        ref.initialize_weights_kaimingnormal_forOC = orig_init
+    assert calls["i"] == 16
+    out = {"loss": np.array(float(loss))}
+    for key in ("layer0.0.weight", "layer0.1.weight", "layer1.0.conv1.weight", "layer1.2.instance_norm_layer.weight",
+                "layer2.0.conv2.weight", "final1.0.weight", "final2.0.weight", "final2.0.bias"):
+        gparam = dict(m.named_parameters())[key].grad.double()
+        out["g_" + key] = np.array([float(gparam.sum()), float(gparam.abs().sum()), float((gparam * gparam).sum())])
+        out["gs_" + key] = gparam.flatten()[:: max(1, gparam.numel() // 64)][:64].numpy()
+    for k in range(8):
+        bn = getattr(m, BNS[k])
+        out[f"rm{k}"] = bn.running_mean.numpy().copy()
+    np.savez_compressed(os.path.join(HERE, "full_model.npz"), **out)
+    print("full_model.npz loss", float(loss))
+
+
 if __name__ == "__main__":
     gen_npplus()
     gen_lut()
     m = ref_hrfp_modules()
     gen_hrfp(m)
     gen_rng_order(m)
+    gen_full_model(m)

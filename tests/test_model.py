@@ -1,0 +1,165 @@
+"""Drop-in module: state_dict compatibility, eval-path equality with the reference (container only) and the
+full training forward/backward against a fixture produced by the reference itself."""
+import json
+import os
+import random
+
+import numpy as np
+import pytest
+import torch
+
+from tests.common import GOLDEN, make_hrfp_params, make_draws, fill_state_dict
+
+
+def _criterion():
+    return torch.nn.CrossEntropyLoss(ignore_index=255)
+
+
+def test_state_dict_matches_reference_keys_and_shapes():
+    from mrfp_b200.model import MRFPPlus
+    with open(os.path.join(GOLDEN, "known_answers.json")) as f:
+        known = json.load(f)
+    m = MRFPPlus(19, criterion=_criterion())
+    sd = m.state_dict()
+    assert list(sd.keys()) == known["all_state_dict_keys"]
+    assert {k: list(v.shape) for k, v in sd.items()} == known["state_dict_shapes"]
+    frozen = sum(p.numel() for p in m.parameters() if not p.requires_grad)
+    train = sum(p.numel() for p in m.parameters() if p.requires_grad)
+    assert (frozen, train) == (known["frozen_params"], known["trainable_params"])
+
+
+def test_reinit_rng_order_matches_reference():
+    from mrfp_b200.model import MRFPPlus
+    with open(os.path.join(GOLDEN, "known_answers.json")) as f:
+        known = json.load(f)
+    m = MRFPPlus(19, criterion=_criterion())
+    log = []
+    ok, on = torch.nn.init.kaiming_normal_, torch.nn.init.normal_
+    torch.nn.init.kaiming_normal_ = lambda t, *a, **k: (log.append(["kaiming_normal_", list(t.shape)]), ok(t, *a, **k))[1]
+    torch.nn.init.normal_ = lambda t, *a, **k: (log.append(["normal_", list(t.shape), k.get("std")]), on(t, *a, **k))[1]
+    try:
+        m.reinit_hrfp()
+    finally:
+        torch.nn.init.kaiming_normal_, torch.nn.init.normal_ = ok, on
+    assert log == known["draw_log"][:16]
+
+
+def test_eval_forward_needs_no_kernels_and_is_deterministic():
+    from mrfp_b200.model import MRFPPlus
+    m = MRFPPlus(19, criterion=_criterion()).eval()
+    x = torch.rand(1, 3, 64, 64) * 255
+    with torch.no_grad():
+        a = m(x, training=False)
+        b = m(x, training=False)
+    assert a.shape == (1, 19, 64, 64) and torch.equal(a, b)
+
+
+@pytest.mark.refonly
+def test_eval_forward_equals_reference_on_cpu():
+    from oracle.ref_shim import load_reference
+    from mrfp_b200.model import MRFPPlus
+    ref = load_reference().MRFPPlus(19, criterion=_criterion())
+    mine = MRFPPlus(19, criterion=_criterion())
+    fill_state_dict(ref, 5)
+    mine.load_state_dict(ref.state_dict(), strict=True)
+    ref.eval(); mine.eval()
+    x = torch.rand(2, 3, 64, 64) * 255
+    with torch.no_grad():
+        a = ref(x, training=False)
+        b = mine(x, training=False)
+    assert torch.allclose(a, b, rtol=1e-5, atol=1e-5 * a.abs().max().item())
+
+
+def _train_step(math_mode):
+    from mrfp_b200 import model as M, npplus
+    torch.backends.cudnn.allow_tf32 = False           # the fixture is an fp32 (CPU) run of the reference
+    torch.backends.cuda.matmul.allow_tf32 = False
+    g = np.load(os.path.join(GOLDEN, "full_model.npz"))
+    m = M.MRFPPlus(19, criterion=_criterion(), math_mode=math_mode)
+    fill_state_dict(m, 77)
+    m = m.cuda().train()
+    n, hh, ww = 2, 64, 64
+    rng = np.random.default_rng(78)
+    x = torch.from_numpy(rng.uniform(0, 255, (n, 3, hh, ww)).astype(np.float32)).cuda()
+    gts = torch.from_numpy(rng.integers(0, 19, (n, hh, ww)).astype(np.int64))
+    gts[torch.from_numpy(rng.uniform(size=(n, hh, ww)) < 0.05)] = 255
+    gts = gts.cuda()
+    ws, gs = make_hrfp_params(79)
+    draws = [make_draws(80, n, 64), make_draws(81, n, 256)]
+
+    def fake_reinit():
+        convs, bns = m.hrfp_modules()
+        with torch.no_grad():
+            for k in range(8):
+                convs[k].weight.copy_(torch.from_numpy(ws[k])); convs[k].bias.zero_()
+                bns[k].weight.copy_(torch.from_numpy(gs[k])); bns[k].bias.zero_()
+
+    def fake_draws(feat):
+        a, e = draws.pop(0)
+        return torch.from_numpy(a).to(feat.device), torch.from_numpy(e).to(feat.device)
+
+    m.reinit_hrfp = fake_reinit
+    orig = npplus.draw_np_plus_factors
+    npplus.draw_np_plus_factors = fake_draws
+    try:
+        random.seed(4)
+        loss = m(x, gts, training=True)
+        loss.backward()
+    finally:
+        npplus.draw_np_plus_factors = orig
+    return g, m, float(loss)
+
+
+@pytest.mark.gpu
+def test_training_step_matches_reference_fp32_mode():
+    g, m, loss = _train_step(0)
+    assert abs(loss - float(g["loss"])) <= 2e-4 * abs(float(g["loss"]))
+    params = dict(m.named_parameters())
+    # Gradients of the head (downstream of every MRFP insertion point in the backward pass) are well conditioned
+    # and checked tightly.  Gradients that travelled back through the 50-layer random-weight trunk at this tiny
+    # size (4x4 maps at layer4, BN over 32 values) are chaotic: the reference's own eager code run on the GPU
+    # instead of the CPU moves them by 3-5 % of max (tools/debug_model.py), so they only get a coarse check.
+    for key in [k[3:] for k in g.files if k.startswith("gs_")]:
+        grad = params[key].grad.double().cpu()
+        samp = grad.flatten()[:: max(1, grad.numel() // 64)][:64].numpy()
+        ref = g["gs_" + key]
+        tol = 2e-3 if key.startswith("final") else 1.5e-1
+        assert np.abs(samp - ref).max() <= tol * np.abs(ref).max(), key
+        assert abs(float(grad.abs().sum()) - g["g_" + key][1]) <= tol * g["g_" + key][1], key
+    for k in range(8):
+        bn = m.hrfp_modules()[1][k]
+        assert np.allclose(bn.running_mean.cpu().numpy(), g[f"rm{k}"], rtol=1e-3, atol=1e-4)
+
+
+@pytest.mark.gpu
+def test_training_step_bf16_mode_close_to_reference():
+    g, m, loss = _train_step(2)
+    # the bf16 HRFP branch perturbs the features by ~2 % (tests/test_hrfp_gpu.py); the loss moves accordingly
+    assert abs(loss - float(g["loss"])) <= 5e-2 * abs(float(g["loss"]))
+    grad = dict(m.named_parameters())["final2.0.weight"].grad
+    assert torch.isfinite(grad).all()
+    ref_l1 = g["g_final2.0.weight"][1]
+    assert abs(float(grad.double().abs().sum()) - ref_l1) <= 0.2 * ref_l1
+
+
+@pytest.mark.gpu
+def test_gates_off_is_plain_deeplab_and_skips_hrfp():
+    from mrfp_b200.model import MRFPPlus
+    m = MRFPPlus(19, criterion=_criterion()).cuda().train()
+    x = torch.rand(2, 3, 64, 64, device="cuda") * 255
+    gts = torch.randint(0, 19, (2, 64, 64), device="cuda")
+    random.seed(1)     # 0.134, 0.847, 0.763: p < .5 only  -> HRFP add without NP+ / HRFP+
+    loss = m(x, gts, training=True)
+    loss.backward()
+    assert torch.isfinite(loss)
+    nbt = int(m.OC1_bn.num_batches_tracked)
+    state = random.getstate()
+    random.seed(11)    # find a seed with all three gates >= 0.5
+    for s in range(100):
+        random.seed(s)
+        if min(random.random(), random.random(), random.random()) >= 0.5:
+            random.seed(s)
+            break
+    loss = m(x, gts, training=True)
+    assert int(m.OC1_bn.num_batches_tracked) == nbt       # dead chain skipped (strict_buffers=False)
+    random.setstate(state)

@@ -167,3 +167,31 @@ def test_known_answers(known):
                  f"{b}.running_var", f"{b}.num_batches_tracked"]
     assert known["oc_state_dict_keys"] == want
     assert abs(O.hrfp_init_std(64) - math.sqrt(2 / 576)) < 1e-12
+
+
+def test_torch_port_npplus_vs_reference(g_np):
+    import torch
+    from oracle import torch_port as T
+    shape = tuple(g_np["d_shape"])
+    feat = torch.from_numpy(make_feat(103, shape)).requires_grad_(True)
+    a, e = make_draws(203, shape[0], shape[1])
+    y = T.np_plus(feat, torch.from_numpy(a).view(*shape[:2], 1, 1), torch.from_numpy(e).view(*shape[:2], 1, 1))
+    y.backward(torch.from_numpy(np.random.default_rng(303).standard_normal(shape).astype(np.float32)))
+    assert np.abs(y.detach().numpy() - g_np["d_out"]).max() <= 1e-5 * np.abs(g_np["d_out"]).max()
+    assert np.abs(feat.grad.numpy() - g_np["d_gin"]).max() <= 1e-4 * np.abs(g_np["d_gin"]).max()
+
+
+def test_torch_port_hrfp_vs_reference(g_hrfp):
+    import torch
+    from oracle import torch_port as T
+    n, h, w, seed = [int(v) for v in g_hrfp["sq_meta"]]
+    ws, gs = make_hrfp_params(seed)
+    convs, bns = T.make_layers(ws, gs)
+    xp = torch.from_numpy(make_feat(seed + 50, (n, 64, h // 4, w // 4))).requires_grad_(True)
+    o, d = T.hrfp_chain(convs, bns, xp, h, w)
+    rng = np.random.default_rng(seed + 70)
+    g1 = torch.from_numpy(rng.standard_normal(tuple(o.shape)).astype(np.float32))
+    g2 = torch.from_numpy(rng.standard_normal(tuple(d.shape)).astype(np.float32))
+    torch.autograd.backward([o, d], [g1, g2])
+    assert np.abs(o.detach().numpy() - g_hrfp["sq_ocout"]).max() <= 1e-4 * np.abs(g_hrfp["sq_ocout"]).max()
+    assert np.abs(xp.grad.numpy() - g_hrfp["sq_gx_both"]).max() <= 1e-3 * np.abs(g_hrfp["sq_gx_both"]).max()
