@@ -61,58 +61,107 @@ template <> struct Elem<__nv_bfloat16> {
 // ------------------------------------------------------------------------------------------------------
 // layout conversion at the module boundary
 // ------------------------------------------------------------------------------------------------------
-// src fp32 [N][C][HW] -> dst T [N][HW][C]; accumulate adds into dst (gradient of OCout_dec joining the chain)
+// src fp32 [N][C][HW] -> dst T [N][HW][C]; accumulate adds into dst (gradient of OCout_dec joining the chain).
+// 64 channels x 64 pixels per block through shared memory: 256-byte row reads, 16-byte channel-vector writes.
 template <typename T>
-__global__ void nchw_to_nhwc_kernel(const float* __restrict__ src, T* __restrict__ dst, int C, int HW, int accumulate) {
-  __shared__ float tile[32][33];
-  const int n = blockIdx.z, c0 = blockIdx.y * 32, p0 = blockIdx.x * 32;
+__global__ void __launch_bounds__(256)
+nchw_to_nhwc_kernel(const float* __restrict__ src, T* __restrict__ dst, int C, int HW, int accumulate) {
+  __shared__ float tile[64][65];   // [channel][pixel]
+  const int n = blockIdx.z, c0 = blockIdx.y * 64, p0 = blockIdx.x * 64, t = threadIdx.x;
   const float* s = src + (size_t)n * C * HW;
   T* d = dst + (size_t)n * C * HW;
-  for (int i = threadIdx.y; i < 32; i += 8) {
-    const int c = c0 + i, p = p0 + threadIdx.x;
-    tile[i][threadIdx.x] = (c < C && p < HW) ? s[(size_t)c * HW + p] : 0.f;
+  const bool vec = (HW & 1) == 0;
+  {
+    const int px = (t & 31) * 2, crow = t >> 5;
+#pragma unroll
+    for (int pass = 0; pass < 8; ++pass) {
+      const int c = crow + pass * 8, p = p0 + px;
+      float v0 = 0.f, v1 = 0.f;
+      if (c0 + c < C) {
+        const float* q = s + (size_t)(c0 + c) * HW + p;
+        if (vec && p + 1 < HW) { const float2 v = *reinterpret_cast<const float2*>(q); v0 = v.x; v1 = v.y; }
+        else { if (p < HW) v0 = q[0]; if (p + 1 < HW) v1 = q[1]; }
+      }
+      tile[c][px] = v0; tile[c][px + 1] = v1;
+    }
   }
   __syncthreads();
-  for (int i = threadIdx.y; i < 32; i += 8) {
-    const int p = p0 + i, c = c0 + threadIdx.x;
-    if (p < HW && c < C) {
-      float v = tile[threadIdx.x][i];
-      T* q = d + (size_t)p * C + c;
-      if (accumulate) v += Elem<T>::to_float(*q);
-      *q = Elem<T>::from_float(v);
+  {
+    const int cg = t & 7, pl = t >> 3;
+#pragma unroll
+    for (int pass = 0; pass < 2; ++pass) {
+      const int px = pl + pass * 32, p = p0 + px, c = c0 + cg * 8;
+      if (p < HW && c < C) {
+        float v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = tile[cg * 8 + j][px];
+        T* q = d + (size_t)p * C + c;
+        if (accumulate) {
+          float o[8];
+          Elem<T>::load8(q, o);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) v[j] += o[j];
+        }
+        Elem<T>::store8(q, v);
+      }
     }
   }
 }
 
 // out fp32 [N][C][OH][OW] = f(Y[n][ih[oh]][iw[ow]][c]) (+ add), f = identity or ReLU(scale*y + shift)
 template <typename T>
-__global__ void nhwc_to_nchw_kernel(const T* __restrict__ y, float* __restrict__ out, const float* __restrict__ add,
-                                    const int* __restrict__ idx_h, const int* __restrict__ idx_w,
-                                    const float* __restrict__ scale, const float* __restrict__ shift,
-                                    int C, int IH, int IW, int OH, int OW) {
-  __shared__ float tile[32][33];
-  const int n = blockIdx.x / OH, oh = blockIdx.x % OH;
-  const int c0 = blockIdx.y * 32, w0 = blockIdx.z * 32;
+__global__ void __launch_bounds__(256)
+nhwc_to_nchw_kernel(const T* __restrict__ y, float* __restrict__ out, const float* __restrict__ add,
+                    const int* __restrict__ idx_h, const int* __restrict__ idx_w, const float* __restrict__ scale,
+                    const float* __restrict__ shift, int C, int IH, int IW, int OH, int OW) {
+  __shared__ float tile[64][65];   // [channel][pixel]
+  const int n = blockIdx.x / OH, oh = blockIdx.x % OH, t = threadIdx.x;
+  const int c0 = blockIdx.y * 64, w0 = blockIdx.z * 64;
   const int sh = idx_h ? idx_h[oh] : oh;
   const T* row = y + ((size_t)n * IH + sh) * IW * C;
-  for (int i = threadIdx.y; i < 32; i += 8) {
-    const int ow = w0 + i, c = c0 + threadIdx.x;
-    float v = 0.f;
-    if (ow < OW && c < C) {
-      const int sw = idx_w ? idx_w[ow] : ow;
-      v = Elem<T>::to_float(row[(size_t)sw * C + c]);
-      if (scale) v = fmaxf(fmaf(scale[c], v, shift[c]), 0.f);
+  {
+    const int cg = t & 7, pl = t >> 3, c = c0 + cg * 8;
+    float sc[8], sf[8];
+    if (scale && c < C) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { sc[j] = scale[c + j]; sf[j] = shift[c + j]; }
     }
-    tile[i][threadIdx.x] = v;
+#pragma unroll
+    for (int pass = 0; pass < 2; ++pass) {
+      const int px = pl + pass * 32, ow = w0 + px;
+      float v[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = 0.f;
+      if (ow < OW && c < C) {
+        const int sw = idx_w ? idx_w[ow] : ow;
+        Elem<T>::load8(row + (size_t)sw * C + c, v);
+        if (scale) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) v[j] = fmaxf(fmaf(sc[j], v[j], sf[j]), 0.f);
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) tile[cg * 8 + j][px] = v[j];
+    }
   }
   __syncthreads();
-  for (int i = threadIdx.y; i < 32; i += 8) {
-    const int c = c0 + i, ow = w0 + threadIdx.x;
-    if (c < C && ow < OW) {
-      const size_t o = (((size_t)n * C + c) * OH + oh) * OW + ow;
-      float v = tile[threadIdx.x][i];
-      if (add) v += add[o];
-      out[o] = v;
+  {
+    const int px = (t & 31) * 2, crow = t >> 5;
+    const bool vec = (OW & 1) == 0;
+#pragma unroll
+    for (int pass = 0; pass < 8; ++pass) {
+      const int c = crow + pass * 8, ow = w0 + px;
+      if (c0 + c < C && ow < OW) {
+        const size_t o = (((size_t)n * C + c0 + c) * OH + oh) * OW + ow;
+        float v0 = tile[c][px], v1 = tile[c][px + 1];
+        if (vec && ow + 1 < OW) {
+          if (add) { const float2 a2 = *reinterpret_cast<const float2*>(add + o); v0 += a2.x; v1 += a2.y; }
+          *reinterpret_cast<float2*>(out + o) = make_float2(v0, v1);
+        } else {
+          out[o] = add ? v0 + add[o] : v0;
+          if (ow + 1 < OW) out[o + 1] = add ? v1 + add[o + 1] : v1;
+        }
+      }
     }
   }
 }
@@ -255,88 +304,116 @@ __global__ void pack_weights_kernel(const float* __restrict__ W, void* __restric
 }
 
 // ------------------------------------------------------------------------------------------------------
-// backward of [resample -> BN(train) -> ReLU] at one stage, expressed per SOURCE pixel of the conv output:
-//   mask, xhat depend only on Y[src];  SdA = sum of dA over the replicas of src (a contiguous rectangle);
-//   S1 = sum mask*SdA, S2 = sum mask*xhat*SdA  (then M1 = gamma*S1/count, M2 = gamma*S2/count)
-//   dY[src] = invstd * (mask*gamma*SdA - cnt*(M1 + xhat*M2))
+// backward of [resample -> BN(train) -> ReLU] at one stage.  mask and xhat depend only on Y[src]:
+//   reduce (over DESTINATION rows, both streams contiguous):  U1 = sum mask*dA,  U2 = sum mask*dA*y
+//          -> S1 = U1, S2 = sum mask*dA*xhat = invstd*(U2 - mean*U1);  M1 = gamma*S1/count, M2 = gamma*S2/count
+//   apply  (over SOURCE rows; the replicas of a source pixel are a contiguous <=2x2 rectangle of dA):
+//          dY[src] = invstd*(mask*gamma*SdA - cnt*(M1 + xhat*M2)) = P*mask*SdA - cnt*(Q + R*y)
+// Threads keep a fixed 8-channel group; a block walks whole rows so the row LUT entry is block-uniform.
 // ------------------------------------------------------------------------------------------------------
-template <typename T, bool APPLY>
-__global__ void __launch_bounds__(256)
-bn_bwd_kernel(const T* __restrict__ dA, const T* __restrict__ y, T* __restrict__ dY, const int* __restrict__ start_h,
-              const int* __restrict__ cnt_h, const int* __restrict__ start_w, const int* __restrict__ cnt_w,
-              const float* __restrict__ stats, const float* __restrict__ gamma, double* __restrict__ acc,
-              int N, int C, int IH, int IW, int OH, int OW, double count) {
+template <typename T>
+__global__ void __launch_bounds__(256, 4)
+bn_bwd_reduce_kernel(const T* __restrict__ dA, const T* __restrict__ y, const int* __restrict__ idx_h,
+                     const int* __restrict__ idx_w, const float* __restrict__ stats, double* __restrict__ acc,
+                     int N, int C, int IH, int IW, int OH, int OW) {
   __shared__ float s_acc[2 * kMaxC];
-  const int cg = C >> 3, ppb = 256 / cg;
-  const int cgi = threadIdx.x % cg, pl = threadIdx.x / cg, c = cgi << 3;
-  if (!APPLY) {
-    for (int i = threadIdx.x; i < 2 * kMaxC; i += 256) s_acc[i] = 0.f;
-    __syncthreads();
-  }
-  float mean[8], invstd[8], scale[8], shift[8], gm[8], m1[8], m2[8];
+  const int cg = C >> 3, pstep = 256 / cg;
+  const int c = (threadIdx.x % cg) << 3, pl = threadIdx.x / cg;
+  for (int i = threadIdx.x; i < 2 * kMaxC; i += 256) s_acc[i] = 0.f;
+  float scale[8], shift[8], u1[8], u2[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
-    mean[j] = stats[c + j]; invstd[j] = stats[kMaxC + c + j];
     scale[j] = stats[2 * kMaxC + c + j]; shift[j] = stats[3 * kMaxC + c + j];
-    gm[j] = gamma[c + j];
-    if (APPLY) {
-      m1[j] = (float)((double)gm[j] * acc[c + j] / count);
-      m2[j] = (float)((double)gm[j] * acc[kMaxC + c + j] / count);
+    u1[j] = 0.f; u2[j] = 0.f;
+  }
+  __syncthreads();
+  for (int row = blockIdx.x; row < N * OH; row += gridDim.x) {
+    const int n = row / OH, oh = row % OH;
+    const T* drow = dA + (size_t)row * OW * C + c;
+    const T* yrow = y + ((size_t)n * IH + idx_h[oh]) * IW * C + c;
+#pragma unroll 2
+    for (int ow = pl; ow < OW; ow += pstep) {
+      float g[8], yv[8];
+      Elem<T>::load8(drow + (size_t)ow * C, g);
+      Elem<T>::load8(yrow + (size_t)idx_w[ow] * C, yv);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float t = fmaf(scale[j], yv[j], shift[j]) > 0.f ? g[j] : 0.f;
+        u1[j] += t;
+        u2[j] = fmaf(t, yv[j], u2[j]);
+      }
     }
   }
-  float s1[8], s2[8];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) { s1[j] = 0.f; s2[j] = 0.f; }
-  const long long npix = (long long)N * IH * IW;
-  for (long long p = (long long)blockIdx.x * ppb + pl; p < npix; p += (long long)gridDim.x * ppb) {
-    const int sx = (int)(p % IW), sy = (int)((p / IW) % IH), n = (int)(p / ((long long)IW * IH));
-    const int h0 = start_h[sy], nh = cnt_h[sy], w0 = start_w[sx], nw = cnt_w[sx];
-    float sd[8];
+  for (int j = 0; j < 8; ++j) {
+    atomicAdd(&s_acc[c + j], u1[j]);
+    atomicAdd(&s_acc[kMaxC + c + j], u2[j]);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < C; i += 256) {
+    atomicAdd(acc + i, (double)s_acc[i]);
+    atomicAdd(acc + kMaxC + i, (double)s_acc[kMaxC + i]);
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256, 2)
+bn_bwd_apply_kernel(const T* __restrict__ dA, const T* __restrict__ y, T* __restrict__ dY,
+                    const int* __restrict__ start_h, const int* __restrict__ cnt_h, const int* __restrict__ start_w,
+                    const int* __restrict__ cnt_w, const float* __restrict__ stats, const float* __restrict__ gamma,
+                    const double* __restrict__ acc, int N, int C, int IH, int IW, int OH, int OW, double count) {
+  const int cg = C >> 3, pstep = 256 / cg;
+  const int c = (threadIdx.x % cg) << 3, pl = threadIdx.x / cg;
+  float scale[8], shift[8], P[8], Q[8], R[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) sd[j] = 0.f;
-    for (int a = 0; a < nh; ++a)
-      for (int b = 0; b < nw; ++b) {
-        float g[8];
-        Elem<T>::load8(dA + (((size_t)n * OH + h0 + a) * OW + w0 + b) * C + c, g);
+  for (int j = 0; j < 8; ++j) {
+    const double mean = stats[c + j], invstd = stats[kMaxC + c + j], gm = gamma[c + j];
+    scale[j] = stats[2 * kMaxC + c + j]; shift[j] = stats[3 * kMaxC + c + j];
+    const double S1 = acc[c + j], S2 = invstd * (acc[kMaxC + c + j] - mean * S1);
+    const double M1 = gm * S1 / count, M2 = gm * S2 / count;
+    const double r = invstd * invstd * M2;
+    P[j] = (float)(invstd * gm); R[j] = (float)r; Q[j] = (float)(invstd * M1 - mean * r);
+  }
+  for (int row = blockIdx.x; row < N * IH; row += gridDim.x) {
+    const int n = row / IH, sy = row % IH;
+    const int h0 = start_h[sy], nh = cnt_h[sy];
+    const T* yrow = y + (size_t)row * IW * C + c;
+    T* orow = dY + (size_t)row * IW * C + c;
+    const T* d0 = dA + ((size_t)n * OH + h0) * OW * C + c;
+    for (int x = pl; x < IW; x += pstep) {
+      const int w0 = start_w[x], nw = cnt_w[x];
+      float sd[8], yv[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) sd[j] += g[j];
+      for (int j = 0; j < 8; ++j) sd[j] = 0.f;
+      Elem<T>::load8(yrow + (size_t)x * C, yv);
+      if (nh <= 2 && nw <= 2) {        // the reference geometry (x1.2 up, x0.8 down): at most 2x2 replicas
+        float g00[8], g01[8], g10[8], g11[8];
+        const bool a0 = nh > 0, a1 = nh > 1, b0 = nw > 0, b1 = nw > 1;
+        const T* q = d0 + (size_t)w0 * C;
+        if (a0 && b0) Elem<T>::load8(q, g00);
+        if (a0 && b1) Elem<T>::load8(q + C, g01);
+        if (a1 && b0) Elem<T>::load8(q + (size_t)OW * C, g10);
+        if (a1 && b1) Elem<T>::load8(q + (size_t)OW * C + C, g11);
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          sd[j] = ((a0 && b0) ? g00[j] : 0.f) + ((a0 && b1) ? g01[j] : 0.f) + ((a1 && b0) ? g10[j] : 0.f) + ((a1 && b1) ? g11[j] : 0.f);
+      } else {
+        for (int a = 0; a < nh; ++a)
+          for (int b = 0; b < nw; ++b) {
+            float g[8];
+            Elem<T>::load8(d0 + ((size_t)a * OW + w0 + b) * C, g);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) sd[j] += g[j];
+          }
       }
-    float yv[8];
-    Elem<T>::load8(y + (size_t)p * C + c, yv);
-    if (!APPLY) {
-      if (nh * nw > 0) {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float z = fmaf(scale[j], yv[j], shift[j]);
-          const float xh = (yv[j] - mean[j]) * invstd[j];
-          const float t = z > 0.f ? sd[j] : 0.f;
-          s1[j] += t;
-          s2[j] += t * xh;
-        }
-      }
-    } else {
       const float cnt = (float)(nh * nw);
       float o[8];
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        const float z = fmaf(scale[j], yv[j], shift[j]);
-        const float xh = (yv[j] - mean[j]) * invstd[j];
-        const float t = z > 0.f ? sd[j] * gm[j] : 0.f;
-        o[j] = invstd[j] * (t - cnt * (m1[j] + xh * m2[j]));
+        const float t = fmaf(scale[j], yv[j], shift[j]) > 0.f ? sd[j] : 0.f;
+        o[j] = P[j] * t - cnt * fmaf(R[j], yv[j], Q[j]);
       }
-      Elem<T>::store8(dY + (size_t)p * C + c, o);
-    }
-  }
-  if (!APPLY) {
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      atomicAdd(&s_acc[c + j], s1[j]);
-      atomicAdd(&s_acc[kMaxC + c + j], s2[j]);
-    }
-    __syncthreads();
-    for (int i = threadIdx.x; i < C; i += 256) {
-      atomicAdd(acc + i, (double)s_acc[i]);
-      atomicAdd(acc + kMaxC + i, (double)s_acc[kMaxC + i]);
+      Elem<T>::store8(orow + (size_t)x * C, o);
     }
   }
 }
@@ -390,8 +467,8 @@ int hrfp_forward(const mrfp_hrfp_plan* P, const float* xp, const float* const* W
   T* bufB = reinterpret_cast<T*>(ws + P->bufs_off + P->buf_a_bytes);
   {
     const int HW = P->xh * P->xw;
-    dim3 g((HW + 31) / 32, (P->cin + 31) / 32, P->N);
-    nchw_to_nhwc_kernel<T><<<g, dim3(32, 8), 0, s>>>(xp, bufA, P->cin, HW, 0);
+    dim3 g((HW + 63) / 64, (P->cin + 63) / 64, P->N);
+    nchw_to_nhwc_kernel<T><<<g, 256, 0, s>>>(xp, bufA, P->cin, HW, 0);
   }
   T* cur = bufA;
   T* nxt = bufB;
@@ -419,14 +496,14 @@ int hrfp_forward(const mrfp_hrfp_plan* P, const float* xp, const float* const* W
     bn_finalize_kernel<<<1, 256, 0, s>>>(a, gamma[k], beta ? beta[k] : nullptr, rmean ? rmean[k] : nullptr,
                                          rvar ? rvar[k] : nullptr, stats, st.cout, count, momentum, eps);
     if (k == 3 && ocout_dec) {
-      dim3 g(P->N * st.oh, (st.cout + 31) / 32, (st.ow + 31) / 32);
-      nhwc_to_nchw_kernel<T><<<g, dim3(32, 8), 0, s>>>(Y, ocout_dec, nullptr, lut + st.idx_h, lut + st.idx_w,
+      dim3 g(P->N * st.oh, (st.cout + 63) / 64, (st.ow + 63) / 64);
+      nhwc_to_nchw_kernel<T><<<g, 256, 0, s>>>(Y, ocout_dec, nullptr, lut + st.idx_h, lut + st.idx_w,
                                                         stats + 2 * kMaxC, stats + 3 * kMaxC, st.cout, st.ch, st.cw,
                                                         st.oh, st.ow);
     }
     if (k == kHrfpStages - 1) {
-      dim3 g(P->N * st.oh, (st.cout + 31) / 32, (st.ow + 31) / 32);
-      nhwc_to_nchw_kernel<T><<<g, dim3(32, 8), 0, s>>>(Y, ocout, x_add, lut + st.idx_h, lut + st.idx_w,
+      dim3 g(P->N * st.oh, (st.cout + 63) / 64, (st.ow + 63) / 64);
+      nhwc_to_nchw_kernel<T><<<g, 256, 0, s>>>(Y, ocout, x_add, lut + st.idx_h, lut + st.idx_w,
                                                         stats + 2 * kMaxC, stats + 3 * kMaxC, st.cout, st.ch, st.cw,
                                                         st.oh, st.ow);
     } else if (k + 1 < last) {
@@ -457,9 +534,9 @@ int hrfp_backward(const mrfp_hrfp_plan* P, const float* g_ocout, const float* g_
     const float* gin = (k == kHrfpStages - 1) ? g_ocout : (k == 3 ? g_ocout_dec : nullptr);
     if (gin) {
       const int HW = st.oh * st.ow;
-      dim3 g((HW + 31) / 32, (st.cout + 31) / 32, P->N);
+      dim3 g((HW + 63) / 64, (st.cout + 63) / 64, P->N);
       T* dst = dA ? dA : g0;
-      nchw_to_nhwc_kernel<T><<<g, dim3(32, 8), 0, s>>>(gin, dst, st.cout, HW, dA ? 1 : 0);
+      nchw_to_nhwc_kernel<T><<<g, 256, 0, s>>>(gin, dst, st.cout, HW, dA ? 1 : 0);
       if (!dA) { dA = g0; other = g1; }
     }
     if (!dA) continue;
@@ -467,15 +544,13 @@ int hrfp_backward(const mrfp_hrfp_plan* P, const float* g_ocout, const float* g_
     const float* stats = reinterpret_cast<const float*>(saved + P->stats_off) + (size_t)k * 4 * kMaxC;
     double* a = acc + (size_t)k * 2 * kMaxC;
     const double count = (double)P->N * st.oh * st.ow;
-    const long long npix = (long long)P->N * st.ch * st.cw;
-    const int ppb = 256 / (st.cout / 8);
-    const int grid = grid_for(npix, ppb, di.sm_count, 4);
-    bn_bwd_kernel<T, false><<<grid, 256, 0, s>>>(dA, Y, nullptr, lut + st.start_h, lut + st.cnt_h, lut + st.start_w,
-                                                 lut + st.cnt_w, stats, gamma[k], a, P->N, st.cout, st.ch, st.cw,
-                                                 st.oh, st.ow, count);
-    bn_bwd_kernel<T, true><<<grid, 256, 0, s>>>(dA, Y, dY, lut + st.start_h, lut + st.cnt_h, lut + st.start_w,
-                                                lut + st.cnt_w, stats, gamma[k], a, P->N, st.cout, st.ch, st.cw,
-                                                st.oh, st.ow, count);
+    const int cap = di.sm_count * 8;
+    const int grid_r = P->N * st.oh < cap ? P->N * st.oh : cap, grid_a = P->N * st.ch < cap ? P->N * st.ch : cap;
+    bn_bwd_reduce_kernel<T><<<grid_r, 256, 0, s>>>(dA, Y, lut + st.idx_h, lut + st.idx_w, stats, a, P->N, st.cout, st.ch,
+                                                   st.cw, st.oh, st.ow);
+    bn_bwd_apply_kernel<T><<<grid_a, 256, 0, s>>>(dA, Y, dY, lut + st.start_h, lut + st.cnt_h, lut + st.start_w,
+                                                  lut + st.cnt_w, stats, gamma[k], a, P->N, st.cout, st.ch, st.cw,
+                                                  st.oh, st.ow, count);
     // dgrad: conv of dY (cout channels) with the rotated / transposed kernel -> dA_prev (cin channels)
     if (tc) {
       int rc = conv3x3_tc_bf16(reinterpret_cast<const __nv_bfloat16*>(dY),
@@ -484,7 +559,7 @@ int hrfp_backward(const mrfp_hrfp_plan* P, const float* g_ocout, const float* g_
                                nullptr, nullptr, nullptr, s);
       if (rc) return rc;
     } else {
-      dim3 g((unsigned)((npix + 31) / 32), (st.cin + 63) / 64);
+      dim3 g((unsigned)(((long long)P->N * st.ch * st.cw + 31) / 32), (st.cin + 63) / 64);
       const size_t smem = (size_t)st.cout * 64 * sizeof(float);
       MRFP_CUDA_TRY(cudaFuncSetAttribute(conv3x3_direct_f32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       conv3x3_direct_f32_kernel<<<g, 128, smem, s>>>(reinterpret_cast<const float*>(dY),
@@ -498,8 +573,8 @@ int hrfp_backward(const mrfp_hrfp_plan* P, const float* g_ocout, const float* g_
     MRFP_CUDA_TRY(cudaMemsetAsync(g_xp, 0, (size_t)P->N * P->cin * P->xh * P->xw * sizeof(float), s));
     return MRFP_OK;
   }
-  dim3 g(P->N * P->xh, (P->cin + 31) / 32, (P->xw + 31) / 32);
-  nhwc_to_nchw_kernel<T><<<g, dim3(32, 8), 0, s>>>(dA, g_xp, nullptr, nullptr, nullptr, nullptr, nullptr, P->cin,
+  dim3 g(P->N * P->xh, (P->cin + 63) / 64, (P->xw + 63) / 64);
+  nhwc_to_nchw_kernel<T><<<g, 256, 0, s>>>(dA, g_xp, nullptr, nullptr, nullptr, nullptr, nullptr, P->cin,
                                                     P->xh, P->xw, P->xh, P->xw);
   MRFP_CUDA_TRY(cudaGetLastError());
   return MRFP_OK;
