@@ -25,12 +25,17 @@ constexpr int kThreads = 192;
 constexpr int kATileBytes = 128 * 128;          // 128 pixels x 64 ch x 2 B
 constexpr int kStageOutBytes = 128 * 128;       // 128 pixels x 64 ch x 2 B
 
+// MT = M sub-tiles (of 128 pixels, stacked vertically) per CTA tile.  With MT = 2 one B (weight) tile feeds two
+// MMAs, halving the weight traffic per FLOP: the 64/128-wide layers are bound by the L2->SM operand stream
+// (~100 B/clk/SM), not by the tensor pipe.  COUT = 256 already fills TMEM (2 x 256 columns) with MT = 1.
 template <int COUT> struct Cfg {
+  static constexpr int kMT = COUT == 256 ? 1 : 2;
+  static constexpr int kAStageBytes = kMT * kATileBytes;
   static constexpr int kBTileBytes = COUT * 128;
-  static constexpr int kStages = COUT == 256 ? 4 : (COUT == 128 ? 5 : 6);
-  static constexpr int kOutBufs = COUT == 256 ? 1 : 2;
-  static constexpr int kTmemCols = 2 * COUT < 32 ? 32 : 2 * COUT;   // power of two for COUT in {16..256}
-  static constexpr int kSmemBytes = kStages * (kATileBytes + kBTileBytes) + kOutBufs * kStageOutBytes +
+  static constexpr int kStages = 4;
+  static constexpr int kOutBufs = COUT == 64 ? 2 : 1;
+  static constexpr int kTmemCols = 2 * kMT * COUT;                  // 256 / 512 / 512: powers of two
+  static constexpr int kSmemBytes = kStages * (kAStageBytes + kBTileBytes) + kOutBufs * kStageOutBytes +
                                     2 * COUT * 4 + 256 /* barriers */ + 1024 /* alignment slack */;
 };
 
@@ -120,7 +125,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_cons
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   unsigned char* sA = smem;
-  unsigned char* sB = sA + C::kStages * kATileBytes;
+  unsigned char* sB = sA + C::kStages * C::kAStageBytes;
   unsigned char* sOut = sB + C::kStages * C::kBTileBytes;
   float* s_stats = reinterpret_cast<float*>(sOut + C::kOutBufs * kStageOutBytes);
   uint64_t* full = reinterpret_cast<uint64_t*>(s_stats + 2 * COUT);
@@ -153,13 +158,13 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_cons
       int stage = 0; uint32_t phase = 0;
       for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
         const int tw = t % tiles_w, th = (t / tiles_w) % tiles_h, n = t / (tiles_w * tiles_h);
-        const int h0 = th * kTileH, w0 = tw * kTileW;
+        const int h0 = th * kTileH * C::kMT, w0 = tw * kTileW;
         for (int tap = 0; tap < 9; ++tap) {
           const int dy = (tap / 3 - 1) * dil, dx = (tap % 3 - 1) * dil;
           for (int kc = 0; kc < CIN / kBlockK; ++kc) {
             mbar_wait(&empty[stage], phase ^ 1);
-            mbar_expect_tx(&full[stage], kATileBytes + C::kBTileBytes);
-            tma_load_4d(sA + stage * kATileBytes, &tmap_in, &full[stage], kc * kBlockK, w0 + dx, h0 + dy, n);
+            mbar_expect_tx(&full[stage], C::kAStageBytes + C::kBTileBytes);
+            tma_load_4d(sA + stage * C::kAStageBytes, &tmap_in, &full[stage], kc * kBlockK, w0 + dx, h0 + dy, n);
             tma_load_2d(sB + stage * C::kBTileBytes, &tmap_w, &full[stage], kc * kBlockK, tap * COUT);
             if (++stage == C::kStages) { stage = 0; phase ^= 1; }
           }
@@ -177,15 +182,18 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_cons
         const int acc = it & 1;
         mbar_wait(&tmem_empty[acc], ((it >> 1) & 1) ^ 1);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * COUT);
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * C::kMT * COUT);
         for (int ks = 0; ks < nk; ++ks) {
           mbar_wait(&full[stage], phase);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-          const uint64_t da = make_desc_sw128(smem_u32(sA + stage * kATileBytes));
+          const uint64_t da = make_desc_sw128(smem_u32(sA + stage * C::kAStageBytes));
           const uint64_t db = make_desc_sw128(smem_u32(sB + stage * C::kBTileBytes));
 #pragma unroll
           for (int k = 0; k < kBlockK / kUmmaK; ++k)   // +32 B per UMMA_K inside the swizzle row
-            umma_bf16(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (ks | k) != 0);
+#pragma unroll
+            for (int mt = 0; mt < C::kMT; ++mt)        // the second M sub-tile is the next 128 rows (16 KiB) of the A box
+              umma_bf16(d_tmem + (uint32_t)(mt * COUT), da + (uint64_t)(mt * (kATileBytes >> 4) + k * 2),
+                        db + (uint64_t)(k * 2), idesc, (ks | k) != 0);
           umma_commit(&empty[stage]);                  // frees the smem slot when the MMAs have read it
           if (++stage == C::kStages) { stage = 0; phase ^= 1; }
         }
@@ -201,14 +209,15 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_cons
     int it = 0, obuf = 0;
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
       const int tw = t % tiles_w, th = (t / tiles_w) % tiles_h, n = t / (tiles_w * tiles_h);
-      const int h0 = th * kTileH, w0 = tw * kTileW;
+      const int h0 = th * kTileH * C::kMT, w0 = tw * kTileW;
       const int acc = it & 1;
-      float wgt = 0.f;
-      if (stat_acc) wgt = (float)(cnt_h[h0 + hl] * cnt_w[w0 + wl]);   // 0 outside the image (zero-padded tables)
       mbar_wait(&tmem_full[acc], (it >> 1) & 1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll 1
-      for (int j = 0; j < COUT / 64; ++j) {
+      for (int jj = 0; jj < C::kMT * (COUT / 64); ++jj) {
+        const int mt = jj / (COUT / 64), j = jj % (COUT / 64);
+        float wgt = 0.f;
+        if (stat_acc) wgt = (float)(cnt_h[h0 + mt * kTileH + hl] * cnt_w[w0 + wl]);   // 0 outside the image (zero-padded tables)
         unsigned char* ob = sOut + obuf * kStageOutBytes;
         // the TMA store that last read this staging buffer must have drained
         if (leader) asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(C::kOutBufs - 1) : "memory");
@@ -216,7 +225,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_cons
 #pragma unroll
         for (int half = 0; half < 2; ++half) {
           uint32_t v[32];
-          tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * COUT + j * 64 + half * 32), v);
+          tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((acc * C::kMT + mt) * COUT + j * 64 + half * 32), v);
           if (stat_acc) {
             float x1[32], x2[32];
 #pragma unroll
@@ -242,7 +251,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_cons
             *reinterpret_cast<uint4*>(ob + r * 128 + ((chunk ^ (r & 7)) << 4)) = make_uint4(p[0], p[1], p[2], p[3]);
           }
         }
-        if (j == COUT / 64 - 1) {               // all TMEM reads of this accumulator are done
+        if (jj == C::kMT * (COUT / 64) - 1) {   // all TMEM reads of this accumulator are done
           asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
           __syncwarp();
           if (lane == 0) mbar_arrive(&tmem_empty[acc]);
@@ -250,7 +259,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_cons
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         epi_bar_sync();
         if (leader) {
-          tma_store_4d(&tmap_out, ob, j * 64, w0, h0, n);
+          tma_store_4d(&tmap_out, ob, j * 64, w0, h0 + mt * kTileH, n);
           asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         }
         if (++obuf == C::kOutBufs) obuf = 0;
@@ -311,7 +320,7 @@ int launch(const __nv_bfloat16* in, const __nv_bfloat16* wpack, __nv_bfloat16* o
   {
     const cuuint64_t dims[4] = {(cuuint64_t)cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
     const cuuint64_t strides[3] = {(cuuint64_t)cin * 2, (cuuint64_t)W * cin * 2, (cuuint64_t)H * W * cin * 2};
-    const cuuint32_t box[4] = {kBlockK, kTileW, kTileH, 1};
+    const cuuint32_t box[4] = {kBlockK, kTileW, (cuuint32_t)(kTileH * Cfg<COUT>::kMT), 1};
     int rc = make_map(&m_in, in, 4, dims, strides, box);
     if (rc) return rc;
   }
@@ -332,7 +341,8 @@ int launch(const __nv_bfloat16* in, const __nv_bfloat16* wpack, __nv_bfloat16* o
   DeviceInfo di;
   int rc = get_device_info(&di);
   if (rc) return rc;
-  const int tiles_h = (H + kTileH - 1) / kTileH, tiles_w = (W + kTileW - 1) / kTileW;
+  const int th_px = kTileH * Cfg<COUT>::kMT;
+  const int tiles_h = (H + th_px - 1) / th_px, tiles_w = (W + kTileW - 1) / kTileW;
   const int num_tiles = N * tiles_h * tiles_w;
   const int grid = num_tiles < di.sm_count ? num_tiles : di.sm_count;
   auto kern = conv3x3_tc_kernel<COUT>;

@@ -623,7 +623,8 @@ extern "C" int mrfp_hrfp_plan_create(mrfp_hrfp_plan_t** out, int N, int cin, int
     std::vector<int>& L = P->lut;
     st.idx_h = (int)L.size(); L.resize(L.size() + st.oh); make_index(ch, st.oh, sf, sfs[k], &L[st.idx_h]);
     st.idx_w = (int)L.size(); L.resize(L.size() + st.ow); make_index(cw, st.ow, sf, sfs[k], &L[st.idx_w]);
-    const int ph = (ch + kTileH - 1) / kTileH * kTileH + kTileH, pw = (cw + kTileW - 1) / kTileW * kTileW + kTileW;
+    const int ph = (ch + 2 * kTileH - 1) / (2 * kTileH) * (2 * kTileH) + 2 * kTileH;   // conv tiles are up to 16 rows tall
+    const int pw = (cw + kTileW - 1) / kTileW * kTileW + kTileW;
     st.cnt_h = (int)L.size(); L.resize(L.size() + ph, 0);
     st.cnt_w = (int)L.size(); L.resize(L.size() + pw, 0);
     st.start_h = (int)L.size(); L.resize(L.size() + ch, 0);

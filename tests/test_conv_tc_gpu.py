@@ -37,7 +37,7 @@ def test_conv_matches_torch(cin, cout, dil, shape):
     torch.manual_seed(cin + cout + dil + h)
     x = torch.relu(torch.randn(n, cin, h, w, device="cuda"))
     wt = torch.randn(cout, cin, 3, 3, device="cuda") * (2.0 / (9 * cin)) ** 0.5
-    cnt_h = torch.zeros(((h + 7) // 8 + 1) * 8, dtype=torch.int32, device="cuda")
+    cnt_h = torch.zeros(((h + 15) // 16 + 1) * 16, dtype=torch.int32, device="cuda")
     cnt_w = torch.zeros(((w + 15) // 16 + 1) * 16, dtype=torch.int32, device="cuda")
     cnt_h[:h] = torch.randint(0, 3, (h,), device="cuda", dtype=torch.int32)
     cnt_w[:w] = torch.randint(0, 3, (w,), device="cuda", dtype=torch.int32)
