@@ -60,11 +60,12 @@ def cpu_reference_run(steps, warmup, batch=2):
     draws = [(1 + 0.75 * torch.randn(batch, c, 1, 1, generator=g), 0.75 * torch.randn(batch, c, 1, 1, generator=g)) for c in (64, 256)]
     grads = (torch.randn(batch, 64, XH, XW, generator=g), torch.randn(batch, 256, H_IMG // 2, W_IMG // 2, generator=g),
              torch.randn(batch, 256, XH, XW, generator=g))
+    d1 = torch.randn(batch, 256, H_IMG // 2, W_IMG // 2, generator=g)
     for _ in range(warmup):
-        T.mrfp_step(convs, bns, xp, f2, draws, grads, H_IMG, W_IMG)
+        T.mrfp_step(convs, bns, xp, f2, d1, draws, grads, H_IMG, W_IMG)
     t0 = time.perf_counter()
     for _ in range(steps):
-        T.mrfp_step(convs, bns, xp, f2, draws, grads, H_IMG, W_IMG)
+        T.mrfp_step(convs, bns, xp, f2, d1, draws, grads, H_IMG, W_IMG)
     dt = time.perf_counter() - t0
     return dict(value=batch * steps / dt, unit=UNIT, cores=torch.get_num_threads(), kind="port",
                 sample=f"same step at batch {batch} (BASELINE config[0] shapes), {steps} timed + {warmup} warm-up passes of "
@@ -145,7 +146,8 @@ def run_ours(args):
     lib = _lib.load()
 
     n = N_PER_GPU
-    torch.manual_seed(1 + rank)
+    from mrfp_b200 import dist as D
+    D.seed_rank_streams(1, rank)
     from mrfp_b200.model import HRFP_CONVS, init_hrfp_module
     chans, dils = [64, 64, 64, 128, 256, 128, 64, 64, 64], [1, 1, 2, 2, 1, 1, 2, 2]
     convs = [torch.nn.Conv2d(chans[k], chans[k + 1], 3, padding=dils[k], dilation=dils[k]).to(dev).requires_grad_(False)
@@ -159,18 +161,20 @@ def run_ours(args):
     f2 = torch.relu(torch.randn(n, 256, XH, XW, device=dev) * sig + mu)
     draws = [(1 + 0.75 * torch.randn(n, c, 1, 1, device=dev), 0.75 * torch.randn(n, c, 1, 1, device=dev)) for c in (64, 256)]
     g_x = torch.randn(n, 64, XH, XW, device=dev)
-    g_dec = torch.randn(n, 256, H_IMG // 2, W_IMG // 2, device=dev)
+    g_dec = torch.randn(n, 256, H_IMG // 2, W_IMG // 2, device=dev)     # gradient wrt dec1 after the HRFP+ add
     g_f2 = torch.randn(n, 256, XH, XW, device=dev)
+    dec1_up = torch.randn(n, 256, H_IMG // 2, W_IMG // 2, device=dev)   # the decoder feature the HRFP+ skip adds to
 
-    def step(xp_, f2_, gx_, gdec_, gf2_):
-        """Public API path: autograd Functions over the C ABI."""
+    def step(xp_, f2_, d1_, gx_, gdec_, gf2_):
+        """Public API path: autograd Functions over the C ABI (the same calls MRFPPlus.forward makes)."""
         a = xp_.detach().requires_grad_(True)
         b = f2_.detach().requires_grad_(True)
-        x = NP.np_plus_with_draws(a, *draws[0])
-        x, dec = H.hrfp_chain(a, convs, bns, H_IMG, W_IMG, x_add=x, math_mode=H.MATH_BF16)
-        y2 = NP.np_plus_with_draws(b, *draws[1])
-        torch.autograd.backward([x, dec, y2], [gx_, gdec_, gf2_])
-        return x, dec, y2, a.grad, b.grad
+        x = NP.np_plus_with_draws(a, *draws[0])                                        # deepv3.py:318
+        x, dec = H.hrfp_chain(a, convs, bns, H_IMG, W_IMG, x_add=x, math_mode=H.MATH_BF16, lazy_dec=True)   # :320-330
+        y2 = NP.np_plus_with_draws(b, *draws[1])                                       # :335
+        d1 = H.hrfp_plus_add(d1_, dec)                                                 # :357
+        torch.autograd.backward([x, d1, y2], [gx_, gdec_, gf2_])
+        return x, d1, y2, a.grad, b.grad
 
     def sync_all():
         torch.cuda.synchronize()
@@ -179,7 +183,7 @@ def run_ours(args):
             torch.cuda.synchronize()
 
     for _ in range(max(args.warmup, 3)):
-        step(xp, f2, g_x, g_dec, g_f2)
+        step(xp, f2, dec1_up, g_x, g_dec, g_f2)
     sampler = ClockSampler(local) if rank == 0 else None
     sync_all()
     if sampler:
@@ -187,7 +191,7 @@ def run_ours(args):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(args.steps):
-        step(xp, f2, g_x, g_dec, g_f2)
+        step(xp, f2, dec1_up, g_x, g_dec, g_f2)
     e1.record()
     sync_all()
     ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
@@ -200,9 +204,9 @@ def run_ours(args):
     value = world * n * args.steps / (total_ms * 1e-3)
 
     # ---- e2e: same step through the same API with HOST (pinned) buffers, copies inside the timed region ----
-    host_in = [t.cpu().pin_memory() for t in (xp, f2, g_x, g_dec, g_f2)]
-    dev_in = [torch.empty_like(t) for t in (xp, f2, g_x, g_dec, g_f2)]
-    outs = step(xp, f2, g_x, g_dec, g_f2)
+    host_in = [t.cpu().pin_memory() for t in (xp, f2, dec1_up, g_x, g_dec, g_f2)]
+    dev_in = [torch.empty_like(t) for t in (xp, f2, dec1_up, g_x, g_dec, g_f2)]
+    outs = step(xp, f2, dec1_up, g_x, g_dec, g_f2)
     host_out = [torch.empty(o.shape, dtype=o.dtype).pin_memory() for o in outs]
     h2d = sum(t.numel() * 4 for t in host_in)
     d2h = sum(t.numel() * 4 for t in host_out)
@@ -314,12 +318,12 @@ def run_ours(args):
         return a.elapsed_time(b) / iters
 
     xr = xp.detach().requires_grad_(True)
-    t_chain_f = t_api(lambda: H.hrfp_chain(xr, convs, bns, H_IMG, W_IMG, math_mode=H.MATH_BF16))
+    t_chain_f = t_api(lambda: H.hrfp_plus_add(dec1_up, H.hrfp_chain(xr, convs, bns, H_IMG, W_IMG, math_mode=H.MATH_BF16, lazy_dec=True)[1]))
 
     def chain_fb():
         xr.grad = None
-        o, d = H.hrfp_chain(xr, convs, bns, H_IMG, W_IMG, math_mode=H.MATH_BF16)
-        torch.autograd.backward([o, d], [g_x, g_dec])
+        o, d = H.hrfp_chain(xr, convs, bns, H_IMG, W_IMG, math_mode=H.MATH_BF16, lazy_dec=True)
+        torch.autograd.backward([o, H.hrfp_plus_add(dec1_up, d)], [g_x, g_dec])
     t_chain_fb = t_api(chain_fb)
     hrfp = {"fwd_ms": t_chain_f, "fwd_bwd_ms": t_chain_fb,
             "fwd_tflops_needed_only": HRFP_FLOP_FWD_PER_SAMPLE * n / t_chain_f / 1e9,
@@ -328,8 +332,9 @@ def run_ours(args):
     base, _ = cpu_reference_run(1, 1) if world == 1 else (None, None)
 
     # kernels launched per step (ours; memsets excluded): NP+ 2 fwd + 2 bwd; HRFP fwd 16 weight packs + 1 NCHW->NHWC +
-    # 8 conv + 8 BN finalize + 7 BN/ReLU/resample + 2 NHWC->NCHW epilogues; HRFP bwd 2 NCHW->NHWC + 8 x (2 BN-bwd + conv) + 1
-    launches_per_step = 4 + (16 + 1 + 8 + 8 + 7 + 2) + (2 + 24 + 1)
+    # 8 conv + 8 BN finalize + 7 BN/ReLU/resample + 1 NHWC->NCHW epilogue (OCout + x); 1 fused HRFP+ add;
+    # HRFP bwd 2 NCHW->NHWC + 8 x (2 BN-bwd + conv) + 1 NHWC->NCHW
+    launches_per_step = 4 + (16 + 1 + 8 + 8 + 7 + 1) + 1 + (2 + 24 + 1)
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16 (HRFP tensor-core operands, fp32 accumulate) / f32 (NP+)", "data": "synthetic", "config": CONFIG,

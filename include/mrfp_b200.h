@@ -98,7 +98,8 @@ int    mrfp_hrfp_plan_stage(const mrfp_hrfp_plan_t* plan, int k, int* out7);
  * place with `momentum` (unbiased variance) or skipped when the array pointer is NULL.
  *   ocout      (N,cin,xh,xw)      = OCout (+ x_add when x_add != NULL: deepv3.py:330)
  *   ocout_dec  (N,widths[3],h/2,w/2) = OCout_dec, or NULL when HRFP+ is off
- * ocout == NULL runs the encoder half only (decoder output unused when p >= 0.5). */
+ * ocout == NULL runs the encoder half only (decoder output unused when p >= 0.5); with ocout_dec == NULL as
+ * well the call only leaves the state for a later mrfp_hrfp_plus_add / mrfp_hrfp_bwd in `saved`. */
 int mrfp_hrfp_fwd(const mrfp_hrfp_plan_t* plan, const float* xp,
                   const float* const* W, const float* const* gamma, const float* const* beta,
                   float* const* running_mean, float* const* running_var, float momentum, float eps,
@@ -110,7 +111,14 @@ int mrfp_hrfp_bwd(const mrfp_hrfp_plan_t* plan, const float* g_ocout, const floa
                   const float* const* gamma, const void* lut, const void* saved,
                   float* g_xp, void* ws, void* stream);
 
-/* HRFP+ skip add, deepv3.py:357: out = dec1_up + ocout_dec (both (N,C,H,W) fp32). */
+/* HRFP+ skip add, deepv3.py:357, fused with the production of OCout_dec: out = dec1_up + OCout_dec where
+ * OCout_dec = ReLU(BN(resample(conv4))) is recomputed from the state `saved` by the preceding mrfp_hrfp_fwd
+ * (which may then be called with ocout_dec == NULL): the (N,256,h/2,w/2) fp32 tensor is never materialised.
+ * dec1_up / out: (N, widths[3], h/2, w/2) fp32 NCHW. */
+int mrfp_hrfp_plus_add(const mrfp_hrfp_plan_t* plan, const void* saved, const void* lut, const float* dec1_up,
+                       float* out, void* stream);
+
+/* Plain variant of the same add for a materialised OCout_dec: out = a + b (n elements). */
 int mrfp_add_f32(const float* a, const float* b, float* out, size_t n, void* stream);
 
 #ifdef __cplusplus

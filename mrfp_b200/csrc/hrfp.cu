@@ -694,7 +694,6 @@ extern "C" int mrfp_hrfp_fwd(const mrfp_hrfp_plan_t* P, const float* xp, const f
                              float* ocout_dec, const void* lut, void* saved, void* ws, void* stream) {
   if (!P || P->magic != kPlanMagic) return MRFP_ERR_BAD_PLAN;
   if (!xp || !W || !gamma || !lut || !saved || !ws) return MRFP_ERR_NULL_POINTER;
-  if (!ocout && !ocout_dec) return MRFP_ERR_NULL_POINTER;
   if (((uintptr_t)saved | (uintptr_t)ws | (uintptr_t)lut) & 255) return MRFP_ERR_WORKSPACE;
   const int last = ocout ? kHrfpStages : 4;
   for (int k = 0; k < last; ++k)
@@ -724,6 +723,29 @@ extern "C" int mrfp_hrfp_bwd(const mrfp_hrfp_plan_t* P, const float* g_ocout, co
     return hrfp_backward<__nv_bfloat16>(P, g_ocout, g_ocout_dec, gamma, (const int*)lut, (const char*)saved, g_xp,
                                         (char*)ws, s, di);
   return hrfp_backward<float>(P, g_ocout, g_ocout_dec, gamma, (const int*)lut, (const char*)saved, g_xp, (char*)ws, s, di);
+}
+
+template <typename T>
+static int hrfp_plus_add_impl(const mrfp_hrfp_plan* P, const char* saved, const int* lut, const float* dec1_up,
+                              float* out, cudaStream_t s) {
+  const HrfpStage& st = P->st[3];
+  const T* Y = reinterpret_cast<const T*>(saved + st.y_off);
+  const float* stats = reinterpret_cast<const float*>(saved + P->stats_off) + (size_t)3 * 4 * kMaxC;
+  dim3 g(P->N * st.oh, (st.cout + 63) / 64, (st.ow + 63) / 64);
+  nhwc_to_nchw_kernel<T><<<g, 256, 0, s>>>(Y, out, dec1_up, lut + st.idx_h, lut + st.idx_w, stats + 2 * kMaxC,
+                                            stats + 3 * kMaxC, st.cout, st.ch, st.cw, st.oh, st.ow);
+  MRFP_CUDA_TRY(cudaGetLastError());
+  return MRFP_OK;
+}
+
+extern "C" int mrfp_hrfp_plus_add(const mrfp_hrfp_plan_t* P, const void* saved, const void* lut, const float* dec1_up,
+                                  float* out, void* stream) {
+  if (!P || P->magic != kPlanMagic) return MRFP_ERR_BAD_PLAN;
+  if (!saved || !lut || !dec1_up || !out) return MRFP_ERR_NULL_POINTER;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (P->mode == MRFP_MATH_BF16)
+    return hrfp_plus_add_impl<__nv_bfloat16>(P, (const char*)saved, (const int*)lut, dec1_up, out, s);
+  return hrfp_plus_add_impl<float>(P, (const char*)saved, (const int*)lut, dec1_up, out, s);
 }
 
 extern "C" int mrfp_add_f32(const float* a, const float* b, float* out, size_t n, void* stream) {

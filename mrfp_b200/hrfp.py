@@ -88,11 +88,25 @@ def get_plan(n, cin, xh, xw, h, w, device, math_mode=MATH_BF16, widths=DEFAULT_W
     return p
 
 
+class HrfpDec:
+    """OCout_dec left in the chain's saved state instead of being materialised as a (N,256,h/2,w/2) fp32 tensor:
+    `hrfp_plus_add(dec1_up, handle)` produces `dec1_up + OCout_dec` in one pass and routes the gradient back."""
+
+    def __init__(self, plan, saved, token, mail):
+        self.plan, self.saved, self.token = plan, saved, token
+        self.mail = mail          # {"g": gradient parked by the add's backward}; shared with the chain's ctx (no cycle)
+
+    @property
+    def shape(self):
+        return self.plan.dec_shape
+
+
 class _HrfpFn(torch.autograd.Function):
-    """(xp, x_add) -> (OCout + x_add, OCout_dec).  x_add may be None (returns OCout alone)."""
+    """(xp, x_add) -> (OCout + x_add, OCout_dec | token).  x_add may be None (returns OCout alone)."""
 
     @staticmethod
-    def forward(ctx, xp, x_add, plan, weights, gammas, betas, rmeans, rvars, momentum, eps, want_out, want_dec):
+    def forward(ctx, xp, x_add, plan, weights, gammas, betas, rmeans, rvars, momentum, eps, want_out, want_dec,
+                holder):
         lib = _lib.load()
         if not xp.is_cuda or xp.dtype != torch.float32:
             raise _lib.MrfpError("HRFP kernels need a CUDA fp32 tensor (no CPU fallback)")
@@ -101,7 +115,8 @@ class _HrfpFn(torch.autograd.Function):
         saved = torch.empty(plan.saved_bytes, dtype=torch.uint8, device=dev)
         ws = plan.workspace()
         ocout = torch.empty_like(xp_c) if want_out else None
-        ocdec = torch.empty(plan.dec_shape, dtype=torch.float32, device=dev) if want_dec else None
+        lazy_dec = want_dec and holder is not None
+        ocdec = torch.empty(plan.dec_shape, dtype=torch.float32, device=dev) if (want_dec and not lazy_dec) else None
         xa = x_add.contiguous() if (x_add is not None and want_out) else None
         wa, ga = _ptr_array(weights), _ptr_array(gammas)
         ba = _ptr_array(betas) if betas is not None else None
@@ -119,11 +134,18 @@ class _HrfpFn(torch.autograd.Function):
         ctx.gammas = [g for g in gammas]       # keep alive; gamma is read again in backward
         ctx.has_add = x_add is not None
         ctx.want_out, ctx.want_dec = want_out, want_dec
+        ctx.mail = None
         outs = []
         if want_out:
             outs.append(ocout)
         if want_dec:
-            outs.append(ocdec)
+            if lazy_dec:
+                token = torch.zeros(1, dtype=torch.float32, device=dev)    # carries the autograd edge only
+                ctx.mail = {"g": None}
+                holder.append(HrfpDec(plan, saved, token, ctx.mail))
+                outs.append(token)
+            else:
+                outs.append(ocdec)
         return tuple(outs)
 
     @staticmethod
@@ -133,6 +155,9 @@ class _HrfpFn(torch.autograd.Function):
         gi = iter(grads)
         g_out = next(gi) if ctx.want_out else None
         g_dec = next(gi) if ctx.want_dec else None
+        if ctx.mail is not None:             # the real gradient was parked by _PlusAddFusedFn.backward
+            g_dec = ctx.mail["g"]
+            ctx.mail["g"] = None
         dev = plan.device
         g_out_c = g_out.contiguous() if g_out is not None else None
         g_dec_c = g_dec.contiguous() if g_dec is not None else None
@@ -148,14 +173,15 @@ class _HrfpFn(torch.autograd.Function):
             _lib.check(rc, "mrfp_hrfp_bwd")
         g_add = g_out_c if (ctx.has_add and ctx.needs_input_grad[1]) else None
         ctx.saved_buf = None
-        return (g_xp, g_add) + (None,) * 10
+        return (g_xp, g_add) + (None,) * 11
 
 
 def hrfp_chain(xp, convs, bns, h, w, x_add=None, want_out=True, want_dec=True, math_mode=MATH_BF16,
-               update_running_stats=True):
+               update_running_stats=True, lazy_dec=False):
     """Runs the chain of deepv3.py:320-327 on `xp` with the caller's 8 conv / 8 BN modules.
 
-    Returns (OCout [+ x_add], OCout_dec) restricted to the requested outputs."""
+    Returns (OCout [+ x_add], OCout_dec) restricted to the requested outputs.  With `lazy_dec=True` the second
+    value is an `HrfpDec` handle for `hrfp_plus_add` instead of a materialised tensor."""
     n, cin, xh, xw = xp.shape
     widths = tuple(c.out_channels for c in convs[:4])
     plan = get_plan(n, cin, xh, xw, h, w, xp.device, math_mode, widths)
@@ -167,8 +193,9 @@ def hrfp_chain(xp, convs, bns, h, w, x_add=None, want_out=True, want_dec=True, m
     rvars = [b.running_var for b in bns] if track else None
     momentum = bns[0].momentum if bns[0].momentum is not None else 0.1
     eps = bns[0].eps
+    holder = [] if (lazy_dec and want_dec) else None
     outs = _HrfpFn.apply(xp, x_add, plan, weights, gammas, betas, rmeans, rvars, float(momentum), float(eps),
-                         want_out, want_dec)
+                         want_out, want_dec, holder)
     if track:
         n_run = 8 if want_out else 4
         for b in bns[:n_run]:
@@ -176,12 +203,40 @@ def hrfp_chain(xp, convs, bns, h, w, x_add=None, want_out=True, want_dec=True, m
     outs = list(outs)
     out = outs.pop(0) if want_out else None
     dec = outs.pop(0) if want_dec else None
+    if holder:
+        holder[0].token = dec             # the autograd-tracked output of the Function
+        dec = holder[0]
     return out, dec
 
 
-def hrfp_plus_add(dec1_up: torch.Tensor, ocout_dec: torch.Tensor) -> torch.Tensor:
-    """deepv3.py:357 — `torch.add(OCout_dec, dec1)` as one streaming kernel (autograd: identity to both)."""
+def hrfp_plus_add(dec1_up: torch.Tensor, ocout_dec) -> torch.Tensor:
+    """deepv3.py:357 — `torch.add(OCout_dec, dec1)` as one streaming kernel (autograd: identity to both).
+    `ocout_dec` is either the materialised tensor or the `HrfpDec` handle of `hrfp_chain(lazy_dec=True)`."""
+    if isinstance(ocout_dec, HrfpDec):
+        return _PlusAddFusedFn.apply(dec1_up, ocout_dec.token, ocout_dec)
     return _AddFn.apply(dec1_up, ocout_dec)
+
+
+class _PlusAddFusedFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, dec1_up, token, handle):
+        lib = _lib.load()
+        plan = handle.plan
+        if tuple(dec1_up.shape) != tuple(plan.dec_shape) or dec1_up.dtype != torch.float32:
+            raise _lib.MrfpError(f"hrfp_plus_add: dec1 must be fp32 of shape {plan.dec_shape}")
+        a = dec1_up.contiguous()
+        out = torch.empty_like(a)
+        with torch.cuda.device(a.device):
+            rc = lib.mrfp_hrfp_plus_add(plan.handle, handle.saved.data_ptr(), plan.lut.data_ptr(), a.data_ptr(),
+                                        out.data_ptr(), _stream_ptr(a.device))
+        _lib.check(rc, "mrfp_hrfp_plus_add")
+        ctx.mail = handle.mail
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        ctx.mail["g"] = g if ctx.mail["g"] is None else ctx.mail["g"] + g
+        return g, torch.zeros(1, dtype=torch.float32, device=g.device), None
 
 
 class _AddFn(torch.autograd.Function):

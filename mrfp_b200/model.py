@@ -95,7 +95,7 @@ class MRFPMixin:
         if want_out or want_dec:
             convs, bns = self.hrfp_modules()
             out, dec = _hrfp.hrfp_chain(xp, convs, bns, h, w, x_add=x if want_out else None,
-                                        want_out=want_out, want_dec=want_dec, math_mode=self.math_mode)
+                                        want_out=want_out, want_dec=want_dec, math_mode=self.math_mode, lazy_dec=True)
             if want_out:
                 x = out                                                     # OCout + x  (deepv3.py:330)
         elif training and self.strict_buffers:

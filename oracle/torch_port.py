@@ -53,15 +53,16 @@ def hrfp_chain(convs, bns, xp, h, w):
     return o, dec
 
 
-def mrfp_step(convs, bns, xp, feat2, draws, grads, h, w):
-    """One forward+backward pass of the whole MRFP path (both NP+ calls, HRFP, HRFP+ gradient entry)."""
+def mrfp_step(convs, bns, xp, feat2, dec1_up, draws, grads, h, w):
+    """One forward+backward pass of the whole MRFP path: both NP+ calls, the HRFP chain, the HRFP and HRFP+ adds."""
     (a1, e1), (a2, e2) = draws
-    g_x, g_dec, g_f2 = grads
+    g_x, g_d1, g_f2 = grads
     xp = xp.detach().requires_grad_(True)
     feat2 = feat2.detach().requires_grad_(True)
-    x = np_plus(xp, a1, e1)
-    ocout, dec = hrfp_chain(convs, bns, xp, h, w)
+    x = np_plus(xp, a1, e1)                                              # :318
+    ocout, dec = hrfp_chain(convs, bns, xp, h, w)                        # :320-327
     x = ocout + x                                                        # :330
     y2 = np_plus(feat2, a2, e2)                                          # :335
-    torch.autograd.backward([x, dec, y2], [g_x, g_dec, g_f2])
-    return x.detach(), dec.detach(), y2.detach(), xp.grad, feat2.grad
+    d1 = torch.add(dec, dec1_up)                                         # :357
+    torch.autograd.backward([x, d1, y2], [g_x, g_d1, g_f2])
+    return x.detach(), d1.detach(), y2.detach(), xp.grad, feat2.grad

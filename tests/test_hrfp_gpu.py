@@ -147,6 +147,38 @@ def test_plus_add():
     assert torch.equal(a.grad, torch.ones_like(a)) and torch.equal(b.grad, torch.ones_like(b))
 
 
+def test_lazy_dec_handle_matches_materialised_path():
+    """hrfp_plus_add on the HrfpDec handle (OCout_dec never materialised) == add of the materialised tensor,
+    forward and both gradients."""
+    from mrfp_b200.hrfp import hrfp_chain, hrfp_plus_add
+    n, h, w = 2, 48, 48
+    ws, gs = make_hrfp_params(3)
+    xp_np = make_feat(4, (n, 64, 12, 12))
+    res = []
+    for lazy in (False, True):
+        convs, bns = _modules(ws, gs, "cuda")
+        xp = torch.from_numpy(xp_np).cuda().requires_grad_(True)
+        dec1 = torch.from_numpy(np.random.default_rng(5).standard_normal((n, 256, 24, 24)).astype(np.float32)).cuda().requires_grad_(True)
+        out, dec = hrfp_chain(xp, convs, bns, h, w, math_mode=0, lazy_dec=lazy)
+        y = hrfp_plus_add(dec1, dec)
+        g1 = torch.from_numpy(np.random.default_rng(6).standard_normal((n, 64, 12, 12)).astype(np.float32)).cuda()
+        g2 = torch.from_numpy(np.random.default_rng(7).standard_normal((n, 256, 24, 24)).astype(np.float32)).cuda()
+        torch.autograd.backward([out, y], [g1, g2])
+        res.append((y.detach().clone(), xp.grad.clone(), dec1.grad.clone()))
+    for a, b in zip(res[0], res[1]):
+        assert torch.allclose(a, b, rtol=1e-5, atol=1e-5 * a.abs().max().item())
+    # encoder-only chain with the handle (p >= .5, p3 < .5 in the reference's gating)
+    convs, bns = _modules(ws, gs, "cuda")
+    xp = torch.from_numpy(xp_np).cuda().requires_grad_(True)
+    dec1 = torch.zeros(n, 256, 24, 24, device="cuda")
+    out, dec = hrfp_chain(xp, convs, bns, h, w, math_mode=0, want_out=False, want_dec=True, lazy_dec=True)
+    assert out is None
+    y = hrfp_plus_add(dec1, dec)
+    y.backward(g2)
+    assert torch.isfinite(xp.grad).all() and xp.grad.abs().sum() > 0
+    assert int(bns[3].num_batches_tracked) == 1 and int(bns[4].num_batches_tracked) == 0
+
+
 def test_bad_plan_arguments():
     import ctypes
     from mrfp_b200 import _lib
