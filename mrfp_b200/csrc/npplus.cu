@@ -254,10 +254,10 @@ npplus_ring_kernel(const float* __restrict__ x, const float* __restrict__ alpha,
   };
   stamp(0);
   float4* ring = reinterpret_cast<float4*>(smem_raw);                                   // S x 32 KiB
-  double* wp = reinterpret_cast<double*>(smem_raw + (size_t)S * kUnitVecs * 16);        // [S][kWarps]
-  uint64_t* full = reinterpret_cast<uint64_t*>(wp + S * kWarps);                        // [S]
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + (size_t)S * kUnitVecs * 16);  // [S]
   uint64_t* empty = full + S;                                                           // [S]
   float2* coef = reinterpret_cast<float2*>(empty + S);                                  // [max_local_planes]
+  double* wplane = reinterpret_cast<double*>(coef + g.max_local_planes);                // [max_local_planes][kWarps]
   __shared__ NpShared sh;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -266,11 +266,10 @@ npplus_ring_kernel(const float* __restrict__ x, const float* __restrict__ alpha,
   const long long u1 = g.U * (long long)(blockIdx.x + 1) / gridDim.x;
   const int nA = (int)(u1 - u0);
   const int res = nA < S ? nA : S;                       // units resident after phase A
+  const int pl0 = (int)(u0 / g.K), part0 = (int)(u0 % g.K);
+  const int last_len = g.HWV - (g.K - 1) * g.Q;          // the last unit of a plane may be shorter
   const float4* xv = reinterpret_cast<const float4*>(x);
   float4* ov = reinterpret_cast<float4*>(out);
-
-  auto unit_len = [&](long long u) { return min(g.Q, g.HWV - (int)(u % g.K) * g.Q); };
-  auto unit_off = [&](long long u) { return (u / g.K) * (long long)g.HWV + (u % g.K) * (long long)g.Q; };
   auto fills_a = [&](int s) { return s < nA ? (nA - s + S - 1) / S : 0; };   // phase-A fills of slot s
 
   if (tid == 0) {
@@ -280,44 +279,30 @@ npplus_ring_kernel(const float* __restrict__ x, const float* __restrict__ alpha,
   __syncthreads();
 
   // ---------------- phase A ----------------
-  // the producer folds the warp partials of each finished unit, in unit order, into one partial per plane
-  double run_total = 0;
-  const int pl0 = (int)(u0 / g.K);
-  auto fold = [&](int j) {
-    const int s = j % S;
-    double t = 0;
-#pragma unroll
-    for (int w = 0; w < kWarps; ++w) t += wp[s * kWarps + w];
-    run_total += t;
-    const long long u = u0 + j;
-    if ((int)(u % g.K) == g.K - 1 || j == nA - 1) {      // last unit of the plane, or of this CTA's range
-      ps[(long long)blockIdx.x * g.max_local_planes + ((int)(u / g.K) - pl0)] = run_total;
-      run_total = 0;
-    }
-  };
-  uint64_t pol_keep, pol_stream;
-  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol_keep));
-  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol_stream));
+  // All per-unit bookkeeping is incremental 32-bit arithmetic: the single producer thread must stay far ahead
+  // of HBM (a 64-bit division per unit in its loop was enough to make it the bottleneck).
   if (is_producer) {
     if (lane == 0) {
+      uint64_t pol_keep, pol_stream;
+      asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol_keep));
+      asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol_stream));
+      int plane = pl0, part = part0, s = 0, k = 0;
+      const int keep_lo = nA - res - g.keep_units, keep_hi = nA - res;   // re-read from L2 in phase B: keep them there
       for (int j = 0; j < nA; ++j) {
-        const int s = j % S, k = j / S;
-        if (k > 0) {                                   // recycle: all 16 warps released fill k-1 of this slot
-          mbar_wait(&empty[s], (k - 1) & 1);
-          fold(j - S);
-        }
-        const long long u = u0 + j;
-        const uint32_t bytes = (uint32_t)unit_len(u) * 16u;
+        if (k > 0) mbar_wait(&empty[s], (k - 1) & 1);  // all 16 warps released fill k-1 of this slot
+        const uint32_t bytes = (uint32_t)(part == g.K - 1 ? last_len : g.Q) * 16u;
         mbar_expect_tx(&full[s], bytes);
-        // units re-read from L2 in phase B are the newest non-resident ones
-        const bool keep = (j < nA - res) && (j >= nA - res - g.keep_units);
-        bulk_load(ring + (size_t)s * kUnitVecs, xv + unit_off(u), bytes, &full[s], keep ? pol_keep : pol_stream);
+        bulk_load(ring + (size_t)s * kUnitVecs, xv + (long long)plane * g.HWV + part * g.Q, bytes, &full[s],
+                  (j >= keep_lo && j < keep_hi) ? pol_keep : pol_stream);
+        if (++part == g.K) { part = 0; ++plane; }
+        if (++s == S) { s = 0; ++k; }
       }
     }
   } else {
+    int plane = pl0, part = part0, s = 0, k = 0;
+    double run = 0;                                      // lane 0: this warp's running sum of the current plane
     for (int j = 0; j < nA; ++j) {
-      const int s = j % S, k = j / S;
-      const int len = unit_len(u0 + j);
+      const int len = part == g.K - 1 ? last_len : g.Q;
       mbar_wait(&full[s], k & 1);
       const float4* src = ring + (size_t)s * kUnitVecs;
       float acc = 0.f;
@@ -326,17 +311,27 @@ npplus_ring_kernel(const float* __restrict__ x, const float* __restrict__ alpha,
         const int i = tid + b * kConsumers;
         if (i < len) { const float4 v = src[i]; acc += (v.x + v.y) + (v.z + v.w); }
       }
-      const double w = warp_sum((double)acc);
+      run += warp_sum((double)acc);
+      const bool plane_done = part == g.K - 1 || j == nA - 1;
       if (lane == 0) {
-        wp[s * kWarps + warp] = w;
-        if (j < nA - res) mbar_arrive(&empty[s]);      // resident units are released in phase B
+        if (plane_done) { wplane[(plane - pl0) * kWarps + warp] = run; run = 0; }
+        if (j < nA - res) mbar_arrive(&empty[s]);        // resident units are released in phase B
       }
+      if (++part == g.K) { part = 0; ++plane; }
+      if (++s == S) { s = 0; ++k; }
     }
   }
   __syncthreads();
   stamp(1);
-  if (is_producer && lane == 0)                        // partials of the resident units
-    for (int j = nA - res; j < nA; ++j) fold(j);
+  {
+    const int nlp = nA > 0 ? (int)((u1 - 1) / g.K) - pl0 + 1 : 0;       // planes this CTA touched
+    for (int j = tid; j < nlp; j += kConsumers + 32) {
+      double t = 0;
+#pragma unroll
+      for (int w = 0; w < kWarps; ++w) t += wplane[j * kWarps + w];
+      ps[(long long)blockIdx.x * g.max_local_planes + j] = t;
+    }
+  }
   __threadfence();
   cg::this_grid().sync();
   stamp(2);
@@ -351,25 +346,31 @@ npplus_ring_kernel(const float* __restrict__ x, const float* __restrict__ alpha,
   stamp(3);
 
   // ---------------- phase B: newest units first ----------------
+  const int planeL = nA > 0 ? (int)((u1 - 1) / g.K) : pl0, partL = nA > 0 ? (int)((u1 - 1) % g.K) : 0;   // last unit
   if (is_producer) {
-    if (lane == 0) {
-      for (int i = S; i < nA; ++i) {                   // refills (only when nA > S)
-        const int j = nA - 1 - i, s = j % S;
+    if (lane == 0 && nA > S) {
+      uint64_t pol_stream;
+      asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol_stream));
+      // refills start at local unit j = nA-1-S
+      int plane = planeL, part = partL;
+      for (int t = 0; t < S; ++t) { if (--part < 0) { part = g.K - 1; --plane; } }
+      int s = (nA - 1 - S) % S;
+      for (int i = S; i < nA; ++i) {
         const int done = fills_a(s) - 1 + i / S - 1;   // index of the release that frees the slot
         mbar_wait(&empty[s], done & 1);
-        const long long u = u0 + j;
-        const uint32_t bytes = (uint32_t)unit_len(u) * 16u;
+        const uint32_t bytes = (uint32_t)(part == g.K - 1 ? last_len : g.Q) * 16u;
         mbar_expect_tx(&full[s], bytes);
-        bulk_load(ring + (size_t)s * kUnitVecs, xv + unit_off(u), bytes, &full[s], pol_stream);
+        bulk_load(ring + (size_t)s * kUnitVecs, xv + (long long)plane * g.HWV + part * g.Q, bytes, &full[s], pol_stream);
+        if (--part < 0) { part = g.K - 1; --plane; }
+        if (--s < 0) s = S - 1;
       }
     }
   } else {
+    int plane = planeL, part = partL, s = nA > 0 ? (nA - 1) % S : 0;
     for (int i = 0; i < nA; ++i) {
-      const int j = nA - 1 - i, s = j % S;
-      const long long u = u0 + j;
-      const int len = unit_len(u);
+      const int len = part == g.K - 1 ? last_len : g.Q;
       if (i >= S) mbar_wait(&full[s], (fills_a(s) + i / S - 1) & 1);
-      const float2 ab = coef[(int)(u / g.K) - pl0];
+      const float2 ab = coef[plane - pl0];
       const float4* src = ring + (size_t)s * kUnitVecs;
       float4 v[kBatch];
 #pragma unroll
@@ -384,12 +385,14 @@ npplus_ring_kernel(const float* __restrict__ x, const float* __restrict__ alpha,
         __syncwarp();
         if (lane == 0) mbar_arrive(&empty[s]);
       }
-      float4* dst = ov + unit_off(u);
+      float4* dst = ov + (long long)plane * g.HWV + part * g.Q;
 #pragma unroll
       for (int b = 0; b < kBatch; ++b) {
         const int idx = tid + b * kConsumers;
         if (idx < len) st_stream_f4(dst + idx, v[b]);
       }
+      if (--part < 0) { part = g.K - 1; --plane; }
+      if (--s < 0) s = S - 1;
     }
   }
   if (trace) { __syncthreads(); stamp(4); }
@@ -478,14 +481,14 @@ void plan_launch(int N, int C, int HW, bool ring, const DeviceInfo& di, NpLaunch
   const long long upc = (g.U + L->grid - 1) / L->grid;           // units per CTA (max)
   const long long min_upc = g.U / L->grid;                       // ... (min)
   g.max_local_planes = (int)(upc / g.K + 2);
-  const size_t coef_bytes = align_up((size_t)g.max_local_planes * sizeof(float2), 16);
+  const size_t coef_bytes = align_up((size_t)g.max_local_planes * (sizeof(float2) + (ring ? kWarps * sizeof(double) : 0)), 16);
   const size_t fixed = 1024 /* static smem + alignment slack */ + coef_bytes;
   g.grid = L->grid;
   g.per_cta = ring ? 1 : 0;
   g.scratch_off = ring ? (long long)L->grid * g.max_local_planes : g.U;
   g.keep_units = 0;
   if (ring) {
-    const size_t per_slot = (size_t)kUnitVecs * 16 + kWarps * 8 + 16;
+    const size_t per_slot = (size_t)kUnitVecs * 16 + 16;
     long long s = (long long)(((size_t)di.max_smem_optin - fixed) / per_slot);
     if (s > kMaxSlots) s = kMaxSlots;
     if (s > upc) s = upc;
