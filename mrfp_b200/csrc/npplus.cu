@@ -23,6 +23,7 @@
 #include <cooperative_groups.h>
 #include <math.h>
 #include <stdlib.h>
+#include <atomic>
 
 namespace cg = cooperative_groups;
 
@@ -43,11 +44,12 @@ struct NpGeom {
   int HWV;       // HW / VEC
   long long U;   // total units = P*K
   int slots;     // ring slots / resident units per CTA
-  int max_local_planes;
-  int grid;      // CTAs (needed to locate per-CTA plane partials)
-  int per_cta;   // 1: ps[b*max_local_planes + j] = CTA b's partial of its j-th plane; 0: ps[u] per unit
-  int keep_units;  // phase-A units per CTA loaded with an L2 evict_last hint (re-read in phase B)
-  long long scratch_off;   // doubles: ps[0..scratch_off) partials, then pm[P], then chan[4*C]
+  int max_local_planes;   // scalar path: planes a CTA can touch
+  int grid;      // CTAs
+  int keep_units;  // ring path: units (grid-wide) loaded with an L2 evict_last hint because phase B re-reads them
+  long long scratch_off;   // scalar path, doubles: ps[0..scratch_off) partials, then pm[P], then chan[4*C]
+  int grab;      // ring path: units taken from the grid-wide queue per atomic
+  int max_jobs;  // ring path: capacity of a CTA's job list
 };
 
 // ------------------------------------------------------------------------------------------------------
@@ -56,18 +58,8 @@ struct NpGeom {
 // unit partials are written by other CTAs earlier in this launch: read through L2 (ld.global.cg)
 __device__ __forceinline__ double plane_total(const double* ps, int plane, const NpGeom& g) {
   double s = 0;
-  if (g.per_cta) {
-    // CTAs own contiguous unit ranges [U*b/G, U*(b+1)/G): sum the partial of every CTA touching the plane
-    const long long ua = (long long)plane * g.K, ub = ua + g.K - 1;
-    const int b0 = (int)(((ua + 1) * g.grid - 1) / g.U), b1 = (int)(((ub + 1) * g.grid - 1) / g.U);
-    for (int b = b0; b <= b1; ++b) {
-      const int first_plane = (int)((g.U * b / g.grid) / g.K);
-      s += __ldcg(ps + (long long)b * g.max_local_planes + (plane - first_plane));
-    }
-  } else {
 #pragma unroll 4
-    for (int k = 0; k < g.K; ++k) s += __ldcg(ps + (long long)plane * g.K + k);
-  }
+  for (int k = 0; k < g.K; ++k) s += __ldcg(ps + (long long)plane * g.K + k);
   return s;
 }
 
@@ -133,18 +125,10 @@ __device__ void np_stage1(const double* ps, const float* __restrict__ mean_in, c
   }
 }
 
-// Stage 2 (every CTA): global max / arg-max of d and the backward's cross-channel sum, then
-// coef[j] = (a, b) for the planes pl0..pl1 touched by this CTA (one thread per plane).
+// Stage 2a (every CTA): global max / arg-max of d and the backward's cross-channel sum -> sh.dmax, sh.cstar, sh.T
 template <bool BWD>
-__device__ void np_stage2(const double* pm, const double* chan, const float* __restrict__ mean_in,
-                          const float* __restrict__ alpha, const float* __restrict__ eps,
-                          float* __restrict__ mean_out, float* __restrict__ beta_out, const NpGeom& g,
-                          long long u0, long long u1, float2* coef, NpShared& sh, int nthreads) {
+__device__ void np_global_reduce(const double* chan, const NpGeom& g, NpShared& sh, int nthreads) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = nthreads >> 5;
-  const double inv_hw = 1.0 / (double)g.HW;
-  // this CTA's planes: issue their loads first so they overlap the block reduction
-  const int pl0 = (int)(u0 / g.K);
-  const int pl1 = (u1 > u0) ? (int)((u1 - 1) / g.K) : pl0 - 1;
   double best = -1.0, tsum = 0.0;
   int bestc = 0x7fffffff;
   bool anynan = false;
@@ -178,33 +162,38 @@ __device__ void np_stage2(const double* pm, const double* chan, const float* __r
     sh.T = 1.5 * t / (sh.dmax * sh.dmax);     // sum_c dL/ds[c] * 1.5 * d[c] / dmax^2
   }
   __syncthreads();
-  const double dmax = sh.dmax;
-  for (int j = tid; j <= pl1 - pl0; j += nthreads) {
-    const int p = pl0 + j, c = p % g.C;
-    const double tot = __ldcg(pm + p);
-    const double mbar = __ldcg(chan + 4 * c + 0), d = __ldcg(chan + 4 * c + 1);
-    const double a = (double)alpha[p];
-    const double beta = 1.0 + (double)eps[p] * (d / dmax * 1.5);            // deepv3.py:273,275
-    double b;
-    if (!BWD) {
-      const double m = tot * inv_hw;
-      b = (beta - a) * m;                                                   // out = a*x + (beta-a)*m  (:276)
-      if ((long long)p * g.K >= u0) {   // the CTA owning unit 0 of the plane publishes the side outputs
-        mean_out[p] = (float)m;
-        if (beta_out) beta_out[p] = (float)beta;
-      }
-    } else {
-      const double m = (double)mean_in[p];
-      double dLdd = 1.5 / dmax * __ldcg(chan + 4 * c + 2);
-      if (c == sh.cstar) dLdd -= sh.T;
-      // torch's std_backward zero-fills where std == 0
-      const double dd_dm = (d == 0.0) ? 0.0 : (m - mbar) / ((double)(g.N - 1) * d);
-      const double dLdm = (beta - a) * tot + dLdd * dd_dm;
-      b = dLdm * inv_hw;
+}
+
+// Stage 2b: (a, b) of plane p, y = a*x + b.  `publish`: this thread also writes the (N,C) side outputs of the plane.
+template <bool BWD>
+__device__ __forceinline__ float2 np_plane_coef(int p, bool publish, const double* pm, const double* chan,
+                                                const float* __restrict__ mean_in, const float* __restrict__ alpha,
+                                                const float* __restrict__ eps, float* __restrict__ mean_out,
+                                                float* __restrict__ beta_out, const NpGeom& g, const NpShared& sh) {
+  const double inv_hw = 1.0 / (double)g.HW, dmax = sh.dmax;
+  const int c = p % g.C;
+  const double tot = __ldcg(pm + p);
+  const double mbar = __ldcg(chan + 4 * c + 0), d = __ldcg(chan + 4 * c + 1);
+  const double a = (double)alpha[p];
+  const double beta = 1.0 + (double)eps[p] * (d / dmax * 1.5);            // deepv3.py:273,275
+  double b;
+  if (!BWD) {
+    const double m = tot * inv_hw;
+    b = (beta - a) * m;                                                   // out = a*x + (beta-a)*m  (:276)
+    if (publish) {
+      mean_out[p] = (float)m;
+      if (beta_out) beta_out[p] = (float)beta;
     }
-    coef[j] = make_float2((float)a, (float)b);
+  } else {
+    const double m = (double)mean_in[p];
+    double dLdd = 1.5 / dmax * __ldcg(chan + 4 * c + 2);
+    if (c == sh.cstar) dLdd -= sh.T;
+    // torch's std_backward zero-fills where std == 0
+    const double dd_dm = (d == 0.0) ? 0.0 : (m - mbar) / ((double)(g.N - 1) * d);
+    const double dLdm = (beta - a) * tot + dLdd * dd_dm;
+    b = dLdm * inv_hw;
   }
-  __syncthreads();
+  return make_float2((float)a, (float)b);
 }
 
 // ------------------------------------------------------------------------------------------------------
@@ -236,13 +225,24 @@ __device__ __forceinline__ void bulk_load(void* smem_dst, const void* gsrc, uint
 }
 
 // ------------------------------------------------------------------------------------------------------
-// TMA-ring kernel (planes and base addresses 16-byte aligned)
+// TMA-ring kernel with a grid-wide dynamic unit queue (planes and base addresses 16-byte aligned)
 // ------------------------------------------------------------------------------------------------------
+// SMs do not stream from HBM at the same rate (the slowest took 40 % longer than the fastest on a static
+// split), so units are handed out from an atomic counter in batches of g.grab; every CTA remembers its jobs in
+// order and replays them backwards in phase B.  The counter is (re)initialised by CTA 0 of each launch and
+// published with a per-launch nonce, so the workspace needs no host-side clearing.
+struct NpCtrl {
+  unsigned long long nonce;
+  unsigned int counter;
+  unsigned int pad[13];
+};
+
 template <bool BWD>
 __global__ void __launch_bounds__(kConsumers + 32, 1)
 npplus_ring_kernel(const float* __restrict__ x, const float* __restrict__ alpha, const float* __restrict__ eps,
                    const float* __restrict__ mean_in, float* __restrict__ out, float* __restrict__ mean_out,
-                   float* __restrict__ beta_out, double* ps, const NpGeom g, unsigned long long* trace) {
+                   float* __restrict__ beta_out, unsigned char* ws, const NpGeom g, unsigned long long nonce,
+                   unsigned long long* trace) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int S = g.slots;
   auto stamp = [&](int i) {
@@ -256,54 +256,84 @@ npplus_ring_kernel(const float* __restrict__ x, const float* __restrict__ alpha,
   float4* ring = reinterpret_cast<float4*>(smem_raw);                                   // S x 32 KiB
   uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + (size_t)S * kUnitVecs * 16);  // [S]
   uint64_t* empty = full + S;                                                           // [S]
-  float2* coef = reinterpret_cast<float2*>(empty + S);                                  // [max_local_planes]
-  double* wplane = reinterpret_cast<double*>(coef + g.max_local_planes);                // [max_local_planes][kWarps]
+  float2* coefj = reinterpret_cast<float2*>(empty + S);                                 // [max_jobs]
+  int* joblist = reinterpret_cast<int*>(coefj + g.max_jobs);                            // [max_jobs]
   __shared__ NpShared sh;
+
+  NpCtrl* ctrl = reinterpret_cast<NpCtrl*>(ws);
+  double* ps = reinterpret_cast<double*>(ws + sizeof(NpCtrl));      // [U] unit partials
+  double* pm = ps + g.U;                                            // [P] plane totals
+  double* chan = pm + g.P;                                          // [4C] channel statistics
+  double* wpg = chan + 4 * g.C + (size_t)blockIdx.x * g.max_jobs * kWarps;   // [max_jobs][kWarps] warp partials of this CTA
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const bool is_producer = warp == kWarps;
-  const long long u0 = g.U * (long long)blockIdx.x / gridDim.x;
-  const long long u1 = g.U * (long long)(blockIdx.x + 1) / gridDim.x;
-  const int nA = (int)(u1 - u0);
-  const int res = nA < S ? nA : S;                       // units resident after phase A
-  const int pl0 = (int)(u0 / g.K), part0 = (int)(u0 % g.K);
+  const int U = (int)g.U;
   const int last_len = g.HWV - (g.K - 1) * g.Q;          // the last unit of a plane may be shorter
   const float4* xv = reinterpret_cast<const float4*>(x);
   float4* ov = reinterpret_cast<float4*>(out);
-  auto fills_a = [&](int s) { return s < nA ? (nA - s + S - 1) / S : 0; };   // phase-A fills of slot s
 
   if (tid == 0) {
     for (int s = 0; s < S; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], kWarps); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    if (blockIdx.x == 0) {                               // open this launch's queue: the first batches are static
+      ctrl->counter = gridDim.x * g.grab;
+      __threadfence();
+      *reinterpret_cast<volatile unsigned long long*>(&ctrl->nonce) = nonce;
+    }
   }
   __syncthreads();
 
   // ---------------- phase A ----------------
-  // All per-unit bookkeeping is incremental 32-bit arithmetic: the single producer thread must stay far ahead
-  // of HBM (a 64-bit division per unit in its loop was enough to make it the bottleneck).
+  int nA = 0;                                            // jobs taken by this CTA (known after the loop)
   if (is_producer) {
     if (lane == 0) {
       uint64_t pol_keep, pol_stream;
       asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol_keep));
       asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol_stream));
-      int plane = pl0, part = part0, s = 0, k = 0;
-      const int keep_lo = nA - res - g.keep_units, keep_hi = nA - res;   // re-read from L2 in phase B: keep them there
-      for (int j = 0; j < nA; ++j) {
-        if (k > 0) mbar_wait(&empty[s], (k - 1) & 1);  // all 16 warps released fill k-1 of this slot
-        const uint32_t bytes = (uint32_t)(part == g.K - 1 ? last_len : g.Q) * 16u;
-        mbar_expect_tx(&full[s], bytes);
-        bulk_load(ring + (size_t)s * kUnitVecs, xv + (long long)plane * g.HWV + part * g.Q, bytes, &full[s],
-                  (j >= keep_lo && j < keep_hi) ? pol_keep : pol_stream);
-        if (++part == g.K) { part = 0; ++plane; }
-        if (++s == S) { s = 0; ++k; }
+      // the globally last units are the ones re-read in phase B: the newest S per CTA stay in shared memory, the
+      // g.keep_units before them are asked to stay in L2
+      const int keep_hi = U - (int)gridDim.x * S, keep_lo = keep_hi - g.keep_units;
+      int j = 0, s = 0, k = 0;
+      unsigned base = blockIdx.x * g.grab, nbase = 0;
+      bool open = blockIdx.x == 0, have_next = false;
+      while (base < (unsigned)U && j < g.max_jobs - 1) {
+        if (!have_next && j + 2 * g.grab < g.max_jobs - 1) {          // fetch the next batch while this one streams
+          if (!open) {
+            while (*reinterpret_cast<volatile unsigned long long*>(&ctrl->nonce) != nonce) {}
+            __threadfence();
+            open = true;
+          }
+          nbase = atomicAdd(&ctrl->counter, (unsigned)g.grab);
+          have_next = true;
+        }
+        for (int q = 0; q < g.grab && base + q < (unsigned)U && j < g.max_jobs - 1; ++q) {
+          const int u = (int)base + q;
+          if (k > 0) mbar_wait(&empty[s], (k - 1) & 1);  // all 16 warps released fill k-1 of this slot
+          const int plane = u / g.K, part = u - plane * g.K;
+          const uint32_t bytes = (uint32_t)(part == g.K - 1 ? last_len : g.Q) * 16u;
+          joblist[j] = u;
+          mbar_expect_tx(&full[s], bytes);
+          bulk_load(ring + (size_t)s * kUnitVecs, xv + (long long)plane * g.HWV + part * g.Q, bytes, &full[s],
+                    (u >= keep_lo && u < keep_hi) ? pol_keep : pol_stream);
+          ++j;
+          if (++s == S) { s = 0; ++k; }
+        }
+        if (!have_next) break;
+        base = nbase; have_next = false;
       }
+      if (k > 0) mbar_wait(&empty[s], (k - 1) & 1);
+      joblist[j] = -1;                                   // end marker: completes one phase of full[s] without data
+      mbar_arrive(&full[s]);
     }
   } else {
-    int plane = pl0, part = part0, s = 0, k = 0;
-    double run = 0;                                      // lane 0: this warp's running sum of the current plane
-    for (int j = 0; j < nA; ++j) {
-      const int len = part == g.K - 1 ? last_len : g.Q;
+    int s = 0, k = 0;
+    for (;; ++nA) {
       mbar_wait(&full[s], k & 1);
+      const int u = joblist[nA];
+      if (u < 0) break;
+      const int plane = u / g.K, part = u - plane * g.K;
+      const int len = part == g.K - 1 ? last_len : g.Q;
       const float4* src = ring + (size_t)s * kUnitVecs;
       float acc = 0.f;
 #pragma unroll
@@ -311,66 +341,67 @@ npplus_ring_kernel(const float* __restrict__ x, const float* __restrict__ alpha,
         const int i = tid + b * kConsumers;
         if (i < len) { const float4 v = src[i]; acc += (v.x + v.y) + (v.z + v.w); }
       }
-      run += warp_sum((double)acc);
-      const bool plane_done = part == g.K - 1 || j == nA - 1;
+      const double w = warp_sum((double)acc);
       if (lane == 0) {
-        if (plane_done) { wplane[(plane - pl0) * kWarps + warp] = run; run = 0; }
-        if (j < nA - res) mbar_arrive(&empty[s]);        // resident units are released in phase B
+        wpg[nA * kWarps + warp] = w;
+        mbar_arrive(&empty[s]);                          // always released; the last S fills simply stay in the ring
       }
-      if (++part == g.K) { part = 0; ++plane; }
       if (++s == S) { s = 0; ++k; }
     }
   }
+  if (tid == 0) sh.cstar = nA;                           // publish the job count to the producer warp
+  __syncthreads();
+  nA = sh.cstar;
   __syncthreads();
   stamp(1);
-  {
-    const int nlp = nA > 0 ? (int)((u1 - 1) / g.K) - pl0 + 1 : 0;       // planes this CTA touched
-    for (int j = tid; j < nlp; j += kConsumers + 32) {
-      double t = 0;
+  for (int j = tid; j < nA; j += kConsumers + 32) {      // fold the 16 warp partials of each unit, fixed order
+    double t = 0;
 #pragma unroll
-      for (int w = 0; w < kWarps; ++w) t += wplane[j * kWarps + w];
-      ps[(long long)blockIdx.x * g.max_local_planes + j] = t;
-    }
+    for (int w = 0; w < kWarps; ++w) t += __ldcg(wpg + j * kWarps + w);
+    ps[joblist[j]] = t;
   }
   __threadfence();
   cg::this_grid().sync();
   stamp(2);
 
   // ---------------- statistics ----------------
-  double* pm = ps + g.scratch_off;
-  double* chan = pm + g.P;
   np_stage1<BWD>(ps, mean_in, eps, g, pm, chan, kConsumers + 32);
   __threadfence();
   cg::this_grid().sync();
-  np_stage2<BWD>(pm, chan, mean_in, alpha, eps, mean_out, beta_out, g, u0, u1, coef, sh, kConsumers + 32);
+  np_global_reduce<BWD>(chan, g, sh, kConsumers + 32);
+  for (int j = tid; j < nA; j += kConsumers + 32) {
+    const int u = joblist[j], plane = u / g.K;
+    coefj[j] = np_plane_coef<BWD>(plane, u - plane * g.K == 0, pm, chan, mean_in, alpha, eps, mean_out, beta_out, g, sh);
+  }
+  __syncthreads();
   stamp(3);
 
-  // ---------------- phase B: newest units first ----------------
-  const int planeL = nA > 0 ? (int)((u1 - 1) / g.K) : pl0, partL = nA > 0 ? (int)((u1 - 1) % g.K) : 0;   // last unit
+  // ---------------- phase B: this CTA's jobs, newest first ----------------
+  const int s_end = nA % S;                              // the slot whose full barrier took the end-marker arrive
+  auto fills_a = [&](int s) { return (s < nA ? (nA - s + S - 1) / S : 0); };   // phase-A data fills of slot s
   if (is_producer) {
     if (lane == 0 && nA > S) {
       uint64_t pol_stream;
       asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol_stream));
-      // refills start at local unit j = nA-1-S
-      int plane = planeL, part = partL;
-      for (int t = 0; t < S; ++t) { if (--part < 0) { part = g.K - 1; --plane; } }
       int s = (nA - 1 - S) % S;
-      for (int i = S; i < nA; ++i) {
-        const int done = fills_a(s) - 1 + i / S - 1;   // index of the release that frees the slot
-        mbar_wait(&empty[s], done & 1);
+      for (int i = S; i < nA; ++i) {                     // refill with job nA-1-i once job nA-1-(i-S) left the slot
+        const int u = joblist[nA - 1 - i];
+        mbar_wait(&empty[s], (fills_a(s) + i / S - 1) & 1);
+        const int plane = u / g.K, part = u - plane * g.K;
         const uint32_t bytes = (uint32_t)(part == g.K - 1 ? last_len : g.Q) * 16u;
         mbar_expect_tx(&full[s], bytes);
         bulk_load(ring + (size_t)s * kUnitVecs, xv + (long long)plane * g.HWV + part * g.Q, bytes, &full[s], pol_stream);
-        if (--part < 0) { part = g.K - 1; --plane; }
         if (--s < 0) s = S - 1;
       }
     }
   } else {
-    int plane = planeL, part = partL, s = nA > 0 ? (nA - 1) % S : 0;
+    int s = nA > 0 ? (nA - 1) % S : 0;
     for (int i = 0; i < nA; ++i) {
+      const int j = nA - 1 - i, u = joblist[j];
+      const int plane = u / g.K, part = u - plane * g.K;
       const int len = part == g.K - 1 ? last_len : g.Q;
-      if (i >= S) mbar_wait(&full[s], (fills_a(s) + i / S - 1) & 1);
-      const float2 ab = coef[plane - pl0];
+      if (i >= S) mbar_wait(&full[s], (fills_a(s) + (s == s_end ? 1 : 0) + i / S - 1) & 1);
+      const float2 ab = coefj[j];
       const float4* src = ring + (size_t)s * kUnitVecs;
       float4 v[kBatch];
 #pragma unroll
@@ -381,17 +412,14 @@ npplus_ring_kernel(const float* __restrict__ x, const float* __restrict__ alpha,
           v[b] = make_float4(fmaf(ab.x, t.x, ab.y), fmaf(ab.x, t.y, ab.y), fmaf(ab.x, t.z, ab.y), fmaf(ab.x, t.w, ab.y));
         }
       }
-      if (i + S < nA) {                                // slot will be refilled: release it
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&empty[s]);
-      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty[s]);
       float4* dst = ov + (long long)plane * g.HWV + part * g.Q;
 #pragma unroll
       for (int b = 0; b < kBatch; ++b) {
         const int idx = tid + b * kConsumers;
         if (idx < len) st_stream_f4(dst + idx, v[b]);
       }
-      if (--part < 0) { part = g.K - 1; --plane; }
       if (--s < 0) s = S - 1;
     }
   }
@@ -447,8 +475,15 @@ npplus_scalar_kernel(const float* __restrict__ x, const float* __restrict__ alph
   np_stage1<BWD>(ps, mean_in, eps, g, pm, chan, kConsumers);
   __threadfence();
   cg::this_grid().sync();
-  np_stage2<BWD>(pm, chan, mean_in, alpha, eps, mean_out, beta_out, g, u0, u1, coef, sh, kConsumers);
+  np_global_reduce<BWD>(chan, g, sh, kConsumers);
   const int pl0 = (int)(u0 / g.K);
+  {
+    const int pl1 = (u1 > u0) ? (int)((u1 - 1) / g.K) : pl0 - 1;
+    for (int j = tid; j <= pl1 - pl0; j += kConsumers)   // the CTA owning unit 0 of a plane publishes its side outputs
+      coef[j] = np_plane_coef<BWD>(pl0 + j, (long long)(pl0 + j) * g.K >= u0, pm, chan, mean_in, alpha, eps, mean_out,
+                                   beta_out, g, sh);
+    __syncthreads();
+  }
   for (long long u = u1 - 1; u >= u0; --u) {
     const int len = unit_len(u);
     const float2 ab = coef[(int)(u / g.K) - pl0];
@@ -469,6 +504,16 @@ struct NpLaunch {
   size_t smem;
 };
 
+// workspace layout (bytes): [NpCtrl 64][ps: units][pm: P][chan: 4C][ring path: per-CTA warp partials]
+size_t ws_layout_bytes(int N, int C, int HW) {
+  const long long P = (long long)N * C;
+  const long long u_scalar = P * (((long long)HW + kUnitVecs - 1) / kUnitVecs);                 // 2048 floats per unit
+  const long long u_ring = P * (((long long)HW / 4 + kUnitVecs - 1) / kUnitVecs + 1);           // 2048 float4 per unit
+  const long long units = u_scalar > u_ring ? u_scalar : u_ring;
+  const long long jobs = 2 * u_ring + 32LL * 1024;       // sum over CTAs of max_jobs (<= 2*upc + 24 each, <= 1024 CTAs)
+  return (size_t)(sizeof(NpCtrl) + 8 * (units + P + 4LL * C + jobs * kWarps));
+}
+
 void plan_launch(int N, int C, int HW, bool ring, const DeviceInfo& di, NpLaunch* L) {
   NpGeom& g = L->g;
   const int vec = ring ? 4 : 1;
@@ -478,35 +523,41 @@ void plan_launch(int N, int C, int HW, bool ring, const DeviceInfo& di, NpLaunch
   g.K = (g.HWV + g.Q - 1) / g.Q;                                 // last unit of a plane may be shorter
   g.U = (long long)g.P * g.K;
   L->grid = (int)((g.U < di.sm_count) ? g.U : di.sm_count);
-  const long long upc = (g.U + L->grid - 1) / L->grid;           // units per CTA (max)
+  g.grid = L->grid;
+  const long long upc = (g.U + L->grid - 1) / L->grid;           // units per CTA (static split: max)
   const long long min_upc = g.U / L->grid;                       // ... (min)
   g.max_local_planes = (int)(upc / g.K + 2);
-  const size_t coef_bytes = align_up((size_t)g.max_local_planes * (sizeof(float2) + (ring ? kWarps * sizeof(double) : 0)), 16);
-  const size_t fixed = 1024 /* static smem + alignment slack */ + coef_bytes;
-  g.grid = L->grid;
-  g.per_cta = ring ? 1 : 0;
-  g.scratch_off = ring ? (long long)L->grid * g.max_local_planes : g.U;
-  g.keep_units = 0;
+  g.scratch_off = g.U;
+  g.keep_units = 0; g.grab = 1; g.max_jobs = 0;
+  const size_t slack = 1024;                                     // static smem + alignment
   if (ring) {
+    long long grab = upc / 8;
+    g.grab = (int)(grab < 1 ? 1 : (grab > 4 ? 4 : grab));
+    g.max_jobs = (int)(2 * upc + 4 * g.grab + 8);
+    const size_t tables = align_up((size_t)g.max_jobs * (sizeof(float2) + sizeof(int)), 16);
     const size_t per_slot = (size_t)kUnitVecs * 16 + 16;
-    long long s = (long long)(((size_t)di.max_smem_optin - fixed) / per_slot);
+    long long s = (long long)(((size_t)di.max_smem_optin - slack - tables) / per_slot);
     if (s > kMaxSlots) s = kMaxSlots;
     if (s > upc) s = upc;
     if (s < 1) s = 1;
     g.slots = (int)s;
-    L->smem = (size_t)g.slots * per_slot + coef_bytes;
+    L->smem = (size_t)g.slots * per_slot + tables;
     // L2 share reserved for phase-B re-reads (MRFP_NPPLUS_KEEP_MB overrides; default 64 MiB)
     static const long long keep_mb = getenv("MRFP_NPPLUS_KEEP_MB") ? atoll(getenv("MRFP_NPPLUS_KEEP_MB")) : 64;
-    long long ku = (keep_mb << 20) / ((long long)L->grid * kUnitVecs * 16);
-    if (ku > upc) ku = upc;
-    g.keep_units = (int)ku;
+    g.keep_units = (int)((keep_mb << 20) / ((long long)kUnitVecs * 16));
   } else {
+    const size_t coef_bytes = align_up((size_t)g.max_local_planes * sizeof(float2), 16);
     const size_t unit_bytes = (size_t)g.Q * 4;
-    long long s = (long long)(((size_t)di.max_smem_optin - fixed) / unit_bytes);
+    long long s = (long long)(((size_t)di.max_smem_optin - slack - coef_bytes) / unit_bytes);
     if (s > min_upc) s = min_upc;   // the resident window must not start before u0
     g.slots = (int)s;
     L->smem = align_up((size_t)g.slots * unit_bytes, 16) + coef_bytes;
   }
+}
+
+unsigned long long next_nonce() {
+  static std::atomic<unsigned long long> counter{0x9E3779B97F4A7C15ull};
+  return counter.fetch_add(0x9E3779B97F4A7C15ull) | 1ull;       // never 0, never repeats within a process
 }
 
 template <bool BWD>
@@ -514,26 +565,36 @@ int run(const float* x, const float* alpha, const float* eps, const float* mean_
         float* beta_out, void* ws, size_t ws_bytes, int N, int C, int HW, void* stream) {
   if (!x || !alpha || !eps || !out || !ws || (BWD && !mean_in) || (!BWD && !mean_out)) return MRFP_ERR_NULL_POINTER;
   if (N <= 0 || C <= 0 || HW <= 0 || (long long)N * C > (1 << 24)) return MRFP_ERR_BAD_SHAPE;
-  if (ws_bytes < mrfp_npplus_ws_bytes(N, C, HW) || ((uintptr_t)ws & 7)) return MRFP_ERR_WORKSPACE;
+  if (ws_bytes < mrfp_npplus_ws_bytes(N, C, HW) || ((uintptr_t)ws & 15)) return MRFP_ERR_WORKSPACE;
   DeviceInfo di;
   int rc = get_device_info(&di);
   if (rc) return rc;
   const bool ring = (HW % 4 == 0) && (((uintptr_t)x | (uintptr_t)out) & 15) == 0;
   NpLaunch L;
   plan_launch(N, C, HW, ring, di, &L);
+  if (ring && L.g.U >= (1LL << 31)) return MRFP_ERR_BAD_SHAPE;
   NpGeom g = L.g;
-  double* ps = (double*)ws;
   // debug: MRFP_NPPLUS_TRACE=1 and a workspace with room for grid*8 extra u64 -> per-CTA phase timestamps
   static const bool want_trace = getenv("MRFP_NPPLUS_TRACE") != nullptr;
   const size_t base = align_up(mrfp_npplus_ws_bytes(N, C, HW), 8);
   unsigned long long* trace = nullptr;
   if (want_trace && ws_bytes >= base + (size_t)L.grid * 64) trace = (unsigned long long*)((char*)ws + base);
-  void* args[] = {(void*)&x, (void*)&alpha, (void*)&eps, (void*)&mean_in, (void*)&out,
-                  (void*)&mean_out, (void*)&beta_out, (void*)&ps, (void*)&g, (void*)&trace};
-  void* kern = ring ? (void*)npplus_ring_kernel<BWD> : (void*)npplus_scalar_kernel<BWD>;
-  MRFP_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.smem));
-  MRFP_CUDA_TRY(cudaLaunchCooperativeKernel(kern, dim3(L.grid), dim3(ring ? kConsumers + 32 : kConsumers), args,
-                                            L.smem, (cudaStream_t)stream));
+  if (ring) {
+    unsigned char* wsb = (unsigned char*)ws;
+    unsigned long long nonce = next_nonce();
+    void* args[] = {(void*)&x, (void*)&alpha, (void*)&eps, (void*)&mean_in, (void*)&out, (void*)&mean_out,
+                    (void*)&beta_out, (void*)&wsb, (void*)&g, (void*)&nonce, (void*)&trace};
+    void* kern = (void*)npplus_ring_kernel<BWD>;
+    MRFP_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.smem));
+    MRFP_CUDA_TRY(cudaLaunchCooperativeKernel(kern, dim3(L.grid), dim3(kConsumers + 32), args, L.smem, (cudaStream_t)stream));
+  } else {
+    double* ps = (double*)((char*)ws + sizeof(NpCtrl));
+    void* args[] = {(void*)&x, (void*)&alpha, (void*)&eps, (void*)&mean_in, (void*)&out,
+                    (void*)&mean_out, (void*)&beta_out, (void*)&ps, (void*)&g, (void*)&trace};
+    void* kern = (void*)npplus_scalar_kernel<BWD>;
+    MRFP_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.smem));
+    MRFP_CUDA_TRY(cudaLaunchCooperativeKernel(kern, dim3(L.grid), dim3(kConsumers), args, L.smem, (cudaStream_t)stream));
+  }
   return MRFP_OK;
 }
 
@@ -542,11 +603,7 @@ int run(const float* x, const float* alpha, const float* eps, const float* mean_
 
 extern "C" size_t mrfp_npplus_ws_bytes(int N, int C, int HW) {
   if (N <= 0 || C <= 0 || HW <= 0) return 0;
-  // one double per unit; the scalar path (2048 floats per unit) has the most units per plane
-  const long long per_plane = ((long long)HW + mrfp::kUnitVecs - 1) / mrfp::kUnitVecs + 1;
-  // partials: per unit (scalar path) or per (CTA, local plane) <= planes + 2 per CTA, CTAs <= 1024 (ring path);
-  // then the plane totals pm[P] and the channel statistics chan[4*C]
-  return (size_t)(((long long)N * C * (per_plane + 1) + 4 * 1024 + 4LL * C) * 8);
+  return mrfp::ws_layout_bytes(N, C, HW);
 }
 
 extern "C" int mrfp_npplus_fwd_f32(const float* x, const float* alpha, const float* eps, float* out, float* mean,
