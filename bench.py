@@ -97,14 +97,20 @@ class ClockSampler(threading.Thread):
     def __init__(self, index):
         super().__init__(daemon=True)
         self.index, self.rows, self.stop_flag, self.err = index, [], False, None
-        self.max_mhz = None
+        self.max_mhz, self.nv, self.h = None, None, None
+        try:                              # NVML start-up takes longer than a short timed region: do it up front
+            import pynvml as nv
+            nv.nvmlInit()
+            self.nv, self.h = nv, nv.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = nv.nvmlDeviceGetMaxClockInfo(self.h, nv.NVML_CLOCK_SM)
+        except Exception as e:          # noqa: BLE001
+            self.err = repr(e)
 
     def run(self):
         try:
-            import pynvml as nv
-            nv.nvmlInit()
-            h = nv.nvmlDeviceGetHandleByIndex(self.index)
-            self.max_mhz = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+            nv, h = self.nv, self.h
+            if nv is None:
+                return
             while not self.stop_flag:
                 self.rows.append((nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM),
                                   nv.nvmlDeviceGetCurrentClocksEventReasons(h) if hasattr(nv, "nvmlDeviceGetCurrentClocksEventReasons")
@@ -121,6 +127,96 @@ class ClockSampler(threading.Thread):
                 "hw_power_brake_slowdown": 0x80}
         reasons = [n for n, b in bits.items() if any(r[1] & b for r in self.rows)]
         return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": self.max_mhz, "reasons": reasons, "samples": len(self.rows)}
+
+
+def _use_reference_ops(model):
+    """Swap the three MRFP insertion points of `model` for the reference's own op sequence (eager ATen / cuDNN on the
+    GPU, deepv3.py:268-277 and :320-330, :357) — the practical bar the kernels must beat inside a training step."""
+    import math
+    import torch
+    import torch.nn.functional as F
+    from mrfp_b200 import hrfp as H
+
+    def np_eager(feat):
+        m = feat.mean((2, 3), keepdim=True)
+        d = torch.std(m, 0, keepdim=True)
+        s = d / d.max() * 1.5
+        a = torch.normal(torch.ones_like(m), 0.75 * torch.ones_like(m))
+        b = 1 + torch.normal(torch.zeros_like(m), 0.75 * torch.ones_like(m)) * s
+        return a * feat - a * m + b * m
+
+    def stem(xp, h, w, training, p, p2, p3):
+        c, b = model.hrfp_modules()
+        x = np_eager(xp) if (training and p2 < 0.5) else xp
+        o = F.relu(b[0](F.interpolate(c[0](xp), scale_factor=(1.205, 1.205))))
+        o = F.relu(b[1](F.interpolate(c[1](o), scale_factor=(1.2, 1.2))))
+        o = F.relu(b[2](F.interpolate(c[2](o), scale_factor=(1.2, 1.2))))
+        dec = F.relu(b[3](F.interpolate(c[3](o), size=(int(h / 2), int(w / 2)))))
+        o = F.relu(b[4](F.interpolate(c[4](dec), size=(int(h / 2), int(w / 2)))))
+        o = F.relu(b[5](F.interpolate(c[5](o), scale_factor=(0.838, 0.838))))
+        o = F.relu(b[6](F.interpolate(c[6](o), scale_factor=(0.798, 0.798))))
+        o = F.relu(b[7](F.interpolate(c[7](o), size=(math.ceil(h / 4), math.ceil(w / 4)))))
+        if training and p < 0.5:
+            x = torch.add(o, x)
+        return x, dec
+
+    model.Normalization_Perturbation_Plus = np_eager
+    model.mrfp_stem = stem
+    model._plus_add = lambda a, d: torch.add(d, a)
+
+
+def train_bench(world, rank, dev, steps=8, warmup=3, global_batch=16, reference_ops=False):
+    """BASELINE config[2]: MRFP+ DeepLabV3+/ResNet-50 training step (main.py:845-871 recipe) on synthetic GTAV-shaped
+    768x768 crops, 19 classes, global batch 16 sharded over the ranks (DDP, NCCL gradient all-reduce is the only
+    collective; BatchNorm stays per-rank)."""
+    import random
+    import torch
+    import torch.distributed as dist
+    from mrfp_b200.model import MRFPPlus
+    from mrfp_b200 import dist as D
+    lo, hi = D.shard_bounds(global_batch, world, rank)
+    nb = hi - lo
+    D.seed_rank_streams(3, rank)
+    random.seed(100 + rank)
+    model = MRFPPlus(19, criterion=torch.nn.CrossEntropyLoss(ignore_index=255)).to(dev)
+    if reference_ops:
+        _use_reference_ops(model)
+    if world > 1:
+        for p_ in model.parameters():                       # same start on every rank (DDP would broadcast rank 0 anyway)
+            dist.broadcast(p_.data, 0)
+        model = torch.nn.parallel.DistributedDataParallel(model, device_ids=[dev.index], broadcast_buffers=False)
+    opt = torch.optim.SGD([p_ for p_ in model.parameters() if p_.requires_grad], lr=1e-2, momentum=0.9, weight_decay=5e-4)
+    img = torch.rand(nb, 3, H_IMG, W_IMG, device=dev) * 255.0       # the reference feeds un-normalised pixels
+    lab = torch.randint(0, 19, (nb, H_IMG, W_IMG), device=dev)
+    lab[torch.rand(nb, H_IMG, W_IMG, device=dev) < 0.05] = 255
+
+    def one():
+        opt.zero_grad(set_to_none=True)
+        loss = model(img, lab, training=True)
+        loss.backward()
+        opt.step()
+        return loss
+
+    for _ in range(warmup):
+        one()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        loss = one()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = D.max_over_ranks(e0.elapsed_time(e1), dev)
+    out = {"metric": "deeplabv3plus_r50_mrfp_plus_train_throughput", "mrfp_ops": "reference eager ATen/cuDNN" if reference_ops else "libmrfp_b200", "value": global_batch * steps / (ms * 1e-3), "unit": "img/s",
+           "global_batch": global_batch, "per_gpu_batch": nb, "steps": steps, "warmup": warmup, "ms_per_step": ms / steps,
+           "parallelism": f"ddp{world}", "loss_finite": bool(torch.isfinite(loss).item()),
+           "precision": "fp32 host model (cuDNN TF32 default, as the reference on this torch), bf16 tcgen05 HRFP, fp32 NP+",
+           "gates": "natural Bernoulli(0.5) x3 per step (python random, seed 100+rank)", "data": "synthetic U[0,255) images, 19 classes, 5% ignore"}
+    del model, opt, img, lab
+    torch.cuda.empty_cache()
+    return out
 
 
 def run_ours(args):
@@ -232,6 +328,18 @@ def run_ours(args):
         dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
     e2e_value = world * n * e2e_steps / (float(ms2.item()) * 1e-3)
 
+    # ---- BASELINE config[2]: the training step that hosts the path (all ranks) ----
+    train = None
+    if os.environ.get("MRFP_BENCH_TRAIN", "1") != "0":
+        del host_in, host_out, dev_in, outs
+        torch.cuda.empty_cache()
+        try:
+            train = train_bench(world, rank, dev)
+            ref_t = train_bench(world, rank, dev, steps=4, warmup=2, reference_ops=True)
+            train["same_step_with_reference_mrfp_ops"] = {k: ref_t[k] for k in ("value", "unit", "ms_per_step", "steps", "mrfp_ops")}
+        except Exception as e:          # noqa: BLE001  (e.g. out of memory on a smaller GPU): report, do not hide
+            train = {"error": repr(e)[:300]}
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -340,7 +448,7 @@ def run_ours(args):
             "dtype": "bf16 (HRFP tensor-core operands, fp32 accumulate) / f32 (NP+)", "data": "synthetic", "config": CONFIG,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps},
             "gpu_launches": launches_per_step * args.steps,
-            "roofline": roofline, "roofline_npplus": roof_np, "hrfp_chain": hrfp,
+            "roofline": roofline, "roofline_npplus": roof_np, "hrfp_chain": hrfp, "train": train,
             "clocks": sampler.summary() if sampler else None}
     if base is not None:
         line["cpu_baseline"] = base

@@ -84,6 +84,10 @@ class MRFPMixin:
         """deepv3.py:268-277 on the fused NP+ kernels."""
         return _npplus.normalization_perturbation_plus(feat)
 
+    def _plus_add(self, dec1_up, ocout_dec):
+        """Insertion point 3 (deepv3.py:357)."""
+        return _hrfp.hrfp_plus_add(dec1_up, ocout_dec)
+
     def mrfp_stem(self, xp, h, w, training, p, p2, p3):
         """Insertion point 1 (deepv3.py:316-330).  Returns (x, OCout_dec or None)."""
         x = xp
@@ -226,7 +230,7 @@ class MRFPPlus(nn.Module, MRFPMixin):
         dec1 = self.final1(dec0)
         if training and p3 < 0.5:                                           # deepv3.py:355-357
             dec1 = upsample_bilinear(dec1, (int(h / 2), int(w / 2)))
-            dec1 = _hrfp.hrfp_plus_add(dec1, ocout_dec)
+            dec1 = self._plus_add(dec1, ocout_dec)
         main_out = upsample_bilinear(self.final2(dec1), (h, w))
         if training:
             return self.criterion(main_out, gts)
