@@ -3,19 +3,19 @@
 //
 // Both directions are the same memory-bound shape:  y = a[n,c] * x + b[n,c]  where (a, b) depend on the
 // plane sums of x for ALL planes of the local batch (batch std of the plane means + global channel max).
-// One cooperative persistent kernel, one CTA per SM, each CTA owning a contiguous range of "units"
-// (a unit = <= 32 KiB slice of one plane):
-//   phase A  a producer thread streams the units into a shared-memory ring with 1-D TMA bulk copies
+// One cooperative persistent kernel, one CTA per SM, work in "units" (a unit = <= 32 KiB slice of one plane):
+//   phase A  a producer thread streams units into a shared-memory ring with 1-D TMA bulk copies
 //            (cp.async.bulk + mbarrier complete_tx); 16 consumer warps reduce each unit from shared memory
-//            (128-bit LDS, fp32 lane partials, double warp-shuffle tree); the producer folds the 16 warp
-//            partials of a unit when it recycles the slot.  The LAST units of the range stay resident in the
-//            ring (up to 7 x 32 KiB per SM);
+//            (128-bit LDS, fp32 lane partials, double warp-shuffle tree); the last warp to finish a unit folds the
+//            16 warp partials in fixed order.  Units come from a grid-wide atomic queue, framed by two static
+//            sets per CTA that STAY ON CHIP: a head of up to 8 units parked in tensor memory (TMEM is otherwise
+//            idle: no MMA here) and a tail of up to 7 units left in the ring  (15 x 32 KiB x 148 SMs = 71 MB);
 //   barrier  grid-wide (cooperative groups);
-//   stats    every CTA derives d[c], max_c d, arg-max and the backward's extra reductions from the unit
-//            partials (<= N*C*K doubles, L2 resident) and the (a, b) pair of each plane it owns;
-//   phase B  the CTA walks its range BACKWARDS: first the units still resident in shared memory (no re-read
-//            at all), then the rest, most-recently-read first so the re-read is served from L2 while it
-//            lasts; 128-bit streaming (evict-first) stores.
+//   stats    grid-parallel per-channel statistics, second barrier, then every CTA reduces max_c d / arg-max /
+//            the backward's cross-channel sum and derives (a, b) for its resident units;
+//   phase B  resident units first (no re-read at all), then the rest from a second atomic queue in DESCENDING
+//            order — most recently read first, so the re-read is served from L2 while it lasts; the producer warp
+//            derives each unit's (a, b) one batch ahead; 128-bit streaming (evict-first) stores.
 // HBM traffic therefore sits between 1R+1W (everything cached on chip) and 2R+1W.
 // A register-staged variant of the same algorithm (no TMA; scalar loads) handles planes whose size or base
 // address is not a multiple of 16 bytes.
@@ -35,6 +35,7 @@ constexpr int kWarps = kConsumers / 32;
 constexpr int kBatch = 4;                       // vectors per consumer thread per unit
 constexpr int kUnitVecs = kConsumers * kBatch;  // 2048 float4 = 32 KiB
 constexpr int kMaxSlots = 7;
+constexpr int kTmemUnits = 8;                    // 512 TMEM columns / 64 columns per parked unit
 
 struct NpGeom {
   int N, C, HW;
@@ -48,8 +49,11 @@ struct NpGeom {
   int grid;      // CTAs
   int keep_units;  // ring path: units (grid-wide) loaded with an L2 evict_last hint because phase B re-reads them
   long long scratch_off;   // scalar path, doubles: ps[0..scratch_off) partials, then pm[P], then chan[4*C]
-  int grab;      // ring path: units taken from the grid-wide queue per atomic
-  int max_jobs;  // ring path: capacity of a CTA's job list
+  int grab;      // ring path: units taken from the phase-A queue per atomic
+  int grab_b;    // ring path: units taken from the phase-B queue per atomic (small: the tail of phase B ends the kernel)
+  int u_dyn;     // ring path: units [0, u_dyn) are handed out dynamically; the rest is the static resident tail
+  int tmem_units;  // ring path: head units per CTA parked in tensor memory
+  int mid_units;   // ring path: units before the keep_units band loaded with L2 evict_normal
 };
 
 // ------------------------------------------------------------------------------------------------------
@@ -75,21 +79,21 @@ struct NpShared {
   int cstar;
 };
 
-// Stage 1 (grid-parallel, between two grid barriers): per-channel statistics of the plane means over the
-// local batch (deepv3.py:272) and the plane totals, written once to global scratch:
-//   pm[p]      = plane total (sum over HW) of plane p
+// Stage 1: per-channel statistics of the plane means over the local batch (deepv3.py:272):
 //   chan[4c..] = { mbar, d = unbiased std of the plane means, dL/ds (backward only), - }
+// and, when `pm` is given, the plane totals pm[p] (sum over HW).  Warp `wfirst` of `wcount` takes every
+// wcount-th channel group: (blockIdx*nwarps+warp, gridDim*nwarps) spreads the work over the grid (scalar kernel,
+// followed by a second grid barrier); (warp, nwarps) makes every CTA compute the whole table for itself (ring kernel).
 template <bool BWD>
 __device__ void np_stage1(const double* ps, const float* __restrict__ mean_in, const float* __restrict__ eps,
-                          const NpGeom& g, double* pm, double* chan, int nthreads) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = nthreads >> 5;
+                          const NpGeom& g, double* pm, double* chan, int wfirst, int wcount) {
+  const int lane = threadIdx.x & 31;
   const double inv_hw = 1.0 / (double)g.HW;
   // lanes = (channel sub-group, batch index): group width = pow2 >= N (capped at 32)
   int gw = 1;
   while (gw < g.N && gw < 32) gw <<= 1;
   const int cpw = 32 / gw, sub = lane % gw, cg_i = lane / gw;
-  const int gwarp = blockIdx.x * nwarps + warp, gwarps = gridDim.x * nwarps;
-  for (int cbase = gwarp * cpw; cbase < g.C; cbase += gwarps * cpw) {     // warp-uniform trip count
+  for (int cbase = wfirst * cpw; cbase < g.C; cbase += wcount * cpw) {    // warp-uniform trip count
     const int c = cbase + cg_i;
     const bool valid = c < g.C;
     double s = 0, m0 = 0, G0 = 0;
@@ -97,7 +101,7 @@ __device__ void np_stage1(const double* ps, const float* __restrict__ mean_in, c
       for (int n = sub; n < g.N; n += gw) {
         const int p = n * g.C + c;
         const double tot = plane_total(ps, p, g);
-        pm[p] = tot;
+        if (pm) pm[p] = tot;
         const double m = BWD ? (double)mean_in[p] : tot * inv_hw;
         if (n == sub) { m0 = m; G0 = tot; }
         s += m;
@@ -164,36 +168,58 @@ __device__ void np_global_reduce(const double* chan, const NpGeom& g, NpShared& 
   __syncthreads();
 }
 
-// Stage 2b: (a, b) of plane p, y = a*x + b.  `publish`: this thread also writes the (N,C) side outputs of the plane.
+// Stage 2b: (a, b) of plane p, y = a*x + b, in two steps so that a caller can put other work between the loads and
+// their first use.  `publish`: this thread also writes the (N,C) side outputs of the plane.
+struct NpCoefIn {
+  double tot, mbar, d, dLds;
+  float alpha, eps, mean;
+};
 template <bool BWD>
-__device__ __forceinline__ float2 np_plane_coef(int p, bool publish, const double* pm, const double* chan,
-                                                const float* __restrict__ mean_in, const float* __restrict__ alpha,
-                                                const float* __restrict__ eps, float* __restrict__ mean_out,
-                                                float* __restrict__ beta_out, const NpGeom& g, const NpShared& sh) {
-  const double inv_hw = 1.0 / (double)g.HW, dmax = sh.dmax;
+__device__ __forceinline__ NpCoefIn np_coef_load(int p, const double* pm, const double* chan,
+                                                 const float* __restrict__ mean_in, const float* __restrict__ alpha,
+                                                 const float* __restrict__ eps, const NpGeom& g) {
+  NpCoefIn r;
   const int c = p % g.C;
-  const double tot = __ldcg(pm + p);
-  const double mbar = __ldcg(chan + 4 * c + 0), d = __ldcg(chan + 4 * c + 1);
-  const double a = (double)alpha[p];
-  const double beta = 1.0 + (double)eps[p] * (d / dmax * 1.5);            // deepv3.py:273,275
+  r.tot = __ldcg(pm + p);
+  r.mbar = __ldcg(chan + 4 * c + 0);
+  r.d = __ldcg(chan + 4 * c + 1);
+  r.dLds = BWD ? __ldcg(chan + 4 * c + 2) : 0.0;
+  r.alpha = alpha[p];
+  r.eps = eps[p];
+  r.mean = BWD ? mean_in[p] : 0.f;
+  return r;
+}
+template <bool BWD>
+__device__ __forceinline__ float2 np_coef_finish(const NpCoefIn& r, int p, bool publish, float* __restrict__ mean_out,
+                                                 float* __restrict__ beta_out, const NpGeom& g, const NpShared& sh) {
+  const double inv_hw = 1.0 / (double)g.HW, dmax = sh.dmax;
+  const double a = (double)r.alpha;
+  const double beta = 1.0 + (double)r.eps * (r.d / dmax * 1.5);          // deepv3.py:273,275
   double b;
   if (!BWD) {
-    const double m = tot * inv_hw;
+    const double m = r.tot * inv_hw;
     b = (beta - a) * m;                                                   // out = a*x + (beta-a)*m  (:276)
     if (publish) {
       mean_out[p] = (float)m;
       if (beta_out) beta_out[p] = (float)beta;
     }
   } else {
-    const double m = (double)mean_in[p];
-    double dLdd = 1.5 / dmax * __ldcg(chan + 4 * c + 2);
-    if (c == sh.cstar) dLdd -= sh.T;
+    const double m = (double)r.mean;
+    double dLdd = 1.5 / dmax * r.dLds;
+    if (p % g.C == sh.cstar) dLdd -= sh.T;
     // torch's std_backward zero-fills where std == 0
-    const double dd_dm = (d == 0.0) ? 0.0 : (m - mbar) / ((double)(g.N - 1) * d);
-    const double dLdm = (beta - a) * tot + dLdd * dd_dm;
+    const double dd_dm = (r.d == 0.0) ? 0.0 : (m - r.mbar) / ((double)(g.N - 1) * r.d);
+    const double dLdm = (beta - a) * r.tot + dLdd * dd_dm;
     b = dLdm * inv_hw;
   }
   return make_float2((float)a, (float)b);
+}
+template <bool BWD>
+__device__ __forceinline__ float2 np_plane_coef(int p, bool publish, const double* pm, const double* chan,
+                                                const float* __restrict__ mean_in, const float* __restrict__ alpha,
+                                                const float* __restrict__ eps, float* __restrict__ mean_out,
+                                                float* __restrict__ beta_out, const NpGeom& g, const NpShared& sh) {
+  return np_coef_finish<BWD>(np_coef_load<BWD>(p, pm, chan, mean_in, alpha, eps, g), p, publish, mean_out, beta_out, g, sh);
 }
 
 // ------------------------------------------------------------------------------------------------------
@@ -225,17 +251,43 @@ __device__ __forceinline__ void bulk_load(void* smem_dst, const void* gsrc, uint
 }
 
 // ------------------------------------------------------------------------------------------------------
-// TMA-ring kernel with a grid-wide dynamic unit queue (planes and base addresses 16-byte aligned)
+// TMA-ring kernel with grid-wide dynamic unit queues (planes and base addresses 16-byte aligned)
 // ------------------------------------------------------------------------------------------------------
 // SMs do not stream from HBM at the same rate (the slowest took 40 % longer than the fastest on a static
-// split), so units are handed out from an atomic counter in batches of g.grab; every CTA remembers its jobs in
-// order and replays them backwards in phase B.  The counter is (re)initialised by CTA 0 of each launch and
-// published with a per-launch nonce, so the workspace needs no host-side clearing.
+// split), so both passes hand units out from atomic counters in batches of g.grab:
+//   phase A   units [0, u_dyn) in ascending order from counterA, then a STATIC tail of `slots` units per CTA
+//             (unit u_dyn + blockIdx*slots + j) which stays resident in the ring;
+//   phase B   the resident tail first (no re-read), then units [0, u_dyn) in DESCENDING order from counterB —
+//             the most recently read data first, so the re-read is served from L2 while it lasts.
+// A fill of ring slot s carries its unit index (and, in phase B, the plane's (a, b) pair) in shared memory next to
+// the slot.  The counters are (re)initialised by CTA 0 of each launch and published with a per-launch nonce, so
+// the workspace needs no host-side clearing.
 struct NpCtrl {
   unsigned long long nonce;
-  unsigned int counter;
-  unsigned int pad[13];
+  unsigned int counter_a;
+  unsigned int counter_b;
+  unsigned int pad[12];
 };
+
+// Tensor memory as a scratchpad: this kernel issues no MMA, so the SM's 256 KiB of TMEM (128 lanes x 512 32-bit
+// columns) hold 8 more resident units.  A consumer thread parks the 16 floats it owns of a unit in 16 columns of
+// its own lane (tcgen05.st 32x32b.x16) and reads them back in phase B (tcgen05.ld); warp w may only touch lanes
+// 32*(w%4)..+31, so the unit occupies columns [64*j + 16*(w/4), +16) of every lane.
+__device__ __forceinline__ void tmem_park(uint32_t taddr, const float4 (&v)[kBatch]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+      ::"r"(taddr), "f"(v[0].x), "f"(v[0].y), "f"(v[0].z), "f"(v[0].w), "f"(v[1].x), "f"(v[1].y), "f"(v[1].z), "f"(v[1].w),
+        "f"(v[2].x), "f"(v[2].y), "f"(v[2].z), "f"(v[2].w), "f"(v[3].x), "f"(v[3].y), "f"(v[3].z), "f"(v[3].w) : "memory");
+  asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_fetch(uint32_t taddr, float4 (&v)[kBatch]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=f"(v[0].x), "=f"(v[0].y), "=f"(v[0].z), "=f"(v[0].w), "=f"(v[1].x), "=f"(v[1].y), "=f"(v[1].z), "=f"(v[1].w),
+        "=f"(v[2].x), "=f"(v[2].y), "=f"(v[2].z), "=f"(v[2].w), "=f"(v[3].x), "=f"(v[3].y), "=f"(v[3].z), "=f"(v[3].w)
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
 
 template <bool BWD>
 __global__ void __launch_bounds__(kConsumers + 32, 1)
@@ -244,7 +296,9 @@ npplus_ring_kernel(const float* __restrict__ x, const float* __restrict__ alpha,
                    float* __restrict__ beta_out, unsigned char* ws, const NpGeom g, unsigned long long nonce,
                    unsigned long long* trace) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  const int S = g.slots;
+  // resident units of this CTA: a static HEAD of T units parked in TMEM at the very start (their imbalance is absorbed
+  // by the dynamic queue that follows) and a static TAIL of S units that stays in the ring
+  const int S = g.slots, T = g.tmem_units;
   auto stamp = [&](int i) {
     if (trace && threadIdx.x == 0) {
       unsigned long long t;
@@ -256,171 +310,254 @@ npplus_ring_kernel(const float* __restrict__ x, const float* __restrict__ alpha,
   float4* ring = reinterpret_cast<float4*>(smem_raw);                                   // S x 32 KiB
   uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + (size_t)S * kUnitVecs * 16);  // [S]
   uint64_t* empty = full + S;                                                           // [S]
-  float2* coefj = reinterpret_cast<float2*>(empty + S);                                 // [max_jobs]
-  int* joblist = reinterpret_cast<int*>(coefj + g.max_jobs);                            // [max_jobs]
+  volatile double* wp = reinterpret_cast<volatile double*>(empty + S);                  // [S][kWarps] warp partials of a fill
+  float2* slot_coef = reinterpret_cast<float2*>(const_cast<double*>(wp) + S * kWarps);  // [S]
+  volatile int* slot_unit = reinterpret_cast<volatile int*>(slot_coef + S);             // [S]
+  int* slot_cnt = const_cast<int*>(slot_unit) + S;                                      // [S] warps that delivered their partial
   __shared__ NpShared sh;
+  __shared__ float2 head_coef[kTmemUnits];
+  __shared__ uint32_t tmem_base_s;
 
   NpCtrl* ctrl = reinterpret_cast<NpCtrl*>(ws);
   double* ps = reinterpret_cast<double*>(ws + sizeof(NpCtrl));      // [U] unit partials
   double* pm = ps + g.U;                                            // [P] plane totals
   double* chan = pm + g.P;                                          // [4C] channel statistics
-  double* wpg = chan + 4 * g.C + (size_t)blockIdx.x * g.max_jobs * kWarps;   // [max_jobs][kWarps] warp partials of this CTA
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const bool is_producer = warp == kWarps;
-  const int U = (int)g.U;
+  const int u_dyn = g.u_dyn;
+  const int head0 = (int)blockIdx.x * T;                 // unit space: [heads: grid*T][dynamic queue: u_dyn][tails: grid*S]
+  const int dyn0 = (int)gridDim.x * T;
+  const int tail0 = dyn0 + u_dyn + (int)blockIdx.x * S;
   const int last_len = g.HWV - (g.K - 1) * g.Q;          // the last unit of a plane may be shorter
   const float4* xv = reinterpret_cast<const float4*>(x);
   float4* ov = reinterpret_cast<float4*>(out);
 
   if (tid == 0) {
-    for (int s = 0; s < S; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], kWarps); }
+    for (int s = 0; s < S; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], kWarps); slot_cnt[s] = 0; }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    if (blockIdx.x == 0) {                               // open this launch's queue: the first batches are static
-      ctrl->counter = gridDim.x * g.grab;
+    if (blockIdx.x == 0) {                               // open this launch's queues: the first batches are static
+      ctrl->counter_a = gridDim.x * g.grab;
+      ctrl->counter_b = 0;
       __threadfence();
       *reinterpret_cast<volatile unsigned long long*>(&ctrl->nonce) = nonce;
     }
   }
+  if (is_producer && T > 0) {                            // the whole TMEM (one CTA per SM, no MMA in this kernel)
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(&tmem_base_s)) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  }
   __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  // this thread's window into TMEM: its own lane, 16 columns per parked unit
+  const uint32_t tmem_mine = T > 0 ? tmem_base_s + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)((warp >> 2) * 16) : 0u;
+
+  // ring position of the next fill; producer and consumers count the same fills, so they agree after phase A
+  int s = 0, k = 0;
+  auto advance = [&]() { if (++s == S) { s = 0; ++k; } };
+  auto unit_src = [&](int u, uint32_t* bytes) {
+    const int plane = u / g.K, part = u - plane * g.K;
+    *bytes = (uint32_t)(part == g.K - 1 ? last_len : g.Q) * 16u;
+    return (long long)plane * g.HWV + part * g.Q;
+  };
 
   // ---------------- phase A ----------------
-  int nA = 0;                                            // jobs taken by this CTA (known after the loop)
   if (is_producer) {
     if (lane == 0) {
-      uint64_t pol_keep, pol_stream;
+      uint64_t pol_keep, pol_mid, pol_stream;
       asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol_keep));
+      asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(pol_mid));
       asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol_stream));
-      // the globally last units are the ones re-read in phase B: the newest S per CTA stay in shared memory, the
-      // g.keep_units before them are asked to stay in L2
-      const int keep_hi = U - (int)gridDim.x * S, keep_lo = keep_hi - g.keep_units;
-      int j = 0, s = 0, k = 0;
-      unsigned base = blockIdx.x * g.grab, nbase = 0;
-      bool open = blockIdx.x == 0, have_next = false;
-      while (base < (unsigned)U && j < g.max_jobs - 1) {
-        if (!have_next && j + 2 * g.grab < g.max_jobs - 1) {          // fetch the next batch while this one streams
-          if (!open) {
-            while (*reinterpret_cast<volatile unsigned long long*>(&ctrl->nonce) != nonce) {}
-            __threadfence();
-            open = true;
-          }
-          nbase = atomicAdd(&ctrl->counter, (unsigned)g.grab);
-          have_next = true;
+      auto issue = [&](int u, uint64_t pol) {
+        if (k > 0) mbar_wait(&empty[s], (k - 1) & 1);    // all 16 warps released the previous fill of this slot
+        uint32_t bytes;
+        const long long off = unit_src(u, &bytes);
+        slot_unit[s] = u;
+        mbar_expect_tx(&full[s], bytes);
+        bulk_load(ring + (size_t)s * kUnitVecs, xv + off, bytes, &full[s], pol);
+        advance();
+      };
+      for (int j = 0; j < T; ++j) issue(head0 + j, pol_stream);
+      // the last g.keep_units of the dynamic range are the first ones re-read in phase B: ask L2 to keep them
+      const int keep_lo = u_dyn - g.keep_units, mid_lo = keep_lo - g.mid_units;
+      unsigned base = blockIdx.x * g.grab;
+      bool open = blockIdx.x == 0;
+      while (base < (unsigned)u_dyn) {
+        if (!open) {
+          while (*reinterpret_cast<volatile unsigned long long*>(&ctrl->nonce) != nonce) {}
+          __threadfence();
+          open = true;
         }
-        for (int q = 0; q < g.grab && base + q < (unsigned)U && j < g.max_jobs - 1; ++q) {
+        const unsigned nbase = atomicAdd(&ctrl->counter_a, (unsigned)g.grab);   // in flight while this batch is issued
+        for (int q = 0; q < g.grab && base + q < (unsigned)u_dyn; ++q) {
           const int u = (int)base + q;
-          if (k > 0) mbar_wait(&empty[s], (k - 1) & 1);  // all 16 warps released fill k-1 of this slot
-          const int plane = u / g.K, part = u - plane * g.K;
-          const uint32_t bytes = (uint32_t)(part == g.K - 1 ? last_len : g.Q) * 16u;
-          joblist[j] = u;
-          mbar_expect_tx(&full[s], bytes);
-          bulk_load(ring + (size_t)s * kUnitVecs, xv + (long long)plane * g.HWV + part * g.Q, bytes, &full[s],
-                    (u >= keep_lo && u < keep_hi) ? pol_keep : pol_stream);
-          ++j;
-          if (++s == S) { s = 0; ++k; }
+          issue(dyn0 + u, u >= keep_lo ? pol_keep : (u >= mid_lo ? pol_mid : pol_stream));
         }
-        if (!have_next) break;
-        base = nbase; have_next = false;
+        base = nbase;
       }
-      if (k > 0) mbar_wait(&empty[s], (k - 1) & 1);
-      joblist[j] = -1;                                   // end marker: completes one phase of full[s] without data
-      mbar_arrive(&full[s]);
+      for (int j = 0; j < S; ++j) issue(tail0 + j, pol_stream);
     }
   } else {
-    int s = 0, k = 0;
-    for (;; ++nA) {
+    for (;;) {
       mbar_wait(&full[s], k & 1);
-      const int u = joblist[nA];
-      if (u < 0) break;
+      const int u = slot_unit[s];
       const int plane = u / g.K, part = u - plane * g.K;
       const int len = part == g.K - 1 ? last_len : g.Q;
       const float4* src = ring + (size_t)s * kUnitVecs;
+      const int hj = u - head0;                          // 0 .. T-1: position in this CTA's head
+      float4 v[kBatch];
       float acc = 0.f;
 #pragma unroll
       for (int b = 0; b < kBatch; ++b) {
         const int i = tid + b * kConsumers;
-        if (i < len) { const float4 v = src[i]; acc += (v.x + v.y) + (v.z + v.w); }
+        v[b] = i < len ? src[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+        acc += (v[b].x + v[b].y) + (v[b].z + v[b].w);
       }
+      if (hj >= 0 && hj < T) tmem_park(tmem_mine + (uint32_t)(hj * 64), v);
       const double w = warp_sum((double)acc);
+      const bool stays = u >= tail0;                     // the S tail fills stay in the ring until phase B
       if (lane == 0) {
-        wpg[nA * kWarps + warp] = w;
-        mbar_arrive(&empty[s]);                          // always released; the last S fills simply stay in the ring
+        wp[s * kWarps + warp] = w;
+        __threadfence_block();
+        if (atomicAdd(&slot_cnt[s], 1) == kWarps - 1) {  // last warp of this fill: fold the 16 partials in fixed order
+          __threadfence_block();
+          double t = 0;
+#pragma unroll
+          for (int i = 0; i < kWarps; ++i) t += wp[s * kWarps + i];
+          ps[u] = t;
+          slot_cnt[s] = 0;
+        }
+        if (!stays) mbar_arrive(&empty[s]);
       }
-      if (++s == S) { s = 0; ++k; }
+      advance();
+      if (u == tail0 + S - 1) break;
     }
   }
-  if (tid == 0) sh.cstar = nA;                           // publish the job count to the producer warp
-  __syncthreads();
-  nA = sh.cstar;
+  if (is_producer) {                                     // lanes 1..31 of the producer warp: adopt lane 0's ring position
+    s = __shfl_sync(0xffffffffu, s, 0);
+    k = __shfl_sync(0xffffffffu, k, 0);
+  }
   __syncthreads();
   stamp(1);
-  for (int j = tid; j < nA; j += kConsumers + 32) {      // fold the 16 warp partials of each unit, fixed order
-    double t = 0;
-#pragma unroll
-    for (int w = 0; w < kWarps; ++w) t += __ldcg(wpg + j * kWarps + w);
-    ps[joblist[j]] = t;
-  }
   __threadfence();
   cg::this_grid().sync();
   stamp(2);
 
   // ---------------- statistics ----------------
-  np_stage1<BWD>(ps, mean_in, eps, g, pm, chan, kConsumers + 32);
+  np_stage1<BWD>(ps, mean_in, eps, g, pm, chan, blockIdx.x * (kWarps + 1) + warp, gridDim.x * (kWarps + 1));
   __threadfence();
   cg::this_grid().sync();
   np_global_reduce<BWD>(chan, g, sh, kConsumers + 32);
-  for (int j = tid; j < nA; j += kConsumers + 32) {
-    const int u = joblist[j], plane = u / g.K;
-    coefj[j] = np_plane_coef<BWD>(plane, u - plane * g.K == 0, pm, chan, mean_in, alpha, eps, mean_out, beta_out, g, sh);
+  if (tid < S + T) {                                     // the resident units
+    const int u = tid < T ? head0 + tid : tail0 + (tid - T), plane = u / g.K;
+    const float2 ab = np_plane_coef<BWD>(plane, u - plane * g.K == 0, pm, chan, mean_in, alpha, eps, mean_out, beta_out, g, sh);
+    if (tid < T) head_coef[tid] = ab;
+    else {
+      int sl = s + (tid - T);                            // tail fill j sits in slot (s + j) mod S
+      if (sl >= S) sl -= S;
+      slot_coef[sl] = ab;
+    }
   }
   __syncthreads();
   stamp(3);
 
-  // ---------------- phase B: this CTA's jobs, newest first ----------------
-  const int s_end = nA % S;                              // the slot whose full barrier took the end-marker arrive
-  auto fills_a = [&](int s) { return (s < nA ? (nA - s + S - 1) / S : 0); };   // phase-A data fills of slot s
+  // ---------------- phase B ----------------
   if (is_producer) {
-    if (lane == 0 && nA > S) {
-      uint64_t pol_stream;
-      asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol_stream));
-      int s = (nA - 1 - S) % S;
-      for (int i = S; i < nA; ++i) {                     // refill with job nA-1-i once job nA-1-(i-S) left the slot
-        const int u = joblist[nA - 1 - i];
-        mbar_wait(&empty[s], (fills_a(s) + i / S - 1) & 1);
-        const int plane = u / g.K, part = u - plane * g.K;
-        const uint32_t bytes = (uint32_t)(part == g.K - 1 ? last_len : g.Q) * 16u;
-        mbar_expect_tx(&full[s], bytes);
-        bulk_load(ring + (size_t)s * kUnitVecs, xv + (long long)plane * g.HWV + part * g.Q, bytes, &full[s], pol_stream);
-        if (--s < 0) s = S - 1;
+    uint64_t pol_stream;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol_stream));
+    // software pipeline, one batch deep: while batch j is being issued (which blocks on free slots), the index of
+    // batch j+1 and the inputs of its (a, b) pairs are already in flight
+    auto grab = [&]() {
+      unsigned v = 0;
+      if (lane == 0) v = atomicAdd(&ctrl->counter_b, (unsigned)g.grab_b);
+      return v;
+    };
+    unsigned idx = __shfl_sync(0xffffffffu, grab(), 0);
+    unsigned nidx = grab();
+    NpCoefIn ci = {};
+    int u = 0, cnt = 0;
+    auto stage = [&](unsigned id) {                      // lane q < cnt takes queue entry (u_dyn-1-id-q): start its loads
+      cnt = id < (unsigned)u_dyn ? min(g.grab_b, u_dyn - (int)id) : 0;
+      if (lane < cnt) {
+        u = dyn0 + u_dyn - 1 - (int)id - lane;
+        ci = np_coef_load<BWD>(u / g.K, pm, chan, mean_in, alpha, eps, g);
+      }
+    };
+    stage(idx);
+    while (cnt > 0) {
+      float2 ab = make_float2(0.f, 0.f);
+      const int cur_u = u, cur_cnt = cnt;
+      if (lane < cnt) {
+        const int plane = u / g.K;
+        ab = np_coef_finish<BWD>(ci, plane, u - plane * g.K == 0, mean_out, beta_out, g, sh);
+      }
+      idx = __shfl_sync(0xffffffffu, nidx, 0);
+      nidx = grab();
+      stage(idx);                                        // loads for the next batch leave before this one blocks
+      for (int q = 0; q < cur_cnt; ++q) {
+        const int uq = __shfl_sync(0xffffffffu, cur_u, q);
+        const float ax = __shfl_sync(0xffffffffu, ab.x, q), ay = __shfl_sync(0xffffffffu, ab.y, q);
+        if (lane == 0) {
+          mbar_wait(&empty[s], (k - 1) & 1);             // k >= 1 here: every slot took a phase-A fill
+          uint32_t bytes;
+          const long long off = unit_src(uq, &bytes);
+          slot_unit[s] = uq;
+          slot_coef[s] = make_float2(ax, ay);
+          mbar_expect_tx(&full[s], bytes);
+          bulk_load(ring + (size_t)s * kUnitVecs, xv + off, bytes, &full[s], pol_stream);
+        }
+        advance();
       }
     }
+    if (lane == 0) {
+      mbar_wait(&empty[s], (k - 1) & 1);
+      slot_unit[s] = -1;                                 // end marker: completes one phase of full[s] without data
+      mbar_arrive(&full[s]);
+    }
   } else {
-    int s = nA > 0 ? (nA - 1) % S : 0;
-    for (int i = 0; i < nA; ++i) {
-      const int j = nA - 1 - i, u = joblist[j];
+    auto emit = [&](int u, const float2 ab, float4 (&v)[kBatch]) {
       const int plane = u / g.K, part = u - plane * g.K;
       const int len = part == g.K - 1 ? last_len : g.Q;
-      if (i >= S) mbar_wait(&full[s], (fills_a(s) + (s == s_end ? 1 : 0) + i / S - 1) & 1);
-      const float2 ab = coefj[j];
-      const float4* src = ring + (size_t)s * kUnitVecs;
-      float4 v[kBatch];
-#pragma unroll
-      for (int b = 0; b < kBatch; ++b) {
-        const int idx = tid + b * kConsumers;
-        if (idx < len) {
-          const float4 t = src[idx];
-          v[b] = make_float4(fmaf(ab.x, t.x, ab.y), fmaf(ab.x, t.y, ab.y), fmaf(ab.x, t.z, ab.y), fmaf(ab.x, t.w, ab.y));
-        }
-      }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&empty[s]);
       float4* dst = ov + (long long)plane * g.HWV + part * g.Q;
 #pragma unroll
       for (int b = 0; b < kBatch; ++b) {
         const int idx = tid + b * kConsumers;
-        if (idx < len) st_stream_f4(dst + idx, v[b]);
+        if (idx < len)
+          st_stream_f4(dst + idx, make_float4(fmaf(ab.x, v[b].x, ab.y), fmaf(ab.x, v[b].y, ab.y), fmaf(ab.x, v[b].z, ab.y),
+                                              fmaf(ab.x, v[b].w, ab.y)));
       }
-      if (--s < 0) s = S - 1;
+    };
+    // the ring part of the tail first (frees the slots for the producer), then the TMEM part, then the queue
+    for (int i = 0;; ++i) {
+      if (i == S) {
+        for (int j = 0; j < T; ++j) {
+          float4 v[kBatch];
+          tmem_fetch(tmem_mine + (uint32_t)(j * 64), v);
+          emit(head0 + j, head_coef[j], v);
+        }
+      }
+      if (i >= S) mbar_wait(&full[s], k & 1);            // the first S fills are the resident tail, waited for in phase A
+      const int u = slot_unit[s];
+      if (u < 0) break;
+      const float2 ab = slot_coef[s];
+      const float4* src = ring + (size_t)s * kUnitVecs;
+      float4 v[kBatch];
+#pragma unroll
+      for (int b = 0; b < kBatch; ++b) v[b] = src[tid + b * kConsumers];   // (slack beyond a short unit is never stored)
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty[s]);
+      emit(u, ab, v);
+      if (i < S) { if (++s == S) s = 0; }                // replaying the tail does not start a new round
+      else advance();
+    }
+  }
+  if (T > 0) {
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (is_producer) {
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base_s) : "memory");
     }
   }
   if (trace) { __syncthreads(); stamp(4); }
@@ -472,7 +609,7 @@ npplus_scalar_kernel(const float* __restrict__ x, const float* __restrict__ alph
   cg::this_grid().sync();
   double* pm = ps + g.scratch_off;
   double* chan = pm + g.P;
-  np_stage1<BWD>(ps, mean_in, eps, g, pm, chan, kConsumers);
+  np_stage1<BWD>(ps, mean_in, eps, g, pm, chan, blockIdx.x * kWarps + (threadIdx.x >> 5), gridDim.x * kWarps);
   __threadfence();
   cg::this_grid().sync();
   np_global_reduce<BWD>(chan, g, sh, kConsumers);
@@ -504,14 +641,15 @@ struct NpLaunch {
   size_t smem;
 };
 
-// workspace layout (bytes): [NpCtrl 64][ps: units][pm: P][chan: 4C][ring path: per-CTA warp partials]
+constexpr int kMaxGrid = 1024;
+
+// workspace layout (bytes): [NpCtrl 64][ps: units][pm: P][chan: 4C]
 size_t ws_layout_bytes(int N, int C, int HW) {
   const long long P = (long long)N * C;
   const long long u_scalar = P * (((long long)HW + kUnitVecs - 1) / kUnitVecs);                 // 2048 floats per unit
   const long long u_ring = P * (((long long)HW / 4 + kUnitVecs - 1) / kUnitVecs + 1);           // 2048 float4 per unit
   const long long units = u_scalar > u_ring ? u_scalar : u_ring;
-  const long long jobs = 2 * u_ring + 32LL * 1024;       // sum over CTAs of max_jobs (<= 2*upc + 24 each, <= 1024 CTAs)
-  return (size_t)(sizeof(NpCtrl) + 8 * (units + P + 4LL * C + jobs * kWarps));
+  return (size_t)(sizeof(NpCtrl) + 8 * (units + P + 4LL * C));
 }
 
 void plan_launch(int N, int C, int HW, bool ring, const DeviceInfo& di, NpLaunch* L) {
@@ -522,29 +660,39 @@ void plan_launch(int N, int C, int HW, bool ring, const DeviceInfo& di, NpLaunch
   g.Q = g.HWV < kUnitVecs ? g.HWV : kUnitVecs;
   g.K = (g.HWV + g.Q - 1) / g.Q;                                 // last unit of a plane may be shorter
   g.U = (long long)g.P * g.K;
-  L->grid = (int)((g.U < di.sm_count) ? g.U : di.sm_count);
+  const int sms = di.sm_count < kMaxGrid ? di.sm_count : kMaxGrid;
+  L->grid = (int)((g.U < sms) ? g.U : sms);
   g.grid = L->grid;
   const long long upc = (g.U + L->grid - 1) / L->grid;           // units per CTA (static split: max)
-  const long long min_upc = g.U / L->grid;                       // ... (min)
+  const long long min_upc = g.U / L->grid;                       // ... (min, >= 1)
   g.max_local_planes = (int)(upc / g.K + 2);
   g.scratch_off = g.U;
-  g.keep_units = 0; g.grab = 1; g.max_jobs = 0;
+  g.keep_units = 0; g.grab = 1; g.grab_b = 1; g.u_dyn = 0; g.tmem_units = 0; g.mid_units = 0;
   const size_t slack = 1024;                                     // static smem + alignment
   if (ring) {
     long long grab = upc / 8;
     g.grab = (int)(grab < 1 ? 1 : (grab > 4 ? 4 : grab));
-    g.max_jobs = (int)(2 * upc + 4 * g.grab + 8);
-    const size_t tables = align_up((size_t)g.max_jobs * (sizeof(float2) + sizeof(int)), 16);
-    const size_t per_slot = (size_t)kUnitVecs * 16 + 16;
-    long long s = (long long)(((size_t)di.max_smem_optin - slack - tables) / per_slot);
+    static const int grab_b = getenv("MRFP_NPPLUS_GRAB_B") ? atoi(getenv("MRFP_NPPLUS_GRAB_B")) : 2;
+    g.grab_b = g.grab < grab_b ? g.grab : grab_b;
+    // per slot: the unit, two mbarriers, 16 warp partials, (a, b), unit index, fold counter
+    const size_t per_slot = (size_t)kUnitVecs * 16 + 16 + kWarps * 8 + 8 + 4 + 4;
+    long long s = (long long)(((size_t)di.max_smem_optin - slack) / per_slot);
     if (s > kMaxSlots) s = kMaxSlots;
-    if (s > upc) s = upc;
+    if (s > min_upc) s = min_upc;                                // every CTA owns a full static tail
     if (s < 1) s = 1;
     g.slots = (int)s;
-    L->smem = (size_t)g.slots * per_slot + tables;
+    static const long long tmem_max = getenv("MRFP_NPPLUS_TMEM_UNITS") ? atoll(getenv("MRFP_NPPLUS_TMEM_UNITS")) : kTmemUnits;
+    long long t = min_upc - s;
+    if (t > tmem_max) t = tmem_max;
+    if (t > kTmemUnits) t = kTmemUnits;
+    g.tmem_units = (int)(t < 0 ? 0 : t);
+    g.u_dyn = (int)(g.U - (long long)L->grid * (g.slots + g.tmem_units));
+    L->smem = align_up((size_t)g.slots * per_slot, 16);
     // L2 share reserved for phase-B re-reads (MRFP_NPPLUS_KEEP_MB overrides; default 64 MiB)
     static const long long keep_mb = getenv("MRFP_NPPLUS_KEEP_MB") ? atoll(getenv("MRFP_NPPLUS_KEEP_MB")) : 64;
     g.keep_units = (int)((keep_mb << 20) / ((long long)kUnitVecs * 16));
+    static const long long mid_mb = getenv("MRFP_NPPLUS_MID_MB") ? atoll(getenv("MRFP_NPPLUS_MID_MB")) : 0;
+    g.mid_units = (int)((mid_mb << 20) / ((long long)kUnitVecs * 16));
   } else {
     const size_t coef_bytes = align_up((size_t)g.max_local_planes * sizeof(float2), 16);
     const size_t unit_bytes = (size_t)g.Q * 4;

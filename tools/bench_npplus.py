@@ -60,6 +60,12 @@ def bench(n, c, h, w, iters=20):
 
 
 if __name__ == "__main__":
+    if len(sys.argv) > 1:      # e.g. 8,256,192,192
+        for a in sys.argv[1:]:
+            shape = tuple(int(v) for v in a.split(","))
+            r = bench(*shape)
+            print(shape, "fwd %.1f us %.0f GB/s | bwd %.1f us %.0f GB/s" % (r["fwd"]["ms"] * 1e3, r["fwd"]["gbps"], r["bwd"]["ms"] * 1e3, r["bwd"]["gbps"]))
+        sys.exit(0)
     for shape in [(8, 64, 192, 192), (8, 256, 192, 192), (2, 64, 192, 192), (2, 256, 192, 192),
                   (8, 16, 384, 384), (8, 116, 96, 96)]:
         print(shape, json.dumps(bench(*shape)))
