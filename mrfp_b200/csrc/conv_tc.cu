@@ -15,6 +15,7 @@
 #include "hrfp.cuh"
 #include <cuda.h>
 #include <mutex>
+#include <stdlib.h>
 
 namespace mrfp {
 namespace {
@@ -283,6 +284,220 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_cons
 }
 
 // ------------------------------------------------------------------------------------------------------
+// Halo variant: the 9 taps read SHIFTED VIEWS of one input halo tile instead of 9 separate TMA boxes.
+// ------------------------------------------------------------------------------------------------------
+// The tap kernel above pulls 9 x (A box + B box) per 64-channel chunk through L2 -> SM, which is what bounds the
+// 64- and 128-wide layers (~100 B/clk/SM).  Here one 4-D TMA box {64 ch, BoxW, 16 + 2*dil, 1} brings the whole
+// (16 + 2d) x (8*MT + 2d) input neighbourhood of a tile once per chunk; the M sub-tile is 16 rows x 8 columns, so
+// its 16 eight-row groups are the 16 image rows of the tile, one box row (BoxW * 128 B) apart = the descriptor's
+// stride-byte-offset, and tap (dy, dx) is simply a start address (dy*d*BoxW + dx*d) * 128 B into the box.
+// BoxW is a multiple of 8, so the 128-byte swizzle phase of a row is its box column & 7; a view whose first row
+// is not 1024-byte aligned carries that phase in the descriptor's base-offset field.
+// Weights stream through their own small ring, one {64, COUT} box per (chunk, tap).
+template <int COUT> struct HCfg {
+  static constexpr int kMT = COUT == 256 ? 1 : 2;
+  static constexpr int kBoxW = kMT == 2 ? 24 : 16;                  // >= 8*MT + 2*dil, multiple of 8
+  static constexpr int kBoxHMax = 20;                               // 16 + 2*dil, dil <= 2
+  static constexpr int kAStageBytes = kBoxW * kBoxHMax * 128;       // 61440 / 40960: multiples of 1024
+  static constexpr int kAStages = 2;
+  static constexpr int kBTileBytes = COUT * 128;
+  static constexpr int kBStages = COUT == 256 ? 3 : 4;
+  static constexpr int kOutBufs = COUT == 64 ? 2 : 1;
+  static constexpr int kTmemCols = 2 * kMT * COUT;
+  static constexpr int kSmemBytes = kAStages * kAStageBytes + kBStages * kBTileBytes + kOutBufs * kStageOutBytes +
+                                    2 * COUT * 4 + 256 /* barriers */ + 1024 /* alignment slack */;
+};
+constexpr int kHaloTileH = 16, kHaloSubW = 8;
+
+// K-major, 128-byte swizzle; sbo16 = byte distance between 8-row groups >> 4; phase = (start address >> 7) & 7
+__device__ __forceinline__ uint64_t make_desc_sw128_view(uint32_t smem_addr, uint32_t sbo16, uint32_t phase) {
+  return (uint64_t)((smem_addr >> 4) & 0x3FFF) | (1ull << 16) | ((uint64_t)sbo16 << 32) | (1ull << 46) |
+         ((uint64_t)phase << 49) | (2ull << 61);
+}
+
+template <int COUT>
+__global__ void __launch_bounds__(kThreads, 1)
+conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constant__ CUtensorMap tmap_w,
+                    const __grid_constant__ CUtensorMap tmap_out, int CIN, int dil, int tiles_h, int tiles_w,
+                    int num_tiles, const int* __restrict__ cnt_h, const int* __restrict__ cnt_w,
+                    double* __restrict__ stat_acc, int bo_mode) {
+  using C = HCfg<COUT>;
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  unsigned char* sA = smem;
+  unsigned char* sB = sA + C::kAStages * C::kAStageBytes;
+  unsigned char* sOut = sB + C::kBStages * C::kBTileBytes;
+  float* s_stats = reinterpret_cast<float*>(sOut + C::kOutBufs * kStageOutBytes);
+  uint64_t* full_a = reinterpret_cast<uint64_t*>(s_stats + 2 * COUT);
+  uint64_t* empty_a = full_a + C::kAStages;
+  uint64_t* full_b = empty_a + C::kAStages;
+  uint64_t* empty_b = full_b + C::kBStages;
+  uint64_t* tmem_full = empty_b + C::kBStages;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nchunks = CIN / kBlockK;
+  const uint32_t a_bytes = (uint32_t)(C::kBoxW * (kHaloTileH + 2 * dil) * 128);
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < C::kAStages; ++i) { mbar_init(&full_a[i], 1); mbar_init(&empty_a[i], 1); }
+    for (int i = 0; i < C::kBStages; ++i) { mbar_init(&full_b[i], 1); mbar_init(&empty_b[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  for (int i = threadIdx.x; i < 2 * COUT; i += kThreads) s_stats[i] = 0.f;
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)), "n"(C::kTmemCols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int as = 0, bs = 0; uint32_t aph = 0, bph = 0;
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+        const int tw = t % tiles_w, th = (t / tiles_w) % tiles_h, n = t / (tiles_w * tiles_h);
+        const int h0 = th * kHaloTileH, w0 = tw * kHaloSubW * C::kMT;
+        for (int kc = 0; kc < nchunks; ++kc) {
+          mbar_wait(&empty_a[as], aph ^ 1);
+          mbar_expect_tx(&full_a[as], a_bytes);
+          tma_load_4d(sA + as * C::kAStageBytes, &tmap_in, &full_a[as], kc * kBlockK, w0 - dil, h0 - dil, n);
+          if (++as == C::kAStages) { as = 0; aph ^= 1; }
+          for (int tap = 0; tap < 9; ++tap) {
+            mbar_wait(&empty_b[bs], bph ^ 1);
+            mbar_expect_tx(&full_b[bs], C::kBTileBytes);
+            tma_load_2d(sB + bs * C::kBTileBytes, &tmap_w, &full_b[bs], kc * kBlockK, tap * COUT);
+            if (++bs == C::kBStages) { bs = 0; bph ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(COUT >> 3) << 17) | ((128u >> 4) << 24);
+      int as = 0, bs = 0; uint32_t aph = 0, bph = 0;
+      int it = 0;
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+        const int acc = it & 1;
+        mbar_wait(&tmem_empty[acc], ((it >> 1) & 1) ^ 1);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * C::kMT * COUT);
+        for (int kc = 0; kc < nchunks; ++kc) {
+          mbar_wait(&full_a[as], aph);
+          const uint32_t a_base = smem_u32(sA + as * C::kAStageBytes);
+          for (int tap = 0; tap < 9; ++tap) {
+            mbar_wait(&full_b[bs], bph);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t b_base = smem_u32(sB + bs * C::kBTileBytes);
+            const int row0 = (tap / 3) * dil * C::kBoxW + (tap % 3) * dil;    // first box pixel of this tap's view
+#pragma unroll
+            for (int k = 0; k < kBlockK / kUmmaK; ++k) {
+              const uint64_t db = make_desc_sw128(b_base + k * 32);
+#pragma unroll
+              for (int mt = 0; mt < C::kMT; ++mt) {
+                const uint32_t a_addr = a_base + (uint32_t)(row0 + mt * kHaloSubW) * 128u + k * 32;
+                const uint32_t phase = bo_mode ? ((a_addr >> 7) & 7u) : 0u;
+                umma_bf16(d_tmem + (uint32_t)(mt * COUT), make_desc_sw128_view(a_addr, C::kBoxW * 8, phase), db, idesc,
+                          (kc | tap | k) != 0);
+              }
+            }
+            umma_commit(&empty_b[bs]);
+            if (++bs == C::kBStages) { bs = 0; bph ^= 1; }
+          }
+          umma_commit(&empty_a[as]);                   // the halo tile is free once all 9 taps have read it
+          if (++as == C::kAStages) { as = 0; aph ^= 1; }
+        }
+        umma_commit(&tmem_full[acc]);
+      }
+    }
+  } else {
+    // ===================== epilogue (warps 2..5) =====================
+    const int q = warp & 3;                     // TMEM lane quarter this warp may access
+    const int r = q * 32 + lane;                // accumulator row = pixel inside the 16 x 8 sub-tile
+    const int hl = r / kHaloSubW, wl = r % kHaloSubW;
+    const bool leader = threadIdx.x == 64;      // first epilogue thread issues the TMA stores
+    int it = 0, obuf = 0;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+      const int tw = t % tiles_w, th = (t / tiles_w) % tiles_h, n = t / (tiles_w * tiles_h);
+      const int h0 = th * kHaloTileH, w0 = tw * kHaloSubW * C::kMT;
+      const int acc = it & 1;
+      mbar_wait(&tmem_full[acc], (it >> 1) & 1);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll 1
+      for (int jj = 0; jj < C::kMT * (COUT / 64); ++jj) {
+        const int mt = jj / (COUT / 64), j = jj % (COUT / 64);
+        float wgt = 0.f;
+        if (stat_acc) wgt = (float)(cnt_h[h0 + hl] * cnt_w[w0 + mt * kHaloSubW + wl]);   // 0 outside the image (zero-padded tables)
+        unsigned char* ob = sOut + obuf * kStageOutBytes;
+        if (leader) asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(C::kOutBufs - 1) : "memory");
+        epi_bar_sync();
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          uint32_t v[32];
+          tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((acc * C::kMT + mt) * COUT + j * 64 + half * 32), v);
+          if (stat_acc) {
+            float x1[32], x2[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              const float f = __uint_as_float(v[i]);
+              x1[i] = wgt * f;
+              x2[i] = x1[i] * f;
+            }
+            const float s1 = warp_transpose_sum(x1, lane);
+            const float s2 = warp_transpose_sum(x2, lane);
+            atomicAdd(&s_stats[j * 64 + half * 32 + lane], s1);
+            atomicAdd(&s_stats[COUT + j * 64 + half * 32 + lane], s2);
+          }
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            uint32_t p[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const __nv_bfloat162 h2 = __floats2bfloat162_rn(__uint_as_float(v[c * 8 + 2 * i]), __uint_as_float(v[c * 8 + 2 * i + 1]));
+              p[i] = *reinterpret_cast<const uint32_t*>(&h2);
+            }
+            const int chunk = half * 4 + c;
+            *reinterpret_cast<uint4*>(ob + r * 128 + ((chunk ^ (r & 7)) << 4)) = make_uint4(p[0], p[1], p[2], p[3]);
+          }
+        }
+        if (jj == C::kMT * (COUT / 64) - 1) {
+          asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        epi_bar_sync();
+        if (leader) {
+          tma_store_4d(&tmap_out, ob, j * 64, w0 + mt * kHaloSubW, h0, n);
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+        if (++obuf == C::kOutBufs) obuf = 0;
+      }
+    }
+    if (leader) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    epi_bar_sync();
+    if (stat_acc) {
+      for (int c = threadIdx.x - 64; c < COUT; c += 128) {
+        atomicAdd(stat_acc + c, (double)s_stats[c]);
+        atomicAdd(stat_acc + kMaxC + c, (double)s_stats[COUT + c]);
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(C::kTmemCols) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------
 // host side: tensor maps (driver entry point fetched through the runtime; no link against libcuda)
 // ------------------------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -353,6 +568,48 @@ int launch(const __nv_bfloat16* in, const __nv_bfloat16* wpack, __nv_bfloat16* o
   return MRFP_OK;
 }
 
+template <int COUT>
+int launch_halo(const __nv_bfloat16* in, const __nv_bfloat16* wpack, __nv_bfloat16* out, int N, int H, int W, int cin,
+                int dil, const int* cnt_h, const int* cnt_w, double* stat_acc, int bo_mode, cudaStream_t stream) {
+  using C = HCfg<COUT>;
+  if (dil < 1 || 2 * dil + kHaloSubW * C::kMT > C::kBoxW || kHaloTileH + 2 * dil > C::kBoxHMax) return MRFP_ERR_UNSUPPORTED;
+  CUtensorMap m_in, m_w, m_out;
+  {
+    const cuuint64_t dims[4] = {(cuuint64_t)cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+    const cuuint64_t strides[3] = {(cuuint64_t)cin * 2, (cuuint64_t)W * cin * 2, (cuuint64_t)H * W * cin * 2};
+    const cuuint32_t box[4] = {kBlockK, (cuuint32_t)C::kBoxW, (cuuint32_t)(kHaloTileH + 2 * dil), 1};
+    int rc = make_map(&m_in, in, 4, dims, strides, box);
+    if (rc) return rc;
+  }
+  {
+    const cuuint64_t dims[2] = {(cuuint64_t)cin, (cuuint64_t)9 * COUT};
+    const cuuint64_t strides[1] = {(cuuint64_t)cin * 2};
+    const cuuint32_t box[2] = {kBlockK, COUT};
+    int rc = make_map(&m_w, wpack, 2, dims, strides, box);
+    if (rc) return rc;
+  }
+  {
+    const cuuint64_t dims[4] = {(cuuint64_t)COUT, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+    const cuuint64_t strides[3] = {(cuuint64_t)COUT * 2, (cuuint64_t)W * COUT * 2, (cuuint64_t)H * W * COUT * 2};
+    const cuuint32_t box[4] = {64, kHaloSubW, kHaloTileH, 1};
+    int rc = make_map(&m_out, out, 4, dims, strides, box);
+    if (rc) return rc;
+  }
+  DeviceInfo di;
+  int rc = get_device_info(&di);
+  if (rc) return rc;
+  const int tw_px = kHaloSubW * C::kMT;
+  const int tiles_h = (H + kHaloTileH - 1) / kHaloTileH, tiles_w = (W + tw_px - 1) / tw_px;
+  const int num_tiles = N * tiles_h * tiles_w;
+  const int grid = num_tiles < di.sm_count ? num_tiles : di.sm_count;
+  auto kern = conv3x3_halo_kernel<COUT>;
+  MRFP_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
+  kern<<<grid, kThreads, C::kSmemBytes, stream>>>(m_in, m_w, m_out, cin, dil, tiles_h, tiles_w, num_tiles, cnt_h, cnt_w,
+                                                  stat_acc, bo_mode);
+  MRFP_CUDA_TRY(cudaGetLastError());
+  return MRFP_OK;
+}
+
 }  // namespace
 
 bool conv3x3_tc_supported(int cin, int cout) {
@@ -364,6 +621,15 @@ int conv3x3_tc_bf16(const __nv_bfloat16* in, const __nv_bfloat16* wpack, __nv_bf
                     cudaStream_t stream) {
   if (!conv3x3_tc_supported(cin, cout)) return MRFP_ERR_UNSUPPORTED;
   if (((uintptr_t)in | (uintptr_t)wpack | (uintptr_t)out) & 15) return MRFP_ERR_WORKSPACE;
+  static const int mode = getenv("MRFP_CONV_MODE") ? atoi(getenv("MRFP_CONV_MODE")) : 0;   // 0 = one box per tap, 1 = halo tile
+  static const int bo_mode = getenv("MRFP_CONV_BO") ? atoi(getenv("MRFP_CONV_BO")) : 1;
+  if (mode == 1 && dil <= 2) {
+    switch (cout) {
+      case 64: return launch_halo<64>(in, wpack, out, N, H, W, cin, dil, cnt_h, cnt_w, stat_acc, bo_mode, stream);
+      case 128: return launch_halo<128>(in, wpack, out, N, H, W, cin, dil, cnt_h, cnt_w, stat_acc, bo_mode, stream);
+      case 256: return launch_halo<256>(in, wpack, out, N, H, W, cin, dil, cnt_h, cnt_w, stat_acc, bo_mode, stream);
+    }
+  }
   switch (cout) {
     case 64: return launch<64>(in, wpack, out, N, H, W, cin, dil, cnt_h, cnt_w, stat_acc, stream);
     case 128: return launch<128>(in, wpack, out, N, H, W, cin, dil, cnt_h, cnt_w, stat_acc, stream);

@@ -34,6 +34,13 @@ template <> struct Elem<float> {
   }
   static __device__ __forceinline__ float to_float(float x) { return x; }
   static __device__ __forceinline__ float from_float(float x) { return x; }
+  struct Raw { float4 a, b; };                       // 8 channels as loaded, before unpacking
+  static __device__ __forceinline__ Raw load_raw(const float* p) {
+    return Raw{*reinterpret_cast<const float4*>(p), *reinterpret_cast<const float4*>(p + 4)};
+  }
+  static __device__ __forceinline__ void add_raw(const Raw& r, float (&v)[8]) {
+    v[0] += r.a.x; v[1] += r.a.y; v[2] += r.a.z; v[3] += r.a.w; v[4] += r.b.x; v[5] += r.b.y; v[6] += r.b.z; v[7] += r.b.w;
+  }
 };
 template <> struct Elem<__nv_bfloat16> {
   static __device__ __forceinline__ void load8(const __nv_bfloat16* p, float (&v)[8]) {
@@ -56,45 +63,66 @@ template <> struct Elem<__nv_bfloat16> {
   }
   static __device__ __forceinline__ float to_float(__nv_bfloat16 x) { return __bfloat162float(x); }
   static __device__ __forceinline__ __nv_bfloat16 from_float(float x) { return __float2bfloat16_rn(x); }
+  typedef uint4 Raw;
+  static __device__ __forceinline__ Raw load_raw(const __nv_bfloat16* p) { return *reinterpret_cast<const uint4*>(p); }
+  static __device__ __forceinline__ void add_raw(const Raw& r, float (&v)[8]) {
+    const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      v[2 * i] += __uint_as_float(w[i] << 16);
+      v[2 * i + 1] += __uint_as_float(w[i] & 0xffff0000u);
+    }
+  }
 };
 
 // ------------------------------------------------------------------------------------------------------
 // layout conversion at the module boundary
 // ------------------------------------------------------------------------------------------------------
+// Both kernels move a 64-channel x 128-pixel tile through shared memory, so the fp32 NCHW side is touched in 512-byte
+// runs per channel (16-byte accesses, a full warp per run) and the NHWC side in whole 128-byte channel vectors.
+constexpr int kLayPx = 128;
+constexpr int kLayRow = 133;                          // odd row pitch; pixel px sits in column (px & 3) * 33 + (px >> 2),
+__device__ __forceinline__ int lay_col(int px) { return (px & 3) * 33 + (px >> 2); }   // so both access patterns spread over the banks
+
 // src fp32 [N][C][HW] -> dst T [N][HW][C]; accumulate adds into dst (gradient of OCout_dec joining the chain).
-// 64 channels x 64 pixels per block through shared memory: 256-byte row reads, 16-byte channel-vector writes.
 template <typename T>
 __global__ void __launch_bounds__(256)
 nchw_to_nhwc_kernel(const float* __restrict__ src, T* __restrict__ dst, int C, int HW, int accumulate) {
-  __shared__ float tile[64][65];   // [channel][pixel]
-  const int n = blockIdx.z, c0 = blockIdx.y * 64, p0 = blockIdx.x * 64, t = threadIdx.x;
+  __shared__ float tile[64][kLayRow];   // [channel][lay_col(pixel)]
+  const int n = blockIdx.z, c0 = blockIdx.y * 64, p0 = blockIdx.x * kLayPx, t = threadIdx.x;
   const float* s = src + (size_t)n * C * HW;
   T* d = dst + (size_t)n * C * HW;
-  const bool vec = (HW & 1) == 0;
+  const bool vec = (HW & 3) == 0;
   {
-    const int px = (t & 31) * 2, crow = t >> 5;
+    const int px = (t & 31) * 4, crow = t >> 5;
 #pragma unroll
     for (int pass = 0; pass < 8; ++pass) {
       const int c = crow + pass * 8, p = p0 + px;
-      float v0 = 0.f, v1 = 0.f;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
       if (c0 + c < C) {
         const float* q = s + (size_t)(c0 + c) * HW + p;
-        if (vec && p + 1 < HW) { const float2 v = *reinterpret_cast<const float2*>(q); v0 = v.x; v1 = v.y; }
-        else { if (p < HW) v0 = q[0]; if (p + 1 < HW) v1 = q[1]; }
+        if (vec && p + 3 < HW) v = *reinterpret_cast<const float4*>(q);
+        else {
+          if (p < HW) v.x = q[0];
+          if (p + 1 < HW) v.y = q[1];
+          if (p + 2 < HW) v.z = q[2];
+          if (p + 3 < HW) v.w = q[3];
+        }
       }
-      tile[c][px] = v0; tile[c][px + 1] = v1;
+      const int col = px >> 2;                          // lay_col(px + k) = 33 * k + col
+      tile[c][col] = v.x; tile[c][33 + col] = v.y; tile[c][66 + col] = v.z; tile[c][99 + col] = v.w;
     }
   }
   __syncthreads();
   {
     const int cg = t & 7, pl = t >> 3;
 #pragma unroll
-    for (int pass = 0; pass < 2; ++pass) {
+    for (int pass = 0; pass < kLayPx / 32; ++pass) {
       const int px = pl + pass * 32, p = p0 + px, c = c0 + cg * 8;
       if (p < HW && c < C) {
         float v[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) v[j] = tile[cg * 8 + j][px];
+        for (int j = 0; j < 8; ++j) v[j] = tile[cg * 8 + j][lay_col(px)];
         T* q = d + (size_t)p * C + c;
         if (accumulate) {
           float o[8];
@@ -114,9 +142,12 @@ __global__ void __launch_bounds__(256)
 nhwc_to_nchw_kernel(const T* __restrict__ y, float* __restrict__ out, const float* __restrict__ add,
                     const int* __restrict__ idx_h, const int* __restrict__ idx_w, const float* __restrict__ scale,
                     const float* __restrict__ shift, int C, int IH, int IW, int OH, int OW) {
-  __shared__ float tile[64][65];   // [channel][pixel]
-  const int n = blockIdx.x / OH, oh = blockIdx.x % OH, t = threadIdx.x;
-  const int c0 = blockIdx.y * 64, w0 = blockIdx.z * 64;
+  __shared__ float tile[64][kLayRow];   // [channel][lay_col(pixel)]
+  // flat grid, output rows fastest, then channel tiles, then w-tiles
+  const int ct = (C + 63) >> 6, rows = (int)(gridDim.x / (((OW + kLayPx - 1) / kLayPx) * ct));
+  const int orow = blockIdx.x % rows, rem = blockIdx.x / rows;
+  const int n = orow / OH, oh = orow - n * OH, t = threadIdx.x;
+  const int c0 = (rem % ct) * 64, w0 = (rem / ct) * kLayPx;
   const int sh = idx_h ? idx_h[oh] : oh;
   const T* row = y + ((size_t)n * IH + sh) * IW * C;
   {
@@ -127,7 +158,7 @@ nhwc_to_nchw_kernel(const T* __restrict__ y, float* __restrict__ out, const floa
       for (int j = 0; j < 8; ++j) { sc[j] = scale[c + j]; sf[j] = shift[c + j]; }
     }
 #pragma unroll
-    for (int pass = 0; pass < 2; ++pass) {
+    for (int pass = 0; pass < kLayPx / 32; ++pass) {
       const int px = pl + pass * 32, ow = w0 + px;
       float v[8];
 #pragma unroll
@@ -141,25 +172,26 @@ nhwc_to_nchw_kernel(const T* __restrict__ y, float* __restrict__ out, const floa
         }
       }
 #pragma unroll
-      for (int j = 0; j < 8; ++j) tile[cg * 8 + j][px] = v[j];
+      for (int j = 0; j < 8; ++j) tile[cg * 8 + j][lay_col(px)] = v[j];
     }
   }
   __syncthreads();
   {
-    const int px = (t & 31) * 2, crow = t >> 5;
-    const bool vec = (OW & 1) == 0;
+    const int px = (t & 31) * 4, crow = t >> 5;
+    const bool vec = (OW & 3) == 0;
 #pragma unroll
     for (int pass = 0; pass < 8; ++pass) {
       const int c = crow + pass * 8, ow = w0 + px;
       if (c0 + c < C && ow < OW) {
         const size_t o = (((size_t)n * C + c0 + c) * OH + oh) * OW + ow;
-        float v0 = tile[c][px], v1 = tile[c][px + 1];
-        if (vec && ow + 1 < OW) {
-          if (add) { const float2 a2 = *reinterpret_cast<const float2*>(add + o); v0 += a2.x; v1 += a2.y; }
-          *reinterpret_cast<float2*>(out + o) = make_float2(v0, v1);
+        const int col = px >> 2;
+        float4 v = make_float4(tile[c][col], tile[c][33 + col], tile[c][66 + col], tile[c][99 + col]);
+        if (vec && ow + 3 < OW) {
+          if (add) { const float4 a4 = *reinterpret_cast<const float4*>(add + o); v.x += a4.x; v.y += a4.y; v.z += a4.z; v.w += a4.w; }
+          *reinterpret_cast<float4*>(out + o) = v;
         } else {
-          out[o] = add ? v0 + add[o] : v0;
-          if (ow + 1 < OW) out[o + 1] = add ? v1 + add[o + 1] : v1;
+          const float vv[4] = {v.x, v.y, v.z, v.w};
+          for (int i = 0; i < 4 && ow + i < OW; ++i) out[o + i] = add ? vv[i] + add[o + i] : vv[i];
         }
       }
     }
@@ -169,28 +201,41 @@ nhwc_to_nchw_kernel(const T* __restrict__ y, float* __restrict__ out, const floa
 // ------------------------------------------------------------------------------------------------------
 // forward element-wise pass: A_next[n][oh][ow][c] = ReLU(scale[c] * Y[n][ih[oh]][iw[ow]][c] + shift[c])
 // ------------------------------------------------------------------------------------------------------
+// A block walks whole output rows (the source row is block-uniform); a thread keeps a fixed 8-channel group, so the
+// BN scale/shift live in registers and no per-element index arithmetic is left.
 template <typename T>
 __global__ void __launch_bounds__(256)
 bn_relu_resample_kernel(const T* __restrict__ y, T* __restrict__ a, const int* __restrict__ idx_h,
                         const int* __restrict__ idx_w, const float* __restrict__ scale,
                         const float* __restrict__ shift, int N, int C, int IH, int IW, int OH, int OW) {
-  const int cg = C >> 3;
-  const long long total = (long long)N * OH * OW * cg;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int c = (int)(i % cg) << 3;
-    long long p = i / cg;
-    const int ow = (int)(p % OW); p /= OW;
-    const int oh = (int)(p % OH);
-    const int n = (int)(p / OH);
-    float v[8];
-    Elem<T>::load8(y + (((size_t)n * IH + idx_h[oh]) * IW + idx_w[ow]) * C + c, v);
-    const float4 s0 = *reinterpret_cast<const float4*>(scale + c), s1 = *reinterpret_cast<const float4*>(scale + c + 4);
-    const float4 h0 = *reinterpret_cast<const float4*>(shift + c), h1 = *reinterpret_cast<const float4*>(shift + c + 4);
-    const float sc[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
-    const float sf[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
+  const int cg = C >> 3, pstep = 256 / cg;
+  const int c = (threadIdx.x % cg) << 3, pl = threadIdx.x / cg;
+  float sc[8], sf[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) v[j] = fmaxf(fmaf(sc[j], v[j], sf[j]), 0.f);
-    Elem<T>::store8(a + (size_t)i * 8, v);
+  for (int j = 0; j < 8; ++j) { sc[j] = scale[c + j]; sf[j] = shift[c + j]; }
+  for (int row = blockIdx.x; row < N * OH; row += gridDim.x) {
+    const int n = row / OH, oh = row - n * OH;
+    const T* yrow = y + ((size_t)n * IH + idx_h[oh]) * IW * C + c;
+    T* arow = a + (size_t)row * OW * C + c;
+    int ow = pl;
+    for (; ow + 3 * pstep < OW; ow += 4 * pstep) {       // four independent 16-byte loads in flight per thread
+      float v[4][8];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) Elem<T>::load8(yrow + (size_t)idx_w[ow + u * pstep] * C, v[u]);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[u][j] = fmaxf(fmaf(sc[j], v[u][j], sf[j]), 0.f);
+        Elem<T>::store8(arow + (size_t)(ow + u * pstep) * C, v[u]);
+      }
+    }
+    for (; ow < OW; ow += pstep) {
+      float v[8];
+      Elem<T>::load8(yrow + (size_t)idx_w[ow] * C, v);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = fmaxf(fmaf(sc[j], v[j], sf[j]), 0.f);
+      Elem<T>::store8(arow + (size_t)ow * C, v);
+    }
   }
 }
 
@@ -357,63 +402,93 @@ bn_bwd_reduce_kernel(const T* __restrict__ dA, const T* __restrict__ y, const in
 }
 
 template <typename T>
-__global__ void __launch_bounds__(256, 2)
+__global__ void __launch_bounds__(256, 3)
 bn_bwd_apply_kernel(const T* __restrict__ dA, const T* __restrict__ y, T* __restrict__ dY,
                     const int* __restrict__ start_h, const int* __restrict__ cnt_h, const int* __restrict__ start_w,
                     const int* __restrict__ cnt_w, const float* __restrict__ stats, const float* __restrict__ gamma,
                     const double* __restrict__ acc, int N, int C, int IH, int IW, int OH, int OW, double count) {
+  // per-channel constants live in shared memory (read as two float4 per use): registers are kept for loads in flight
+  __shared__ __align__(16) float s_scale[kMaxC], s_shift[kMaxC], s_P[kMaxC], s_Q[kMaxC], s_R[kMaxC];
   const int cg = C >> 3, pstep = 256 / cg;
   const int c = (threadIdx.x % cg) << 3, pl = threadIdx.x / cg;
-  float scale[8], shift[8], P[8], Q[8], R[8];
-#pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const double mean = stats[c + j], invstd = stats[kMaxC + c + j], gm = gamma[c + j];
-    scale[j] = stats[2 * kMaxC + c + j]; shift[j] = stats[3 * kMaxC + c + j];
-    const double S1 = acc[c + j], S2 = invstd * (acc[kMaxC + c + j] - mean * S1);
+  for (int j = threadIdx.x; j < C; j += 256) {
+    const double mean = stats[j], invstd = stats[kMaxC + j], gm = gamma[j];
+    s_scale[j] = stats[2 * kMaxC + j]; s_shift[j] = stats[3 * kMaxC + j];
+    const double S1 = acc[j], S2 = invstd * (acc[kMaxC + j] - mean * S1);
     const double M1 = gm * S1 / count, M2 = gm * S2 / count;
     const double r = invstd * invstd * M2;
-    P[j] = (float)(invstd * gm); R[j] = (float)r; Q[j] = (float)(invstd * M1 - mean * r);
+    s_P[j] = (float)(invstd * gm); s_R[j] = (float)r; s_Q[j] = (float)(invstd * M1 - mean * r);
   }
+  __syncthreads();
+  auto ld8 = [&](const float* t, float (&v)[8]) {
+    const float4 a = *reinterpret_cast<const float4*>(t + c), b = *reinterpret_cast<const float4*>(t + c + 4);
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+  };
+  // one source pixel: sum of its <= 2x2 replicas of dA (the reference geometry: x1.2 up, x0.8 down), general loop otherwise
+  typedef typename Elem<T>::Raw Raw;
+  // raw (still packed) loads of one source pixel: y and its <= 2x2 replicas of dA (the reference geometry: x1.2 up,
+  // x0.8 down); zero bit patterns add nothing
+  struct Px { Raw y, g00, g01, g10, g11; };
+  auto fetch = [&](const T* yrow, const T* d0, int x, int nh, int w0, int nw) {
+    Px p = {};
+    p.y = Elem<T>::load_raw(yrow + (size_t)x * C);
+    const bool a0 = nh > 0, a1 = nh > 1, b0 = nw > 0, b1 = nw > 1;
+    const T* q = d0 + (size_t)w0 * C;
+    if (a0 && b0) p.g00 = Elem<T>::load_raw(q);
+    if (a0 && b1) p.g01 = Elem<T>::load_raw(q + C);
+    if (a1 && b0) p.g10 = Elem<T>::load_raw(q + (size_t)OW * C);
+    if (a1 && b1) p.g11 = Elem<T>::load_raw(q + (size_t)OW * C + C);
+    return p;
+  };
+  auto finish = [&](const float (&sd)[8], const Raw& yraw, float cnt, T* dst) {
+    float o[8], yv[8], k0[8], k1[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) yv[j] = 0.f;
+    Elem<T>::add_raw(yraw, yv);
+    ld8(s_scale, k0); ld8(s_shift, k1);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o[j] = fmaf(k0[j], yv[j], k1[j]) > 0.f ? sd[j] : 0.f;
+    ld8(s_P, k0);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o[j] *= k0[j];
+    ld8(s_R, k0); ld8(s_Q, k1);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o[j] -= cnt * fmaf(k0[j], yv[j], k1[j]);
+    Elem<T>::store8(dst, o);
+  };
+  auto finish_px = [&](const Px& p, float cnt, T* dst) {
+    float sd[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) sd[j] = 0.f;
+    Elem<T>::add_raw(p.g00, sd); Elem<T>::add_raw(p.g01, sd); Elem<T>::add_raw(p.g10, sd); Elem<T>::add_raw(p.g11, sd);
+    finish(sd, p.y, cnt, dst);
+  };
   for (int row = blockIdx.x; row < N * IH; row += gridDim.x) {
     const int n = row / IH, sy = row % IH;
     const int h0 = start_h[sy], nh = cnt_h[sy];
     const T* yrow = y + (size_t)row * IW * C + c;
     T* orow = dY + (size_t)row * IW * C + c;
     const T* d0 = dA + ((size_t)n * OH + h0) * OW * C + c;
-    for (int x = pl; x < IW; x += pstep) {
+    int x = pl;
+    if (nh <= 2) {
+      for (; x + pstep < IW; x += 2 * pstep) {           // two source pixels per iteration: up to 10 loads in flight
+        const int x1 = x + pstep;
+        const int wa = start_w[x], na = cnt_w[x], wb = start_w[x1], nb = cnt_w[x1];
+        if (na > 2 || nb > 2) break;
+        const Px pa = fetch(yrow, d0, x, nh, wa, na), pb = fetch(yrow, d0, x1, nh, wb, nb);
+        finish_px(pa, (float)(nh * na), orow + (size_t)x * C);
+        finish_px(pb, (float)(nh * nb), orow + (size_t)x1 * C);
+      }
+    }
+    for (; x < IW; x += pstep) {                         // row remainder and any other geometry
       const int w0 = start_w[x], nw = cnt_w[x];
-      float sd[8], yv[8];
+      float sd[8];
 #pragma unroll
       for (int j = 0; j < 8; ++j) sd[j] = 0.f;
-      Elem<T>::load8(yrow + (size_t)x * C, yv);
-      if (nh <= 2 && nw <= 2) {        // the reference geometry (x1.2 up, x0.8 down): at most 2x2 replicas
-        float g00[8], g01[8], g10[8], g11[8];
-        const bool a0 = nh > 0, a1 = nh > 1, b0 = nw > 0, b1 = nw > 1;
-        const T* q = d0 + (size_t)w0 * C;
-        if (a0 && b0) Elem<T>::load8(q, g00);
-        if (a0 && b1) Elem<T>::load8(q + C, g01);
-        if (a1 && b0) Elem<T>::load8(q + (size_t)OW * C, g10);
-        if (a1 && b1) Elem<T>::load8(q + (size_t)OW * C + C, g11);
-#pragma unroll
-        for (int j = 0; j < 8; ++j)
-          sd[j] = ((a0 && b0) ? g00[j] : 0.f) + ((a0 && b1) ? g01[j] : 0.f) + ((a1 && b0) ? g10[j] : 0.f) + ((a1 && b1) ? g11[j] : 0.f);
-      } else {
-        for (int a = 0; a < nh; ++a)
-          for (int b = 0; b < nw; ++b) {
-            float g[8];
-            Elem<T>::load8(d0 + ((size_t)a * OW + w0 + b) * C, g);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) sd[j] += g[j];
-          }
-      }
-      const float cnt = (float)(nh * nw);
-      float o[8];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float t = fmaf(scale[j], yv[j], shift[j]) > 0.f ? sd[j] : 0.f;
-        o[j] = P[j] * t - cnt * fmaf(R[j], yv[j], Q[j]);
-      }
-      Elem<T>::store8(orow + (size_t)x * C, o);
+      const Raw yraw = Elem<T>::load_raw(yrow + (size_t)x * C);
+      for (int a = 0; a < nh; ++a)
+        for (int b = 0; b < nw; ++b) Elem<T>::add_raw(Elem<T>::load_raw(d0 + ((size_t)a * OW + w0 + b) * C), sd);
+      finish(sd, yraw, (float)(nh * nw), orow + (size_t)x * C);
     }
   }
 }
@@ -446,6 +521,9 @@ int grid_for(long long work_items, int block, int sm_count, int waves = 8) {
   return g < 1 ? 1 : (int)g;
 }
 
+// blocks for a row-walking kernel (several waves of blocks: a plain cap measured better than an even split)
+int even_grid(int rows, int cap) { return rows < cap ? rows : cap; }
+
 bool pow2_ge8(int c) { return c >= 8 && c <= kMaxC && (c & (c - 1)) == 0; }
 
 template <typename T>
@@ -467,7 +545,7 @@ int hrfp_forward(const mrfp_hrfp_plan* P, const float* xp, const float* const* W
   T* bufB = reinterpret_cast<T*>(ws + P->bufs_off + P->buf_a_bytes);
   {
     const int HW = P->xh * P->xw;
-    dim3 g((HW + 63) / 64, (P->cin + 63) / 64, P->N);
+    dim3 g((HW + kLayPx - 1) / kLayPx, (P->cin + 63) / 64, P->N);
     nchw_to_nhwc_kernel<T><<<g, 256, 0, s>>>(xp, bufA, P->cin, HW, 0);
   }
   T* cur = bufA;
@@ -496,19 +574,18 @@ int hrfp_forward(const mrfp_hrfp_plan* P, const float* xp, const float* const* W
     bn_finalize_kernel<<<1, 256, 0, s>>>(a, gamma[k], beta ? beta[k] : nullptr, rmean ? rmean[k] : nullptr,
                                          rvar ? rvar[k] : nullptr, stats, st.cout, count, momentum, eps);
     if (k == 3 && ocout_dec) {
-      dim3 g(P->N * st.oh, (st.cout + 63) / 64, (st.ow + 63) / 64);
+      const unsigned g = (unsigned)(((st.ow + kLayPx - 1) / kLayPx) * ((st.cout + 63) / 64)) * (unsigned)(P->N * st.oh);
       nhwc_to_nchw_kernel<T><<<g, 256, 0, s>>>(Y, ocout_dec, nullptr, lut + st.idx_h, lut + st.idx_w,
                                                         stats + 2 * kMaxC, stats + 3 * kMaxC, st.cout, st.ch, st.cw,
                                                         st.oh, st.ow);
     }
     if (k == kHrfpStages - 1) {
-      dim3 g(P->N * st.oh, (st.cout + 63) / 64, (st.ow + 63) / 64);
+      const unsigned g = (unsigned)(((st.ow + kLayPx - 1) / kLayPx) * ((st.cout + 63) / 64)) * (unsigned)(P->N * st.oh);
       nhwc_to_nchw_kernel<T><<<g, 256, 0, s>>>(Y, ocout, x_add, lut + st.idx_h, lut + st.idx_w,
                                                         stats + 2 * kMaxC, stats + 3 * kMaxC, st.cout, st.ch, st.cw,
                                                         st.oh, st.ow);
     } else if (k + 1 < last) {
-      const long long items = (long long)P->N * st.oh * st.ow * (st.cout / 8);
-      bn_relu_resample_kernel<T><<<grid_for(items, 256, di.sm_count), 256, 0, s>>>(
+      bn_relu_resample_kernel<T><<<even_grid(P->N * st.oh, di.sm_count * 8), 256, 0, s>>>(
           Y, nxt, lut + st.idx_h, lut + st.idx_w, stats + 2 * kMaxC, stats + 3 * kMaxC, P->N, st.cout, st.ch, st.cw,
           st.oh, st.ow);
       T* t = cur; cur = nxt; nxt = t;
@@ -534,7 +611,7 @@ int hrfp_backward(const mrfp_hrfp_plan* P, const float* g_ocout, const float* g_
     const float* gin = (k == kHrfpStages - 1) ? g_ocout : (k == 3 ? g_ocout_dec : nullptr);
     if (gin) {
       const int HW = st.oh * st.ow;
-      dim3 g((HW + 63) / 64, (st.cout + 63) / 64, P->N);
+      dim3 g((HW + kLayPx - 1) / kLayPx, (st.cout + 63) / 64, P->N);
       T* dst = dA ? dA : g0;
       nchw_to_nhwc_kernel<T><<<g, 256, 0, s>>>(gin, dst, st.cout, HW, dA ? 1 : 0);
       if (!dA) { dA = g0; other = g1; }
@@ -544,8 +621,7 @@ int hrfp_backward(const mrfp_hrfp_plan* P, const float* g_ocout, const float* g_
     const float* stats = reinterpret_cast<const float*>(saved + P->stats_off) + (size_t)k * 4 * kMaxC;
     double* a = acc + (size_t)k * 2 * kMaxC;
     const double count = (double)P->N * st.oh * st.ow;
-    const int cap = di.sm_count * 8;
-    const int grid_r = P->N * st.oh < cap ? P->N * st.oh : cap, grid_a = P->N * st.ch < cap ? P->N * st.ch : cap;
+    const int grid_r = even_grid(P->N * st.oh, di.sm_count * 8), grid_a = even_grid(P->N * st.ch, di.sm_count * 9);
     bn_bwd_reduce_kernel<T><<<grid_r, 256, 0, s>>>(dA, Y, lut + st.idx_h, lut + st.idx_w, stats, a, P->N, st.cout, st.ch,
                                                    st.cw, st.oh, st.ow);
     bn_bwd_apply_kernel<T><<<grid_a, 256, 0, s>>>(dA, Y, dY, lut + st.start_h, lut + st.cnt_h, lut + st.start_w,
@@ -573,7 +649,7 @@ int hrfp_backward(const mrfp_hrfp_plan* P, const float* g_ocout, const float* g_
     MRFP_CUDA_TRY(cudaMemsetAsync(g_xp, 0, (size_t)P->N * P->cin * P->xh * P->xw * sizeof(float), s));
     return MRFP_OK;
   }
-  dim3 g(P->N * P->xh, (P->cin + 63) / 64, (P->xw + 63) / 64);
+  const unsigned g = (unsigned)(((P->xw + kLayPx - 1) / kLayPx) * ((P->cin + 63) / 64)) * (unsigned)(P->N * P->xh);
   nhwc_to_nchw_kernel<T><<<g, 256, 0, s>>>(dA, g_xp, nullptr, nullptr, nullptr, nullptr, nullptr, P->cin,
                                                     P->xh, P->xw, P->xh, P->xw);
   MRFP_CUDA_TRY(cudaGetLastError());
@@ -731,7 +807,7 @@ static int hrfp_plus_add_impl(const mrfp_hrfp_plan* P, const char* saved, const 
   const HrfpStage& st = P->st[3];
   const T* Y = reinterpret_cast<const T*>(saved + st.y_off);
   const float* stats = reinterpret_cast<const float*>(saved + P->stats_off) + (size_t)3 * 4 * kMaxC;
-  dim3 g(P->N * st.oh, (st.cout + 63) / 64, (st.ow + 63) / 64);
+  const unsigned g = (unsigned)(((st.ow + kLayPx - 1) / kLayPx) * ((st.cout + 63) / 64)) * (unsigned)(P->N * st.oh);
   nhwc_to_nchw_kernel<T><<<g, 256, 0, s>>>(Y, out, dec1_up, lut + st.idx_h, lut + st.idx_w, stats + 2 * kMaxC,
                                             stats + 3 * kMaxC, st.cout, st.ch, st.cw, st.oh, st.ow);
   MRFP_CUDA_TRY(cudaGetLastError());
