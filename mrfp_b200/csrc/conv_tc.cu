@@ -37,7 +37,7 @@ template <int COUT> struct Cfg {
   static constexpr int kOutBufs = COUT == 64 ? 2 : 1;
   static constexpr int kTmemCols = 2 * kMT * COUT;                  // 256 / 512 / 512: powers of two
   static constexpr int kSmemBytes = kStages * (kAStageBytes + kBTileBytes) + kOutBufs * kStageOutBytes +
-                                    2 * COUT * 4 + 256 /* barriers */ + 1024 /* alignment slack */;
+                                    2 * COUT * 4 + 512 /* row weights */ + 256 /* barriers */ + 1024 /* alignment slack */;
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -99,6 +99,11 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
       : "r"(taddr));
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
 
 // transposed butterfly: on return x[0] of lane l = sum over the 32 lanes of their x[l]   (31 shuffles)
@@ -129,7 +134,8 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_cons
   unsigned char* sB = sA + C::kStages * C::kAStageBytes;
   unsigned char* sOut = sB + C::kStages * C::kBTileBytes;
   float* s_stats = reinterpret_cast<float*>(sOut + C::kOutBufs * kStageOutBytes);
-  uint64_t* full = reinterpret_cast<uint64_t*>(s_stats + 2 * COUT);
+  float* s_wgt = s_stats + 2 * COUT;                                    // [128] replication count of each tile row's pixel
+  uint64_t* full = reinterpret_cast<uint64_t*>(s_wgt + 128);
   uint64_t* empty = full + C::kStages;
   uint64_t* tmem_full = empty + C::kStages;
   uint64_t* tmem_empty = tmem_full + 2;
@@ -154,8 +160,8 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_cons
   const uint32_t tmem_base = *tmem_ptr;
 
   if (warp == 0) {
-    // ===================== TMA producer =====================
-    if (lane == 0) {
+    // ===================== TMA producer (whole warp walks, one elected lane issues) =====================
+    {
       int stage = 0; uint32_t phase = 0;
       for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
         const int tw = t % tiles_w, th = (t / tiles_w) % tiles_h, n = t / (tiles_w * tiles_h);
@@ -164,9 +170,12 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_cons
           const int dy = (tap / 3 - 1) * dil, dx = (tap % 3 - 1) * dil;
           for (int kc = 0; kc < CIN / kBlockK; ++kc) {
             mbar_wait(&empty[stage], phase ^ 1);
-            mbar_expect_tx(&full[stage], C::kAStageBytes + C::kBTileBytes);
-            tma_load_4d(sA + stage * C::kAStageBytes, &tmap_in, &full[stage], kc * kBlockK, w0 + dx, h0 + dy, n);
-            tma_load_2d(sB + stage * C::kBTileBytes, &tmap_w, &full[stage], kc * kBlockK, tap * COUT);
+            if (elect_one()) {
+              mbar_expect_tx(&full[stage], C::kAStageBytes + C::kBTileBytes);
+              tma_load_4d(sA + stage * C::kAStageBytes, &tmap_in, &full[stage], kc * kBlockK, w0 + dx, h0 + dy, n);
+              tma_load_2d(sB + stage * C::kBTileBytes, &tmap_w, &full[stage], kc * kBlockK, tap * COUT);
+            }
+            __syncwarp();
             if (++stage == C::kStages) { stage = 0; phase ^= 1; }
           }
         }
@@ -174,31 +183,39 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_cons
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
+    // The whole warp walks the loops with warp-uniform values (descriptors stay in uniform registers); one elected
+    // lane issues the tcgen05 instructions.
+    {
       // instruction descriptor: D=f32, A=B=bf16, both K-major, N=COUT, M=128
       constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(COUT >> 3) << 17) | ((128u >> 4) << 24);
+      const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
+      const uint32_t sA_u = smem_u32(sA), sB_u = smem_u32(sB);
       int stage = 0; uint32_t phase = 0;
       int it = 0;
       for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
         const int acc = it & 1;
         mbar_wait(&tmem_empty[acc], ((it >> 1) & 1) ^ 1);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * C::kMT * COUT);
+        const uint32_t d_tmem = tmem_u + (uint32_t)(acc * C::kMT * COUT);
         for (int ks = 0; ks < nk; ++ks) {
           mbar_wait(&full[stage], phase);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-          const uint64_t da = make_desc_sw128(smem_u32(sA + stage * C::kAStageBytes));
-          const uint64_t db = make_desc_sw128(smem_u32(sB + stage * C::kBTileBytes));
+          if (elect_one()) {
+            const uint64_t da = make_desc_sw128(sA_u + stage * C::kAStageBytes);
+            const uint64_t db = make_desc_sw128(sB_u + stage * C::kBTileBytes);
 #pragma unroll
-          for (int k = 0; k < kBlockK / kUmmaK; ++k)   // +32 B per UMMA_K inside the swizzle row
+            for (int k = 0; k < kBlockK / kUmmaK; ++k)   // +32 B per UMMA_K inside the swizzle row
 #pragma unroll
-            for (int mt = 0; mt < C::kMT; ++mt)        // the second M sub-tile is the next 128 rows (16 KiB) of the A box
-              umma_bf16(d_tmem + (uint32_t)(mt * COUT), da + (uint64_t)(mt * (kATileBytes >> 4) + k * 2),
-                        db + (uint64_t)(k * 2), idesc, (ks | k) != 0);
-          umma_commit(&empty[stage]);                  // frees the smem slot when the MMAs have read it
+              for (int mt = 0; mt < C::kMT; ++mt)        // the second M sub-tile is the next 128 rows (16 KiB) of the A box
+                umma_bf16(d_tmem + (uint32_t)(mt * COUT), da + (uint64_t)(mt * (kATileBytes >> 4) + k * 2),
+                          db + (uint64_t)(k * 2), idesc, (ks | k) != 0);
+            umma_commit(&empty[stage]);                  // frees the smem slot when the MMAs have read it
+          }
+          __syncwarp();
           if (++stage == C::kStages) { stage = 0; phase ^= 1; }
         }
-        umma_commit(&tmem_full[acc]);                  // accumulator complete
+        if (elect_one()) umma_commit(&tmem_full[acc]);   // accumulator complete
+        __syncwarp();
       }
     }
   } else {
@@ -206,7 +223,12 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_cons
     const int q = warp & 3;                     // TMEM lane quarter this warp may access
     const int r = q * 32 + lane;                // accumulator row = pixel inside the tile
     const int hl = r / kTileW, wl = r % kTileW;
-    const bool leader = threadIdx.x == 64;      // first epilogue thread issues the TMA stores
+    const int et = threadIdx.x - 64;            // 0..127
+    const bool leader = et == 0;                // first epilogue thread issues the TMA stores
+    // statistics: thread (channel pair cp, row group pg) sums 32 rows of the bf16 staging tile (the values that are
+    // stored and later normalised), weighted by the replication count of each row's pixel
+    const int cp = et & 31, pg = et >> 5;
+    float a1x = 0.f, a1y = 0.f, a2x = 0.f, a2y = 0.f;
     int it = 0, obuf = 0;
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
       const int tw = t % tiles_w, th = (t / tiles_w) % tiles_h, n = t / (tiles_w * tiles_h);
@@ -217,29 +239,15 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_cons
 #pragma unroll 1
       for (int jj = 0; jj < C::kMT * (COUT / 64); ++jj) {
         const int mt = jj / (COUT / 64), j = jj % (COUT / 64);
-        float wgt = 0.f;
-        if (stat_acc) wgt = (float)(cnt_h[h0 + mt * kTileH + hl] * cnt_w[w0 + wl]);   // 0 outside the image (zero-padded tables)
         unsigned char* ob = sOut + obuf * kStageOutBytes;
         // the TMA store that last read this staging buffer must have drained
         if (leader) asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(C::kOutBufs - 1) : "memory");
         epi_bar_sync();
+        if (stat_acc) s_wgt[r] = (float)(cnt_h[h0 + mt * kTileH + hl] * cnt_w[w0 + wl]);   // 0 outside the image (zero-padded tables)
 #pragma unroll
         for (int half = 0; half < 2; ++half) {
           uint32_t v[32];
           tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((acc * C::kMT + mt) * COUT + j * 64 + half * 32), v);
-          if (stat_acc) {
-            float x1[32], x2[32];
-#pragma unroll
-            for (int i = 0; i < 32; ++i) {
-              const float f = __uint_as_float(v[i]);
-              x1[i] = wgt * f;
-              x2[i] = x1[i] * f;
-            }
-            const float s1 = warp_transpose_sum(x1, lane);
-            const float s2 = warp_transpose_sum(x2, lane);
-            atomicAdd(&s_stats[j * 64 + half * 32 + lane], s1);
-            atomicAdd(&s_stats[COUT + j * 64 + half * 32 + lane], s2);
-          }
 #pragma unroll
           for (int c = 0; c < 4; ++c) {          // four 16-byte chunks (8 channels each) per half
             uint32_t p[4];
@@ -263,10 +271,35 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_cons
           tma_store_4d(&tmap_out, ob, j * 64, w0, h0 + mt * kTileH, n);
           asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         }
+        if (stat_acc) {
+          // channel pair cp lives in 16-byte chunk cp/4 of a row, word cp%4; 32 lanes read one whole (swizzled) row
+          const unsigned char* col = ob + (cp & 3) * 4;
+          const int ch = cp >> 2;
+          float s1x = 0.f, s1y = 0.f, s2x = 0.f, s2y = 0.f;
+#pragma unroll 8
+          for (int i = 0; i < 32; ++i) {
+            const int row = pg * 32 + i;
+            const uint32_t w2 = *reinterpret_cast<const uint32_t*>(col + row * 128 + ((ch ^ (row & 7)) << 4));
+            const float wg = s_wgt[row];
+            const float y0 = __uint_as_float(w2 << 16), y1 = __uint_as_float(w2 & 0xffff0000u);
+            const float t0 = wg * y0, t1 = wg * y1;
+            s1x += t0; s1y += t1;
+            s2x = fmaf(t0, y0, s2x); s2y = fmaf(t1, y1, s2y);
+          }
+          if (COUT == 64) { a1x += s1x; a1y += s1y; a2x += s2x; a2y += s2y; }   // one channel set: keep in registers
+          else {
+            atomicAdd(&s_stats[j * 64 + 2 * cp], s1x); atomicAdd(&s_stats[j * 64 + 2 * cp + 1], s1y);
+            atomicAdd(&s_stats[COUT + j * 64 + 2 * cp], s2x); atomicAdd(&s_stats[COUT + j * 64 + 2 * cp + 1], s2y);
+          }
+        }
         if (++obuf == C::kOutBufs) obuf = 0;
       }
     }
     if (leader) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    if (stat_acc && COUT == 64) {
+      atomicAdd(&s_stats[2 * cp], a1x); atomicAdd(&s_stats[2 * cp + 1], a1y);
+      atomicAdd(&s_stats[COUT + 2 * cp], a2x); atomicAdd(&s_stats[COUT + 2 * cp + 1], a2y);
+    }
     epi_bar_sync();
     if (stat_acc) {
       for (int c = threadIdx.x - 64; c < COUT; c += 128) {
@@ -357,63 +390,75 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_co
   const uint32_t tmem_base = *tmem_ptr;
 
   if (warp == 0) {
-    // ===================== TMA producer =====================
-    if (lane == 0) {
+    // ===================== TMA producer (whole warp walks, one elected lane issues) =====================
+    {
       int as = 0, bs = 0; uint32_t aph = 0, bph = 0;
       for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
         const int tw = t % tiles_w, th = (t / tiles_w) % tiles_h, n = t / (tiles_w * tiles_h);
         const int h0 = th * kHaloTileH, w0 = tw * kHaloSubW * C::kMT;
         for (int kc = 0; kc < nchunks; ++kc) {
           mbar_wait(&empty_a[as], aph ^ 1);
-          mbar_expect_tx(&full_a[as], a_bytes);
-          tma_load_4d(sA + as * C::kAStageBytes, &tmap_in, &full_a[as], kc * kBlockK, w0 - dil, h0 - dil, n);
+          if (elect_one()) {
+            mbar_expect_tx(&full_a[as], a_bytes);
+            tma_load_4d(sA + as * C::kAStageBytes, &tmap_in, &full_a[as], kc * kBlockK, w0 - dil, h0 - dil, n);
+          }
+          __syncwarp();
           if (++as == C::kAStages) { as = 0; aph ^= 1; }
           for (int tap = 0; tap < 9; ++tap) {
             mbar_wait(&empty_b[bs], bph ^ 1);
-            mbar_expect_tx(&full_b[bs], C::kBTileBytes);
-            tma_load_2d(sB + bs * C::kBTileBytes, &tmap_w, &full_b[bs], kc * kBlockK, tap * COUT);
+            if (elect_one()) {
+              mbar_expect_tx(&full_b[bs], C::kBTileBytes);
+              tma_load_2d(sB + bs * C::kBTileBytes, &tmap_w, &full_b[bs], kc * kBlockK, tap * COUT);
+            }
+            __syncwarp();
             if (++bs == C::kBStages) { bs = 0; bph ^= 1; }
           }
         }
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
+    // ===================== MMA issuer (whole warp walks, one elected lane issues) =====================
+    {
       constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(COUT >> 3) << 17) | ((128u >> 4) << 24);
+      const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
+      const uint32_t sA_u = smem_u32(sA), sB_u = smem_u32(sB);
       int as = 0, bs = 0; uint32_t aph = 0, bph = 0;
       int it = 0;
       for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
         const int acc = it & 1;
         mbar_wait(&tmem_empty[acc], ((it >> 1) & 1) ^ 1);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * C::kMT * COUT);
+        const uint32_t d_tmem = tmem_u + (uint32_t)(acc * C::kMT * COUT);
         for (int kc = 0; kc < nchunks; ++kc) {
           mbar_wait(&full_a[as], aph);
-          const uint32_t a_base = smem_u32(sA + as * C::kAStageBytes);
+          const uint32_t a_base = sA_u + as * C::kAStageBytes;
           for (int tap = 0; tap < 9; ++tap) {
             mbar_wait(&full_b[bs], bph);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const uint32_t b_base = smem_u32(sB + bs * C::kBTileBytes);
-            const int row0 = (tap / 3) * dil * C::kBoxW + (tap % 3) * dil;    // first box pixel of this tap's view
+            if (elect_one()) {
+              const uint32_t b_base = sB_u + bs * C::kBTileBytes;
+              const int row0 = (tap / 3) * dil * C::kBoxW + (tap % 3) * dil;    // first box pixel of this tap's view
 #pragma unroll
-            for (int k = 0; k < kBlockK / kUmmaK; ++k) {
-              const uint64_t db = make_desc_sw128(b_base + k * 32);
+              for (int k = 0; k < kBlockK / kUmmaK; ++k) {
+                const uint64_t db = make_desc_sw128(b_base + k * 32);
 #pragma unroll
-              for (int mt = 0; mt < C::kMT; ++mt) {
-                const uint32_t a_addr = a_base + (uint32_t)(row0 + mt * kHaloSubW) * 128u + k * 32;
-                const uint32_t phase = bo_mode ? ((a_addr >> 7) & 7u) : 0u;
-                umma_bf16(d_tmem + (uint32_t)(mt * COUT), make_desc_sw128_view(a_addr, C::kBoxW * 8, phase), db, idesc,
-                          (kc | tap | k) != 0);
+                for (int mt = 0; mt < C::kMT; ++mt) {
+                  const uint32_t a_addr = a_base + (uint32_t)(row0 + mt * kHaloSubW) * 128u + k * 32;
+                  const uint32_t phase = bo_mode ? ((a_addr >> 7) & 7u) : 0u;
+                  umma_bf16(d_tmem + (uint32_t)(mt * COUT), make_desc_sw128_view(a_addr, C::kBoxW * 8, phase), db, idesc,
+                            (kc | tap | k) != 0);
+                }
               }
+              umma_commit(&empty_b[bs]);
+              if (tap == 8) umma_commit(&empty_a[as]);   // the halo tile is free once all 9 taps have read it
             }
-            umma_commit(&empty_b[bs]);
+            __syncwarp();
             if (++bs == C::kBStages) { bs = 0; bph ^= 1; }
           }
-          umma_commit(&empty_a[as]);                   // the halo tile is free once all 9 taps have read it
           if (++as == C::kAStages) { as = 0; aph ^= 1; }
         }
-        umma_commit(&tmem_full[acc]);
+        if (elect_one()) umma_commit(&tmem_full[acc]);
+        __syncwarp();
       }
     }
   } else {
@@ -622,7 +667,7 @@ int conv3x3_tc_bf16(const __nv_bfloat16* in, const __nv_bfloat16* wpack, __nv_bf
   if (!conv3x3_tc_supported(cin, cout)) return MRFP_ERR_UNSUPPORTED;
   if (((uintptr_t)in | (uintptr_t)wpack | (uintptr_t)out) & 15) return MRFP_ERR_WORKSPACE;
   static const int mode = getenv("MRFP_CONV_MODE") ? atoi(getenv("MRFP_CONV_MODE")) : 0;   // 0 = one box per tap, 1 = halo tile
-  static const int bo_mode = getenv("MRFP_CONV_BO") ? atoi(getenv("MRFP_CONV_BO")) : 1;
+  static const int bo_mode = getenv("MRFP_CONV_BO") ? atoi(getenv("MRFP_CONV_BO")) : 0;   // measured: views are swizzled by absolute address, phase field stays 0
   if (mode == 1 && dil <= 2) {
     switch (cout) {
       case 64: return launch_halo<64>(in, wpack, out, N, H, W, cin, dil, cnt_h, cnt_w, stat_acc, bo_mode, stream);
