@@ -121,12 +121,12 @@ __device__ __forceinline__ float warp_transpose_sum(float (&x)[32], int lane) {
   return x[0];
 }
 
-template <int COUT>
+template <int COUT, bool BWD>
 __global__ void __launch_bounds__(kThreads, 1)
 conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constant__ CUtensorMap tmap_w,
                   const __grid_constant__ CUtensorMap tmap_out, int CIN, int dil, int tiles_h, int tiles_w,
                   int num_tiles, const int* __restrict__ cnt_h, const int* __restrict__ cnt_w,
-                  double* __restrict__ stat_acc) {
+                  double* __restrict__ stat_acc, const ConvBwdStats bs) {
   using C = Cfg<COUT>;
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -228,6 +228,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_cons
     // statistics: thread (channel pair cp, row group pg) sums 32 rows of the bf16 staging tile (the values that are
     // stored and later normalised), weighted by the replication count of each row's pixel
     const int cp = et & 31, pg = et >> 5;
+    constexpr bool bwd = BWD;               // dgrad that also takes the previous stage's BN-backward sums (experimental)
     float a1x = 0.f, a1y = 0.f, a2x = 0.f, a2y = 0.f;
     int it = 0, obuf = 0;
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
@@ -243,7 +244,22 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_cons
         // the TMA store that last read this staging buffer must have drained
         if (leader) asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(C::kOutBufs - 1) : "memory");
         epi_bar_sync();
-        if (stat_acc) s_wgt[r] = (float)(cnt_h[h0 + mt * kTileH + hl] * cnt_w[w0 + wl]);   // 0 outside the image (zero-padded tables)
+        if (stat_acc && !bwd) s_wgt[r] = (float)(cnt_h[h0 + mt * kTileH + hl] * cnt_w[w0 + wl]);   // 0 outside the image (zero-padded tables)
+        // dgrad + BN-backward sums: start the gathered loads of the next stage's conv output now, use them after the pack
+        uint32_t yv[32], yvalid = 0;
+        if (bwd) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const int row = pg * 32 + i;
+            const int hh = h0 + mt * kTileH + row / kTileW, ww = w0 + row % kTileW;
+            yv[i] = 0;
+            if (hh < bs.H && ww < bs.W) {
+              yvalid |= 1u << i;
+              yv[i] = __ldg(reinterpret_cast<const uint32_t*>(
+                  bs.y + (((size_t)n * bs.IH + bs.idx_h[hh]) * bs.IW + bs.idx_w[ww]) * COUT + j * 64 + 2 * cp));
+            }
+          }
+        }
 #pragma unroll
         for (int half = 0; half < 2; ++half) {
           uint32_t v[32];
@@ -276,15 +292,33 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_cons
           const unsigned char* col = ob + (cp & 3) * 4;
           const int ch = cp >> 2;
           float s1x = 0.f, s1y = 0.f, s2x = 0.f, s2y = 0.f;
+          if (!bwd) {
 #pragma unroll 8
-          for (int i = 0; i < 32; ++i) {
-            const int row = pg * 32 + i;
-            const uint32_t w2 = *reinterpret_cast<const uint32_t*>(col + row * 128 + ((ch ^ (row & 7)) << 4));
-            const float wg = s_wgt[row];
-            const float y0 = __uint_as_float(w2 << 16), y1 = __uint_as_float(w2 & 0xffff0000u);
-            const float t0 = wg * y0, t1 = wg * y1;
-            s1x += t0; s1y += t1;
-            s2x = fmaf(t0, y0, s2x); s2y = fmaf(t1, y1, s2y);
+            for (int i = 0; i < 32; ++i) {
+              const int row = pg * 32 + i;
+              const uint32_t w2 = *reinterpret_cast<const uint32_t*>(col + row * 128 + ((ch ^ (row & 7)) << 4));
+              const float wg = s_wgt[row];
+              const float y0 = __uint_as_float(w2 << 16), y1 = __uint_as_float(w2 & 0xffff0000u);
+              const float t0 = wg * y0, t1 = wg * y1;
+              s1x += t0; s1y += t1;
+              s2x = fmaf(t0, y0, s2x); s2y = fmaf(t1, y1, s2y);
+            }
+          } else {
+            // U1 = sum mask*dA, U2 = sum mask*dA*y over the (stored, bf16) gradient tile; mask = ReLU'(scale*y + shift)
+            const float2 sc = *reinterpret_cast<const float2*>(bs.scale + j * 64 + 2 * cp);
+            const float2 sf = *reinterpret_cast<const float2*>(bs.shift + j * 64 + 2 * cp);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              const int row = pg * 32 + i;
+              const uint32_t w2 = *reinterpret_cast<const uint32_t*>(col + row * 128 + ((ch ^ (row & 7)) << 4));
+              const float d0 = __uint_as_float(w2 << 16), d1 = __uint_as_float(w2 & 0xffff0000u);
+              const float y0 = __uint_as_float(yv[i] << 16), y1 = __uint_as_float(yv[i] & 0xffff0000u);
+              const bool ok = (yvalid >> i) & 1u;
+              const float t0 = (ok && fmaf(sc.x, y0, sf.x) > 0.f) ? d0 : 0.f;
+              const float t1 = (ok && fmaf(sc.y, y1, sf.y) > 0.f) ? d1 : 0.f;
+              s1x += t0; s1y += t1;
+              s2x = fmaf(t0, y0, s2x); s2y = fmaf(t1, y1, s2y);
+            }
           }
           if (COUT == 64) { a1x += s1x; a1y += s1y; a2x += s2x; a2y += s2y; }   // one channel set: keep in registers
           else {
@@ -575,7 +609,7 @@ int make_map(CUtensorMap* m, const void* base, int rank, const cuuint64_t* dims,
 
 template <int COUT>
 int launch(const __nv_bfloat16* in, const __nv_bfloat16* wpack, __nv_bfloat16* out, int N, int H, int W, int cin,
-           int dil, const int* cnt_h, const int* cnt_w, double* stat_acc, cudaStream_t stream) {
+           int dil, const int* cnt_h, const int* cnt_w, double* stat_acc, const ConvBwdStats& bs, cudaStream_t stream) {
   CUtensorMap m_in, m_w, m_out;
   {
     const cuuint64_t dims[4] = {(cuuint64_t)cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
@@ -605,10 +639,10 @@ int launch(const __nv_bfloat16* in, const __nv_bfloat16* wpack, __nv_bfloat16* o
   const int tiles_h = (H + th_px - 1) / th_px, tiles_w = (W + kTileW - 1) / kTileW;
   const int num_tiles = N * tiles_h * tiles_w;
   const int grid = num_tiles < di.sm_count ? num_tiles : di.sm_count;
-  auto kern = conv3x3_tc_kernel<COUT>;
+  auto kern = bs.y ? conv3x3_tc_kernel<COUT, true> : conv3x3_tc_kernel<COUT, false>;
   MRFP_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<COUT>::kSmemBytes));
   kern<<<grid, kThreads, Cfg<COUT>::kSmemBytes, stream>>>(m_in, m_w, m_out, cin, dil, tiles_h, tiles_w, num_tiles, cnt_h,
-                                                           cnt_w, stat_acc);
+                                                           cnt_w, stat_acc, bs);
   MRFP_CUDA_TRY(cudaGetLastError());
   return MRFP_OK;
 }
@@ -663,12 +697,19 @@ bool conv3x3_tc_supported(int cin, int cout) {
 
 int conv3x3_tc_bf16(const __nv_bfloat16* in, const __nv_bfloat16* wpack, __nv_bfloat16* out, int N, int H, int W,
                     int cin, int cout, int dil, const int* cnt_h, const int* cnt_w, double* stat_acc,
-                    cudaStream_t stream) {
+                    cudaStream_t stream, const ConvBwdStats* bwd_stats) {
+  ConvBwdStats bs = {};
+  if (bwd_stats) {
+    if (!stat_acc || !bwd_stats->y || !bwd_stats->idx_h || !bwd_stats->idx_w || !bwd_stats->scale || !bwd_stats->shift)
+      return MRFP_ERR_NULL_POINTER;
+    bs = *bwd_stats;
+    bs.H = H; bs.W = W;
+  }
   if (!conv3x3_tc_supported(cin, cout)) return MRFP_ERR_UNSUPPORTED;
   if (((uintptr_t)in | (uintptr_t)wpack | (uintptr_t)out) & 15) return MRFP_ERR_WORKSPACE;
   static const int mode = getenv("MRFP_CONV_MODE") ? atoi(getenv("MRFP_CONV_MODE")) : 0;   // 0 = one box per tap, 1 = halo tile
   static const int bo_mode = getenv("MRFP_CONV_BO") ? atoi(getenv("MRFP_CONV_BO")) : 0;   // measured: views are swizzled by absolute address, phase field stays 0
-  if (mode == 1 && dil <= 2) {
+  if (mode == 1 && dil <= 2 && !bwd_stats) {
     switch (cout) {
       case 64: return launch_halo<64>(in, wpack, out, N, H, W, cin, dil, cnt_h, cnt_w, stat_acc, bo_mode, stream);
       case 128: return launch_halo<128>(in, wpack, out, N, H, W, cin, dil, cnt_h, cnt_w, stat_acc, bo_mode, stream);
@@ -676,9 +717,9 @@ int conv3x3_tc_bf16(const __nv_bfloat16* in, const __nv_bfloat16* wpack, __nv_bf
     }
   }
   switch (cout) {
-    case 64: return launch<64>(in, wpack, out, N, H, W, cin, dil, cnt_h, cnt_w, stat_acc, stream);
-    case 128: return launch<128>(in, wpack, out, N, H, W, cin, dil, cnt_h, cnt_w, stat_acc, stream);
-    case 256: return launch<256>(in, wpack, out, N, H, W, cin, dil, cnt_h, cnt_w, stat_acc, stream);
+    case 64: return launch<64>(in, wpack, out, N, H, W, cin, dil, cnt_h, cnt_w, stat_acc, bs, stream);
+    case 128: return launch<128>(in, wpack, out, N, H, W, cin, dil, cnt_h, cnt_w, stat_acc, bs, stream);
+    case 256: return launch<256>(in, wpack, out, N, H, W, cin, dil, cnt_h, cnt_w, stat_acc, bs, stream);
   }
   return MRFP_ERR_UNSUPPORTED;
 }
@@ -690,5 +731,5 @@ extern "C" int mrfp_debug_conv3x3_bf16(const void* in, const void* wpack, void* 
                                        int cout, int dil, const int* cnt_h, const int* cnt_w, double* stat_acc,
                                        void* stream) {
   return mrfp::conv3x3_tc_bf16((const __nv_bfloat16*)in, (const __nv_bfloat16*)wpack, (__nv_bfloat16*)out, N, H, W, cin,
-                               cout, dil, cnt_h, cnt_w, stat_acc, (cudaStream_t)stream);
+                               cout, dil, cnt_h, cnt_w, stat_acc, (cudaStream_t)stream, nullptr);
 }

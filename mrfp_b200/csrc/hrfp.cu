@@ -13,6 +13,7 @@
 // (the same conv kernel with rotated, transposed weights).  No weight gradients (deepv3.py:221-237).
 #include "hrfp.cuh"
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 #include <new>
 
@@ -606,6 +607,10 @@ int hrfp_backward(const mrfp_hrfp_plan* P, const float* g_ocout, const float* g_
   const bool tc = P->mode == MRFP_MATH_BF16;
   T* dA = nullptr;    // gradient wrt the stage output A_{k+1}, NHWC at (oh, ow)
   T* other = g1;
+  // measured on B200: the gathered loads make the epilogue the bottleneck of the dgrad (latency-bound), so the separate
+  // reduction kernel stays the default; MRFP_FUSE_REDUCE=1 selects the fused path
+  static const bool fuse_reduce = getenv("MRFP_FUSE_REDUCE") && atoi(getenv("MRFP_FUSE_REDUCE")) == 1;
+  bool reduced = false;   // the BN-backward sums of the stage about to be processed were taken by the previous dgrad
   for (int k = kHrfpStages - 1; k >= 0; --k) {
     const HrfpStage& st = P->st[k];
     const float* gin = (k == kHrfpStages - 1) ? g_ocout : (k == 3 ? g_ocout_dec : nullptr);
@@ -622,18 +627,33 @@ int hrfp_backward(const mrfp_hrfp_plan* P, const float* g_ocout, const float* g_
     double* a = acc + (size_t)k * 2 * kMaxC;
     const double count = (double)P->N * st.oh * st.ow;
     const int grid_r = even_grid(P->N * st.oh, di.sm_count * 8), grid_a = even_grid(P->N * st.ch, di.sm_count * 9);
-    bn_bwd_reduce_kernel<T><<<grid_r, 256, 0, s>>>(dA, Y, lut + st.idx_h, lut + st.idx_w, stats, a, P->N, st.cout, st.ch,
-                                                   st.cw, st.oh, st.ow);
+    if (!reduced)
+      bn_bwd_reduce_kernel<T><<<grid_r, 256, 0, s>>>(dA, Y, lut + st.idx_h, lut + st.idx_w, stats, a, P->N, st.cout, st.ch,
+                                                     st.cw, st.oh, st.ow);
+    reduced = false;
     bn_bwd_apply_kernel<T><<<grid_a, 256, 0, s>>>(dA, Y, dY, lut + st.start_h, lut + st.cnt_h, lut + st.start_w,
                                                   lut + st.cnt_w, stats, gamma[k], a, P->N, st.cout, st.ch, st.cw,
                                                   st.oh, st.ow, count);
     // dgrad: conv of dY (cout channels) with the rotated / transposed kernel -> dA_prev (cin channels)
     if (tc) {
+      // the dgrad epilogue also takes the BN-backward sums of stage k-1 (its output IS that stage's dA), unless an
+      // external gradient still has to join that dA (g_ocout_dec at stage 3)
+      ConvBwdStats bs = {};
+      const bool fuse = fuse_reduce && k > 0 && !(k - 1 == 3 && g_ocout_dec);
+      if (fuse) {
+        const HrfpStage& pv = P->st[k - 1];
+        const float* pstats = reinterpret_cast<const float*>(saved + P->stats_off) + (size_t)(k - 1) * 4 * kMaxC;
+        bs.y = reinterpret_cast<const __nv_bfloat16*>(saved + pv.y_off);
+        bs.idx_h = lut + pv.idx_h; bs.idx_w = lut + pv.idx_w;
+        bs.scale = pstats + 2 * kMaxC; bs.shift = pstats + 3 * kMaxC;
+        bs.IH = pv.ch; bs.IW = pv.cw;
+      }
       int rc = conv3x3_tc_bf16(reinterpret_cast<const __nv_bfloat16*>(dY),
                                reinterpret_cast<const __nv_bfloat16*>(saved + st.wb_off),
                                reinterpret_cast<__nv_bfloat16*>(other), P->N, st.ch, st.cw, st.cout, st.cin, st.dil,
-                               nullptr, nullptr, nullptr, s);
+                               nullptr, nullptr, fuse ? acc + (size_t)(k - 1) * 2 * kMaxC : nullptr, s, fuse ? &bs : nullptr);
       if (rc) return rc;
+      reduced = fuse;
     } else {
       dim3 g((unsigned)(((long long)P->N * st.ch * st.cw + 31) / 32), (st.cin + 63) / 64);
       const size_t smem = (size_t)st.cout * 64 * sizeof(float);

@@ -45,8 +45,20 @@ constexpr uint32_t kPlanMagic = 0x4d524650u;   // 'MRFP'
 //   in  [N][H][W][cin], wpack [9][cout][cin] (tap-major, K contiguous), out [N][H][W][cout]
 //   cnt_h / cnt_w: zero-padded replication counts (device) -> per-channel weighted sum / sum of squares of the
 //   fp32 accumulators are added to stat_acc[0..cout) / stat_acc[kMaxC..kMaxC+cout); pass nullptr to skip.
+//   bwd_stats (dgrad use): the conv output is the gradient dA of the PREVIOUS chain stage's output; its epilogue then
+//   also accumulates that stage's BN-backward sums  U1 = sum mask*dA, U2 = sum mask*dA*y  into stat_acc, where y is
+//   the stage's saved conv output gathered through its nearest-neighbour tables and mask = [scale*y + shift > 0].
+struct ConvBwdStats {
+  const __nv_bfloat16* y;     // [N][IH][IW][cout]
+  const int* idx_h;           // [H] output row -> row of y
+  const int* idx_w;           // [W]
+  const float* scale;         // [cout] BN scale / shift of that stage (ReLU mask)
+  const float* shift;
+  int IH, IW;
+  int H, W;                   // filled in by conv3x3_tc_bf16
+};
 int conv3x3_tc_bf16(const __nv_bfloat16* in, const __nv_bfloat16* wpack, __nv_bfloat16* out, int N, int H, int W,
                     int cin, int cout, int dil, const int* cnt_h, const int* cnt_w, double* stat_acc,
-                    cudaStream_t stream);
+                    cudaStream_t stream, const ConvBwdStats* bwd_stats = nullptr);
 bool conv3x3_tc_supported(int cin, int cout);
 }  // namespace mrfp

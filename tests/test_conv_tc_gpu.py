@@ -52,8 +52,8 @@ def test_conv_matches_torch(cin, cout, dil, shape):
     wgt = (cnt_h[:h].double()[:, None] * cnt_w[:w].double()[None, :])[None, None]
     gd = got.double()
     s1 = (gd * wgt).sum((0, 2, 3)); s2 = (gd * gd * wgt).sum((0, 2, 3))
-    assert torch.allclose(acc[0, :cout], s1, rtol=1e-5, atol=1e-5 * s1.abs().max().item())
-    assert torch.allclose(acc[1, :cout], s2, rtol=1e-5, atol=1e-5 * s2.abs().max().item())
+    assert torch.allclose(acc[0, :cout], s1, rtol=1e-4, atol=1e-4 * s1.abs().max().item())
+    assert torch.allclose(acc[1, :cout], s2, rtol=1e-4, atol=1e-4 * s2.abs().max().item())
 
 
 def test_conv_without_stats_full_size_linearity():
