@@ -230,7 +230,7 @@ def hrfp_forward(xp: np.ndarray, weights: Sequence[np.ndarray], gammas: Sequence
 
     `quant` (e.g. `round_bf16`) models a reduced-precision STORAGE format: it is applied where the
     tensor-core CUDA path stores bf16 (stem feature, weights, each conv output, each activation); the
-    arithmetic stays exact and the BN statistics come from the unrounded accumulators, as on the device."""
+    arithmetic stays exact and the BN statistics are those of the stored (rounded) conv output, as on the device."""
     stages = hrfp_geometry(h, w, xp.shape[2], xp.shape[3], layers)
     q = quant if quant is not None else (lambda t: t)
     a = q(xp)
@@ -238,11 +238,10 @@ def hrfp_forward(xp: np.ndarray, weights: Sequence[np.ndarray], gammas: Sequence
     ocout_dec = None
     for k, st in enumerate(stages):
         y_acc = conv3x3(a, q(weights[k]), st.dil, None if biases is None else biases[k])
-        r_acc = resample(y_acc, st.idx_h, st.idx_w)
-        mu = r_acc.mean((0, 2, 3))
-        var = r_acc.var((0, 2, 3))                               # biased, used for normalisation
+        r = resample(q(y_acc), st.idx_h, st.idx_w)               # statistics of the STORED conv output, as on the device
+        mu = r.mean((0, 2, 3))
+        var = r.var((0, 2, 3))                                   # biased, used for normalisation
         invstd = 1.0 / np.sqrt(var + BN_EPS)
-        r = resample(q(y_acc), st.idx_h, st.idx_w)
         xhat = (r - mu[None, :, None, None]) * invstd[None, :, None, None]
         z = xhat * gammas[k][None, :, None, None]
         if betas is not None:

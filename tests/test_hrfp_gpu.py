@@ -125,6 +125,41 @@ def test_vs_oracle_odd_geometry_and_add(mode):
         assert _relerr(gx, qg) <= TOL_VS_BF16_ORACLE["bwd"]
 
 
+@pytest.mark.parametrize("mode", [0, 2])
+def test_wide_stem_128_channels(mode):
+    """R101-style stem (BASELINE config 4): xp has 128 channels, so OClayer1 is 128->64 and OCdeclayer4 is 64->128
+    (`OCout + x` needs the stem width back).  The reference hard-wires 64 (deepv3.py:221-237); this is the documented
+    extension of SURVEY.md 8f-2, checked against the oracle run with the same layer table."""
+    n, h, w, xh, xw = 2, 64, 48, 16, 12
+    layers = ((128, 64, 1), (64, 64, 1), (64, 128, 2), (128, 256, 2), (256, 128, 1), (128, 64, 1), (64, 64, 2), (64, 128, 2))
+    rng = np.random.default_rng(21)
+    ws = [(rng.standard_normal((co, ci, 3, 3)) * math.sqrt(2.0 / (9 * ci))).astype(np.float32) for ci, co, _ in layers]
+    gs = [(0.5 * rng.standard_normal(co)).astype(np.float32) for _, co, _ in layers]
+    xp = make_feat(22, (n, 128, xh, xw))
+    g1 = rng.standard_normal((n, 128, xh, xw)).astype(np.float32)
+    g2 = rng.standard_normal((n, 256, h // 2, w // 2)).astype(np.float32)
+    from mrfp_b200.hrfp import hrfp_chain
+    convs, bns = [], []
+    for (ci, co, dil), wt, g in zip(layers, ws, gs):
+        c = torch.nn.Conv2d(ci, co, 3, padding=dil, dilation=dil).to("cuda").requires_grad_(False)
+        b = torch.nn.BatchNorm2d(co).to("cuda").requires_grad_(False)
+        with torch.no_grad():
+            c.weight.copy_(torch.from_numpy(wt)); c.bias.zero_()
+            b.weight.copy_(torch.from_numpy(g)); b.bias.zero_()
+        convs.append(c); bns.append(b)
+    x = torch.from_numpy(xp).cuda().requires_grad_(True)
+    out, dec = hrfp_chain(x, convs, bns, h, w, math_mode=mode)
+    torch.autograd.backward([out, dec], [torch.from_numpy(g1).cuda(), torch.from_numpy(g2).cuda()])
+    ws64 = [a.astype(np.float64) for a in ws]; gs64 = [a.astype(np.float64) for a in gs]
+    ro, rd, saved = O.hrfp_forward(xp.astype(np.float64), ws64, gs64, h, w, layers=layers)
+    rg = O.hrfp_backward(g1.astype(np.float64), g2.astype(np.float64), ws64, gs64, saved)
+    t = TOL[mode]
+    assert out.shape == (n, 128, xh, xw)
+    assert _relerr(out.detach().cpu().numpy(), ro) <= t["fwd"]
+    assert _relerr(dec.detach().cpu().numpy(), rd) <= t["fwd"]
+    assert _relerr(x.grad.cpu().numpy(), rg) <= t["bwd"]
+
+
 def test_plan_geometry_768():
     from mrfp_b200.hrfp import HrfpPlan
     p = HrfpPlan(8, 64, 192, 192, 768, 768, "cuda", 0)

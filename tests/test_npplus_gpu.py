@@ -44,8 +44,12 @@ def test_vs_reference_fixture(i, name):
     _close(gin, g[f"{name}_gin"], 2e-4)
 
 
+# incl. the stem / layer1 shapes of the other trunks (BASELINE configs 4-5, batch 2): R101 128ch@192^2, MobileNetV2
+# 16ch@384^2 + 32ch@96^2, ShuffleNetV2 24ch@192^2 + 116ch@96^2
 @pytest.mark.parametrize("shape", [(2, 64, 192, 192), (2, 256, 96, 96), (8, 16, 48, 48), (3, 24, 33, 31),
-                                   (4, 116, 96, 96), (2, 3, 1, 1), (5, 7, 2, 2), (2, 600, 8, 8)])
+                                   (4, 116, 96, 96), (2, 3, 1, 1), (5, 7, 2, 2), (2, 600, 8, 8),
+                                   (2, 128, 192, 192), (2, 16, 384, 384), (2, 32, 96, 96), (2, 24, 192, 192),
+                                   (16, 64, 192, 192)])
 def test_vs_oracle(shape):
     feat = make_feat(7, shape)
     a, e = make_draws(8, shape[0], shape[1])
