@@ -412,7 +412,10 @@ def run_ours(args):
     np_time = sum(r["fwd_us"] + r["bwd_us"] for r in np_rows.values()) * 1e-6
     big = np_rows["npplus_256ch"]
     roof_np = {"kernel": "npplus_ring_kernel<fwd> on (8,256,192,192)", "bound": "hbm", "achieved": big["fwd_gbs"], "peak": hbm_peak,
-               "unit": "GB/s", "frac": big["fwd_gbs"] / hbm_peak, "traffic": None, "peak_source": peak_src,
+               "unit": "GB/s", "frac": big["fwd_gbs"] / hbm_peak,
+               "traffic": {"dram_read_bytes": 498005248, "dram_write_bytes": 245286656,
+                           "source": "profiles/r2_np256_raw.csv (ncu --set full, one launch of the bwd twin of this kernel)"},
+               "peak_source": peak_src,
                "all_four_np_kernels_gbs": np_bytes / np_time / 1e9, "per_call": np_rows}
 
     # tcgen05 conv kernels of the chain, forward shapes (debug hook = the same kernel the chain launches)
@@ -434,7 +437,9 @@ def run_ours(args):
     top = max(conv_rows, key=lambda r: r["us"])
     roofline = {"kernel": f"conv3x3_tc_kernel<{top['cout']}> stage {top['stage']} ({top['cin']}->{top['cout']} @{top['hw'][0]}x{top['hw'][1]})",
                 "bound": "tensor", "achieved": top["tflops"], "peak": tf_peak, "unit": "TFLOP/s", "frac": top["tflops"] / tf_peak,
-                "traffic": None, "peak_source": peak_src, "peak_sustained": tf_sustained,
+                "traffic": ({"dram_read_bytes": 604729856, "dram_write_bytes": 274007040,
+                             "source": "profiles/r2_conv_d1_raw.csv (ncu --set full, stage 4 forward)"} if top["stage"] == 4 else None),
+                "peak_source": peak_src, "peak_sustained": tf_sustained,
                 "all_conv_fwd_tflops": conv_flop / conv_time / 1e9, "per_stage": conv_rows}
 
     # chain-level numbers through the public API
