@@ -4,6 +4,8 @@
 #include <cuda_bf16.h>
 #include <stdint.h>
 #include <stddef.h>
+#include <stdlib.h>
+#include <utility>
 #include "../../include/mrfp_b200.h"
 
 #define MRFP_CUDA_TRY(expr)                          \
@@ -22,6 +24,31 @@ struct DeviceInfo {
 int get_device_info(DeviceInfo* out);
 
 __host__ __device__ inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// Programmatic dependent launch: every kernel of the HRFP chain is launched with the stream-serialisation attribute and
+// starts with pdl_sync().  The trigger lets the NEXT kernel be scheduled (block launch, barrier / TMEM set-up,
+// descriptor fetch) while this one is still running; the wait returns only when all prerequisite grids have
+// completed and flushed, so every global access behind it sees the same ordering as a plain stream launch.
+__device__ __forceinline__ void pdl_sync() {
+#ifdef MRFP_PDL_EARLY_TRIGGER
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+#endif
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+inline bool pdl_enabled() {
+  static const bool on = !(getenv("MRFP_PDL") && atoi(getenv("MRFP_PDL")) == 0);
+  return on;
+}
+template <typename... Exp, typename... Act>
+inline cudaError_t launch_k(void (*kern)(Exp...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Act&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kern, std::forward<Act>(args)...);
+}
 
 __device__ __forceinline__ float4 ld_stream_f4(const float4* p) {
   float4 r;

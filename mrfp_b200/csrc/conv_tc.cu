@@ -145,6 +145,9 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_cons
   const int nk = 9 * (CIN / kBlockK);       // k-steps per tile
 
   if (threadIdx.x == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap_in)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap_w)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap_out)) : "memory");
     for (int i = 0; i < C::kStages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 4); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -158,6 +161,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_cons
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_ptr;
+  pdl_sync();                                 // set-up above overlaps the previous kernel's tail
 
   if (warp == 0) {
     // ===================== TMA producer (whole warp walks, one elected lane issues) =====================
@@ -180,6 +184,8 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_cons
           }
         }
       }
+      // all loads of this CTA are in flight: let the next kernel of the stream start its set-up (PDL)
+      asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
@@ -368,8 +374,8 @@ template <int COUT> struct HCfg {
   static constexpr int kAStageBytes = kBoxW * kBoxHMax * 128;       // 61440 / 40960: multiples of 1024
   static constexpr int kAStages = 2;
   static constexpr int kBTileBytes = COUT * 128;
-  static constexpr int kBStages = COUT == 256 ? 3 : 4;
-  static constexpr int kOutBufs = COUT == 64 ? 2 : 1;
+  static constexpr int kBStages = COUT == 256 ? 3 : (COUT == 128 ? 5 : 10);   // 64: the ring holds all 9 taps of a chunk
+  static constexpr int kOutBufs = 1;
   static constexpr int kTmemCols = 2 * kMT * COUT;
   static constexpr int kSmemBytes = kAStages * kAStageBytes + kBStages * kBTileBytes + kOutBufs * kStageOutBytes +
                                     2 * COUT * 4 + 256 /* barriers */ + 1024 /* alignment slack */;
@@ -422,6 +428,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_co
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_ptr;
+  pdl_sync();                                 // set-up above overlaps the previous kernel's tail
 
   if (warp == 0) {
     // ===================== TMA producer (whole warp walks, one elected lane issues) =====================
@@ -641,7 +648,7 @@ int launch(const __nv_bfloat16* in, const __nv_bfloat16* wpack, __nv_bfloat16* o
   const int grid = num_tiles < di.sm_count ? num_tiles : di.sm_count;
   auto kern = bs.y ? conv3x3_tc_kernel<COUT, true> : conv3x3_tc_kernel<COUT, false>;
   MRFP_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<COUT>::kSmemBytes));
-  kern<<<grid, kThreads, Cfg<COUT>::kSmemBytes, stream>>>(m_in, m_w, m_out, cin, dil, tiles_h, tiles_w, num_tiles, cnt_h,
+  launch_k(kern, dim3(grid), dim3(kThreads), Cfg<COUT>::kSmemBytes, stream, m_in, m_w, m_out, cin, dil, tiles_h, tiles_w, num_tiles, cnt_h,
                                                            cnt_w, stat_acc, bs);
   MRFP_CUDA_TRY(cudaGetLastError());
   return MRFP_OK;
@@ -683,7 +690,7 @@ int launch_halo(const __nv_bfloat16* in, const __nv_bfloat16* wpack, __nv_bfloat
   const int grid = num_tiles < di.sm_count ? num_tiles : di.sm_count;
   auto kern = conv3x3_halo_kernel<COUT>;
   MRFP_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
-  kern<<<grid, kThreads, C::kSmemBytes, stream>>>(m_in, m_w, m_out, cin, dil, tiles_h, tiles_w, num_tiles, cnt_h, cnt_w,
+  launch_k(kern, dim3(grid), dim3(kThreads), C::kSmemBytes, stream, m_in, m_w, m_out, cin, dil, tiles_h, tiles_w, num_tiles, cnt_h, cnt_w,
                                                   stat_acc, bo_mode);
   MRFP_CUDA_TRY(cudaGetLastError());
   return MRFP_OK;

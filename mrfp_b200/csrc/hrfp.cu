@@ -89,6 +89,7 @@ __device__ __forceinline__ int lay_col(int px) { return (px & 3) * 33 + (px >> 2
 template <typename T>
 __global__ void __launch_bounds__(256)
 nchw_to_nhwc_kernel(const float* __restrict__ src, T* __restrict__ dst, int C, int HW, int accumulate) {
+  pdl_sync();
   __shared__ float tile[64][kLayRow];   // [channel][lay_col(pixel)]
   const int n = blockIdx.z, c0 = blockIdx.y * 64, p0 = blockIdx.x * kLayPx, t = threadIdx.x;
   const float* s = src + (size_t)n * C * HW;
@@ -143,6 +144,7 @@ __global__ void __launch_bounds__(256)
 nhwc_to_nchw_kernel(const T* __restrict__ y, float* __restrict__ out, const float* __restrict__ add,
                     const int* __restrict__ idx_h, const int* __restrict__ idx_w, const float* __restrict__ scale,
                     const float* __restrict__ shift, int C, int IH, int IW, int OH, int OW) {
+  pdl_sync();
   __shared__ float tile[64][kLayRow];   // [channel][lay_col(pixel)]
   // flat grid, output rows fastest, then channel tiles, then w-tiles
   const int ct = (C + 63) >> 6, rows = (int)(gridDim.x / (((OW + kLayPx - 1) / kLayPx) * ct));
@@ -209,6 +211,7 @@ __global__ void __launch_bounds__(256)
 bn_relu_resample_kernel(const T* __restrict__ y, T* __restrict__ a, const int* __restrict__ idx_h,
                         const int* __restrict__ idx_w, const float* __restrict__ scale,
                         const float* __restrict__ shift, int N, int C, int IH, int IW, int OH, int OW) {
+  pdl_sync();
   const int cg = C >> 3, pstep = 256 / cg;
   const int c = (threadIdx.x % cg) << 3, pl = threadIdx.x / cg;
   float sc[8], sf[8];
@@ -248,6 +251,7 @@ __global__ void bn_finalize_kernel(const double* __restrict__ acc, const float* 
                                    const float* __restrict__ beta, float* __restrict__ running_mean,
                                    float* __restrict__ running_var, float* __restrict__ stats, int C,
                                    double count, float momentum, float eps) {
+  pdl_sync();
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
     const double mean = acc[c] / count;
     double var = acc[kMaxC + c] / count - mean * mean;
@@ -272,6 +276,7 @@ __global__ void __launch_bounds__(128)
 conv3x3_direct_f32_kernel(const float* __restrict__ in, const float* __restrict__ w, float* __restrict__ out,
                           int N, int H, int W, int CIN, int COUT, int dil, const int* __restrict__ cnt_h,
                           const int* __restrict__ cnt_w, double* __restrict__ stat_acc) {
+  pdl_sync();
   extern __shared__ float s_w[];   // [CIN][64]
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const long long pix = (long long)blockIdx.x * 32 + lane;
@@ -337,6 +342,7 @@ conv3x3_direct_f32_kernel(const float* __restrict__ in, const float* __restrict_
 //   mode 3 (tc dgrad)     out[tap][ci][co] = W[co][ci][8-tap]        bf16   (rows = N = ci, K = co contiguous)
 // ------------------------------------------------------------------------------------------------------
 __global__ void pack_weights_kernel(const float* __restrict__ W, void* __restrict__ out, int cin, int cout, int mode) {
+  pdl_sync();
   const int total = 9 * cin * cout;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
     const int tap = i / (cin * cout), r = i % (cin * cout);
@@ -362,6 +368,7 @@ __global__ void __launch_bounds__(256, 4)
 bn_bwd_reduce_kernel(const T* __restrict__ dA, const T* __restrict__ y, const int* __restrict__ idx_h,
                      const int* __restrict__ idx_w, const float* __restrict__ stats, double* __restrict__ acc,
                      int N, int C, int IH, int IW, int OH, int OW) {
+  pdl_sync();
   __shared__ float s_acc[2 * kMaxC];
   const int cg = C >> 3, pstep = 256 / cg;
   const int c = (threadIdx.x % cg) << 3, pl = threadIdx.x / cg;
@@ -408,6 +415,7 @@ bn_bwd_apply_kernel(const T* __restrict__ dA, const T* __restrict__ y, T* __rest
                     const int* __restrict__ start_h, const int* __restrict__ cnt_h, const int* __restrict__ start_w,
                     const int* __restrict__ cnt_w, const float* __restrict__ stats, const float* __restrict__ gamma,
                     const double* __restrict__ acc, int N, int C, int IH, int IW, int OH, int OW, double count) {
+  pdl_sync();
   // per-channel constants live in shared memory (read as two float4 per use): registers are kept for loads in flight
   __shared__ __align__(16) float s_scale[kMaxC], s_shift[kMaxC], s_P[kMaxC], s_Q[kMaxC], s_R[kMaxC];
   const int cg = C >> 3, pstep = 256 / cg;
@@ -496,6 +504,7 @@ bn_bwd_apply_kernel(const T* __restrict__ dA, const T* __restrict__ y, T* __rest
 
 __global__ void add_f32_kernel(const float4* __restrict__ a, const float4* __restrict__ b, float4* __restrict__ o,
                                size_t n4, const float* a1, const float* b1, float* o1, size_t n) {
+  pdl_sync();
   const size_t stride = (size_t)gridDim.x * blockDim.x;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n4; i += stride) {
     const float4 x = ld_stream_f4(a + i), y = ld_stream_f4(b + i);
@@ -539,15 +548,15 @@ int hrfp_forward(const mrfp_hrfp_plan* P, const float* xp, const float* const* W
   for (int k = 0; k < last; ++k) {
     const HrfpStage& st = P->st[k];
     const int nw = 9 * st.cin * st.cout;
-    pack_weights_kernel<<<grid_for(nw, 256, di.sm_count, 2), 256, 0, s>>>(W[k], ws + st.wf_off, st.cin, st.cout, tc ? 2 : 0);
-    pack_weights_kernel<<<grid_for(nw, 256, di.sm_count, 2), 256, 0, s>>>(W[k], saved + st.wb_off, st.cin, st.cout, tc ? 3 : 1);
+    launch_k(pack_weights_kernel, dim3(grid_for(nw, 256, di.sm_count, 2)), dim3(256), 0, s, W[k], ws + st.wf_off, st.cin, st.cout, tc ? 2 : 0);
+    launch_k(pack_weights_kernel, dim3(grid_for(nw, 256, di.sm_count, 2)), dim3(256), 0, s, W[k], saved + st.wb_off, st.cin, st.cout, tc ? 3 : 1);
   }
   T* bufA = reinterpret_cast<T*>(ws + P->bufs_off);
   T* bufB = reinterpret_cast<T*>(ws + P->bufs_off + P->buf_a_bytes);
   {
     const int HW = P->xh * P->xw;
     dim3 g((HW + kLayPx - 1) / kLayPx, (P->cin + 63) / 64, P->N);
-    nchw_to_nhwc_kernel<T><<<g, 256, 0, s>>>(xp, bufA, P->cin, HW, 0);
+    launch_k(nchw_to_nhwc_kernel<T>, dim3(g), dim3(256), 0, s, xp, bufA, P->cin, HW, 0);
   }
   T* cur = bufA;
   T* nxt = bufB;
@@ -565,28 +574,28 @@ int hrfp_forward(const mrfp_hrfp_plan* P, const float* xp, const float* const* W
       dim3 g((unsigned)(((long long)P->N * st.ch * st.cw + 31) / 32), (st.cout + 63) / 64);
       const size_t smem = (size_t)st.cin * 64 * sizeof(float);
       MRFP_CUDA_TRY(cudaFuncSetAttribute(conv3x3_direct_f32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      conv3x3_direct_f32_kernel<<<g, 128, smem, s>>>(reinterpret_cast<const float*>(cur),
+      launch_k(conv3x3_direct_f32_kernel, dim3(g), dim3(128), smem, s, reinterpret_cast<const float*>(cur),
                                                      reinterpret_cast<const float*>(ws + st.wf_off),
                                                      reinterpret_cast<float*>(Y), P->N, st.ch, st.cw, st.cin, st.cout,
                                                      st.dil, lut + st.cnt_h, lut + st.cnt_w, a);
     }
     float* stats = reinterpret_cast<float*>(saved + P->stats_off) + (size_t)k * 4 * kMaxC;
     const double count = (double)P->N * st.oh * st.ow;
-    bn_finalize_kernel<<<1, 256, 0, s>>>(a, gamma[k], beta ? beta[k] : nullptr, rmean ? rmean[k] : nullptr,
+    launch_k(bn_finalize_kernel, dim3(1), dim3(256), 0, s, a, gamma[k], beta ? beta[k] : nullptr, rmean ? rmean[k] : nullptr,
                                          rvar ? rvar[k] : nullptr, stats, st.cout, count, momentum, eps);
     if (k == 3 && ocout_dec) {
       const unsigned g = (unsigned)(((st.ow + kLayPx - 1) / kLayPx) * ((st.cout + 63) / 64)) * (unsigned)(P->N * st.oh);
-      nhwc_to_nchw_kernel<T><<<g, 256, 0, s>>>(Y, ocout_dec, nullptr, lut + st.idx_h, lut + st.idx_w,
+      launch_k(nhwc_to_nchw_kernel<T>, dim3(g), dim3(256), 0, s, Y, ocout_dec, nullptr, lut + st.idx_h, lut + st.idx_w,
                                                         stats + 2 * kMaxC, stats + 3 * kMaxC, st.cout, st.ch, st.cw,
                                                         st.oh, st.ow);
     }
     if (k == kHrfpStages - 1) {
       const unsigned g = (unsigned)(((st.ow + kLayPx - 1) / kLayPx) * ((st.cout + 63) / 64)) * (unsigned)(P->N * st.oh);
-      nhwc_to_nchw_kernel<T><<<g, 256, 0, s>>>(Y, ocout, x_add, lut + st.idx_h, lut + st.idx_w,
+      launch_k(nhwc_to_nchw_kernel<T>, dim3(g), dim3(256), 0, s, Y, ocout, x_add, lut + st.idx_h, lut + st.idx_w,
                                                         stats + 2 * kMaxC, stats + 3 * kMaxC, st.cout, st.ch, st.cw,
                                                         st.oh, st.ow);
     } else if (k + 1 < last) {
-      bn_relu_resample_kernel<T><<<even_grid(P->N * st.oh, di.sm_count * 8), 256, 0, s>>>(
+      launch_k(bn_relu_resample_kernel<T>, dim3(even_grid(P->N * st.oh, di.sm_count * 8)), dim3(256), 0, s, 
           Y, nxt, lut + st.idx_h, lut + st.idx_w, stats + 2 * kMaxC, stats + 3 * kMaxC, P->N, st.cout, st.ch, st.cw,
           st.oh, st.ow);
       T* t = cur; cur = nxt; nxt = t;
@@ -618,7 +627,7 @@ int hrfp_backward(const mrfp_hrfp_plan* P, const float* g_ocout, const float* g_
       const int HW = st.oh * st.ow;
       dim3 g((HW + kLayPx - 1) / kLayPx, (st.cout + 63) / 64, P->N);
       T* dst = dA ? dA : g0;
-      nchw_to_nhwc_kernel<T><<<g, 256, 0, s>>>(gin, dst, st.cout, HW, dA ? 1 : 0);
+      launch_k(nchw_to_nhwc_kernel<T>, dim3(g), dim3(256), 0, s, gin, dst, st.cout, HW, dA ? 1 : 0);
       if (!dA) { dA = g0; other = g1; }
     }
     if (!dA) continue;
@@ -628,10 +637,10 @@ int hrfp_backward(const mrfp_hrfp_plan* P, const float* g_ocout, const float* g_
     const double count = (double)P->N * st.oh * st.ow;
     const int grid_r = even_grid(P->N * st.oh, di.sm_count * 8), grid_a = even_grid(P->N * st.ch, di.sm_count * 9);
     if (!reduced)
-      bn_bwd_reduce_kernel<T><<<grid_r, 256, 0, s>>>(dA, Y, lut + st.idx_h, lut + st.idx_w, stats, a, P->N, st.cout, st.ch,
+      launch_k(bn_bwd_reduce_kernel<T>, dim3(grid_r), dim3(256), 0, s, dA, Y, lut + st.idx_h, lut + st.idx_w, stats, a, P->N, st.cout, st.ch,
                                                      st.cw, st.oh, st.ow);
     reduced = false;
-    bn_bwd_apply_kernel<T><<<grid_a, 256, 0, s>>>(dA, Y, dY, lut + st.start_h, lut + st.cnt_h, lut + st.start_w,
+    launch_k(bn_bwd_apply_kernel<T>, dim3(grid_a), dim3(256), 0, s, dA, Y, dY, lut + st.start_h, lut + st.cnt_h, lut + st.start_w,
                                                   lut + st.cnt_w, stats, gamma[k], a, P->N, st.cout, st.ch, st.cw,
                                                   st.oh, st.ow, count);
     // dgrad: conv of dY (cout channels) with the rotated / transposed kernel -> dA_prev (cin channels)
@@ -658,7 +667,7 @@ int hrfp_backward(const mrfp_hrfp_plan* P, const float* g_ocout, const float* g_
       dim3 g((unsigned)(((long long)P->N * st.ch * st.cw + 31) / 32), (st.cin + 63) / 64);
       const size_t smem = (size_t)st.cout * 64 * sizeof(float);
       MRFP_CUDA_TRY(cudaFuncSetAttribute(conv3x3_direct_f32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      conv3x3_direct_f32_kernel<<<g, 128, smem, s>>>(reinterpret_cast<const float*>(dY),
+      launch_k(conv3x3_direct_f32_kernel, dim3(g), dim3(128), smem, s, reinterpret_cast<const float*>(dY),
                                                      reinterpret_cast<const float*>(saved + st.wb_off),
                                                      reinterpret_cast<float*>(other), P->N, st.ch, st.cw, st.cout,
                                                      st.cin, st.dil, nullptr, nullptr, nullptr);
@@ -670,7 +679,7 @@ int hrfp_backward(const mrfp_hrfp_plan* P, const float* g_ocout, const float* g_
     return MRFP_OK;
   }
   const unsigned g = (unsigned)(((P->xw + kLayPx - 1) / kLayPx) * ((P->cin + 63) / 64)) * (unsigned)(P->N * P->xh);
-  nhwc_to_nchw_kernel<T><<<g, 256, 0, s>>>(dA, g_xp, nullptr, nullptr, nullptr, nullptr, nullptr, P->cin,
+  launch_k(nhwc_to_nchw_kernel<T>, dim3(g), dim3(256), 0, s, dA, g_xp, nullptr, nullptr, nullptr, nullptr, nullptr, P->cin,
                                                     P->xh, P->xw, P->xh, P->xw);
   MRFP_CUDA_TRY(cudaGetLastError());
   return MRFP_OK;
@@ -828,7 +837,7 @@ static int hrfp_plus_add_impl(const mrfp_hrfp_plan* P, const char* saved, const 
   const T* Y = reinterpret_cast<const T*>(saved + st.y_off);
   const float* stats = reinterpret_cast<const float*>(saved + P->stats_off) + (size_t)3 * 4 * kMaxC;
   const unsigned g = (unsigned)(((st.ow + kLayPx - 1) / kLayPx) * ((st.cout + 63) / 64)) * (unsigned)(P->N * st.oh);
-  nhwc_to_nchw_kernel<T><<<g, 256, 0, s>>>(Y, out, dec1_up, lut + st.idx_h, lut + st.idx_w, stats + 2 * kMaxC,
+  launch_k(nhwc_to_nchw_kernel<T>, dim3(g), dim3(256), 0, s, Y, out, dec1_up, lut + st.idx_h, lut + st.idx_w, stats + 2 * kMaxC,
                                             stats + 3 * kMaxC, st.cout, st.ch, st.cw, st.oh, st.ow);
   MRFP_CUDA_TRY(cudaGetLastError());
   return MRFP_OK;
@@ -853,7 +862,7 @@ extern "C" int mrfp_add_f32(const float* a, const float* b, float* out, size_t n
   const bool al = ((((uintptr_t)a | (uintptr_t)b | (uintptr_t)out) & 15) == 0);
   const size_t n4 = al ? n / 4 : 0;
   const int grid = grid_for((long long)(n4 ? n4 : n), 256, di.sm_count, 16);
-  add_f32_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const float4*)a, (const float4*)b, (float4*)out, n4, a, b, out, n);
+  launch_k(add_f32_kernel, dim3(grid), dim3(256), 0, (cudaStream_t)stream, (const float4*)a, (const float4*)b, (float4*)out, n4, a, b, out, n);
   MRFP_CUDA_TRY(cudaGetLastError());
   return MRFP_OK;
 }
