@@ -469,10 +469,10 @@ def run_ours(args):
 
     base, _ = cpu_reference_run(1, 1) if world == 1 else (None, None)
 
-    # kernels launched per step (ours; memsets excluded): NP+ 2 fwd + 2 bwd; HRFP fwd 16 weight packs + 1 NCHW->NHWC +
+    # kernels launched per step (ours; memsets excluded): NP+ 2 fwd + 2 bwd; HRFP fwd 1 weight pack + 1 NCHW->NHWC +
     # 8 conv + 8 BN finalize + 7 BN/ReLU/resample + 1 NHWC->NCHW epilogue (OCout + x); 1 fused HRFP+ add;
     # HRFP bwd 2 NCHW->NHWC + 8 x (2 BN-bwd + conv) + 1 NHWC->NCHW
-    launches_per_step = 4 + (16 + 1 + 8 + 8 + 7 + 1) + 1 + (2 + 24 + 1)
+    launches_per_step = 4 + (1 + 1 + 8 + 8 + 7 + 1) + 1 + (2 + 24 + 1)
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16 (HRFP tensor-core operands, fp32 accumulate) / f32 (NP+)", "data": "synthetic", "config": CONFIG,

@@ -341,8 +341,17 @@ conv3x3_direct_f32_kernel(const float* __restrict__ in, const float* __restrict_
 //   mode 2 (tc fwd)       out[tap][co][ci] = W[co][ci][tap]          bf16   (rows = N, K = ci contiguous)
 //   mode 3 (tc dgrad)     out[tap][ci][co] = W[co][ci][8-tap]        bf16   (rows = N = ci, K = co contiguous)
 // ------------------------------------------------------------------------------------------------------
-__global__ void pack_weights_kernel(const float* __restrict__ W, void* __restrict__ out, int cin, int cout, int mode) {
+struct PackJobs {             // one launch packs every layer for both directions: blockIdx.y = job
+  const float* W[2 * kHrfpStages];
+  void* out[2 * kHrfpStages];
+  int cin[2 * kHrfpStages], cout[2 * kHrfpStages], mode[2 * kHrfpStages];
+};
+__global__ void pack_weights_kernel(const PackJobs jobs) {
   pdl_sync();
+  const int job = blockIdx.y;
+  const float* __restrict__ W = jobs.W[job];
+  void* __restrict__ out = jobs.out[job];
+  const int cin = jobs.cin[job], cout = jobs.cout[job], mode = jobs.mode[job];
   const int total = 9 * cin * cout;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
     const int tap = i / (cin * cout), r = i % (cin * cout);
@@ -545,11 +554,19 @@ int hrfp_forward(const mrfp_hrfp_plan* P, const float* xp, const float* const* W
   MRFP_CUDA_TRY(cudaMemsetAsync(acc, 0, (size_t)kHrfpStages * 2 * kMaxC * sizeof(double), s));
   const int last = ocout ? kHrfpStages : 4;
   const bool tc = P->mode == MRFP_MATH_BF16;
-  for (int k = 0; k < last; ++k) {
-    const HrfpStage& st = P->st[k];
-    const int nw = 9 * st.cin * st.cout;
-    launch_k(pack_weights_kernel, dim3(grid_for(nw, 256, di.sm_count, 2)), dim3(256), 0, s, W[k], ws + st.wf_off, st.cin, st.cout, tc ? 2 : 0);
-    launch_k(pack_weights_kernel, dim3(grid_for(nw, 256, di.sm_count, 2)), dim3(256), 0, s, W[k], saved + st.wb_off, st.cin, st.cout, tc ? 3 : 1);
+  {
+    PackJobs jobs = {};
+    for (int k = 0; k < last; ++k) {
+      const HrfpStage& st = P->st[k];
+      for (int d = 0; d < 2; ++d) {
+        const int j = 2 * k + d;
+        jobs.W[j] = W[k];
+        jobs.out[j] = d == 0 ? (void*)(ws + st.wf_off) : (void*)(saved + st.wb_off);
+        jobs.cin[j] = st.cin; jobs.cout[j] = st.cout;
+        jobs.mode[j] = (tc ? 2 : 0) + d;
+      }
+    }
+    launch_k(pack_weights_kernel, dim3(64, 2 * last), dim3(256), 0, s, jobs);
   }
   T* bufA = reinterpret_cast<T*>(ws + P->bufs_off);
   T* bufB = reinterpret_cast<T*>(ws + P->bufs_off + P->buf_a_bytes);
