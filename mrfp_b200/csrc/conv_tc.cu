@@ -126,7 +126,7 @@ __global__ void __launch_bounds__(kThreads, 1)
 conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constant__ CUtensorMap tmap_w,
                   const __grid_constant__ CUtensorMap tmap_out, int CIN, int dil, int tiles_h, int tiles_w,
                   int num_tiles, const int* __restrict__ cnt_h, const int* __restrict__ cnt_w,
-                  double* __restrict__ stat_acc, const ConvBwdStats bs) {
+                  double* __restrict__ stat_acc, const ConvBwdStats bs, int rev) {
   using C = Cfg<COUT>;
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -167,7 +167,8 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_cons
     // ===================== TMA producer (whole warp walks, one elected lane issues) =====================
     {
       int stage = 0; uint32_t phase = 0;
-      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+      for (int t0 = blockIdx.x; t0 < num_tiles; t0 += gridDim.x) {
+        const int t = rev ? num_tiles - 1 - t0 : t0;     // rev: walk the image from its end (where the producer of `in` finished)
         const int tw = t % tiles_w, th = (t / tiles_w) % tiles_h, n = t / (tiles_w * tiles_h);
         const int h0 = th * kTileH * C::kMT, w0 = tw * kTileW;
         for (int tap = 0; tap < 9; ++tap) {
@@ -237,7 +238,8 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_cons
     constexpr bool bwd = BWD;               // dgrad that also takes the previous stage's BN-backward sums (experimental)
     float a1x = 0.f, a1y = 0.f, a2x = 0.f, a2y = 0.f;
     int it = 0, obuf = 0;
-    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+    for (int t0 = blockIdx.x; t0 < num_tiles; t0 += gridDim.x, ++it) {
+      const int t = rev ? num_tiles - 1 - t0 : t0;
       const int tw = t % tiles_w, th = (t / tiles_w) % tiles_h, n = t / (tiles_w * tiles_h);
       const int h0 = th * kTileH * C::kMT, w0 = tw * kTileW;
       const int acc = it & 1;
@@ -616,7 +618,8 @@ int make_map(CUtensorMap* m, const void* base, int rank, const cuuint64_t* dims,
 
 template <int COUT>
 int launch(const __nv_bfloat16* in, const __nv_bfloat16* wpack, __nv_bfloat16* out, int N, int H, int W, int cin,
-           int dil, const int* cnt_h, const int* cnt_w, double* stat_acc, const ConvBwdStats& bs, cudaStream_t stream) {
+           int dil, const int* cnt_h, const int* cnt_w, double* stat_acc, const ConvBwdStats& bs, int rev,
+           cudaStream_t stream) {
   CUtensorMap m_in, m_w, m_out;
   {
     const cuuint64_t dims[4] = {(cuuint64_t)cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
@@ -649,7 +652,7 @@ int launch(const __nv_bfloat16* in, const __nv_bfloat16* wpack, __nv_bfloat16* o
   auto kern = bs.y ? conv3x3_tc_kernel<COUT, true> : conv3x3_tc_kernel<COUT, false>;
   MRFP_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<COUT>::kSmemBytes));
   launch_k(kern, dim3(grid), dim3(kThreads), Cfg<COUT>::kSmemBytes, stream, m_in, m_w, m_out, cin, dil, tiles_h, tiles_w, num_tiles, cnt_h,
-                                                           cnt_w, stat_acc, bs);
+                                                           cnt_w, stat_acc, bs, rev);
   MRFP_CUDA_TRY(cudaGetLastError());
   return MRFP_OK;
 }
@@ -704,8 +707,9 @@ bool conv3x3_tc_supported(int cin, int cout) {
 
 int conv3x3_tc_bf16(const __nv_bfloat16* in, const __nv_bfloat16* wpack, __nv_bfloat16* out, int N, int H, int W,
                     int cin, int cout, int dil, const int* cnt_h, const int* cnt_w, double* stat_acc,
-                    cudaStream_t stream, const ConvBwdStats* bwd_stats) {
+                    cudaStream_t stream, const ConvBwdStats* bwd_stats, bool reverse_tiles) {
   ConvBwdStats bs = {};
+  const int rev = reverse_tiles ? 1 : 0;
   if (bwd_stats) {
     if (!stat_acc || !bwd_stats->y || !bwd_stats->idx_h || !bwd_stats->idx_w || !bwd_stats->scale || !bwd_stats->shift)
       return MRFP_ERR_NULL_POINTER;
@@ -724,9 +728,9 @@ int conv3x3_tc_bf16(const __nv_bfloat16* in, const __nv_bfloat16* wpack, __nv_bf
     }
   }
   switch (cout) {
-    case 64: return launch<64>(in, wpack, out, N, H, W, cin, dil, cnt_h, cnt_w, stat_acc, bs, stream);
-    case 128: return launch<128>(in, wpack, out, N, H, W, cin, dil, cnt_h, cnt_w, stat_acc, bs, stream);
-    case 256: return launch<256>(in, wpack, out, N, H, W, cin, dil, cnt_h, cnt_w, stat_acc, bs, stream);
+    case 64: return launch<64>(in, wpack, out, N, H, W, cin, dil, cnt_h, cnt_w, stat_acc, bs, rev, stream);
+    case 128: return launch<128>(in, wpack, out, N, H, W, cin, dil, cnt_h, cnt_w, stat_acc, bs, rev, stream);
+    case 256: return launch<256>(in, wpack, out, N, H, W, cin, dil, cnt_h, cnt_w, stat_acc, bs, rev, stream);
   }
   return MRFP_ERR_UNSUPPORTED;
 }
@@ -738,5 +742,5 @@ extern "C" int mrfp_debug_conv3x3_bf16(const void* in, const void* wpack, void* 
                                        int cout, int dil, const int* cnt_h, const int* cnt_w, double* stat_acc,
                                        void* stream) {
   return mrfp::conv3x3_tc_bf16((const __nv_bfloat16*)in, (const __nv_bfloat16*)wpack, (__nv_bfloat16*)out, N, H, W, cin,
-                               cout, dil, cnt_h, cnt_w, stat_acc, (cudaStream_t)stream, nullptr);
+                               cout, dil, cnt_h, cnt_w, stat_acc, (cudaStream_t)stream, nullptr, false);
 }

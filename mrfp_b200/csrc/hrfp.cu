@@ -210,14 +210,15 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 bn_relu_resample_kernel(const T* __restrict__ y, T* __restrict__ a, const int* __restrict__ idx_h,
                         const int* __restrict__ idx_w, const float* __restrict__ scale,
-                        const float* __restrict__ shift, int N, int C, int IH, int IW, int OH, int OW) {
+                        const float* __restrict__ shift, int N, int C, int IH, int IW, int OH, int OW, int rev) {
   pdl_sync();
   const int cg = C >> 3, pstep = 256 / cg;
   const int c = (threadIdx.x % cg) << 3, pl = threadIdx.x / cg;
   float sc[8], sf[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) { sc[j] = scale[c + j]; sf[j] = shift[c + j]; }
-  for (int row = blockIdx.x; row < N * OH; row += gridDim.x) {
+  for (int r = blockIdx.x; r < N * OH; r += gridDim.x) {
+    const int row = rev ? N * OH - 1 - r : r;          // rev: start where the previous kernel of the chain ended (L2)
     const int n = row / OH, oh = row - n * OH;
     const T* yrow = y + ((size_t)n * IH + idx_h[oh]) * IW * C + c;
     T* arow = a + (size_t)row * OW * C + c;
@@ -376,7 +377,7 @@ template <typename T>
 __global__ void __launch_bounds__(256, 4)
 bn_bwd_reduce_kernel(const T* __restrict__ dA, const T* __restrict__ y, const int* __restrict__ idx_h,
                      const int* __restrict__ idx_w, const float* __restrict__ stats, double* __restrict__ acc,
-                     int N, int C, int IH, int IW, int OH, int OW) {
+                     int N, int C, int IH, int IW, int OH, int OW, int rev) {
   pdl_sync();
   __shared__ float s_acc[2 * kMaxC];
   const int cg = C >> 3, pstep = 256 / cg;
@@ -389,7 +390,8 @@ bn_bwd_reduce_kernel(const T* __restrict__ dA, const T* __restrict__ y, const in
     u1[j] = 0.f; u2[j] = 0.f;
   }
   __syncthreads();
-  for (int row = blockIdx.x; row < N * OH; row += gridDim.x) {
+  for (int r = blockIdx.x; r < N * OH; r += gridDim.x) {
+    const int row = rev ? N * OH - 1 - r : r;
     const int n = row / OH, oh = row % OH;
     const T* drow = dA + (size_t)row * OW * C + c;
     const T* yrow = y + ((size_t)n * IH + idx_h[oh]) * IW * C + c;
@@ -418,12 +420,12 @@ bn_bwd_reduce_kernel(const T* __restrict__ dA, const T* __restrict__ y, const in
   }
 }
 
-template <typename T>
-__global__ void __launch_bounds__(256, 3)
+template <typename T, bool REGC>
+__global__ void __launch_bounds__(256, REGC ? 2 : 3)
 bn_bwd_apply_kernel(const T* __restrict__ dA, const T* __restrict__ y, T* __restrict__ dY,
                     const int* __restrict__ start_h, const int* __restrict__ cnt_h, const int* __restrict__ start_w,
                     const int* __restrict__ cnt_w, const float* __restrict__ stats, const float* __restrict__ gamma,
-                    const double* __restrict__ acc, int N, int C, int IH, int IW, int OH, int OW, double count) {
+                    const double* __restrict__ acc, int N, int C, int IH, int IW, int OH, int OW, double count, int rev) {
   pdl_sync();
   // per-channel constants live in shared memory (read as two float4 per use): registers are kept for loads in flight
   __shared__ __align__(16) float s_scale[kMaxC], s_shift[kMaxC], s_P[kMaxC], s_Q[kMaxC], s_R[kMaxC];
@@ -442,6 +444,8 @@ bn_bwd_apply_kernel(const T* __restrict__ dA, const T* __restrict__ y, T* __rest
     const float4 a = *reinterpret_cast<const float4*>(t + c), b = *reinterpret_cast<const float4*>(t + c + 4);
     v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
   };
+  float r_scale[8], r_shift[8], r_P[8], r_Q[8], r_R[8];   // REGC: the thread's constants stay in registers (2 blocks/SM)
+  if (REGC) { ld8(s_scale, r_scale); ld8(s_shift, r_shift); ld8(s_P, r_P); ld8(s_Q, r_Q); ld8(s_R, r_R); }
   // one source pixel: sum of its <= 2x2 replicas of dA (the reference geometry: x1.2 up, x0.8 down), general loop otherwise
   typedef typename Elem<T>::Raw Raw;
   // raw (still packed) loads of one source pixel: y and its <= 2x2 replicas of dA (the reference geometry: x1.2 up,
@@ -463,6 +467,15 @@ bn_bwd_apply_kernel(const T* __restrict__ dA, const T* __restrict__ y, T* __rest
 #pragma unroll
     for (int j = 0; j < 8; ++j) yv[j] = 0.f;
     Elem<T>::add_raw(yraw, yv);
+    if (REGC) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float t = fmaf(r_scale[j], yv[j], r_shift[j]) > 0.f ? sd[j] : 0.f;
+        o[j] = r_P[j] * t - cnt * fmaf(r_R[j], yv[j], r_Q[j]);
+      }
+      Elem<T>::store8(dst, o);
+      return;
+    }
     ld8(s_scale, k0); ld8(s_shift, k1);
 #pragma unroll
     for (int j = 0; j < 8; ++j) o[j] = fmaf(k0[j], yv[j], k1[j]) > 0.f ? sd[j] : 0.f;
@@ -481,7 +494,8 @@ bn_bwd_apply_kernel(const T* __restrict__ dA, const T* __restrict__ y, T* __rest
     Elem<T>::add_raw(p.g00, sd); Elem<T>::add_raw(p.g01, sd); Elem<T>::add_raw(p.g10, sd); Elem<T>::add_raw(p.g11, sd);
     finish(sd, p.y, cnt, dst);
   };
-  for (int row = blockIdx.x; row < N * IH; row += gridDim.x) {
+  for (int r = blockIdx.x; r < N * IH; r += gridDim.x) {
+    const int row = rev ? N * IH - 1 - r : r;
     const int n = row / IH, sy = row % IH;
     const int h0 = start_h[sy], nh = cnt_h[sy];
     const T* yrow = y + (size_t)row * IW * C + c;
@@ -554,6 +568,9 @@ int hrfp_forward(const mrfp_hrfp_plan* P, const float* xp, const float* const* W
   MRFP_CUDA_TRY(cudaMemsetAsync(acc, 0, (size_t)kHrfpStages * 2 * kMaxC * sizeof(double), s));
   const int last = ocout ? kHrfpStages : 4;
   const bool tc = P->mode == MRFP_MATH_BF16;
+  // L2-friendly ordering: a kernel starts walking its tensor where its producer finished.  Forward: every conv walks
+  // front to back, every BN/ReLU/resample pass back to front.  (MRFP_L2_ORDER=0 restores front-to-back everywhere.)
+  static const bool l2_order = !(getenv("MRFP_L2_ORDER") && atoi(getenv("MRFP_L2_ORDER")) == 0);
   {
     PackJobs jobs = {};
     for (int k = 0; k < last; ++k) {
@@ -614,7 +631,7 @@ int hrfp_forward(const mrfp_hrfp_plan* P, const float* xp, const float* const* W
     } else if (k + 1 < last) {
       launch_k(bn_relu_resample_kernel<T>, dim3(even_grid(P->N * st.oh, di.sm_count * 8)), dim3(256), 0, s, 
           Y, nxt, lut + st.idx_h, lut + st.idx_w, stats + 2 * kMaxC, stats + 3 * kMaxC, P->N, st.cout, st.ch, st.cw,
-          st.oh, st.ow);
+          st.oh, st.ow, l2_order ? 1 : 0);
       T* t = cur; cur = nxt; nxt = t;
     }
   }
@@ -635,6 +652,8 @@ int hrfp_backward(const mrfp_hrfp_plan* P, const float* g_ocout, const float* g_
   T* other = g1;
   // measured on B200: the gathered loads make the epilogue the bottleneck of the dgrad (latency-bound), so the separate
   // reduction kernel stays the default; MRFP_FUSE_REDUCE=1 selects the fused path
+  static const bool l2_order = !(getenv("MRFP_L2_ORDER") && atoi(getenv("MRFP_L2_ORDER")) == 0);
+  bool at_end = true;     // where the last kernel that touched dA finished (the layout kernels walk front to back)
   static const bool fuse_reduce = getenv("MRFP_FUSE_REDUCE") && atoi(getenv("MRFP_FUSE_REDUCE")) == 1;
   bool reduced = false;   // the BN-backward sums of the stage about to be processed were taken by the previous dgrad
   for (int k = kHrfpStages - 1; k >= 0; --k) {
@@ -653,13 +672,19 @@ int hrfp_backward(const mrfp_hrfp_plan* P, const float* g_ocout, const float* g_
     double* a = acc + (size_t)k * 2 * kMaxC;
     const double count = (double)P->N * st.oh * st.ow;
     const int grid_r = even_grid(P->N * st.oh, di.sm_count * 8), grid_a = even_grid(P->N * st.ch, di.sm_count * 9);
-    if (!reduced)
+    if (gin) at_end = true;
+    if (!reduced) {
       launch_k(bn_bwd_reduce_kernel<T>, dim3(grid_r), dim3(256), 0, s, dA, Y, lut + st.idx_h, lut + st.idx_w, stats, a, P->N, st.cout, st.ch,
-                                                     st.cw, st.oh, st.ow);
+                                                     st.cw, st.oh, st.ow, (l2_order && at_end) ? 1 : 0);
+      if (l2_order) at_end = !at_end;
+    }
     reduced = false;
-    launch_k(bn_bwd_apply_kernel<T>, dim3(grid_a), dim3(256), 0, s, dA, Y, dY, lut + st.start_h, lut + st.cnt_h, lut + st.start_w,
-                                                  lut + st.cnt_w, stats, gamma[k], a, P->N, st.cout, st.ch, st.cw,
-                                                  st.oh, st.ow, count);
+    const int rev_apply = (l2_order && at_end) ? 1 : 0;
+    if (l2_order) at_end = !at_end;
+    static const bool regc = getenv("MRFP_APPLY_REGC") && atoi(getenv("MRFP_APPLY_REGC")) == 1;
+    launch_k(regc ? bn_bwd_apply_kernel<T, true> : bn_bwd_apply_kernel<T, false>, dim3(grid_a), dim3(256), 0, s, dA, Y, dY,
+             lut + st.start_h, lut + st.cnt_h, lut + st.start_w, lut + st.cnt_w, stats, gamma[k], a, P->N, st.cout, st.ch,
+             st.cw, st.oh, st.ow, count, rev_apply);
     // dgrad: conv of dY (cout channels) with the rotated / transposed kernel -> dA_prev (cin channels)
     if (tc) {
       // the dgrad epilogue also takes the BN-backward sums of stage k-1 (its output IS that stage's dA), unless an
@@ -677,8 +702,10 @@ int hrfp_backward(const mrfp_hrfp_plan* P, const float* g_ocout, const float* g_
       int rc = conv3x3_tc_bf16(reinterpret_cast<const __nv_bfloat16*>(dY),
                                reinterpret_cast<const __nv_bfloat16*>(saved + st.wb_off),
                                reinterpret_cast<__nv_bfloat16*>(other), P->N, st.ch, st.cw, st.cout, st.cin, st.dil,
-                               nullptr, nullptr, fuse ? acc + (size_t)(k - 1) * 2 * kMaxC : nullptr, s, fuse ? &bs : nullptr);
+                               nullptr, nullptr, fuse ? acc + (size_t)(k - 1) * 2 * kMaxC : nullptr, s, fuse ? &bs : nullptr,
+                               l2_order && at_end);
       if (rc) return rc;
+      if (l2_order) at_end = !at_end;
       reduced = fuse;
     } else {
       dim3 g((unsigned)(((long long)P->N * st.ch * st.cw + 31) / 32), (st.cin + 63) / 64);

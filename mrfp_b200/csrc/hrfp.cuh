@@ -59,6 +59,6 @@ struct ConvBwdStats {
 };
 int conv3x3_tc_bf16(const __nv_bfloat16* in, const __nv_bfloat16* wpack, __nv_bfloat16* out, int N, int H, int W,
                     int cin, int cout, int dil, const int* cnt_h, const int* cnt_w, double* stat_acc,
-                    cudaStream_t stream, const ConvBwdStats* bwd_stats = nullptr);
+                    cudaStream_t stream, const ConvBwdStats* bwd_stats = nullptr, bool reverse_tiles = false);
 bool conv3x3_tc_supported(int cin, int cout);
 }  // namespace mrfp
