@@ -539,8 +539,9 @@ __global__ void add_f32_kernel(const float4* __restrict__ a, const float4* __res
 // ------------------------------------------------------------------------------------------------------
 // host: geometry (must be bit-identical to ATen's upsample_nearest2d index rule)
 // ------------------------------------------------------------------------------------------------------
+float index_scale(int in, int out, bool has_sf, double sf) { return has_sf ? (float)(1.0 / sf) : ((float)in / (float)out); }
 void make_index(int in, int out, bool has_sf, double sf, int* idx) {
-  const float scale = has_sf ? (float)(1.0 / sf) : ((float)in / (float)out);
+  const float scale = index_scale(in, out, has_sf, sf);
   for (int d = 0; d < out; ++d) {
     int s = (int)floorf((float)d * scale);
     idx[d] = s < in - 1 ? s : in - 1;
@@ -674,8 +675,16 @@ int hrfp_backward(const mrfp_hrfp_plan* P, const float* g_ocout, const float* g_
     const int grid_r = even_grid(P->N * st.oh, di.sm_count * 8), grid_a = even_grid(P->N * st.ch, di.sm_count * 9);
     if (gin) at_end = true;
     if (!reduced) {
-      launch_k(bn_bwd_reduce_kernel<T>, dim3(grid_r), dim3(256), 0, s, dA, Y, lut + st.idx_h, lut + st.idx_w, stats, a, P->N, st.cout, st.ch,
-                                                     st.cw, st.oh, st.ow, (l2_order && at_end) ? 1 : 0);
+      static const bool ring_reduce = getenv("MRFP_RING_REDUCE") && atoi(getenv("MRFP_RING_REDUCE")) == 1;
+      int rr = MRFP_ERR_UNSUPPORTED;
+      if (tc && ring_reduce)
+        rr = bn_bwd_reduce_ring(reinterpret_cast<const __nv_bfloat16*>(dA), reinterpret_cast<const __nv_bfloat16*>(Y),
+                                lut + st.idx_h, lut + st.idx_w, P->lut.data() + st.idx_w, st.scale_w, stats, a, P->N, st.cout, st.ch,
+                                st.cw, st.oh, st.ow, l2_order && at_end, s);
+      if (rr == MRFP_ERR_UNSUPPORTED)
+        launch_k(bn_bwd_reduce_kernel<T>, dim3(grid_r), dim3(256), 0, s, dA, Y, lut + st.idx_h, lut + st.idx_w, stats, a, P->N,
+                 st.cout, st.ch, st.cw, st.oh, st.ow, (l2_order && at_end) ? 1 : 0);
+      else if (rr) return rr;
       if (l2_order) at_end = !at_end;
     }
     reduced = false;
@@ -770,6 +779,7 @@ extern "C" int mrfp_hrfp_plan_create(mrfp_hrfp_plan_t** out, int N, int cin, int
     if (st.oh <= 0 || st.ow <= 0) { delete P; return MRFP_ERR_BAD_SHAPE; }
     if (math_mode == MRFP_MATH_BF16 && !conv3x3_tc_supported(st.cin, st.cout)) { delete P; return MRFP_ERR_UNSUPPORTED; }
     std::vector<int>& L = P->lut;
+    st.scale_h = index_scale(ch, st.oh, sf, sfs[k]); st.scale_w = index_scale(cw, st.ow, sf, sfs[k]);
     st.idx_h = (int)L.size(); L.resize(L.size() + st.oh); make_index(ch, st.oh, sf, sfs[k], &L[st.idx_h]);
     st.idx_w = (int)L.size(); L.resize(L.size() + st.ow); make_index(cw, st.ow, sf, sfs[k], &L[st.idx_w]);
     const int ph = (ch + 2 * kTileH - 1) / (2 * kTileH) * (2 * kTileH) + 2 * kTileH;   // conv tiles are up to 16 rows tall

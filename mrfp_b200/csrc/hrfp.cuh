@@ -15,6 +15,7 @@ struct HrfpStage {
   int cin, cout, dil;
   int ch, cw;      // conv resolution (input and output of the 3x3 conv)
   int oh, ow;      // resolution after the nearest resample
+  float scale_h, scale_w;   // ATen's nearest rule: src = min(floorf(dst * scale), in - 1)  (== the idx tables)
   // offsets (in ints) into the LUT blob
   int idx_h, idx_w;       // dst -> src index, [oh], [ow]
   int cnt_h, cnt_w;       // replication count of each src row/col, zero-padded to a tile multiple (+1 tile)
@@ -61,4 +62,9 @@ int conv3x3_tc_bf16(const __nv_bfloat16* in, const __nv_bfloat16* wpack, __nv_bf
                     int cin, int cout, int dil, const int* cnt_h, const int* cnt_w, double* stat_acc,
                     cudaStream_t stream, const ConvBwdStats* bwd_stats = nullptr, bool reverse_tiles = false);
 bool conv3x3_tc_supported(int cin, int cout);
+
+// TMA-fed BN-backward reduction (bn_ring.cu); MRFP_ERR_UNSUPPORTED -> use the LDG kernel
+int bn_bwd_reduce_ring(const __nv_bfloat16* dA, const __nv_bfloat16* y, const int* idx_h, const int* idx_w,
+                       const int* host_idx_w, float scale_w, const float* stats, double* acc, int N, int C, int IH, int IW,
+                       int OH, int OW, bool reverse, cudaStream_t stream);
 }  // namespace mrfp
