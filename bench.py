@@ -265,8 +265,8 @@ def run_ours(args):
         """Public API path: autograd Functions over the C ABI (the same calls MRFPPlus.forward makes)."""
         a = xp_.detach().requires_grad_(True)
         b = f2_.detach().requires_grad_(True)
-        x = NP.np_plus_with_draws(a, *draws[0])                                        # deepv3.py:318
-        x, dec = H.hrfp_chain(a, convs, bns, H_IMG, W_IMG, x_add=x, math_mode=H.MATH_BF16, lazy_dec=True)   # :320-330
+        # deepv3.py:316-330: x = OCout + NP+(xp); NP+ call 1 rides on the chain's passes (SURVEY.md 8f-1)
+        x, dec = H.hrfp_chain(a, convs, bns, H_IMG, W_IMG, np_draws=draws[0], math_mode=H.MATH_BF16, lazy_dec=True)
         y2 = NP.np_plus_with_draws(b, *draws[1])                                       # :335
         d1 = H.hrfp_plus_add(d1_, dec)                                                 # :357
         torch.autograd.backward([x, d1, y2], [gx_, gdec_, gf2_])
@@ -469,10 +469,10 @@ def run_ours(args):
 
     base, _ = cpu_reference_run(1, 1) if world == 1 else (None, None)
 
-    # kernels launched per step (ours; memsets excluded): NP+ 2 fwd + 2 bwd; HRFP fwd 1 weight pack + 1 NCHW->NHWC +
+    # kernels launched per step (ours; memsets excluded): NP+ call 2 fwd + bwd (call 1 is folded into the chain: +1 coefficient block each way); HRFP fwd 1 weight pack + 1 NCHW->NHWC +
     # 8 conv + 8 BN finalize + 7 BN/ReLU/resample + 1 NHWC->NCHW epilogue (OCout + x); 1 fused HRFP+ add;
     # HRFP bwd 2 NCHW->NHWC + 8 x (2 BN-bwd + conv) + 1 NHWC->NCHW
-    launches_per_step = 4 + (1 + 1 + 8 + 8 + 7 + 1) + 1 + (2 + 24 + 1)
+    launches_per_step = 2 + (1 + 1 + 1 + 8 + 8 + 7 + 1) + 1 + (2 + 1 + 24 + 1)
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16 (HRFP tensor-core operands, fp32 accumulate) / f32 (NP+)", "data": "synthetic", "config": CONFIG,

@@ -111,6 +111,22 @@ int mrfp_hrfp_bwd(const mrfp_hrfp_plan_t* plan, const float* g_ocout, const floa
                   const float* const* gamma, const void* lut, const void* saved,
                   float* g_xp, void* ws, void* stream);
 
+/* NP+ call 1 folded into the chain:  ocout = OCout + NP+(xp)  — deepv3.py:316-318 followed by
+ * :320-330 when both gates are on — without materialising NP+(xp): the plane totals of xp are taken by the layout pass
+ * that feeds the chain, the per-plane (a, b) by one block, and the chain's output pass adds a*xp + b.
+ *   np_alpha, np_eps (N,cin): the two Gaussian draws of deepv3.py:274-275;  np_mean (N,cin) out: plane means, needed
+ *   by the backward;  np_beta (N,cin) out, may be NULL;  np_ws: >= mrfp_hrfp_np_ws_bytes(N,cin) bytes, 16-byte aligned.
+ * Everything else as in mrfp_hrfp_fwd / mrfp_hrfp_bwd; g_xp receives the sum of both gradient paths into xp. */
+size_t mrfp_hrfp_np_ws_bytes(int N, int C);
+int mrfp_hrfp_fwd_np(const mrfp_hrfp_plan_t* plan, const float* xp,
+                     const float* const* W, const float* const* gamma, const float* const* beta,
+                     float* const* running_mean, float* const* running_var, float momentum, float eps,
+                     const float* np_alpha, const float* np_eps, float* np_mean, float* np_beta, void* np_ws,
+                     float* ocout, float* ocout_dec, const void* lut, void* saved, void* ws, void* stream);
+int mrfp_hrfp_bwd_np(const mrfp_hrfp_plan_t* plan, const float* g_ocout, const float* g_ocout_dec,
+                     const float* const* gamma, const float* np_alpha, const float* np_eps, const float* np_mean,
+                     void* np_ws, const void* lut, const void* saved, float* g_xp, void* ws, void* stream);
+
 /* HRFP+ skip add, deepv3.py:357, fused with the production of OCout_dec: out = dec1_up + OCout_dec where
  * OCout_dec = ReLU(BN(resample(conv4))) is recomputed from the state `saved` by the preceding mrfp_hrfp_fwd
  * (which may then be called with ocout_dec == NULL): the (N,256,h/2,w/2) fp32 tensor is never materialised.

@@ -36,6 +36,14 @@ SIGNATURES = {
                                      ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
     "mrfp_hrfp_bwd": (ctypes.c_int, [ctypes.c_void_p, c_float_p, c_float_p, c_void_pp, ctypes.c_void_p,
                                      ctypes.c_void_p, c_float_p, ctypes.c_void_p, ctypes.c_void_p]),
+    "mrfp_hrfp_np_ws_bytes": (ctypes.c_size_t, [ctypes.c_int, ctypes.c_int]),
+    "mrfp_hrfp_fwd_np": (ctypes.c_int, [ctypes.c_void_p, c_float_p, c_void_pp, c_void_pp, c_void_pp, c_void_pp,
+                                        c_void_pp, ctypes.c_float, ctypes.c_float, c_float_p, c_float_p, c_float_p,
+                                        c_float_p, ctypes.c_void_p, c_float_p, c_float_p,
+                                        ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
+    "mrfp_hrfp_bwd_np": (ctypes.c_int, [ctypes.c_void_p, c_float_p, c_float_p, c_void_pp, c_float_p, c_float_p,
+                                        c_float_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, c_float_p,
+                                        ctypes.c_void_p, ctypes.c_void_p]),
     "mrfp_hrfp_plus_add": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, c_float_p, c_float_p,
                                           ctypes.c_void_p]),
     "mrfp_add_f32": (ctypes.c_int, [c_float_p, c_float_p, c_float_p, ctypes.c_size_t, ctypes.c_void_p]),

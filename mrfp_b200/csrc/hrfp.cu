@@ -88,7 +88,8 @@ __device__ __forceinline__ int lay_col(int px) { return (px & 3) * 33 + (px >> 2
 // src fp32 [N][C][HW] -> dst T [N][HW][C]; accumulate adds into dst (gradient of OCout_dec joining the chain).
 template <typename T>
 __global__ void __launch_bounds__(256)
-nchw_to_nhwc_kernel(const float* __restrict__ src, T* __restrict__ dst, int C, int HW, int accumulate) {
+nchw_to_nhwc_kernel(const float* __restrict__ src, T* __restrict__ dst, int C, int HW, int accumulate,
+                    double* __restrict__ psum) {
   pdl_sync();
   __shared__ float tile[64][kLayRow];   // [channel][lay_col(pixel)]
   const int n = blockIdx.z, c0 = blockIdx.y * 64, p0 = blockIdx.x * kLayPx, t = threadIdx.x;
@@ -113,6 +114,10 @@ nchw_to_nhwc_kernel(const float* __restrict__ src, T* __restrict__ dst, int C, i
       }
       const int col = px >> 2;                          // lay_col(px + k) = 33 * k + col
       tile[c][col] = v.x; tile[c][33 + col] = v.y; tile[c][66 + col] = v.z; tile[c][99 + col] = v.w;
+      if (psum) {                                        // plane totals for the fused NP+ (a warp = one channel row)
+        const float ps = warp_sum((v.x + v.y) + (v.z + v.w));
+        if ((t & 31) == 0 && c0 + c < C) atomicAdd(psum + (size_t)n * C + c0 + c, (double)ps);
+      }
     }
   }
   __syncthreads();
@@ -143,7 +148,8 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 nhwc_to_nchw_kernel(const T* __restrict__ y, float* __restrict__ out, const float* __restrict__ add,
                     const int* __restrict__ idx_h, const int* __restrict__ idx_w, const float* __restrict__ scale,
-                    const float* __restrict__ shift, int C, int IH, int IW, int OH, int OW) {
+                    const float* __restrict__ shift, int C, int IH, int IW, int OH, int OW,
+                    const float2* __restrict__ coef) {
   pdl_sync();
   __shared__ float tile[64][kLayRow];   // [channel][lay_col(pixel)]
   // flat grid, output rows fastest, then channel tiles, then w-tiles
@@ -189,12 +195,17 @@ nhwc_to_nchw_kernel(const T* __restrict__ y, float* __restrict__ out, const floa
         const size_t o = (((size_t)n * C + c0 + c) * OH + oh) * OW + ow;
         const int col = px >> 2;
         float4 v = make_float4(tile[c][col], tile[c][33 + col], tile[c][66 + col], tile[c][99 + col]);
+        // out = v + add, or with the fused NP+: out = v + (a * add + b) with the plane's (a, b)
+        const float2 ab = coef ? coef[(size_t)n * C + c0 + c] : make_float2(1.f, 0.f);
         if (vec && ow + 3 < OW) {
-          if (add) { const float4 a4 = *reinterpret_cast<const float4*>(add + o); v.x += a4.x; v.y += a4.y; v.z += a4.z; v.w += a4.w; }
+          if (add) {
+            const float4 a4 = *reinterpret_cast<const float4*>(add + o);
+            v.x += fmaf(ab.x, a4.x, ab.y); v.y += fmaf(ab.x, a4.y, ab.y); v.z += fmaf(ab.x, a4.z, ab.y); v.w += fmaf(ab.x, a4.w, ab.y);
+          }
           *reinterpret_cast<float4*>(out + o) = v;
         } else {
           const float vv[4] = {v.x, v.y, v.z, v.w};
-          for (int i = 0; i < 4 && ow + i < OW; ++i) out[o + i] = add ? vv[i] + add[o + i] : vv[i];
+          for (int i = 0; i < 4 && ow + i < OW; ++i) out[o + i] = add ? vv[i] + fmaf(ab.x, add[o + i], ab.y) : vv[i];
         }
       }
     }
@@ -537,6 +548,100 @@ __global__ void add_f32_kernel(const float4* __restrict__ a, const float4* __res
 }
 
 // ------------------------------------------------------------------------------------------------------
+// NP+ call 1 folded into the chain.  x = OCout + NP+(xp) with NP+(xp) = a[n,c]*xp + b[n,c]
+// (deepv3.py:268-277, :316-318, :329-330): the plane totals of xp ride on the NCHW->NHWC pass that feeds the chain,
+// one block turns them into the per-plane (a, b), and the chain's output pass applies them to its add operand —
+// NP+(xp) is never written or re-read.  Backward mirrors it with the totals of g_ocout (gin = alpha*g + dL/dm/HW,
+// SURVEY.md 8 a-1).  Same formulas, in double, as npplus.cu.
+// ------------------------------------------------------------------------------------------------------
+struct NpStem {
+  const float* alpha;   // (N,C) draw #1
+  const float* eps;     // (N,C) draw #2
+  float* mean;          // (N,C) plane means: written by the forward, read by the backward
+  float* beta;          // (N,C) forward diagnostic, may be null
+  double* psum;         // (N,C) scratch: plane totals
+  float2* coef;         // (N,C) scratch: (a, b)
+};
+
+template <bool BWD>
+__global__ void __launch_bounds__(256)
+np_stem_coef_kernel(const double* __restrict__ psum, const float* __restrict__ alpha, const float* __restrict__ eps,
+                    const float* __restrict__ mean_in, float2* __restrict__ coef, float* __restrict__ mean_out,
+                    float* __restrict__ beta_out, int N, int C, int HW) {
+  pdl_sync();
+  __shared__ double s_mbar[kMaxC], s_d[kMaxC], s_l[kMaxC];
+  __shared__ double w_best[8], w_tsum[8];
+  __shared__ int w_c[8], w_nan[8];
+  __shared__ double s_dmax, s_T;
+  __shared__ int s_cstar;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const double inv_hw = 1.0 / (double)HW;
+  double best = -1.0, tsum = 0.0;
+  int bestc = 0x7fffffff;
+  bool anynan = false;
+  for (int c = tid; c < C; c += 256) {
+    double sm = 0;
+    for (int n = 0; n < N; ++n) sm += BWD ? (double)mean_in[n * C + c] : psum[n * C + c] * inv_hw;
+    const double mbar = sm / (double)N;
+    double q = 0, l = 0;
+    for (int n = 0; n < N; ++n) {
+      const double G = psum[n * C + c];
+      const double m = BWD ? (double)mean_in[n * C + c] : G * inv_hw;
+      q += (m - mbar) * (m - mbar);
+      if (BWD) l += (double)eps[n * C + c] * m * G;                      // dL/ds[c] = sum_n eps*m*G
+    }
+    const double d = sqrt(q / (double)(N - 1));                           // N == 1 -> NaN, as torch.std (deepv3.py:272)
+    s_mbar[c] = mbar; s_d[c] = d; s_l[c] = l;
+    if (d != d) anynan = true;
+    if (d > best) { best = d; bestc = c; }
+    if (BWD) tsum += l * d;
+  }
+  for (int o = 16; o > 0; o >>= 1) {                                      // arg-max, first index wins, NaN-propagating
+    const double ob = __shfl_xor_sync(0xffffffffu, best, o);
+    const int oc = __shfl_xor_sync(0xffffffffu, bestc, o);
+    const int on = __shfl_xor_sync(0xffffffffu, (int)anynan, o);
+    tsum += __shfl_xor_sync(0xffffffffu, tsum, o);
+    if (ob > best || (ob == best && oc < bestc)) { best = ob; bestc = oc; }
+    anynan = anynan || (on != 0);
+  }
+  if (lane == 0) { w_best[warp] = best; w_c[warp] = bestc; w_nan[warp] = anynan; w_tsum[warp] = tsum; }
+  __syncthreads();
+  if (tid == 0) {
+    double b = w_best[0], t = w_tsum[0];
+    int bc = w_c[0], nn = w_nan[0];
+    for (int i = 1; i < 8; ++i) {
+      if (w_best[i] > b || (w_best[i] == b && w_c[i] < bc)) { b = w_best[i]; bc = w_c[i]; }
+      nn |= w_nan[i];
+      t += w_tsum[i];
+    }
+    s_dmax = nn ? (double)NAN : b;
+    s_cstar = bc;
+    s_T = 1.5 * t / (s_dmax * s_dmax);
+  }
+  __syncthreads();
+  const double dmax = s_dmax;
+  for (int p = tid; p < N * C; p += 256) {
+    const int c = p % C;
+    const double a = (double)alpha[p], d = s_d[c];
+    const double beta = 1.0 + (double)eps[p] * (d / dmax * 1.5);         // deepv3.py:273,275
+    double b;
+    if (!BWD) {
+      const double m = psum[p] * inv_hw;
+      b = (beta - a) * m;                                                 // out = a*x + (beta-a)*m  (:276)
+      mean_out[p] = (float)m;
+      if (beta_out) beta_out[p] = (float)beta;
+    } else {
+      const double m = (double)mean_in[p];
+      double dLdd = 1.5 / dmax * s_l[c];
+      if (c == s_cstar) dLdd -= s_T;
+      const double dd_dm = (d == 0.0) ? 0.0 : (m - s_mbar[c]) / ((double)(N - 1) * d);   // std_backward zero-fills
+      b = ((beta - a) * psum[p] + dLdd * dd_dm) * inv_hw;
+    }
+    coef[p] = make_float2((float)a, (float)b);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------
 // host: geometry (must be bit-identical to ATen's upsample_nearest2d index rule)
 // ------------------------------------------------------------------------------------------------------
 float index_scale(int in, int out, bool has_sf, double sf) { return has_sf ? (float)(1.0 / sf) : ((float)in / (float)out); }
@@ -564,8 +669,9 @@ template <typename T>
 int hrfp_forward(const mrfp_hrfp_plan* P, const float* xp, const float* const* W, const float* const* gamma,
                  const float* const* beta, float* const* rmean, float* const* rvar, float momentum, float eps,
                  const float* x_add, float* ocout, float* ocout_dec, const int* lut, char* saved, char* ws,
-                 cudaStream_t s, const DeviceInfo& di) {
+                 cudaStream_t s, const DeviceInfo& di, const NpStem* np) {
   double* acc = reinterpret_cast<double*>(ws + P->acc_fwd_off);
+  if (np) MRFP_CUDA_TRY(cudaMemsetAsync(np->psum, 0, (size_t)P->N * P->cin * sizeof(double), s));
   MRFP_CUDA_TRY(cudaMemsetAsync(acc, 0, (size_t)kHrfpStages * 2 * kMaxC * sizeof(double), s));
   const int last = ocout ? kHrfpStages : 4;
   const bool tc = P->mode == MRFP_MATH_BF16;
@@ -591,7 +697,10 @@ int hrfp_forward(const mrfp_hrfp_plan* P, const float* xp, const float* const* W
   {
     const int HW = P->xh * P->xw;
     dim3 g((HW + kLayPx - 1) / kLayPx, (P->cin + 63) / 64, P->N);
-    launch_k(nchw_to_nhwc_kernel<T>, dim3(g), dim3(256), 0, s, xp, bufA, P->cin, HW, 0);
+    launch_k(nchw_to_nhwc_kernel<T>, dim3(g), dim3(256), 0, s, xp, bufA, P->cin, HW, 0, np ? np->psum : (double*)nullptr);
+    if (np)      // NP+ call 1 folded into the chain: plane totals came with the layout pass, (a, b) per plane from one block
+      launch_k(np_stem_coef_kernel<false>, dim3(1), dim3(256), 0, s, (const double*)np->psum, np->alpha, np->eps,
+               (const float*)nullptr, np->coef, np->mean, np->beta, P->N, P->cin, HW);
   }
   T* cur = bufA;
   T* nxt = bufB;
@@ -622,13 +731,14 @@ int hrfp_forward(const mrfp_hrfp_plan* P, const float* xp, const float* const* W
       const unsigned g = (unsigned)(((st.ow + kLayPx - 1) / kLayPx) * ((st.cout + 63) / 64)) * (unsigned)(P->N * st.oh);
       launch_k(nhwc_to_nchw_kernel<T>, dim3(g), dim3(256), 0, s, Y, ocout_dec, nullptr, lut + st.idx_h, lut + st.idx_w,
                                                         stats + 2 * kMaxC, stats + 3 * kMaxC, st.cout, st.ch, st.cw,
-                                                        st.oh, st.ow);
+                                                        st.oh, st.ow, (const float2*)nullptr);
     }
     if (k == kHrfpStages - 1) {
       const unsigned g = (unsigned)(((st.ow + kLayPx - 1) / kLayPx) * ((st.cout + 63) / 64)) * (unsigned)(P->N * st.oh);
-      launch_k(nhwc_to_nchw_kernel<T>, dim3(g), dim3(256), 0, s, Y, ocout, x_add, lut + st.idx_h, lut + st.idx_w,
+      // with the fused NP+ the add operand is xp itself under the plane's affine map: OCout + (a*xp + b)
+      launch_k(nhwc_to_nchw_kernel<T>, dim3(g), dim3(256), 0, s, Y, ocout, np ? xp : x_add, lut + st.idx_h, lut + st.idx_w,
                                                         stats + 2 * kMaxC, stats + 3 * kMaxC, st.cout, st.ch, st.cw,
-                                                        st.oh, st.ow);
+                                                        st.oh, st.ow, np ? np->coef : (const float2*)nullptr);
     } else if (k + 1 < last) {
       launch_k(bn_relu_resample_kernel<T>, dim3(even_grid(P->N * st.oh, di.sm_count * 8)), dim3(256), 0, s, 
           Y, nxt, lut + st.idx_h, lut + st.idx_w, stats + 2 * kMaxC, stats + 3 * kMaxC, P->N, st.cout, st.ch, st.cw,
@@ -642,8 +752,11 @@ int hrfp_forward(const mrfp_hrfp_plan* P, const float* xp, const float* const* W
 
 template <typename T>
 int hrfp_backward(const mrfp_hrfp_plan* P, const float* g_ocout, const float* g_ocout_dec, const float* const* gamma,
-                  const int* lut, const char* saved, float* g_xp, char* ws, cudaStream_t s, const DeviceInfo& di) {
+                  const int* lut, const char* saved, float* g_xp, char* ws, cudaStream_t s, const DeviceInfo& di,
+                  const NpStem* np) {
   double* acc = reinterpret_cast<double*>(ws + P->acc_bwd_off);
+  if (np && !g_ocout) np = nullptr;                      // no gradient through `x`: NP+ contributes nothing
+  if (np) MRFP_CUDA_TRY(cudaMemsetAsync(np->psum, 0, (size_t)P->N * P->cin * sizeof(double), s));
   MRFP_CUDA_TRY(cudaMemsetAsync(acc, 0, (size_t)kHrfpStages * 2 * kMaxC * sizeof(double), s));
   T* g0 = reinterpret_cast<T*>(ws + P->bufs_off);
   T* g1 = reinterpret_cast<T*>(ws + P->bufs_off + P->buf_g_bytes);
@@ -664,7 +777,12 @@ int hrfp_backward(const mrfp_hrfp_plan* P, const float* g_ocout, const float* g_
       const int HW = st.oh * st.ow;
       dim3 g((HW + kLayPx - 1) / kLayPx, (st.cout + 63) / 64, P->N);
       T* dst = dA ? dA : g0;
-      launch_k(nchw_to_nhwc_kernel<T>, dim3(g), dim3(256), 0, s, gin, dst, st.cout, HW, dA ? 1 : 0);
+      const bool np_here = np && k == kHrfpStages - 1;       // plane totals of g_ocout for the fused NP+ backward
+      launch_k(nchw_to_nhwc_kernel<T>, dim3(g), dim3(256), 0, s, gin, dst, st.cout, HW, dA ? 1 : 0,
+               np_here ? np->psum : (double*)nullptr);
+      if (np_here)
+        launch_k(np_stem_coef_kernel<true>, dim3(1), dim3(256), 0, s, (const double*)np->psum, np->alpha, np->eps,
+                 (const float*)np->mean, np->coef, (float*)nullptr, (float*)nullptr, P->N, P->cin, P->xh * P->xw);
       if (!dA) { dA = g0; other = g1; }
     }
     if (!dA) continue;
@@ -732,8 +850,10 @@ int hrfp_backward(const mrfp_hrfp_plan* P, const float* g_ocout, const float* g_
     return MRFP_OK;
   }
   const unsigned g = (unsigned)(((P->xw + kLayPx - 1) / kLayPx) * ((P->cin + 63) / 64)) * (unsigned)(P->N * P->xh);
-  launch_k(nhwc_to_nchw_kernel<T>, dim3(g), dim3(256), 0, s, dA, g_xp, nullptr, nullptr, nullptr, nullptr, nullptr, P->cin,
-                                                    P->xh, P->xw, P->xh, P->xw);
+  // fused NP+ backward: g_xp = dA_0 + (a' * g_ocout + b') with the plane's backward coefficients
+  const bool np_add = np && g_ocout;
+  launch_k(nhwc_to_nchw_kernel<T>, dim3(g), dim3(256), 0, s, dA, g_xp, np_add ? g_ocout : (const float*)nullptr, nullptr, nullptr,
+           nullptr, nullptr, P->cin, P->xh, P->xw, P->xh, P->xw, np_add ? np->coef : (const float2*)nullptr);
   MRFP_CUDA_TRY(cudaGetLastError());
   return MRFP_OK;
 }
@@ -847,10 +967,10 @@ extern "C" int mrfp_hrfp_plan_stage(const mrfp_hrfp_plan_t* P, int k, int* out7)
   return MRFP_OK;
 }
 
-extern "C" int mrfp_hrfp_fwd(const mrfp_hrfp_plan_t* P, const float* xp, const float* const* W,
-                             const float* const* gamma, const float* const* beta, float* const* running_mean,
-                             float* const* running_var, float momentum, float eps, const float* x_add, float* ocout,
-                             float* ocout_dec, const void* lut, void* saved, void* ws, void* stream) {
+static int hrfp_fwd_entry(const mrfp_hrfp_plan_t* P, const float* xp, const float* const* W, const float* const* gamma,
+                          const float* const* beta, float* const* running_mean, float* const* running_var, float momentum,
+                          float eps, const float* x_add, float* ocout, float* ocout_dec, const void* lut, void* saved,
+                          void* ws, void* stream, const NpStem* np) {
   if (!P || P->magic != kPlanMagic) return MRFP_ERR_BAD_PLAN;
   if (!xp || !W || !gamma || !lut || !saved || !ws) return MRFP_ERR_NULL_POINTER;
   if (((uintptr_t)saved | (uintptr_t)ws | (uintptr_t)lut) & 255) return MRFP_ERR_WORKSPACE;
@@ -863,14 +983,14 @@ extern "C" int mrfp_hrfp_fwd(const mrfp_hrfp_plan_t* P, const float* xp, const f
   cudaStream_t s = (cudaStream_t)stream;
   if (P->mode == MRFP_MATH_BF16)
     return hrfp_forward<__nv_bfloat16>(P, xp, W, gamma, beta, running_mean, running_var, momentum, eps, x_add, ocout,
-                                       ocout_dec, (const int*)lut, (char*)saved, (char*)ws, s, di);
+                                       ocout_dec, (const int*)lut, (char*)saved, (char*)ws, s, di, np);
   return hrfp_forward<float>(P, xp, W, gamma, beta, running_mean, running_var, momentum, eps, x_add, ocout, ocout_dec,
-                             (const int*)lut, (char*)saved, (char*)ws, s, di);
+                             (const int*)lut, (char*)saved, (char*)ws, s, di, np);
 }
 
-extern "C" int mrfp_hrfp_bwd(const mrfp_hrfp_plan_t* P, const float* g_ocout, const float* g_ocout_dec,
-                             const float* const* gamma, const void* lut, const void* saved, float* g_xp, void* ws,
-                             void* stream) {
+static int hrfp_bwd_entry(const mrfp_hrfp_plan_t* P, const float* g_ocout, const float* g_ocout_dec,
+                          const float* const* gamma, const void* lut, const void* saved, float* g_xp, void* ws,
+                          void* stream, const NpStem* np) {
   if (!P || P->magic != kPlanMagic) return MRFP_ERR_BAD_PLAN;
   if (!gamma || !lut || !saved || !g_xp || !ws) return MRFP_ERR_NULL_POINTER;
   if (((uintptr_t)saved | (uintptr_t)ws | (uintptr_t)lut) & 255) return MRFP_ERR_WORKSPACE;
@@ -880,8 +1000,61 @@ extern "C" int mrfp_hrfp_bwd(const mrfp_hrfp_plan_t* P, const float* g_ocout, co
   cudaStream_t s = (cudaStream_t)stream;
   if (P->mode == MRFP_MATH_BF16)
     return hrfp_backward<__nv_bfloat16>(P, g_ocout, g_ocout_dec, gamma, (const int*)lut, (const char*)saved, g_xp,
-                                        (char*)ws, s, di);
-  return hrfp_backward<float>(P, g_ocout, g_ocout_dec, gamma, (const int*)lut, (const char*)saved, g_xp, (char*)ws, s, di);
+                                        (char*)ws, s, di, np);
+  return hrfp_backward<float>(P, g_ocout, g_ocout_dec, gamma, (const int*)lut, (const char*)saved, g_xp, (char*)ws, s, di,
+                              np);
+}
+
+extern "C" int mrfp_hrfp_fwd(const mrfp_hrfp_plan_t* P, const float* xp, const float* const* W,
+                             const float* const* gamma, const float* const* beta, float* const* running_mean,
+                             float* const* running_var, float momentum, float eps, const float* x_add, float* ocout,
+                             float* ocout_dec, const void* lut, void* saved, void* ws, void* stream) {
+  return hrfp_fwd_entry(P, xp, W, gamma, beta, running_mean, running_var, momentum, eps, x_add, ocout, ocout_dec, lut,
+                        saved, ws, stream, nullptr);
+}
+
+extern "C" int mrfp_hrfp_bwd(const mrfp_hrfp_plan_t* P, const float* g_ocout, const float* g_ocout_dec,
+                             const float* const* gamma, const void* lut, const void* saved, float* g_xp, void* ws,
+                             void* stream) {
+  return hrfp_bwd_entry(P, g_ocout, g_ocout_dec, gamma, lut, saved, g_xp, ws, stream, nullptr);
+}
+
+// ---- NP+ call 1 folded into the chain ----
+extern "C" size_t mrfp_hrfp_np_ws_bytes(int N, int C) {
+  if (N <= 0 || C <= 0) return 0;
+  return (size_t)N * C * (sizeof(double) + sizeof(float2));
+}
+
+static bool np_stem_setup(const mrfp_hrfp_plan_t* P, const float* alpha, const float* eps, float* mean, float* beta,
+                          void* np_ws, NpStem* np) {
+  if (!P || P->magic != kPlanMagic || !alpha || !eps || !mean || !np_ws || ((uintptr_t)np_ws & 15)) return false;
+  np->alpha = alpha; np->eps = eps; np->mean = mean; np->beta = beta;
+  np->psum = reinterpret_cast<double*>(np_ws);
+  np->coef = reinterpret_cast<float2*>(np->psum + (size_t)P->N * P->cin);
+  return true;
+}
+
+extern "C" int mrfp_hrfp_fwd_np(const mrfp_hrfp_plan_t* P, const float* xp, const float* const* W,
+                                const float* const* gamma, const float* const* beta, float* const* running_mean,
+                                float* const* running_var, float momentum, float eps, const float* np_alpha,
+                                const float* np_eps, float* np_mean, float* np_beta, void* np_ws, float* ocout,
+                                float* ocout_dec, const void* lut, void* saved, void* ws, void* stream) {
+  NpStem np;
+  if (!ocout) return MRFP_ERR_NULL_POINTER;              // the fused form only exists for x = OCout + NP+(xp)
+  if (!np_stem_setup(P, np_alpha, np_eps, np_mean, np_beta, np_ws, &np))
+    return (P && P->magic == kPlanMagic) ? MRFP_ERR_NULL_POINTER : MRFP_ERR_BAD_PLAN;
+  return hrfp_fwd_entry(P, xp, W, gamma, beta, running_mean, running_var, momentum, eps, nullptr, ocout, ocout_dec, lut,
+                        saved, ws, stream, &np);
+}
+
+extern "C" int mrfp_hrfp_bwd_np(const mrfp_hrfp_plan_t* P, const float* g_ocout, const float* g_ocout_dec,
+                                const float* const* gamma, const float* np_alpha, const float* np_eps,
+                                const float* np_mean, void* np_ws, const void* lut, const void* saved, float* g_xp,
+                                void* ws, void* stream) {
+  NpStem np;
+  if (!np_stem_setup(P, np_alpha, np_eps, const_cast<float*>(np_mean), nullptr, np_ws, &np))
+    return (P && P->magic == kPlanMagic) ? MRFP_ERR_NULL_POINTER : MRFP_ERR_BAD_PLAN;
+  return hrfp_bwd_entry(P, g_ocout, g_ocout_dec, gamma, lut, saved, g_xp, ws, stream, &np);
 }
 
 template <typename T>
@@ -892,7 +1065,7 @@ static int hrfp_plus_add_impl(const mrfp_hrfp_plan* P, const char* saved, const 
   const float* stats = reinterpret_cast<const float*>(saved + P->stats_off) + (size_t)3 * 4 * kMaxC;
   const unsigned g = (unsigned)(((st.ow + kLayPx - 1) / kLayPx) * ((st.cout + 63) / 64)) * (unsigned)(P->N * st.oh);
   launch_k(nhwc_to_nchw_kernel<T>, dim3(g), dim3(256), 0, s, Y, out, dec1_up, lut + st.idx_h, lut + st.idx_w, stats + 2 * kMaxC,
-                                            stats + 3 * kMaxC, st.cout, st.ch, st.cw, st.oh, st.ow);
+                                            stats + 3 * kMaxC, st.cout, st.ch, st.cw, st.oh, st.ow, (const float2*)nullptr);
   MRFP_CUDA_TRY(cudaGetLastError());
   return MRFP_OK;
 }

@@ -102,11 +102,12 @@ class HrfpDec:
 
 
 class _HrfpFn(torch.autograd.Function):
-    """(xp, x_add) -> (OCout + x_add, OCout_dec | token).  x_add may be None (returns OCout alone)."""
+    """(xp, x_add) -> (OCout + x_add, OCout_dec | token).  x_add may be None (returns OCout alone).
+    With `np_draws = (alpha, eps)` the first output is OCout + NP+(xp) (deepv3.py:316-318 folded into the chain)."""
 
     @staticmethod
     def forward(ctx, xp, x_add, plan, weights, gammas, betas, rmeans, rvars, momentum, eps, want_out, want_dec,
-                holder):
+                holder, np_draws=None):
         lib = _lib.load()
         if not xp.is_cuda or xp.dtype != torch.float32:
             raise _lib.MrfpError("HRFP kernels need a CUDA fp32 tensor (no CPU fallback)")
@@ -122,13 +123,31 @@ class _HrfpFn(torch.autograd.Function):
         ba = _ptr_array(betas) if betas is not None else None
         rma = _ptr_array(rmeans) if rmeans is not None else None
         rva = _ptr_array(rvars) if rvars is not None else None
-        with torch.cuda.device(dev):
-            rc = lib.mrfp_hrfp_fwd(plan.handle, xp_c.data_ptr(), wa, ga, ba, rma, rva, momentum, eps,
-                                   None if xa is None else xa.data_ptr(),
-                                   None if ocout is None else ocout.data_ptr(),
-                                   None if ocdec is None else ocdec.data_ptr(),
-                                   plan.lut.data_ptr(), saved.data_ptr(), ws.data_ptr(), _stream_ptr(dev))
-        _lib.check(rc, "mrfp_hrfp_fwd")
+        ctx.np = None
+        if np_draws is not None:
+            if x_add is not None or not want_out:
+                raise _lib.MrfpError("np_draws folds NP+(xp) into OCout + x: it needs want_out and no x_add")
+            n, c = plan.n, plan.cin
+            np_alpha = np_draws[0].reshape(n, c).to(torch.float32).contiguous()
+            np_eps = np_draws[1].reshape(n, c).to(torch.float32).contiguous()
+            np_mean = torch.empty((n, c), dtype=torch.float32, device=dev)
+            np_ws = torch.empty(lib.mrfp_hrfp_np_ws_bytes(n, c), dtype=torch.uint8, device=dev)
+            with torch.cuda.device(dev):
+                rc = lib.mrfp_hrfp_fwd_np(plan.handle, xp_c.data_ptr(), wa, ga, ba, rma, rva, momentum, eps,
+                                          np_alpha.data_ptr(), np_eps.data_ptr(), np_mean.data_ptr(), None,
+                                          np_ws.data_ptr(), ocout.data_ptr(),
+                                          None if ocdec is None else ocdec.data_ptr(),
+                                          plan.lut.data_ptr(), saved.data_ptr(), ws.data_ptr(), _stream_ptr(dev))
+            _lib.check(rc, "mrfp_hrfp_fwd_np")
+            ctx.np = (np_alpha, np_eps, np_mean, np_ws)
+        else:
+            with torch.cuda.device(dev):
+                rc = lib.mrfp_hrfp_fwd(plan.handle, xp_c.data_ptr(), wa, ga, ba, rma, rva, momentum, eps,
+                                       None if xa is None else xa.data_ptr(),
+                                       None if ocout is None else ocout.data_ptr(),
+                                       None if ocdec is None else ocdec.data_ptr(),
+                                       plan.lut.data_ptr(), saved.data_ptr(), ws.data_ptr(), _stream_ptr(dev))
+            _lib.check(rc, "mrfp_hrfp_fwd")
         ctx.plan = plan
         ctx.saved_buf = saved
         ctx.gammas = [g for g in gammas]       # keep alive; gamma is read again in backward
@@ -167,18 +186,29 @@ class _HrfpFn(torch.autograd.Function):
             ga = _ptr_array(ctx.gammas)
             ws = plan.workspace()
             with torch.cuda.device(dev):
-                rc = lib.mrfp_hrfp_bwd(plan.handle, None if g_out_c is None else g_out_c.data_ptr(),
-                                       None if g_dec_c is None else g_dec_c.data_ptr(), ga, plan.lut.data_ptr(),
-                                       ctx.saved_buf.data_ptr(), g_xp.data_ptr(), ws.data_ptr(), _stream_ptr(dev))
+                if ctx.np is not None:      # gradient through NP+(xp) joins in the chain's last pass
+                    a_, e_, m_, w_ = ctx.np
+                    rc = lib.mrfp_hrfp_bwd_np(plan.handle, None if g_out_c is None else g_out_c.data_ptr(),
+                                              None if g_dec_c is None else g_dec_c.data_ptr(), ga, a_.data_ptr(),
+                                              e_.data_ptr(), m_.data_ptr(), w_.data_ptr(), plan.lut.data_ptr(),
+                                              ctx.saved_buf.data_ptr(), g_xp.data_ptr(), ws.data_ptr(), _stream_ptr(dev))
+                else:
+                    rc = lib.mrfp_hrfp_bwd(plan.handle, None if g_out_c is None else g_out_c.data_ptr(),
+                                           None if g_dec_c is None else g_dec_c.data_ptr(), ga, plan.lut.data_ptr(),
+                                           ctx.saved_buf.data_ptr(), g_xp.data_ptr(), ws.data_ptr(), _stream_ptr(dev))
             _lib.check(rc, "mrfp_hrfp_bwd")
         g_add = g_out_c if (ctx.has_add and ctx.needs_input_grad[1]) else None
         ctx.saved_buf = None
-        return (g_xp, g_add) + (None,) * 11
+        ctx.np = None
+        return (g_xp, g_add) + (None,) * 12
 
 
 def hrfp_chain(xp, convs, bns, h, w, x_add=None, want_out=True, want_dec=True, math_mode=MATH_BF16,
-               update_running_stats=True, lazy_dec=False):
+               update_running_stats=True, lazy_dec=False, np_draws=None):
     """Runs the chain of deepv3.py:320-327 on `xp` with the caller's 8 conv / 8 BN modules.
+
+    `np_draws=(alpha, eps)` (the two draws of deepv3.py:274-275) makes the first output OCout + NP+(xp) — NP+ call 1
+    (deepv3.py:316-318) rides on the chain's own passes and NP+(xp) is never materialised.
 
     Returns (OCout [+ x_add], OCout_dec) restricted to the requested outputs.  With `lazy_dec=True` the second
     value is an `HrfpDec` handle for `hrfp_plus_add` instead of a materialised tensor."""
@@ -195,7 +225,7 @@ def hrfp_chain(xp, convs, bns, h, w, x_add=None, want_out=True, want_dec=True, m
     eps = bns[0].eps
     holder = [] if (lazy_dec and want_dec) else None
     outs = _HrfpFn.apply(xp, x_add, plan, weights, gammas, betas, rmeans, rvars, float(momentum), float(eps),
-                         want_out, want_dec, holder)
+                         want_out, want_dec, holder, np_draws)
     if track:
         n_run = 8 if want_out else 4
         for b in bns[:n_run]:

@@ -17,6 +17,8 @@ reference's buffer updates (running_mean / running_var / num_batches_tracked) in
 import math
 import random
 
+import os
+
 import torch
 import torch.nn as nn
 import torch.nn.functional as F
@@ -61,6 +63,8 @@ def init_head(*models):
 class MRFPMixin:
     """The MRFP layers and insertion points, independent of the trunk (used by MRFPPlus below and usable
     on other trunks: SURVEY.md §8f-2)."""
+    # fold NP+ call 1 into the HRFP chain when both gates are on (same result, two passes fewer); MRFP_FUSE_STEM_NP=0: off
+    fuse_stem_np = os.environ.get("MRFP_FUSE_STEM_NP", "1") != "0"
 
     def _build_hrfp(self, in_ch=64, widths=(64, 64, 128, 256)):
         chans = [in_ch, widths[0], widths[1], widths[2], widths[3], widths[2], widths[1], widths[0], in_ch]
@@ -91,15 +95,20 @@ class MRFPMixin:
     def mrfp_stem(self, xp, h, w, training, p, p2, p3):
         """Insertion point 1 (deepv3.py:316-330).  Returns (x, OCout_dec or None)."""
         x = xp
-        if training and p2 < 0.5:
-            x = self.Normalization_Perturbation_Plus(xp)
         want_out = training and p < 0.5
         want_dec = training and p3 < 0.5
+        np_draws = None
+        if training and p2 < 0.5:
+            if want_out and self.fuse_stem_np:       # OCout + NP+(xp): NP+ rides on the chain's passes (SURVEY 8f-1)
+                np_draws = _npplus.draw_np_plus_factors(xp)                 # same RNG position as the unfused call
+            else:
+                x = self.Normalization_Perturbation_Plus(xp)
         dec = None
         if want_out or want_dec:
             convs, bns = self.hrfp_modules()
-            out, dec = _hrfp.hrfp_chain(xp, convs, bns, h, w, x_add=x if want_out else None,
-                                        want_out=want_out, want_dec=want_dec, math_mode=self.math_mode, lazy_dec=True)
+            out, dec = _hrfp.hrfp_chain(xp, convs, bns, h, w, x_add=x if (want_out and np_draws is None) else None,
+                                        want_out=want_out, want_dec=want_dec, math_mode=self.math_mode, lazy_dec=True,
+                                        np_draws=np_draws)
             if want_out:
                 x = out                                                     # OCout + x  (deepv3.py:330)
         elif training and self.strict_buffers:

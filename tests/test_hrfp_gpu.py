@@ -160,6 +160,47 @@ def test_wide_stem_128_channels(mode):
     assert _relerr(x.grad.cpu().numpy(), rg) <= t["bwd"]
 
 
+@pytest.mark.parametrize("mode", [0, 2])
+def test_np_plus_folded_into_the_chain_equals_the_two_step_form(mode):
+    """x = OCout + NP+(xp) (deepv3.py:316-330) through the fused entry points vs NP+ kernel followed by the chain with
+    x_add: same output, same gradient into xp, and NP+ vs the oracle on the difference OCout+NP+(xp) - OCout."""
+    from mrfp_b200.hrfp import hrfp_chain
+    from mrfp_b200.npplus import np_plus_with_draws
+    n, h, w, xh, xw = 3, 96, 80, 24, 20
+    ws, gs = make_hrfp_params(31)
+    convs, bns = _modules(ws, gs, "cuda")
+    xp_np = make_feat(32, (n, 64, xh, xw))
+    rng = np.random.default_rng(33)
+    alpha = torch.from_numpy((1 + 0.75 * rng.standard_normal((n, 64, 1, 1))).astype(np.float32)).cuda()
+    eps = torch.from_numpy((0.75 * rng.standard_normal((n, 64, 1, 1))).astype(np.float32)).cuda()
+    g1 = torch.from_numpy(rng.standard_normal((n, 64, xh, xw)).astype(np.float32)).cuda()
+    g2 = torch.from_numpy(rng.standard_normal((n, 256, h // 2, w // 2)).astype(np.float32)).cuda()
+
+    xa = torch.from_numpy(xp_np).cuda().requires_grad_(True)
+    out_a, dec_a = hrfp_chain(xa, convs, bns, h, w, np_draws=(alpha, eps), math_mode=mode, update_running_stats=False)
+    torch.autograd.backward([out_a, dec_a], [g1, g2])
+
+    xb = torch.from_numpy(xp_np).cuda().requires_grad_(True)
+    out_b, dec_b = hrfp_chain(xb, convs, bns, h, w, x_add=np_plus_with_draws(xb, alpha, eps), math_mode=mode,
+                              update_running_stats=False)
+    torch.autograd.backward([out_b, dec_b], [g1, g2])
+
+    # fp32 mode: the two forms differ by fp32 rounding only.  bf16 mode: the BN statistics are accumulated with
+    # atomics, so two runs of the SAME chain already differ by bf16 rounding flips (the documented bf16 tolerances).
+    t_f, t_b = (2e-6, 5e-6) if mode == 0 else (TOL_VS_BF16_ORACLE["fwd"], TOL_VS_BF16_ORACLE["bwd"])
+    scale = out_b.abs().max().item()
+    assert (out_a - out_b).abs().max().item() <= t_f * scale
+    assert (dec_a - dec_b).abs().max().item() <= t_f * dec_b.abs().max().item()
+    gscale = xb.grad.abs().max().item()
+    assert (xa.grad - xb.grad).abs().max().item() <= t_b * gscale
+    # and against the oracle's NP+ (fp64): (OCout + NP+(xp)) - OCout
+    out_plain, _ = hrfp_chain(xb.detach(), convs, bns, h, w, want_dec=False, math_mode=mode, update_running_stats=False)
+    ref, _, _ = O.np_plus_forward(xp_np.astype(np.float64), alpha.cpu().numpy().astype(np.float64).reshape(n, 64),
+                                  eps.cpu().numpy().astype(np.float64).reshape(n, 64))
+    got = (out_a - out_plain).detach().cpu().numpy()
+    assert np.abs(got - ref).max() <= 1e-5 * np.abs(ref).max() + (2e-6 if mode == 0 else t_f) * scale
+
+
 def test_plan_geometry_768():
     from mrfp_b200.hrfp import HrfpPlan
     p = HrfpPlan(8, 64, 192, 192, 768, 768, "cuda", 0)
