@@ -126,7 +126,7 @@ __global__ void __launch_bounds__(kThreads, 1)
 conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constant__ CUtensorMap tmap_w,
                   const __grid_constant__ CUtensorMap tmap_out, int CIN, int dil, int tiles_h, int tiles_w,
                   int num_tiles, const int* __restrict__ cnt_h, const int* __restrict__ cnt_w,
-                  double* __restrict__ stat_acc, const ConvBwdStats bs, int rev) {
+                  double* __restrict__ stat_acc, const ConvBwdStats bs, int rev, const ConvBnFinalize fin) {
   using C = Cfg<COUT>;
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -347,6 +347,32 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_cons
       for (int c = threadIdx.x - 64; c < COUT; c += 128) {
         atomicAdd(stat_acc + c, (double)s_stats[c]);
         atomicAdd(stat_acc + kMaxC + c, (double)s_stats[COUT + c]);
+      }
+    }
+    if (!BWD && stat_acc && fin.stats) {
+      // BN finalisation by the last CTA to arrive (its adds and everybody else's are visible behind the fences)
+      __threadfence();
+      epi_bar_sync();
+      if (leader) s_wgt[0] = (atomicAdd(fin.counter, 1u) == gridDim.x - 1) ? 1.f : 0.f;
+      epi_bar_sync();
+      if (s_wgt[0] != 0.f) {
+        __threadfence();
+        for (int c = et; c < COUT; c += 128) {
+          const double mean = __ldcg(stat_acc + c) / fin.count;
+          double var = __ldcg(stat_acc + kMaxC + c) / fin.count - mean * mean;
+          if (var < 0) var = 0;
+          const double invstd = 1.0 / sqrt(var + (double)fin.eps);
+          const float sc = (float)((double)fin.gamma[c] * invstd);
+          const float b = fin.beta ? fin.beta[c] : 0.f;
+          fin.stats[0 * kMaxC + c] = (float)mean;
+          fin.stats[1 * kMaxC + c] = (float)invstd;
+          fin.stats[2 * kMaxC + c] = sc;
+          fin.stats[3 * kMaxC + c] = (float)((double)b - mean * (double)sc);
+          if (fin.running_mean) fin.running_mean[c] = (1.f - fin.momentum) * fin.running_mean[c] + fin.momentum * (float)mean;
+          if (fin.running_var)
+            fin.running_var[c] = (1.f - fin.momentum) * fin.running_var[c] +
+                                 fin.momentum * (float)(var * (fin.count / (fin.count - 1.0)));
+        }
       }
     }
   }
@@ -619,7 +645,7 @@ int make_map(CUtensorMap* m, const void* base, int rank, const cuuint64_t* dims,
 template <int COUT>
 int launch(const __nv_bfloat16* in, const __nv_bfloat16* wpack, __nv_bfloat16* out, int N, int H, int W, int cin,
            int dil, const int* cnt_h, const int* cnt_w, double* stat_acc, const ConvBwdStats& bs, int rev,
-           cudaStream_t stream) {
+           const ConvBnFinalize& fin, cudaStream_t stream) {
   CUtensorMap m_in, m_w, m_out;
   {
     const cuuint64_t dims[4] = {(cuuint64_t)cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
@@ -652,7 +678,7 @@ int launch(const __nv_bfloat16* in, const __nv_bfloat16* wpack, __nv_bfloat16* o
   auto kern = bs.y ? conv3x3_tc_kernel<COUT, true> : conv3x3_tc_kernel<COUT, false>;
   MRFP_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<COUT>::kSmemBytes));
   launch_k(kern, dim3(grid), dim3(kThreads), Cfg<COUT>::kSmemBytes, stream, m_in, m_w, m_out, cin, dil, tiles_h, tiles_w, num_tiles, cnt_h,
-                                                           cnt_w, stat_acc, bs, rev);
+                                                           cnt_w, stat_acc, bs, rev, fin);
   MRFP_CUDA_TRY(cudaGetLastError());
   return MRFP_OK;
 }
@@ -707,8 +733,14 @@ bool conv3x3_tc_supported(int cin, int cout) {
 
 int conv3x3_tc_bf16(const __nv_bfloat16* in, const __nv_bfloat16* wpack, __nv_bfloat16* out, int N, int H, int W,
                     int cin, int cout, int dil, const int* cnt_h, const int* cnt_w, double* stat_acc,
-                    cudaStream_t stream, const ConvBwdStats* bwd_stats, bool reverse_tiles) {
+                    cudaStream_t stream, const ConvBwdStats* bwd_stats, bool reverse_tiles,
+                    const ConvBnFinalize* finalize) {
   ConvBwdStats bs = {};
+  ConvBnFinalize fin = {};
+  if (finalize) {
+    if (!stat_acc || !finalize->gamma || !finalize->stats || !finalize->counter) return MRFP_ERR_NULL_POINTER;
+    fin = *finalize;
+  }
   const int rev = reverse_tiles ? 1 : 0;
   if (bwd_stats) {
     if (!stat_acc || !bwd_stats->y || !bwd_stats->idx_h || !bwd_stats->idx_w || !bwd_stats->scale || !bwd_stats->shift)
@@ -720,7 +752,7 @@ int conv3x3_tc_bf16(const __nv_bfloat16* in, const __nv_bfloat16* wpack, __nv_bf
   if (((uintptr_t)in | (uintptr_t)wpack | (uintptr_t)out) & 15) return MRFP_ERR_WORKSPACE;
   static const int mode = getenv("MRFP_CONV_MODE") ? atoi(getenv("MRFP_CONV_MODE")) : 0;   // 0 = one box per tap, 1 = halo tile
   static const int bo_mode = getenv("MRFP_CONV_BO") ? atoi(getenv("MRFP_CONV_BO")) : 0;   // measured: views are swizzled by absolute address, phase field stays 0
-  if (mode == 1 && dil <= 2 && !bwd_stats) {
+  if (mode == 1 && dil <= 2 && !bwd_stats && !finalize) {
     switch (cout) {
       case 64: return launch_halo<64>(in, wpack, out, N, H, W, cin, dil, cnt_h, cnt_w, stat_acc, bo_mode, stream);
       case 128: return launch_halo<128>(in, wpack, out, N, H, W, cin, dil, cnt_h, cnt_w, stat_acc, bo_mode, stream);
@@ -728,9 +760,9 @@ int conv3x3_tc_bf16(const __nv_bfloat16* in, const __nv_bfloat16* wpack, __nv_bf
     }
   }
   switch (cout) {
-    case 64: return launch<64>(in, wpack, out, N, H, W, cin, dil, cnt_h, cnt_w, stat_acc, bs, rev, stream);
-    case 128: return launch<128>(in, wpack, out, N, H, W, cin, dil, cnt_h, cnt_w, stat_acc, bs, rev, stream);
-    case 256: return launch<256>(in, wpack, out, N, H, W, cin, dil, cnt_h, cnt_w, stat_acc, bs, rev, stream);
+    case 64: return launch<64>(in, wpack, out, N, H, W, cin, dil, cnt_h, cnt_w, stat_acc, bs, rev, fin, stream);
+    case 128: return launch<128>(in, wpack, out, N, H, W, cin, dil, cnt_h, cnt_w, stat_acc, bs, rev, fin, stream);
+    case 256: return launch<256>(in, wpack, out, N, H, W, cin, dil, cnt_h, cnt_w, stat_acc, bs, rev, fin, stream);
   }
   return MRFP_ERR_UNSUPPORTED;
 }
@@ -742,5 +774,5 @@ extern "C" int mrfp_debug_conv3x3_bf16(const void* in, const void* wpack, void* 
                                        int cout, int dil, const int* cnt_h, const int* cnt_w, double* stat_acc,
                                        void* stream) {
   return mrfp::conv3x3_tc_bf16((const __nv_bfloat16*)in, (const __nv_bfloat16*)wpack, (__nv_bfloat16*)out, N, H, W, cin,
-                               cout, dil, cnt_h, cnt_w, stat_acc, (cudaStream_t)stream, nullptr, false);
+                               cout, dil, cnt_h, cnt_w, stat_acc, (cudaStream_t)stream, nullptr, false, nullptr);
 }

@@ -671,13 +671,15 @@ int hrfp_forward(const mrfp_hrfp_plan* P, const float* xp, const float* const* W
                  const float* x_add, float* ocout, float* ocout_dec, const int* lut, char* saved, char* ws,
                  cudaStream_t s, const DeviceInfo& di, const NpStem* np) {
   double* acc = reinterpret_cast<double*>(ws + P->acc_fwd_off);
+  unsigned int* fin_counters = reinterpret_cast<unsigned int*>(acc + (size_t)kHrfpStages * 2 * kMaxC);   // [8], zeroed with acc
   if (np) MRFP_CUDA_TRY(cudaMemsetAsync(np->psum, 0, (size_t)P->N * P->cin * sizeof(double), s));
-  MRFP_CUDA_TRY(cudaMemsetAsync(acc, 0, (size_t)kHrfpStages * 2 * kMaxC * sizeof(double), s));
+  MRFP_CUDA_TRY(cudaMemsetAsync(acc, 0, (size_t)kHrfpStages * 2 * kMaxC * sizeof(double) + kHrfpStages * sizeof(unsigned int), s));
   const int last = ocout ? kHrfpStages : 4;
   const bool tc = P->mode == MRFP_MATH_BF16;
   // L2-friendly ordering: a kernel starts walking its tensor where its producer finished.  Forward: every conv walks
   // front to back, every BN/ReLU/resample pass back to front.  (MRFP_L2_ORDER=0 restores front-to-back everywhere.)
   static const bool l2_order = !(getenv("MRFP_L2_ORDER") && atoi(getenv("MRFP_L2_ORDER")) == 0);
+  static const bool conv_mode_tap = !(getenv("MRFP_CONV_MODE") && atoi(getenv("MRFP_CONV_MODE")) == 1);   // the halo kernel has no finaliser
   {
     PackJobs jobs = {};
     for (int k = 0; k < last; ++k) {
@@ -709,10 +711,16 @@ int hrfp_forward(const mrfp_hrfp_plan* P, const float* xp, const float* const* W
     T* Y = reinterpret_cast<T*>(saved + st.y_off);
     double* a = acc + (size_t)k * 2 * kMaxC;
     if (tc) {
+      ConvBnFinalize fin = {};
+      fin.gamma = gamma[k]; fin.beta = beta ? beta[k] : nullptr;
+      fin.running_mean = rmean ? rmean[k] : nullptr; fin.running_var = rvar ? rvar[k] : nullptr;
+      fin.stats = reinterpret_cast<float*>(saved + P->stats_off) + (size_t)k * 4 * kMaxC;
+      fin.counter = fin_counters + k;
+      fin.count = (double)P->N * st.oh * st.ow; fin.momentum = momentum; fin.eps = eps;
       int rc = conv3x3_tc_bf16(reinterpret_cast<const __nv_bfloat16*>(cur),
                                reinterpret_cast<const __nv_bfloat16*>(ws + st.wf_off),
                                reinterpret_cast<__nv_bfloat16*>(Y), P->N, st.ch, st.cw, st.cin, st.cout, st.dil,
-                               lut + st.cnt_h, lut + st.cnt_w, a, s);
+                               lut + st.cnt_h, lut + st.cnt_w, a, s, nullptr, false, conv_mode_tap ? &fin : nullptr);
       if (rc) return rc;
     } else {
       dim3 g((unsigned)(((long long)P->N * st.ch * st.cw + 31) / 32), (st.cout + 63) / 64);
@@ -725,8 +733,9 @@ int hrfp_forward(const mrfp_hrfp_plan* P, const float* xp, const float* const* W
     }
     float* stats = reinterpret_cast<float*>(saved + P->stats_off) + (size_t)k * 4 * kMaxC;
     const double count = (double)P->N * st.oh * st.ow;
-    launch_k(bn_finalize_kernel, dim3(1), dim3(256), 0, s, a, gamma[k], beta ? beta[k] : nullptr, rmean ? rmean[k] : nullptr,
-                                         rvar ? rvar[k] : nullptr, stats, st.cout, count, momentum, eps);
+    if (!(tc && conv_mode_tap))      // the tcgen05 conv finalises in its last CTA
+      launch_k(bn_finalize_kernel, dim3(1), dim3(256), 0, s, a, gamma[k], beta ? beta[k] : nullptr, rmean ? rmean[k] : nullptr,
+               rvar ? rvar[k] : nullptr, stats, st.cout, count, momentum, eps);
     if (k == 3 && ocout_dec) {
       const unsigned g = (unsigned)(((st.ow + kLayPx - 1) / kLayPx) * ((st.cout + 63) / 64)) * (unsigned)(P->N * st.oh);
       launch_k(nhwc_to_nchw_kernel<T>, dim3(g), dim3(256), 0, s, Y, ocout_dec, nullptr, lut + st.idx_h, lut + st.idx_w,
@@ -929,7 +938,7 @@ extern "C" int mrfp_hrfp_plan_create(mrfp_hrfp_plan_t** out, int N, int cin, int
   for (int k = 0; k < kHrfpStages; ++k) P->st[k].wb_off += y_bytes + stats_bytes;
   P->saved_bytes = y_bytes + stats_bytes + wb_bytes;
   // ws: [acc fwd][acc bwd][fwd weights][buffers: fwd A/B ping-pong | bwd g0, g1, dY]
-  const size_t acc_bytes = (size_t)kHrfpStages * 2 * kMaxC * sizeof(double);
+  const size_t acc_bytes = (size_t)kHrfpStages * 2 * kMaxC * sizeof(double) + 256;   // + finalisation counters
   P->acc_fwd_off = 0;
   P->acc_bwd_off = acc_bytes;
   for (int k = 0; k < kHrfpStages; ++k) P->st[k].wf_off += 2 * acc_bytes;

@@ -58,9 +58,22 @@ struct ConvBwdStats {
   int IH, IW;
   int H, W;                   // filled in by conv3x3_tc_bf16
 };
+//   finalize (forward use, with stat_acc): the LAST CTA to add its partial statistics turns them into the BN
+//   mean / invstd / scale / shift table and updates the running statistics — no separate finalisation launch.
+struct ConvBnFinalize {
+  const float* gamma;         // [cout]
+  const float* beta;          // [cout] or null
+  float* running_mean;        // [cout] or null
+  float* running_var;
+  float* stats;               // [4][kMaxC]: mean, invstd, scale, shift
+  unsigned int* counter;      // zero before the launch
+  double count;               // elements per channel of the resampled tensor
+  float momentum, eps;
+};
 int conv3x3_tc_bf16(const __nv_bfloat16* in, const __nv_bfloat16* wpack, __nv_bfloat16* out, int N, int H, int W,
                     int cin, int cout, int dil, const int* cnt_h, const int* cnt_w, double* stat_acc,
-                    cudaStream_t stream, const ConvBwdStats* bwd_stats = nullptr, bool reverse_tiles = false);
+                    cudaStream_t stream, const ConvBwdStats* bwd_stats = nullptr, bool reverse_tiles = false,
+                    const ConvBnFinalize* finalize = nullptr);
 bool conv3x3_tc_supported(int cin, int cout);
 
 // TMA-fed BN-backward reduction (bn_ring.cu); MRFP_ERR_UNSUPPORTED -> use the LDG kernel

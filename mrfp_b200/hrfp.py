@@ -228,8 +228,7 @@ def hrfp_chain(xp, convs, bns, h, w, x_add=None, want_out=True, want_dec=True, m
                          want_out, want_dec, holder, np_draws)
     if track:
         n_run = 8 if want_out else 4
-        for b in bns[:n_run]:
-            b.num_batches_tracked += 1
+        torch._foreach_add_([b.num_batches_tracked for b in bns[:n_run]], 1)     # one launch instead of eight
     outs = list(outs)
     out = outs.pop(0) if want_out else None
     dec = outs.pop(0) if want_dec else None
