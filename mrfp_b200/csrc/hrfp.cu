@@ -536,6 +536,59 @@ bn_bwd_apply_kernel(const T* __restrict__ dA, const T* __restrict__ y, T* __rest
   }
 }
 
+// Same pass for a stage whose resample is the identity (OCdeclayer1: conv and output resolution are both h/2 x w/2):
+// a flat stream, four pixels per thread in flight.
+template <typename T>
+__global__ void __launch_bounds__(256, 2)
+bn_bwd_apply_identity_kernel(const T* __restrict__ dA, const T* __restrict__ y, T* __restrict__ dY,
+                             const float* __restrict__ stats, const float* __restrict__ gamma,
+                             const double* __restrict__ acc, long long npix, int C, double count, int rev) {
+  pdl_sync();
+  const int cg = C >> 3, pstep = 256 / cg;
+  const int c = (threadIdx.x % cg) << 3, pl = threadIdx.x / cg;
+  float scale[8], shift[8], P[8], Q[8], R[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const double mean = stats[c + j], invstd = stats[kMaxC + c + j], gm = gamma[c + j];
+    scale[j] = stats[2 * kMaxC + c + j]; shift[j] = stats[3 * kMaxC + c + j];
+    const double S1 = acc[c + j], S2 = invstd * (acc[kMaxC + c + j] - mean * S1);
+    const double M1 = gm * S1 / count, M2 = gm * S2 / count;
+    const double r = invstd * invstd * M2;
+    P[j] = (float)(invstd * gm); R[j] = (float)r; Q[j] = (float)(invstd * M1 - mean * r);
+  }
+  typedef typename Elem<T>::Raw Raw;
+  constexpr int U = 4;
+  const long long chunk = (long long)U * pstep, nchunks = (npix + chunk - 1) / chunk;
+  for (long long it = blockIdx.x; it < nchunks; it += gridDim.x) {
+    const long long p0 = (rev ? nchunks - 1 - it : it) * chunk + pl;
+    Raw g[U] = {}, yv[U] = {};
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long long p = p0 + (long long)u * pstep;
+      if (p < npix) {
+        g[u] = Elem<T>::load_raw(dA + (size_t)p * C + c);
+        yv[u] = Elem<T>::load_raw(y + (size_t)p * C + c);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long long p = p0 + (long long)u * pstep;
+      if (p < npix) {
+        float gf[8], yf[8], o[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { gf[j] = 0.f; yf[j] = 0.f; }
+        Elem<T>::add_raw(g[u], gf); Elem<T>::add_raw(yv[u], yf);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float t = fmaf(scale[j], yf[j], shift[j]) > 0.f ? gf[j] : 0.f;
+          o[j] = P[j] * t - fmaf(R[j], yf[j], Q[j]);
+        }
+        Elem<T>::store8(dY + (size_t)p * C + c, o);
+      }
+    }
+  }
+}
+
 __global__ void add_f32_kernel(const float4* __restrict__ a, const float4* __restrict__ b, float4* __restrict__ o,
                                size_t n4, const float* a1, const float* b1, float* o1, size_t n) {
   pdl_sync();
@@ -818,9 +871,16 @@ int hrfp_backward(const mrfp_hrfp_plan* P, const float* g_ocout, const float* g_
     const int rev_apply = (l2_order && at_end) ? 1 : 0;
     if (l2_order) at_end = !at_end;
     static const bool regc = getenv("MRFP_APPLY_REGC") && atoi(getenv("MRFP_APPLY_REGC")) == 1;
-    launch_k(regc ? bn_bwd_apply_kernel<T, true> : bn_bwd_apply_kernel<T, false>, dim3(grid_a), dim3(256), 0, s, dA, Y, dY,
-             lut + st.start_h, lut + st.cnt_h, lut + st.start_w, lut + st.cnt_w, stats, gamma[k], a, P->N, st.cout, st.ch,
-             st.cw, st.oh, st.ow, count, rev_apply);
+    static const bool ident_k = !(getenv("MRFP_APPLY_IDENT") && atoi(getenv("MRFP_APPLY_IDENT")) == 0);
+    if (ident_k && st.oh == st.ch && st.ow == st.cw) {   // identity resample: flat stream
+      const long long npix = (long long)P->N * st.ch * st.cw;
+      launch_k(bn_bwd_apply_identity_kernel<T>, dim3(di.sm_count * 8), dim3(256), 0, s, dA, Y, dY, stats, gamma[k], a, npix,
+               st.cout, count, rev_apply);
+    } else {
+      launch_k(regc ? bn_bwd_apply_kernel<T, true> : bn_bwd_apply_kernel<T, false>, dim3(grid_a), dim3(256), 0, s, dA, Y, dY,
+               lut + st.start_h, lut + st.cnt_h, lut + st.start_w, lut + st.cnt_w, stats, gamma[k], a, P->N, st.cout, st.ch,
+               st.cw, st.oh, st.ow, count, rev_apply);
+    }
     // dgrad: conv of dY (cout channels) with the rotated / transposed kernel -> dA_prev (cin channels)
     if (tc) {
       // the dgrad epilogue also takes the BN-backward sums of stage k-1 (its output IS that stage's dA), unless an
@@ -919,6 +979,9 @@ extern "C" int mrfp_hrfp_plan_create(mrfp_hrfp_plan_t** out, int N, int cin, int
     st.start_w = (int)L.size(); L.resize(L.size() + cw, 0);
     for (int d = st.oh - 1; d >= 0; --d) { const int sidx = L[st.idx_h + d]; L[st.cnt_h + sidx]++; L[st.start_h + sidx] = d; }
     for (int d = st.ow - 1; d >= 0; --d) { const int sidx = L[st.idx_w + d]; L[st.cnt_w + sidx]++; L[st.start_w + sidx] = d; }
+    st.max_rep = 0;
+    for (int i = 0; i < ch; ++i) st.max_rep = L[st.cnt_h + i] > st.max_rep ? L[st.cnt_h + i] : st.max_rep;
+    for (int i = 0; i < cw; ++i) st.max_rep = L[st.cnt_w + i] > st.max_rep ? L[st.cnt_w + i] : st.max_rep;
     st.y_off = y_bytes;
     y_bytes += align_up((size_t)N * ch * cw * st.cout * P->esize, 256);
     st.wf_off = wf_bytes; wf_bytes += align_up((size_t)9 * st.cin * st.cout * P->esize, 256);

@@ -15,6 +15,7 @@ struct HrfpStage {
   int cin, cout, dil;
   int ch, cw;      // conv resolution (input and output of the 3x3 conv)
   int oh, ow;      // resolution after the nearest resample
+  int max_rep;     // largest replication count of a source row / column
   float scale_h, scale_w;   // ATen's nearest rule: src = min(floorf(dst * scale), in - 1)  (== the idx tables)
   // offsets (in ints) into the LUT blob
   int idx_h, idx_w;       // dst -> src index, [oh], [ow]
