@@ -174,6 +174,8 @@ def train_bench(world, rank, dev, steps=8, warmup=3, global_batch=16, reference_
     import torch.distributed as dist
     from mrfp_b200.model import MRFPPlus
     from mrfp_b200 import dist as D
+    # host trunk: let cuDNN pick its fastest algorithms for the fixed shapes (applies equally to both MRFP-op variants)
+    torch.backends.cudnn.benchmark = os.environ.get("MRFP_BENCH_CUDNN_AUTOTUNE", "1") != "0"
     lo, hi = D.shard_bounds(global_batch, world, rank)
     nb = hi - lo
     D.seed_rank_streams(3, rank)
@@ -212,7 +214,7 @@ def train_bench(world, rank, dev, steps=8, warmup=3, global_batch=16, reference_
     out = {"metric": "deeplabv3plus_r50_mrfp_plus_train_throughput", "mrfp_ops": "reference eager ATen/cuDNN" if reference_ops else "libmrfp_b200", "value": global_batch * steps / (ms * 1e-3), "unit": "img/s",
            "global_batch": global_batch, "per_gpu_batch": nb, "steps": steps, "warmup": warmup, "ms_per_step": ms / steps,
            "parallelism": f"ddp{world}", "loss_finite": bool(torch.isfinite(loss).item()),
-           "precision": "fp32 host model (cuDNN TF32 default, as the reference on this torch), bf16 tcgen05 HRFP, fp32 NP+",
+           "precision": "fp32 host model (cuDNN TF32 default, as the reference on this torch; cudnn.benchmark=%s), bf16 tcgen05 HRFP, fp32 NP+" % torch.backends.cudnn.benchmark,
            "gates": "natural Bernoulli(0.5) x3 per step (python random, seed 100+rank)", "data": "synthetic U[0,255) images, 19 classes, 5% ignore"}
     del model, opt, img, lab
     torch.cuda.empty_cache()
