@@ -415,8 +415,8 @@ def run_ours(args):
     big = np_rows["npplus_256ch"]
     roof_np = {"kernel": "npplus_ring_kernel<fwd> on (8,256,192,192)", "bound": "hbm", "achieved": big["fwd_gbs"], "peak": hbm_peak,
                "unit": "GB/s", "frac": big["fwd_gbs"] / hbm_peak,
-               "traffic": 498005248 + 245286656,     # dram__bytes_read.sum + dram__bytes_write.sum per launch
-               "traffic_source": "profiles/r2_np256_raw.csv (ncu --set full, one launch of the bwd twin of this kernel); "
+               "traffic": 498743808 + 247726848,     # dram__bytes_read.sum + dram__bytes_write.sum per launch
+               "traffic_source": "profiles/r3_np256_raw.csv (ncu --set full, one launch of this kernel); "
                                  "algorithmic bytes per launch = 603979776",
                "peak_source": peak_src,
                "all_four_np_kernels_gbs": np_bytes / np_time / 1e9, "per_call": np_rows}
@@ -440,8 +440,8 @@ def run_ours(args):
     top = max(conv_rows, key=lambda r: r["us"])
     roofline = {"kernel": f"conv3x3_tc_kernel<{top['cout']}> stage {top['stage']} ({top['cin']}->{top['cout']} @{top['hw'][0]}x{top['hw'][1]})",
                 "bound": "tensor", "achieved": top["tflops"], "peak": tf_peak, "unit": "TFLOP/s", "frac": top["tflops"] / tf_peak,
-                "traffic": (604729856 + 274007040) if top["stage"] == 4 else None,   # dram read + write bytes per launch
-                "traffic_source": "profiles/r2_conv_d1_raw.csv (ncu --set full, stage 4 forward): A 604 MB read once, Y 302 MB written",
+                "traffic": (604724480 + 272979456) if top["stage"] == 4 else None,   # dram read + write bytes per launch
+                "traffic_source": "profiles/r3_conv_d1_raw.csv (ncu --set full, stage 4 forward): A 604 MB read once, Y 302 MB written",
                 "peak_source": peak_src, "peak_sustained": tf_sustained,
                 "all_conv_fwd_tflops": conv_flop / conv_time / 1e9, "per_stage": conv_rows}
 
