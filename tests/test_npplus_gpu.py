@@ -107,6 +107,39 @@ def test_full_size_properties():
     assert errg <= 1e-4 * xr.grad.abs().max().item()
 
 
+@pytest.mark.parametrize("shape", [(8, 64, 96, 96), (4, 24, 33, 31), (8, 256, 192, 192)])
+def test_workspace_needs_no_initialisation_and_results_are_deterministic(shape):
+    """The workspace may hold anything (the queues are opened per launch with a nonce): zeros, 0xFF and random bytes
+    give bit-identical outputs, forward and backward, launch after launch."""
+    from mrfp_b200 import _lib
+    lib = _lib.load()
+    n, c, h, w = shape
+    torch.manual_seed(5)
+    x = torch.relu(torch.randn(n, c, h, w, device="cuda"))
+    g = torch.randn(n, c, h, w, device="cuda")
+    alpha = 1 + 0.75 * torch.randn(n, c, device="cuda")
+    eps = 0.75 * torch.randn(n, c, device="cuda")
+    wsb = lib.mrfp_npplus_ws_bytes(n, c, h * w)
+    st = torch.cuda.current_stream().cuda_stream
+    outs = []
+    for fill in ("zero", "ff", "rand", "rand"):
+        ws = torch.zeros(wsb, dtype=torch.uint8, device="cuda")
+        if fill == "ff":
+            ws.fill_(255)
+        elif fill == "rand":
+            ws.random_(0, 256)
+        out = torch.empty_like(x); gin = torch.empty_like(x)
+        mean = torch.empty(n, c, device="cuda"); beta = torch.empty(n, c, device="cuda")
+        assert lib.mrfp_npplus_fwd_f32(x.data_ptr(), alpha.data_ptr(), eps.data_ptr(), out.data_ptr(), mean.data_ptr(),
+                                       beta.data_ptr(), ws.data_ptr(), wsb, n, c, h * w, st) == 0
+        assert lib.mrfp_npplus_bwd_f32(g.data_ptr(), alpha.data_ptr(), eps.data_ptr(), mean.data_ptr(), gin.data_ptr(),
+                                       ws.data_ptr(), wsb, n, c, h * w, st) == 0
+        torch.cuda.synchronize()
+        outs.append((out, gin, mean))
+    for o, gi, m in outs[1:]:
+        assert torch.equal(o, outs[0][0]) and torch.equal(gi, outs[0][1]) and torch.equal(m, outs[0][2])
+
+
 def test_rng_stream_matches_reference_draw_order():
     """Same generator state -> same alpha/eps as the reference's two torch.normal calls (deepv3.py:274-275)."""
     from mrfp_b200.npplus import draw_np_plus_factors
