@@ -421,6 +421,32 @@ def run_ours(args):
                "peak_source": peak_src,
                "all_four_np_kernels_gbs": np_bytes / np_time / 1e9, "per_call": np_rows}
 
+    # NP+ with its statistics taken by the producer: layer1's last ReLU leaves the plane sums, NP+ forward
+    # is one streaming pass.  Timed: the ReLU-with-sums kernel next to ATen's relu (same 1R+1W), and the pre-summed NP+.
+    try:
+        pre = torch.randn(n, 256, XH, XW, device=dev)
+        y_r = torch.empty_like(pre)
+        psum = torch.empty(n, 256, device=dev, dtype=torch.float64)
+        al2, ep2 = draws[1][0].reshape(n, 256).contiguous(), draws[1][1].reshape(n, 256).contiguous()
+        out_p = torch.empty_like(pre); mean_p = torch.empty(n, 256, device=dev)
+        wsb_p = lib.mrfp_npplus_presummed_ws_bytes(n, 256)
+        ws_p = torch.empty(wsb_p, dtype=torch.uint8, device=dev)
+        t_relu = time_launch(lambda: _lib.check(lib.mrfp_relu_psum_f32(pre.data_ptr(), y_r.data_ptr(), psum.data_ptr(), n * 256, XH * XW, st), "relu_psum"))
+        t_aten = time_launch(lambda: torch.relu(pre))
+        t_pre = time_launch(lambda: _lib.check(lib.mrfp_npplus_fwd_presummed_f32(y_r.data_ptr(), psum.data_ptr(), al2.data_ptr(), ep2.data_ptr(), out_p.data_ptr(),
+                                                                                 mean_p.data_ptr(), None, ws_p.data_ptr(), wsb_p, n, 256, XH * XW, st), "np presummed"))
+        b_alg = 2 * pre.numel() * 4
+        roof_np["producer_fused"] = {
+            "what": "layer1's last ReLU also takes the plane sums (mrfp_relu_psum_f32), NP+ forward = coefficient block + one streaming pass "
+                    "(mrfp_npplus_fwd_presummed_f32); the path MRFPPlus.forward uses for call 2; the backward stays on the ring kernel",
+            "relu_psum_us": t_relu * 1e3, "aten_relu_us": t_aten * 1e3, "npplus_fwd_presummed_us": t_pre * 1e3,
+            "npplus_fwd_presummed_gbs": b_alg / t_pre / 1e6, "frac": b_alg / t_pre / 1e6 / hbm_peak,
+            "fwd_plus_bwd_gbs": 2 * b_alg / (t_pre + big["bwd_us"] * 1e-3) / 1e6,
+            "fwd_plus_bwd_frac": 2 * b_alg / (t_pre + big["bwd_us"] * 1e-3) / 1e6 / hbm_peak}
+        del pre, y_r, out_p
+    except Exception as e_:          # noqa: BLE001
+        roof_np["producer_fused"] = {"error": repr(e_)[:200]}
+
     # tcgen05 conv kernels of the chain, forward shapes (debug hook = the same kernel the chain launches)
     import ctypes
     fn = lib.mrfp_debug_conv3x3_bf16

@@ -71,6 +71,17 @@ int mrfp_npplus_fwd_f32(const float* x,       /* (N,C,HW) */
 int mrfp_npplus_bwd_f32(const float* gout, const float* alpha, const float* eps, const float* mean,
                         float* gin, void* ws, size_t ws_bytes, int N, int C, int HW, void* stream);
 
+/* NP+ with its statistics taken by the producer of the feature.  deepv3.py:332-335 applies NP+ to the
+ * output of layer1, which ends in a ReLU (Resnet.py:218-225): mrfp_relu_psum_f32 is that ReLU (y may alias x) and also
+ * leaves psum[n*C+c] = sum_hw y (NC doubles, zeroed by the call); mrfp_npplus_fwd_presummed_f32 is then a single
+ * streaming pass (1R+1W) producing the same out / mean / beta as mrfp_npplus_fwd_f32.  ws: >=
+ * mrfp_npplus_presummed_ws_bytes(N,C) bytes, 16-byte aligned.  Backward: mrfp_npplus_bwd_f32. */
+int mrfp_relu_psum_f32(const float* x, float* y, double* psum, int NC, int HW, void* stream);
+size_t mrfp_npplus_presummed_ws_bytes(int N, int C);
+int mrfp_npplus_fwd_presummed_f32(const float* x, const double* psum, const float* alpha, const float* eps,
+                                  float* out, float* mean, float* beta, void* ws, size_t ws_bytes,
+                                  int N, int C, int HW, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * HRFP — replaces the chain deepv3.py:320-327 (8 x conv3x3 -> F.interpolate(nearest) -> BatchNorm2d
  * (train) -> ReLU on the layer types of deepv3.py:221-237), the adds deepv3.py:329-330 and

@@ -23,6 +23,11 @@ SIGNATURES = {
     "mrfp_npplus_bwd_f32": (ctypes.c_int, [c_float_p, c_float_p, c_float_p, c_float_p, c_float_p,
                                            ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int, ctypes.c_int,
                                            ctypes.c_int, ctypes.c_void_p]),
+    "mrfp_relu_psum_f32": (ctypes.c_int, [c_float_p, c_float_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]),
+    "mrfp_npplus_presummed_ws_bytes": (ctypes.c_size_t, [ctypes.c_int, ctypes.c_int]),
+    "mrfp_npplus_fwd_presummed_f32": (ctypes.c_int, [c_float_p, ctypes.c_void_p, c_float_p, c_float_p, c_float_p, c_float_p,
+                                                     c_float_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int, ctypes.c_int,
+                                                     ctypes.c_int, ctypes.c_void_p]),
     "mrfp_hrfp_plan_create": (ctypes.c_int, [c_void_pp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                              ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_int), ctypes.c_int]),
     "mrfp_hrfp_plan_destroy": (None, [ctypes.c_void_p]),

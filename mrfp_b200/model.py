@@ -65,6 +65,8 @@ class MRFPMixin:
     on other trunks: SURVEY.md §8f-2)."""
     # fold NP+ call 1 into the HRFP chain when both gates are on (same result, two passes fewer); MRFP_FUSE_STEM_NP=0: off
     fuse_stem_np = os.environ.get("MRFP_FUSE_STEM_NP", "1") != "0"
+    # take the NP+ statistics of call 2 in layer1's last ReLU (same result, NP+ forward becomes 1R+1W); MRFP_FUSE_LAYER1_NP=0: off
+    fuse_layer1_np = os.environ.get("MRFP_FUSE_LAYER1_NP", "1") != "0"
 
     def _build_hrfp(self, in_ch=64, widths=(64, 64, 128, 256)):
         chans = [in_ch, widths[0], widths[1], widths[2], widths[3], widths[2], widths[1], widths[0], in_ch]
@@ -135,6 +137,8 @@ class Bottleneck(nn.Module):
         if instance_norm:
             self.instance_norm_layer = nn.InstanceNorm2d(planes * 4, affine=True)
         self.has_in = instance_norm
+        self.emit_plane_sums = False       # set on the last block of layer1 by MRFPPlus
+        self.plane_sums = None
         self.relu = nn.ReLU(inplace=True)
 
     def forward(self, x):
@@ -144,6 +148,11 @@ class Bottleneck(nn.Module):
         out = out + (x if self.downsample is None else self.downsample(x))
         if self.has_in:
             out = self.instance_norm_layer(out)
+        if self.emit_plane_sums and out.is_cuda and self.training:
+            # the block's ReLU also leaves the plane sums of its output for the NP+ call that follows
+            out, self.plane_sums = _npplus.relu_with_plane_sums(out)
+            return out
+        self.plane_sums = None
         return self.relu(out)
 
 
@@ -228,9 +237,16 @@ class MRFPPlus(nn.Module, MRFPMixin):
             self.reinit_hrfp()                                              # deepv3.py:290-306
         xp = self.layer0(x)                                                 # deepv3.py:309-316
         x, ocout_dec = self.mrfp_stem(xp, h, w, training, p, p2, p3)        # deepv3.py:317-330
+        last = self.layer1[-1]
+        last.emit_plane_sums = bool(training and p2 < 0.5 and self.fuse_layer1_np)
         x = self.layer1(x)                                                  # deepv3.py:332
-        if training and p2 < 0.5:
-            x = self.Normalization_Perturbation_Plus(x)                     # deepv3.py:334-335
+        if training and p2 < 0.5:                                           # deepv3.py:334-335
+            if last.plane_sums is not None:      # statistics came with layer1's last ReLU: NP+ is one streaming pass
+                alpha, eps = _npplus.draw_np_plus_factors(x)
+                x = _npplus.np_plus_presummed(x, last.plane_sums, alpha, eps)
+                last.plane_sums = None
+            else:
+                x = self.Normalization_Perturbation_Plus(x)
         low_level = x
         x = self.layer4(self.layer3(self.layer2(x)))
         dec0_up = self.bot_aspp(self.aspp(x))

@@ -140,6 +140,38 @@ def test_workspace_needs_no_initialisation_and_results_are_deterministic(shape):
         assert torch.equal(o, outs[0][0]) and torch.equal(gi, outs[0][1]) and torch.equal(m, outs[0][2])
 
 
+@pytest.mark.parametrize("shape", [(2, 256, 192, 192), (3, 24, 33, 31), (4, 116, 96, 96), (8, 64, 48, 48)])
+def test_producer_fused_path_equals_the_ring_kernel(shape):
+    """relu_with_plane_sums + np_plus_presummed (NP+ statistics taken by the producer's ReLU) vs
+    torch.relu + the standalone NP+ kernel: same output and the same gradient into the pre-ReLU tensor."""
+    from mrfp_b200.npplus import np_plus_with_draws, np_plus_presummed, relu_with_plane_sums
+    n, c, h, w = shape
+    rng = np.random.default_rng(41)
+    pre = torch.from_numpy(rng.standard_normal(shape).astype(np.float32) + 0.3).cuda()
+    a, e = make_draws(42, n, c)
+    a, e = torch.from_numpy(a).cuda(), torch.from_numpy(e).cuda()
+    g = torch.from_numpy(rng.standard_normal(shape).astype(np.float32)).cuda()
+
+    x1 = pre.clone().requires_grad_(True)
+    y1, psum = relu_with_plane_sums(x1)
+    o1 = np_plus_presummed(y1, psum, a, e)
+    o1.backward(g)
+    x2 = pre.clone().requires_grad_(True)
+    y2 = torch.relu(x2)
+    o2 = np_plus_with_draws(y2, a, e)
+    o2.backward(g)
+
+    assert torch.equal(y1, y2)
+    ref_sum = y2.double().sum((2, 3))
+    assert torch.allclose(psum, ref_sum, rtol=1e-6, atol=1e-6 * ref_sum.abs().max().item())
+    _close(o1.detach().cpu().numpy(), o2.detach().cpu().numpy(), 2e-6)
+    _close(x1.grad.cpu().numpy(), x2.grad.cpu().numpy(), 2e-6)
+    # and against the oracle
+    ref, _, _ = O.np_plus_forward(y2.detach().cpu().numpy().astype(np.float64), a.cpu().numpy().astype(np.float64),
+                                  e.cpu().numpy().astype(np.float64))
+    _close(o1.detach().cpu().numpy(), ref, FWD_TOL)
+
+
 def test_rng_stream_matches_reference_draw_order():
     """Same generator state -> same alpha/eps as the reference's two torch.normal calls (deepv3.py:274-275)."""
     from mrfp_b200.npplus import draw_np_plus_factors
