@@ -671,7 +671,8 @@ void plan_launch(int N, int C, int HW, bool ring, const DeviceInfo& di, NpLaunch
   const size_t slack = 1024;                                     // static smem + alignment
   if (ring) {
     long long grab = upc / 8;
-    g.grab = (int)(grab < 1 ? 1 : (grab > 4 ? 4 : grab));
+    static const long long grab_a = getenv("MRFP_NPPLUS_GRAB_A") ? atoll(getenv("MRFP_NPPLUS_GRAB_A")) : 2;   // measured: 2 beats 1 (queue-bound) and 4, 8
+    g.grab = (int)(grab < 1 ? 1 : (grab > grab_a ? grab_a : grab));
     static const int grab_b = getenv("MRFP_NPPLUS_GRAB_B") ? atoi(getenv("MRFP_NPPLUS_GRAB_B")) : 2;
     g.grab_b = g.grab < grab_b ? g.grab : grab_b;
     // per slot: the unit, two mbarriers, 16 warp partials, (a, b), unit index, fold counter

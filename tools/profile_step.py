@@ -7,7 +7,7 @@ from mrfp_b200 import hrfp as H, npplus as NP
 from mrfp_b200.model import init_hrfp_module
 dev = "cuda"
 torch.manual_seed(1)
-n = 8
+n = int(os.environ.get("MRFP_PROFILE_N", "8"))
 chans, dils = [64, 64, 64, 128, 256, 128, 64, 64, 64], [1, 1, 2, 2, 1, 1, 2, 2]
 convs = [torch.nn.Conv2d(chans[k], chans[k + 1], 3, padding=dils[k], dilation=dils[k]).to(dev).requires_grad_(False) for k in range(8)]
 bns = [torch.nn.BatchNorm2d(chans[k + 1]).to(dev).requires_grad_(False) for k in range(8)]
