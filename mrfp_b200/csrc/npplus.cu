@@ -8,8 +8,9 @@
 //            (cp.async.bulk + mbarrier complete_tx); 16 consumer warps reduce each unit from shared memory
 //            (128-bit LDS, fp32 lane partials, double warp-shuffle tree); the last warp to finish a unit folds the
 //            16 warp partials in fixed order.  Units come from a grid-wide atomic queue, framed by two static
-//            sets per CTA that STAY ON CHIP: a head of up to 8 units parked in tensor memory (TMEM is otherwise
-//            idle: no MMA here) and a tail of up to 7 units left in the ring  (15 x 32 KiB x 148 SMs = 71 MB);
+//            sets per CTA that STAY ON CHIP: a head of 2 units kept in the consumers' registers plus up to 8 units
+//            parked in tensor memory (TMEM is otherwise idle: no MMA here) and a tail of up to 7 units left in the ring
+//            (17 x 32 KiB x 148 SMs = 80 MB);
 //   barrier  grid-wide (cooperative groups);
 //   stats    grid-parallel per-channel statistics, second barrier, then every CTA reduces max_c d / arg-max /
 //            the backward's cross-channel sum and derives (a, b) for its resident units;
@@ -36,6 +37,7 @@ constexpr int kBatch = 4;                       // vectors per consumer thread p
 constexpr int kUnitVecs = kConsumers * kBatch;  // 2048 float4 = 32 KiB
 constexpr int kMaxSlots = 7;
 constexpr int kTmemUnits = 8;                    // 512 TMEM columns / 64 columns per parked unit
+constexpr int kRegUnits = 2;                     // head units a consumer thread keeps in registers (16 floats each)
 
 struct NpGeom {
   int N, C, HW;
@@ -53,6 +55,7 @@ struct NpGeom {
   int grab_b;    // ring path: units taken from the phase-B queue per atomic (small: the tail of phase B ends the kernel)
   int u_dyn;     // ring path: units [0, u_dyn) are handed out dynamically; the rest is the static resident tail
   int tmem_units;  // ring path: head units per CTA parked in tensor memory
+  int reg_units;   // ring path: head units per CTA parked in the consumers' registers (0 or kRegUnits), before the TMEM ones
   int mid_units;   // ring path: units before the keep_units band loaded with L2 evict_normal
 };
 
@@ -298,7 +301,7 @@ npplus_ring_kernel(const float* __restrict__ x, const float* __restrict__ alpha,
   extern __shared__ __align__(128) unsigned char smem_raw[];
   // resident units of this CTA: a static HEAD of T units parked in TMEM at the very start (their imbalance is absorbed
   // by the dynamic queue that follows) and a static TAIL of S units that stays in the ring
-  const int S = g.slots, T = g.tmem_units;
+  const int S = g.slots, RG = g.reg_units, T = g.reg_units + g.tmem_units;   // T: all head units (registers first, then TMEM)
   auto stamp = [&](int i) {
     if (trace && threadIdx.x == 0) {
       unsigned long long t;
@@ -315,7 +318,8 @@ npplus_ring_kernel(const float* __restrict__ x, const float* __restrict__ alpha,
   volatile int* slot_unit = reinterpret_cast<volatile int*>(slot_coef + S);             // [S]
   int* slot_cnt = const_cast<int*>(slot_unit) + S;                                      // [S] warps that delivered their partial
   __shared__ NpShared sh;
-  __shared__ float2 head_coef[kTmemUnits];
+  __shared__ float2 head_coef[kTmemUnits + kRegUnits];
+  float4 preg0[kBatch] = {}, preg1[kBatch] = {};             // register-parked head units (consumer threads); a third one spills
   __shared__ uint32_t tmem_base_s;
 
   NpCtrl* ctrl = reinterpret_cast<NpCtrl*>(ws);
@@ -343,7 +347,7 @@ npplus_ring_kernel(const float* __restrict__ x, const float* __restrict__ alpha,
       *reinterpret_cast<volatile unsigned long long*>(&ctrl->nonce) = nonce;
     }
   }
-  if (is_producer && T > 0) {                            // the whole TMEM (one CTA per SM, no MMA in this kernel)
+  if (is_producer && T > RG) {                           // the whole TMEM (one CTA per SM, no MMA in this kernel)
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(&tmem_base_s)) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -351,7 +355,7 @@ npplus_ring_kernel(const float* __restrict__ x, const float* __restrict__ alpha,
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   // this thread's window into TMEM: its own lane, 16 columns per parked unit
-  const uint32_t tmem_mine = T > 0 ? tmem_base_s + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)((warp >> 2) * 16) : 0u;
+  const uint32_t tmem_mine = T > RG ? tmem_base_s + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)((warp >> 2) * 16) : 0u;
 
   // ring position of the next fill; producer and consumers count the same fills, so they agree after phase A
   int s = 0, k = 0;
@@ -414,7 +418,14 @@ npplus_ring_kernel(const float* __restrict__ x, const float* __restrict__ alpha,
         v[b] = i < len ? src[i] : make_float4(0.f, 0.f, 0.f, 0.f);
         acc += (v[b].x + v[b].y) + (v[b].z + v[b].w);
       }
-      if (hj >= 0 && hj < T) tmem_park(tmem_mine + (uint32_t)(hj * 64), v);
+      if (hj >= 0 && hj < RG) {                          // registers first ...
+#pragma unroll
+        for (int b = 0; b < kBatch; ++b) {
+          if (hj == 0) preg0[b] = v[b]; else preg1[b] = v[b];
+        }
+      } else if (hj >= RG && hj < T) {                   // ... then tensor memory
+        tmem_park(tmem_mine + (uint32_t)((hj - RG) * 64), v);
+      }
       const double w = warp_sum((double)acc);
       const bool stays = u >= tail0;                     // the S tail fills stay in the ring until phase B
       if (lane == 0) {
@@ -531,9 +542,10 @@ npplus_ring_kernel(const float* __restrict__ x, const float* __restrict__ alpha,
     // the ring part of the tail first (frees the slots for the producer), then the TMEM part, then the queue
     for (int i = 0;; ++i) {
       if (i == S) {
-        for (int j = 0; j < T; ++j) {
+        if (RG > 0) { emit(head0, head_coef[0], preg0); emit(head0 + 1, head_coef[1], preg1); }
+        for (int j = RG; j < T; ++j) {
           float4 v[kBatch];
-          tmem_fetch(tmem_mine + (uint32_t)(j * 64), v);
+          tmem_fetch(tmem_mine + (uint32_t)((j - RG) * 64), v);
           emit(head0 + j, head_coef[j], v);
         }
       }
@@ -552,7 +564,7 @@ npplus_ring_kernel(const float* __restrict__ x, const float* __restrict__ alpha,
       else advance();
     }
   }
-  if (T > 0) {
+  if (T > RG) {
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     if (is_producer) {
@@ -667,7 +679,7 @@ void plan_launch(int N, int C, int HW, bool ring, const DeviceInfo& di, NpLaunch
   const long long min_upc = g.U / L->grid;                       // ... (min, >= 1)
   g.max_local_planes = (int)(upc / g.K + 2);
   g.scratch_off = g.U;
-  g.keep_units = 0; g.grab = 1; g.grab_b = 1; g.u_dyn = 0; g.tmem_units = 0; g.mid_units = 0;
+  g.keep_units = 0; g.grab = 1; g.grab_b = 1; g.u_dyn = 0; g.tmem_units = 0; g.reg_units = 0; g.mid_units = 0;
   const size_t slack = 1024;                                     // static smem + alignment
   if (ring) {
     long long grab = upc / 8;
@@ -687,7 +699,9 @@ void plan_launch(int N, int C, int HW, bool ring, const DeviceInfo& di, NpLaunch
     if (t > tmem_max) t = tmem_max;
     if (t > kTmemUnits) t = kTmemUnits;
     g.tmem_units = (int)(t < 0 ? 0 : t);
-    g.u_dyn = (int)(g.U - (long long)L->grid * (g.slots + g.tmem_units));
+    static const bool reg_park = !(getenv("MRFP_NPPLUS_REG_UNITS") && atoi(getenv("MRFP_NPPLUS_REG_UNITS")) == 0);
+    g.reg_units = (reg_park && min_upc - s - g.tmem_units >= kRegUnits) ? kRegUnits : 0;
+    g.u_dyn = (int)(g.U - (long long)L->grid * (g.slots + g.tmem_units + g.reg_units));
     L->smem = align_up((size_t)g.slots * per_slot, 16);
     // L2 share reserved for phase-B re-reads (MRFP_NPPLUS_KEEP_MB overrides; default 64 MiB)
     static const long long keep_mb = getenv("MRFP_NPPLUS_KEEP_MB") ? atoll(getenv("MRFP_NPPLUS_KEEP_MB")) : 64;
