@@ -64,9 +64,19 @@ struct NpGeom {
 // ------------------------------------------------------------------------------------------------------
 // unit partials are written by other CTAs earlier in this launch: read through L2 (ld.global.cg)
 __device__ __forceinline__ double plane_total(const double* ps, int plane, const NpGeom& g) {
+  const double* p = ps + (long long)plane * g.K;
+  if (g.K <= 8) {                       // all loads leave together (one L2 round trip), summed in index order
+    double v[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v[k] = k < g.K ? __ldcg(p + k) : 0.0;
+    double s = v[0];
+#pragma unroll
+    for (int k = 1; k < 8; ++k) s += v[k];
+    return s;
+  }
   double s = 0;
 #pragma unroll 4
-  for (int k = 0; k < g.K; ++k) s += __ldcg(ps + (long long)plane * g.K + k);
+  for (int k = 0; k < g.K; ++k) s += __ldcg(p + k);
   return s;
 }
 
@@ -457,9 +467,12 @@ npplus_ring_kernel(const float* __restrict__ x, const float* __restrict__ alpha,
 
   // ---------------- statistics ----------------
   np_stage1<BWD>(ps, mean_in, eps, g, pm, chan, blockIdx.x * (kWarps + 1) + warp, gridDim.x * (kWarps + 1));
+  stamp(5);
   __threadfence();
   cg::this_grid().sync();
+  stamp(6);
   np_global_reduce<BWD>(chan, g, sh, kConsumers + 32);
+  stamp(7);
   if (tid < S + T) {                                     // the resident units
     const int u = tid < T ? head0 + tid : tail0 + (tid - T), plane = u / g.K;
     const float2 ab = np_plane_coef<BWD>(plane, u - plane * g.K == 0, pm, chan, mean_in, alpha, eps, mean_out, beta_out, g, sh);

@@ -22,9 +22,9 @@ def run(n, c, h, w, reps=6):
                                      beta.data_ptr(), ws.data_ptr(), wsb, n, c, h * w, st)
         assert rc == 0
         torch.cuda.synchronize()
-    t = ws[base:].cpu().numpy().view(np.uint64).reshape(148, 8)[:, :5].astype(np.int64)
+    t = ws[base:].cpu().numpy().view(np.uint64).reshape(148, 8)[:, :8].astype(np.int64)
     t0 = t[:, 0].min()
-    names = ["start", "phaseA_end", "after_gridsync", "after_stats", "end"]
+    names = ["start", "phaseA_end", "after_gridsync", "after_stats", "end", "after_stage1", "after_sync2", "after_reduce"]
     print((n, c, h, w))
     for i, nm in enumerate(names):
         col = (t[:, i] - t0) / 1e3
