@@ -126,7 +126,8 @@ __global__ void __launch_bounds__(kThreads, 1)
 conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constant__ CUtensorMap tmap_w,
                   const __grid_constant__ CUtensorMap tmap_out, int CIN, int dil, int tiles_h, int tiles_w,
                   int num_tiles, const int* __restrict__ cnt_h, const int* __restrict__ cnt_w,
-                  double* __restrict__ stat_acc, const ConvBwdStats bs, int rev, const ConvBnFinalize fin) {
+                  double* __restrict__ stat_acc, const ConvBwdStats bs, int rev, const ConvBnFinalize fin,
+                  const __nv_bfloat16* __restrict__ add_src, int H, int W) {
   using C = Cfg<COUT>;
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -237,6 +238,24 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_cons
     const int cp = et & 31, pg = et >> 5;
     constexpr bool bwd = BWD;               // dgrad that also takes the previous stage's BN-backward sums (experimental)
     float a1x = 0.f, a1y = 0.f, a2x = 0.f, a2y = 0.f;
+    // add_src: this thread's 64 channels of its pixel, fetched ONE CHUNK AHEAD so the loads overlap the previous chunk
+    uint4 ad_nxt[8], ad_cur[8];
+    bool ad_nxt_ok = false, ad_ok = false;
+    auto add_fetch = [&](int t0_, int jj_) {
+      ad_nxt_ok = false;
+      if (add_src == nullptr || t0_ >= num_tiles) return;
+      const int t_ = rev ? num_tiles - 1 - t0_ : t0_;
+      const int tw_ = t_ % tiles_w, th_ = (t_ / tiles_w) % tiles_h, n_ = t_ / (tiles_w * tiles_h);
+      const int mt_ = jj_ / (COUT / 64), j_ = jj_ % (COUT / 64);
+      const int hh = th_ * kTileH * C::kMT + mt_ * kTileH + hl, ww = tw_ * kTileW + wl;
+      if (hh < H && ww < W) {
+        const uint4* ap = reinterpret_cast<const uint4*>(add_src + (((size_t)n_ * H + hh) * W + ww) * COUT + j_ * 64);
+#pragma unroll
+        for (int c = 0; c < 8; ++c) ad_nxt[c] = __ldg(ap + c);
+        ad_nxt_ok = true;
+      }
+    };
+    add_fetch(blockIdx.x, 0);
     int it = 0, obuf = 0;
     for (int t0 = blockIdx.x; t0 < num_tiles; t0 += gridDim.x, ++it) {
       const int t = rev ? num_tiles - 1 - t0 : t0;
@@ -248,6 +267,12 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_cons
 #pragma unroll 1
       for (int jj = 0; jj < C::kMT * (COUT / 64); ++jj) {
         const int mt = jj / (COUT / 64), j = jj % (COUT / 64);
+        if (add_src != nullptr) {                // rotate the prefetch: this chunk's data, then start the next chunk's loads
+#pragma unroll
+          for (int c = 0; c < 8; ++c) ad_cur[c] = ad_nxt[c];
+          ad_ok = ad_nxt_ok;
+          if (jj + 1 < C::kMT * (COUT / 64)) add_fetch(t0, jj + 1); else add_fetch(t0 + gridDim.x, 0);
+        }
         unsigned char* ob = sOut + obuf * kStageOutBytes;
         // the TMA store that last read this staging buffer must have drained
         if (leader) asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(C::kOutBufs - 1) : "memory");
@@ -271,7 +296,22 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_cons
 #pragma unroll
         for (int half = 0; half < 2; ++half) {
           uint32_t v[32];
+          const bool has_add = ad_ok;
+          uint4 ad[4];
+#pragma unroll
+          for (int c = 0; c < 4; ++c) ad[c] = ad_cur[half * 4 + c];
           tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((acc * C::kMT + mt) * COUT + j * 64 + half * 32), v);
+          if (has_add) {                         // summed in fp32, rounded once
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              const uint32_t w4[4] = {ad[c].x, ad[c].y, ad[c].z, ad[c].w};
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                v[c * 8 + 2 * i] = __float_as_uint(__uint_as_float(v[c * 8 + 2 * i]) + __uint_as_float(w4[i] << 16));
+                v[c * 8 + 2 * i + 1] = __float_as_uint(__uint_as_float(v[c * 8 + 2 * i + 1]) + __uint_as_float(w4[i] & 0xffff0000u));
+              }
+            }
+          }
 #pragma unroll
           for (int c = 0; c < 4; ++c) {          // four 16-byte chunks (8 channels each) per half
             uint32_t p[4];
@@ -645,7 +685,7 @@ int make_map(CUtensorMap* m, const void* base, int rank, const cuuint64_t* dims,
 template <int COUT>
 int launch(const __nv_bfloat16* in, const __nv_bfloat16* wpack, __nv_bfloat16* out, int N, int H, int W, int cin,
            int dil, const int* cnt_h, const int* cnt_w, double* stat_acc, const ConvBwdStats& bs, int rev,
-           const ConvBnFinalize& fin, cudaStream_t stream) {
+           const ConvBnFinalize& fin, const __nv_bfloat16* add_src, cudaStream_t stream) {
   CUtensorMap m_in, m_w, m_out;
   {
     const cuuint64_t dims[4] = {(cuuint64_t)cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
@@ -678,7 +718,7 @@ int launch(const __nv_bfloat16* in, const __nv_bfloat16* wpack, __nv_bfloat16* o
   auto kern = bs.y ? conv3x3_tc_kernel<COUT, true> : conv3x3_tc_kernel<COUT, false>;
   MRFP_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<COUT>::kSmemBytes));
   launch_k(kern, dim3(grid), dim3(kThreads), Cfg<COUT>::kSmemBytes, stream, m_in, m_w, m_out, cin, dil, tiles_h, tiles_w, num_tiles, cnt_h,
-                                                           cnt_w, stat_acc, bs, rev, fin);
+                                                           cnt_w, stat_acc, bs, rev, fin, add_src, H, W);
   MRFP_CUDA_TRY(cudaGetLastError());
   return MRFP_OK;
 }
@@ -734,7 +774,7 @@ bool conv3x3_tc_supported(int cin, int cout) {
 int conv3x3_tc_bf16(const __nv_bfloat16* in, const __nv_bfloat16* wpack, __nv_bfloat16* out, int N, int H, int W,
                     int cin, int cout, int dil, const int* cnt_h, const int* cnt_w, double* stat_acc,
                     cudaStream_t stream, const ConvBwdStats* bwd_stats, bool reverse_tiles,
-                    const ConvBnFinalize* finalize) {
+                    const ConvBnFinalize* finalize, const __nv_bfloat16* add_src) {
   ConvBwdStats bs = {};
   ConvBnFinalize fin = {};
   if (finalize) {
@@ -752,7 +792,7 @@ int conv3x3_tc_bf16(const __nv_bfloat16* in, const __nv_bfloat16* wpack, __nv_bf
   if (((uintptr_t)in | (uintptr_t)wpack | (uintptr_t)out) & 15) return MRFP_ERR_WORKSPACE;
   static const int mode = getenv("MRFP_CONV_MODE") ? atoi(getenv("MRFP_CONV_MODE")) : 0;   // 0 = one box per tap, 1 = halo tile
   static const int bo_mode = getenv("MRFP_CONV_BO") ? atoi(getenv("MRFP_CONV_BO")) : 0;   // measured: views are swizzled by absolute address, phase field stays 0
-  if (mode == 1 && dil <= 2 && !bwd_stats && !finalize) {
+  if (mode == 1 && dil <= 2 && !bwd_stats && !finalize && !add_src) {
     switch (cout) {
       case 64: return launch_halo<64>(in, wpack, out, N, H, W, cin, dil, cnt_h, cnt_w, stat_acc, bo_mode, stream);
       case 128: return launch_halo<128>(in, wpack, out, N, H, W, cin, dil, cnt_h, cnt_w, stat_acc, bo_mode, stream);
@@ -760,9 +800,9 @@ int conv3x3_tc_bf16(const __nv_bfloat16* in, const __nv_bfloat16* wpack, __nv_bf
     }
   }
   switch (cout) {
-    case 64: return launch<64>(in, wpack, out, N, H, W, cin, dil, cnt_h, cnt_w, stat_acc, bs, rev, fin, stream);
-    case 128: return launch<128>(in, wpack, out, N, H, W, cin, dil, cnt_h, cnt_w, stat_acc, bs, rev, fin, stream);
-    case 256: return launch<256>(in, wpack, out, N, H, W, cin, dil, cnt_h, cnt_w, stat_acc, bs, rev, fin, stream);
+    case 64: return launch<64>(in, wpack, out, N, H, W, cin, dil, cnt_h, cnt_w, stat_acc, bs, rev, fin, add_src, stream);
+    case 128: return launch<128>(in, wpack, out, N, H, W, cin, dil, cnt_h, cnt_w, stat_acc, bs, rev, fin, add_src, stream);
+    case 256: return launch<256>(in, wpack, out, N, H, W, cin, dil, cnt_h, cnt_w, stat_acc, bs, rev, fin, add_src, stream);
   }
   return MRFP_ERR_UNSUPPORTED;
 }
@@ -774,5 +814,5 @@ extern "C" int mrfp_debug_conv3x3_bf16(const void* in, const void* wpack, void* 
                                        int cout, int dil, const int* cnt_h, const int* cnt_w, double* stat_acc,
                                        void* stream) {
   return mrfp::conv3x3_tc_bf16((const __nv_bfloat16*)in, (const __nv_bfloat16*)wpack, (__nv_bfloat16*)out, N, H, W, cin,
-                               cout, dil, cnt_h, cnt_w, stat_acc, (cudaStream_t)stream, nullptr, false, nullptr);
+                               cout, dil, cnt_h, cnt_w, stat_acc, (cudaStream_t)stream, nullptr, false, nullptr, nullptr);
 }

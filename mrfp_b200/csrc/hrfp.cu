@@ -831,10 +831,13 @@ int hrfp_backward(const mrfp_hrfp_plan* P, const float* g_ocout, const float* g_
   static const bool l2_order = !(getenv("MRFP_L2_ORDER") && atoi(getenv("MRFP_L2_ORDER")) == 0);
   bool at_end = true;     // where the last kernel that touched dA finished (the layout kernels walk front to back)
   static const bool fuse_reduce = getenv("MRFP_FUSE_REDUCE") && atoi(getenv("MRFP_FUSE_REDUCE")) == 1;
+  static const bool join_dec = !(getenv("MRFP_JOIN_DEC") && atoi(getenv("MRFP_JOIN_DEC")) == 0);
+  bool dec_joined = false;
   bool reduced = false;   // the BN-backward sums of the stage about to be processed were taken by the previous dgrad
   for (int k = kHrfpStages - 1; k >= 0; --k) {
     const HrfpStage& st = P->st[k];
     const float* gin = (k == kHrfpStages - 1) ? g_ocout : (k == 3 ? g_ocout_dec : nullptr);
+    if (k == 3 && dec_joined) gin = nullptr;               // already added by the dgrad of stage 4
     if (gin) {
       const int HW = st.oh * st.ow;
       dim3 g((HW + kLayPx - 1) / kLayPx, (st.cout + 63) / 64, P->N);
@@ -895,11 +898,24 @@ int hrfp_backward(const mrfp_hrfp_plan* P, const float* g_ocout, const float* g_
         bs.scale = pstats + 2 * kMaxC; bs.shift = pstats + 3 * kMaxC;
         bs.IH = pv.ch; bs.IW = pv.cw;
       }
+      // stage 4's dgrad produces dA_3, which the gradient of OCout_dec has to join: convert that gradient into the
+      // buffer apply(4) has just finished reading and let the conv epilogue add it in fp32 (one rounding, and the
+      // read-modify-write pass over dA_3 disappears)
+      const __nv_bfloat16* add_src = nullptr;
+      if (join_dec && k == 4 && g_ocout_dec) {
+        const HrfpStage& pv = P->st[3];
+        const int HWp = pv.oh * pv.ow;
+        dim3 gd((HWp + kLayPx - 1) / kLayPx, (pv.cout + 63) / 64, P->N);
+        launch_k(nchw_to_nhwc_kernel<T>, dim3(gd), dim3(256), 0, s, g_ocout_dec, dA, pv.cout, HWp, 0, (double*)nullptr);
+        add_src = reinterpret_cast<const __nv_bfloat16*>(dA);
+        dec_joined = true;
+        at_end = true;
+      }
       int rc = conv3x3_tc_bf16(reinterpret_cast<const __nv_bfloat16*>(dY),
                                reinterpret_cast<const __nv_bfloat16*>(saved + st.wb_off),
                                reinterpret_cast<__nv_bfloat16*>(other), P->N, st.ch, st.cw, st.cout, st.cin, st.dil,
                                nullptr, nullptr, fuse ? acc + (size_t)(k - 1) * 2 * kMaxC : nullptr, s, fuse ? &bs : nullptr,
-                               l2_order && at_end);
+                               l2_order && at_end, nullptr, add_src);
       if (rc) return rc;
       if (l2_order) at_end = !at_end;
       reduced = fuse;

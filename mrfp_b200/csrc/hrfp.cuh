@@ -59,6 +59,8 @@ struct ConvBwdStats {
   int IH, IW;
   int H, W;                   // filled in by conv3x3_tc_bf16
 };
+//   add_src (dgrad use): a tensor of the output's shape that is added to the accumulators in fp32 before the single
+//   rounding to bf16 (the gradient of OCout_dec joining dA_3).
 //   finalize (forward use, with stat_acc): the LAST CTA to add its partial statistics turns them into the BN
 //   mean / invstd / scale / shift table and updates the running statistics — no separate finalisation launch.
 struct ConvBnFinalize {
@@ -74,7 +76,7 @@ struct ConvBnFinalize {
 int conv3x3_tc_bf16(const __nv_bfloat16* in, const __nv_bfloat16* wpack, __nv_bfloat16* out, int N, int H, int W,
                     int cin, int cout, int dil, const int* cnt_h, const int* cnt_w, double* stat_acc,
                     cudaStream_t stream, const ConvBwdStats* bwd_stats = nullptr, bool reverse_tiles = false,
-                    const ConvBnFinalize* finalize = nullptr);
+                    const ConvBnFinalize* finalize = nullptr, const __nv_bfloat16* add_src = nullptr);
 bool conv3x3_tc_supported(int cin, int cout);
 
 // TMA-fed BN-backward reduction (bn_ring.cu); MRFP_ERR_UNSUPPORTED -> use the LDG kernel
