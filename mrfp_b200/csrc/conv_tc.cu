@@ -9,9 +9,9 @@
 //   * B operand: 2-D TMA box {64, COUT} of the tap-major packed weights [9*COUT][CIN]
 //   * accumulators: 2 TMEM stages x COUT fp32 columns (epilogue of tile i overlaps the MMAs of tile i+1)
 // Warp roles (192 threads, persistent over tiles): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer
-// (one elected thread), warps 2-5 = epilogue: tcgen05.ld -> replication-count-weighted per-channel sum / sum of
-// squares of the fp32 accumulators (BN batch statistics of the resampled tensor, warp-transposed shuffle
-// reduction) -> bf16 pack into a swizzled staging tile -> TMA store (clips the ragged image edge).
+// (whole warp walks the loops, one elected lane issues), warps 2-5 = epilogue: tcgen05.ld -> bf16 pack into a swizzled
+// staging tile -> TMA store (clips the ragged image edge) -> replication-count-weighted per-channel column sums of the
+// stored tile (BN batch statistics of the resampled tensor); the last CTA finalises the statistics.
 #include "hrfp.cuh"
 #include <cuda.h>
 #include <mutex>
@@ -105,21 +105,6 @@ __device__ __forceinline__ bool elect_one() {
   return pred != 0;
 }
 __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
-
-// transposed butterfly: on return x[0] of lane l = sum over the 32 lanes of their x[l]   (31 shuffles)
-__device__ __forceinline__ float warp_transpose_sum(float (&x)[32], int lane) {
-#pragma unroll
-  for (int s = 16; s >= 1; s >>= 1) {
-    const bool up = (lane & s) != 0;
-#pragma unroll
-    for (int i = 0; i < s; ++i) {
-      const float send = up ? x[i] : x[i + s];
-      const float keep = up ? x[i + s] : x[i];
-      x[i] = keep + __shfl_xor_sync(0xffffffffu, send, s);
-    }
-  }
-  return x[0];
-}
 
 template <int COUT, bool BWD>
 __global__ void __launch_bounds__(kThreads, 1)
@@ -446,7 +431,7 @@ template <int COUT> struct HCfg {
   static constexpr int kOutBufs = 1;
   static constexpr int kTmemCols = 2 * kMT * COUT;
   static constexpr int kSmemBytes = kAStages * kAStageBytes + kBStages * kBTileBytes + kOutBufs * kStageOutBytes +
-                                    2 * COUT * 4 + 256 /* barriers */ + 1024 /* alignment slack */;
+                                    2 * COUT * 4 + 512 /* row weights */ + 256 /* barriers */ + 1024 /* alignment slack */;
 };
 constexpr int kHaloTileH = 16, kHaloSubW = 8;
 
@@ -469,7 +454,8 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_co
   unsigned char* sB = sA + C::kAStages * C::kAStageBytes;
   unsigned char* sOut = sB + C::kBStages * C::kBTileBytes;
   float* s_stats = reinterpret_cast<float*>(sOut + C::kOutBufs * kStageOutBytes);
-  uint64_t* full_a = reinterpret_cast<uint64_t*>(s_stats + 2 * COUT);
+  float* s_wgt = s_stats + 2 * COUT;                                    // [128] replication count of each tile row's pixel
+  uint64_t* full_a = reinterpret_cast<uint64_t*>(s_wgt + 128);
   uint64_t* empty_a = full_a + C::kAStages;
   uint64_t* full_b = empty_a + C::kAStages;
   uint64_t* empty_b = full_b + C::kBStages;
@@ -586,28 +572,14 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_co
 #pragma unroll 1
       for (int jj = 0; jj < C::kMT * (COUT / 64); ++jj) {
         const int mt = jj / (COUT / 64), j = jj % (COUT / 64);
-        float wgt = 0.f;
-        if (stat_acc) wgt = (float)(cnt_h[h0 + hl] * cnt_w[w0 + mt * kHaloSubW + wl]);   // 0 outside the image (zero-padded tables)
         unsigned char* ob = sOut + obuf * kStageOutBytes;
         if (leader) asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(C::kOutBufs - 1) : "memory");
         epi_bar_sync();
+        if (stat_acc) s_wgt[r] = (float)(cnt_h[h0 + hl] * cnt_w[w0 + mt * kHaloSubW + wl]);   // 0 outside the image (zero-padded tables)
 #pragma unroll
         for (int half = 0; half < 2; ++half) {
           uint32_t v[32];
           tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((acc * C::kMT + mt) * COUT + j * 64 + half * 32), v);
-          if (stat_acc) {
-            float x1[32], x2[32];
-#pragma unroll
-            for (int i = 0; i < 32; ++i) {
-              const float f = __uint_as_float(v[i]);
-              x1[i] = wgt * f;
-              x2[i] = x1[i] * f;
-            }
-            const float s1 = warp_transpose_sum(x1, lane);
-            const float s2 = warp_transpose_sum(x2, lane);
-            atomicAdd(&s_stats[j * 64 + half * 32 + lane], s1);
-            atomicAdd(&s_stats[COUT + j * 64 + half * 32 + lane], s2);
-          }
 #pragma unroll
           for (int c = 0; c < 4; ++c) {
             uint32_t p[4];
@@ -630,6 +602,24 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_co
         if (leader) {
           tma_store_4d(&tmap_out, ob, j * 64, w0 + mt * kHaloSubW, h0, n);
           asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+        if (stat_acc) {                          // column sums of the stored bf16 tile, as in the tap kernel
+          const int et = threadIdx.x - 64, cp = et & 31, pg = et >> 5;
+          const unsigned char* col = ob + (cp & 3) * 4;
+          const int ch = cp >> 2;
+          float s1x = 0.f, s1y = 0.f, s2x = 0.f, s2y = 0.f;
+#pragma unroll 8
+          for (int i = 0; i < 32; ++i) {
+            const int row = pg * 32 + i;
+            const uint32_t w2 = *reinterpret_cast<const uint32_t*>(col + row * 128 + ((ch ^ (row & 7)) << 4));
+            const float wg = s_wgt[row];
+            const float y0 = __uint_as_float(w2 << 16), y1 = __uint_as_float(w2 & 0xffff0000u);
+            const float t0 = wg * y0, t1 = wg * y1;
+            s1x += t0; s1y += t1;
+            s2x = fmaf(t0, y0, s2x); s2y = fmaf(t1, y1, s2y);
+          }
+          atomicAdd(&s_stats[j * 64 + 2 * cp], s1x); atomicAdd(&s_stats[j * 64 + 2 * cp + 1], s1y);
+          atomicAdd(&s_stats[COUT + j * 64 + 2 * cp], s2x); atomicAdd(&s_stats[COUT + j * 64 + 2 * cp + 1], s2y);
         }
         if (++obuf == C::kOutBufs) obuf = 0;
       }

@@ -46,7 +46,7 @@ constexpr uint32_t kPlanMagic = 0x4d524650u;   // 'MRFP'
 // tcgen05 implicit-GEMM 3x3 convolution, bf16 NHWC in/out, fp32 accumulation in TMEM (conv_tc.cu).
 //   in  [N][H][W][cin], wpack [9][cout][cin] (tap-major, K contiguous), out [N][H][W][cout]
 //   cnt_h / cnt_w: zero-padded replication counts (device) -> per-channel weighted sum / sum of squares of the
-//   fp32 accumulators are added to stat_acc[0..cout) / stat_acc[kMaxC..kMaxC+cout); pass nullptr to skip.
+//   stored (bf16) conv output are added to stat_acc[0..cout) / stat_acc[kMaxC..kMaxC+cout); pass nullptr to skip.
 //   bwd_stats (dgrad use): the conv output is the gradient dA of the PREVIOUS chain stage's output; its epilogue then
 //   also accumulates that stage's BN-backward sums  U1 = sum mask*dA, U2 = sum mask*dA*y  into stat_acc, where y is
 //   the stage's saved conv output gathered through its nearest-neighbour tables and mask = [scale*y + shift > 0].
