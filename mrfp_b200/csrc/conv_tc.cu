@@ -33,8 +33,8 @@ template <int COUT> struct Cfg {
   static constexpr int kMT = COUT == 256 ? 1 : 2;
   static constexpr int kAStageBytes = kMT * kATileBytes;
   static constexpr int kBTileBytes = COUT * 128;
-  static constexpr int kStages = 4;
-  static constexpr int kOutBufs = COUT == 64 ? 2 : 1;
+  static constexpr int kStages = COUT == 64 ? 5 : 4;
+  static constexpr int kOutBufs = 1;
   static constexpr int kTmemCols = 2 * kMT * COUT;                  // 256 / 512 / 512: powers of two
   static constexpr int kSmemBytes = kStages * (kAStageBytes + kBTileBytes) + kOutBufs * kStageOutBytes +
                                     2 * COUT * 4 + 512 /* row weights */ + 256 /* barriers */ + 1024 /* alignment slack */;
