@@ -29,7 +29,8 @@ METRIC = "mrfp_fwd_bwd_throughput"
 UNIT = "img/s"
 CONFIG = {
     "workload": "mrfp_fwd_bwd: NP+ on (8,64,192,192) and (8,256,192,192) + HRFP/HRFP+ chain 64ch@192^2 -> 256ch@384^2 -> "
-                "64ch@192^2, fwd + input-gradient bwd, per-GPU batch 8 (BASELINE config[1], 768x768 crop)",
+                "64ch@192^2 incl. the bilinear Upsample of the decoder feature in front of the HRFP+ add (deepv3.py:356-357, fused into the add kernel), "
+                "fwd + input-gradient bwd, per-GPU batch 8 (BASELINE config[1], 768x768 crop)",
     "per_gpu_batch": N_PER_GPU, "crop": [H_IMG, W_IMG], "hrfp_math": "bf16 tcgen05 (fp32 accumulate)", "np_plus_math": "fp32",
     "cache": "inputs larger than L2 (302 MB / 1.2 GB tensors per step); the per-kernel roofline launches flush L2 first",
 }
@@ -60,7 +61,7 @@ def cpu_reference_run(steps, warmup, batch=2):
     draws = [(1 + 0.75 * torch.randn(batch, c, 1, 1, generator=g), 0.75 * torch.randn(batch, c, 1, 1, generator=g)) for c in (64, 256)]
     grads = (torch.randn(batch, 64, XH, XW, generator=g), torch.randn(batch, 256, H_IMG // 2, W_IMG // 2, generator=g),
              torch.randn(batch, 256, XH, XW, generator=g))
-    d1 = torch.randn(batch, 256, H_IMG // 2, W_IMG // 2, generator=g)
+    d1 = torch.randn(batch, 256, XH, XW, generator=g)                   # decoder feature before the Upsample of deepv3.py:356
     for _ in range(warmup):
         T.mrfp_step(convs, bns, xp, f2, d1, draws, grads, H_IMG, W_IMG)
     t0 = time.perf_counter()
@@ -225,6 +226,7 @@ def run_ours(args):
     import torch
     import torch.distributed as dist
     from mrfp_b200 import build, _lib
+    import torch.nn.functional as F
     from mrfp_b200 import hrfp as H
     from mrfp_b200 import npplus as NP
 
@@ -261,7 +263,7 @@ def run_ours(args):
     g_x = torch.randn(n, 64, XH, XW, device=dev)
     g_dec = torch.randn(n, 256, H_IMG // 2, W_IMG // 2, device=dev)     # gradient wrt dec1 after the HRFP+ add
     g_f2 = torch.randn(n, 256, XH, XW, device=dev)
-    dec1_up = torch.randn(n, 256, H_IMG // 2, W_IMG // 2, device=dev)   # the decoder feature the HRFP+ skip adds to
+    dec1_up = torch.randn(n, 256, XH, XW, device=dev)   # the decoder feature BEFORE the reference's bilinear Upsample (deepv3.py:356)
 
     def step(xp_, f2_, d1_, gx_, gdec_, gf2_):
         """Public API path: autograd Functions over the C ABI (the same calls MRFPPlus.forward makes)."""
@@ -270,7 +272,7 @@ def run_ours(args):
         # deepv3.py:316-330: x = OCout + NP+(xp); NP+ call 1 rides on the chain's passes
         x, dec = H.hrfp_chain(a, convs, bns, H_IMG, W_IMG, np_draws=draws[0], math_mode=H.MATH_BF16, lazy_dec=True)
         y2 = NP.np_plus_with_draws(b, *draws[1])                                       # :335
-        d1 = H.hrfp_plus_add(d1_, dec)                                                 # :357
+        d1 = H.hrfp_plus_add_upsampled(d1_, dec)                                       # :356-357 (Upsample + add, one kernel)
         torch.autograd.backward([x, d1, y2], [gx_, gdec_, gf2_])
         return x, d1, y2, a.grad, b.grad
 
@@ -484,12 +486,12 @@ def run_ours(args):
         return a.elapsed_time(b) / iters
 
     xr = xp.detach().requires_grad_(True)
-    t_chain_f = t_api(lambda: H.hrfp_plus_add(dec1_up, H.hrfp_chain(xr, convs, bns, H_IMG, W_IMG, math_mode=H.MATH_BF16, lazy_dec=True)[1]))
+    t_chain_f = t_api(lambda: H.hrfp_plus_add_upsampled(dec1_up, H.hrfp_chain(xr, convs, bns, H_IMG, W_IMG, math_mode=H.MATH_BF16, lazy_dec=True)[1]))
 
     def chain_fb():
         xr.grad = None
         o, d = H.hrfp_chain(xr, convs, bns, H_IMG, W_IMG, math_mode=H.MATH_BF16, lazy_dec=True)
-        torch.autograd.backward([o, H.hrfp_plus_add(dec1_up, d)], [g_x, g_dec])
+        torch.autograd.backward([o, H.hrfp_plus_add_upsampled(dec1_up, d)], [g_x, g_dec])
     t_chain_fb = t_api(chain_fb)
     hrfp = {"fwd_ms": t_chain_f, "fwd_bwd_ms": t_chain_fb,
             "fwd_tflops_needed_only": HRFP_FLOP_FWD_PER_SAMPLE * n / t_chain_f / 1e9,

@@ -145,6 +145,12 @@ int mrfp_hrfp_bwd_np(const mrfp_hrfp_plan_t* plan, const float* g_ocout, const f
 int mrfp_hrfp_plus_add(const mrfp_hrfp_plan_t* plan, const void* saved, const void* lut, const float* dec1_up,
                        float* out, void* stream);
 
+/* The same with the reference's Upsample in front (deepv3.py:356-357, mynn.py:114-119): out = bilinear(dec1, size =
+ * (h/2, w/2), align_corners=True) + OCout_dec, evaluated from the LOW-resolution dec1 (N, widths[3], lh, lw) with ATen's
+ * interpolation formula — the upsampled (N,256,h/2,w/2) tensor is never materialised either. */
+int mrfp_hrfp_plus_add_bilinear(const mrfp_hrfp_plan_t* plan, const void* saved, const void* lut, const float* dec1,
+                                int lh, int lw, float* out, void* stream);
+
 /* Plain variant of the same add for a materialised OCout_dec: out = a + b (n elements). */
 int mrfp_add_f32(const float* a, const float* b, float* out, size_t n, void* stream);
 

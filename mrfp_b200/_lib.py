@@ -51,6 +51,8 @@ SIGNATURES = {
                                         ctypes.c_void_p, ctypes.c_void_p]),
     "mrfp_hrfp_plus_add": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, c_float_p, c_float_p,
                                           ctypes.c_void_p]),
+    "mrfp_hrfp_plus_add_bilinear": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, c_float_p, ctypes.c_int,
+                                                   ctypes.c_int, c_float_p, ctypes.c_void_p]),
     "mrfp_add_f32": (ctypes.c_int, [c_float_p, c_float_p, c_float_p, ctypes.c_size_t, ctypes.c_void_p]),
 }
 

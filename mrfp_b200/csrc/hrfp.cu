@@ -144,12 +144,12 @@ nchw_to_nhwc_kernel(const float* __restrict__ src, T* __restrict__ dst, int C, i
 }
 
 // out fp32 [N][C][OH][OW] = f(Y[n][ih[oh]][iw[ow]][c]) (+ add), f = identity or ReLU(scale*y + shift)
-template <typename T>
+template <typename T, bool BILIN>
 __global__ void __launch_bounds__(256)
 nhwc_to_nchw_kernel(const T* __restrict__ y, float* __restrict__ out, const float* __restrict__ add,
                     const int* __restrict__ idx_h, const int* __restrict__ idx_w, const float* __restrict__ scale,
                     const float* __restrict__ shift, int C, int IH, int IW, int OH, int OW,
-                    const float2* __restrict__ coef) {
+                    const float2* __restrict__ coef, const float* __restrict__ add_lo, int LH, int LW) {
   pdl_sync();
   __shared__ float tile[64][kLayRow];   // [channel][lay_col(pixel)]
   // flat grid, output rows fastest, then channel tiles, then w-tiles
@@ -188,6 +188,47 @@ nhwc_to_nchw_kernel(const T* __restrict__ y, float* __restrict__ out, const floa
   {
     const int px = (t & 31) * 4, crow = t >> 5;
     const bool vec = (OW & 3) == 0;
+    if (BILIN) {
+      // HRFP+ tail (deepv3.py:356-357): the add operand is Upsample(dec1) — bilinear, align_corners=True
+      // (mynn.py:114-119) — evaluated here from the low-resolution tensor with ATen's own formula
+      // (upsample_bilinear2d: src = dst * (in-1)/(out-1), lambda weights, same association), so dec1 at (h/2, w/2)
+      // never exists.  Row and column weights are the same for every channel pass of this thread.
+      const float rh = OH > 1 ? (float)(LH - 1) / (float)(OH - 1) : 0.f;
+      const float rw = OW > 1 ? (float)(LW - 1) / (float)(OW - 1) : 0.f;
+      const float h1r = rh * (float)oh;
+      const int h1 = (int)h1r, h1p = h1 < LH - 1 ? 1 : 0;
+      const float hl1 = h1r - (float)h1, hl0 = 1.f - hl1;
+      int w1[4], w1p[4];
+      float wl0[4], wl1[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int ow = min(w0 + px + i, OW - 1);
+        const float w1r = rw * (float)ow;
+        w1[i] = (int)w1r;
+        w1p[i] = w1[i] < LW - 1 ? 1 : 0;
+        wl1[i] = w1r - (float)w1[i]; wl0[i] = 1.f - wl1[i];
+      }
+#pragma unroll
+      for (int pass = 0; pass < 8; ++pass) {
+        const int c = crow + pass * 8, ow = w0 + px;
+        if (c0 + c < C && ow < OW) {
+          const size_t o = (((size_t)n * C + c0 + c) * OH + oh) * OW + ow;
+          const int col = px >> 2;
+          const float vv[4] = {tile[c][col], tile[c][33 + col], tile[c][66 + col], tile[c][99 + col]};
+          const float* r0 = add_lo + (((size_t)n * C + c0 + c) * LH + h1) * LW;
+          const float* r1 = r0 + (size_t)h1p * LW;
+          float res[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            res[i] = vv[i] + (hl0 * (wl0[i] * r0[w1[i]] + wl1[i] * r0[w1[i] + w1p[i]]) +
+                              hl1 * (wl0[i] * r1[w1[i]] + wl1[i] * r1[w1[i] + w1p[i]]));
+          if (vec && ow + 3 < OW) *reinterpret_cast<float4*>(out + o) = make_float4(res[0], res[1], res[2], res[3]);
+          else
+            for (int i = 0; i < 4 && ow + i < OW; ++i) out[o + i] = res[i];
+        }
+      }
+      return;
+    }
 #pragma unroll
     for (int pass = 0; pass < 8; ++pass) {
       const int c = crow + pass * 8, ow = w0 + px;
@@ -791,16 +832,16 @@ int hrfp_forward(const mrfp_hrfp_plan* P, const float* xp, const float* const* W
                rvar ? rvar[k] : nullptr, stats, st.cout, count, momentum, eps);
     if (k == 3 && ocout_dec) {
       const unsigned g = (unsigned)(((st.ow + kLayPx - 1) / kLayPx) * ((st.cout + 63) / 64)) * (unsigned)(P->N * st.oh);
-      launch_k(nhwc_to_nchw_kernel<T>, dim3(g), dim3(256), 0, s, Y, ocout_dec, nullptr, lut + st.idx_h, lut + st.idx_w,
+      launch_k(nhwc_to_nchw_kernel<T, false>, dim3(g), dim3(256), 0, s, Y, ocout_dec, nullptr, lut + st.idx_h, lut + st.idx_w,
                                                         stats + 2 * kMaxC, stats + 3 * kMaxC, st.cout, st.ch, st.cw,
-                                                        st.oh, st.ow, (const float2*)nullptr);
+                                                        st.oh, st.ow, (const float2*)nullptr, (const float*)nullptr, 0, 0);
     }
     if (k == kHrfpStages - 1) {
       const unsigned g = (unsigned)(((st.ow + kLayPx - 1) / kLayPx) * ((st.cout + 63) / 64)) * (unsigned)(P->N * st.oh);
       // with the fused NP+ the add operand is xp itself under the plane's affine map: OCout + (a*xp + b)
-      launch_k(nhwc_to_nchw_kernel<T>, dim3(g), dim3(256), 0, s, Y, ocout, np ? xp : x_add, lut + st.idx_h, lut + st.idx_w,
+      launch_k(nhwc_to_nchw_kernel<T, false>, dim3(g), dim3(256), 0, s, Y, ocout, np ? xp : x_add, lut + st.idx_h, lut + st.idx_w,
                                                         stats + 2 * kMaxC, stats + 3 * kMaxC, st.cout, st.ch, st.cw,
-                                                        st.oh, st.ow, np ? np->coef : (const float2*)nullptr);
+                                                        st.oh, st.ow, np ? np->coef : (const float2*)nullptr, (const float*)nullptr, 0, 0);
     } else if (k + 1 < last) {
       launch_k(bn_relu_resample_kernel<T>, dim3(even_grid(P->N * st.oh, di.sm_count * 8)), dim3(256), 0, s, 
           Y, nxt, lut + st.idx_h, lut + st.idx_w, stats + 2 * kMaxC, stats + 3 * kMaxC, P->N, st.cout, st.ch, st.cw,
@@ -937,8 +978,8 @@ int hrfp_backward(const mrfp_hrfp_plan* P, const float* g_ocout, const float* g_
   const unsigned g = (unsigned)(((P->xw + kLayPx - 1) / kLayPx) * ((P->cin + 63) / 64)) * (unsigned)(P->N * P->xh);
   // fused NP+ backward: g_xp = dA_0 + (a' * g_ocout + b') with the plane's backward coefficients
   const bool np_add = np && g_ocout;
-  launch_k(nhwc_to_nchw_kernel<T>, dim3(g), dim3(256), 0, s, dA, g_xp, np_add ? g_ocout : (const float*)nullptr, nullptr, nullptr,
-           nullptr, nullptr, P->cin, P->xh, P->xw, P->xh, P->xw, np_add ? np->coef : (const float2*)nullptr);
+  launch_k(nhwc_to_nchw_kernel<T, false>, dim3(g), dim3(256), 0, s, dA, g_xp, np_add ? g_ocout : (const float*)nullptr, nullptr, nullptr,
+           nullptr, nullptr, P->cin, P->xh, P->xw, P->xh, P->xw, np_add ? np->coef : (const float2*)nullptr, (const float*)nullptr, 0, 0);
   MRFP_CUDA_TRY(cudaGetLastError());
   return MRFP_OK;
 }
@@ -1147,13 +1188,15 @@ extern "C" int mrfp_hrfp_bwd_np(const mrfp_hrfp_plan_t* P, const float* g_ocout,
 
 template <typename T>
 static int hrfp_plus_add_impl(const mrfp_hrfp_plan* P, const char* saved, const int* lut, const float* dec1_up,
-                              float* out, cudaStream_t s) {
+                              const float* dec1_lo, int lh, int lw, float* out, cudaStream_t s) {
   const HrfpStage& st = P->st[3];
   const T* Y = reinterpret_cast<const T*>(saved + st.y_off);
   const float* stats = reinterpret_cast<const float*>(saved + P->stats_off) + (size_t)3 * 4 * kMaxC;
   const unsigned g = (unsigned)(((st.ow + kLayPx - 1) / kLayPx) * ((st.cout + 63) / 64)) * (unsigned)(P->N * st.oh);
-  launch_k(nhwc_to_nchw_kernel<T>, dim3(g), dim3(256), 0, s, Y, out, dec1_up, lut + st.idx_h, lut + st.idx_w, stats + 2 * kMaxC,
-                                            stats + 3 * kMaxC, st.cout, st.ch, st.cw, st.oh, st.ow, (const float2*)nullptr);
+  if (dec1_lo && (lw > st.ow || lh > st.oh)) return MRFP_ERR_BAD_SHAPE;      // an Upsample: the source is not larger
+  launch_k(dec1_lo ? nhwc_to_nchw_kernel<T, true> : nhwc_to_nchw_kernel<T, false>, dim3(g), dim3(256), 0, s, Y, out, dec1_up,
+           lut + st.idx_h, lut + st.idx_w, stats + 2 * kMaxC, stats + 3 * kMaxC, st.cout, st.ch, st.cw, st.oh, st.ow,
+           (const float2*)nullptr, dec1_lo, lh, lw);
   MRFP_CUDA_TRY(cudaGetLastError());
   return MRFP_OK;
 }
@@ -1164,8 +1207,19 @@ extern "C" int mrfp_hrfp_plus_add(const mrfp_hrfp_plan_t* P, const void* saved, 
   if (!saved || !lut || !dec1_up || !out) return MRFP_ERR_NULL_POINTER;
   cudaStream_t s = (cudaStream_t)stream;
   if (P->mode == MRFP_MATH_BF16)
-    return hrfp_plus_add_impl<__nv_bfloat16>(P, (const char*)saved, (const int*)lut, dec1_up, out, s);
-  return hrfp_plus_add_impl<float>(P, (const char*)saved, (const int*)lut, dec1_up, out, s);
+    return hrfp_plus_add_impl<__nv_bfloat16>(P, (const char*)saved, (const int*)lut, dec1_up, nullptr, 0, 0, out, s);
+  return hrfp_plus_add_impl<float>(P, (const char*)saved, (const int*)lut, dec1_up, nullptr, 0, 0, out, s);
+}
+
+extern "C" int mrfp_hrfp_plus_add_bilinear(const mrfp_hrfp_plan_t* P, const void* saved, const void* lut,
+                                           const float* dec1, int lh, int lw, float* out, void* stream) {
+  if (!P || P->magic != kPlanMagic) return MRFP_ERR_BAD_PLAN;
+  if (!saved || !lut || !dec1 || !out) return MRFP_ERR_NULL_POINTER;
+  if (lh <= 0 || lw <= 0) return MRFP_ERR_BAD_SHAPE;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (P->mode == MRFP_MATH_BF16)
+    return hrfp_plus_add_impl<__nv_bfloat16>(P, (const char*)saved, (const int*)lut, nullptr, dec1, lh, lw, out, s);
+  return hrfp_plus_add_impl<float>(P, (const char*)saved, (const int*)lut, nullptr, dec1, lh, lw, out, s);
 }
 
 extern "C" int mrfp_add_f32(const float* a, const float* b, float* out, size_t n, void* stream) {

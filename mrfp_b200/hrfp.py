@@ -268,6 +268,40 @@ class _PlusAddFusedFn(torch.autograd.Function):
         return g, torch.zeros(1, dtype=torch.float32, device=g.device), None
 
 
+def hrfp_plus_add_upsampled(dec1: torch.Tensor, ocout_dec: "HrfpDec") -> torch.Tensor:
+    """deepv3.py:356-357 in one kernel: Upsample(dec1) (bilinear, align_corners=True, mynn.py:114-119) + OCout_dec, from
+    the low-resolution `dec1` and the `HrfpDec` handle of `hrfp_chain(lazy_dec=True)`.  Neither the upsampled dec1 nor
+    OCout_dec is materialised.  Autograd: bilinear-transpose of the gradient to dec1 (ATen), identity to the chain."""
+    return _PlusAddUpFn.apply(dec1, ocout_dec.token, ocout_dec)
+
+
+class _PlusAddUpFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, dec1, token, handle):
+        lib = _lib.load()
+        plan = handle.plan
+        n, c, oh, ow = plan.dec_shape
+        if dec1.dim() != 4 or dec1.shape[0] != n or dec1.shape[1] != c or dec1.dtype != torch.float32 or not dec1.is_cuda:
+            raise _lib.MrfpError(f"hrfp_plus_add_upsampled: dec1 must be CUDA fp32 (N={n}, C={c}, lh, lw)")
+        a = dec1.contiguous()
+        out = torch.empty(plan.dec_shape, dtype=torch.float32, device=a.device)
+        with torch.cuda.device(a.device):
+            rc = lib.mrfp_hrfp_plus_add_bilinear(plan.handle, handle.saved.data_ptr(), plan.lut.data_ptr(), a.data_ptr(),
+                                                 a.shape[2], a.shape[3], out.data_ptr(), _stream_ptr(a.device))
+        _lib.check(rc, "mrfp_hrfp_plus_add_bilinear")
+        ctx.mail = handle.mail
+        ctx.lo_shape = tuple(a.shape)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        ctx.mail["g"] = g if ctx.mail["g"] is None else ctx.mail["g"] + g
+        g_lo = None
+        if ctx.needs_input_grad[0]:
+            g_lo = torch.ops.aten.upsample_bilinear2d_backward(g.contiguous(), list(g.shape[2:]), list(ctx.lo_shape), True, None, None)
+        return g_lo, torch.zeros(1, dtype=torch.float32, device=g.device), None
+
+
 class _AddFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, a, b):

@@ -67,6 +67,8 @@ class MRFPMixin:
     fuse_stem_np = os.environ.get("MRFP_FUSE_STEM_NP", "1") != "0"
     # take the NP+ statistics of call 2 in layer1's last ReLU (same result, NP+ forward becomes 1R+1W); MRFP_FUSE_LAYER1_NP=0: off
     fuse_layer1_np = os.environ.get("MRFP_FUSE_LAYER1_NP", "1") != "0"
+    # HRFP+ tail: bilinear Upsample of dec1 evaluated inside the add kernel (no (N,256,h/2,w/2) intermediate); MRFP_FUSE_PLUS_TAIL=0: off
+    fuse_plus_tail = os.environ.get("MRFP_FUSE_PLUS_TAIL", "1") != "0"
 
     def _build_hrfp(self, in_ch=64, widths=(64, 64, 128, 256)):
         chans = [in_ch, widths[0], widths[1], widths[2], widths[3], widths[2], widths[1], widths[0], in_ch]
@@ -254,8 +256,11 @@ class MRFPPlus(nn.Module, MRFPMixin):
         dec0 = torch.cat([dec0_fine, upsample_bilinear(dec0_up, low_level.shape[2:])], 1)
         dec1 = self.final1(dec0)
         if training and p3 < 0.5:                                           # deepv3.py:355-357
-            dec1 = upsample_bilinear(dec1, (int(h / 2), int(w / 2)))
-            dec1 = self._plus_add(dec1, ocout_dec)
+            if self.fuse_plus_tail and isinstance(ocout_dec, _hrfp.HrfpDec) and dec1.is_cuda:
+                dec1 = _hrfp.hrfp_plus_add_upsampled(dec1, ocout_dec)       # Upsample + add in one kernel
+            else:
+                dec1 = upsample_bilinear(dec1, (int(h / 2), int(w / 2)))
+                dec1 = self._plus_add(dec1, ocout_dec)
         main_out = upsample_bilinear(self.final2(dec1), (h, w))
         if training:
             return self.criterion(main_out, gts)

@@ -53,8 +53,10 @@ def hrfp_chain(convs, bns, xp, h, w):
     return o, dec
 
 
-def mrfp_step(convs, bns, xp, feat2, dec1_up, draws, grads, h, w):
-    """One forward+backward pass of the whole MRFP path: both NP+ calls, the HRFP chain, the HRFP and HRFP+ adds."""
+def mrfp_step(convs, bns, xp, feat2, dec1, draws, grads, h, w):
+    """One forward+backward pass of the whole MRFP path: both NP+ calls, the HRFP chain, the HRFP and HRFP+ adds.
+    `dec1` is the decoder feature before the reference's Upsample (deepv3.py:356, mynn.py:114-119); a tensor that
+    already has the (h/2, w/2) size passes through the interpolation unchanged."""
     (a1, e1), (a2, e2) = draws
     g_x, g_d1, g_f2 = grads
     xp = xp.detach().requires_grad_(True)
@@ -63,6 +65,7 @@ def mrfp_step(convs, bns, xp, feat2, dec1_up, draws, grads, h, w):
     ocout, dec = hrfp_chain(convs, bns, xp, h, w)                        # :320-327
     x = ocout + x                                                        # :330
     y2 = np_plus(feat2, a2, e2)                                          # :335
+    dec1_up = F.interpolate(dec1, size=(int(h / 2), int(w / 2)), mode="bilinear", align_corners=True)   # :356
     d1 = torch.add(dec, dec1_up)                                         # :357
     torch.autograd.backward([x, d1, y2], [g_x, g_d1, g_f2])
     return x.detach(), d1.detach(), y2.detach(), xp.grad, feat2.grad

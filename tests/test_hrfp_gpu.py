@@ -223,6 +223,42 @@ def test_plus_add():
     assert torch.equal(a.grad, torch.ones_like(a)) and torch.equal(b.grad, torch.ones_like(b))
 
 
+@pytest.mark.parametrize("mode", [0, 2])
+@pytest.mark.parametrize("lo", [(12, 10), (24, 20), (7, 33)])
+def test_plus_add_with_bilinear_upsample_matches_aten(lo, mode):
+    """HRFP+ tail (deepv3.py:356-357): Upsample(dec1, bilinear, align_corners=True) + OCout_dec from the low-resolution
+    dec1 in one kernel vs F.interpolate + the materialised add; gradient wrt dec1 = ATen's bilinear backward."""
+    import torch.nn.functional as F
+    from mrfp_b200.hrfp import hrfp_chain, hrfp_plus_add, hrfp_plus_add_upsampled
+    n, h, w, xh, xw = 2, 96, 80, 24, 20
+    ws, gs = make_hrfp_params(51)
+    convs, bns = _modules(ws, gs, "cuda")
+    xp = torch.from_numpy(make_feat(52, (n, 64, xh, xw))).cuda()
+    torch.manual_seed(53)
+    d_lo = torch.randn(n, 256, *lo, device="cuda")
+    g = torch.randn(n, 256, h // 2, w // 2, device="cuda")
+    xa = xp.clone().requires_grad_(True); da = d_lo.clone().requires_grad_(True)
+    _, dec_a = hrfp_chain(xa, convs, bns, h, w, want_out=False, math_mode=mode, lazy_dec=True, update_running_stats=False)
+    oa = hrfp_plus_add_upsampled(da, dec_a)
+    oa.backward(g)
+    xb = xp.clone().requires_grad_(True); db = d_lo.clone().requires_grad_(True)
+    _, dec_b = hrfp_chain(xb, convs, bns, h, w, want_out=False, math_mode=mode, lazy_dec=True, update_running_stats=False)
+    ob = hrfp_plus_add(F.interpolate(db, size=(h // 2, w // 2), mode="bilinear", align_corners=True), dec_b)
+    ob.backward(g)
+    t_f, t_b = (2e-6, 5e-6) if mode == 0 else (TOL_VS_BF16_ORACLE["fwd"], TOL_VS_BF16_ORACLE["bwd"])
+    assert (oa - ob).abs().max().item() <= t_f * ob.abs().max().item()
+    assert torch.allclose(da.grad, db.grad, rtol=1e-6, atol=1e-6 * db.grad.abs().max().item())
+    assert (xa.grad - xb.grad).abs().max().item() <= t_b * xb.grad.abs().max().item()
+    # the interpolation alone, tight: subtract the OCout_dec-only output (fp32 mode is deterministic up to the BN atomics)
+    zero = torch.zeros_like(d_lo)
+    _, dec_c = hrfp_chain(xp, convs, bns, h, w, want_out=False, math_mode=0, lazy_dec=True, update_running_stats=False)
+    only_dec = hrfp_plus_add_upsampled(zero, dec_c)
+    _, dec_d = hrfp_chain(xp, convs, bns, h, w, want_out=False, math_mode=0, lazy_dec=True, update_running_stats=False)
+    interp = hrfp_plus_add_upsampled(d_lo, dec_d) - only_dec
+    ref = F.interpolate(d_lo, size=(h // 2, w // 2), mode="bilinear", align_corners=True)
+    assert (interp - ref).abs().max().item() <= 2e-6 * ref.abs().max().item() + 2e-6 * only_dec.abs().max().item()
+
+
 def test_lazy_dec_handle_matches_materialised_path():
     """hrfp_plus_add on the HrfpDec handle (OCout_dec never materialised) == add of the materialised tensor,
     forward and both gradients."""

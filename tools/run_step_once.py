@@ -14,14 +14,14 @@ for c, b in zip(convs, bns):
     init_hrfp_module(c); init_hrfp_module(b)
 xp = torch.relu(torch.randn(n, 64, 192, 192, device=dev))
 f2 = torch.relu(torch.randn(n, 256, 192, 192, device=dev))
-d1 = torch.randn(n, 256, 384, 384, device=dev)
+d1 = torch.randn(n, 256, 192, 192, device=dev)
 draws = [(1 + 0.75 * torch.randn(n, c, 1, 1, device=dev), 0.75 * torch.randn(n, c, 1, 1, device=dev)) for c in (64, 256)]
 g_x = torch.randn(n, 64, 192, 192, device=dev); g_d = torch.randn(n, 256, 384, 384, device=dev); g_f = torch.randn(n, 256, 192, 192, device=dev)
 for _ in range(2):
     a = xp.detach().requires_grad_(True); b = f2.detach().requires_grad_(True)
     x, dec = H.hrfp_chain(a, convs, bns, 768, 768, np_draws=draws[0], math_mode=H.MATH_BF16, lazy_dec=True)
     y2 = NP.np_plus_with_draws(b, *draws[1])
-    o = H.hrfp_plus_add(d1, dec)
+    o = H.hrfp_plus_add_upsampled(d1, dec)
     torch.autograd.backward([x, o, y2], [g_x, g_d, g_f])
 torch.cuda.synchronize()
 print("ok")
