@@ -154,6 +154,26 @@ int mrfp_hrfp_plus_add_bilinear(const mrfp_hrfp_plan_t* plan, const void* saved,
 /* Plain variant of the same add for a materialised OCout_dec: out = a + b (n elements). */
 int mrfp_add_f32(const float* a, const float* b, float* out, size_t n, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * InstanceNorm2d(affine=True) [+ ReLU] of the trunk next to the insertion points — replaces
+ * nn.InstanceNorm2d + nn.ReLU at network/Resnet.py:534-536 / :591-598 (stem, wt_layer[2] == 4) and
+ * network/Resnet.py:176-178 + :218-225 (last Bottleneck of layer1 / layer2, iw == 4), and their autograd backward.
+ *
+ *   y = (x - mean_hw x) / sqrt(var_hw x + eps) * gamma[c] + beta[c]      (biased variance, no running statistics)
+ *   y = max(y, 0) when relu != 0;   psum[n*C+c] = sum_hw y when psum != NULL (the plane sums NP+ call 2 needs,
+ *   deepv3.py:334-335: layer1's IN + ReLU is its producer)
+ *
+ * One thread-block cluster per plane keeps the plane in shared memory between the statistics and the write: forward
+ * 1R + 1W, backward 2R + 1W of HBM traffic.  x, y, gy, gx: (N,C,HW) fp32; gamma, beta: (C) or NULL (= 1, 0);
+ * mean, invstd: (N,C) out (forward) / in (backward).  The backward recomputes the ReLU mask from x with the forward's
+ * expression and leaves per-plane partials dgamma_part, dbeta_part (N,C): d_gamma[c] = sum_n dgamma_part[n,c].
+ * ---------------------------------------------------------------------------------------------- */
+int mrfp_instnorm_fwd_f32(const float* x, const float* gamma, const float* beta, float* y, float* mean, float* invstd,
+                          double* psum, int N, int C, int HW, float eps, int relu, void* stream);
+int mrfp_instnorm_bwd_f32(const float* gy, const float* x, const float* gamma, const float* beta, const float* mean,
+                          const float* invstd, float* gx, float* dgamma_part, float* dbeta_part, int N, int C, int HW,
+                          int relu, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

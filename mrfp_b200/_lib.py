@@ -54,6 +54,12 @@ SIGNATURES = {
     "mrfp_hrfp_plus_add_bilinear": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, c_float_p, ctypes.c_int,
                                                    ctypes.c_int, c_float_p, ctypes.c_void_p]),
     "mrfp_add_f32": (ctypes.c_int, [c_float_p, c_float_p, c_float_p, ctypes.c_size_t, ctypes.c_void_p]),
+    "mrfp_instnorm_fwd_f32": (ctypes.c_int, [c_float_p, c_float_p, c_float_p, c_float_p, c_float_p, c_float_p, ctypes.c_void_p,
+                                             ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_float, ctypes.c_int,
+                                             ctypes.c_void_p]),
+    "mrfp_instnorm_bwd_f32": (ctypes.c_int, [c_float_p, c_float_p, c_float_p, c_float_p, c_float_p, c_float_p, c_float_p,
+                                             c_float_p, c_float_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                             ctypes.c_void_p]),
 }
 
 _lib = None

@@ -1,0 +1,387 @@
+// InstanceNorm2d(affine) [+ ReLU] [+ plane sums for NP+] with the plane RESIDENT ON CHIP, sm_100a.
+//
+// The reference's trunk normalises per (n, c) plane at three places next to the MRFP insertion points
+// (wt_layer=[0,0,4,4,4,0,0]): the stem (Resnet.py:534-536, 64 x 384^2 at a 768^2 crop), the end of layer1
+// (Resnet.py:176-178 + :218-225, 256 x 192^2 — the producer of NP+ call 2) and the end of layer2 (512 x 96^2), each
+// followed by a ReLU.  Unlike NP+, a plane's statistics need nothing from other planes, so a plane (or a slice of
+// it) can stay in shared memory between the statistics and the write: one thread-block CLUSTER per plane, every CTA
+// holds one slice (1-D TMA bulk loads, per-chunk mbarriers so the first reduction overlaps the loads), partial sums
+// meet through distributed shared memory, and the plane is read from HBM exactly once:
+//   forward   1R + 1W   (ATen: statistics + normalise + ReLU = 3R + 2W)
+//   backward  2R + 1W   (gy and x once each; ATen: ReLU backward + batch-norm backward = 5R + 2W)
+// Statistics are two-pass over the resident copy (mean first, then centred squares; double across lanes) — the same
+// biased variance F.instance_norm uses.  Planes too large for an 8-CTA cluster fall back to re-reading global memory.
+#include "common.cuh"
+#include "tma.cuh"
+#include <cooperative_groups.h>
+#include <math.h>
+
+namespace cg = cooperative_groups;
+
+namespace mrfp {
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int kWarps = kThreads / 32;
+constexpr int kChunkElems = 4096;                 // 16 KiB per TMA bulk copy / mbarrier
+constexpr int kMaxChunks = 16;                    // <= 256 KiB per buffer (more than shared memory holds)
+constexpr int kMaxCluster = 8;                    // portable cluster size
+
+struct Red2 { double a, b; };
+
+// block-wide sum of two doubles (fixed order), result in every thread
+__device__ __forceinline__ Red2 block_sum2(double a, double b, double (*s_w)[2]) {
+  a = warp_sum(a); b = warp_sum(b);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  __syncthreads();                                 // s_w may still be read from the previous round
+  if (lane == 0) { s_w[warp][0] = a; s_w[warp][1] = b; }
+  __syncthreads();
+  Red2 r{0.0, 0.0};
+#pragma unroll
+  for (int i = 0; i < kWarps; ++i) { r.a += s_w[i][0]; r.b += s_w[i][1]; }
+  return r;
+}
+
+// cluster-wide sum: every CTA publishes its pair in slot `round` and reads all ranks in rank order
+__device__ __forceinline__ Red2 cluster_sum2(cg::cluster_group& cluster, Red2 mine, double (*s_pub)[2], int round) {
+  const unsigned cs = cluster.num_blocks();
+  if (cs == 1) return mine;
+  if (threadIdx.x == 0) { s_pub[round][0] = mine.a; s_pub[round][1] = mine.b; }
+  cluster.sync();
+  Red2 r{0.0, 0.0};
+  for (unsigned k = 0; k < cs; ++k) {
+    const double* remote = cluster.map_shared_rank(&s_pub[round][0], k);
+    r.a += remote[0]; r.b += remote[1];
+  }
+  return r;
+}
+
+// Brings the CTA's slice of one plane into shared memory.  VEC: chunked 1-D bulk copies (thread 0 issues, everyone
+// waits per chunk while reducing); otherwise a plain element copy.
+template <bool VEC>
+__device__ __forceinline__ void issue_slice_load(float* dst, const float* src, int len, uint64_t* bars) {
+  if (VEC) {
+    if (threadIdx.x == 0) {
+      const int nchunk = (len + kChunkElems - 1) / kChunkElems;
+      for (int k = 0; k < nchunk; ++k) {
+        const int n = min(kChunkElems, len - k * kChunkElems);
+        tma::mbar_expect_tx(&bars[k], (uint32_t)n * 4u);
+        tma::bulk_load(dst + k * kChunkElems, src + k * kChunkElems, (uint32_t)n * 4u, &bars[k]);
+      }
+    }
+  } else {
+    for (int i = threadIdx.x; i < len; i += kThreads) dst[i] = src[i];
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ forward
+template <bool VEC, bool RESIDENT>
+__global__ void __launch_bounds__(kThreads)
+instnorm_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
+                    float* __restrict__ y, float* __restrict__ mean_out, float* __restrict__ invstd_out,
+                    double* __restrict__ psum, int C, int HW, float eps, int relu, int slice) {
+  cg::cluster_group cluster = cg::this_cluster();
+  const unsigned cs = cluster.num_blocks(), cr = cluster.block_rank();
+  const long long plane = blockIdx.x / cs;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  float* buf = reinterpret_cast<float*>(smem_raw);
+  __shared__ __align__(8) uint64_t bars[kMaxChunks];
+  __shared__ double s_w[kWarps][2];
+  __shared__ double s_pub[3][2];
+
+  const int tid = threadIdx.x;
+  const int begin = (int)cr * slice;
+  const int len = max(0, min(slice, HW - begin));
+  const float* src = x + plane * (long long)HW + begin;
+  float* dst = y + plane * (long long)HW + begin;
+  const int nchunk = (len + kChunkElems - 1) / kChunkElems;
+
+  if (RESIDENT) {
+    if (VEC) {
+      if (tid == 0) {
+        for (int k = 0; k < nchunk; ++k) tma::mbar_init(&bars[k], 1);
+        tma::mbar_fence_init();
+      }
+      __syncthreads();
+    }
+    issue_slice_load<VEC>(buf, src, len, bars);
+    if (!VEC) __syncthreads();
+  }
+  const float* in = RESIDENT ? buf : src;
+
+  // pass 1: sum -> mean
+  float acc = 0.f;
+  if (VEC) {
+    for (int k = 0; k < nchunk; ++k) {
+      if (RESIDENT) tma::mbar_wait(&bars[k], 0);
+      const int n4 = min(kChunkElems, len - k * kChunkElems) >> 2;
+      const float4* p = reinterpret_cast<const float4*>(in + k * kChunkElems);
+      float4 a4 = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int i = tid; i < n4; i += kThreads) {
+        const float4 v = RESIDENT ? p[i] : ld_stream_f4(p + i);
+        a4.x += v.x; a4.y += v.y; a4.z += v.z; a4.w += v.w;
+      }
+      acc += (a4.x + a4.y) + (a4.z + a4.w);
+    }
+  } else {
+    for (int i = tid; i < len; i += kThreads) acc += in[i];
+  }
+  Red2 t = cluster_sum2(cluster, block_sum2((double)acc, 0.0, s_w), s_pub, 0);
+  const float mean = (float)(t.a / (double)HW);
+
+  // pass 2: centred squares -> invstd (biased variance, as F.instance_norm)
+  acc = 0.f;
+  if (VEC) {
+    const float4* p = reinterpret_cast<const float4*>(in);
+    float4 a4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int i = tid; i < (len >> 2); i += kThreads) {
+      const float4 v = p[i];
+      const float dx = v.x - mean, dy = v.y - mean, dz = v.z - mean, dw = v.w - mean;
+      a4.x = fmaf(dx, dx, a4.x); a4.y = fmaf(dy, dy, a4.y); a4.z = fmaf(dz, dz, a4.z); a4.w = fmaf(dw, dw, a4.w);
+    }
+    acc = (a4.x + a4.y) + (a4.z + a4.w);
+  } else {
+    for (int i = tid; i < len; i += kThreads) { const float d = in[i] - mean; acc = fmaf(d, d, acc); }
+  }
+  t = cluster_sum2(cluster, block_sum2((double)acc, 0.0, s_w), s_pub, 1);
+  const float invstd = (float)(1.0 / sqrt(t.a / (double)HW + (double)eps));
+
+  // pass 3: y = (x - mean) * (gamma * invstd) + beta, optional ReLU, optional plane sum of y
+  const int c = (int)(plane % C);
+  const float a = (gamma ? gamma[c] : 1.f) * invstd, b = beta ? beta[c] : 0.f;
+  const float lo = relu ? 0.f : -INFINITY;
+  acc = 0.f;
+  if (VEC) {
+    const float4* p = reinterpret_cast<const float4*>(in);
+    float4* q = reinterpret_cast<float4*>(dst);
+    float4 a4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int i = tid; i < (len >> 2); i += kThreads) {
+      float4 v = p[i];
+      v.x = fmaxf(fmaf(v.x - mean, a, b), lo); v.y = fmaxf(fmaf(v.y - mean, a, b), lo);
+      v.z = fmaxf(fmaf(v.z - mean, a, b), lo); v.w = fmaxf(fmaf(v.w - mean, a, b), lo);
+      a4.x += v.x; a4.y += v.y; a4.z += v.z; a4.w += v.w;
+      q[i] = v;
+    }
+    acc = (a4.x + a4.y) + (a4.z + a4.w);
+  } else {
+    for (int i = tid; i < len; i += kThreads) {
+      const float v = fmaxf(fmaf(in[i] - mean, a, b), lo);
+      acc += v;
+      dst[i] = v;
+    }
+  }
+  if (psum) {
+    t = cluster_sum2(cluster, block_sum2((double)acc, 0.0, s_w), s_pub, 2);
+    if (cr == 0 && tid == 0) psum[plane] = t.a;
+  }
+  if (cr == 0 && tid == 0) { mean_out[plane] = mean; invstd_out[plane] = invstd; }
+  if (cs > 1) cluster.sync();                      // peers may still be reading this CTA's published partials
+}
+
+// ------------------------------------------------------------------------------------------------ backward
+// xh = (x - mean) * invstd;  g' = gy * [y > 0] (ReLU variant; y recomputed with the forward's expression);
+// S1 = sum g', S2 = sum g' * xh;  gx = gamma * invstd * (g' - S1/HW - xh * S2/HW);  d_gamma += S2, d_beta += S1.
+template <bool VEC, bool RESIDENT>
+__global__ void __launch_bounds__(kThreads)
+instnorm_bwd_kernel(const float* __restrict__ gy, const float* __restrict__ x, const float* __restrict__ gamma,
+                    const float* __restrict__ beta, const float* __restrict__ mean_in, const float* __restrict__ invstd_in,
+                    float* __restrict__ gx, float* __restrict__ dgamma_part, float* __restrict__ dbeta_part, int C, int HW,
+                    int relu, int slice) {
+  cg::cluster_group cluster = cg::this_cluster();
+  const unsigned cs = cluster.num_blocks(), cr = cluster.block_rank();
+  const long long plane = blockIdx.x / cs;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  float* bx = reinterpret_cast<float*>(smem_raw);
+  float* bg = bx + slice;                          // slice is a multiple of 4: both buffers 16-byte aligned
+  __shared__ __align__(8) uint64_t bars[2 * kMaxChunks];
+  __shared__ double s_w[kWarps][2];
+  __shared__ double s_pub[1][2];
+
+  const int tid = threadIdx.x;
+  const int begin = (int)cr * slice;
+  const int len = max(0, min(slice, HW - begin));
+  const long long off = plane * (long long)HW + begin;
+  const int nchunk = (len + kChunkElems - 1) / kChunkElems;
+
+  if (RESIDENT) {
+    if (VEC) {
+      if (tid == 0) {
+        for (int k = 0; k < 2 * nchunk; ++k) tma::mbar_init(&bars[k], 1);
+        tma::mbar_fence_init();
+      }
+      __syncthreads();
+      if (tid == 0) {                               // interleave the two streams chunk by chunk
+        for (int k = 0; k < nchunk; ++k) {
+          const uint32_t nb = (uint32_t)min(kChunkElems, len - k * kChunkElems) * 4u;
+          tma::mbar_expect_tx(&bars[2 * k], nb);
+          tma::bulk_load(bx + k * kChunkElems, x + off + k * kChunkElems, nb, &bars[2 * k]);
+          tma::mbar_expect_tx(&bars[2 * k + 1], nb);
+          tma::bulk_load(bg + k * kChunkElems, gy + off + k * kChunkElems, nb, &bars[2 * k + 1]);
+        }
+      }
+    } else {
+      for (int i = tid; i < len; i += kThreads) { bx[i] = x[off + i]; bg[i] = gy[off + i]; }
+      __syncthreads();
+    }
+  }
+  const int c = (int)(plane % C);
+  const float mean = mean_in[plane], invstd = invstd_in[plane];
+  const float gm = gamma ? gamma[c] : 1.f;
+  const float a = gm * invstd, b = beta ? beta[c] : 0.f;
+  const float* px = RESIDENT ? bx : x + off;
+  const float* pg = RESIDENT ? bg : gy + off;
+
+  // pass 1: xh and g' (kept in place when resident), S1, S2
+  float s1 = 0.f, s2 = 0.f;
+  auto one = [&](float xv, float gv, float& xh, float& gp) {
+    const float d = xv - mean;
+    xh = d * invstd;
+    gp = (relu && !(fmaf(d, a, b) > 0.f)) ? 0.f : gv;
+    s1 += gp;
+    s2 = fmaf(gp, xh, s2);
+  };
+  if (VEC) {
+    for (int k = 0; k < nchunk; ++k) {
+      if (RESIDENT) { tma::mbar_wait(&bars[2 * k], 0); tma::mbar_wait(&bars[2 * k + 1], 0); }
+      const int n4 = min(kChunkElems, len - k * kChunkElems) >> 2;
+      const float4* p = reinterpret_cast<const float4*>(px + k * kChunkElems);
+      const float4* q = reinterpret_cast<const float4*>(pg + k * kChunkElems);
+      for (int i = tid; i < n4; i += kThreads) {
+        const float4 xv = RESIDENT ? p[i] : ld_stream_f4(p + i);
+        const float4 gv = RESIDENT ? q[i] : ld_stream_f4(q + i);
+        float4 xh, gp;
+        one(xv.x, gv.x, xh.x, gp.x); one(xv.y, gv.y, xh.y, gp.y); one(xv.z, gv.z, xh.z, gp.z); one(xv.w, gv.w, xh.w, gp.w);
+        if (RESIDENT) {
+          reinterpret_cast<float4*>(bx + k * kChunkElems)[i] = xh;
+          reinterpret_cast<float4*>(bg + k * kChunkElems)[i] = gp;
+        }
+      }
+    }
+  } else {
+    for (int i = tid; i < len; i += kThreads) {
+      float xh, gp;
+      one(px[i], pg[i], xh, gp);
+      if (RESIDENT) { bx[i] = xh; bg[i] = gp; }
+    }
+  }
+  const Red2 t = cluster_sum2(cluster, block_sum2((double)s1, (double)s2, s_w), s_pub, 0);
+  const float m1 = (float)(t.a / (double)HW), m2 = (float)(t.b / (double)HW);
+
+  // pass 2: gx (each thread re-reads exactly the elements it wrote in pass 1)
+  float* out = gx + off;
+  auto fin = [&](float xh, float gp) { return a * (gp - m1 - xh * m2); };
+  if (VEC) {
+    for (int i = tid; i < (len >> 2); i += kThreads) {
+      float4 xh, gp;
+      if (RESIDENT) {
+        xh = reinterpret_cast<const float4*>(bx)[i];
+        gp = reinterpret_cast<const float4*>(bg)[i];
+      } else {
+        const float4 xv = reinterpret_cast<const float4*>(px)[i], gv = reinterpret_cast<const float4*>(pg)[i];
+        const float s1_keep = s1, s2_keep = s2;      // (the sums are final: `one` is reused only for its xh / g')
+        one(xv.x, gv.x, xh.x, gp.x); one(xv.y, gv.y, xh.y, gp.y); one(xv.z, gv.z, xh.z, gp.z); one(xv.w, gv.w, xh.w, gp.w);
+        s1 = s1_keep; s2 = s2_keep;
+      }
+      reinterpret_cast<float4*>(out)[i] = make_float4(fin(xh.x, gp.x), fin(xh.y, gp.y), fin(xh.z, gp.z), fin(xh.w, gp.w));
+    }
+  } else {
+    for (int i = tid; i < len; i += kThreads) {
+      float xh, gp;
+      if (RESIDENT) { xh = bx[i]; gp = bg[i]; }
+      else { const float s1_keep = s1, s2_keep = s2; one(px[i], pg[i], xh, gp); s1 = s1_keep; s2 = s2_keep; }
+      out[i] = fin(xh, gp);
+    }
+  }
+  if (cr == 0 && tid == 0) { dgamma_part[plane] = (float)t.b; dbeta_part[plane] = (float)t.a; }
+  if (cs > 1) cluster.sync();
+}
+
+// slice geometry: the smallest cluster whose slice fits `want` bytes per buffer set, else the largest cluster if it
+// fits `cap`, else non-resident (slices are still spread over an 8-CTA cluster so one plane keeps 8 SMs busy)
+struct Geo { int cs, slice; bool resident; size_t smem; };
+Geo pick_geo(int HW, int nbuf, int max_smem_optin) {
+  static const int want_kb = getenv("MRFP_IN_SLICE_KB") ? atoi(getenv("MRFP_IN_SLICE_KB")) : 72;
+  const size_t want = (size_t)(want_kb > 0 ? want_kb : 72) << 10;
+  const size_t cap = (size_t)max_smem_optin - 2048;              // static shared memory of the kernels
+  Geo g{};
+  for (int pass = 0; pass < 2; ++pass) {
+    const size_t lim = pass == 0 ? (want < cap ? want : cap) : cap;
+    for (int cs = 1; cs <= kMaxCluster; cs *= 2) {
+      const int slice = (int)align_up((size_t)(HW + cs - 1) / cs, 4);
+      const size_t bytes = (size_t)slice * 4 * nbuf;
+      if (bytes <= lim && slice <= kMaxChunks * kChunkElems) {
+        g.cs = cs; g.slice = slice; g.resident = true; g.smem = bytes;
+        return g;
+      }
+    }
+  }
+  g.cs = HW >= 8 * 16384 ? kMaxCluster : 1;
+  g.slice = (int)align_up((size_t)(HW + g.cs - 1) / g.cs, 4);
+  g.resident = false; g.smem = 0;
+  return g;
+}
+
+template <typename K, typename... Args>
+cudaError_t launch_cluster(K kern, long long planes, const Geo& g, cudaStream_t s, Args... args) {
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem);
+  if (e != cudaSuccess) return e;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(planes * g.cs)); cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = g.smem; cfg.stream = s;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = (unsigned)g.cs; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kern, args...);
+}
+
+}  // namespace
+}  // namespace mrfp
+
+using namespace mrfp;
+
+extern "C" int mrfp_instnorm_fwd_f32(const float* x, const float* gamma, const float* beta, float* y, float* mean,
+                                     float* invstd, double* psum, int N, int C, int HW, float eps, int relu, void* stream) {
+  if (!x || !y || !mean || !invstd) return MRFP_ERR_NULL_POINTER;
+  if (N <= 0 || C <= 0 || HW <= 0 || (long long)N * C > (1ll << 28)) return MRFP_ERR_BAD_SHAPE;
+  if (psum && ((uintptr_t)psum & 7)) return MRFP_ERR_WORKSPACE;
+  DeviceInfo di;
+  int rc = get_device_info(&di);
+  if (rc) return rc;
+  const bool vec = (HW & 3) == 0 && (((uintptr_t)x | (uintptr_t)y) & 15) == 0;
+  const Geo g = pick_geo(HW, 1, di.max_smem_optin);
+  cudaStream_t s = (cudaStream_t)stream;
+  const long long planes = (long long)N * C;
+  cudaError_t e;
+  if (g.resident)
+    e = vec ? launch_cluster(instnorm_fwd_kernel<true, true>, planes, g, s, x, gamma, beta, y, mean, invstd, psum, C, HW, eps, relu, g.slice)
+            : launch_cluster(instnorm_fwd_kernel<false, true>, planes, g, s, x, gamma, beta, y, mean, invstd, psum, C, HW, eps, relu, g.slice);
+  else
+    e = vec ? launch_cluster(instnorm_fwd_kernel<true, false>, planes, g, s, x, gamma, beta, y, mean, invstd, psum, C, HW, eps, relu, g.slice)
+            : launch_cluster(instnorm_fwd_kernel<false, false>, planes, g, s, x, gamma, beta, y, mean, invstd, psum, C, HW, eps, relu, g.slice);
+  MRFP_CUDA_TRY(e);
+  return MRFP_OK;
+}
+
+extern "C" int mrfp_instnorm_bwd_f32(const float* gy, const float* x, const float* gamma, const float* beta,
+                                     const float* mean, const float* invstd, float* gx, float* dgamma_part,
+                                     float* dbeta_part, int N, int C, int HW, int relu, void* stream) {
+  if (!gy || !x || !mean || !invstd || !gx || !dgamma_part || !dbeta_part) return MRFP_ERR_NULL_POINTER;
+  if (N <= 0 || C <= 0 || HW <= 0 || (long long)N * C > (1ll << 28)) return MRFP_ERR_BAD_SHAPE;
+  DeviceInfo di;
+  int rc = get_device_info(&di);
+  if (rc) return rc;
+  const bool vec = (HW & 3) == 0 && (((uintptr_t)x | (uintptr_t)gy | (uintptr_t)gx) & 15) == 0;
+  const Geo g = pick_geo(HW, 2, di.max_smem_optin);
+  cudaStream_t s = (cudaStream_t)stream;
+  const long long planes = (long long)N * C;
+  cudaError_t e;
+  if (g.resident)
+    e = vec ? launch_cluster(instnorm_bwd_kernel<true, true>, planes, g, s, gy, x, gamma, beta, mean, invstd, gx, dgamma_part, dbeta_part, C, HW, relu, g.slice)
+            : launch_cluster(instnorm_bwd_kernel<false, true>, planes, g, s, gy, x, gamma, beta, mean, invstd, gx, dgamma_part, dbeta_part, C, HW, relu, g.slice);
+  else
+    e = vec ? launch_cluster(instnorm_bwd_kernel<true, false>, planes, g, s, gy, x, gamma, beta, mean, invstd, gx, dgamma_part, dbeta_part, C, HW, relu, g.slice)
+            : launch_cluster(instnorm_bwd_kernel<false, false>, planes, g, s, gy, x, gamma, beta, mean, invstd, gx, dgamma_part, dbeta_part, C, HW, relu, g.slice);
+  MRFP_CUDA_TRY(e);
+  return MRFP_OK;
+}

@@ -1,0 +1,78 @@
+"""InstanceNorm2d(affine) + ReLU of the trunk next to the MRFP insertion points, on the sm_100a cluster kernels.
+
+Host-side mirror of `nn.InstanceNorm2d(C, affine=True)` followed by `nn.ReLU` as the reference's trunk applies
+them with wt_layer=[0,0,4,4,4,0,0] (/root/reference/network/Resnet.py:534-536 + :596-598 stem;
+:176-178 + :218-225 last Bottleneck of layer1 and layer2) — SURVEY.md §8f-3.  `nn.InstanceNorm2d` keeps no running
+statistics by default, so training and eval compute the same thing.  The layer1 instance is the producer of NP+
+call 2 (deepv3.py:334-335): `want_plane_sums=True` makes the same pass leave sum_hw of its output per plane.
+"""
+import torch
+
+from . import _lib
+
+
+def _stream_ptr(t: torch.Tensor) -> int:
+    return torch.cuda.current_stream(t.device).cuda_stream
+
+
+class _InstNormReluFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, weight, bias, eps, relu, want_plane_sums):
+        lib = _lib.load()
+        if not x.is_cuda or x.dtype != torch.float32:
+            raise _lib.MrfpError("instance_norm_relu needs a CUDA fp32 tensor (no CPU fallback)")
+        n, c, h, w = x.shape
+        xc = x.contiguous()
+        wt = None if weight is None else weight.detach().to(torch.float32).contiguous()
+        bs = None if bias is None else bias.detach().to(torch.float32).contiguous()
+        y = torch.empty_like(xc)
+        mean = torch.empty((n, c), device=x.device, dtype=torch.float32)
+        invstd = torch.empty((n, c), device=x.device, dtype=torch.float32)
+        psum = torch.empty((n, c), device=x.device, dtype=torch.float64) if want_plane_sums else None
+        with torch.cuda.device(x.device):
+            rc = lib.mrfp_instnorm_fwd_f32(xc.data_ptr(), None if wt is None else wt.data_ptr(),
+                                           None if bs is None else bs.data_ptr(), y.data_ptr(), mean.data_ptr(),
+                                           invstd.data_ptr(), None if psum is None else psum.data_ptr(),
+                                           n, c, h * w, float(eps), int(bool(relu)), _stream_ptr(xc))
+        _lib.check(rc, "mrfp_instnorm_fwd_f32")
+        ctx.save_for_backward(xc, wt, bs, mean, invstd)
+        ctx.relu = bool(relu)
+        ctx.has_affine = (weight is not None, bias is not None)
+        if psum is None:
+            psum = torch.empty(0, device=x.device, dtype=torch.float64)
+        ctx.mark_non_differentiable(psum)
+        return y, psum
+
+    @staticmethod
+    def backward(ctx, gy, _gpsum):
+        lib = _lib.load()
+        x, wt, bs, mean, invstd = ctx.saved_tensors
+        n, c, h, w = x.shape
+        g = gy.contiguous()
+        gx = torch.empty_like(x)
+        dg = torch.empty((n, c), device=x.device, dtype=torch.float32)
+        db = torch.empty((n, c), device=x.device, dtype=torch.float32)
+        with torch.cuda.device(x.device):
+            rc = lib.mrfp_instnorm_bwd_f32(g.data_ptr(), x.data_ptr(), None if wt is None else wt.data_ptr(),
+                                           None if bs is None else bs.data_ptr(), mean.data_ptr(), invstd.data_ptr(),
+                                           gx.data_ptr(), dg.data_ptr(), db.data_ptr(), n, c, h * w, int(ctx.relu),
+                                           _stream_ptr(x))
+        _lib.check(rc, "mrfp_instnorm_bwd_f32")
+        gw = dg.sum(0) if ctx.has_affine[0] and ctx.needs_input_grad[1] else None
+        gb = db.sum(0) if ctx.has_affine[1] and ctx.needs_input_grad[2] else None
+        return gx, gw, gb, None, None, None
+
+
+def instance_norm_relu(x, weight=None, bias=None, eps=1e-5, relu=True, want_plane_sums=False):
+    """relu(F.instance_norm(x, weight=weight, bias=bias, eps=eps)) in one on-chip pass per plane.
+    Returns y, or (y, psum) with psum[n, c] = sum_hw y (float64) when want_plane_sums."""
+    y, psum = _InstNormReluFn.apply(x, weight, bias, eps, relu, want_plane_sums)
+    return (y, psum) if want_plane_sums else y
+
+
+def module_instance_norm_relu(module: torch.nn.InstanceNorm2d, x, relu=True, want_plane_sums=False):
+    """The fused op with the parameters of an `nn.InstanceNorm2d` module (state_dict keys unchanged).  Modules that
+    track running statistics are not what the reference builds (Resnet.py:176-178, :534-536) and are refused."""
+    if module.track_running_stats:
+        raise _lib.MrfpError("instance_norm_relu: track_running_stats=True is not supported")
+    return instance_norm_relu(x, module.weight, module.bias, module.eps, relu, want_plane_sums)

@@ -24,7 +24,12 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from . import hrfp as _hrfp
+from . import instnorm as _instnorm
 from . import npplus as _npplus
+
+# the trunk's InstanceNorm2d + ReLU pairs next to the insertion points run on the on-chip plane kernels
+# (same result, forward 1R+1W); MRFP_FUSE_INSTNORM=0: ATen
+FUSE_INSTNORM = os.environ.get("MRFP_FUSE_INSTNORM", "1") != "0"
 
 HRFP_CONVS = ("OClayer1", "OClayer2", "OClayer3", "OClayer4",
               "OCdeclayer1", "OCdeclayer2", "OCdeclayer3", "OCdeclayer4")
@@ -148,6 +153,13 @@ class Bottleneck(nn.Module):
         out = self.relu(self.bn2(self.conv2(out)))
         out = self.bn3(self.conv3(out))
         out = out + (x if self.downsample is None else self.downsample(x))
+        if self.has_in and FUSE_INSTNORM and out.is_cuda and out.dtype == torch.float32:
+            # IN + ReLU in one on-chip pass per plane; for layer1's last block also the plane sums NP+ call 2 needs
+            if self.emit_plane_sums and self.training:
+                out, self.plane_sums = _instnorm.module_instance_norm_relu(self.instance_norm_layer, out, True, True)
+                return out
+            self.plane_sums = None
+            return _instnorm.module_instance_norm_relu(self.instance_norm_layer, out, True)
         if self.has_in:
             out = self.instance_norm_layer(out)
         if self.emit_plane_sums and out.is_cuda and self.training:
@@ -232,12 +244,19 @@ class MRFPPlus(nn.Module, MRFPMixin):
         self.whitening = False
         self.three_input_layer = False
 
+    def _stem(self, x):
+        """layer0 = conv7x7 -> InstanceNorm2d(64, affine) -> ReLU -> maxpool (Resnet.py:591-599)."""
+        if FUSE_INSTNORM and x.is_cuda and x.dtype == torch.float32:
+            conv, inorm, _, pool = self.layer0
+            return pool(_instnorm.module_instance_norm_relu(inorm, conv(x), True))
+        return self.layer0(x)
+
     def forward(self, x, gts=None, training=True):
         p, p2, p3 = random.random(), random.random(), random.random()       # deepv3.py:281-283
         h, w = x.shape[2:]
         if training and p < 0.5:
             self.reinit_hrfp()                                              # deepv3.py:290-306
-        xp = self.layer0(x)                                                 # deepv3.py:309-316
+        xp = self._stem(x)                                                  # deepv3.py:309-316
         x, ocout_dec = self.mrfp_stem(xp, h, w, training, p, p2, p3)        # deepv3.py:317-330
         last = self.layer1[-1]
         last.emit_plane_sums = bool(training and p2 < 0.5 and self.fuse_layer1_np)

@@ -318,3 +318,43 @@ def bilinear_align_corners(x: np.ndarray, out_h: int, out_w: int) -> np.ndarray:
 def hrfp_plus_add(dec1: np.ndarray, ocout_dec: np.ndarray) -> np.ndarray:
     """deepv3.py:356-357."""
     return bilinear_align_corners(dec1, ocout_dec.shape[2], ocout_dec.shape[3]) + ocout_dec
+
+
+# --------------------------------------------------------------------------------------
+# InstanceNorm2d(affine=True) + ReLU of the trunk (SURVEY.md 8f-3) — network/Resnet.py:176-178 + :218-225 (last
+# Bottleneck of layer1 / layer2, iw == 4) and :534-536 + :596-598 (stem, wt_layer[2] == 4).  nn.InstanceNorm2d
+# semantics: per-(n, c) plane, biased variance, eps inside the square root, no running statistics.
+# --------------------------------------------------------------------------------------
+IN_EPS = 1e-5          # nn.InstanceNorm2d default
+
+
+def instance_norm_relu_forward(x: np.ndarray, gamma: np.ndarray, beta: np.ndarray, eps: float = IN_EPS, relu: bool = True):
+    """Returns (y, mean (N,C), invstd (N,C), psum (N,C) = sum_hw y)."""
+    x = np.asarray(x, dtype=np.float64)
+    mean = x.mean(axis=(2, 3))
+    var = ((x - mean[:, :, None, None]) ** 2).mean(axis=(2, 3))
+    invstd = 1.0 / np.sqrt(var + eps)
+    y = (x - mean[:, :, None, None]) * invstd[:, :, None, None] * np.asarray(gamma, np.float64)[None, :, None, None] \
+        + np.asarray(beta, np.float64)[None, :, None, None]
+    if relu:
+        y = np.maximum(y, 0.0)
+    return y, mean, invstd, y.sum(axis=(2, 3))
+
+
+def instance_norm_relu_backward(gy: np.ndarray, x: np.ndarray, gamma: np.ndarray, beta: np.ndarray, eps: float = IN_EPS,
+                                relu: bool = True):
+    """Closed-form backward of relu(IN(x)): returns (gx, d_gamma (C), d_beta (C)).  ReLU passes gradient where y > 0
+    (threshold_backward)."""
+    x = np.asarray(x, dtype=np.float64)
+    g = np.asarray(gy, dtype=np.float64).copy()
+    gm = np.asarray(gamma, np.float64)[None, :, None, None]
+    mean = x.mean(axis=(2, 3), keepdims=True)
+    var = ((x - mean) ** 2).mean(axis=(2, 3), keepdims=True)
+    invstd = 1.0 / np.sqrt(var + eps)
+    xh = (x - mean) * invstd
+    if relu:
+        g[(xh * gm + np.asarray(beta, np.float64)[None, :, None, None]) <= 0.0] = 0.0
+    m1 = g.mean(axis=(2, 3), keepdims=True)
+    m2 = (g * xh).mean(axis=(2, 3), keepdims=True)
+    gx = gm * invstd * (g - m1 - xh * m2)
+    return gx, (g * xh).sum(axis=(0, 2, 3)), g.sum(axis=(0, 2, 3))

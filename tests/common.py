@@ -66,3 +66,16 @@ def fill_state_dict(model, seed: int):
                 fan_in = int(np.prod(shape[1:]))
                 v = rng.standard_normal(shape) * math.sqrt(2.0 / fan_in)
             t.copy_(torch.from_numpy(v.astype(np.float32)))
+
+
+def make_in_case(seed: int, shape):
+    """Inputs of one InstanceNorm2d(affine)+ReLU case: pre-norm features of both signs with channel-varying offsets,
+    gamma ~ N(1, 0.3) (some negative via a sign flip), beta ~ N(0, 0.3), upstream gradient ~ N(0, 1)."""
+    rng = np.random.default_rng(seed)
+    n, c, h, w = shape
+    x = (rng.standard_normal(shape) * rng.uniform(0.5, 2.0, size=(1, c, 1, 1)) + 3.0 * rng.standard_normal((1, c, 1, 1))).astype(np.float32)
+    gamma = (1.0 + 0.3 * rng.standard_normal(c)).astype(np.float32)
+    gamma[::5] *= -1.0
+    beta = (0.3 * rng.standard_normal(c)).astype(np.float32)
+    gy = rng.standard_normal(shape).astype(np.float32)
+    return x, gamma, beta, gy

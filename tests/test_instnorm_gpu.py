@@ -1,0 +1,118 @@
+"""InstanceNorm2d(affine)+ReLU cluster kernels (through the C ABI) vs the numpy oracle, the
+reference-generated fixtures and ATen's own F.instance_norm on the device."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import mrfp_oracle as O
+from tests.common import GOLDEN, make_in_case
+
+pytestmark = pytest.mark.gpu
+
+# fp32 tolerances, relative to max|ref|: 2e-5 forward, 1e-4 input gradient (away from ReLU-mask ties), 1e-3 parameter gradients
+FWD_TOL, BWD_TOL, PAR_TOL = 2e-5, 1e-4, 1e-3
+
+
+def _run(x, gamma, beta, gy, relu=True, want_sums=False):
+    from mrfp_b200.instnorm import instance_norm_relu
+    xt = torch.from_numpy(x).cuda().requires_grad_(True)
+    wt = torch.from_numpy(gamma).cuda().requires_grad_(True)
+    bt = torch.from_numpy(beta).cuda().requires_grad_(True)
+    out = instance_norm_relu(xt, wt, bt, 1e-5, relu, want_sums)
+    y, psum = out if want_sums else (out, None)
+    y.backward(torch.from_numpy(gy).cuda())
+    return (y.detach().cpu().numpy(), xt.grad.cpu().numpy(), wt.grad.cpu().numpy(), bt.grad.cpu().numpy(),
+            None if psum is None else psum.cpu().numpy())
+
+
+def _check(x, gamma, beta, gy, got, relu=True):
+    y, gx, gw, gb, psum = got
+    ry, _, _, rps = O.instance_norm_relu_forward(x, gamma, beta, relu=relu)
+    rgx, rgw, rgb = O.instance_norm_relu_backward(gy, x, gamma, beta, relu=relu)
+    assert np.abs(y - ry).max() <= FWD_TOL * max(1.0, np.abs(ry).max())
+    pre = O.instance_norm_relu_forward(x, gamma, beta, relu=False)[0]
+    far = np.abs(pre) > 1e-4 if relu else np.ones_like(pre, dtype=bool)
+    assert np.abs(gx - rgx)[far].max() <= BWD_TOL * np.abs(rgx).max()
+    # parameter gradients: elements whose pre-activation is within 1e-4 of the ReLU threshold may fall on either side
+    # in fp32 vs the fp64 oracle; each such element can move d_beta[c] by |gy| and d_gamma[c] by |gy * xhat|
+    near = (~far).astype(np.float64)
+    _, mean, invstd, _ = O.instance_norm_relu_forward(x, gamma, beta, relu=False)
+    xh = (x.astype(np.float64) - mean[:, :, None, None]) * invstd[:, :, None, None]
+    slack_b = (np.abs(gy) * near).sum(axis=(0, 2, 3))
+    slack_w = (np.abs(gy * xh) * near).sum(axis=(0, 2, 3))
+    cnt = x.shape[0] * x.shape[2] * x.shape[3]
+    assert (np.abs(gw - rgw) <= PAR_TOL * max(1.0, np.abs(rgw).max()) + 1e-5 * cnt ** 0.5 + slack_w).all()
+    assert (np.abs(gb - rgb) <= PAR_TOL * max(1.0, np.abs(rgb).max()) + 1e-5 * cnt ** 0.5 + slack_b).all()
+    if psum is not None:
+        np.testing.assert_allclose(psum, rps, rtol=1e-5, atol=1e-3)
+
+
+@pytest.mark.parametrize("name", list("abcd"))
+def test_vs_reference_fixture(name):
+    g = np.load(os.path.join(GOLDEN, "instnorm.npz"))
+    shape = tuple(int(v) for v in g[f"{name}_shape"])
+    x, gamma, beta, gy = make_in_case(400 + "abcd".index(name), shape)
+    y, gx, gw, gb, _ = _run(x, gamma, beta, gy)
+    assert np.abs(y - g[f"{name}_y"]).max() <= FWD_TOL * np.abs(g[f"{name}_y"]).max()
+    far = np.abs(O.instance_norm_relu_forward(x, gamma, beta, relu=False)[0]) > 1e-4
+    assert np.abs(gx - g[f"{name}_gx"])[far].max() <= BWD_TOL * np.abs(g[f"{name}_gx"]).max()
+    np.testing.assert_allclose(gw, g[f"{name}_gw"], rtol=PAR_TOL, atol=PAR_TOL)
+    np.testing.assert_allclose(gb, g[f"{name}_gb"], rtol=PAR_TOL, atol=PAR_TOL)
+
+
+# the three sites of the R50 trunk at a 768^2 crop (batch 2): stem 64x384^2 (8-CTA clusters), layer1 256x192^2 (2 / 4),
+# layer2 512x96^2 (single CTA); odd / unaligned planes (scalar path); 1x1 planes; a plane larger than an 8-CTA cluster
+# holds (non-resident path, e.g. the stem at a 1024x2048 evaluation image)
+@pytest.mark.parametrize("shape", [(2, 64, 384, 384), (2, 256, 192, 192), (2, 512, 96, 96), (3, 5, 33, 31), (2, 3, 1, 1),
+                                   (4, 7, 2, 2), (2, 6, 101, 100), (1, 2, 512, 1024), (1, 2, 511, 1023), (2, 16, 48, 48)])
+@pytest.mark.parametrize("relu", [True, False])
+def test_vs_oracle(shape, relu):
+    if not relu and shape[2] * shape[3] > 200 * 200:
+        pytest.skip("large planes are covered by the ReLU variant")
+    x, gamma, beta, gy = make_in_case(11, shape)
+    _check(x, gamma, beta, gy, _run(x, gamma, beta, gy, relu, want_sums=True), relu)
+
+
+def test_matches_aten_on_device():
+    """Same inputs through ATen's F.instance_norm + relu on the GPU (the op sequence being replaced)."""
+    import torch.nn.functional as F
+    from mrfp_b200.instnorm import instance_norm_relu
+    torch.manual_seed(3)
+    x = (torch.randn(4, 256, 192, 192, device="cuda") * 2 + 1).requires_grad_(True)
+    w = (1 + 0.2 * torch.randn(256, device="cuda")).requires_grad_(True)
+    b = (0.2 * torch.randn(256, device="cuda")).requires_grad_(True)
+    gy = torch.randn_like(x)
+    ref = F.relu(F.instance_norm(x, weight=w, bias=b, eps=1e-5))
+    rgx, rgw, rgb = torch.autograd.grad(ref, [x, w, b], gy)
+    y, psum = instance_norm_relu(x, w, b, 1e-5, True, True)
+    gx, gw, gb = torch.autograd.grad(y, [x, w, b], gy)
+    assert (y - ref).abs().max().item() <= 2e-5 * ref.abs().max().item()
+    pre = F.instance_norm(x, weight=w, bias=b, eps=1e-5).detach()
+    far = pre.abs() > 1e-4
+    assert ((gx - rgx).abs() * far).max().item() <= 1e-4 * rgx.abs().max().item()
+    # parameter gradients: an element within 1e-4 of the ReLU threshold may fall on either side (see _check)
+    xh = F.instance_norm(x.detach(), eps=1e-5)
+    slack_b = (gy.abs() * ~far).sum((0, 2, 3))
+    slack_w = ((gy * xh).abs() * ~far).sum((0, 2, 3))
+    assert ((gw - rgw).abs() <= 1e-3 * rgw.abs().max() + 2e-2 + slack_w).all()
+    assert ((gb - rgb).abs() <= 1e-3 * rgb.abs().max() + 2e-2 + slack_b).all()
+    torch.testing.assert_close(psum, ref.double().sum((2, 3)), rtol=1e-5, atol=1e-2)
+
+
+def test_deterministic_and_no_affine():
+    from mrfp_b200.instnorm import instance_norm_relu
+    x = torch.randn(2, 8, 192, 192, device="cuda")
+    a = instance_norm_relu(x)
+    b = instance_norm_relu(x)
+    assert torch.equal(a, b)
+    ref = torch.relu(torch.nn.functional.instance_norm(x))
+    assert (a - ref).abs().max().item() <= 2e-5 * ref.abs().max().item()
+
+
+def test_rejects_cpu_tensor():
+    from mrfp_b200 import _lib
+    from mrfp_b200.instnorm import instance_norm_relu
+    with pytest.raises(_lib.MrfpError):
+        instance_norm_relu(torch.randn(1, 2, 4, 4))

@@ -195,3 +195,22 @@ def test_torch_port_hrfp_vs_reference(g_hrfp):
     torch.autograd.backward([o, d], [g1, g2])
     assert np.abs(o.detach().numpy() - g_hrfp["sq_ocout"]).max() <= 1e-4 * np.abs(g_hrfp["sq_ocout"]).max()
     assert np.abs(xp.grad.numpy() - g_hrfp["sq_gx_both"]).max() <= 1e-3 * np.abs(g_hrfp["sq_gx_both"]).max()
+
+
+@pytest.mark.parametrize("name", list("abcd"))
+def test_instance_norm_relu_vs_reference_fixture(name):
+    """Oracle IN+ReLU against the reference's own Bottleneck(iw=4) layers (tests/golden/make_golden_instnorm.py)."""
+    from tests.common import make_in_case
+    g = np.load(os.path.join(GOLDEN, "instnorm.npz"))
+    shape = tuple(int(v) for v in g[f"{name}_shape"])
+    x, gamma, beta, gy = make_in_case(400 + "abcd".index(name), shape)
+    y, mean, invstd, psum = O.instance_norm_relu_forward(x, gamma, beta)
+    gx, gw, gb = O.instance_norm_relu_backward(gy, x, gamma, beta)
+    np.testing.assert_allclose(y, g[f"{name}_y"], rtol=2e-5, atol=2e-5)
+    # the fp32 reference and the fp64 oracle may disagree on the ReLU mask where |y| ~ 1e-7: compare away from it
+    far = np.abs(O.instance_norm_relu_forward(x, gamma, beta, relu=False)[0]) > 1e-4
+    scale = np.abs(g[f"{name}_gx"]).max()
+    assert np.abs(gx - g[f"{name}_gx"])[far].max() <= 1e-4 * scale
+    np.testing.assert_allclose(gw, g[f"{name}_gw"], rtol=1e-3, atol=1e-3)
+    np.testing.assert_allclose(gb, g[f"{name}_gb"], rtol=1e-3, atol=1e-3)
+    np.testing.assert_allclose(psum, y.sum(axis=(2, 3)))
