@@ -164,9 +164,10 @@ def _use_reference_ops(model):
     model.Normalization_Perturbation_Plus = np_eager
     model.mrfp_stem = stem
     model._plus_add = lambda a, d: torch.add(d, a)
+    model.fuse_layer1_np = False        # NP+ call 2: the eager sequence above, not the producer-fused kernels
 
 
-def train_bench(world, rank, dev, steps=8, warmup=3, global_batch=16, reference_ops=False):
+def train_bench(world, rank, dev, steps=8, warmup=3, global_batch=16, reference_ops=False, trunk="resnet-50"):
     """BASELINE config[2]: MRFP+ DeepLabV3+/ResNet-50 training step (main.py:845-871 recipe) on synthetic GTAV-shaped
     768x768 crops, 19 classes, global batch 16 sharded over the ranks (DDP, NCCL gradient all-reduce is the only
     collective; BatchNorm stays per-rank)."""
@@ -181,7 +182,9 @@ def train_bench(world, rank, dev, steps=8, warmup=3, global_batch=16, reference_
     nb = hi - lo
     D.seed_rank_streams(3, rank)
     random.seed(100 + rank)
-    model = MRFPPlus(19, criterion=torch.nn.CrossEntropyLoss(ignore_index=255)).to(dev)
+    from mrfp_b200 import model as M
+    M.FUSE_INSTNORM = (not reference_ops) and os.environ.get("MRFP_FUSE_INSTNORM", "1") != "0"   # reference arm: ATen InstanceNorm + ReLU
+    model = MRFPPlus(19, trunk=trunk, criterion=torch.nn.CrossEntropyLoss(ignore_index=255)).to(dev)
     if reference_ops:
         _use_reference_ops(model)
     if world > 1:
@@ -212,12 +215,14 @@ def train_bench(world, rank, dev, steps=8, warmup=3, global_batch=16, reference_
     e1.record()
     torch.cuda.synchronize()
     ms = D.max_over_ranks(e0.elapsed_time(e1), dev)
-    out = {"metric": "deeplabv3plus_r50_mrfp_plus_train_throughput", "mrfp_ops": "reference eager ATen/cuDNN" if reference_ops else "libmrfp_b200", "value": global_batch * steps / (ms * 1e-3), "unit": "img/s",
+    out = {"metric": "deeplabv3plus_%s_mrfp_plus_train_throughput" % {"resnet-50": "r50", "resnet-101": "r101"}[trunk], "mrfp_ops": "reference eager ATen/cuDNN" if reference_ops else "libmrfp_b200", "value": global_batch * steps / (ms * 1e-3), "unit": "img/s",
            "global_batch": global_batch, "per_gpu_batch": nb, "steps": steps, "warmup": warmup, "ms_per_step": ms / steps,
            "parallelism": f"ddp{world}", "loss_finite": bool(torch.isfinite(loss).item()),
+           "instance_norm": "mrfp_instnorm cluster kernels" if M.FUSE_INSTNORM else "ATen",
            "precision": "fp32 host model (cuDNN TF32 default, as the reference on this torch; cudnn.benchmark=%s), bf16 tcgen05 HRFP, fp32 NP+" % torch.backends.cudnn.benchmark,
            "gates": "natural Bernoulli(0.5) x3 per step (python random, seed 100+rank)", "data": "synthetic U[0,255) images, 19 classes, 5% ignore"}
     del model, opt, img, lab
+    M.FUSE_INSTNORM = os.environ.get("MRFP_FUSE_INSTNORM", "1") != "0"
     torch.cuda.empty_cache()
     return out
 
@@ -365,6 +370,11 @@ def run_ours(args):
             train = train_bench(world, rank, dev)
             ref_t = train_bench(world, rank, dev, steps=4, warmup=2, reference_ops=True)
             train["same_step_with_reference_mrfp_ops"] = {k: ref_t[k] for k in ("value", "unit", "ms_per_step", "steps", "mrfp_ops")}
+            if os.environ.get("MRFP_BENCH_TRAIN_R101", "1") != "0":
+                # BASELINE config[3] per-GPU shard: ResNet-101 host, global batch 32 at 8 GPUs = 4 per GPU
+                r101 = train_bench(world, rank, dev, steps=4, warmup=2, global_batch=4 * world, trunk="resnet-101")
+                train["resnet101_config3_shard"] = {k: r101[k] for k in ("metric", "value", "unit", "ms_per_step", "steps", "global_batch",
+                                                                         "per_gpu_batch", "loss_finite")}
         except Exception as e:          # noqa: BLE001  (e.g. out of memory on a smaller GPU): report, do not hide
             train = {"error": repr(e)[:300]}
 
@@ -395,7 +405,8 @@ def run_ours(args):
             a.record(); fn(); b.record(); torch.cuda.synchronize()
             if i >= 3:
                 ts.append(a.elapsed_time(b))
-        return sum(ts) / len(ts)
+        ts.sort()
+        return ts[len(ts) // 2]          # median: one preempted launch must not move a per-kernel figure
 
     np_rows = {}
     for name, x_t, (al, ep) in (("npplus_64ch", xp, draws[0]), ("npplus_256ch", f2, draws[1])):
@@ -448,6 +459,31 @@ def run_ours(args):
         del pre, y_r, out_p
     except Exception as e_:          # noqa: BLE001
         roof_np["producer_fused"] = {"error": repr(e_)[:200]}
+
+    # InstanceNorm2d(affine)+ReLU of the trunk next to the insertion points: layer1's site, the producer of NP+ call 2
+    roof_in = None
+    try:
+        xin = torch.randn(n, 256, XH, XW, device=dev) * 2 + 1
+        gin_ = torch.randn_like(xin)
+        w_in = 1 + 0.2 * torch.randn(256, device=dev); b_in = 0.2 * torch.randn(256, device=dev)
+        y_in = torch.empty_like(xin); gx_in = torch.empty_like(xin)
+        m_in = torch.empty(n, 256, device=dev); i_in = torch.empty(n, 256, device=dev)
+        dg_in = torch.empty(n, 256, device=dev); db_in = torch.empty(n, 256, device=dev)
+        ps_in = torch.empty(n, 256, device=dev, dtype=torch.float64)
+        t_if = time_launch(lambda: _lib.check(lib.mrfp_instnorm_fwd_f32(xin.data_ptr(), w_in.data_ptr(), b_in.data_ptr(), y_in.data_ptr(), m_in.data_ptr(),
+                                                                        i_in.data_ptr(), ps_in.data_ptr(), n, 256, XH * XW, 1e-5, 1, st), "instnorm fwd"))
+        t_ib = time_launch(lambda: _lib.check(lib.mrfp_instnorm_bwd_f32(gin_.data_ptr(), xin.data_ptr(), w_in.data_ptr(), b_in.data_ptr(), m_in.data_ptr(),
+                                                                        i_in.data_ptr(), gx_in.data_ptr(), dg_in.data_ptr(), db_in.data_ptr(), n, 256,
+                                                                        XH * XW, 1, st), "instnorm bwd"))
+        t_ia = time_launch(lambda: F.relu(F.instance_norm(xin, weight=w_in, bias=b_in)))
+        nb_in = xin.numel() * 4
+        roof_in = {"kernel": "instnorm_fwd_kernel / instnorm_bwd_kernel on (8,256,192,192), ReLU and NP+ plane sums fused", "bound": "hbm",
+                   "fwd_us": t_if * 1e3, "fwd_gbs": 2 * nb_in / t_if / 1e6, "fwd_frac": 2 * nb_in / t_if / 1e6 / hbm_peak,
+                   "bwd_us": t_ib * 1e3, "bwd_gbs": 3 * nb_in / t_ib / 1e6, "bwd_frac": 3 * nb_in / t_ib / 1e6 / hbm_peak,
+                   "algorithmic_bytes": {"fwd": 2 * nb_in, "bwd": 3 * nb_in}, "aten_instance_norm_relu_fwd_us": t_ia * 1e3, "peak": hbm_peak}
+        del xin, gin_, y_in, gx_in
+    except Exception as e_:          # noqa: BLE001
+        roof_in = {"error": repr(e_)[:200]}
 
     # tcgen05 conv kernels of the chain, forward shapes (debug hook = the same kernel the chain launches)
     import ctypes
@@ -509,7 +545,7 @@ def run_ours(args):
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
                     "pipeline": "H2D / kernels / D2H on three streams, double-buffered; every step moves its own inputs and results"},
             "gpu_launches": launches_per_step * args.steps,
-            "roofline": roofline, "roofline_npplus": roof_np, "hrfp_chain": hrfp, "train": train,
+            "roofline": roofline, "roofline_npplus": roof_np, "roofline_instnorm": roof_in, "hrfp_chain": hrfp, "train": train,
             "clocks": sampler.summary() if sampler else None}
     if base is not None:
         line["cpu_baseline"] = base

@@ -202,12 +202,13 @@ class ASPP(nn.Module):
 
 class MRFPPlus(nn.Module, MRFPMixin):
     """DeepLabV3+ / ResNet-50 (IN at the stem and at the end of layer1, layer2: wt_layer=[0,0,4,4,4,0,0]) with
-    MRFP+ applied while training."""
+    MRFP+ applied while training.  trunk="resnet-101" (BASELINE config[3]) is this repo's extension: same insertion
+    points on the reference's deep-stem ResNet-101, HRFP on its 128 stem channels."""
 
     def __init__(self, num_classes, trunk="resnet-50", criterion=None, criterion_aux=None, variant="D16",
                  wt_layer=(0, 0, 4, 4, 4, 0, 0), use_wtloss=False, math_mode=_hrfp.MATH_BF16, strict_buffers=False):
         super().__init__()
-        if trunk != "resnet-50":
+        if trunk not in ("resnet-50", "resnet-101"):
             raise ValueError("Not a valid network arch")                    # deepv3.py:177-178
         if tuple(wt_layer) != (0, 0, 4, 4, 4, 0, 0):
             raise ValueError("only the reference's wt_layer=[0,0,4,4,4,0,0] host is provided")
@@ -215,13 +216,25 @@ class MRFPPlus(nn.Module, MRFPMixin):
         self.variant, self.wt_layer, self.use_wtloss, self.trunk = variant, list(wt_layer), use_wtloss, trunk
         self.math_mode, self.strict_buffers = math_mode, strict_buffers
 
-        self.layer0 = nn.Sequential(nn.Conv2d(3, 64, 7, stride=2, padding=3, bias=False),
-                                    nn.InstanceNorm2d(64, affine=True), nn.ReLU(inplace=True),
-                                    nn.MaxPool2d(3, stride=2, padding=1))
-        self.layer1 = _make_layer(64, 64, 3, 1, True)
-        self.layer2 = _make_layer(256, 128, 4, 2, True)
-        self.layer3 = _make_layer(512, 256, 6, 2, False)
-        self.layer4 = _make_layer(1024, 512, 3, 2, False)
+        if trunk == "resnet-50":                                            # Resnet.py:519-560 (7x7 stem), [3,4,6,3]
+            stem_ch, blocks = 64, (3, 4, 6, 3)
+            self.layer0 = nn.Sequential(nn.Conv2d(3, 64, 7, stride=2, padding=3, bias=False),
+                                        nn.InstanceNorm2d(64, affine=True), nn.ReLU(inplace=True),
+                                        nn.MaxPool2d(3, stride=2, padding=1))
+        else:
+            # SURVEY.md 8f-2 (extension: the reference's MRFPPlus only builds resnet-50): the reference's ResNet-101 is the
+            # deep-stem ResNet3X3 (Resnet.py:352-433, :678-693), 128 channels at stride 4, [3,4,23,3]; wt_layer[2] == 4
+            # puts the InstanceNorm on the third stem conv (layer0 laid out as network/deepv3.py:462-471 does)
+            stem_ch, blocks = 128, (3, 4, 23, 3)
+            self.layer0 = nn.Sequential(nn.Conv2d(3, 64, 3, stride=2, padding=1, bias=False), nn.BatchNorm2d(64), nn.ReLU(inplace=True),
+                                        nn.Conv2d(64, 64, 3, stride=1, padding=1, bias=False), nn.BatchNorm2d(64), nn.ReLU(inplace=True),
+                                        nn.Conv2d(64, 128, 3, stride=1, padding=1, bias=False),
+                                        nn.InstanceNorm2d(128, affine=True), nn.ReLU(inplace=True),
+                                        nn.MaxPool2d(3, stride=2, padding=1))
+        self.layer1 = _make_layer(stem_ch, 64, blocks[0], 1, True)
+        self.layer2 = _make_layer(256, 128, blocks[1], 2, True)
+        self.layer3 = _make_layer(512, 256, blocks[2], 2, False)
+        self.layer4 = _make_layer(1024, 512, blocks[3], 2, False)
         for m in self.modules():                                            # network/Resnet.py:563-570
             if isinstance(m, nn.Conv2d):
                 nn.init.kaiming_normal_(m.weight, mode="fan_out", nonlinearity="relu")
@@ -238,17 +251,19 @@ class MRFPPlus(nn.Module, MRFPMixin):
         self.final1 = nn.Sequential(nn.Conv2d(304, 256, 3, padding=1, bias=False), nn.BatchNorm2d(256), nn.ReLU(inplace=True),
                                     nn.Conv2d(256, 256, 3, padding=1, bias=False), nn.BatchNorm2d(256), nn.ReLU(inplace=True))
         self.final2 = nn.Sequential(nn.Conv2d(256, num_classes, 1, bias=True))
-        self._build_hrfp(64)
+        self._build_hrfp(stem_ch)                                           # HRFP runs on the stem's channel count
         init_head(self.aspp, self.bot_aspp, self.bot_fine, self.final1, self.final2)
         self.eps = 1e-5
         self.whitening = False
         self.three_input_layer = False
 
     def _stem(self, x):
-        """layer0 = conv7x7 -> InstanceNorm2d(64, affine) -> ReLU -> maxpool (Resnet.py:591-599)."""
+        """layer0 = conv(s) -> ... -> InstanceNorm2d(affine) -> ReLU -> maxpool (Resnet.py:591-599; ResNet3X3: :476-494)."""
         if FUSE_INSTNORM and x.is_cuda and x.dtype == torch.float32:
-            conv, inorm, _, pool = self.layer0
-            return pool(_instnorm.module_instance_norm_relu(inorm, conv(x), True))
+            mods = list(self.layer0)
+            for m in mods[:-3]:
+                x = m(x)
+            return mods[-1](_instnorm.module_instance_norm_relu(mods[-3], x, True))
         return self.layer0(x)
 
     def forward(self, x, gts=None, training=True):

@@ -166,3 +166,70 @@ def test_gates_off_is_plain_deeplab_and_skips_hrfp():
     loss = m(x, gts, training=True)
     assert int(m.OC1_bn.num_batches_tracked) == nbt       # dead chain skipped (strict_buffers=False)
     random.setstate(state)
+
+
+# ---- trunk="resnet-101" (BASELINE config[3]): the reference's deep-stem ResNet-101 under the same hooks ----
+_R101_STEM = {"conv1": "layer0.0", "bn1": "layer0.1", "conv2": "layer0.3", "bn2": "layer0.4", "conv3": "layer0.6", "bn3": "layer0.7"}
+
+
+def test_resnet101_host_shapes():
+    from mrfp_b200.model import MRFPPlus
+    m = MRFPPlus(19, trunk="resnet-101", criterion=_criterion())
+    assert [len(l) for l in (m.layer1, m.layer2, m.layer3, m.layer4)] == [3, 4, 23, 3]
+    assert m.OClayer1.in_channels == 128 and m.OCdeclayer4.out_channels == 128 and m.OClayer4.out_channels == 256
+    assert isinstance(m.layer0[7], torch.nn.InstanceNorm2d) and m.layer0[7].num_features == 128
+    assert m.layer1[-1].has_in and m.layer2[-1].has_in and not m.layer3[-1].has_in
+    m.eval()
+    with torch.no_grad():
+        out = m(torch.rand(1, 3, 64, 64) * 255, training=False)
+    assert out.shape == (1, 19, 64, 64)
+    with pytest.raises(ValueError):
+        MRFPPlus(19, trunk="resnet-18", criterion=_criterion())
+
+
+@pytest.mark.refonly
+def test_resnet101_trunk_equals_reference_resnet101_on_cpu():
+    """layer0..layer2 (all three InstanceNorm sites) against the reference's own network/Resnet.py resnet101."""
+    from oracle.ref_shim import load_reference
+    from mrfp_b200.model import MRFPPlus
+    load_reference()
+    from network import Resnet
+    ref = Resnet.resnet101(pretrained=False, wt_layer=[0, 0, 4, 4, 4, 0, 0])
+    mine = MRFPPlus(19, trunk="resnet-101", criterion=_criterion())
+    fill_state_dict(ref, 6)
+    sd = {}
+    for k, v in ref.state_dict().items():
+        head = k.split(".")[0]
+        if head in _R101_STEM:
+            sd[_R101_STEM[head] + k[len(head):]] = v
+        elif head.startswith("layer"):
+            sd[k] = v
+    missing, unexpected = mine.load_state_dict(sd, strict=False)
+    assert not unexpected
+    assert all(not k.startswith(("layer0", "layer1", "layer2", "layer3", "layer4")) for k in missing), missing
+    ref.eval(); mine.eval()
+    x = torch.rand(2, 3, 64, 64) * 255
+    with torch.no_grad():
+        r = ref.maxpool(ref.relu3(ref.bn3(ref.conv3(ref.relu2(ref.bn2(ref.conv2(ref.relu1(ref.bn1(ref.conv1(x))))))))))
+        r = ref.layer2(ref.layer1([r, []]))[0]
+        o = mine.layer2(mine.layer1(mine._stem(x)))
+    assert torch.allclose(r, o, rtol=1e-5, atol=1e-5 * r.abs().max().item())
+
+
+@pytest.mark.gpu
+def test_resnet101_training_step_runs_all_branches():
+    """One training step of the ResNet-101 host with all three MRFP branches on: the kernels run on the 128-channel stem
+    (HRFP with NP+ call 1 folded in, IN+ReLU with plane sums -> pre-summed NP+ call 2, fused HRFP+ tail)."""
+    from mrfp_b200.model import MRFPPlus
+    torch.manual_seed(0)
+    m = MRFPPlus(19, trunk="resnet-101", criterion=_criterion()).cuda().train()
+    x = torch.rand(2, 3, 96, 128, device="cuda") * 255
+    gts = torch.randint(0, 19, (2, 96, 128), device="cuda")
+    random.seed(4)      # all three gates < 0.5 (tests/golden/known_answers.json)
+    loss = m(x, gts, training=True)
+    loss.backward()
+    assert torch.isfinite(loss)
+    assert int(m.OC1_bn.num_batches_tracked) == 1
+    for name in ("layer0.0.weight", "layer0.7.weight", "layer1.2.instance_norm_layer.weight", "final2.0.weight"):
+        g = dict(m.named_parameters())[name].grad
+        assert g is not None and torch.isfinite(g).all() and float(g.abs().sum()) > 0, name
