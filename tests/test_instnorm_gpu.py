@@ -45,8 +45,8 @@ def _check(x, gamma, beta, gy, got, relu=True):
     cnt = x.shape[0] * x.shape[2] * x.shape[3]
     assert (np.abs(gw - rgw) <= PAR_TOL * max(1.0, np.abs(rgw).max()) + 1e-5 * cnt ** 0.5 + slack_w).all()
     assert (np.abs(gb - rgb) <= PAR_TOL * max(1.0, np.abs(rgb).max()) + 1e-5 * cnt ** 0.5 + slack_b).all()
-    if psum is not None:
-        np.testing.assert_allclose(psum, rps, rtol=1e-5, atol=1e-3)
+    if psum is not None:      # a sum of fp32 outputs: error bounded relative to sum |y| (without ReLU the terms cancel to beta*HW)
+        assert (np.abs(psum - rps) <= 1e-6 * np.abs(ry).sum(axis=(2, 3)) + 1e-6).all()
 
 
 @pytest.mark.parametrize("name", list("abcd"))
