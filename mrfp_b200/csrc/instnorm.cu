@@ -321,6 +321,258 @@ Geo pick_geo(int HW, int nbuf, int max_smem_optin) {
   return g;
 }
 
+// ------------------------------------------------------------------------------------------------ persistent ring variant
+// The kernels above pay a load -> compute -> store sequence per CTA, so a CTA's HBM loads and stores never overlap
+// (131 us for (8,256,192,192) forward with one CTA per SM where the traffic alone takes ~95 us).  Here a CTA (or cluster) is PERSISTENT and
+// walks a sequence of planes: a producer lane streams 8 KiB chunks of consecutive planes into a 26-slot shared-memory
+// ring with 1-D bulk copies; the consumers run the passes of plane p over its <= 18 resident chunks while the other
+// slots already receive the head of the next plane, and every chunk's slot is handed back to the producer as soon
+// as the output pass has stored it — loads of plane p+1 run under the compute and the stores of plane p.
+// Same arithmetic, in the same order per CTA slice, as the kernels above (results are bit-identical for equal geometry).
+constexpr int kRChunk = 2048;                    // floats per ring chunk (8 KiB)
+constexpr int kRSlots = 26;                      // 208 KiB ring
+constexpr int kRMaxRes = 18;                     // chunks of the plane in work a CTA may hold (x and gy together in backward)
+constexpr int kRCons = 256;                      // consumer threads (8 warps) + one producer warp
+constexpr int kRWarps = kRCons / 32;
+
+struct RingArgs {
+  const float* x; const float* gy; const float* gamma; const float* beta;
+  float* out;                                    // forward: y; backward: gx
+  float* mean; float* invstd;                    // forward: written; backward: read
+  double* psum; float* dgamma_part; float* dbeta_part;
+  int C, HW, relu, slice, planes;
+  float eps;
+};
+
+__device__ __forceinline__ void cons_bar() { asm volatile("bar.sync 1, %0;" ::"n"(kRCons) : "memory"); }
+
+__device__ __forceinline__ Red2 cons_sum2(double a, double b, double (*s_w)[2]) {
+  a = warp_sum(a); b = warp_sum(b);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  cons_bar();
+  if (lane == 0) { s_w[warp][0] = a; s_w[warp][1] = b; }
+  cons_bar();
+  Red2 r{0.0, 0.0};
+#pragma unroll
+  for (int i = 0; i < kRWarps; ++i) { r.a += s_w[i][0]; r.b += s_w[i][1]; }
+  return r;
+}
+
+// cluster-wide sum among the consumers; the producer warp joins every cluster barrier (ring_producer_sync)
+__device__ __forceinline__ Red2 ring_cluster_sum2(cg::cluster_group& cluster, Red2 mine, double (*s_pub)[2], int& rnd) {
+  const unsigned cs = cluster.num_blocks();
+  if (cs == 1) return mine;
+  const int slot = rnd % 3;                      // a slot is rewritten only after two further cluster barriers
+  ++rnd;
+  if (threadIdx.x == 0) { s_pub[slot][0] = mine.a; s_pub[slot][1] = mine.b; }
+  cluster.sync();
+  Red2 r{0.0, 0.0};
+  for (unsigned k = 0; k < cs; ++k) {
+    const double* remote = cluster.map_shared_rank(&s_pub[slot][0], k);
+    r.a += remote[0]; r.b += remote[1];
+  }
+  return r;
+}
+
+template <bool BWD>
+__global__ void __launch_bounds__(kRCons + 32, 1)
+instnorm_ring_kernel(const RingArgs a) {
+  cg::cluster_group cluster = cg::this_cluster();
+  const unsigned cs = cluster.num_blocks(), cr = cluster.block_rank();
+  const int ncl = (int)(gridDim.x / cs), q = (int)(blockIdx.x / cs);
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  float* ring = reinterpret_cast<float*>(smem_raw);                 // [kRSlots][kRChunk]
+  __shared__ __align__(8) uint64_t full[kRSlots], empty[kRSlots];
+  __shared__ double s_w[kRWarps][2];
+  __shared__ double s_pub[3][2];
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const bool is_producer = warp == kRWarps;
+  const int begin = (int)cr * a.slice;
+  const int len = max(0, min(a.slice, a.HW - begin));
+  const int nch = (len + kRChunk - 1) / kRChunk;                    // chunks per stream of this CTA's slice
+  constexpr int NB = BWD ? 2 : 1;
+  const int F = NB * nch;                                           // ring fills per plane
+  const int H = min(F, kRSlots - F);                                // fills of the NEXT plane that fit beside the one in work
+  const int nsync = cs == 1 ? 0 : (BWD ? 1 : 2);                    // cluster barriers before the output pass
+
+  if (tid == 0) {
+    for (int s = 0; s < kRSlots; ++s) { tma::mbar_init(&full[s], 1); tma::mbar_init(&empty[s], kRWarps); }
+    tma::mbar_fence_init();
+  }
+  __syncthreads();
+
+  if (is_producer) {
+    int fill = 0;
+    auto issue = [&](int plane, int j0, int j1) {                   // fills j0..j1-1 of `plane` (lane 0 only)
+      for (int j = j0; j < j1; ++j, ++fill) {
+        const int slot = fill % kRSlots, round = fill / kRSlots;
+        if (round > 0) tma::mbar_wait(&empty[slot], (round - 1) & 1);
+        const int chunk = BWD ? (j >> 1) : j;
+        const float* base = (BWD && (j & 1)) ? a.gy : a.x;
+        const uint32_t bytes = (uint32_t)min(kRChunk, len - chunk * kRChunk) * 4u;
+        tma::mbar_expect_tx(&full[slot], bytes);
+        tma::bulk_load(ring + (size_t)slot * kRChunk, base + (long long)plane * a.HW + begin + chunk * kRChunk, bytes, &full[slot]);
+      }
+    };
+    if (lane == 0 && q < a.planes) issue(q, 0, F);
+    for (int p = q; p < a.planes; p += ncl) {
+      const int pn = p + ncl;
+      if (lane == 0 && pn < a.planes) issue(pn, 0, H);              // slots freed by the output pass of the plane before p
+      __syncwarp();
+      for (int i = 0; i < nsync; ++i) cluster.sync();               // the statistics barriers of plane p
+      if (lane == 0 && pn < a.planes) issue(pn, H, F);              // slots freed by the output pass of plane p
+      __syncwarp();
+      if (!BWD && a.psum && cs > 1) cluster.sync();                 // the plane-sum barrier after the output pass
+    }
+  } else {
+    int cfill = 0, rnd = 0;
+    for (int p = q; p < a.planes; p += ncl) {
+      const int c = p % a.C;
+      const float gm = a.gamma ? a.gamma[c] : 1.f, bt = a.beta ? a.beta[c] : 0.f;
+      const long long off = (long long)p * a.HW + begin;
+      auto slot_of = [&](int j) { return (cfill + j) % kRSlots; };
+      auto wait_fill = [&](int j) { tma::mbar_wait(&full[slot_of(j)], ((cfill + j) / kRSlots) & 1); };
+      auto release = [&](int j) {                                   // this warp is done with fill j of the plane
+        __syncwarp();
+        if (lane == 0) tma::mbar_arrive(&empty[slot_of(j)]);
+      };
+      if (!BWD) {
+        // pass 1: sum -> mean (chunk by chunk as the copies land)
+        float acc = 0.f;
+        for (int j = 0; j < nch; ++j) {
+          wait_fill(j);
+          const int n4 = min(kRChunk, len - j * kRChunk) >> 2;
+          const float4* s4 = reinterpret_cast<const float4*>(ring + (size_t)slot_of(j) * kRChunk);
+          float4 a4 = make_float4(0.f, 0.f, 0.f, 0.f);
+          for (int i = tid; i < n4; i += kRCons) { const float4 v = s4[i]; a4.x += v.x; a4.y += v.y; a4.z += v.z; a4.w += v.w; }
+          acc += (a4.x + a4.y) + (a4.z + a4.w);
+        }
+        Red2 t = ring_cluster_sum2(cluster, cons_sum2((double)acc, 0.0, s_w), s_pub, rnd);
+        const float mean = (float)(t.a / (double)a.HW);
+        // pass 2: centred squares -> invstd
+        float4 q4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int j = 0; j < nch; ++j) {
+          const int n4 = min(kRChunk, len - j * kRChunk) >> 2;
+          const float4* s4 = reinterpret_cast<const float4*>(ring + (size_t)slot_of(j) * kRChunk);
+          for (int i = tid; i < n4; i += kRCons) {
+            const float4 v = s4[i];
+            const float dx = v.x - mean, dy = v.y - mean, dz = v.z - mean, dw = v.w - mean;
+            q4.x = fmaf(dx, dx, q4.x); q4.y = fmaf(dy, dy, q4.y); q4.z = fmaf(dz, dz, q4.z); q4.w = fmaf(dw, dw, q4.w);
+          }
+        }
+        t = ring_cluster_sum2(cluster, cons_sum2((double)((q4.x + q4.y) + (q4.z + q4.w)), 0.0, s_w), s_pub, rnd);
+        const float invstd = (float)(1.0 / sqrt(t.a / (double)a.HW + (double)a.eps));
+        // pass 3: normalise, ReLU, store; hand every chunk back as soon as this warp has read it
+        const float sc = gm * invstd, lo = a.relu ? 0.f : -INFINITY;
+        float4 y4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int j = 0; j < nch; ++j) {
+          const int n4 = min(kRChunk, len - j * kRChunk) >> 2;
+          const float4* s4 = reinterpret_cast<const float4*>(ring + (size_t)slot_of(j) * kRChunk);
+          float4* d4 = reinterpret_cast<float4*>(a.out + off + j * kRChunk);
+          for (int i = tid; i < n4; i += kRCons) {
+            float4 v = s4[i];
+            v.x = fmaxf(fmaf(v.x - mean, sc, bt), lo); v.y = fmaxf(fmaf(v.y - mean, sc, bt), lo);
+            v.z = fmaxf(fmaf(v.z - mean, sc, bt), lo); v.w = fmaxf(fmaf(v.w - mean, sc, bt), lo);
+            y4.x += v.x; y4.y += v.y; y4.z += v.z; y4.w += v.w;
+            d4[i] = v;
+          }
+          release(j);
+        }
+        if (a.psum) {
+          t = ring_cluster_sum2(cluster, cons_sum2((double)((y4.x + y4.y) + (y4.z + y4.w)), 0.0, s_w), s_pub, rnd);
+          if (cr == 0 && tid == 0) a.psum[p] = t.a;
+        }
+        if (cr == 0 && tid == 0) { a.mean[p] = mean; a.invstd[p] = invstd; }
+      } else {
+        const float mean = a.mean[p], invstd = a.invstd[p];
+        const float sc = gm * invstd;
+        // pass 1: xhat and g' in place, S1, S2
+        float s1 = 0.f, s2 = 0.f;
+        auto one = [&](float& xv, float& gv) {
+          const float d = xv - mean;
+          xv = d * invstd;
+          gv = (a.relu && !(fmaf(d, sc, bt) > 0.f)) ? 0.f : gv;
+          s1 += gv;
+          s2 = fmaf(gv, xv, s2);
+        };
+        for (int j = 0; j < nch; ++j) {
+          wait_fill(2 * j); wait_fill(2 * j + 1);
+          const int n4 = min(kRChunk, len - j * kRChunk) >> 2;
+          float4* x4 = reinterpret_cast<float4*>(ring + (size_t)slot_of(2 * j) * kRChunk);
+          float4* g4 = reinterpret_cast<float4*>(ring + (size_t)slot_of(2 * j + 1) * kRChunk);
+          for (int i = tid; i < n4; i += kRCons) {
+            float4 xv = x4[i], gv = g4[i];
+            one(xv.x, gv.x); one(xv.y, gv.y); one(xv.z, gv.z); one(xv.w, gv.w);
+            x4[i] = xv; g4[i] = gv;
+          }
+        }
+        const Red2 t = ring_cluster_sum2(cluster, cons_sum2((double)s1, (double)s2, s_w), s_pub, rnd);
+        const float m1 = (float)(t.a / (double)a.HW), m2 = (float)(t.b / (double)a.HW);
+        // pass 2: gx (each thread re-reads exactly the elements it wrote in pass 1)
+        for (int j = 0; j < nch; ++j) {
+          const int n4 = min(kRChunk, len - j * kRChunk) >> 2;
+          const float4* x4 = reinterpret_cast<const float4*>(ring + (size_t)slot_of(2 * j) * kRChunk);
+          const float4* g4 = reinterpret_cast<const float4*>(ring + (size_t)slot_of(2 * j + 1) * kRChunk);
+          float4* d4 = reinterpret_cast<float4*>(a.out + off + j * kRChunk);
+          for (int i = tid; i < n4; i += kRCons) {
+            const float4 xh = x4[i], gp = g4[i];
+            d4[i] = make_float4(sc * (gp.x - m1 - xh.x * m2), sc * (gp.y - m1 - xh.y * m2), sc * (gp.z - m1 - xh.z * m2),
+                                sc * (gp.w - m1 - xh.w * m2));
+          }
+          // the slots were written through the generic proxy: order those writes before the bulk copy that refills them
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          release(2 * j); release(2 * j + 1);
+        }
+        if (cr == 0 && tid == 0) { a.dgamma_part[p] = (float)t.b; a.dbeta_part[p] = (float)t.a; }
+      }
+      cfill += F;
+    }
+  }
+  if (cs > 1) cluster.sync();                      // peers may still be reading this CTA's published partials
+}
+
+// ring geometry: smallest cluster whose slice fits kRMaxRes chunks; 0 = not eligible / not chosen.
+// Measured on B200 (tools/bench_instnorm.py, profiles/README.md): one consumer group per SM serialises the three
+// passes of a plane, so the ring only wins where the one-shot kernels are down to ONE resident CTA per SM anyway (slices
+// above ~100 KB: the backward of the 64 x 384^2 stem, 223 us vs 258 us); everywhere else several one-shot CTAs per SM
+// overlap each other's loads and stores better (forward (8,256,192,192): 135 us vs 184 us).  MRFP_IN_RING = 0 never,
+// 1 (default) only in that regime, 2 wherever the geometry allows.
+int ring_cluster_size(int HW, int nbuf, size_t oneshot_smem) {
+  static const int mode = getenv("MRFP_IN_RING") ? atoi(getenv("MRFP_IN_RING")) : 1;
+  if (mode <= 0 || (HW & 3) || HW < kRChunk) return 0;
+  if (mode == 1 && oneshot_smem <= (100u << 10)) return 0;
+  for (int cs = 1; cs <= kMaxCluster; cs *= 2) {
+    const int slice = (int)align_up((size_t)(HW + cs - 1) / cs, 4);
+    if (nbuf * ((slice + kRChunk - 1) / kRChunk) <= kRMaxRes) return cs;
+  }
+  return 0;
+}
+
+template <bool BWD>
+cudaError_t launch_ring(RingArgs a, int cs, int sm_count, cudaStream_t s) {
+  constexpr size_t smem = (size_t)kRSlots * kRChunk * 4;
+  auto kern = instnorm_ring_kernel<BWD>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  a.slice = (int)align_up((size_t)(a.HW + cs - 1) / cs, 4);
+  cudaLaunchConfig_t cfg = {};
+  cfg.blockDim = dim3(kRCons + 32); cfg.dynamicSmemBytes = smem; cfg.stream = s;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = (unsigned)cs; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  int ncl = sm_count / cs;                        // one CTA per SM; clusters that cannot be co-resident simply run later
+  if (cs > 1) {
+    cfg.gridDim = dim3((unsigned)(ncl * cs));
+    int active = 0;
+    if (cudaOccupancyMaxActiveClusters(&active, kern, &cfg) == cudaSuccess && active > 0 && active < ncl) ncl = active;
+  }
+  if (ncl > a.planes) ncl = a.planes;
+  cfg.gridDim = dim3((unsigned)(ncl * cs));
+  return cudaLaunchKernelEx(&cfg, kern, a);
+}
+
 template <typename K, typename... Args>
 cudaError_t launch_cluster(K kern, long long planes, const Geo& g, cudaStream_t s, Args... args) {
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem);
@@ -349,10 +601,15 @@ extern "C" int mrfp_instnorm_fwd_f32(const float* x, const float* gamma, const f
   int rc = get_device_info(&di);
   if (rc) return rc;
   const bool vec = (HW & 3) == 0 && (((uintptr_t)x | (uintptr_t)y) & 15) == 0;
-  const Geo g = pick_geo(HW, 1, di.max_smem_optin);
   cudaStream_t s = (cudaStream_t)stream;
   const long long planes = (long long)N * C;
   cudaError_t e;
+  const Geo g = pick_geo(HW, 1, di.max_smem_optin);
+  if (const int rcs = vec ? ring_cluster_size(HW, 1, g.resident ? g.smem : 0) : 0) {
+    RingArgs a = {x, nullptr, gamma, beta, y, mean, invstd, psum, nullptr, nullptr, C, HW, relu, 0, (int)planes, eps};
+    MRFP_CUDA_TRY(launch_ring<false>(a, rcs, di.sm_count, s));
+    return MRFP_OK;
+  }
   if (g.resident)
     e = vec ? launch_cluster(instnorm_fwd_kernel<true, true>, planes, g, s, x, gamma, beta, y, mean, invstd, psum, C, HW, eps, relu, g.slice)
             : launch_cluster(instnorm_fwd_kernel<false, true>, planes, g, s, x, gamma, beta, y, mean, invstd, psum, C, HW, eps, relu, g.slice);
@@ -372,10 +629,16 @@ extern "C" int mrfp_instnorm_bwd_f32(const float* gy, const float* x, const floa
   int rc = get_device_info(&di);
   if (rc) return rc;
   const bool vec = (HW & 3) == 0 && (((uintptr_t)x | (uintptr_t)gy | (uintptr_t)gx) & 15) == 0;
-  const Geo g = pick_geo(HW, 2, di.max_smem_optin);
   cudaStream_t s = (cudaStream_t)stream;
   const long long planes = (long long)N * C;
   cudaError_t e;
+  const Geo g = pick_geo(HW, 2, di.max_smem_optin);
+  if (const int rcs = vec ? ring_cluster_size(HW, 2, g.resident ? g.smem : 0) : 0) {
+    RingArgs a = {x, gy, gamma, beta, gx, const_cast<float*>(mean), const_cast<float*>(invstd), nullptr, dgamma_part, dbeta_part,
+                  C, HW, relu, 0, (int)planes, 0.f};
+    MRFP_CUDA_TRY(launch_ring<true>(a, rcs, di.sm_count, s));
+    return MRFP_OK;
+  }
   if (g.resident)
     e = vec ? launch_cluster(instnorm_bwd_kernel<true, true>, planes, g, s, gy, x, gamma, beta, mean, invstd, gx, dgamma_part, dbeta_part, C, HW, relu, g.slice)
             : launch_cluster(instnorm_bwd_kernel<false, true>, planes, g, s, gy, x, gamma, beta, mean, invstd, gx, dgamma_part, dbeta_part, C, HW, relu, g.slice);

@@ -116,3 +116,16 @@ def test_rejects_cpu_tensor():
     from mrfp_b200.instnorm import instance_norm_relu
     with pytest.raises(_lib.MrfpError):
         instance_norm_relu(torch.randn(1, 2, 4, 4))
+
+
+def test_ring_variant_everywhere_in_a_subprocess():
+    """The persistent ring kernels are selected automatically only for slices above 100 KB (the stem's backward);
+    MRFP_IN_RING=2 forces them wherever the geometry allows — same oracle checks, fresh process (the switch is read once)."""
+    import subprocess
+    import sys
+    if os.environ.get("MRFP_IN_RING") == "2":
+        pytest.skip("already inside the forced-ring run")
+    env = dict(os.environ, MRFP_IN_RING="2")
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-x", "-q", "-m", "gpu", "-k", "vs_oracle or fixture"],
+                       env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
