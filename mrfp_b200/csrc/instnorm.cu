@@ -42,18 +42,22 @@ __device__ __forceinline__ Red2 block_sum2(double a, double b, double (*s_w)[2])
   return r;
 }
 
-// cluster-wide sum: every CTA publishes its pair in slot `round` and reads all ranks in rank order
-__device__ __forceinline__ Red2 cluster_sum2(cg::cluster_group& cluster, Red2 mine, double (*s_pub)[2], int round) {
-  const unsigned cs = cluster.num_blocks();
-  if (cs == 1) return mine;
-  if (threadIdx.x == 0) { s_pub[round][0] = mine.a; s_pub[round][1] = mine.b; }
-  cluster.sync();
-  Red2 r{0.0, 0.0};
-  for (unsigned k = 0; k < cs; ++k) {
-    const double* remote = cluster.map_shared_rank(&s_pub[round][0], k);
-    r.a += remote[0]; r.b += remote[1];
+// Cluster exchange, push model: every CTA WRITES its partials into each peer's shared memory, one cluster barrier, then
+// everybody reads its own copy in rank order.  Nothing remote is read after the barrier, so a CTA may exit right after
+// its last one (no trailing barrier).  cl_arrive() at kernel entry + cl_wait() before the first push guarantee that
+// every peer has started (its shared memory exists) without ever blocking in practice.
+__device__ __forceinline__ void cl_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+__device__ __forceinline__ void cl_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
+constexpr int kPubVals = 4;
+__device__ __forceinline__ void cluster_push(cg::cluster_group& cluster, double (*s_pub)[kPubVals], unsigned cr, double v0, double v1,
+                                             double v2, double v3) {
+  if (threadIdx.x < cluster.num_blocks()) {
+    double* dst = cluster.map_shared_rank(&s_pub[cr][0], threadIdx.x);
+    dst[0] = v0; dst[1] = v1; dst[2] = v2; dst[3] = v3;
   }
-  return r;
+  __syncwarp();
+  cl_arrive();
+  cl_wait();
 }
 
 // Brings the CTA's slice of one plane into shared memory.  VEC: chunked 1-D bulk copies (thread 0 issues, everyone
@@ -87,7 +91,9 @@ instnorm_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma
   float* buf = reinterpret_cast<float*>(smem_raw);
   __shared__ __align__(8) uint64_t bars[kMaxChunks];
   __shared__ double s_w[kWarps][2];
-  __shared__ double s_pub[3][2];
+  __shared__ double s_pub[kMaxCluster][kPubVals];    // written by the peers (cluster_push)
+  __shared__ double s_ps[kMaxCluster];
+  if (cs > 1) cl_arrive();                         // matched by the cl_wait() in front of the first push
 
   const int tid = threadIdx.x;
   const int begin = (int)cr * slice;
@@ -126,25 +132,44 @@ instnorm_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma
   } else {
     for (int i = tid; i < len; i += kThreads) acc += in[i];
   }
-  Red2 t = cluster_sum2(cluster, block_sum2((double)acc, 0.0, s_w), s_pub, 0);
-  const float mean = (float)(t.a / (double)HW);
+  // the slice's own mean first: the squares are centred locally, and ONE exchange combines the slices exactly
+  const double sum_l = block_sum2((double)acc, 0.0, s_w).a;
+  const float mean_l = len > 0 ? (float)(sum_l / (double)len) : 0.f;
 
-  // pass 2: centred squares -> invstd (biased variance, as F.instance_norm)
+  // pass 2: squares centred on the slice mean
   acc = 0.f;
   if (VEC) {
     const float4* p = reinterpret_cast<const float4*>(in);
     float4 a4 = make_float4(0.f, 0.f, 0.f, 0.f);
     for (int i = tid; i < (len >> 2); i += kThreads) {
       const float4 v = p[i];
-      const float dx = v.x - mean, dy = v.y - mean, dz = v.z - mean, dw = v.w - mean;
+      const float dx = v.x - mean_l, dy = v.y - mean_l, dz = v.z - mean_l, dw = v.w - mean_l;
       a4.x = fmaf(dx, dx, a4.x); a4.y = fmaf(dy, dy, a4.y); a4.z = fmaf(dz, dz, a4.z); a4.w = fmaf(dw, dw, a4.w);
     }
     acc = (a4.x + a4.y) + (a4.z + a4.w);
   } else {
-    for (int i = tid; i < len; i += kThreads) { const float d = in[i] - mean; acc = fmaf(d, d, acc); }
+    for (int i = tid; i < len; i += kThreads) { const float d = in[i] - mean_l; acc = fmaf(d, d, acc); }
   }
-  t = cluster_sum2(cluster, block_sum2((double)acc, 0.0, s_w), s_pub, 1);
-  const float invstd = (float)(1.0 / sqrt(t.a / (double)HW + (double)eps));
+  const double m2_l = block_sum2((double)acc, 0.0, s_w).a;
+  // sum_x (x - mu)^2 = sum_k [ M2_k + 2 (m_k - mu)(S_k - n_k m_k) + n_k (m_k - mu)^2 ]   (m_k: the fp32 centre slice k used)
+  double mu, m2 = 0.0;
+  if (cs > 1) {
+    cl_wait();                                     // (arrived at kernel entry) every peer is running
+    cluster_push(cluster, s_pub, cr, sum_l, m2_l, (double)len, (double)mean_l);
+    double tot = 0.0;
+    for (unsigned k = 0; k < cs; ++k) tot += s_pub[k][0];
+    mu = tot / (double)HW;
+    for (unsigned k = 0; k < cs; ++k) {
+      const double dm = s_pub[k][3] - mu;
+      m2 += s_pub[k][1] + 2.0 * dm * (s_pub[k][0] - s_pub[k][2] * s_pub[k][3]) + s_pub[k][2] * dm * dm;
+    }
+  } else {
+    mu = sum_l / (double)HW;
+    const double dm = (double)mean_l - mu;
+    m2 = m2_l + 2.0 * dm * (sum_l - (double)len * (double)mean_l) + (double)len * dm * dm;
+  }
+  const float mean = (float)mu;
+  const float invstd = (float)(1.0 / sqrt(fmax(m2, 0.0) / (double)HW + (double)eps));
 
   // pass 3: y = (x - mean) * (gamma * invstd) + beta, optional ReLU, optional plane sum of y
   const int c = (int)(plane % C);
@@ -171,11 +196,22 @@ instnorm_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma
     }
   }
   if (psum) {
-    t = cluster_sum2(cluster, block_sum2((double)acc, 0.0, s_w), s_pub, 2);
-    if (cr == 0 && tid == 0) psum[plane] = t.a;
+    const double ys = block_sum2((double)acc, 0.0, s_w).a;
+    if (cs > 1) {                                  // only rank 0 needs the partials
+      if (tid == 0) *cluster.map_shared_rank(&s_ps[cr], 0) = ys;
+      __syncwarp();
+      cl_arrive();
+      cl_wait();
+      if (cr == 0 && tid == 0) {
+        double t = 0.0;
+        for (unsigned k = 0; k < cs; ++k) t += s_ps[k];
+        psum[plane] = t;
+      }
+    } else if (tid == 0) {
+      psum[plane] = ys;
+    }
   }
   if (cr == 0 && tid == 0) { mean_out[plane] = mean; invstd_out[plane] = invstd; }
-  if (cs > 1) cluster.sync();                      // peers may still be reading this CTA's published partials
 }
 
 // ------------------------------------------------------------------------------------------------ backward
@@ -195,7 +231,8 @@ instnorm_bwd_kernel(const float* __restrict__ gy, const float* __restrict__ x, c
   float* bg = bx + slice;                          // slice is a multiple of 4: both buffers 16-byte aligned
   __shared__ __align__(8) uint64_t bars[2 * kMaxChunks];
   __shared__ double s_w[kWarps][2];
-  __shared__ double s_pub[1][2];
+  __shared__ double s_pub[kMaxCluster][kPubVals];    // written by the peers (cluster_push)
+  if (cs > 1) cl_arrive();                         // matched by the cl_wait() in front of the push
 
   const int tid = threadIdx.x;
   const int begin = (int)cr * slice;
@@ -264,7 +301,13 @@ instnorm_bwd_kernel(const float* __restrict__ gy, const float* __restrict__ x, c
       if (RESIDENT) { bx[i] = xh; bg[i] = gp; }
     }
   }
-  const Red2 t = cluster_sum2(cluster, block_sum2((double)s1, (double)s2, s_w), s_pub, 0);
+  Red2 t = block_sum2((double)s1, (double)s2, s_w);
+  if (cs > 1) {
+    cl_wait();
+    cluster_push(cluster, s_pub, cr, t.a, t.b, 0.0, 0.0);
+    t.a = 0.0; t.b = 0.0;
+    for (unsigned k = 0; k < cs; ++k) { t.a += s_pub[k][0]; t.b += s_pub[k][1]; }
+  }
   const float m1 = (float)(t.a / (double)HW), m2 = (float)(t.b / (double)HW);
 
   // pass 2: gx (each thread re-reads exactly the elements it wrote in pass 1)
@@ -293,7 +336,6 @@ instnorm_bwd_kernel(const float* __restrict__ gy, const float* __restrict__ x, c
     }
   }
   if (cr == 0 && tid == 0) { dgamma_part[plane] = (float)t.b; dbeta_part[plane] = (float)t.a; }
-  if (cs > 1) cluster.sync();
 }
 
 // slice geometry: the smallest cluster whose slice fits `want` bytes per buffer set, else the largest cluster if it
