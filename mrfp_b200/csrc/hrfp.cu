@@ -12,6 +12,7 @@
 // Backward per stage: bn_bwd_reduce (sums over replicas) -> bn_bwd_apply (dY at conv resolution) -> dgrad conv
 // (the same conv kernel with rotated, transposed weights).  No weight gradients (deepv3.py:221-237).
 #include "hrfp.cuh"
+#include "tma.cuh"
 #include <math.h>
 #include <stdlib.h>
 #include <string.h>
@@ -248,6 +249,121 @@ nhwc_to_nchw_kernel(const T* __restrict__ y, float* __restrict__ out, const floa
           const float vv[4] = {v.x, v.y, v.z, v.w};
           for (int i = 0; i < 4 && ow + i < OW; ++i) out[o + i] = add ? vv[i] + fmaf(ab.x, add[o + i], ab.y) : vv[i];
         }
+      }
+    }
+  }
+}
+
+// HRFP+ tail with the low-resolution operand STAGED by bulk copies (deepv3.py:356-357, the x2 Upsample of the reference
+// geometry).  The generic BILIN path above issues 16 scalar global loads per four outputs (about six distinct values):
+// it is bound by load latency, 909 us for 1.96 GB.  Here the two source rows a tile needs — for each of its 64 channels
+// the span [ws, ws + cnt) of rows h1 and h1 + h1p, at most 80 floats when the scale is <= 1/2 — arrive in shared memory
+// as 128 1-D bulk copies (one per thread, one mbarrier) while the threads gather and transpose the tile of Y.  The
+// kernel is bound by instruction issue, not by memory (a staged variant that kept ATen's association and selected its
+// taps from four consecutive floats ran at 978 us), so the interpolation is made separable: one vertical blend of the
+// staged rows per tile, then two taps and three flops per output (same formula, different association: ~1 ulp from
+// ATen's).
+constexpr int kSegFloats = 80;
+constexpr size_t kStagedSmem = sizeof(float) * (64 * kLayRow + 64 * 2 * kSegFloats);
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+hrfp_plus_bilinear_staged_kernel(const T* __restrict__ y, float* __restrict__ out, const int* __restrict__ idx_h,
+                                 const int* __restrict__ idx_w, const float* __restrict__ scale, const float* __restrict__ shift,
+                                 int C, int IH, int IW, int OH, int OW, const float* __restrict__ add_lo, int LH, int LW) {
+  pdl_sync();
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  float (*tile)[kLayRow] = reinterpret_cast<float (*)[kLayRow]>(smem_raw);          // [channel][lay_col(pixel)]
+  float* stage = reinterpret_cast<float*>(smem_raw) + 64 * kLayRow;                 // [channel][row 0/1][kSegFloats]
+  __shared__ __align__(8) uint64_t bar;
+  const int ct = (C + 63) >> 6, rows = (int)(gridDim.x / (((OW + kLayPx - 1) / kLayPx) * ct));
+  const int orow = blockIdx.x % rows, rem = blockIdx.x / rows;
+  const int n = orow / OH, oh = orow - n * OH, t = threadIdx.x;
+  const int c0 = (rem % ct) * 64, w0 = (rem / ct) * kLayPx;
+  const int nch = min(64, C - c0);
+  // ATen's upsample_bilinear2d(align_corners=True) source coordinates
+  const float rh = OH > 1 ? (float)(LH - 1) / (float)(OH - 1) : 0.f;
+  const float rw = OW > 1 ? (float)(LW - 1) / (float)(OW - 1) : 0.f;
+  const float h1r = rh * (float)oh;
+  const int h1 = (int)h1r, h1p = h1 < LH - 1 ? 1 : 0;
+  const float hl1 = h1r - (float)h1, hl0 = 1.f - hl1;
+  const int ws = (int)(rw * (float)w0) & ~3;                                        // 16-byte aligned start of the staged span
+  const int w_hi = min(LW - 1, (int)(rw * (float)min(w0 + kLayPx - 1, OW - 1)) + 1);
+  const int cnt = min(kSegFloats, (w_hi - ws + 4) & ~3);
+  if (t == 0) {
+    tma::mbar_init(&bar, 1);
+    tma::mbar_fence_init();
+    tma::mbar_expect_tx(&bar, (uint32_t)(nch * 2 * cnt) * 4u);
+  }
+  __syncthreads();
+  if (t < 2 * nch) {
+    const int c = t >> 1, r = t & 1;
+    const float* src = add_lo + (((size_t)n * C + c0 + c) * LH + h1 + (r ? h1p : 0)) * LW + ws;
+    tma::bulk_load(stage + (size_t)t * kSegFloats, src, (uint32_t)cnt * 4u, &bar);
+  }
+  const int sh = idx_h ? idx_h[oh] : oh;
+  const T* row = y + ((size_t)n * IH + sh) * IW * C;
+  {
+    const int cg = t & 7, pl = t >> 3, c = c0 + cg * 8;
+    float sc[8], sf[8];
+    if (c < C) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { sc[j] = scale[c + j]; sf[j] = shift[c + j]; }
+    }
+#pragma unroll
+    for (int pass = 0; pass < kLayPx / 32; ++pass) {
+      const int px = pl + pass * 32, ow = w0 + px;
+      float v[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = 0.f;
+      if (ow < OW && c < C) {
+        const int sw = idx_w ? idx_w[ow] : ow;
+        Elem<T>::load8(row + (size_t)sw * C + c, v);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = fmaxf(fmaf(sc[j], v[j], sf[j]), 0.f);
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) tile[cg * 8 + j][lay_col(px)] = v[j];
+    }
+  }
+  __syncthreads();
+  tma::mbar_wait(&bar, 0);
+  // vertical blend of the two staged rows, in place over row 0:  vb[c][k] = hl0 * r0[k] + hl1 * r1[k]
+  for (int e = t; e < nch * (cnt >> 2); e += 256) {
+    const int c = e / (cnt >> 2), k4 = e - c * (cnt >> 2);
+    float4* p0 = reinterpret_cast<float4*>(stage + (size_t)(2 * c) * kSegFloats) + k4;
+    const float4 a = *p0, b = *(reinterpret_cast<const float4*>(stage + (size_t)(2 * c + 1) * kSegFloats) + k4);
+    *p0 = make_float4(fmaf(hl1, b.x, hl0 * a.x), fmaf(hl1, b.y, hl0 * a.y), fmaf(hl1, b.z, hl0 * a.z), fmaf(hl1, b.w, hl0 * a.w));
+  }
+  __syncthreads();
+  {
+    const int px = (t & 31) * 4, crow = t >> 5;
+    const bool vec = (OW & 3) == 0;
+    int o0[4], o1[4];                                      // staged columns of the two horizontal taps of each output
+    float wl0[4], wl1[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int ow = min(w0 + px + i, OW - 1);
+      const float w1r = rw * (float)ow;
+      const int w1 = (int)w1r;
+      o0[i] = w1 - ws;
+      o1[i] = o0[i] + (w1 < LW - 1 ? 1 : 0);
+      wl1[i] = w1r - (float)w1; wl0[i] = 1.f - wl1[i];
+    }
+#pragma unroll
+    for (int pass = 0; pass < 8; ++pass) {
+      const int c = crow + pass * 8, ow = w0 + px;
+      if (c0 + c < C && ow < OW) {
+        const size_t o = (((size_t)n * C + c0 + c) * OH + oh) * OW + ow;
+        const int col = px >> 2;
+        const float vv[4] = {tile[c][col], tile[c][33 + col], tile[c][66 + col], tile[c][99 + col]};
+        const float* vb = stage + (size_t)(2 * c) * kSegFloats;
+        float res[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) res[i] = vv[i] + fmaf(wl0[i], vb[o0[i]], wl1[i] * vb[o1[i]]);
+        if (vec && ow + 3 < OW) *reinterpret_cast<float4*>(out + o) = make_float4(res[0], res[1], res[2], res[3]);
+        else
+          for (int i = 0; i < 4 && ow + i < OW; ++i) out[o + i] = res[i];
       }
     }
   }
@@ -1194,6 +1310,16 @@ static int hrfp_plus_add_impl(const mrfp_hrfp_plan* P, const char* saved, const 
   const float* stats = reinterpret_cast<const float*>(saved + P->stats_off) + (size_t)3 * 4 * kMaxC;
   const unsigned g = (unsigned)(((st.ow + kLayPx - 1) / kLayPx) * ((st.cout + 63) / 64)) * (unsigned)(P->N * st.oh);
   if (dec1_lo && (lw > st.ow || lh > st.oh)) return MRFP_ERR_BAD_SHAPE;      // an Upsample: the source is not larger
+  static const bool staged_on = !(getenv("MRFP_PLUS_STAGED") && atoi(getenv("MRFP_PLUS_STAGED")) == 0);
+  // the reference's x2 Upsample: scale <= 1/2 bounds the staged span; 16-byte alignment for the bulk copies
+  if (dec1_lo && staged_on && st.ow > 1 && 2 * (lw - 1) <= st.ow - 1 && (lw & 3) == 0 && ((uintptr_t)dec1_lo & 15) == 0) {
+    auto kern = hrfp_plus_bilinear_staged_kernel<T>;
+    MRFP_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kStagedSmem));
+    launch_k(kern, dim3(g), dim3(256), kStagedSmem, s, Y, out, lut + st.idx_h, lut + st.idx_w, stats + 2 * kMaxC, stats + 3 * kMaxC,
+             st.cout, st.ch, st.cw, st.oh, st.ow, dec1_lo, lh, lw);
+    MRFP_CUDA_TRY(cudaGetLastError());
+    return MRFP_OK;
+  }
   launch_k(dec1_lo ? nhwc_to_nchw_kernel<T, true> : nhwc_to_nchw_kernel<T, false>, dim3(g), dim3(256), 0, s, Y, out, dec1_up,
            lut + st.idx_h, lut + st.idx_w, stats + 2 * kMaxC, stats + 3 * kMaxC, st.cout, st.ch, st.cw, st.oh, st.ow,
            (const float2*)nullptr, dec1_lo, lh, lw);

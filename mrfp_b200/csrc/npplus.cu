@@ -57,6 +57,7 @@ struct NpGeom {
   int tmem_units;  // ring path: head units per CTA parked in tensor memory
   int reg_units;   // ring path: head units per CTA parked in the consumers' registers (0 or kRegUnits), before the TMEM ones
   int mid_units;   // ring path: units before the keep_units band loaded with L2 evict_normal
+  int heads_last;  // ring path: phase B writes the register / TMEM heads after the re-read queue instead of before it
 };
 
 // ------------------------------------------------------------------------------------------------------
@@ -553,15 +554,16 @@ npplus_ring_kernel(const float* __restrict__ x, const float* __restrict__ alpha,
       }
     };
     // the ring part of the tail first (frees the slots for the producer), then the TMEM part, then the queue
-    for (int i = 0;; ++i) {
-      if (i == S) {
-        if (RG > 0) { emit(head0, head_coef[0], preg0); emit(head0 + 1, head_coef[1], preg1); }
-        for (int j = RG; j < T; ++j) {
-          float4 v[kBatch];
-          tmem_fetch(tmem_mine + (uint32_t)((j - RG) * 64), v);
-          emit(head0 + j, head_coef[j], v);
-        }
+    auto emit_heads = [&]() {
+      if (RG > 0) { emit(head0, head_coef[0], preg0); emit(head0 + 1, head_coef[1], preg1); }
+      for (int j = RG; j < T; ++j) {
+        float4 v[kBatch];
+        tmem_fetch(tmem_mine + (uint32_t)((j - RG) * 64), v);
+        emit(head0 + j, head_coef[j], v);
       }
+    };
+    for (int i = 0;; ++i) {
+      if (i == S && !g.heads_last) emit_heads();
       if (i >= S) mbar_wait(&full[s], k & 1);            // the first S fills are the resident tail, waited for in phase A
       const int u = slot_unit[s];
       if (u < 0) break;
@@ -576,6 +578,7 @@ npplus_ring_kernel(const float* __restrict__ x, const float* __restrict__ alpha,
       if (i < S) { if (++s == S) s = 0; }                // replaying the tail does not start a new round
       else advance();
     }
+    if (g.heads_last) emit_heads();
   }
   if (T > RG) {
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -692,7 +695,7 @@ void plan_launch(int N, int C, int HW, bool ring, const DeviceInfo& di, NpLaunch
   const long long min_upc = g.U / L->grid;                       // ... (min, >= 1)
   g.max_local_planes = (int)(upc / g.K + 2);
   g.scratch_off = g.U;
-  g.keep_units = 0; g.grab = 1; g.grab_b = 1; g.u_dyn = 0; g.tmem_units = 0; g.reg_units = 0; g.mid_units = 0;
+  g.keep_units = 0; g.grab = 1; g.grab_b = 1; g.u_dyn = 0; g.tmem_units = 0; g.reg_units = 0; g.mid_units = 0; g.heads_last = 0;
   const size_t slack = 1024;                                     // static smem + alignment
   if (ring) {
     long long grab = upc / 8;
@@ -721,6 +724,8 @@ void plan_launch(int N, int C, int HW, bool ring, const DeviceInfo& di, NpLaunch
     g.keep_units = (int)((keep_mb << 20) / ((long long)kUnitVecs * 16));
     static const long long mid_mb = getenv("MRFP_NPPLUS_MID_MB") ? atoll(getenv("MRFP_NPPLUS_MID_MB")) : 0;
     g.mid_units = (int)((mid_mb << 20) / ((long long)kUnitVecs * 16));
+    static const int heads_last = getenv("MRFP_NPPLUS_HEADS_LAST") ? atoi(getenv("MRFP_NPPLUS_HEADS_LAST")) : 0;
+    g.heads_last = heads_last;
   } else {
     const size_t coef_bytes = align_up((size_t)g.max_local_planes * sizeof(float2), 16);
     const size_t unit_bytes = (size_t)g.Q * 4;
