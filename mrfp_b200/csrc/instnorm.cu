@@ -93,7 +93,15 @@ instnorm_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma
   __shared__ double s_w[kWarps][2];
   __shared__ double s_pub[kMaxCluster][kPubVals];    // written by the peers (cluster_push)
   __shared__ double s_ps[kMaxCluster];
-  if (cs > 1) cl_arrive();                         // matched by the cl_wait() in front of the first push
+  __shared__ __align__(8) uint64_t ps_bar;           // rank 0: the plane-sum partials land here (st.async + complete_tx)
+  if (cs > 1) {
+    if (psum && cr == 0 && threadIdx.x == 0) {
+      tma::mbar_init(&ps_bar, 1);
+      tma::mbar_fence_init();
+      tma::mbar_expect_tx(&ps_bar, cs * 8u);
+    }
+    cl_arrive();                                   // matched by the cl_wait() in front of the first push
+  }
 
   const int tid = threadIdx.x;
   const int begin = (int)cr * slice;
@@ -197,15 +205,22 @@ instnorm_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma
   }
   if (psum) {
     const double ys = block_sum2((double)acc, 0.0, s_w).a;
-    if (cs > 1) {                                  // only rank 0 needs the partials
-      if (tid == 0) *cluster.map_shared_rank(&s_ps[cr], 0) = ys;
-      __syncwarp();
-      cl_arrive();
-      cl_wait();
-      if (cr == 0 && tid == 0) {
-        double t = 0.0;
-        for (unsigned k = 0; k < cs; ++k) t += s_ps[k];
-        psum[plane] = t;
+    if (cs > 1) {
+      // Only rank 0 needs the partials, and this exchange comes AFTER the output stores: a cluster barrier here would
+      // make every thread's release fence wait for its stores to drain (ncu: membar stalls).  An asynchronous remote
+      // store that completes bytes on rank 0's mbarrier carries the value without any fence; the other CTAs are done.
+      if (tid == 0) {
+        uint32_t dst, bar;
+        asm volatile("mapa.shared::cluster.u32 %0, %1, 0;" : "=r"(dst) : "r"(tma::smem_u32(&s_ps[cr])));
+        asm volatile("mapa.shared::cluster.u32 %0, %1, 0;" : "=r"(bar) : "r"(tma::smem_u32(&ps_bar)));
+        asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b64 [%0], %1, [%2];"
+                     ::"r"(dst), "l"(__double_as_longlong(ys)), "r"(bar) : "memory");
+        if (cr == 0) {
+          tma::mbar_wait(&ps_bar, 0);
+          double t = 0.0;
+          for (unsigned k = 0; k < cs; ++k) t += s_ps[k];
+          psum[plane] = t;
+        }
       }
     } else if (tid == 0) {
       psum[plane] = ys;
