@@ -138,6 +138,256 @@ bn_bwd_reduce_ring_kernel(const __nv_bfloat16* __restrict__ dA, const __nv_bfloa
   }
 }
 
+
+// Same reduction with SEVERAL single-buffered CTAs per SM instead of one ring: each CTA copies one item (a <= 20 KiB
+// gradient segment + the gathered span of the conv-output row) into its own buffer, waits, reduces from shared memory and
+// takes the next item; four such CTAs per SM overlap each other's copy and compute phases (the shape that worked for the
+// InstanceNorm kernels, where a single serialised consumer group per SM lost to independent one-shot CTAs).
+constexpr int kBDaBytes = 20480;
+constexpr int kBYBytes = 26624;                 // 1.25x the segment (x0.8 down-sampling stages) + one pixel of 256 channels + slack
+constexpr int kBThreads = 256;
+
+__global__ void __launch_bounds__(kBThreads, 4)
+bn_bwd_reduce_bulk_kernel(const __nv_bfloat16* __restrict__ dA, const __nv_bfloat16* __restrict__ y,
+                          const int* __restrict__ idx_h, const int* __restrict__ idx_w, const float* __restrict__ stats,
+                          double* __restrict__ acc, int N, int C, int IH, int IW, int OH, int OW, int pseg, int nseg,
+                          int items, int rev) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  unsigned char* s_da = smem_raw;
+  unsigned char* s_y = smem_raw + kBDaBytes;
+  __shared__ __align__(8) uint64_t bar;
+  __shared__ float s_acc[2 * kMaxC];
+  const int tid = threadIdx.x;
+  const int cg = C >> 3, cgs = 31 - __clz(cg);
+  const int c = (tid & (cg - 1)) << 3, pl = tid >> cgs, pstep = kBThreads >> cgs;
+  if (tid == 0) { mbar_init(&bar, 1); mbar_fence_init(); }
+  for (int i = tid; i < 2 * kMaxC; i += kBThreads) s_acc[i] = 0.f;
+  __syncthreads();
+  pdl_sync();
+  float scale[8], shift[8], u1[8], u2[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    scale[j] = stats[2 * kMaxC + c + j]; shift[j] = stats[3 * kMaxC + c + j];
+    u1[j] = 0.f; u2[j] = 0.f;
+  }
+  uint32_t phase = 0;
+  for (int it = blockIdx.x; it < items; it += gridDim.x) {
+    const int itr = rev ? items - 1 - it : it;
+    const int row = itr / nseg, seg = itr - row * nseg;
+    const int n = row / OH, oh = row - n * OH;
+    const int ow0 = seg * pseg, npx = min(pseg, OW - ow0);
+    const int s0 = idx_w[ow0];
+    if (tid == 0) {
+      const int s1 = idx_w[ow0 + npx - 1];
+      const uint32_t dab = (uint32_t)(npx * C * 2), yb = (uint32_t)((s1 - s0 + 1) * C * 2);
+      mbar_expect_tx(&bar, dab + yb);
+      bulk_load(s_da, dA + ((long long)row * OW + ow0) * C, dab, &bar);
+      bulk_load(s_y, y + (((long long)n * IH + idx_h[oh]) * IW + s0) * C, yb, &bar);
+    }
+    int j = pl < npx ? idx_w[ow0 + pl] - s0 : 0;         // first look-up travels with the copies
+    mbar_wait(&bar, phase);
+    phase ^= 1u;
+    for (int px = pl; px < npx; px += pstep) {
+      const int jn = px + pstep < npx ? idx_w[ow0 + px + pstep] - s0 : 0;
+      float g[8], yv[8];
+      unpack8(*reinterpret_cast<const uint4*>(s_da + ((size_t)px * C + c) * 2), g);
+      unpack8(*reinterpret_cast<const uint4*>(s_y + ((size_t)j * C + c) * 2), yv);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float t = fmaf(scale[i], yv[i], shift[i]) > 0.f ? g[i] : 0.f;
+        u1[i] += t;
+        u2[i] = fmaf(t, yv[i], u2[i]);
+      }
+      j = jn;
+    }
+    __syncthreads();                                     // every read of the buffer precedes the next item's copies
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    atomicAdd(&s_acc[c + j], u1[j]);
+    atomicAdd(&s_acc[kMaxC + c + j], u2[j]);
+  }
+  __syncthreads();
+  for (int i = tid; i < C; i += kBThreads) {
+    atomicAdd(acc + i, (double)s_acc[i]);
+    atomicAdd(acc + kMaxC + i, (double)s_acc[kMaxC + i]);
+  }
+}
+
+
+// BN-backward APPLY pass in the same shape: an item is a segment of one SOURCE row (its y values, <= 12 KiB) plus the
+// contiguous spans of the <= 2 destination rows that hold its replicas (lo tables: replicas of source s are the
+// destinations [lo[s], lo[s+1])); the result segment goes straight from registers to global memory.
+//   dY[src] = P * [scale*y + shift > 0] * sum_replicas dA - cnt * (Q + R * y)        (constants as in hrfp.cu)
+constexpr int kAYBytes = 12288;
+constexpr int kADaBytes = 16384;                // per destination row: 1.25x the segment + one 256-channel pixel + slack
+
+template <bool REGC>
+__global__ void __launch_bounds__(kBThreads, REGC ? 3 : 4)
+bn_bwd_apply_bulk_kernel(const __nv_bfloat16* __restrict__ dA, const __nv_bfloat16* __restrict__ y, __nv_bfloat16* __restrict__ dY,
+                         const int* __restrict__ lo_h, const int* __restrict__ lo_w, const float* __restrict__ stats,
+                         const float* __restrict__ gamma, const double* __restrict__ acc, int N, int C, int IH, int IW, int OH,
+                         int OW, double count, int pseg, int nseg, int items, int rev) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  unsigned char* s_y = smem_raw;
+  unsigned char* s_da = smem_raw + kAYBytes;             // [2][kADaBytes]
+  __shared__ __align__(8) uint64_t bar;
+  __shared__ __align__(16) float s_scale[kMaxC], s_shift[kMaxC], s_P[kMaxC], s_Q[kMaxC], s_R[kMaxC];
+  const int tid = threadIdx.x;
+  const int cg = C >> 3, cgs = 31 - __clz(cg);
+  const int c = (tid & (cg - 1)) << 3, pl = tid >> cgs, pstep = kBThreads >> cgs;
+  if (tid == 0) { mbar_init(&bar, 1); mbar_fence_init(); }
+  pdl_sync();
+  for (int j = tid; j < C; j += kBThreads) {
+    const double mean = stats[j], invstd = stats[kMaxC + j], gm = gamma[j];
+    s_scale[j] = stats[2 * kMaxC + j]; s_shift[j] = stats[3 * kMaxC + j];
+    const double S1 = acc[j], S2 = invstd * (acc[kMaxC + j] - mean * S1);
+    const double M1 = gm * S1 / count, M2 = gm * S2 / count;
+    const double r = invstd * invstd * M2;
+    s_P[j] = (float)(invstd * gm); s_R[j] = (float)r; s_Q[j] = (float)(invstd * M1 - mean * r);
+  }
+  __syncthreads();
+  auto ld8 = [&](const float* t, float (&v)[8]) {
+    const float4 a = *reinterpret_cast<const float4*>(t + c), b = *reinterpret_cast<const float4*>(t + c + 4);
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+  };
+  float r_scale[8], r_shift[8], r_P[8], r_Q[8], r_R[8];   // REGC: the thread's constants stay in registers (3 CTAs per SM)
+  if (REGC) { ld8(s_scale, r_scale); ld8(s_shift, r_shift); ld8(s_P, r_P); ld8(s_Q, r_Q); ld8(s_R, r_R); }
+  uint32_t phase = 0;
+  for (int it = blockIdx.x; it < items; it += gridDim.x) {
+    const int itr = rev ? items - 1 - it : it;
+    const int row = itr / nseg, seg = itr - row * nseg;  // row = n * IH + sy
+    const int n = row / IH, sy = row - n * IH;
+    const int x0 = seg * pseg, npx = min(pseg, IW - x0);
+    const int h0 = lo_h[sy], nh = lo_h[sy + 1] - h0;      // <= 2 (host check)
+    const int d0 = lo_w[x0], dspan = lo_w[x0 + npx] - d0;
+    if (tid == 0) {
+      const uint32_t yb = (uint32_t)(npx * C * 2), dab = (uint32_t)(dspan * C * 2);
+      mbar_expect_tx(&bar, yb + (uint32_t)nh * dab);
+      bulk_load(s_y, y + ((long long)row * IW + x0) * C, yb, &bar);
+      if (dab)
+        for (int a = 0; a < nh; ++a)
+          bulk_load(s_da + (size_t)a * kADaBytes, dA + (((long long)n * OH + h0 + a) * OW + d0) * C, dab, &bar);
+    }
+    int w0 = 0, w1 = 0;
+    if (pl < npx) { w0 = lo_w[x0 + pl]; w1 = lo_w[x0 + pl + 1]; }          // look-ups travel with the copies
+    mbar_wait(&bar, phase);
+    phase ^= 1u;
+    for (int x = pl; x < npx; x += pstep) {
+      int nw0 = 0, nw1 = 0;
+      if (x + pstep < npx) { nw0 = lo_w[x0 + x + pstep]; nw1 = lo_w[x0 + x + pstep + 1]; }
+      float sd[8], yv[8], k0[8], k1[8], o[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) sd[j] = 0.f;
+      for (int a = 0; a < nh; ++a)
+        for (int b = w0; b < w1; ++b) {
+          float g[8];
+          unpack8(*reinterpret_cast<const uint4*>(s_da + (size_t)a * kADaBytes + ((size_t)(b - d0) * C + c) * 2), g);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) sd[j] += g[j];
+        }
+      unpack8(*reinterpret_cast<const uint4*>(s_y + ((size_t)x * C + c) * 2), yv);
+      const float cnt = (float)(nh * (w1 - w0));
+      if (REGC) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float t = fmaf(r_scale[j], yv[j], r_shift[j]) > 0.f ? sd[j] : 0.f;
+          o[j] = r_P[j] * t - cnt * fmaf(r_R[j], yv[j], r_Q[j]);
+        }
+      } else {
+        ld8(s_scale, k0); ld8(s_shift, k1);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = fmaf(k0[j], yv[j], k1[j]) > 0.f ? sd[j] : 0.f;
+        ld8(s_P, k0);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] *= k0[j];
+        ld8(s_R, k0); ld8(s_Q, k1);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] -= cnt * fmaf(k0[j], yv[j], k1[j]);
+      }
+      uint32_t w[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const __nv_bfloat162 h = __floats2bfloat162_rn(o[2 * i], o[2 * i + 1]);
+        w[i] = *reinterpret_cast<const uint32_t*>(&h);
+      }
+      *reinterpret_cast<uint4*>(dY + ((long long)row * IW + x0 + x) * C + c) = make_uint4(w[0], w[1], w[2], w[3]);
+      w0 = nw0; w1 = nw1;
+    }
+    __syncthreads();                                     // every read of the buffers precedes the next item's copies
+  }
+}
+
+}  // namespace
+
+int bn_bwd_apply_bulk(const __nv_bfloat16* dA, const __nv_bfloat16* y, __nv_bfloat16* dY, const int* lo_h, const int* lo_w,
+                      const int* host_lo_h, const int* host_lo_w, const float* stats, const float* gamma, const double* acc,
+                      int N, int C, int IH, int IW, int OH, int OW, double count, bool reverse, cudaStream_t stream) {
+  if (C < 64 || C > kMaxC || (C & (C - 1))) return MRFP_ERR_UNSUPPORTED;
+  for (int i = 0; i < IH; ++i)
+    if (host_lo_h[i + 1] - host_lo_h[i] > 2) return MRFP_ERR_UNSUPPORTED;        // two destination-row buffers
+  int nseg = (IW * 2 * C + kAYBytes - 1) / kAYBytes;
+  int pseg = (IW + nseg - 1) / nseg;
+  for (;;) {
+    bool ok = true;
+    nseg = (IW + pseg - 1) / pseg;
+    for (int sgi = 0; sgi < nseg && ok; ++sgi) {
+      const int x0 = sgi * pseg, x1 = x0 + pseg < IW ? x0 + pseg : IW;
+      ok = (host_lo_w[x1] - host_lo_w[x0]) * C * 2 <= kADaBytes;
+    }
+    if (ok) break;
+    if (--pseg < 8) return MRFP_ERR_UNSUPPORTED;
+  }
+  const long long items = (long long)N * IH * nseg;
+  if (items <= 0 || items > 0x3fffffff) return MRFP_ERR_UNSUPPORTED;
+  DeviceInfo di;
+  int rc = get_device_info(&di);
+  if (rc) return rc;
+  const size_t smem = (size_t)kAYBytes + 2 * kADaBytes;
+  static const bool regc = !(getenv("MRFP_BULK_APPLY_REGC") && atoi(getenv("MRFP_BULK_APPLY_REGC")) == 0);
+  auto kern = regc ? bn_bwd_apply_bulk_kernel<true> : bn_bwd_apply_bulk_kernel<false>;
+  MRFP_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const long long cap = (long long)di.sm_count * (regc ? 3 : 4);
+  launch_k(kern, dim3((unsigned)(items < cap ? items : cap)), dim3(kBThreads), smem, stream, dA, y, dY, lo_h, lo_w,
+           stats, gamma, acc, N, C, IH, IW, OH, OW, count, pseg, nseg, (int)items, reverse ? 1 : 0);
+  MRFP_CUDA_TRY(cudaGetLastError());
+  return MRFP_OK;
+}
+
+namespace {
+}  // namespace
+
+int bn_bwd_reduce_bulk(const __nv_bfloat16* dA, const __nv_bfloat16* y, const int* idx_h, const int* idx_w,
+                       const int* host_idx_w, const float* stats, double* acc, int N, int C, int IH, int IW, int OH, int OW,
+                       bool reverse, cudaStream_t stream) {
+  if (C < 64 || C > kMaxC || (C & (C - 1))) return MRFP_ERR_UNSUPPORTED;
+  int nseg = (OW * 2 * C + kBDaBytes - 1) / kBDaBytes;
+  int pseg = (OW + nseg - 1) / nseg;                     // balanced segments
+  for (;;) {
+    bool ok = true;
+    nseg = (OW + pseg - 1) / pseg;
+    for (int sgi = 0; sgi < nseg && ok; ++sgi) {
+      const int ow0 = sgi * pseg, ow1 = (ow0 + pseg < OW ? ow0 + pseg : OW) - 1;
+      ok = (host_idx_w[ow1] - host_idx_w[ow0] + 1) * C * 2 <= kBYBytes;
+    }
+    if (ok) break;
+    if (--pseg < 8) return MRFP_ERR_UNSUPPORTED;
+  }
+  const long long items = (long long)N * OH * nseg;
+  if (items <= 0 || items > 0x3fffffff) return MRFP_ERR_UNSUPPORTED;
+  DeviceInfo di;
+  int rc = get_device_info(&di);
+  if (rc) return rc;
+  const size_t smem = (size_t)kBDaBytes + kBYBytes;
+  MRFP_CUDA_TRY(cudaFuncSetAttribute(bn_bwd_reduce_bulk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const long long cap = (long long)di.sm_count * 4;
+  launch_k(bn_bwd_reduce_bulk_kernel, dim3((unsigned)(items < cap ? items : cap)), dim3(kBThreads), smem, stream, dA, y, idx_h, idx_w,
+           stats, acc, N, C, IH, IW, OH, OW, pseg, nseg, (int)items, reverse ? 1 : 0);
+  MRFP_CUDA_TRY(cudaGetLastError());
+  return MRFP_OK;
+}
+
+namespace {
 }  // namespace
 
 // host_idx_w: the plan's host copy of idx_w (span check).  Returns MRFP_ERR_UNSUPPORTED when the geometry does not fit

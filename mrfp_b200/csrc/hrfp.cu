@@ -1015,9 +1015,15 @@ int hrfp_backward(const mrfp_hrfp_plan* P, const float* g_ocout, const float* g_
     const int grid_r = even_grid(P->N * st.oh, di.sm_count * 8), grid_a = even_grid(P->N * st.ch, di.sm_count * 9);
     if (gin) at_end = true;
     if (!reduced) {
-      static const bool ring_reduce = getenv("MRFP_RING_REDUCE") && atoi(getenv("MRFP_RING_REDUCE")) == 1;
+      // 0 LDG rows, 1 single ring per SM, 2 (default, measured best) several single-buffered bulk-copy CTAs per SM
+      static const int reduce_mode = getenv("MRFP_RING_REDUCE") ? atoi(getenv("MRFP_RING_REDUCE")) : 2;
+      const bool ring_reduce = reduce_mode == 1;
       int rr = MRFP_ERR_UNSUPPORTED;
-      if (tc && ring_reduce)
+      if (tc && reduce_mode == 2)
+        rr = bn_bwd_reduce_bulk(reinterpret_cast<const __nv_bfloat16*>(dA), reinterpret_cast<const __nv_bfloat16*>(Y),
+                                lut + st.idx_h, lut + st.idx_w, P->lut.data() + st.idx_w, stats, a, P->N, st.cout, st.ch, st.cw,
+                                st.oh, st.ow, l2_order && at_end, s);
+      else if (tc && ring_reduce)
         rr = bn_bwd_reduce_ring(reinterpret_cast<const __nv_bfloat16*>(dA), reinterpret_cast<const __nv_bfloat16*>(Y),
                                 lut + st.idx_h, lut + st.idx_w, P->lut.data() + st.idx_w, st.scale_w, stats, a, P->N, st.cout, st.ch,
                                 st.cw, st.oh, st.ow, l2_order && at_end, s);
@@ -1037,9 +1043,18 @@ int hrfp_backward(const mrfp_hrfp_plan* P, const float* g_ocout, const float* g_
       launch_k(bn_bwd_apply_identity_kernel<T>, dim3(di.sm_count * 8), dim3(256), 0, s, dA, Y, dY, stats, gamma[k], a, npix,
                st.cout, count, rev_apply);
     } else {
-      launch_k(regc ? bn_bwd_apply_kernel<T, true> : bn_bwd_apply_kernel<T, false>, dim3(grid_a), dim3(256), 0, s, dA, Y, dY,
-               lut + st.start_h, lut + st.cnt_h, lut + st.start_w, lut + st.cnt_w, stats, gamma[k], a, P->N, st.cout, st.ch,
-               st.cw, st.oh, st.ow, count, rev_apply);
+      static const bool bulk_apply = !(getenv("MRFP_BULK_APPLY") && atoi(getenv("MRFP_BULK_APPLY")) == 0);
+      int ra = MRFP_ERR_UNSUPPORTED;
+      if (tc && bulk_apply)
+        ra = bn_bwd_apply_bulk(reinterpret_cast<const __nv_bfloat16*>(dA), reinterpret_cast<const __nv_bfloat16*>(Y),
+                               reinterpret_cast<__nv_bfloat16*>(dY), lut + st.lo_h, lut + st.lo_w, P->lut.data() + st.lo_h,
+                               P->lut.data() + st.lo_w, stats, gamma[k], a, P->N, st.cout, st.ch, st.cw, st.oh, st.ow, count,
+                               rev_apply != 0, s);
+      if (ra == MRFP_ERR_UNSUPPORTED)
+        launch_k(regc ? bn_bwd_apply_kernel<T, true> : bn_bwd_apply_kernel<T, false>, dim3(grid_a), dim3(256), 0, s, dA, Y, dY,
+                 lut + st.start_h, lut + st.cnt_h, lut + st.start_w, lut + st.cnt_w, stats, gamma[k], a, P->N, st.cout, st.ch,
+                 st.cw, st.oh, st.ow, count, rev_apply);
+      else if (ra) return ra;
     }
     // dgrad: conv of dY (cout channels) with the rotated / transposed kernel -> dA_prev (cin channels)
     if (tc) {
@@ -1152,6 +1167,10 @@ extern "C" int mrfp_hrfp_plan_create(mrfp_hrfp_plan_t** out, int N, int cin, int
     st.start_w = (int)L.size(); L.resize(L.size() + cw, 0);
     for (int d = st.oh - 1; d >= 0; --d) { const int sidx = L[st.idx_h + d]; L[st.cnt_h + sidx]++; L[st.start_h + sidx] = d; }
     for (int d = st.ow - 1; d >= 0; --d) { const int sidx = L[st.idx_w + d]; L[st.cnt_w + sidx]++; L[st.start_w + sidx] = d; }
+    st.lo_h = (int)L.size(); L.resize(L.size() + ch + 1, 0);
+    st.lo_w = (int)L.size(); L.resize(L.size() + cw + 1, 0);
+    for (int sidx = 0, d = 0; sidx <= ch; ++sidx) { while (d < st.oh && L[st.idx_h + d] < sidx) ++d; L[st.lo_h + sidx] = d; }
+    for (int sidx = 0, d = 0; sidx <= cw; ++sidx) { while (d < st.ow && L[st.idx_w + d] < sidx) ++d; L[st.lo_w + sidx] = d; }
     st.max_rep = 0;
     for (int i = 0; i < ch; ++i) st.max_rep = L[st.cnt_h + i] > st.max_rep ? L[st.cnt_h + i] : st.max_rep;
     for (int i = 0; i < cw; ++i) st.max_rep = L[st.cnt_w + i] > st.max_rep ? L[st.cnt_w + i] : st.max_rep;

@@ -21,11 +21,21 @@ struct HrfpStage {
   int idx_h, idx_w;       // dst -> src index, [oh], [ow]
   int cnt_h, cnt_w;       // replication count of each src row/col, zero-padded to a tile multiple (+1 tile)
   int start_h, start_w;   // first dst index of each src row/col, [ch], [cw]
+  int lo_h, lo_w;         // first dst index whose source is >= s (monotone), [ch + 1], [cw + 1]: the replicas of source s
+                          // are dst [lo[s], lo[s + 1]); a source segment [a, b) gathers from the contiguous dst span [lo[a], lo[b])
   size_t y_off;           // conv output Y_k in `saved` (bytes)
   size_t wf_off;          // packed forward weights in ws (bytes)
   size_t wb_off;          // packed dgrad weights in `saved` (bytes)
 };
 
+// bulk-copy BN-backward apply pass (bn_ring.cu): dY = P*mask*sum(replicas of dA) - cnt*(Q + R*y); MRFP_ERR_UNSUPPORTED -> LDG kernel
+int bn_bwd_apply_bulk(const __nv_bfloat16* dA, const __nv_bfloat16* y, __nv_bfloat16* dY, const int* lo_h, const int* lo_w,
+                      const int* host_lo_h, const int* host_lo_w, const float* stats, const float* gamma, const double* acc,
+                      int N, int C, int IH, int IW, int OH, int OW, double count, bool reverse, cudaStream_t stream);
+// the same with several single-buffered CTAs per SM (bn_ring.cu)
+int bn_bwd_reduce_bulk(const __nv_bfloat16* dA, const __nv_bfloat16* y, const int* idx_h, const int* idx_w,
+                       const int* host_idx_w, const float* stats, double* acc, int N, int C, int IH, int IW, int OH, int OW,
+                       bool reverse, cudaStream_t stream);
 }  // namespace mrfp
 
 struct mrfp_hrfp_plan {
@@ -83,4 +93,12 @@ bool conv3x3_tc_supported(int cin, int cout);
 int bn_bwd_reduce_ring(const __nv_bfloat16* dA, const __nv_bfloat16* y, const int* idx_h, const int* idx_w,
                        const int* host_idx_w, float scale_w, const float* stats, double* acc, int N, int C, int IH, int IW,
                        int OH, int OW, bool reverse, cudaStream_t stream);
+// bulk-copy BN-backward apply pass (bn_ring.cu): dY = P*mask*sum(replicas of dA) - cnt*(Q + R*y); MRFP_ERR_UNSUPPORTED -> LDG kernel
+int bn_bwd_apply_bulk(const __nv_bfloat16* dA, const __nv_bfloat16* y, __nv_bfloat16* dY, const int* lo_h, const int* lo_w,
+                      const int* host_lo_h, const int* host_lo_w, const float* stats, const float* gamma, const double* acc,
+                      int N, int C, int IH, int IW, int OH, int OW, double count, bool reverse, cudaStream_t stream);
+// the same with several single-buffered CTAs per SM (bn_ring.cu)
+int bn_bwd_reduce_bulk(const __nv_bfloat16* dA, const __nv_bfloat16* y, const int* idx_h, const int* idx_w,
+                       const int* host_idx_w, const float* stats, double* acc, int N, int C, int IH, int IW, int OH, int OW,
+                       bool reverse, cudaStream_t stream);
 }  // namespace mrfp
