@@ -318,6 +318,93 @@ bn_bwd_apply_bulk_kernel(const __nv_bfloat16* __restrict__ dA, const __nv_bfloat
   }
 }
 
+
+// Forward element-wise pass of a stage in the same shape: A_next[n][oh][ow][:] = ReLU(scale * Y[n][ih[oh]][iw[ow]][:] + shift).
+// An item is a <= 16 KiB segment of one destination row; the span of the source row it gathers from arrives by one bulk
+// copy, the result goes from registers to global memory.
+constexpr int kFDstBytes = 16384;
+constexpr int kFYBytes = 21504;                 // 1.25x (x0.8 down-sampling stages) + one 256-channel pixel + slack
+
+__global__ void __launch_bounds__(kBThreads, 5)
+bn_relu_resample_bulk_kernel(const __nv_bfloat16* __restrict__ y, __nv_bfloat16* __restrict__ a, const int* __restrict__ idx_h,
+                             const int* __restrict__ idx_w, const float* __restrict__ scale, const float* __restrict__ shift,
+                             int N, int C, int IH, int IW, int OH, int OW, int pseg, int nseg, int items, int rev) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  __shared__ __align__(8) uint64_t bar;
+  const int tid = threadIdx.x;
+  const int cg = C >> 3, cgs = 31 - __clz(cg);
+  const int c = (tid & (cg - 1)) << 3, pl = tid >> cgs, pstep = kBThreads >> cgs;
+  if (tid == 0) { mbar_init(&bar, 1); mbar_fence_init(); }
+  __syncthreads();
+  pdl_sync();
+  float sc[8], sf[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { sc[j] = scale[c + j]; sf[j] = shift[c + j]; }
+  uint32_t phase = 0;
+  for (int it = blockIdx.x; it < items; it += gridDim.x) {
+    const int itr = rev ? items - 1 - it : it;
+    const int row = itr / nseg, seg = itr - row * nseg;
+    const int n = row / OH, oh = row - n * OH;
+    const int ow0 = seg * pseg, npx = min(pseg, OW - ow0);
+    const int s0 = idx_w[ow0];
+    if (tid == 0) {
+      const uint32_t yb = (uint32_t)((idx_w[ow0 + npx - 1] - s0 + 1) * C * 2);
+      mbar_expect_tx(&bar, yb);
+      bulk_load(smem_raw, y + (((long long)n * IH + idx_h[oh]) * IW + s0) * C, yb, &bar);
+    }
+    int j = pl < npx ? idx_w[ow0 + pl] - s0 : 0;         // first look-up travels with the copy
+    mbar_wait(&bar, phase);
+    phase ^= 1u;
+    __nv_bfloat16* dst = a + ((long long)row * OW + ow0) * C + c;
+    for (int px = pl; px < npx; px += pstep) {
+      const int jn = px + pstep < npx ? idx_w[ow0 + px + pstep] - s0 : 0;
+      float v[8];
+      unpack8(*reinterpret_cast<const uint4*>(smem_raw + ((size_t)j * C + c) * 2), v);
+      uint32_t w[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const __nv_bfloat162 h = __floats2bfloat162_rn(fmaxf(fmaf(sc[2 * i], v[2 * i], sf[2 * i]), 0.f),
+                                                       fmaxf(fmaf(sc[2 * i + 1], v[2 * i + 1], sf[2 * i + 1]), 0.f));
+        w[i] = *reinterpret_cast<const uint32_t*>(&h);
+      }
+      *reinterpret_cast<uint4*>(dst + (size_t)px * C) = make_uint4(w[0], w[1], w[2], w[3]);
+      j = jn;
+    }
+    __syncthreads();                                     // every read of the buffer precedes the next item's copy
+  }
+}
+
+}  // namespace
+
+int bn_relu_resample_bulk(const __nv_bfloat16* y, __nv_bfloat16* a, const int* idx_h, const int* idx_w, const int* host_idx_w,
+                          const float* scale, const float* shift, int N, int C, int IH, int IW, int OH, int OW, bool reverse,
+                          cudaStream_t stream) {
+  if (C < 64 || C > kMaxC || (C & (C - 1))) return MRFP_ERR_UNSUPPORTED;
+  int nseg = (OW * 2 * C + kFDstBytes - 1) / kFDstBytes;
+  int pseg = (OW + nseg - 1) / nseg;
+  for (;;) {
+    bool ok = true;
+    nseg = (OW + pseg - 1) / pseg;
+    for (int sgi = 0; sgi < nseg && ok; ++sgi) {
+      const int ow0 = sgi * pseg, ow1 = (ow0 + pseg < OW ? ow0 + pseg : OW) - 1;
+      ok = (host_idx_w[ow1] - host_idx_w[ow0] + 1) * C * 2 <= kFYBytes;
+    }
+    if (ok) break;
+    if (--pseg < 8) return MRFP_ERR_UNSUPPORTED;
+  }
+  const long long items = (long long)N * OH * nseg;
+  if (items <= 0 || items > 0x3fffffff) return MRFP_ERR_UNSUPPORTED;
+  DeviceInfo di;
+  int rc = get_device_info(&di);
+  if (rc) return rc;
+  const long long cap = (long long)di.sm_count * 5;
+  launch_k(bn_relu_resample_bulk_kernel, dim3((unsigned)(items < cap ? items : cap)), dim3(kBThreads), (size_t)kFYBytes, stream, y, a,
+           idx_h, idx_w, scale, shift, N, C, IH, IW, OH, OW, pseg, nseg, (int)items, reverse ? 1 : 0);
+  MRFP_CUDA_TRY(cudaGetLastError());
+  return MRFP_OK;
+}
+
+namespace {
 }  // namespace
 
 int bn_bwd_apply_bulk(const __nv_bfloat16* dA, const __nv_bfloat16* y, __nv_bfloat16* dY, const int* lo_h, const int* lo_w,

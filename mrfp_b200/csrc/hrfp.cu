@@ -959,9 +959,17 @@ int hrfp_forward(const mrfp_hrfp_plan* P, const float* xp, const float* const* W
                                                         stats + 2 * kMaxC, stats + 3 * kMaxC, st.cout, st.ch, st.cw,
                                                         st.oh, st.ow, np ? np->coef : (const float2*)nullptr, (const float*)nullptr, 0, 0);
     } else if (k + 1 < last) {
-      launch_k(bn_relu_resample_kernel<T>, dim3(even_grid(P->N * st.oh, di.sm_count * 8)), dim3(256), 0, s, 
-          Y, nxt, lut + st.idx_h, lut + st.idx_w, stats + 2 * kMaxC, stats + 3 * kMaxC, P->N, st.cout, st.ch, st.cw,
-          st.oh, st.ow, l2_order ? 1 : 0);
+      static const bool bulk_fwd = !(getenv("MRFP_BULK_RESAMPLE") && atoi(getenv("MRFP_BULK_RESAMPLE")) == 0);
+      int rf = MRFP_ERR_UNSUPPORTED;
+      if (tc && bulk_fwd)
+        rf = bn_relu_resample_bulk(reinterpret_cast<const __nv_bfloat16*>(Y), reinterpret_cast<__nv_bfloat16*>(nxt), lut + st.idx_h,
+                                   lut + st.idx_w, P->lut.data() + st.idx_w, stats + 2 * kMaxC, stats + 3 * kMaxC, P->N, st.cout,
+                                   st.ch, st.cw, st.oh, st.ow, l2_order, s);
+      if (rf == MRFP_ERR_UNSUPPORTED)
+        launch_k(bn_relu_resample_kernel<T>, dim3(even_grid(P->N * st.oh, di.sm_count * 8)), dim3(256), 0, s,
+                 Y, nxt, lut + st.idx_h, lut + st.idx_w, stats + 2 * kMaxC, stats + 3 * kMaxC, P->N, st.cout, st.ch, st.cw,
+                 st.oh, st.ow, l2_order ? 1 : 0);
+      else if (rf) return rf;
       T* t = cur; cur = nxt; nxt = t;
     }
   }

@@ -28,6 +28,10 @@ struct HrfpStage {
   size_t wb_off;          // packed dgrad weights in `saved` (bytes)
 };
 
+// bulk-copy forward element-wise pass (bn_ring.cu): A_next = ReLU(scale * gather(Y) + shift); MRFP_ERR_UNSUPPORTED -> LDG kernel
+int bn_relu_resample_bulk(const __nv_bfloat16* y, __nv_bfloat16* a, const int* idx_h, const int* idx_w, const int* host_idx_w,
+                          const float* scale, const float* shift, int N, int C, int IH, int IW, int OH, int OW, bool reverse,
+                          cudaStream_t stream);
 // bulk-copy BN-backward apply pass (bn_ring.cu): dY = P*mask*sum(replicas of dA) - cnt*(Q + R*y); MRFP_ERR_UNSUPPORTED -> LDG kernel
 int bn_bwd_apply_bulk(const __nv_bfloat16* dA, const __nv_bfloat16* y, __nv_bfloat16* dY, const int* lo_h, const int* lo_w,
                       const int* host_lo_h, const int* host_lo_w, const float* stats, const float* gamma, const double* acc,
@@ -93,6 +97,10 @@ bool conv3x3_tc_supported(int cin, int cout);
 int bn_bwd_reduce_ring(const __nv_bfloat16* dA, const __nv_bfloat16* y, const int* idx_h, const int* idx_w,
                        const int* host_idx_w, float scale_w, const float* stats, double* acc, int N, int C, int IH, int IW,
                        int OH, int OW, bool reverse, cudaStream_t stream);
+// bulk-copy forward element-wise pass (bn_ring.cu): A_next = ReLU(scale * gather(Y) + shift); MRFP_ERR_UNSUPPORTED -> LDG kernel
+int bn_relu_resample_bulk(const __nv_bfloat16* y, __nv_bfloat16* a, const int* idx_h, const int* idx_w, const int* host_idx_w,
+                          const float* scale, const float* shift, int N, int C, int IH, int IW, int OH, int OW, bool reverse,
+                          cudaStream_t stream);
 // bulk-copy BN-backward apply pass (bn_ring.cu): dY = P*mask*sum(replicas of dA) - cnt*(Q + R*y); MRFP_ERR_UNSUPPORTED -> LDG kernel
 int bn_bwd_apply_bulk(const __nv_bfloat16* dA, const __nv_bfloat16* y, __nv_bfloat16* dY, const int* lo_h, const int* lo_w,
                       const int* host_lo_h, const int* host_lo_w, const float* stats, const float* gamma, const double* acc,
