@@ -263,24 +263,26 @@ nhwc_to_nchw_kernel(const T* __restrict__ y, float* __restrict__ out, const floa
 // taps from four consecutive floats ran at 978 us), so the interpolation is made separable: one vertical blend of the
 // staged rows per tile, then two taps and three flops per output (same formula, different association: ~1 ulp from
 // ATen's).
-constexpr int kSegFloats = 80;
-constexpr size_t kStagedSmem = sizeof(float) * (64 * kLayRow + 64 * 2 * kSegFloats);
+constexpr int kSegFloats = 72;                  // 64 + taps + alignment, rounded up to a multiple of 4
+// CT channels per tile: 64 -> 71 KB (3 tiles per SM), 32 -> 35 KB (5-6 tiles per SM; the kernel is latency-bound, so the
+// narrower tile wins although it touches the NHWC side in 64-byte pieces)
+template <int CT> constexpr size_t staged_smem() { return sizeof(float) * (CT * kLayRow + CT * 2 * kSegFloats); }
 
-template <typename T>
-__global__ void __launch_bounds__(256)
+template <typename T, int CT>
+__global__ void __launch_bounds__(256, CT == 32 ? 5 : 3)
 hrfp_plus_bilinear_staged_kernel(const T* __restrict__ y, float* __restrict__ out, const int* __restrict__ idx_h,
                                  const int* __restrict__ idx_w, const float* __restrict__ scale, const float* __restrict__ shift,
                                  int C, int IH, int IW, int OH, int OW, const float* __restrict__ add_lo, int LH, int LW) {
   pdl_sync();
   extern __shared__ __align__(128) unsigned char smem_raw[];
   float (*tile)[kLayRow] = reinterpret_cast<float (*)[kLayRow]>(smem_raw);          // [channel][lay_col(pixel)]
-  float* stage = reinterpret_cast<float*>(smem_raw) + 64 * kLayRow;                 // [channel][row 0/1][kSegFloats]
+  float* stage = reinterpret_cast<float*>(smem_raw) + CT * kLayRow;                 // [channel][row 0/1][kSegFloats]
   __shared__ __align__(8) uint64_t bar;
-  const int ct = (C + 63) >> 6, rows = (int)(gridDim.x / (((OW + kLayPx - 1) / kLayPx) * ct));
+  const int ct = (C + CT - 1) / CT, rows = (int)(gridDim.x / (((OW + kLayPx - 1) / kLayPx) * ct));
   const int orow = blockIdx.x % rows, rem = blockIdx.x / rows;
   const int n = orow / OH, oh = orow - n * OH, t = threadIdx.x;
-  const int c0 = (rem % ct) * 64, w0 = (rem / ct) * kLayPx;
-  const int nch = min(64, C - c0);
+  const int c0 = (rem % ct) * CT, w0 = (rem / ct) * kLayPx;
+  const int nch = min(CT, C - c0);
   // ATen's upsample_bilinear2d(align_corners=True) source coordinates
   const float rh = OH > 1 ? (float)(LH - 1) / (float)(OH - 1) : 0.f;
   const float rw = OW > 1 ? (float)(LW - 1) / (float)(OW - 1) : 0.f;
@@ -304,15 +306,16 @@ hrfp_plus_bilinear_staged_kernel(const T* __restrict__ y, float* __restrict__ ou
   const int sh = idx_h ? idx_h[oh] : oh;
   const T* row = y + ((size_t)n * IH + sh) * IW * C;
   {
-    const int cg = t & 7, pl = t >> 3, c = c0 + cg * 8;
+    constexpr int CG = CT / 8, PL = 256 / CG;            // channel groups of 8, pixel lanes
+    const int cg = t % CG, pl = t / CG, c = c0 + cg * 8;
     float sc[8], sf[8];
     if (c < C) {
 #pragma unroll
       for (int j = 0; j < 8; ++j) { sc[j] = scale[c + j]; sf[j] = shift[c + j]; }
     }
 #pragma unroll
-    for (int pass = 0; pass < kLayPx / 32; ++pass) {
-      const int px = pl + pass * 32, ow = w0 + px;
+    for (int pass = 0; pass < kLayPx / PL; ++pass) {
+      const int px = pl + pass * PL, ow = w0 + px;
       float v[8];
 #pragma unroll
       for (int j = 0; j < 8; ++j) v[j] = 0.f;
@@ -328,12 +331,32 @@ hrfp_plus_bilinear_staged_kernel(const T* __restrict__ y, float* __restrict__ ou
   }
   __syncthreads();
   tma::mbar_wait(&bar, 0);
-  // vertical blend of the two staged rows, in place over row 0:  vb[c][k] = hl0 * r0[k] + hl1 * r1[k]
-  for (int e = t; e < nch * (cnt >> 2); e += 256) {
-    const int c = e / (cnt >> 2), k4 = e - c * (cnt >> 2);
-    float4* p0 = reinterpret_cast<float4*>(stage + (size_t)(2 * c) * kSegFloats) + k4;
-    const float4 a = *p0, b = *(reinterpret_cast<const float4*>(stage + (size_t)(2 * c + 1) * kSegFloats) + k4);
-    *p0 = make_float4(fmaf(hl1, b.x, hl0 * a.x), fmaf(hl1, b.y, hl0 * a.y), fmaf(hl1, b.z, hl0 * a.z), fmaf(hl1, b.w, hl0 * a.w));
+  // vertical blend of the two staged rows, vb[c][k] = hl0 * r0[k] + hl1 * r1[k], written back over row 0 SPLIT BY PARITY
+  // (even columns in floats [0, 36), odd columns in [36, 72)): at the x2 scale consecutive lanes read every second
+  // column, which is a 2-way bank conflict on the plain layout and conflict-free on the split one
+  {
+    constexpr int TPC = 256 / CT, NB = (kSegFloats / 4 + TPC - 1) / TPC;    // threads per channel, float4 per thread
+    const int c = t / TPC, k0 = t % TPC;
+    float4 bl[NB];
+#pragma unroll
+    for (int q = 0; q < NB; ++q) {
+      const int k4 = k0 + q * TPC;
+      if (c < nch && k4 < (cnt >> 2)) {
+        const float4 a = reinterpret_cast<const float4*>(stage + (size_t)(2 * c) * kSegFloats)[k4];
+        const float4 b = reinterpret_cast<const float4*>(stage + (size_t)(2 * c + 1) * kSegFloats)[k4];
+        bl[q] = make_float4(fmaf(hl1, b.x, hl0 * a.x), fmaf(hl1, b.y, hl0 * a.y), fmaf(hl1, b.z, hl0 * a.z), fmaf(hl1, b.w, hl0 * a.w));
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < NB; ++q) {
+      const int k4 = k0 + q * TPC;
+      if (c < nch && k4 < (cnt >> 2)) {
+        float* vb = stage + (size_t)(2 * c) * kSegFloats;
+        *reinterpret_cast<float2*>(vb + 2 * k4) = make_float2(bl[q].x, bl[q].z);
+        *reinterpret_cast<float2*>(vb + kSegFloats / 2 + 2 * k4) = make_float2(bl[q].y, bl[q].w);
+      }
+    }
   }
   __syncthreads();
   {
@@ -346,12 +369,13 @@ hrfp_plus_bilinear_staged_kernel(const T* __restrict__ y, float* __restrict__ ou
       const int ow = min(w0 + px + i, OW - 1);
       const float w1r = rw * (float)ow;
       const int w1 = (int)w1r;
-      o0[i] = w1 - ws;
-      o1[i] = o0[i] + (w1 < LW - 1 ? 1 : 0);
+      const int k0 = w1 - ws, k1 = k0 + (w1 < LW - 1 ? 1 : 0);
+      o0[i] = (k0 & 1) * (kSegFloats / 2) + (k0 >> 1);     // parity-split position of column k
+      o1[i] = (k1 & 1) * (kSegFloats / 2) + (k1 >> 1);
       wl1[i] = w1r - (float)w1; wl0[i] = 1.f - wl1[i];
     }
 #pragma unroll
-    for (int pass = 0; pass < 8; ++pass) {
+    for (int pass = 0; pass < CT / 8; ++pass) {
       const int c = crow + pass * 8, ow = w0 + px;
       if (c0 + c < C && ow < OW) {
         const size_t o = (((size_t)n * C + c0 + c) * OH + oh) * OW + ow;
@@ -1340,9 +1364,13 @@ static int hrfp_plus_add_impl(const mrfp_hrfp_plan* P, const char* saved, const 
   static const bool staged_on = !(getenv("MRFP_PLUS_STAGED") && atoi(getenv("MRFP_PLUS_STAGED")) == 0);
   // the reference's x2 Upsample: scale <= 1/2 bounds the staged span; 16-byte alignment for the bulk copies
   if (dec1_lo && staged_on && st.ow > 1 && 2 * (lw - 1) <= st.ow - 1 && (lw & 3) == 0 && ((uintptr_t)dec1_lo & 15) == 0) {
-    auto kern = hrfp_plus_bilinear_staged_kernel<T>;
-    MRFP_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kStagedSmem));
-    launch_k(kern, dim3(g), dim3(256), kStagedSmem, s, Y, out, lut + st.idx_h, lut + st.idx_w, stats + 2 * kMaxC, stats + 3 * kMaxC,
+    static const int ct_env = getenv("MRFP_PLUS_TILE_CH") ? atoi(getenv("MRFP_PLUS_TILE_CH")) : 32;
+    const int CT = ct_env == 64 ? 64 : 32;
+    const unsigned gs = (unsigned)(((st.ow + kLayPx - 1) / kLayPx) * ((st.cout + CT - 1) / CT)) * (unsigned)(P->N * st.oh);
+    auto kern = CT == 64 ? hrfp_plus_bilinear_staged_kernel<T, 64> : hrfp_plus_bilinear_staged_kernel<T, 32>;
+    const size_t smem = CT == 64 ? staged_smem<64>() : staged_smem<32>();
+    MRFP_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    launch_k(kern, dim3(gs), dim3(256), smem, s, Y, out, lut + st.idx_h, lut + st.idx_w, stats + 2 * kMaxC, stats + 3 * kMaxC,
              st.cout, st.ch, st.cw, st.oh, st.ow, dec1_lo, lh, lw);
     MRFP_CUDA_TRY(cudaGetLastError());
     return MRFP_OK;
