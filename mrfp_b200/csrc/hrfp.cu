@@ -93,7 +93,8 @@ nchw_to_nhwc_kernel(const float* __restrict__ src, T* __restrict__ dst, int C, i
                     double* __restrict__ psum) {
   pdl_sync();
   __shared__ float tile[64][kLayRow];   // [channel][lay_col(pixel)]
-  const int n = blockIdx.z, c0 = blockIdx.y * 64, p0 = blockIdx.x * kLayPx, t = threadIdx.x;
+  // channel tiles fastest in the grid: the CTAs that write the slices of the same NHWC pixels run together
+  const int n = blockIdx.z, c0 = blockIdx.x * 64, p0 = blockIdx.y * kLayPx, t = threadIdx.x;
   const float* s = src + (size_t)n * C * HW;
   T* d = dst + (size_t)n * C * HW;
   const bool vec = (HW & 3) == 0;
@@ -935,7 +936,7 @@ int hrfp_forward(const mrfp_hrfp_plan* P, const float* xp, const float* const* W
   T* bufB = reinterpret_cast<T*>(ws + P->bufs_off + P->buf_a_bytes);
   {
     const int HW = P->xh * P->xw;
-    dim3 g((HW + kLayPx - 1) / kLayPx, (P->cin + 63) / 64, P->N);
+    dim3 g((P->cin + 63) / 64, (HW + kLayPx - 1) / kLayPx, P->N);
     launch_k(nchw_to_nhwc_kernel<T>, dim3(g), dim3(256), 0, s, xp, bufA, P->cin, HW, 0, np ? np->psum : (double*)nullptr);
     if (np)      // NP+ call 1 folded into the chain: plane totals came with the layout pass, (a, b) per plane from one block
       launch_k(np_stem_coef_kernel<false>, dim3(1), dim3(256), 0, s, (const double*)np->psum, np->alpha, np->eps,
@@ -1032,7 +1033,7 @@ int hrfp_backward(const mrfp_hrfp_plan* P, const float* g_ocout, const float* g_
     if (k == 3 && dec_joined) gin = nullptr;               // already added by the dgrad of stage 4
     if (gin) {
       const int HW = st.oh * st.ow;
-      dim3 g((HW + kLayPx - 1) / kLayPx, (st.cout + 63) / 64, P->N);
+      dim3 g((st.cout + 63) / 64, (HW + kLayPx - 1) / kLayPx, P->N);
       T* dst = dA ? dA : g0;
       const bool np_here = np && k == kHrfpStages - 1;       // plane totals of g_ocout for the fused NP+ backward
       launch_k(nchw_to_nhwc_kernel<T>, dim3(g), dim3(256), 0, s, gin, dst, st.cout, HW, dA ? 1 : 0,
@@ -1112,7 +1113,7 @@ int hrfp_backward(const mrfp_hrfp_plan* P, const float* g_ocout, const float* g_
       if (join_dec && k == 4 && g_ocout_dec) {
         const HrfpStage& pv = P->st[3];
         const int HWp = pv.oh * pv.ow;
-        dim3 gd((HWp + kLayPx - 1) / kLayPx, (pv.cout + 63) / 64, P->N);
+        dim3 gd((pv.cout + 63) / 64, (HWp + kLayPx - 1) / kLayPx, P->N);
         launch_k(nchw_to_nhwc_kernel<T>, dim3(gd), dim3(256), 0, s, g_ocout_dec, dA, pv.cout, HWp, 0, (double*)nullptr);
         add_src = reinterpret_cast<const __nv_bfloat16*>(dA);
         dec_joined = true;
