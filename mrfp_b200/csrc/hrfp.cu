@@ -397,6 +397,115 @@ hrfp_plus_bilinear_staged_kernel(const T* __restrict__ y, float* __restrict__ ou
   }
 }
 
+// HRFP+ tail without the fp32 transposition tile (bf16 path).  The ablation of the staged kernel put 360 of its 724 us
+// on "gather Y, BN/ReLU, scalar stores into a [channel][pixel] fp32 tile, read the tile back".  Here the source-pixel span
+// of the tile's row arrives in shared memory AS bf16 NHWC (16-byte cp.async, chunks XOR-swizzled by the pixel index),
+// and `ldmatrix.x4.trans` hands every thread, for one fixed channel, PAIRS OF CONSECUTIVE DESTINATION PIXELS: the eight
+// row addresses a matrix takes are per-lane, so they also perform the nearest-neighbour gather.  BN/ReLU, the two
+// horizontal taps of the (vertically pre-blended) low-resolution row and the add happen in registers; a warp's store
+// instruction writes 32 contiguous bytes in each of eight channel planes.
+constexpr int kLdmSeg = 76;                     // row pitch in floats: 76 * ch mod 32 = 12 * ch mod 32 is distinct for 8 channels
+constexpr int kLdmSpan = 120;                   // source pixels a 128-pixel tile may gather from (128 * 332/384 + 2 = 113)
+constexpr size_t kLdmSmem = (size_t)kLdmSpan * 128 + sizeof(float) * 64 * 2 * kLdmSeg + 128 * sizeof(float4) + 128 * sizeof(int);
+
+__global__ void __launch_bounds__(256, 4)
+hrfp_plus_tail_ldm_kernel(const __nv_bfloat16* __restrict__ y, float* __restrict__ out, const int* __restrict__ idx_h,
+                          const int* __restrict__ idx_w, const float* __restrict__ scale, const float* __restrict__ shift,
+                          int C, int IH, int IW, int OH, int OW, const float* __restrict__ add_lo, int LH, int LW) {
+  pdl_sync();
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  unsigned char* ysm = smem_raw;                                                    // [span pixel][64 ch bf16], swizzled
+  float* stage = reinterpret_cast<float*>(smem_raw + (size_t)kLdmSpan * 128);       // [row 0/1][channel][kLdmSeg]
+  float4* pix = reinterpret_cast<float4*>(stage + 64 * 2 * kLdmSeg);               // per destination pixel: o0, o1, wl0, wl1
+  int* spx = reinterpret_cast<int*>(pix + 128);                                     // per destination pixel: source pixel - s0
+  __shared__ __align__(8) uint64_t bar;
+  const int ct = C >> 6, rows = (int)(gridDim.x / (((OW + kLayPx - 1) / kLayPx) * ct));
+  const int ctile = blockIdx.x % ct, rest = blockIdx.x / ct;                        // channel tiles fastest
+  const int orow = rest % rows, wtile = rest / rows;
+  const int n = orow / OH, oh = orow - n * OH, t = threadIdx.x;
+  const int c0 = ctile * 64, w0 = wtile * kLayPx;
+  const float rh = OH > 1 ? (float)(LH - 1) / (float)(OH - 1) : 0.f;               // ATen upsample_bilinear2d(align_corners=True)
+  const float rw = OW > 1 ? (float)(LW - 1) / (float)(OW - 1) : 0.f;
+  const float h1r = rh * (float)oh;
+  const int h1 = (int)h1r, h1p = h1 < LH - 1 ? 1 : 0;
+  const float hl1 = h1r - (float)h1, hl0 = 1.f - hl1;
+  const int ws = (int)(rw * (float)w0) & ~3;
+  const int w_last = min(w0 + kLayPx - 1, OW - 1);
+  const int w_hi = min(LW - 1, (int)(rw * (float)w_last) + 1);
+  const int cnt = min(kLdmSeg, (w_hi - ws + 4) & ~3);
+  if (t == 0) {
+    tma::mbar_init(&bar, 1);
+    tma::mbar_fence_init();
+    tma::mbar_expect_tx(&bar, (uint32_t)(64 * 2 * cnt) * 4u);
+  }
+  __syncthreads();
+  if (t < 128) {                                                                     // the two low-resolution rows of 64 channels
+    const int c = t >> 1, r = t & 1;
+    const float* src = add_lo + (((size_t)n * C + c0 + c) * LH + h1 + (r ? h1p : 0)) * LW + ws;
+    tma::bulk_load(stage + (size_t)(r * 64 + c) * kLdmSeg, src, (uint32_t)cnt * 4u, &bar);
+  }
+  // the span of the source row this tile gathers from, 64 channels of every pixel
+  const int s0 = idx_w[w0], nsp = idx_w[w_last] - s0 + 1;
+  const __nv_bfloat16* yrow = y + (((size_t)n * IH + idx_h[oh]) * IW + s0) * C + c0;
+  for (int e = t; e < nsp * 8; e += 256) {
+    const int p = e >> 3, ch = e & 7;
+    const uint32_t dst = tma::smem_u32(ysm + p * 128 + ((ch ^ (p & 7)) << 4));
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(yrow + (size_t)p * C + ch * 8) : "memory");
+  }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  if (t < 128) {
+    const int ow = min(w0 + t, OW - 1);
+    const float w1r = rw * (float)ow;
+    const int w1 = (int)w1r;
+    const float wl1 = w1r - (float)w1;
+    pix[t] = make_float4(__int_as_float(w1 - ws), __int_as_float(w1 - ws + (w1 < LW - 1 ? 1 : 0)), 1.f - wl1, wl1);
+    spx[t] = idx_w[ow] - s0;
+  }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  tma::mbar_wait(&bar, 0);
+  __syncthreads();
+  {                                                                                  // vertical blend in place over row 0
+    const int c = t >> 2;
+    float4* p0 = reinterpret_cast<float4*>(stage + (size_t)c * kLdmSeg);
+    const float4* p1 = reinterpret_cast<const float4*>(stage + (size_t)(64 + c) * kLdmSeg);
+    for (int k4 = t & 3; k4 < (cnt >> 2); k4 += 4) {
+      const float4 a = p0[k4], b = p1[k4];
+      p0[k4] = make_float4(fmaf(hl1, b.x, hl0 * a.x), fmaf(hl1, b.y, hl0 * a.y), fmaf(hl1, b.z, hl0 * a.z), fmaf(hl1, b.w, hl0 * a.w));
+    }
+  }
+  __syncthreads();
+  const int warp = t >> 5, lane = t & 31;
+  const int ch = warp * 8 + (lane >> 2);                                             // this thread's channel, whole kernel
+  const float sc = scale[c0 + ch], sf = shift[c0 + ch];
+  const float* vb = stage + (size_t)ch * kLdmSeg;
+  float* orow_p = out + (((size_t)n * C + c0 + ch) * OH + oh) * OW + w0;
+  const bool pair_ok = (OW & 1) == 0;
+#pragma unroll
+  for (int iter = 0; iter < 4; ++iter) {
+    // lane L supplies row (L & 7) of matrix (L >> 3): the source pixel of destination pixel (4 iter + L/8) * 8 + L%8
+    const int sidx = spx[(4 * iter + (lane >> 3)) * 8 + (lane & 7)];
+    const uint32_t addr = tma::smem_u32(ysm + sidx * 128 + ((warp ^ (sidx & 7)) << 4));
+    uint32_t r[4];
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+#pragma unroll
+    for (int m = 0; m < 4; ++m) {
+      const int px = (4 * iter + m) * 8 + 2 * (lane & 3);                            // this thread's pixel pair of matrix m
+      const float y0 = fmaxf(fmaf(sc, __uint_as_float(r[m] << 16), sf), 0.f);
+      const float y1 = fmaxf(fmaf(sc, __uint_as_float(r[m] & 0xffff0000u), sf), 0.f);
+      const float4 t0 = pix[px], t1 = pix[px + 1];
+      const float o0 = y0 + fmaf(t0.z, vb[__float_as_int(t0.x)], t0.w * vb[__float_as_int(t0.y)]);
+      const float o1 = y1 + fmaf(t1.z, vb[__float_as_int(t1.x)], t1.w * vb[__float_as_int(t1.y)]);
+      const int ow = w0 + px;
+      if (pair_ok && ow + 1 < OW) *reinterpret_cast<float2*>(orow_p + px) = make_float2(o0, o1);
+      else {
+        if (ow < OW) orow_p[px] = o0;
+        if (ow + 1 < OW) orow_p[px + 1] = o1;
+      }
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------------
 // forward element-wise pass: A_next[n][oh][ow][c] = ReLU(scale[c] * Y[n][ih[oh]][iw[ow]][c] + shift[c])
 // ------------------------------------------------------------------------------------------------------
@@ -1368,6 +1477,25 @@ static int hrfp_plus_add_impl(const mrfp_hrfp_plan* P, const char* saved, const 
   static const bool staged_on = !(getenv("MRFP_PLUS_STAGED") && atoi(getenv("MRFP_PLUS_STAGED")) == 0);
   // the reference's x2 Upsample: scale <= 1/2 bounds the staged span; 16-byte alignment for the bulk copies
   if (dec1_lo && staged_on && st.ow > 1 && 2 * (lw - 1) <= st.ow - 1 && (lw & 3) == 0 && ((uintptr_t)dec1_lo & 15) == 0) {
+    // bf16 path: the ldmatrix kernel when every tile's source span fits its buffer (host copy of the index table)
+    static const bool ldm_on = !(getenv("MRFP_PLUS_LDM") && atoi(getenv("MRFP_PLUS_LDM")) == 0);
+    if (ldm_on && sizeof(T) == 2 && (st.cout & 63) == 0 && (st.ow & 3) == 0) {
+      const int* hidx = P->lut.data() + st.idx_w;
+      bool fits = true;
+      for (int w0 = 0; w0 < st.ow && fits; w0 += kLayPx) {
+        const int w1 = (w0 + kLayPx < st.ow ? w0 + kLayPx : st.ow) - 1;
+        fits = hidx[w1] - hidx[w0] + 1 <= kLdmSpan;
+      }
+      if (fits) {
+        const unsigned gl = (unsigned)(((st.ow + kLayPx - 1) / kLayPx) * (st.cout / 64)) * (unsigned)(P->N * st.oh);
+        MRFP_CUDA_TRY(cudaFuncSetAttribute(hrfp_plus_tail_ldm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLdmSmem));
+        launch_k(hrfp_plus_tail_ldm_kernel, dim3(gl), dim3(256), kLdmSmem, s, reinterpret_cast<const __nv_bfloat16*>(Y), out,
+                 lut + st.idx_h, lut + st.idx_w, stats + 2 * kMaxC, stats + 3 * kMaxC, st.cout, st.ch, st.cw, st.oh, st.ow, dec1_lo,
+                 lh, lw);
+        MRFP_CUDA_TRY(cudaGetLastError());
+        return MRFP_OK;
+      }
+    }
     static const int ct_env = getenv("MRFP_PLUS_TILE_CH") ? atoi(getenv("MRFP_PLUS_TILE_CH")) : 32;
     const int CT = ct_env == 64 ? 64 : 32;
     const unsigned gs = (unsigned)(((st.ow + kLayPx - 1) / kLayPx) * ((st.cout + CT - 1) / CT)) * (unsigned)(P->N * st.oh);

@@ -245,7 +245,9 @@ def test_plus_add_with_bilinear_upsample_matches_aten(lo, mode):
     _, dec_b = hrfp_chain(xb, convs, bns, h, w, want_out=False, math_mode=mode, lazy_dec=True, update_running_stats=False)
     ob = hrfp_plus_add(F.interpolate(db, size=(h // 2, w // 2), mode="bilinear", align_corners=True), dec_b)
     ob.backward(g)
-    t_f, t_b = (2e-6, 5e-6) if mode == 0 else (TOL_VS_BF16_ORACLE["fwd"], TOL_VS_BF16_ORACLE["bwd"])
+    # both sides take OCout_dec from the same stored conv output, so the forward agrees tightly in either mode (bf16 mode:
+    # the BN statistics of the two chain runs differ in their last bits through the atomics' order)
+    t_f, t_b = (2e-6, 5e-6) if mode == 0 else (2e-5, TOL_VS_BF16_ORACLE["bwd"])
     assert (oa - ob).abs().max().item() <= t_f * ob.abs().max().item()
     assert torch.allclose(da.grad, db.grad, rtol=1e-6, atol=1e-6 * db.grad.abs().max().item())
     assert (xa.grad - xb.grad).abs().max().item() <= t_b * xb.grad.abs().max().item()
@@ -257,6 +259,24 @@ def test_plus_add_with_bilinear_upsample_matches_aten(lo, mode):
     interp = hrfp_plus_add_upsampled(d_lo, dec_d) - only_dec
     ref = F.interpolate(d_lo, size=(h // 2, w // 2), mode="bilinear", align_corners=True)
     assert (interp - ref).abs().max().item() <= 2e-6 * ref.abs().max().item() + 2e-6 * only_dec.abs().max().item()
+
+
+def test_plus_tail_multi_tile_bf16_matches_materialised_add():
+    """The ldmatrix tail kernel (bf16 path) on a row of three 128-pixel tiles, the last one partial: fused Upsample + add
+    from the low-resolution dec1 vs F.interpolate + the materialised add on the same chain state."""
+    import torch.nn.functional as F
+    from mrfp_b200.hrfp import hrfp_chain, hrfp_plus_add, hrfp_plus_add_upsampled
+    n, h, w, xh, xw = 1, 96, 544, 24, 136
+    ws, gs = make_hrfp_params(61)
+    convs, bns = _modules(ws, gs, "cuda")
+    xp = torch.from_numpy(make_feat(62, (n, 64, xh, xw))).cuda()
+    torch.manual_seed(63)
+    d_lo = torch.randn(n, 256, 24, 136, device="cuda")
+    _, dec = hrfp_chain(xp, convs, bns, h, w, want_out=False, math_mode=2, lazy_dec=True, update_running_stats=False)
+    fused = hrfp_plus_add_upsampled(d_lo, dec)
+    ref = hrfp_plus_add(F.interpolate(d_lo, size=(h // 2, w // 2), mode="bilinear", align_corners=True), dec)
+    assert fused.shape == (n, 256, 48, 272)
+    assert (fused - ref).abs().max().item() <= 2e-6 * ref.abs().max().item()
 
 
 def test_lazy_dec_handle_matches_materialised_path():
