@@ -145,6 +145,52 @@ nchw_to_nhwc_kernel(const float* __restrict__ src, T* __restrict__ dst, int C, i
   }
 }
 
+// The same conversion for the bf16 path without the fp32 tile (plain form: no accumulation, no plane sums): a thread
+// loads float4 = four consecutive pixels of one channel, packs two bf16 pairs, and `stmatrix.x4.trans` scatters the
+// transposed 8x8 blocks into a [pixel][64 channels] bf16 tile (the per-lane row addresses are chosen so that a float4 is
+// exactly the thread's share of two matrices: matrix rows {4i, 4i+1} and {4i+2, 4i+3}); the tile leaves as whole 128-byte
+// channel vectors.  16-byte chunks are XOR-swizzled so that both the matrix stores and the row reads spread over the banks.
+__device__ __forceinline__ int stm_swz(int px) { return (((px >> 2) & 3) << 1) | (px & 1); }
+
+__global__ void __launch_bounds__(256)
+nchw_to_nhwc_stm_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int C, int HW) {
+  pdl_sync();
+  __shared__ __align__(128) unsigned char sm[kLayPx * 128];        // [pixel][64 ch bf16]
+  const int n = blockIdx.z, c0 = blockIdx.x * 64, p0 = blockIdx.y * kLayPx, t = threadIdx.x;
+  const int warp = t >> 5, lane = t & 31, q = lane & 3;
+  const float* s = src + ((size_t)n * C + c0 + warp * 8 + (lane >> 2)) * HW + p0;   // this thread's channel row
+  // row of matrix m (= lane >> 3) this lane addresses: pixel (within a 32-pixel group) 16 (m >> 1) + 4 (j >> 1) + 2 (m & 1) + (j & 1)
+  const int j = lane & 7, m = lane >> 3;
+  const int prow = 16 * (m >> 1) + 4 * (j >> 1) + 2 * (m & 1) + (j & 1);
+#pragma unroll
+  for (int it = 0; it < kLayPx / 32; ++it) {
+    const int pa = it * 32 + 4 * q, pb = pa + 16;
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
+    if (p0 + pa < HW) a = *reinterpret_cast<const float4*>(s + pa);            // HW % 4 == 0: a float4 is in or out as a whole
+    if (p0 + pb < HW) b = *reinterpret_cast<const float4*>(s + pb);
+    uint32_t r[4];
+    {
+      const __nv_bfloat162 h0 = __floats2bfloat162_rn(a.x, a.y), h1 = __floats2bfloat162_rn(a.z, a.w);
+      const __nv_bfloat162 h2 = __floats2bfloat162_rn(b.x, b.y), h3 = __floats2bfloat162_rn(b.z, b.w);
+      r[0] = *reinterpret_cast<const uint32_t*>(&h0); r[1] = *reinterpret_cast<const uint32_t*>(&h1);
+      r[2] = *reinterpret_cast<const uint32_t*>(&h2); r[3] = *reinterpret_cast<const uint32_t*>(&h3);
+    }
+    const int px = it * 32 + prow;
+    const uint32_t addr = tma::smem_u32(sm + px * 128 + ((warp ^ stm_swz(px)) << 4));
+    asm volatile("stmatrix.sync.aligned.m8n8.x4.trans.shared.b16 [%0], {%1, %2, %3, %4};"
+                 ::"r"(addr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]) : "memory");
+  }
+  __syncthreads();
+  __nv_bfloat16* d = dst + ((size_t)n * HW + p0) * C + c0;
+#pragma unroll
+  for (int k = 0; k < kLayPx * 8 / 256; ++k) {
+    const int e = t + k * 256, px = e >> 3, chunk = e & 7;
+    if (p0 + px < HW)
+      *reinterpret_cast<uint4*>(d + (size_t)px * C + chunk * 8) =
+          *reinterpret_cast<const uint4*>(sm + px * 128 + ((chunk ^ stm_swz(px)) << 4));
+  }
+}
+
 // out fp32 [N][C][OH][OW] = f(Y[n][ih[oh]][iw[ow]][c]) (+ add), f = identity or ReLU(scale*y + shift)
 template <typename T, bool BILIN>
 __global__ void __launch_bounds__(256)
@@ -1223,7 +1269,11 @@ int hrfp_backward(const mrfp_hrfp_plan* P, const float* g_ocout, const float* g_
         const HrfpStage& pv = P->st[3];
         const int HWp = pv.oh * pv.ow;
         dim3 gd((pv.cout + 63) / 64, (HWp + kLayPx - 1) / kLayPx, P->N);
-        launch_k(nchw_to_nhwc_kernel<T>, dim3(gd), dim3(256), 0, s, g_ocout_dec, dA, pv.cout, HWp, 0, (double*)nullptr);
+        static const bool stm_on = !(getenv("MRFP_LAYOUT_STM") && atoi(getenv("MRFP_LAYOUT_STM")) == 0);
+        if (stm_on && sizeof(T) == 2 && (pv.cout & 63) == 0 && (HWp & 3) == 0 && ((uintptr_t)g_ocout_dec & 15) == 0)
+          launch_k(nchw_to_nhwc_stm_kernel, dim3(gd), dim3(256), 0, s, g_ocout_dec, reinterpret_cast<__nv_bfloat16*>(dA), pv.cout, HWp);
+        else
+          launch_k(nchw_to_nhwc_kernel<T>, dim3(gd), dim3(256), 0, s, g_ocout_dec, dA, pv.cout, HWp, 0, (double*)nullptr);
         add_src = reinterpret_cast<const __nv_bfloat16*>(dA);
         dec_joined = true;
         at_end = true;
