@@ -1,10 +1,16 @@
-// TMA-fed variants of the BN-backward passes of the HRFP chain (bf16 NHWC), sm_100a.
+// Bulk-copy (TMA 1-D) forms of the row passes of the HRFP chain (bf16 NHWC), sm_100a.
 //
-// The LDG-based row kernels in hrfp.cu plateau near 4.8 TB/s of HBM reads (ncu: warps on the long scoreboard, HBM
-// channels 32-63 % busy), while the bulk-copy ring of the NP+ kernel streams at 6 TB/s.  Same structure here: one
-// persistent CTA per SM, a producer warp that turns work items into 1-D bulk copies (cp.async.bulk + mbarrier
-// complete_tx) into a shared-memory ring, 16 consumer warps that compute from shared memory.  An item is one
-// 16 KiB segment of a gradient row plus the span of the saved conv-output row that its pixels gather from.
+// The LDG-based row kernels in hrfp.cu plateau near 4.3-4.8 TB/s of HBM reads (ncu: warps on the long scoreboard, HBM
+// channels 32-63 % busy).  Two shapes were built on `cp.async.bulk` + mbarrier complete_tx:
+//   * bn_bwd_reduce_ring_kernel  one persistent CTA per SM, a producer warp feeding a 5-slot shared-memory ring, 16
+//                                consumer warps (the NP+ structure) — SLOWER than the LDG kernel (865 vs 702 us), kept
+//                                as MRFP_RING_REDUCE=1;
+//   * *_bulk_kernel              several single-buffered CTAs per SM: a CTA copies one work item (a row segment of
+//                                <= 12-20 KiB plus the contiguous span of the other tensor it gathers from), waits,
+//                                computes from shared memory, writes results from registers and takes the next item;
+//                                the copy / compute / store phases of the 3-5 CTAs on an SM overlap each other.  This
+//                                is the adopted form of the forward BN/ReLU/resample pass and of the BN-backward
+//                                reduce and apply passes (521 / 573 / 675 us vs 550 / 720 / 850 us, profiles/README.md).
 #include "hrfp.cuh"
 #include "tma.cuh"
 

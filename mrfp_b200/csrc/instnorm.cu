@@ -15,6 +15,7 @@
 #include "tma.cuh"
 #include <cooperative_groups.h>
 #include <math.h>
+#include <atomic>
 
 namespace cg = cooperative_groups;
 
@@ -621,9 +622,14 @@ cudaError_t launch_ring(RingArgs a, int cs, int sm_count, cudaStream_t s) {
   cfg.attrs = at; cfg.numAttrs = 1;
   int ncl = sm_count / cs;                        // one CTA per SM; clusters that cannot be co-resident simply run later
   if (cs > 1) {
-    cfg.gridDim = dim3((unsigned)(ncl * cs));
-    int active = 0;
-    if (cudaOccupancyMaxActiveClusters(&active, kern, &cfg) == cudaSuccess && active > 0 && active < ncl) ncl = active;
+    static std::atomic<int> cached[2][kMaxCluster + 1];          // co-resident clusters per (direction, cluster size); 0 = not asked yet
+    int active = cached[BWD ? 1 : 0][cs].load(std::memory_order_relaxed);
+    if (active == 0) {
+      cfg.gridDim = dim3((unsigned)(ncl * cs));
+      if (cudaOccupancyMaxActiveClusters(&active, kern, &cfg) != cudaSuccess || active <= 0) active = ncl;
+      cached[BWD ? 1 : 0][cs].store(active, std::memory_order_relaxed);
+    }
+    if (active < ncl) ncl = active;
   }
   if (ncl > a.planes) ncl = a.planes;
   cfg.gridDim = dim3((unsigned)(ncl * cs));
