@@ -303,9 +303,9 @@ nhwc_to_nchw_kernel(const T* __restrict__ y, float* __restrict__ out, const floa
 
 // HRFP+ tail with the low-resolution operand STAGED by bulk copies (deepv3.py:356-357, the x2 Upsample of the reference
 // geometry).  The generic BILIN path above issues 16 scalar global loads per four outputs (about six distinct values):
-// it is bound by load latency, 909 us for 1.96 GB.  Here the two source rows a tile needs — for each of its 64 channels
+// it is bound by load latency, 909 us for 1.96 GB.  Here the two source rows a tile needs — for each of its CT channels
 // the span [ws, ws + cnt) of rows h1 and h1 + h1p, at most 80 floats when the scale is <= 1/2 — arrive in shared memory
-// as 128 1-D bulk copies (one per thread, one mbarrier) while the threads gather and transpose the tile of Y.  The
+// as 2 CT 1-D bulk copies (one per thread, one mbarrier) while the threads gather and transpose the tile of Y.  The
 // kernel is bound by instruction issue, not by memory (a staged variant that kept ATen's association and selected its
 // taps from four consecutive floats ran at 978 us), so the interpolation is made separable: one vertical blend of the
 // staged rows per tile, then two taps and three flops per output (same formula, different association: ~1 ulp from
