@@ -160,6 +160,50 @@ def test_wide_stem_128_channels(mode):
     assert _relerr(x.grad.cpu().numpy(), rg) <= t["bwd"]
 
 
+def test_shufflenet_stem_width_is_refused_loudly():
+    """24 channels (ShuffleNetV2 stem) is not a power of two: the row kernels keep fixed 8-channel groups per thread and
+    the plan refuses it (no silent fallback)."""
+    from mrfp_b200 import _lib
+    from mrfp_b200.hrfp import get_plan
+    with pytest.raises(_lib.MrfpError):
+        get_plan(2, 24, 16, 12, 64, 48, torch.device("cuda"), 0)
+
+
+@pytest.mark.parametrize("cin", [16])
+def test_narrow_stems_fp32_mode(cin):
+    """MobileNetV2-style stem (BASELINE config 5: 16 channels): OClayer1 is cin->64 and OCdeclayer4 64->cin.  No
+    tensor-core path exists for this width (K = 9*cin is not a multiple of 64), so it runs in the CUDA-core fp32 mode;
+    checked against the oracle with the same layer table (extension of SURVEY.md 8f-2)."""
+    n, h, w, xh, xw = 2, 64, 48, 16, 12
+    layers = ((cin, 64, 1), (64, 64, 1), (64, 128, 2), (128, 256, 2), (256, 128, 1), (128, 64, 1), (64, 64, 2), (64, cin, 2))
+    rng = np.random.default_rng(31)
+    ws = [(rng.standard_normal((co, ci, 3, 3)) * math.sqrt(2.0 / (9 * ci))).astype(np.float32) for ci, co, _ in layers]
+    gs = [(0.5 * rng.standard_normal(co)).astype(np.float32) for _, co, _ in layers]
+    xp = make_feat(32, (n, cin, xh, xw))
+    g1 = rng.standard_normal((n, cin, xh, xw)).astype(np.float32)
+    g2 = rng.standard_normal((n, 256, h // 2, w // 2)).astype(np.float32)
+    from mrfp_b200.hrfp import hrfp_chain
+    convs, bns = [], []
+    for (ci, co, dil), wt, g in zip(layers, ws, gs):
+        c = torch.nn.Conv2d(ci, co, 3, padding=dil, dilation=dil).to("cuda").requires_grad_(False)
+        b = torch.nn.BatchNorm2d(co).to("cuda").requires_grad_(False)
+        with torch.no_grad():
+            c.weight.copy_(torch.from_numpy(wt)); c.bias.zero_()
+            b.weight.copy_(torch.from_numpy(g)); b.bias.zero_()
+        convs.append(c); bns.append(b)
+    x = torch.from_numpy(xp).cuda().requires_grad_(True)
+    out, dec = hrfp_chain(x, convs, bns, h, w, math_mode=0)
+    torch.autograd.backward([out, dec], [torch.from_numpy(g1).cuda(), torch.from_numpy(g2).cuda()])
+    ws64 = [a.astype(np.float64) for a in ws]; gs64 = [a.astype(np.float64) for a in gs]
+    ro, rd, saved = O.hrfp_forward(xp.astype(np.float64), ws64, gs64, h, w, layers=layers)
+    rg = O.hrfp_backward(g1.astype(np.float64), g2.astype(np.float64), ws64, gs64, saved)
+    t = TOL[0]
+    assert out.shape == (n, cin, xh, xw)
+    assert _relerr(out.detach().cpu().numpy(), ro) <= t["fwd"]
+    assert _relerr(dec.detach().cpu().numpy(), rd) <= t["fwd"]
+    assert _relerr(x.grad.cpu().numpy(), rg) <= t["bwd"]
+
+
 @pytest.mark.parametrize("mode", [0, 2])
 def test_np_plus_folded_into_the_chain_equals_the_two_step_form(mode):
     """x = OCout + NP+(xp) (deepv3.py:316-330) through the fused entry points vs NP+ kernel followed by the chain with
