@@ -153,7 +153,7 @@ nchw_to_nhwc_kernel(const float* __restrict__ src, T* __restrict__ dst, int C, i
 __device__ __forceinline__ int stm_swz(int px) { return (((px >> 2) & 3) << 1) | (px & 1); }
 
 __global__ void __launch_bounds__(256)
-nchw_to_nhwc_stm_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int C, int HW) {
+nchw_to_nhwc_stm_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int C, int HW, double* __restrict__ psum) {
   pdl_sync();
   __shared__ __align__(128) unsigned char sm[kLayPx * 128];        // [pixel][64 ch bf16]
   const int n = blockIdx.z, c0 = blockIdx.x * 64, p0 = blockIdx.y * kLayPx, t = threadIdx.x;
@@ -162,12 +162,14 @@ nchw_to_nhwc_stm_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict
   // row of matrix m (= lane >> 3) this lane addresses: pixel (within a 32-pixel group) 16 (m >> 1) + 4 (j >> 1) + 2 (m & 1) + (j & 1)
   const int j = lane & 7, m = lane >> 3;
   const int prow = 16 * (m >> 1) + 4 * (j >> 1) + 2 * (m & 1) + (j & 1);
+  float csum = 0.f;                                   // this thread's share of its channel's plane total (fused NP+)
 #pragma unroll
   for (int it = 0; it < kLayPx / 32; ++it) {
     const int pa = it * 32 + 4 * q, pb = pa + 16;
     float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
     if (p0 + pa < HW) a = *reinterpret_cast<const float4*>(s + pa);            // HW % 4 == 0: a float4 is in or out as a whole
     if (p0 + pb < HW) b = *reinterpret_cast<const float4*>(s + pb);
+    csum += ((a.x + a.y) + (a.z + a.w)) + ((b.x + b.y) + (b.z + b.w));
     uint32_t r[4];
     {
       const __nv_bfloat162 h0 = __floats2bfloat162_rn(a.x, a.y), h1 = __floats2bfloat162_rn(a.z, a.w);
@@ -180,6 +182,11 @@ nchw_to_nhwc_stm_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict
     asm volatile("stmatrix.sync.aligned.m8n8.x4.trans.shared.b16 [%0], {%1, %2, %3, %4};"
                  ::"r"(addr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]) : "memory");
   }
+  if (psum) {                                         // the four lanes of a channel, then one double atomic per (CTA, channel)
+    csum += __shfl_xor_sync(0xffffffffu, csum, 1);
+    csum += __shfl_xor_sync(0xffffffffu, csum, 2);
+    if (q == 0) atomicAdd(psum + (size_t)n * C + c0 + warp * 8 + (lane >> 2), (double)csum);
+  }
   __syncthreads();
   __nv_bfloat16* d = dst + ((size_t)n * HW + p0) * C + c0;
 #pragma unroll
@@ -189,6 +196,13 @@ nchw_to_nhwc_stm_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict
       *reinterpret_cast<uint4*>(d + (size_t)px * C + chunk * 8) =
           *reinterpret_cast<const uint4*>(sm + px * 128 + ((chunk ^ stm_swz(px)) << 4));
   }
+}
+
+// the stmatrix kernel serves the bf16 path when the tile decomposition is exact (MRFP_LAYOUT_STM=0: always the fp32-tile kernel)
+template <typename T>
+static bool stm_layout_ok(int C, int HW, const float* src) {
+  static const bool on = !(getenv("MRFP_LAYOUT_STM") && atoi(getenv("MRFP_LAYOUT_STM")) == 0);
+  return on && sizeof(T) == 2 && (C & 63) == 0 && (HW & 3) == 0 && ((uintptr_t)src & 15) == 0;
 }
 
 // out fp32 [N][C][OH][OW] = f(Y[n][ih[oh]][iw[ow]][c]) (+ add), f = identity or ReLU(scale*y + shift)
@@ -1092,7 +1106,11 @@ int hrfp_forward(const mrfp_hrfp_plan* P, const float* xp, const float* const* W
   {
     const int HW = P->xh * P->xw;
     dim3 g((P->cin + 63) / 64, (HW + kLayPx - 1) / kLayPx, P->N);
-    launch_k(nchw_to_nhwc_kernel<T>, dim3(g), dim3(256), 0, s, xp, bufA, P->cin, HW, 0, np ? np->psum : (double*)nullptr);
+    if (stm_layout_ok<T>(P->cin, HW, xp))
+      launch_k(nchw_to_nhwc_stm_kernel, dim3(g), dim3(256), 0, s, xp, reinterpret_cast<__nv_bfloat16*>(bufA), P->cin, HW,
+               np ? np->psum : (double*)nullptr);
+    else
+      launch_k(nchw_to_nhwc_kernel<T>, dim3(g), dim3(256), 0, s, xp, bufA, P->cin, HW, 0, np ? np->psum : (double*)nullptr);
     if (np)      // NP+ call 1 folded into the chain: plane totals came with the layout pass, (a, b) per plane from one block
       launch_k(np_stem_coef_kernel<false>, dim3(1), dim3(256), 0, s, (const double*)np->psum, np->alpha, np->eps,
                (const float*)nullptr, np->coef, np->mean, np->beta, P->N, P->cin, HW);
@@ -1191,8 +1209,12 @@ int hrfp_backward(const mrfp_hrfp_plan* P, const float* g_ocout, const float* g_
       dim3 g((st.cout + 63) / 64, (HW + kLayPx - 1) / kLayPx, P->N);
       T* dst = dA ? dA : g0;
       const bool np_here = np && k == kHrfpStages - 1;       // plane totals of g_ocout for the fused NP+ backward
-      launch_k(nchw_to_nhwc_kernel<T>, dim3(g), dim3(256), 0, s, gin, dst, st.cout, HW, dA ? 1 : 0,
-               np_here ? np->psum : (double*)nullptr);
+      if (!dA && stm_layout_ok<T>(st.cout, HW, gin))        // plain conversion (nothing to accumulate into)
+        launch_k(nchw_to_nhwc_stm_kernel, dim3(g), dim3(256), 0, s, gin, reinterpret_cast<__nv_bfloat16*>(dst), st.cout, HW,
+                 np_here ? np->psum : (double*)nullptr);
+      else
+        launch_k(nchw_to_nhwc_kernel<T>, dim3(g), dim3(256), 0, s, gin, dst, st.cout, HW, dA ? 1 : 0,
+                 np_here ? np->psum : (double*)nullptr);
       if (np_here)
         launch_k(np_stem_coef_kernel<true>, dim3(1), dim3(256), 0, s, (const double*)np->psum, np->alpha, np->eps,
                  (const float*)np->mean, np->coef, (float*)nullptr, (float*)nullptr, P->N, P->cin, P->xh * P->xw);
@@ -1269,9 +1291,9 @@ int hrfp_backward(const mrfp_hrfp_plan* P, const float* g_ocout, const float* g_
         const HrfpStage& pv = P->st[3];
         const int HWp = pv.oh * pv.ow;
         dim3 gd((pv.cout + 63) / 64, (HWp + kLayPx - 1) / kLayPx, P->N);
-        static const bool stm_on = !(getenv("MRFP_LAYOUT_STM") && atoi(getenv("MRFP_LAYOUT_STM")) == 0);
-        if (stm_on && sizeof(T) == 2 && (pv.cout & 63) == 0 && (HWp & 3) == 0 && ((uintptr_t)g_ocout_dec & 15) == 0)
-          launch_k(nchw_to_nhwc_stm_kernel, dim3(gd), dim3(256), 0, s, g_ocout_dec, reinterpret_cast<__nv_bfloat16*>(dA), pv.cout, HWp);
+        if (stm_layout_ok<T>(pv.cout, HWp, g_ocout_dec))
+          launch_k(nchw_to_nhwc_stm_kernel, dim3(gd), dim3(256), 0, s, g_ocout_dec, reinterpret_cast<__nv_bfloat16*>(dA), pv.cout, HWp,
+                   (double*)nullptr);
         else
           launch_k(nchw_to_nhwc_kernel<T>, dim3(gd), dim3(256), 0, s, g_ocout_dec, dA, pv.cout, HWp, 0, (double*)nullptr);
         add_src = reinterpret_cast<const __nv_bfloat16*>(dA);
