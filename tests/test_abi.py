@@ -30,3 +30,28 @@ def test_strerror_and_version_without_gpu():
     assert b"shape" in lib.mrfp_strerror(-2)
     assert lib.mrfp_npplus_ws_bytes(8, 256, 36864) >= 8 * 256 * 5 * 8
     assert lib.mrfp_npplus_ws_bytes(0, 1, 1) == 0
+
+
+def test_host_wrappers_refuse_cpu_tensors_without_gpu():
+    """No CPU fallback behind the Python host either: the autograd Functions raise before any launch."""
+    import pytest
+    import torch
+    from mrfp_b200 import _lib
+    from mrfp_b200.instnorm import instance_norm_relu
+    from mrfp_b200.npplus import np_plus_with_draws, relu_with_plane_sums
+    x = torch.randn(2, 8, 4, 4)
+    with pytest.raises(_lib.MrfpError):
+        instance_norm_relu(x)
+    with pytest.raises(_lib.MrfpError):
+        relu_with_plane_sums(x)
+    with pytest.raises(_lib.MrfpError):
+        np_plus_with_draws(x, torch.ones(2, 8), torch.zeros(2, 8))
+
+
+def test_instnorm_argument_errors_without_gpu():
+    """Argument validation of the InstanceNorm entry points happens before any CUDA call."""
+    from mrfp_b200 import _lib
+    lib = _lib.load()
+    assert lib.mrfp_instnorm_fwd_f32(None, None, None, None, None, None, None, 1, 1, 1, 1e-5, 1, None) == -1
+    assert lib.mrfp_instnorm_bwd_f32(None, None, None, None, None, None, None, None, None, 1, 1, 1, 1, None) == -1
+    assert lib.mrfp_instnorm_fwd_f32(8, None, None, 8, 8, 8, None, 0, 1, 1, 1e-5, 1, None) == -2
