@@ -214,3 +214,27 @@ def test_instance_norm_relu_vs_reference_fixture(name):
     np.testing.assert_allclose(gw, g[f"{name}_gw"], rtol=1e-3, atol=1e-3)
     np.testing.assert_allclose(gb, g[f"{name}_gb"], rtol=1e-3, atol=1e-3)
     np.testing.assert_allclose(psum, y.sum(axis=(2, 3)))
+
+
+@pytest.mark.parametrize("shape,relu", [((2, 3, 5, 7), True), ((1, 6, 16, 16), True), ((3, 4, 9, 1), False), ((2, 8, 32, 24), True)])
+def test_instance_norm_relu_oracle_vs_torch_autograd_on_cpu(shape, relu):
+    """Second pin of the InstanceNorm oracle: torch's own F.instance_norm (+ relu) and its autograd in float64 on CPU —
+    the operators the reference's layers call (Resnet.py:176-178, :534-536)."""
+    import torch
+    import torch.nn.functional as F
+    from tests.common import make_in_case
+    x, gamma, beta, gy = make_in_case(500 + shape[1], shape)
+    xt = torch.from_numpy(x).double().requires_grad_(True)
+    wt = torch.from_numpy(gamma).double().requires_grad_(True)
+    bt = torch.from_numpy(beta).double().requires_grad_(True)
+    y = F.instance_norm(xt, weight=wt, bias=bt, eps=O.IN_EPS)
+    if relu:
+        y = F.relu(y)
+    y.backward(torch.from_numpy(gy).double())
+    oy, mean, invstd, psum = O.instance_norm_relu_forward(x, gamma, beta, relu=relu)
+    ogx, ogw, ogb = O.instance_norm_relu_backward(gy, x, gamma, beta, relu=relu)
+    np.testing.assert_allclose(oy, y.detach().numpy(), rtol=1e-10, atol=1e-10)
+    np.testing.assert_allclose(ogx, xt.grad.numpy(), rtol=1e-8, atol=1e-10)
+    np.testing.assert_allclose(ogw, wt.grad.numpy(), rtol=1e-9, atol=1e-9)
+    np.testing.assert_allclose(ogb, bt.grad.numpy(), rtol=1e-9, atol=1e-9)
+    np.testing.assert_allclose(mean, x.astype(np.float64).mean(axis=(2, 3)))
