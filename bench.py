@@ -167,21 +167,30 @@ def _use_reference_ops(model):
     model.fuse_layer1_np = False        # NP+ call 2: the eager sequence above, not the producer-fused kernels
 
 
-def train_bench(world, rank, dev, steps=8, warmup=3, global_batch=16, reference_ops=False, trunk="resnet-50"):
+def train_bench(world, rank, dev, steps=30, warmup=10, global_batch=16, reference_ops=False, trunk="resnet-50", graphs=True,
+                ddp_eager=False):
     """BASELINE config[2]: MRFP+ DeepLabV3+/ResNet-50 training step (main.py:845-871 recipe) on synthetic GTAV-shaped
-    768x768 crops, 19 classes, global batch 16 sharded over the ranks (DDP, NCCL gradient all-reduce is the only
-    collective; BatchNorm stays per-rank)."""
+    768x768 crops, 19 classes, `global_batch` sharded over the ranks.  The gradient all-reduce over NCCL is the only
+    collective; BatchNorm and the MRFP statistics stay per rank.
+
+    graphs=True: mrfp_b200.train_step.GraphedTrainStep — forward+backward replayed as a CUDA graph per gate combination,
+    one flat-buffer all-reduce, eager SGD step.  graphs=False: the same class without capture (eager launches).
+    ddp_eager=True: torch DistributedDataParallel + eager launches (round 1's configuration), for comparison.
+    The three MRFP gates are drawn ONCE PER GLOBAL STEP (same Python seed on every rank), as in the reference where one
+    forward call — one (p, p2, p3) — covers the whole batch (deepv3.py:281-283); alpha / eps / HRFP weights use per-rank
+    torch streams."""
     import random
     import torch
     import torch.distributed as dist
     from mrfp_b200.model import MRFPPlus
+    from mrfp_b200.train_step import GraphedTrainStep
     from mrfp_b200 import dist as D
     # host trunk: let cuDNN pick its fastest algorithms for the fixed shapes (applies equally to both MRFP-op variants)
     torch.backends.cudnn.benchmark = os.environ.get("MRFP_BENCH_CUDNN_AUTOTUNE", "1") != "0"
     lo, hi = D.shard_bounds(global_batch, world, rank)
     nb = hi - lo
     D.seed_rank_streams(3, rank)
-    random.seed(100 + rank)
+    random.seed(100)                                            # gates: one draw per global step, identical on every rank
     from mrfp_b200 import model as M
     M.FUSE_INSTNORM = (not reference_ops) and os.environ.get("MRFP_FUSE_INSTNORM", "1") != "0"   # reference arm: ATen InstanceNorm + ReLU
     model = MRFPPlus(19, trunk=trunk, criterion=torch.nn.CrossEntropyLoss(ignore_index=255)).to(dev)
@@ -190,39 +199,60 @@ def train_bench(world, rank, dev, steps=8, warmup=3, global_batch=16, reference_
     if world > 1:
         for p_ in model.parameters():                       # same start on every rank (DDP would broadcast rank 0 anyway)
             dist.broadcast(p_.data, 0)
-        model = torch.nn.parallel.DistributedDataParallel(model, device_ids=[dev.index], broadcast_buffers=False)
+    net = model
+    if ddp_eager and world > 1:
+        net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[dev.index], broadcast_buffers=False)
     opt = torch.optim.SGD([p_ for p_ in model.parameters() if p_.requires_grad], lr=1e-2, momentum=0.9, weight_decay=5e-4)
     img = torch.rand(nb, 3, H_IMG, W_IMG, device=dev) * 255.0       # the reference feeds un-normalised pixels
     lab = torch.randint(0, 19, (nb, H_IMG, W_IMG), device=dev)
     lab[torch.rand(nb, H_IMG, W_IMG, device=dev) < 0.05] = 255
 
-    def one():
-        opt.zero_grad(set_to_none=True)
-        loss = model(img, lab, training=True)
-        loss.backward()
-        opt.step()
-        return loss
+    if ddp_eager or reference_ops:
+        def one():
+            opt.zero_grad(set_to_none=True)
+            loss = net(img, lab, training=True)
+            loss.backward()
+            opt.step()
+            return loss
+        mode = "torch DDP, eager launches" if ddp_eager else "eager launches"
+    else:
+        stepper = GraphedTrainStep(model, opt, img, lab, eager_steps=2, use_graphs=graphs)
+        if graphs:
+            stepper.warm_all(img, lab)                          # untimed: every gate combination captured
+        def one():
+            return stepper(img, lab)
+        mode = "CUDA graph per gate combination (8), flat-buffer all-reduce, eager SGD" if graphs else "eager launches, flat-buffer all-reduce"
 
     for _ in range(warmup):
         one()
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
+        torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
     e0.record()
     for _ in range(steps):
         loss = one()
     e1.record()
+    host_ms = (time.perf_counter() - t0) * 1e3 / steps
     torch.cuda.synchronize()
     ms = D.max_over_ranks(e0.elapsed_time(e1), dev)
-    out = {"metric": "deeplabv3plus_%s_mrfp_plus_train_throughput" % {"resnet-50": "r50", "resnet-101": "r101"}[trunk], "mrfp_ops": "reference eager ATen/cuDNN" if reference_ops else "libmrfp_b200", "value": global_batch * steps / (ms * 1e-3), "unit": "img/s",
+    out = {"metric": "deeplabv3plus_%s_mrfp_plus_train_throughput" % {"resnet-50": "r50", "resnet-101": "r101"}[trunk],
+           "mrfp_ops": "reference eager ATen/cuDNN" if reference_ops else "libmrfp_b200", "value": global_batch * steps / (ms * 1e-3), "unit": "img/s",
            "global_batch": global_batch, "per_gpu_batch": nb, "steps": steps, "warmup": warmup, "ms_per_step": ms / steps,
-           "parallelism": f"ddp{world}", "loss_finite": bool(torch.isfinite(loss).item()),
+           "host_enqueue_ms_per_step": host_ms, "launch_mode": mode,
+           "parallelism": f"dp{world}", "loss_finite": bool(torch.isfinite(loss).item()),
            "instance_norm": "mrfp_instnorm cluster kernels" if M.FUSE_INSTNORM else "ATen",
            "precision": "fp32 host model (cuDNN TF32 default, as the reference on this torch; cudnn.benchmark=%s), bf16 tcgen05 HRFP, fp32 NP+" % torch.backends.cudnn.benchmark,
-           "gates": "natural Bernoulli(0.5) x3 per step (python random, seed 100+rank)", "data": "synthetic U[0,255) images, 19 classes, 5% ignore"}
-    del model, opt, img, lab
+           "gates": "natural Bernoulli(0.5) x3, one draw per global step (python random, seed 100 on every rank)",
+           "data": "synthetic U[0,255) images, 19 classes, 5% ignore"}
+    del model, net, opt, img, lab
+    if not (ddp_eager or reference_ops):
+        del stepper
     M.FUSE_INSTNORM = os.environ.get("MRFP_FUSE_INSTNORM", "1") != "0"
+    import gc
+    gc.collect()
     torch.cuda.empty_cache()
     return out
 
@@ -361,22 +391,34 @@ def run_ours(args):
         dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
     e2e_value = world * n * e2e_steps / (float(ms2.item()) * 1e-3)
 
-    # ---- BASELINE config[2]: the training step that hosts the path (all ranks) ----
+    # ---- BASELINE config[2] / [3]: the training step that hosts the path (all ranks) ----
     train = None
     if os.environ.get("MRFP_BENCH_TRAIN", "1") != "0":
         del host_in, host_out, dev_in
         torch.cuda.empty_cache()
+        keys = ("value", "unit", "ms_per_step", "host_enqueue_ms_per_step", "steps", "warmup", "global_batch", "per_gpu_batch",
+                "launch_mode", "mrfp_ops", "loss_finite")
         try:
-            train = train_bench(world, rank, dev)
-            ref_t = train_bench(world, rank, dev, steps=4, warmup=2, reference_ops=True)
-            train["same_step_with_reference_mrfp_ops"] = {k: ref_t[k] for k in ("value", "unit", "ms_per_step", "steps", "mrfp_ops")}
+            # strong scaling: global batch 16 (the configuration the BASELINE metric names), SURVEY §8d: 10 warm-up + 50 timed
+            train = train_bench(world, rank, dev, steps=50, warmup=10)
+            train["scaling"] = "strong (global batch 16)"
+            eager = train_bench(world, rank, dev, steps=10, warmup=5, graphs=False)
+            train["same_step_eager_launches"] = {k: eager[k] for k in keys}
+            if world > 1:
+                ddp = train_bench(world, rank, dev, steps=10, warmup=5, ddp_eager=True)
+                train["same_step_torch_ddp_eager"] = {k: ddp[k] for k in keys}
+            ref_t = train_bench(world, rank, dev, steps=10, warmup=5, reference_ops=True)
+            train["same_step_with_reference_mrfp_ops"] = {k: ref_t[k] for k in keys}
+            # weak scaling: per-GPU batch 8 (BASELINE config[1]'s per-GPU batch), global batch 8 x n_gpus
+            weak = train_bench(world, rank, dev, steps=30, warmup=10, global_batch=8 * world)
+            train["weak_scaling_per_gpu_batch_8"] = {k: weak[k] for k in keys}
             if os.environ.get("MRFP_BENCH_TRAIN_R101", "1") != "0":
                 # BASELINE config[3] per-GPU shard: ResNet-101 host, global batch 32 at 8 GPUs = 4 per GPU
-                r101 = train_bench(world, rank, dev, steps=4, warmup=2, global_batch=4 * world, trunk="resnet-101")
-                train["resnet101_config3_shard"] = {k: r101[k] for k in ("metric", "value", "unit", "ms_per_step", "steps", "global_batch",
-                                                                         "per_gpu_batch", "loss_finite")}
+                r101 = train_bench(world, rank, dev, steps=30, warmup=10, global_batch=4 * world, trunk="resnet-101")
+                train["resnet101_config3_shard"] = {k: r101[k] for k in ("metric",) + keys}
         except Exception as e:          # noqa: BLE001  (e.g. out of memory on a smaller GPU): report, do not hide
-            train = {"error": repr(e)[:300]}
+            import traceback
+            train = dict(train or {}, error=repr(e)[:400], traceback=traceback.format_exc()[-800:])
 
     if rank != 0:
         if world > 1:
@@ -415,7 +457,7 @@ def run_ours(args):
         mean = torch.empty(nn_, c, device=dev); beta = torch.empty(nn_, c, device=dev)
         al2, ep2 = al.reshape(nn_, c).contiguous(), ep.reshape(nn_, c).contiguous()
         wsb = lib.mrfp_npplus_ws_bytes(nn_, c, XH * XW)
-        wsp = torch.empty(wsb, dtype=torch.uint8, device=dev)
+        wsp = torch.zeros(wsb, dtype=torch.uint8, device=dev)         # control block zero on first use (mrfp_npplus_ws_init)
         bytes_alg = 2 * x_t.numel() * 4
         t_f = time_launch(lambda: _lib.check(lib.mrfp_npplus_fwd_f32(x_t.data_ptr(), al2.data_ptr(), ep2.data_ptr(), out.data_ptr(),
                                                                      mean.data_ptr(), beta.data_ptr(), wsp.data_ptr(), wsb, nn_, c, XH * XW, st), "np fwd"))

@@ -16,8 +16,10 @@
  *   - all work is enqueued on `stream` (a cudaStream_t passed as void*); no host synchronisation;
  *   - return value: 0 success; < 0 invalid argument (nothing was launched, see mrfp_strerror);
  *     > 0 a cudaError_t raised by a launch / attribute call;
- *   - re-entrant: no global mutable state except call_once-guarded per-device function attributes,
- *     safe under nn.DataParallel's per-device host threads and under DDP.
+ *   - re-entrant: no global mutable state except once-per-device function attributes and a mutex-guarded cache of TMA
+ *     descriptors inside each plan; safe under nn.DataParallel's per-device host threads and under DDP;
+ *   - every entry point may be called while `stream` is being captured into a CUDA graph (no synchronisation, no
+ *     allocation, no per-launch host state in kernel arguments).
  */
 #ifndef MRFP_B200_H_
 #define MRFP_B200_H_
@@ -38,6 +40,8 @@ extern "C" {
 #define MRFP_ERR_DRIVER        (-6)   /* cuTensorMapEncodeTiled entry point unavailable / failed */
 
 #define MRFP_MATH_FP32  0   /* CUDA-core direct convolution, fp32 activations (tight parity mode)   */
+#define MRFP_MATH_TF32  1   /* tcgen05 implicit-GEMM convolution, tf32 operands, fp32 activations and accumulation:
+                               the arithmetic of the reference's cuDNN convolutions under torch's TF32 default */
 #define MRFP_MATH_BF16  2   /* tcgen05 implicit-GEMM convolution, bf16 operands, fp32 accumulation  */
 
 int         mrfp_version(void);
@@ -58,6 +62,12 @@ const char* mrfp_strerror(int rc);
  * phase A from shared memory / L2.  N == 1 gives NaN exactly like torch.std (deepv3.py:272).
  * ---------------------------------------------------------------------------------------------- */
 size_t mrfp_npplus_ws_bytes(int N, int C, int HW);
+/* The first 64 bytes of `ws` are the kernel's queue counters: they must be ZERO when a buffer is used for the first time
+ * (mrfp_npplus_ws_init enqueues that memset; an allocation that zero-fills serves as well); from then on the kernels
+ * maintain them (the phase-A counter is cleared behind the first grid barrier of every launch, the phase-B counter at
+ * kernel entry), so one workspace serves any sequence of stream-ordered calls — including replays of a captured CUDA
+ * graph, since no per-launch host value enters the kernel. */
+int    mrfp_npplus_ws_init(void* ws, size_t ws_bytes, void* stream);
 
 int mrfp_npplus_fwd_f32(const float* x,       /* (N,C,HW) */
                         const float* alpha,   /* (N,C) draw #1 */

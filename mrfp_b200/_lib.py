@@ -17,6 +17,7 @@ SIGNATURES = {
     "mrfp_version": (ctypes.c_int, []),
     "mrfp_strerror": (ctypes.c_char_p, [ctypes.c_int]),
     "mrfp_npplus_ws_bytes": (ctypes.c_size_t, [ctypes.c_int, ctypes.c_int, ctypes.c_int]),
+    "mrfp_npplus_ws_init": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p]),
     "mrfp_npplus_fwd_f32": (ctypes.c_int, [c_float_p, c_float_p, c_float_p, c_float_p, c_float_p, c_float_p,
                                            ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int, ctypes.c_int,
                                            ctypes.c_int, ctypes.c_void_p]),
@@ -62,6 +63,17 @@ SIGNATURES = {
                                              ctypes.c_void_p]),
 }
 
+# test / bench hooks exported by the library but not declared in the public header (single kernels on caller buffers)
+DEBUG_SIGNATURES = {
+    "mrfp_debug_conv3x3_bf16": (ctypes.c_int, [ctypes.c_void_p] * 3 + [ctypes.c_int] * 6 + [ctypes.c_void_p] * 4),
+    "mrfp_debug_conv3x3_tf32": (ctypes.c_int, [ctypes.c_void_p] * 3 + [ctypes.c_int] * 6 + [ctypes.c_void_p] * 4),
+    "mrfp_debug_stage_op": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                           ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                           ctypes.c_void_p, ctypes.c_void_p]),
+    "mrfp_debug_nchw_to_nhwc": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                               ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]),
+}
+
 _lib = None
 
 
@@ -78,12 +90,43 @@ def load():
         raise MrfpError(f"{LIB_PATH} not found: build it with `python -m mrfp_b200.build` "
                         "(there is no CPU / PyTorch fallback for the MRFP kernels)")
     lib = ctypes.CDLL(LIB_PATH)
-    for name, (res, args) in SIGNATURES.items():
-        fn = getattr(lib, name)          # AttributeError if the symbol is not exported
-        fn.restype = res
-        fn.argtypes = args
+    for table in (SIGNATURES, DEBUG_SIGNATURES):
+        for name, (res, args) in table.items():
+            fn = getattr(lib, name)          # AttributeError if the symbol is not exported
+            fn.restype = res
+            fn.argtypes = args
     _lib = lib
     return lib
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# scratch memory: ONE grow-only, zero-initialised buffer per (device, stream) and purpose, shared by every call on that
+# stream (the kernels' scratch use is stream-ordered, nothing in it outlives a call).  Allocating per call costs a caching-
+# allocator round trip on the launch path and, per HRFP plan, pinned 1.7 GB for the life of the process.
+# ----------------------------------------------------------------------------------------------------------------------
+_SCRATCH = {}
+
+
+def scratch(device, nbytes: int, purpose: str = "ws"):
+    """uint8 tensor of >= nbytes on `device`, private to the current stream; zero-filled when (re)allocated — the NP+
+    kernels need their 64-byte control block zero on first use and re-arm it themselves afterwards (include/mrfp_b200.h)."""
+    import torch
+    device = torch.device(device)
+    key = (device.index if device.index is not None else torch.cuda.current_device(),
+           torch.cuda.current_stream(device).cuda_stream, purpose)
+    buf = _SCRATCH.get(key)
+    if buf is None or buf.numel() < nbytes:
+        if torch.cuda.is_current_stream_capturing():
+            raise MrfpError("scratch buffer would be (re)allocated during CUDA-graph capture: run the same shapes once "
+                            "eagerly on this stream before capturing")
+        buf = torch.zeros(max(int(nbytes), 256), dtype=torch.uint8, device=device)
+        _SCRATCH[key] = buf
+    return buf
+
+
+def release_scratch():
+    """Drops every cached scratch buffer (they are re-created on demand)."""
+    _SCRATCH.clear()
 
 
 def check(rc: int, what: str):

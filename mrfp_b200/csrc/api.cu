@@ -13,6 +13,7 @@ int get_device_info(DeviceInfo* out) {
   std::lock_guard<std::mutex> lock(mu);
   if (!filled[dev]) {
     DeviceInfo d;
+    d.device = dev;
     MRFP_CUDA_TRY(cudaDeviceGetAttribute(&d.sm_count, cudaDevAttrMultiProcessorCount, dev));
     MRFP_CUDA_TRY(cudaDeviceGetAttribute(&d.max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
     cache[dev] = d;

@@ -1,16 +1,12 @@
 // Bulk-copy (TMA 1-D) forms of the row passes of the HRFP chain (bf16 NHWC), sm_100a.
 //
 // The LDG-based row kernels in hrfp.cu plateau near 4.3-4.8 TB/s of HBM reads (ncu: warps on the long scoreboard, HBM
-// channels 32-63 % busy).  Two shapes were built on `cp.async.bulk` + mbarrier complete_tx:
-//   * bn_bwd_reduce_ring_kernel  one persistent CTA per SM, a producer warp feeding a 5-slot shared-memory ring, 16
-//                                consumer warps (the NP+ structure) — SLOWER than the LDG kernel (865 vs 702 us), kept
-//                                as MRFP_RING_REDUCE=1;
-//   * *_bulk_kernel              several single-buffered CTAs per SM: a CTA copies one work item (a row segment of
-//                                <= 12-20 KiB plus the contiguous span of the other tensor it gathers from), waits,
-//                                computes from shared memory, writes results from registers and takes the next item;
-//                                the copy / compute / store phases of the 3-5 CTAs on an SM overlap each other.  This
-//                                is the adopted form of the forward BN/ReLU/resample pass and of the BN-backward
-//                                reduce and apply passes (521 / 573 / 675 us vs 550 / 720 / 850 us, profiles/README.md).
+// channels 32-63 % busy).  Here every pass runs as several single-buffered CTAs per SM: a CTA copies one work item (a row
+// segment of <= 12-20 KiB plus the contiguous span of the other tensor it gathers from) with `cp.async.bulk` + mbarrier
+// complete_tx, waits, computes from shared memory, writes results from registers and takes the next item; the copy /
+// compute / store phases of the 3-5 CTAs on an SM overlap each other.  This is the form of the forward BN/ReLU/resample
+// pass and of the BN-backward reduce and apply passes on the bf16 path (521 / 573 / 675 us vs 550 / 720 / 850 us for the
+// LDG kernels; a single persistent ring per SM measured slower than both, profiles/README.md).
 #include "hrfp.cuh"
 #include "tma.cuh"
 
@@ -18,15 +14,6 @@ namespace mrfp {
 namespace {
 
 using namespace tma;
-
-constexpr int kRConsumers = 512;
-constexpr int kRWarps = kRConsumers / 32;
-constexpr int kRSlots = 5;
-constexpr int kDaBytes = 16384;                 // gradient segment
-constexpr int kYBytes = 24576;                  // gathered span of y (up to 1.5x the segment: down-sampling stages)
-constexpr int kSlotBytes = kDaBytes + kYBytes;
-
-struct RingMeta { int ow0, npx, s0, pad; };
 
 __device__ __forceinline__ void unpack8(const uint4 r, float (&v)[8]) {
   const uint32_t w[4] = {r.x, r.y, r.z, r.w};
@@ -38,117 +25,8 @@ __device__ __forceinline__ void unpack8(const uint4 r, float (&v)[8]) {
 }
 
 // U1[c] = sum mask*dA, U2[c] = sum mask*dA*y over all destination pixels; mask = [scale*y + shift > 0], y gathered.
-__global__ void __launch_bounds__(kRConsumers + 32, 1)
-bn_bwd_reduce_ring_kernel(const __nv_bfloat16* __restrict__ dA, const __nv_bfloat16* __restrict__ y,
-                          const int* __restrict__ idx_h, const int* __restrict__ idx_w, const float* __restrict__ stats,
-                          double* __restrict__ acc, int N, int C, int IH, int IW, int OH, int OW, int pseg, int nseg,
-                          int items, int rev, float scale_w) {
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  unsigned char* ring = smem_raw;
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + (size_t)kRSlots * kSlotBytes);
-  uint64_t* empty = full + kRSlots;
-  RingMeta* meta = reinterpret_cast<RingMeta*>(empty + kRSlots);
-  float* s_acc = reinterpret_cast<float*>(meta + kRSlots);        // [2 * kMaxC]
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-
-  if (tid == 0) {
-    for (int s = 0; s < kRSlots; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], kRWarps); }
-    mbar_fence_init();
-  }
-  for (int i = tid; i < 2 * kMaxC; i += kRConsumers + 32) s_acc[i] = 0.f;
-  __syncthreads();
-  pdl_sync();
-
-  if (warp == kRWarps) {
-    // ---------------- producer warp: 32 item descriptors at a time, lane 0 issues ----------------
-    int s = 0, k = 0;
-    const uint64_t pol = policy_evict_first();
-    for (int base = blockIdx.x; base < items; base += 32 * gridDim.x) {
-      const int it = base + lane * gridDim.x;
-      const bool valid = it < items;
-      int ow0 = 0, npx = 0, s0 = 0, ybytes = 0;
-      long long da_off = 0, y_off = 0;
-      if (valid) {
-        const int itr = rev ? items - 1 - it : it;
-        const int row = itr / nseg, seg = itr - row * nseg;
-        const int n = row / OH, oh = row - n * OH;
-        ow0 = seg * pseg;
-        npx = min(pseg, OW - ow0);
-        s0 = idx_w[ow0];
-        const int s1 = idx_w[ow0 + npx - 1];
-        ybytes = (s1 - s0 + 1) * C * 2;
-        da_off = ((long long)row * OW + ow0) * C;
-        y_off = (((long long)n * IH + idx_h[oh]) * IW + s0) * C;
-      }
-      const int cnt = __popc(__ballot_sync(0xffffffffu, valid));   // valid lanes are a prefix
-      for (int q = 0; q < cnt; ++q) {
-        const int q_ow0 = __shfl_sync(0xffffffffu, ow0, q), q_npx = __shfl_sync(0xffffffffu, npx, q);
-        const int q_s0 = __shfl_sync(0xffffffffu, s0, q), q_yb = __shfl_sync(0xffffffffu, ybytes, q);
-        const long long q_da = __shfl_sync(0xffffffffu, da_off, q), q_y = __shfl_sync(0xffffffffu, y_off, q);
-        if (lane == 0) {
-          if (k > 0) mbar_wait(&empty[s], (k - 1) & 1);
-          meta[s] = RingMeta{q_ow0, q_npx, q_s0, 0};
-          const uint32_t dab = (uint32_t)(q_npx * C * 2);
-          unsigned char* slot = ring + (size_t)s * kSlotBytes;
-          mbar_expect_tx(&full[s], dab + (uint32_t)q_yb);
-          bulk_load_hint(slot, dA + q_da, dab, &full[s], pol);
-          bulk_load_hint(slot + kDaBytes, y + q_y, (uint32_t)q_yb, &full[s], pol);
-        }
-        if (++s == kRSlots) { s = 0; ++k; }
-      }
-    }
-  } else {
-    // ---------------- consumers: thread = fixed 8-channel group, pixels strided ----------------
-    const int cg = C >> 3, cgs = 31 - __clz(cg);          // channel groups per pixel (power of two)
-    const int c = (tid & (cg - 1)) << 3;
-    float scale[8], shift[8], u1[8], u2[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      scale[j] = stats[2 * kMaxC + c + j]; shift[j] = stats[3 * kMaxC + c + j];
-      u1[j] = 0.f; u2[j] = 0.f;
-    }
-    int s = 0, k = 0;
-    for (int it = blockIdx.x; it < items; it += gridDim.x) {
-      mbar_wait(&full[s], k & 1);
-      const RingMeta m = meta[s];
-      const unsigned char* slot = ring + (size_t)s * kSlotBytes;
-      const int nel = m.npx << cgs;
-      for (int e = tid; e < nel; e += kRConsumers) {
-        const int px = e >> cgs;
-        // ATen's nearest rule, bit-identical to the idx_w table (single fp32 multiply, floor, clamp)
-        const int j = min((int)floorf(__fmul_rn((float)(m.ow0 + px), scale_w)), IW - 1) - m.s0;
-        float g[8], yv[8];
-        unpack8(*reinterpret_cast<const uint4*>(slot + ((size_t)px * C + c) * 2), g);
-        unpack8(*reinterpret_cast<const uint4*>(slot + kDaBytes + ((size_t)j * C + c) * 2), yv);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const float t = fmaf(scale[i], yv[i], shift[i]) > 0.f ? g[i] : 0.f;
-          u1[i] += t;
-          u2[i] = fmaf(t, yv[i], u2[i]);
-        }
-      }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&empty[s]);
-      if (++s == kRSlots) { s = 0; ++k; }
-    }
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      atomicAdd(&s_acc[c + j], u1[j]);
-      atomicAdd(&s_acc[kMaxC + c + j], u2[j]);
-    }
-    asm volatile("bar.sync 1, %0;" ::"n"(kRConsumers) : "memory");
-    for (int i = tid; i < C; i += kRConsumers) {
-      atomicAdd(acc + i, (double)s_acc[i]);
-      atomicAdd(acc + kMaxC + i, (double)s_acc[kMaxC + i]);
-    }
-  }
-}
-
-
-// Same reduction with SEVERAL single-buffered CTAs per SM instead of one ring: each CTA copies one item (a <= 20 KiB
-// gradient segment + the gathered span of the conv-output row) into its own buffer, waits, reduces from shared memory and
-// takes the next item; four such CTAs per SM overlap each other's copy and compute phases (the shape that worked for the
-// InstanceNorm kernels, where a single serialised consumer group per SM lost to independent one-shot CTAs).
+// Each CTA copies one item (a <= 20 KiB gradient segment + the gathered span of the conv-output row) into its own buffer,
+// waits, reduces from shared memory and takes the next item; four such CTAs per SM overlap each other's phases.
 constexpr int kBDaBytes = 20480;
 constexpr int kBYBytes = 26624;                 // 1.25x the segment (x0.8 down-sampling stages) + one pixel of 256 channels + slack
 constexpr int kBThreads = 256;
@@ -228,12 +106,11 @@ bn_bwd_reduce_bulk_kernel(const __nv_bfloat16* __restrict__ dA, const __nv_bfloa
 constexpr int kAYBytes = 12288;
 constexpr int kADaBytes = 16384;                // per destination row: 1.25x the segment + one 256-channel pixel + slack
 
-template <bool REGC>
-__global__ void __launch_bounds__(kBThreads, REGC ? 3 : 4)
+__global__ void __launch_bounds__(kBThreads, 3)
 bn_bwd_apply_bulk_kernel(const __nv_bfloat16* __restrict__ dA, const __nv_bfloat16* __restrict__ y, __nv_bfloat16* __restrict__ dY,
                          const int* __restrict__ lo_h, const int* __restrict__ lo_w, const float* __restrict__ stats,
                          const float* __restrict__ gamma, const double* __restrict__ acc, int N, int C, int IH, int IW, int OH,
-                         int OW, double count, int pseg, int nseg, int items, int rev) {
+                         int OW, double count, int pseg, int nseg, int items, int rev, int c_real) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   unsigned char* s_y = smem_raw;
   unsigned char* s_da = smem_raw + kAYBytes;             // [2][kADaBytes]
@@ -245,7 +122,7 @@ bn_bwd_apply_bulk_kernel(const __nv_bfloat16* __restrict__ dA, const __nv_bfloat
   if (tid == 0) { mbar_init(&bar, 1); mbar_fence_init(); }
   pdl_sync();
   for (int j = tid; j < C; j += kBThreads) {
-    const double mean = stats[j], invstd = stats[kMaxC + j], gm = gamma[j];
+    const double mean = stats[j], invstd = stats[kMaxC + j], gm = j < c_real ? gamma[j] : 0.f;   // padded channels: dY = 0
     s_scale[j] = stats[2 * kMaxC + j]; s_shift[j] = stats[3 * kMaxC + j];
     const double S1 = acc[j], S2 = invstd * (acc[kMaxC + j] - mean * S1);
     const double M1 = gm * S1 / count, M2 = gm * S2 / count;
@@ -257,8 +134,9 @@ bn_bwd_apply_bulk_kernel(const __nv_bfloat16* __restrict__ dA, const __nv_bfloat
     const float4 a = *reinterpret_cast<const float4*>(t + c), b = *reinterpret_cast<const float4*>(t + c + 4);
     v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
   };
-  float r_scale[8], r_shift[8], r_P[8], r_Q[8], r_R[8];   // REGC: the thread's constants stay in registers (3 CTAs per SM)
-  if (REGC) { ld8(s_scale, r_scale); ld8(s_shift, r_shift); ld8(s_P, r_P); ld8(s_Q, r_Q); ld8(s_R, r_R); }
+  // the thread's constants stay in registers (3 CTAs per SM; reading them from shared memory at 4 CTAs per SM: 808 vs 680 us)
+  float r_scale[8], r_shift[8], r_P[8], r_Q[8], r_R[8];
+  ld8(s_scale, r_scale); ld8(s_shift, r_shift); ld8(s_P, r_P); ld8(s_Q, r_Q); ld8(s_R, r_R);
   uint32_t phase = 0;
   for (int it = blockIdx.x; it < items; it += gridDim.x) {
     const int itr = rev ? items - 1 - it : it;
@@ -282,7 +160,7 @@ bn_bwd_apply_bulk_kernel(const __nv_bfloat16* __restrict__ dA, const __nv_bfloat
     for (int x = pl; x < npx; x += pstep) {
       int nw0 = 0, nw1 = 0;
       if (x + pstep < npx) { nw0 = lo_w[x0 + x + pstep]; nw1 = lo_w[x0 + x + pstep + 1]; }
-      float sd[8], yv[8], k0[8], k1[8], o[8];
+      float sd[8], yv[8], o[8];
 #pragma unroll
       for (int j = 0; j < 8; ++j) sd[j] = 0.f;
       for (int a = 0; a < nh; ++a)
@@ -294,22 +172,10 @@ bn_bwd_apply_bulk_kernel(const __nv_bfloat16* __restrict__ dA, const __nv_bfloat
         }
       unpack8(*reinterpret_cast<const uint4*>(s_y + ((size_t)x * C + c) * 2), yv);
       const float cnt = (float)(nh * (w1 - w0));
-      if (REGC) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float t = fmaf(r_scale[j], yv[j], r_shift[j]) > 0.f ? sd[j] : 0.f;
-          o[j] = r_P[j] * t - cnt * fmaf(r_R[j], yv[j], r_Q[j]);
-        }
-      } else {
-        ld8(s_scale, k0); ld8(s_shift, k1);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) o[j] = fmaf(k0[j], yv[j], k1[j]) > 0.f ? sd[j] : 0.f;
-        ld8(s_P, k0);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) o[j] *= k0[j];
-        ld8(s_R, k0); ld8(s_Q, k1);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) o[j] -= cnt * fmaf(k0[j], yv[j], k1[j]);
+      for (int j = 0; j < 8; ++j) {
+        const float t = fmaf(r_scale[j], yv[j], r_shift[j]) > 0.f ? sd[j] : 0.f;
+        o[j] = r_P[j] * t - cnt * fmaf(r_R[j], yv[j], r_Q[j]);
       }
       uint32_t w[4];
 #pragma unroll
@@ -410,12 +276,9 @@ int bn_relu_resample_bulk(const __nv_bfloat16* y, __nv_bfloat16* a, const int* i
   return MRFP_OK;
 }
 
-namespace {
-}  // namespace
-
 int bn_bwd_apply_bulk(const __nv_bfloat16* dA, const __nv_bfloat16* y, __nv_bfloat16* dY, const int* lo_h, const int* lo_w,
                       const int* host_lo_h, const int* host_lo_w, const float* stats, const float* gamma, const double* acc,
-                      int N, int C, int IH, int IW, int OH, int OW, double count, bool reverse, cudaStream_t stream) {
+                      int N, int C, int IH, int IW, int OH, int OW, double count, bool reverse, cudaStream_t stream, int c_real) {
   if (C < 64 || C > kMaxC || (C & (C - 1))) return MRFP_ERR_UNSUPPORTED;
   for (int i = 0; i < IH; ++i)
     if (host_lo_h[i + 1] - host_lo_h[i] > 2) return MRFP_ERR_UNSUPPORTED;        // two destination-row buffers
@@ -437,18 +300,14 @@ int bn_bwd_apply_bulk(const __nv_bfloat16* dA, const __nv_bfloat16* y, __nv_bflo
   int rc = get_device_info(&di);
   if (rc) return rc;
   const size_t smem = (size_t)kAYBytes + 2 * kADaBytes;
-  static const bool regc = !(getenv("MRFP_BULK_APPLY_REGC") && atoi(getenv("MRFP_BULK_APPLY_REGC")) == 0);
-  auto kern = regc ? bn_bwd_apply_bulk_kernel<true> : bn_bwd_apply_bulk_kernel<false>;
-  MRFP_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  const long long cap = (long long)di.sm_count * (regc ? 3 : 4);
-  launch_k(kern, dim3((unsigned)(items < cap ? items : cap)), dim3(kBThreads), smem, stream, dA, y, dY, lo_h, lo_w,
-           stats, gamma, acc, N, C, IH, IW, OH, OW, count, pseg, nseg, (int)items, reverse ? 1 : 0);
+  MRFP_SMEM_OPT_IN(bn_bwd_apply_bulk_kernel, smem, di.device);
+  const long long cap = (long long)di.sm_count * 3;
+  launch_k(bn_bwd_apply_bulk_kernel, dim3((unsigned)(items < cap ? items : cap)), dim3(kBThreads), smem, stream, dA, y, dY, lo_h,
+           lo_w, stats, gamma, acc, N, C, IH, IW, OH, OW, count, pseg, nseg, (int)items, reverse ? 1 : 0,
+           c_real > 0 ? c_real : C);
   MRFP_CUDA_TRY(cudaGetLastError());
   return MRFP_OK;
 }
-
-namespace {
-}  // namespace
 
 int bn_bwd_reduce_bulk(const __nv_bfloat16* dA, const __nv_bfloat16* y, const int* idx_h, const int* idx_w,
                        const int* host_idx_w, const float* stats, double* acc, int N, int C, int IH, int IW, int OH, int OW,
@@ -472,40 +331,10 @@ int bn_bwd_reduce_bulk(const __nv_bfloat16* dA, const __nv_bfloat16* y, const in
   int rc = get_device_info(&di);
   if (rc) return rc;
   const size_t smem = (size_t)kBDaBytes + kBYBytes;
-  MRFP_CUDA_TRY(cudaFuncSetAttribute(bn_bwd_reduce_bulk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  MRFP_SMEM_OPT_IN(bn_bwd_reduce_bulk_kernel, smem, di.device);
   const long long cap = (long long)di.sm_count * 4;
   launch_k(bn_bwd_reduce_bulk_kernel, dim3((unsigned)(items < cap ? items : cap)), dim3(kBThreads), smem, stream, dA, y, idx_h, idx_w,
            stats, acc, N, C, IH, IW, OH, OW, pseg, nseg, (int)items, reverse ? 1 : 0);
-  MRFP_CUDA_TRY(cudaGetLastError());
-  return MRFP_OK;
-}
-
-namespace {
-}  // namespace
-
-// host_idx_w: the plan's host copy of idx_w (span check).  Returns MRFP_ERR_UNSUPPORTED when the geometry does not fit
-// the ring (the caller then uses the LDG kernel).
-int bn_bwd_reduce_ring(const __nv_bfloat16* dA, const __nv_bfloat16* y, const int* idx_h, const int* idx_w,
-                       const int* host_idx_w, float scale_w, const float* stats, double* acc, int N, int C, int IH, int IW,
-                       int OH, int OW, bool reverse, cudaStream_t stream) {
-  if (C < 64 || C > kMaxC || (C & (C - 1))) return MRFP_ERR_UNSUPPORTED;
-  const int pseg = kDaBytes / (2 * C);
-  const int nseg = (OW + pseg - 1) / pseg;
-  for (int sgi = 0; sgi < nseg; ++sgi) {
-    const int ow0 = sgi * pseg, ow1 = (ow0 + pseg < OW ? ow0 + pseg : OW) - 1;
-    if ((host_idx_w[ow1] - host_idx_w[ow0] + 1) * C * 2 > kYBytes) return MRFP_ERR_UNSUPPORTED;
-  }
-  const long long items = (long long)N * OH * nseg;
-  if (items <= 0 || items > 0x3fffffff) return MRFP_ERR_UNSUPPORTED;
-  DeviceInfo di;
-  int rc = get_device_info(&di);
-  if (rc) return rc;
-  const size_t smem = (size_t)kRSlots * kSlotBytes + 2 * kRSlots * 8 + kRSlots * sizeof(RingMeta) + 2 * kMaxC * 4;
-  if (smem > (size_t)di.max_smem_optin) return MRFP_ERR_UNSUPPORTED;
-  MRFP_CUDA_TRY(cudaFuncSetAttribute(bn_bwd_reduce_ring_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  const int grid = items < di.sm_count ? (int)items : di.sm_count;
-  launch_k(bn_bwd_reduce_ring_kernel, dim3(grid), dim3(kRConsumers + 32), smem, stream, dA, y, idx_h, idx_w, stats, acc, N, C,
-           IH, IW, OH, OW, pseg, nseg, (int)items, reverse ? 1 : 0, scale_w);
   MRFP_CUDA_TRY(cudaGetLastError());
   return MRFP_OK;
 }

@@ -6,6 +6,7 @@
 #include <stddef.h>
 #include <stdlib.h>
 #include <utility>
+#include <atomic>
 #include "../../include/mrfp_b200.h"
 
 #define MRFP_CUDA_TRY(expr)                          \
@@ -17,6 +18,7 @@
 namespace mrfp {
 
 struct DeviceInfo {
+  int device;
   int sm_count;
   int max_smem_optin;
 };
@@ -29,23 +31,25 @@ __host__ __device__ inline size_t align_up(size_t v, size_t a) { return (v + a -
 // starts with pdl_sync().  The trigger lets the NEXT kernel be scheduled (block launch, barrier / TMEM set-up,
 // descriptor fetch) while this one is still running; the wait returns only when all prerequisite grids have
 // completed and flushed, so every global access behind it sees the same ordering as a plain stream launch.
-__device__ __forceinline__ void pdl_sync() {
-#ifdef MRFP_PDL_EARLY_TRIGGER
-  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-#endif
-  asm volatile("griddepcontrol.wait;" ::: "memory");
-}
-inline bool pdl_enabled() {
-  static const bool on = !(getenv("MRFP_PDL") && atoi(getenv("MRFP_PDL")) == 0);
-  return on;
-}
+__device__ __forceinline__ void pdl_sync() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) once per (kernel, device): `flag` is a static of the call site
+#define MRFP_SMEM_OPT_IN(kern, bytes, device)                                                              \
+  do {                                                                                                     \
+    static std::atomic<unsigned long long> _done{0};                                                       \
+    const unsigned long long _bit = 1ull << ((device) & 63);                                               \
+    if (!(_done.load(std::memory_order_acquire) & _bit)) {                                                 \
+      MRFP_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes))); \
+      _done.fetch_or(_bit, std::memory_order_release);                                                     \
+    }                                                                                                      \
+  } while (0)
+
 template <typename... Exp, typename... Act>
 inline cudaError_t launch_k(void (*kern)(Exp...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Act&&... args) {
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
   cudaLaunchAttribute at[1];
   at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  at[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = at; cfg.numAttrs = 1;
   return cudaLaunchKernelEx(&cfg, kern, std::forward<Act>(args)...);
 }

@@ -86,18 +86,19 @@ constexpr int kLayPx = 128;
 constexpr int kLayRow = 133;                          // odd row pitch; pixel px sits in column (px & 3) * 33 + (px >> 2),
 __device__ __forceinline__ int lay_col(int px) { return (px & 3) * 33 + (px >> 2); }   // so both access patterns spread over the banks
 
-// src fp32 [N][C][HW] -> dst T [N][HW][C]; accumulate adds into dst (gradient of OCout_dec joining the chain).
+// src fp32 [N][C][HW] -> dst T [N][HW][CD]; CD >= C is the stored channel count of a padded stem (channels C..CD-1 are
+// written as zeros); accumulate adds into dst (gradient of OCout_dec joining the chain).
 template <typename T>
 __global__ void __launch_bounds__(256)
-nchw_to_nhwc_kernel(const float* __restrict__ src, T* __restrict__ dst, int C, int HW, int accumulate,
+nchw_to_nhwc_kernel(const float* __restrict__ src, T* __restrict__ dst, int C, int CD, int HW, int accumulate,
                     double* __restrict__ psum) {
   pdl_sync();
   __shared__ float tile[64][kLayRow];   // [channel][lay_col(pixel)]
   // channel tiles fastest in the grid: the CTAs that write the slices of the same NHWC pixels run together
   const int n = blockIdx.z, c0 = blockIdx.x * 64, p0 = blockIdx.y * kLayPx, t = threadIdx.x;
   const float* s = src + (size_t)n * C * HW;
-  T* d = dst + (size_t)n * C * HW;
-  const bool vec = (HW & 3) == 0;
+  T* d = dst + (size_t)n * CD * HW;
+  const bool vec = (HW & 3) == 0 && ((uintptr_t)src & 15) == 0;
   {
     const int px = (t & 31) * 4, crow = t >> 5;
 #pragma unroll
@@ -128,11 +129,11 @@ nchw_to_nhwc_kernel(const float* __restrict__ src, T* __restrict__ dst, int C, i
 #pragma unroll
     for (int pass = 0; pass < kLayPx / 32; ++pass) {
       const int px = pl + pass * 32, p = p0 + px, c = c0 + cg * 8;
-      if (p < HW && c < C) {
+      if (p < HW && c < CD) {
         float v[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) v[j] = tile[cg * 8 + j][lay_col(px)];
-        T* q = d + (size_t)p * C + c;
+        T* q = d + (size_t)p * CD + c;
         if (accumulate) {
           float o[8];
           Elem<T>::load8(q, o);
@@ -198,11 +199,10 @@ nchw_to_nhwc_stm_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict
   }
 }
 
-// the stmatrix kernel serves the bf16 path when the tile decomposition is exact (MRFP_LAYOUT_STM=0: always the fp32-tile kernel)
+// the stmatrix kernel serves the bf16 path when the tile decomposition is exact (no channel padding)
 template <typename T>
-static bool stm_layout_ok(int C, int HW, const float* src) {
-  static const bool on = !(getenv("MRFP_LAYOUT_STM") && atoi(getenv("MRFP_LAYOUT_STM")) == 0);
-  return on && sizeof(T) == 2 && (C & 63) == 0 && (HW & 3) == 0 && ((uintptr_t)src & 15) == 0;
+static bool stm_layout_ok(int C, int CD, int HW, const float* src) {
+  return sizeof(T) == 2 && C == CD && (C & 63) == 0 && (HW & 3) == 0 && ((uintptr_t)src & 15) == 0;
 }
 
 // out fp32 [N][C][OH][OW] = f(Y[n][ih[oh]][iw[ow]][c]) (+ add), f = identity or ReLU(scale*y + shift)
@@ -210,8 +210,9 @@ template <typename T, bool BILIN>
 __global__ void __launch_bounds__(256)
 nhwc_to_nchw_kernel(const T* __restrict__ y, float* __restrict__ out, const float* __restrict__ add,
                     const int* __restrict__ idx_h, const int* __restrict__ idx_w, const float* __restrict__ scale,
-                    const float* __restrict__ shift, int C, int IH, int IW, int OH, int OW,
+                    const float* __restrict__ shift, int C, int CS, int IH, int IW, int OH, int OW,
                     const float2* __restrict__ coef, const float* __restrict__ add_lo, int LH, int LW) {
+  // C: channels of the fp32 NCHW side; CS >= C: channel stride of the NHWC side (padded stem)
   pdl_sync();
   __shared__ float tile[64][kLayRow];   // [channel][lay_col(pixel)]
   // flat grid, output rows fastest, then channel tiles, then w-tiles
@@ -220,11 +221,11 @@ nhwc_to_nchw_kernel(const T* __restrict__ y, float* __restrict__ out, const floa
   const int n = orow / OH, oh = orow - n * OH, t = threadIdx.x;
   const int c0 = (rem % ct) * 64, w0 = (rem / ct) * kLayPx;
   const int sh = idx_h ? idx_h[oh] : oh;
-  const T* row = y + ((size_t)n * IH + sh) * IW * C;
+  const T* row = y + ((size_t)n * IH + sh) * IW * CS;
   {
     const int cg = t & 7, pl = t >> 3, c = c0 + cg * 8;
     float sc[8], sf[8];
-    if (scale && c < C) {
+    if (scale && c < CS) {
 #pragma unroll
       for (int j = 0; j < 8; ++j) { sc[j] = scale[c + j]; sf[j] = shift[c + j]; }
     }
@@ -234,9 +235,9 @@ nhwc_to_nchw_kernel(const T* __restrict__ y, float* __restrict__ out, const floa
       float v[8];
 #pragma unroll
       for (int j = 0; j < 8; ++j) v[j] = 0.f;
-      if (ow < OW && c < C) {
+      if (ow < OW && c < CS) {
         const int sw = idx_w ? idx_w[ow] : ow;
-        Elem<T>::load8(row + (size_t)sw * C + c, v);
+        Elem<T>::load8(row + (size_t)sw * CS + c, v);
         if (scale) {
 #pragma unroll
           for (int j = 0; j < 8; ++j) v[j] = fmaxf(fmaf(sc[j], v[j], sf[j]), 0.f);
@@ -615,7 +616,7 @@ bn_relu_resample_kernel(const T* __restrict__ y, T* __restrict__ a, const int* _
 // ------------------------------------------------------------------------------------------------------
 __global__ void bn_finalize_kernel(const double* __restrict__ acc, const float* __restrict__ gamma,
                                    const float* __restrict__ beta, float* __restrict__ running_mean,
-                                   float* __restrict__ running_var, float* __restrict__ stats, int C,
+                                   float* __restrict__ running_var, float* __restrict__ stats, int C, int c_real,
                                    double count, float momentum, float eps) {
   pdl_sync();
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
@@ -623,14 +624,15 @@ __global__ void bn_finalize_kernel(const double* __restrict__ acc, const float* 
     double var = acc[kMaxC + c] / count - mean * mean;
     if (var < 0) var = 0;
     const double invstd = 1.0 / sqrt(var + (double)eps);
-    const float sc = (float)((double)gamma[c] * invstd);
-    const float b = beta ? beta[c] : 0.f;
+    const bool live = c < c_real;                      // padded output channels (zero weights) are pinned to zero
+    const float sc = live ? (float)((double)gamma[c] * invstd) : 0.f;
+    const float b = (live && beta) ? beta[c] : 0.f;
     stats[0 * kMaxC + c] = (float)mean;
     stats[1 * kMaxC + c] = (float)invstd;
     stats[2 * kMaxC + c] = sc;
     stats[3 * kMaxC + c] = (float)((double)b - mean * (double)sc);
-    if (running_mean) running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * (float)mean;
-    if (running_var) running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)(var * (count / (count - 1.0)));
+    if (live && running_mean) running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * (float)mean;
+    if (live && running_var) running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)(var * (count / (count - 1.0)));
   }
 }
 
@@ -701,31 +703,36 @@ conv3x3_direct_f32_kernel(const float* __restrict__ in, const float* __restrict_
 }
 
 // ------------------------------------------------------------------------------------------------------
-// weight packing.  W: (cout, cin, 3, 3) fp32 OIHW.
-//   mode 0 (direct fwd)   out[tap][ci][co] = W[co][ci][tap]          fp32
-//   mode 1 (direct dgrad) out[tap][co][ci] = W[co][ci][8-tap]        fp32   (conv input = co, output = ci)
-//   mode 2 (tc fwd)       out[tap][co][ci] = W[co][ci][tap]          bf16   (rows = N, K = ci contiguous)
-//   mode 3 (tc dgrad)     out[tap][ci][co] = W[co][ci][8-tap]        bf16   (rows = N = ci, K = co contiguous)
+// weight packing.  W: (cout_r, cin_r, 3, 3) fp32 OIHW; the packed tensor has cin x cout channels (>= the real counts for a
+// padded stem: the extra rows / columns are zeros).
+//   layout 0: out[tap][ci][co]     layout 1: out[tap][co][ci]  (K = ci contiguous)
+//   flip: tap -> 8 - tap (dgrad: the kernel rotated by 180 degrees)
+//   direct fwd   layout 0, no flip, fp32: out[tap][ci][co] = W[co][ci][tap]
+//   direct dgrad layout 1, flip,    fp32: out[tap][co][ci] = W[co][ci][8-tap]   (conv input = co, output = ci)
+//   tc fwd       layout 1, no flip, bf16 / fp32(tf32): rows = N = co, K = ci contiguous
+//   tc dgrad     layout 0, flip,    bf16 / fp32(tf32): rows = N = ci, K = co contiguous
 // ------------------------------------------------------------------------------------------------------
 struct PackJobs {             // one launch packs every layer for both directions: blockIdx.y = job
   const float* W[2 * kHrfpStages];
   void* out[2 * kHrfpStages];
-  int cin[2 * kHrfpStages], cout[2 * kHrfpStages], mode[2 * kHrfpStages];
+  int cin[2 * kHrfpStages], cout[2 * kHrfpStages], cin_r[2 * kHrfpStages], cout_r[2 * kHrfpStages];
+  unsigned char layout[2 * kHrfpStages], flip[2 * kHrfpStages], bf16[2 * kHrfpStages];
 };
 __global__ void pack_weights_kernel(const PackJobs jobs) {
   pdl_sync();
   const int job = blockIdx.y;
   const float* __restrict__ W = jobs.W[job];
   void* __restrict__ out = jobs.out[job];
-  const int cin = jobs.cin[job], cout = jobs.cout[job], mode = jobs.mode[job];
+  const int cin = jobs.cin[job], cout = jobs.cout[job], cin_r = jobs.cin_r[job], cout_r = jobs.cout_r[job];
+  const int layout = jobs.layout[job], flip = jobs.flip[job], bf16 = jobs.bf16[job];
   const int total = 9 * cin * cout;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
     const int tap = i / (cin * cout), r = i % (cin * cout);
     int ci, co;
-    if (mode == 0 || mode == 3) { ci = r / cout; co = r % cout; } else { co = r / cin; ci = r % cin; }
-    const int st = (mode == 1 || mode == 3) ? 8 - tap : tap;
-    const float v = W[((size_t)co * cin + ci) * 9 + st];
-    if (mode < 2) reinterpret_cast<float*>(out)[i] = v;
+    if (layout == 0) { ci = r / cout; co = r % cout; } else { co = r / cin; ci = r % cin; }
+    const int st = flip ? 8 - tap : tap;
+    const float v = (ci < cin_r && co < cout_r) ? W[((size_t)co * cin_r + ci) * 9 + st] : 0.f;
+    if (!bf16) reinterpret_cast<float*>(out)[i] = v;
     else reinterpret_cast<__nv_bfloat16*>(out)[i] = __float2bfloat16_rn(v);
   }
 }
@@ -785,19 +792,20 @@ bn_bwd_reduce_kernel(const T* __restrict__ dA, const T* __restrict__ y, const in
   }
 }
 
-template <typename T, bool REGC>
-__global__ void __launch_bounds__(256, REGC ? 2 : 3)
+template <typename T>
+__global__ void __launch_bounds__(256, 3)
 bn_bwd_apply_kernel(const T* __restrict__ dA, const T* __restrict__ y, T* __restrict__ dY,
                     const int* __restrict__ start_h, const int* __restrict__ cnt_h, const int* __restrict__ start_w,
                     const int* __restrict__ cnt_w, const float* __restrict__ stats, const float* __restrict__ gamma,
-                    const double* __restrict__ acc, int N, int C, int IH, int IW, int OH, int OW, double count, int rev) {
+                    const double* __restrict__ acc, int N, int C, int IH, int IW, int OH, int OW, double count, int rev,
+                    int c_real) {
   pdl_sync();
   // per-channel constants live in shared memory (read as two float4 per use): registers are kept for loads in flight
   __shared__ __align__(16) float s_scale[kMaxC], s_shift[kMaxC], s_P[kMaxC], s_Q[kMaxC], s_R[kMaxC];
   const int cg = C >> 3, pstep = 256 / cg;
   const int c = (threadIdx.x % cg) << 3, pl = threadIdx.x / cg;
   for (int j = threadIdx.x; j < C; j += 256) {
-    const double mean = stats[j], invstd = stats[kMaxC + j], gm = gamma[j];
+    const double mean = stats[j], invstd = stats[kMaxC + j], gm = j < c_real ? gamma[j] : 0.f;   // padded channels: dY = 0
     s_scale[j] = stats[2 * kMaxC + j]; s_shift[j] = stats[3 * kMaxC + j];
     const double S1 = acc[j], S2 = invstd * (acc[kMaxC + j] - mean * S1);
     const double M1 = gm * S1 / count, M2 = gm * S2 / count;
@@ -809,8 +817,6 @@ bn_bwd_apply_kernel(const T* __restrict__ dA, const T* __restrict__ y, T* __rest
     const float4 a = *reinterpret_cast<const float4*>(t + c), b = *reinterpret_cast<const float4*>(t + c + 4);
     v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
   };
-  float r_scale[8], r_shift[8], r_P[8], r_Q[8], r_R[8];   // REGC: the thread's constants stay in registers (2 blocks/SM)
-  if (REGC) { ld8(s_scale, r_scale); ld8(s_shift, r_shift); ld8(s_P, r_P); ld8(s_Q, r_Q); ld8(s_R, r_R); }
   // one source pixel: sum of its <= 2x2 replicas of dA (the reference geometry: x1.2 up, x0.8 down), general loop otherwise
   typedef typename Elem<T>::Raw Raw;
   // raw (still packed) loads of one source pixel: y and its <= 2x2 replicas of dA (the reference geometry: x1.2 up,
@@ -832,15 +838,6 @@ bn_bwd_apply_kernel(const T* __restrict__ dA, const T* __restrict__ y, T* __rest
 #pragma unroll
     for (int j = 0; j < 8; ++j) yv[j] = 0.f;
     Elem<T>::add_raw(yraw, yv);
-    if (REGC) {
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float t = fmaf(r_scale[j], yv[j], r_shift[j]) > 0.f ? sd[j] : 0.f;
-        o[j] = r_P[j] * t - cnt * fmaf(r_R[j], yv[j], r_Q[j]);
-      }
-      Elem<T>::store8(dst, o);
-      return;
-    }
     ld8(s_scale, k0); ld8(s_shift, k1);
 #pragma unroll
     for (int j = 0; j < 8; ++j) o[j] = fmaf(k0[j], yv[j], k1[j]) > 0.f ? sd[j] : 0.f;
@@ -896,14 +893,14 @@ template <typename T>
 __global__ void __launch_bounds__(256, 2)
 bn_bwd_apply_identity_kernel(const T* __restrict__ dA, const T* __restrict__ y, T* __restrict__ dY,
                              const float* __restrict__ stats, const float* __restrict__ gamma,
-                             const double* __restrict__ acc, long long npix, int C, double count, int rev) {
+                             const double* __restrict__ acc, long long npix, int C, double count, int rev, int c_real) {
   pdl_sync();
   const int cg = C >> 3, pstep = 256 / cg;
   const int c = (threadIdx.x % cg) << 3, pl = threadIdx.x / cg;
   float scale[8], shift[8], P[8], Q[8], R[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
-    const double mean = stats[c + j], invstd = stats[kMaxC + c + j], gm = gamma[c + j];
+    const double mean = stats[c + j], invstd = stats[kMaxC + c + j], gm = c + j < c_real ? gamma[c + j] : 0.f;
     scale[j] = stats[2 * kMaxC + c + j]; shift[j] = stats[3 * kMaxC + c + j];
     const double S1 = acc[c + j], S2 = invstd * (acc[kMaxC + c + j] - mean * S1);
     const double M1 = gm * S1 / count, M2 = gm * S2 / count;
@@ -1072,6 +1069,111 @@ int even_grid(int rows, int cap) { return rows < cap ? rows : cap; }
 
 bool pow2_ge8(int c) { return c >= 8 && c <= kMaxC && (c & (c - 1)) == 0; }
 
+// Stored channel count of the stem inside the chain: the row kernels keep fixed 8-channel groups with a power-of-two
+// number of groups, the tensor-core convolutions need K and N in multiples of 64 — a narrower or odd stem
+// (MobileNetV2: 16, ShuffleNetV2: 24 / 116 channels) is zero-padded to the next such width.  The
+// padded input channels meet zero weights, the padded output channels have zero weights, BN scale and shift.
+int stem_pad(int cin, int mode) {
+  int p = 8;
+  while (p < cin) p <<= 1;
+  const int lo = mode == MRFP_MATH_FP32 ? 16 : 64;
+  return p < lo ? lo : p;
+}
+
+constexpr size_t kDirectConvSmemMax = (size_t)kMaxC * 64 * sizeof(float);
+
+template <typename T>
+int launch_direct_conv(const T* in, const void* w, T* out, int N, int H, int W, int cin, int cout, int dil, const int* cnt_h,
+                       const int* cnt_w, double* acc, const DeviceInfo& di, cudaStream_t s) {
+  if constexpr (sizeof(T) == 4) {
+    dim3 g((unsigned)(((long long)N * H * W + 31) / 32), (cout + 63) / 64);
+    const size_t smem = (size_t)cin * 64 * sizeof(float);
+    MRFP_SMEM_OPT_IN(conv3x3_direct_f32_kernel, kDirectConvSmemMax, di.device);
+    launch_k(conv3x3_direct_f32_kernel, dim3(g), dim3(128), smem, s, in, reinterpret_cast<const float*>(w), out, N, H, W, cin, cout,
+             dil, cnt_h, cnt_w, acc);
+    return MRFP_OK;
+  } else {
+    return MRFP_ERR_UNSUPPORTED;
+  }
+}
+
+// --- single passes of a stage, shared by the chain and by the debug hooks (variant 0: LDG row kernel, 1: product path) ---
+template <typename T>
+int run_resample(const mrfp_hrfp_plan* P, int k, const int* lut, const T* Y, T* A, const float* stats, bool rev, bool bulk,
+                 const DeviceInfo& di, cudaStream_t s) {
+  const HrfpStage& st = P->st[k];
+  int rf = MRFP_ERR_UNSUPPORTED;
+  if constexpr (sizeof(T) == 2) {
+    if (bulk)
+      rf = bn_relu_resample_bulk(Y, A, lut + st.idx_h, lut + st.idx_w, P->lut.data() + st.idx_w, stats + 2 * kMaxC,
+                                 stats + 3 * kMaxC, P->N, st.cout, st.ch, st.cw, st.oh, st.ow, rev, s);
+  }
+  if (rf == MRFP_ERR_UNSUPPORTED) {
+    launch_k(bn_relu_resample_kernel<T>, dim3(even_grid(P->N * st.oh, di.sm_count * 8)), dim3(256), 0, s, Y, A, lut + st.idx_h,
+             lut + st.idx_w, stats + 2 * kMaxC, stats + 3 * kMaxC, P->N, st.cout, st.ch, st.cw, st.oh, st.ow, rev ? 1 : 0);
+    rf = MRFP_OK;
+  }
+  return rf;
+}
+
+template <typename T>
+int run_bwd_reduce(const mrfp_hrfp_plan* P, int k, const int* lut, const T* dA, const T* Y, const float* stats, double* acc,
+                   bool rev, bool bulk, const DeviceInfo& di, cudaStream_t s) {
+  const HrfpStage& st = P->st[k];
+  int rr = MRFP_ERR_UNSUPPORTED;
+  if constexpr (sizeof(T) == 2) {
+    if (bulk)
+      rr = bn_bwd_reduce_bulk(dA, Y, lut + st.idx_h, lut + st.idx_w, P->lut.data() + st.idx_w, stats, acc, P->N, st.cout, st.ch,
+                              st.cw, st.oh, st.ow, rev, s);
+  }
+  if (rr == MRFP_ERR_UNSUPPORTED) {
+    launch_k(bn_bwd_reduce_kernel<T>, dim3(even_grid(P->N * st.oh, di.sm_count * 8)), dim3(256), 0, s, dA, Y, lut + st.idx_h,
+             lut + st.idx_w, stats, acc, P->N, st.cout, st.ch, st.cw, st.oh, st.ow, rev ? 1 : 0);
+    rr = MRFP_OK;
+  }
+  return rr;
+}
+
+template <typename T>
+int run_bwd_apply(const mrfp_hrfp_plan* P, int k, const int* lut, const T* dA, const T* Y, T* dY, const float* stats,
+                  const float* gamma, const double* acc, bool rev, bool product, const DeviceInfo& di, cudaStream_t s) {
+  const HrfpStage& st = P->st[k];
+  const double count = (double)P->N * st.oh * st.ow;
+  if (product && st.oh == st.ch && st.ow == st.cw) {   // identity resample (OCdeclayer1): flat stream
+    const long long npix = (long long)P->N * st.ch * st.cw;
+    launch_k(bn_bwd_apply_identity_kernel<T>, dim3(di.sm_count * 8), dim3(256), 0, s, dA, Y, dY, stats, gamma, acc, npix, st.cout,
+             count, rev ? 1 : 0, st.cout_real);
+    return MRFP_OK;
+  }
+  int ra = MRFP_ERR_UNSUPPORTED;
+  if constexpr (sizeof(T) == 2) {
+    if (product)
+      ra = bn_bwd_apply_bulk(dA, Y, dY, lut + st.lo_h, lut + st.lo_w, P->lut.data() + st.lo_h, P->lut.data() + st.lo_w, stats,
+                             gamma, acc, P->N, st.cout, st.ch, st.cw, st.oh, st.ow, count, rev, s, st.cout_real);
+  }
+  if (ra == MRFP_ERR_UNSUPPORTED) {
+    launch_k(bn_bwd_apply_kernel<T>, dim3(even_grid(P->N * st.ch, di.sm_count * 9)), dim3(256), 0, s, dA, Y, dY,
+             lut + st.start_h, lut + st.cnt_h, lut + st.start_w, lut + st.cnt_w, stats, gamma, acc, P->N, st.cout, st.ch, st.cw,
+             st.oh, st.ow, count, rev ? 1 : 0, st.cout_real);
+    ra = MRFP_OK;
+  }
+  return ra;
+}
+
+// fp32 NCHW (C planes) -> T NHWC with CD stored channels
+template <typename T>
+void run_nchw_to_nhwc(const float* src, T* dst, int N, int C, int CD, int HW, bool accumulate, double* psum, bool allow_stm,
+                      cudaStream_t s) {
+  dim3 g((CD + 63) / 64, (HW + kLayPx - 1) / kLayPx, N);
+  if constexpr (sizeof(T) == 2) {
+    if (allow_stm && !accumulate && stm_layout_ok<T>(C, CD, HW, src)) {
+      launch_k(nchw_to_nhwc_stm_kernel, dim3(g), dim3(256), 0, s, src, dst, C, HW, psum);
+      return;
+    }
+  }
+  launch_k(nchw_to_nhwc_kernel<T>, dim3(g), dim3(256), 0, s, src, dst, C, CD, HW, accumulate ? 1 : 0, psum);
+}
+
 template <typename T>
 int hrfp_forward(const mrfp_hrfp_plan* P, const float* xp, const float* const* W, const float* const* gamma,
                  const float* const* beta, float* const* rmean, float* const* rvar, float momentum, float eps,
@@ -1082,11 +1184,9 @@ int hrfp_forward(const mrfp_hrfp_plan* P, const float* xp, const float* const* W
   if (np) MRFP_CUDA_TRY(cudaMemsetAsync(np->psum, 0, (size_t)P->N * P->cin * sizeof(double), s));
   MRFP_CUDA_TRY(cudaMemsetAsync(acc, 0, (size_t)kHrfpStages * 2 * kMaxC * sizeof(double) + kHrfpStages * sizeof(unsigned int), s));
   const int last = ocout ? kHrfpStages : 4;
-  const bool tc = P->mode == MRFP_MATH_BF16;
+  const bool tc = P->mode != MRFP_MATH_FP32;
   // L2-friendly ordering: a kernel starts walking its tensor where its producer finished.  Forward: every conv walks
-  // front to back, every BN/ReLU/resample pass back to front.  (MRFP_L2_ORDER=0 restores front-to-back everywhere.)
-  static const bool l2_order = !(getenv("MRFP_L2_ORDER") && atoi(getenv("MRFP_L2_ORDER")) == 0);
-  static const bool conv_mode_tap = !(getenv("MRFP_CONV_MODE") && atoi(getenv("MRFP_CONV_MODE")) == 1);   // the halo kernel has no finaliser
+  // front to back, every BN/ReLU/resample pass back to front (-0.8 % on the step).
   {
     PackJobs jobs = {};
     for (int k = 0; k < last; ++k) {
@@ -1095,8 +1195,10 @@ int hrfp_forward(const mrfp_hrfp_plan* P, const float* xp, const float* const* W
         const int j = 2 * k + d;
         jobs.W[j] = W[k];
         jobs.out[j] = d == 0 ? (void*)(ws + st.wf_off) : (void*)(saved + st.wb_off);
-        jobs.cin[j] = st.cin; jobs.cout[j] = st.cout;
-        jobs.mode[j] = (tc ? 2 : 0) + d;
+        jobs.cin[j] = st.cin; jobs.cout[j] = st.cout; jobs.cin_r[j] = st.cin_real; jobs.cout_r[j] = st.cout_real;
+        jobs.layout[j] = (unsigned char)(tc ? (d == 0 ? 1 : 0) : (d == 0 ? 0 : 1));
+        jobs.flip[j] = (unsigned char)d;
+        jobs.bf16[j] = (unsigned char)(P->mode == MRFP_MATH_BF16);
       }
     }
     launch_k(pack_weights_kernel, dim3(64, 2 * last), dim3(256), 0, s, jobs);
@@ -1105,12 +1207,7 @@ int hrfp_forward(const mrfp_hrfp_plan* P, const float* xp, const float* const* W
   T* bufB = reinterpret_cast<T*>(ws + P->bufs_off + P->buf_a_bytes);
   {
     const int HW = P->xh * P->xw;
-    dim3 g((P->cin + 63) / 64, (HW + kLayPx - 1) / kLayPx, P->N);
-    if (stm_layout_ok<T>(P->cin, HW, xp))
-      launch_k(nchw_to_nhwc_stm_kernel, dim3(g), dim3(256), 0, s, xp, reinterpret_cast<__nv_bfloat16*>(bufA), P->cin, HW,
-               np ? np->psum : (double*)nullptr);
-    else
-      launch_k(nchw_to_nhwc_kernel<T>, dim3(g), dim3(256), 0, s, xp, bufA, P->cin, HW, 0, np ? np->psum : (double*)nullptr);
+    run_nchw_to_nhwc<T>(xp, bufA, P->N, P->cin, P->st[0].cin, HW, false, np ? np->psum : (double*)nullptr, true, s);
     if (np)      // NP+ call 1 folded into the chain: plane totals came with the layout pass, (a, b) per plane from one block
       launch_k(np_stem_coef_kernel<false>, dim3(1), dim3(256), 0, s, (const double*)np->psum, np->alpha, np->eps,
                (const float*)nullptr, np->coef, np->mean, np->beta, P->N, P->cin, HW);
@@ -1121,56 +1218,41 @@ int hrfp_forward(const mrfp_hrfp_plan* P, const float* xp, const float* const* W
     const HrfpStage& st = P->st[k];
     T* Y = reinterpret_cast<T*>(saved + st.y_off);
     double* a = acc + (size_t)k * 2 * kMaxC;
+    float* stats = reinterpret_cast<float*>(saved + P->stats_off) + (size_t)k * 4 * kMaxC;
+    const double count = (double)P->N * st.oh * st.ow;
     if (tc) {
       ConvBnFinalize fin = {};
       fin.gamma = gamma[k]; fin.beta = beta ? beta[k] : nullptr;
       fin.running_mean = rmean ? rmean[k] : nullptr; fin.running_var = rvar ? rvar[k] : nullptr;
-      fin.stats = reinterpret_cast<float*>(saved + P->stats_off) + (size_t)k * 4 * kMaxC;
+      fin.stats = stats;
       fin.counter = fin_counters + k;
-      fin.count = (double)P->N * st.oh * st.ow; fin.momentum = momentum; fin.eps = eps;
-      int rc = conv3x3_tc_bf16(reinterpret_cast<const __nv_bfloat16*>(cur),
-                               reinterpret_cast<const __nv_bfloat16*>(ws + st.wf_off),
-                               reinterpret_cast<__nv_bfloat16*>(Y), P->N, st.ch, st.cw, st.cin, st.cout, st.dil,
-                               lut + st.cnt_h, lut + st.cnt_w, a, s, nullptr, false, conv_mode_tap ? &fin : nullptr);
+      fin.count = count; fin.momentum = momentum; fin.eps = eps; fin.cout_real = st.cout_real;
+      int rc = conv3x3_tc(cur, ws + st.wf_off, Y, P->esize, P->N, st.ch, st.cw, st.cin, st.cout, st.dil, lut + st.cnt_h,
+                          lut + st.cnt_w, a, s, false, &fin, nullptr, &P->maps[0][k]);
       if (rc) return rc;
     } else {
-      dim3 g((unsigned)(((long long)P->N * st.ch * st.cw + 31) / 32), (st.cout + 63) / 64);
-      const size_t smem = (size_t)st.cin * 64 * sizeof(float);
-      MRFP_CUDA_TRY(cudaFuncSetAttribute(conv3x3_direct_f32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      launch_k(conv3x3_direct_f32_kernel, dim3(g), dim3(128), smem, s, reinterpret_cast<const float*>(cur),
-                                                     reinterpret_cast<const float*>(ws + st.wf_off),
-                                                     reinterpret_cast<float*>(Y), P->N, st.ch, st.cw, st.cin, st.cout,
-                                                     st.dil, lut + st.cnt_h, lut + st.cnt_w, a);
+      int rc = launch_direct_conv<T>(cur, ws + st.wf_off, Y, P->N, st.ch, st.cw, st.cin, st.cout, st.dil, lut + st.cnt_h,
+                                     lut + st.cnt_w, a, di, s);
+      if (rc) return rc;
+      launch_k(bn_finalize_kernel, dim3(1), dim3(256), 0, s, (const double*)a, gamma[k], beta ? beta[k] : (const float*)nullptr,
+               rmean ? rmean[k] : (float*)nullptr, rvar ? rvar[k] : (float*)nullptr, stats, st.cout, st.cout_real, count,
+               momentum, eps);
     }
-    float* stats = reinterpret_cast<float*>(saved + P->stats_off) + (size_t)k * 4 * kMaxC;
-    const double count = (double)P->N * st.oh * st.ow;
-    if (!(tc && conv_mode_tap))      // the tcgen05 conv finalises in its last CTA
-      launch_k(bn_finalize_kernel, dim3(1), dim3(256), 0, s, a, gamma[k], beta ? beta[k] : nullptr, rmean ? rmean[k] : nullptr,
-               rvar ? rvar[k] : nullptr, stats, st.cout, count, momentum, eps);
     if (k == 3 && ocout_dec) {
       const unsigned g = (unsigned)(((st.ow + kLayPx - 1) / kLayPx) * ((st.cout + 63) / 64)) * (unsigned)(P->N * st.oh);
-      launch_k(nhwc_to_nchw_kernel<T, false>, dim3(g), dim3(256), 0, s, Y, ocout_dec, nullptr, lut + st.idx_h, lut + st.idx_w,
-                                                        stats + 2 * kMaxC, stats + 3 * kMaxC, st.cout, st.ch, st.cw,
-                                                        st.oh, st.ow, (const float2*)nullptr, (const float*)nullptr, 0, 0);
+      launch_k(nhwc_to_nchw_kernel<T, false>, dim3(g), dim3(256), 0, s, (const T*)Y, ocout_dec, (const float*)nullptr,
+               lut + st.idx_h, lut + st.idx_w, (const float*)(stats + 2 * kMaxC), (const float*)(stats + 3 * kMaxC), st.cout,
+               st.cout, st.ch, st.cw, st.oh, st.ow, (const float2*)nullptr, (const float*)nullptr, 0, 0);
     }
     if (k == kHrfpStages - 1) {
-      const unsigned g = (unsigned)(((st.ow + kLayPx - 1) / kLayPx) * ((st.cout + 63) / 64)) * (unsigned)(P->N * st.oh);
+      const unsigned g = (unsigned)(((st.ow + kLayPx - 1) / kLayPx) * ((st.cout_real + 63) / 64)) * (unsigned)(P->N * st.oh);
       // with the fused NP+ the add operand is xp itself under the plane's affine map: OCout + (a*xp + b)
-      launch_k(nhwc_to_nchw_kernel<T, false>, dim3(g), dim3(256), 0, s, Y, ocout, np ? xp : x_add, lut + st.idx_h, lut + st.idx_w,
-                                                        stats + 2 * kMaxC, stats + 3 * kMaxC, st.cout, st.ch, st.cw,
-                                                        st.oh, st.ow, np ? np->coef : (const float2*)nullptr, (const float*)nullptr, 0, 0);
+      launch_k(nhwc_to_nchw_kernel<T, false>, dim3(g), dim3(256), 0, s, (const T*)Y, ocout, np ? xp : x_add, lut + st.idx_h,
+               lut + st.idx_w, (const float*)(stats + 2 * kMaxC), (const float*)(stats + 3 * kMaxC), st.cout_real, st.cout,
+               st.ch, st.cw, st.oh, st.ow, np ? (const float2*)np->coef : (const float2*)nullptr, (const float*)nullptr, 0, 0);
     } else if (k + 1 < last) {
-      static const bool bulk_fwd = !(getenv("MRFP_BULK_RESAMPLE") && atoi(getenv("MRFP_BULK_RESAMPLE")) == 0);
-      int rf = MRFP_ERR_UNSUPPORTED;
-      if (tc && bulk_fwd)
-        rf = bn_relu_resample_bulk(reinterpret_cast<const __nv_bfloat16*>(Y), reinterpret_cast<__nv_bfloat16*>(nxt), lut + st.idx_h,
-                                   lut + st.idx_w, P->lut.data() + st.idx_w, stats + 2 * kMaxC, stats + 3 * kMaxC, P->N, st.cout,
-                                   st.ch, st.cw, st.oh, st.ow, l2_order, s);
-      if (rf == MRFP_ERR_UNSUPPORTED)
-        launch_k(bn_relu_resample_kernel<T>, dim3(even_grid(P->N * st.oh, di.sm_count * 8)), dim3(256), 0, s,
-                 Y, nxt, lut + st.idx_h, lut + st.idx_w, stats + 2 * kMaxC, stats + 3 * kMaxC, P->N, st.cout, st.ch, st.cw,
-                 st.oh, st.ow, l2_order ? 1 : 0);
-      else if (rf) return rf;
+      int rf = run_resample<T>(P, k, lut, Y, nxt, stats, true, true, di, s);
+      if (rf) return rf;
       T* t = cur; cur = nxt; nxt = t;
     }
   }
@@ -1189,133 +1271,57 @@ int hrfp_backward(const mrfp_hrfp_plan* P, const float* g_ocout, const float* g_
   T* g0 = reinterpret_cast<T*>(ws + P->bufs_off);
   T* g1 = reinterpret_cast<T*>(ws + P->bufs_off + P->buf_g_bytes);
   T* dY = reinterpret_cast<T*>(ws + P->bufs_off + 2 * P->buf_g_bytes);
-  const bool tc = P->mode == MRFP_MATH_BF16;
+  const bool tc = P->mode != MRFP_MATH_FP32;
   T* dA = nullptr;    // gradient wrt the stage output A_{k+1}, NHWC at (oh, ow)
   T* other = g1;
-  // measured on B200: the gathered loads make the epilogue the bottleneck of the dgrad (latency-bound), so the separate
-  // reduction kernel stays the default; MRFP_FUSE_REDUCE=1 selects the fused path
-  static const bool l2_order = !(getenv("MRFP_L2_ORDER") && atoi(getenv("MRFP_L2_ORDER")) == 0);
   bool at_end = true;     // where the last kernel that touched dA finished (the layout kernels walk front to back)
-  static const bool fuse_reduce = getenv("MRFP_FUSE_REDUCE") && atoi(getenv("MRFP_FUSE_REDUCE")) == 1;
-  static const bool join_dec = !(getenv("MRFP_JOIN_DEC") && atoi(getenv("MRFP_JOIN_DEC")) == 0);
   bool dec_joined = false;
-  bool reduced = false;   // the BN-backward sums of the stage about to be processed were taken by the previous dgrad
   for (int k = kHrfpStages - 1; k >= 0; --k) {
     const HrfpStage& st = P->st[k];
     const float* gin = (k == kHrfpStages - 1) ? g_ocout : (k == 3 ? g_ocout_dec : nullptr);
     if (k == 3 && dec_joined) gin = nullptr;               // already added by the dgrad of stage 4
     if (gin) {
       const int HW = st.oh * st.ow;
-      dim3 g((st.cout + 63) / 64, (HW + kLayPx - 1) / kLayPx, P->N);
       T* dst = dA ? dA : g0;
       const bool np_here = np && k == kHrfpStages - 1;       // plane totals of g_ocout for the fused NP+ backward
-      if (!dA && stm_layout_ok<T>(st.cout, HW, gin))        // plain conversion (nothing to accumulate into)
-        launch_k(nchw_to_nhwc_stm_kernel, dim3(g), dim3(256), 0, s, gin, reinterpret_cast<__nv_bfloat16*>(dst), st.cout, HW,
-                 np_here ? np->psum : (double*)nullptr);
-      else
-        launch_k(nchw_to_nhwc_kernel<T>, dim3(g), dim3(256), 0, s, gin, dst, st.cout, HW, dA ? 1 : 0,
-                 np_here ? np->psum : (double*)nullptr);
+      run_nchw_to_nhwc<T>(gin, dst, P->N, st.cout_real, st.cout, HW, dA != nullptr, np_here ? np->psum : (double*)nullptr, true, s);
       if (np_here)
         launch_k(np_stem_coef_kernel<true>, dim3(1), dim3(256), 0, s, (const double*)np->psum, np->alpha, np->eps,
                  (const float*)np->mean, np->coef, (float*)nullptr, (float*)nullptr, P->N, P->cin, P->xh * P->xw);
       if (!dA) { dA = g0; other = g1; }
+      at_end = true;
     }
     if (!dA) continue;
     const T* Y = reinterpret_cast<const T*>(saved + st.y_off);
     const float* stats = reinterpret_cast<const float*>(saved + P->stats_off) + (size_t)k * 4 * kMaxC;
     double* a = acc + (size_t)k * 2 * kMaxC;
-    const double count = (double)P->N * st.oh * st.ow;
-    const int grid_r = even_grid(P->N * st.oh, di.sm_count * 8), grid_a = even_grid(P->N * st.ch, di.sm_count * 9);
-    if (gin) at_end = true;
-    if (!reduced) {
-      // 0 LDG rows, 1 single ring per SM, 2 (default, measured best) several single-buffered bulk-copy CTAs per SM
-      static const int reduce_mode = getenv("MRFP_RING_REDUCE") ? atoi(getenv("MRFP_RING_REDUCE")) : 2;
-      const bool ring_reduce = reduce_mode == 1;
-      int rr = MRFP_ERR_UNSUPPORTED;
-      if (tc && reduce_mode == 2)
-        rr = bn_bwd_reduce_bulk(reinterpret_cast<const __nv_bfloat16*>(dA), reinterpret_cast<const __nv_bfloat16*>(Y),
-                                lut + st.idx_h, lut + st.idx_w, P->lut.data() + st.idx_w, stats, a, P->N, st.cout, st.ch, st.cw,
-                                st.oh, st.ow, l2_order && at_end, s);
-      else if (tc && ring_reduce)
-        rr = bn_bwd_reduce_ring(reinterpret_cast<const __nv_bfloat16*>(dA), reinterpret_cast<const __nv_bfloat16*>(Y),
-                                lut + st.idx_h, lut + st.idx_w, P->lut.data() + st.idx_w, st.scale_w, stats, a, P->N, st.cout, st.ch,
-                                st.cw, st.oh, st.ow, l2_order && at_end, s);
-      if (rr == MRFP_ERR_UNSUPPORTED)
-        launch_k(bn_bwd_reduce_kernel<T>, dim3(grid_r), dim3(256), 0, s, dA, Y, lut + st.idx_h, lut + st.idx_w, stats, a, P->N,
-                 st.cout, st.ch, st.cw, st.oh, st.ow, (l2_order && at_end) ? 1 : 0);
-      else if (rr) return rr;
-      if (l2_order) at_end = !at_end;
-    }
-    reduced = false;
-    const int rev_apply = (l2_order && at_end) ? 1 : 0;
-    if (l2_order) at_end = !at_end;
-    static const bool regc = getenv("MRFP_APPLY_REGC") && atoi(getenv("MRFP_APPLY_REGC")) == 1;
-    static const bool ident_k = !(getenv("MRFP_APPLY_IDENT") && atoi(getenv("MRFP_APPLY_IDENT")) == 0);
-    if (ident_k && st.oh == st.ch && st.ow == st.cw) {   // identity resample: flat stream
-      const long long npix = (long long)P->N * st.ch * st.cw;
-      launch_k(bn_bwd_apply_identity_kernel<T>, dim3(di.sm_count * 8), dim3(256), 0, s, dA, Y, dY, stats, gamma[k], a, npix,
-               st.cout, count, rev_apply);
-    } else {
-      static const bool bulk_apply = !(getenv("MRFP_BULK_APPLY") && atoi(getenv("MRFP_BULK_APPLY")) == 0);
-      int ra = MRFP_ERR_UNSUPPORTED;
-      if (tc && bulk_apply)
-        ra = bn_bwd_apply_bulk(reinterpret_cast<const __nv_bfloat16*>(dA), reinterpret_cast<const __nv_bfloat16*>(Y),
-                               reinterpret_cast<__nv_bfloat16*>(dY), lut + st.lo_h, lut + st.lo_w, P->lut.data() + st.lo_h,
-                               P->lut.data() + st.lo_w, stats, gamma[k], a, P->N, st.cout, st.ch, st.cw, st.oh, st.ow, count,
-                               rev_apply != 0, s);
-      if (ra == MRFP_ERR_UNSUPPORTED)
-        launch_k(regc ? bn_bwd_apply_kernel<T, true> : bn_bwd_apply_kernel<T, false>, dim3(grid_a), dim3(256), 0, s, dA, Y, dY,
-                 lut + st.start_h, lut + st.cnt_h, lut + st.start_w, lut + st.cnt_w, stats, gamma[k], a, P->N, st.cout, st.ch,
-                 st.cw, st.oh, st.ow, count, rev_apply);
-      else if (ra) return ra;
-    }
+    int rr = run_bwd_reduce<T>(P, k, lut, dA, Y, stats, a, at_end, true, di, s);
+    if (rr) return rr;
+    at_end = !at_end;
+    int ra = run_bwd_apply<T>(P, k, lut, dA, Y, dY, stats, gamma[k], a, at_end, true, di, s);
+    if (ra) return ra;
+    at_end = !at_end;
     // dgrad: conv of dY (cout channels) with the rotated / transposed kernel -> dA_prev (cin channels)
     if (tc) {
-      // the dgrad epilogue also takes the BN-backward sums of stage k-1 (its output IS that stage's dA), unless an
-      // external gradient still has to join that dA (g_ocout_dec at stage 3)
-      ConvBwdStats bs = {};
-      const bool fuse = fuse_reduce && k > 0 && !(k - 1 == 3 && g_ocout_dec);
-      if (fuse) {
-        const HrfpStage& pv = P->st[k - 1];
-        const float* pstats = reinterpret_cast<const float*>(saved + P->stats_off) + (size_t)(k - 1) * 4 * kMaxC;
-        bs.y = reinterpret_cast<const __nv_bfloat16*>(saved + pv.y_off);
-        bs.idx_h = lut + pv.idx_h; bs.idx_w = lut + pv.idx_w;
-        bs.scale = pstats + 2 * kMaxC; bs.shift = pstats + 3 * kMaxC;
-        bs.IH = pv.ch; bs.IW = pv.cw;
-      }
       // stage 4's dgrad produces dA_3, which the gradient of OCout_dec has to join: convert that gradient into the
       // buffer apply(4) has just finished reading and let the conv epilogue add it in fp32 (one rounding, and the
       // read-modify-write pass over dA_3 disappears)
-      const __nv_bfloat16* add_src = nullptr;
-      if (join_dec && k == 4 && g_ocout_dec) {
+      const T* add_src = nullptr;
+      if (k == 4 && g_ocout_dec) {
         const HrfpStage& pv = P->st[3];
-        const int HWp = pv.oh * pv.ow;
-        dim3 gd((pv.cout + 63) / 64, (HWp + kLayPx - 1) / kLayPx, P->N);
-        if (stm_layout_ok<T>(pv.cout, HWp, g_ocout_dec))
-          launch_k(nchw_to_nhwc_stm_kernel, dim3(gd), dim3(256), 0, s, g_ocout_dec, reinterpret_cast<__nv_bfloat16*>(dA), pv.cout, HWp,
-                   (double*)nullptr);
-        else
-          launch_k(nchw_to_nhwc_kernel<T>, dim3(gd), dim3(256), 0, s, g_ocout_dec, dA, pv.cout, HWp, 0, (double*)nullptr);
-        add_src = reinterpret_cast<const __nv_bfloat16*>(dA);
+        run_nchw_to_nhwc<T>(g_ocout_dec, dA, P->N, pv.cout, pv.cout, pv.oh * pv.ow, false, (double*)nullptr, true, s);
+        add_src = dA;
         dec_joined = true;
         at_end = true;
       }
-      int rc = conv3x3_tc_bf16(reinterpret_cast<const __nv_bfloat16*>(dY),
-                               reinterpret_cast<const __nv_bfloat16*>(saved + st.wb_off),
-                               reinterpret_cast<__nv_bfloat16*>(other), P->N, st.ch, st.cw, st.cout, st.cin, st.dil,
-                               nullptr, nullptr, fuse ? acc + (size_t)(k - 1) * 2 * kMaxC : nullptr, s, fuse ? &bs : nullptr,
-                               l2_order && at_end, nullptr, add_src);
+      int rc = conv3x3_tc(dY, saved + st.wb_off, other, P->esize, P->N, st.ch, st.cw, st.cout, st.cin, st.dil, nullptr, nullptr,
+                          nullptr, s, at_end, nullptr, add_src, &P->maps[1][k]);
       if (rc) return rc;
-      if (l2_order) at_end = !at_end;
-      reduced = fuse;
+      at_end = !at_end;
     } else {
-      dim3 g((unsigned)(((long long)P->N * st.ch * st.cw + 31) / 32), (st.cin + 63) / 64);
-      const size_t smem = (size_t)st.cout * 64 * sizeof(float);
-      MRFP_CUDA_TRY(cudaFuncSetAttribute(conv3x3_direct_f32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      launch_k(conv3x3_direct_f32_kernel, dim3(g), dim3(128), smem, s, reinterpret_cast<const float*>(dY),
-                                                     reinterpret_cast<const float*>(saved + st.wb_off),
-                                                     reinterpret_cast<float*>(other), P->N, st.ch, st.cw, st.cout,
-                                                     st.cin, st.dil, nullptr, nullptr, nullptr);
+      int rc = launch_direct_conv<T>(dY, saved + st.wb_off, other, P->N, st.ch, st.cw, st.cout, st.cin, st.dil, nullptr, nullptr,
+                                     nullptr, di, s);
+      if (rc) return rc;
     }
     T* t = dA; dA = other; other = t;
   }
@@ -1326,8 +1332,9 @@ int hrfp_backward(const mrfp_hrfp_plan* P, const float* g_ocout, const float* g_
   const unsigned g = (unsigned)(((P->xw + kLayPx - 1) / kLayPx) * ((P->cin + 63) / 64)) * (unsigned)(P->N * P->xh);
   // fused NP+ backward: g_xp = dA_0 + (a' * g_ocout + b') with the plane's backward coefficients
   const bool np_add = np && g_ocout;
-  launch_k(nhwc_to_nchw_kernel<T, false>, dim3(g), dim3(256), 0, s, dA, g_xp, np_add ? g_ocout : (const float*)nullptr, nullptr, nullptr,
-           nullptr, nullptr, P->cin, P->xh, P->xw, P->xh, P->xw, np_add ? np->coef : (const float2*)nullptr, (const float*)nullptr, 0, 0);
+  launch_k(nhwc_to_nchw_kernel<T, false>, dim3(g), dim3(256), 0, s, (const T*)dA, g_xp, np_add ? g_ocout : (const float*)nullptr,
+           (const int*)nullptr, (const int*)nullptr, (const float*)nullptr, (const float*)nullptr, P->cin, P->st[0].cin, P->xh,
+           P->xw, P->xh, P->xw, np_add ? (const float2*)np->coef : (const float2*)nullptr, (const float*)nullptr, 0, 0);
   MRFP_CUDA_TRY(cudaGetLastError());
   return MRFP_OK;
 }
@@ -1343,18 +1350,24 @@ extern "C" int mrfp_hrfp_plan_create(mrfp_hrfp_plan_t** out, int N, int cin, int
   *out = nullptr;
   static const int kDefaultWidths[4] = {64, 64, 128, 256};
   const int* wd = widths ? widths : kDefaultWidths;
-  if (N <= 0 || xh <= 0 || xw <= 0 || h < 4 || w < 4) return MRFP_ERR_BAD_SHAPE;
-  if (math_mode != MRFP_MATH_FP32 && math_mode != MRFP_MATH_BF16) return MRFP_ERR_UNSUPPORTED;
-  if (!pow2_ge8(cin)) return MRFP_ERR_UNSUPPORTED;
+  if (N <= 0 || xh <= 0 || xw <= 0 || h < 4 || w < 4 || cin <= 0) return MRFP_ERR_BAD_SHAPE;
+  if (math_mode != MRFP_MATH_FP32 && math_mode != MRFP_MATH_TF32 && math_mode != MRFP_MATH_BF16) return MRFP_ERR_UNSUPPORTED;
+  if (cin > kMaxC) return MRFP_ERR_UNSUPPORTED;
   for (int i = 0; i < 4; ++i)
     if (!pow2_ge8(wd[i])) return MRFP_ERR_UNSUPPORTED;
+  // the chain ends at (ceil(h/4), ceil(w/4)) (deepv3.py:327) and its output is added to xp (deepv3.py:330): the two
+  // sizes must agree, as torch.add would demand in the reference
+  if ((h + 3) / 4 != xh || (w + 3) / 4 != xw) return MRFP_ERR_BAD_SHAPE;
   mrfp_hrfp_plan* P = new (std::nothrow) mrfp_hrfp_plan();
   if (!P) return MRFP_ERR_WORKSPACE;
   P->magic = kPlanMagic;
   P->N = N; P->cin = cin; P->xh = xh; P->xw = xw; P->h = h; P->w = w; P->mode = math_mode;
   P->esize = math_mode == MRFP_MATH_BF16 ? 2 : 4;
-  // layer table of deepv3.py:221-237, parametrised by the encoder widths
-  const int chans[9] = {cin, wd[0], wd[1], wd[2], wd[3], wd[2], wd[1], wd[0], cin};
+  P->cin_pad = stem_pad(cin, math_mode);
+  for (int d = 0; d < 2; ++d)
+    for (int k = 0; k < kHrfpStages; ++k) P->maps[d][k].valid = 0;
+  // layer table of deepv3.py:221-237, parametrised by the encoder widths and the (padded) stem width
+  const int chans[9] = {P->cin_pad, wd[0], wd[1], wd[2], wd[3], wd[2], wd[1], wd[0], P->cin_pad};
   const int dils[8] = {1, 1, 2, 2, 1, 1, 2, 2};
   // resample spec of deepv3.py:320-327
   const double sfs[8] = {1.205, 1.2, 1.2, 0, 0, 0.838, 0.798, 0};
@@ -1362,16 +1375,19 @@ extern "C" int mrfp_hrfp_plan_create(mrfp_hrfp_plan_t** out, int N, int cin, int
   const int sz_w[8] = {0, 0, 0, w / 2, w / 2, 0, 0, (w + 3) / 4};
   int ch = xh, cw = xw;
   size_t y_bytes = 0, wf_bytes = 0, wb_bytes = 0, max_act = 0, max_g = 0, max_dy = 0;
-  max_act = (size_t)N * xh * xw * cin * P->esize;
+  max_act = (size_t)N * xh * xw * P->cin_pad * P->esize;
   for (int k = 0; k < kHrfpStages; ++k) {
     HrfpStage& st = P->st[k];
     st.cin = chans[k]; st.cout = chans[k + 1]; st.dil = dils[k];
+    st.cin_real = k == 0 ? cin : st.cin;
+    st.cout_real = k == kHrfpStages - 1 ? cin : st.cout;
     st.ch = ch; st.cw = cw;
     const bool sf = sfs[k] > 0;
     st.oh = sf ? (int)floor((double)ch * sfs[k]) : sz_h[k];
     st.ow = sf ? (int)floor((double)cw * sfs[k]) : sz_w[k];
     if (st.oh <= 0 || st.ow <= 0) { delete P; return MRFP_ERR_BAD_SHAPE; }
-    if (math_mode == MRFP_MATH_BF16 && !conv3x3_tc_supported(st.cin, st.cout)) { delete P; return MRFP_ERR_UNSUPPORTED; }
+    if (math_mode != MRFP_MATH_FP32 && (!conv3x3_tc_supported(st.cin, st.cout, P->esize) ||
+                                        !conv3x3_tc_supported(st.cout, st.cin, P->esize))) { delete P; return MRFP_ERR_UNSUPPORTED; }
     std::vector<int>& L = P->lut;
     st.scale_h = index_scale(ch, st.oh, sf, sfs[k]); st.scale_w = index_scale(cw, st.ow, sf, sfs[k]);
     st.idx_h = (int)L.size(); L.resize(L.size() + st.oh); make_index(ch, st.oh, sf, sfs[k], &L[st.idx_h]);
@@ -1444,7 +1460,7 @@ extern "C" int mrfp_hrfp_plan_stage(const mrfp_hrfp_plan_t* P, int k, int* out7)
   if (!out7) return MRFP_ERR_NULL_POINTER;
   if (k < 0 || k >= kHrfpStages) return MRFP_ERR_BAD_SHAPE;
   const HrfpStage& st = P->st[k];
-  out7[0] = st.cin; out7[1] = st.cout; out7[2] = st.dil; out7[3] = st.ch; out7[4] = st.cw; out7[5] = st.oh; out7[6] = st.ow;
+  out7[0] = st.cin_real; out7[1] = st.cout_real; out7[2] = st.dil; out7[3] = st.ch; out7[4] = st.cw; out7[5] = st.oh; out7[6] = st.ow;
   return MRFP_OK;
 }
 
@@ -1462,6 +1478,7 @@ static int hrfp_fwd_entry(const mrfp_hrfp_plan_t* P, const float* xp, const floa
   int rc = get_device_info(&di);
   if (rc) return rc;
   cudaStream_t s = (cudaStream_t)stream;
+  std::lock_guard<std::mutex> lock(P->mu);               // the plan's tensor-map cache
   if (P->mode == MRFP_MATH_BF16)
     return hrfp_forward<__nv_bfloat16>(P, xp, W, gamma, beta, running_mean, running_var, momentum, eps, x_add, ocout,
                                        ocout_dec, (const int*)lut, (char*)saved, (char*)ws, s, di, np);
@@ -1479,6 +1496,7 @@ static int hrfp_bwd_entry(const mrfp_hrfp_plan_t* P, const float* g_ocout, const
   int rc = get_device_info(&di);
   if (rc) return rc;
   cudaStream_t s = (cudaStream_t)stream;
+  std::lock_guard<std::mutex> lock(P->mu);
   if (P->mode == MRFP_MATH_BF16)
     return hrfp_backward<__nv_bfloat16>(P, g_ocout, g_ocout_dec, gamma, (const int*)lut, (const char*)saved, g_xp,
                                         (char*)ws, s, di, np);
@@ -1546,42 +1564,46 @@ static int hrfp_plus_add_impl(const mrfp_hrfp_plan* P, const char* saved, const 
   const float* stats = reinterpret_cast<const float*>(saved + P->stats_off) + (size_t)3 * 4 * kMaxC;
   const unsigned g = (unsigned)(((st.ow + kLayPx - 1) / kLayPx) * ((st.cout + 63) / 64)) * (unsigned)(P->N * st.oh);
   if (dec1_lo && (lw > st.ow || lh > st.oh)) return MRFP_ERR_BAD_SHAPE;      // an Upsample: the source is not larger
-  static const bool staged_on = !(getenv("MRFP_PLUS_STAGED") && atoi(getenv("MRFP_PLUS_STAGED")) == 0);
+  DeviceInfo di;
+  int rc = get_device_info(&di);
+  if (rc) return rc;
   // the reference's x2 Upsample: scale <= 1/2 bounds the staged span; 16-byte alignment for the bulk copies
-  if (dec1_lo && staged_on && st.ow > 1 && 2 * (lw - 1) <= st.ow - 1 && (lw & 3) == 0 && ((uintptr_t)dec1_lo & 15) == 0) {
+  if (dec1_lo && st.ow > 1 && 2 * (lw - 1) <= st.ow - 1 && (lw & 3) == 0 && ((uintptr_t)dec1_lo & 15) == 0) {
     // bf16 path: the ldmatrix kernel when every tile's source span fits its buffer (host copy of the index table)
-    static const bool ldm_on = !(getenv("MRFP_PLUS_LDM") && atoi(getenv("MRFP_PLUS_LDM")) == 0);
-    if (ldm_on && sizeof(T) == 2 && (st.cout & 63) == 0 && (st.ow & 3) == 0) {
-      const int* hidx = P->lut.data() + st.idx_w;
-      bool fits = true;
-      for (int w0 = 0; w0 < st.ow && fits; w0 += kLayPx) {
-        const int w1 = (w0 + kLayPx < st.ow ? w0 + kLayPx : st.ow) - 1;
-        fits = hidx[w1] - hidx[w0] + 1 <= kLdmSpan;
-      }
-      if (fits) {
-        const unsigned gl = (unsigned)(((st.ow + kLayPx - 1) / kLayPx) * (st.cout / 64)) * (unsigned)(P->N * st.oh);
-        MRFP_CUDA_TRY(cudaFuncSetAttribute(hrfp_plus_tail_ldm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLdmSmem));
-        launch_k(hrfp_plus_tail_ldm_kernel, dim3(gl), dim3(256), kLdmSmem, s, reinterpret_cast<const __nv_bfloat16*>(Y), out,
-                 lut + st.idx_h, lut + st.idx_w, stats + 2 * kMaxC, stats + 3 * kMaxC, st.cout, st.ch, st.cw, st.oh, st.ow, dec1_lo,
-                 lh, lw);
-        MRFP_CUDA_TRY(cudaGetLastError());
-        return MRFP_OK;
+    if constexpr (sizeof(T) == 2) {
+      if ((st.cout & 63) == 0 && (st.ow & 3) == 0) {
+        const int* hidx = P->lut.data() + st.idx_w;
+        bool fits = true;
+        for (int w0 = 0; w0 < st.ow && fits; w0 += kLayPx) {
+          const int w1 = (w0 + kLayPx < st.ow ? w0 + kLayPx : st.ow) - 1;
+          fits = hidx[w1] - hidx[w0] + 1 <= kLdmSpan;
+        }
+        if (fits) {
+          const unsigned gl = (unsigned)(((st.ow + kLayPx - 1) / kLayPx) * (st.cout / 64)) * (unsigned)(P->N * st.oh);
+          MRFP_SMEM_OPT_IN(hrfp_plus_tail_ldm_kernel, kLdmSmem, di.device);
+          launch_k(hrfp_plus_tail_ldm_kernel, dim3(gl), dim3(256), kLdmSmem, s, Y, out, lut + st.idx_h, lut + st.idx_w,
+                   stats + 2 * kMaxC, stats + 3 * kMaxC, st.cout, st.ch, st.cw, st.oh, st.ow, dec1_lo, lh, lw);
+          MRFP_CUDA_TRY(cudaGetLastError());
+          return MRFP_OK;
+        }
       }
     }
-    static const int ct_env = getenv("MRFP_PLUS_TILE_CH") ? atoi(getenv("MRFP_PLUS_TILE_CH")) : 32;
-    const int CT = ct_env == 64 ? 64 : 32;
-    const unsigned gs = (unsigned)(((st.ow + kLayPx - 1) / kLayPx) * ((st.cout + CT - 1) / CT)) * (unsigned)(P->N * st.oh);
-    auto kern = CT == 64 ? hrfp_plus_bilinear_staged_kernel<T, 64> : hrfp_plus_bilinear_staged_kernel<T, 32>;
-    const size_t smem = CT == 64 ? staged_smem<64>() : staged_smem<32>();
-    MRFP_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    launch_k(kern, dim3(gs), dim3(256), smem, s, Y, out, lut + st.idx_h, lut + st.idx_w, stats + 2 * kMaxC, stats + 3 * kMaxC,
-             st.cout, st.ch, st.cw, st.oh, st.ow, dec1_lo, lh, lw);
+    // 32-channel tiles: 35 KB, 5-6 tiles per SM (720 vs 742 us for 64-channel tiles)
+    const unsigned gs = (unsigned)(((st.ow + kLayPx - 1) / kLayPx) * ((st.cout + 31) / 32)) * (unsigned)(P->N * st.oh);
+    MRFP_SMEM_OPT_IN((hrfp_plus_bilinear_staged_kernel<T, 32>), staged_smem<32>(), di.device);
+    launch_k(hrfp_plus_bilinear_staged_kernel<T, 32>, dim3(gs), dim3(256), staged_smem<32>(), s, Y, out, lut + st.idx_h,
+             lut + st.idx_w, stats + 2 * kMaxC, stats + 3 * kMaxC, st.cout, st.ch, st.cw, st.oh, st.ow, dec1_lo, lh, lw);
     MRFP_CUDA_TRY(cudaGetLastError());
     return MRFP_OK;
   }
-  launch_k(dec1_lo ? nhwc_to_nchw_kernel<T, true> : nhwc_to_nchw_kernel<T, false>, dim3(g), dim3(256), 0, s, Y, out, dec1_up,
-           lut + st.idx_h, lut + st.idx_w, stats + 2 * kMaxC, stats + 3 * kMaxC, st.cout, st.ch, st.cw, st.oh, st.ow,
-           (const float2*)nullptr, dec1_lo, lh, lw);
+  if (dec1_lo)
+    launch_k(nhwc_to_nchw_kernel<T, true>, dim3(g), dim3(256), 0, s, Y, out, dec1_up, lut + st.idx_h, lut + st.idx_w,
+             stats + 2 * kMaxC, stats + 3 * kMaxC, st.cout, st.cout, st.ch, st.cw, st.oh, st.ow, (const float2*)nullptr, dec1_lo,
+             lh, lw);
+  else
+    launch_k(nhwc_to_nchw_kernel<T, false>, dim3(g), dim3(256), 0, s, Y, out, dec1_up, lut + st.idx_h, lut + st.idx_w,
+             stats + 2 * kMaxC, stats + 3 * kMaxC, st.cout, st.cout, st.ch, st.cw, st.oh, st.ow, (const float2*)nullptr, dec1_lo,
+             lh, lw);
   MRFP_CUDA_TRY(cudaGetLastError());
   return MRFP_OK;
 }
@@ -1617,6 +1639,53 @@ extern "C" int mrfp_add_f32(const float* a, const float* b, float* out, size_t n
   const size_t n4 = al ? n / 4 : 0;
   const int grid = grid_for((long long)(n4 ? n4 : n), 256, di.sm_count, 16);
   launch_k(add_f32_kernel, dim3(grid), dim3(256), 0, (cudaStream_t)stream, (const float4*)a, (const float4*)b, (float4*)out, n4, a, b, out, n);
+  MRFP_CUDA_TRY(cudaGetLastError());
+  return MRFP_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// test hooks (not part of the public header): ONE element-wise pass of one stage on caller-provided NHWC buffers in the
+// plan's element type, so that each product kernel can be pinned on its own against an fp64 evaluation of the same inputs.
+//   op 0  forward BN/ReLU/resample   y (N,ch,cw,C) -> out (N,oh,ow,C)          stats = [4][256] mean, invstd, scale, shift
+//   op 1  BN-backward reduce         in2 = dA (N,oh,ow,C), y -> acc[0..C) = sum mask*dA, acc[256..) = sum mask*dA*y
+//   op 2  BN-backward apply          in2 = dA, y, acc, gamma -> out = dY (N,ch,cw,C)
+//   variant 0: the LDG row kernel;  1: the kernel the chain launches (bulk-copy / identity-stream forms on the bf16 path)
+// ------------------------------------------------------------------------------------------------------
+template <typename T>
+static int debug_stage_op(const mrfp_hrfp_plan* P, const int* lut, int k, int op, int variant, const void* y, const void* in2,
+                          void* out, const float* stats, const float* gamma, double* acc, cudaStream_t s) {
+  DeviceInfo di;
+  int rc = get_device_info(&di);
+  if (rc) return rc;
+  const bool product = variant != 0;
+  switch (op) {
+    case 0: return run_resample<T>(P, k, lut, (const T*)y, (T*)out, stats, false, product, di, s);
+    case 1: return run_bwd_reduce<T>(P, k, lut, (const T*)in2, (const T*)y, stats, acc, false, product, di, s);
+    case 2: return run_bwd_apply<T>(P, k, lut, (const T*)in2, (const T*)y, (T*)out, stats, gamma, acc, false, product, di, s);
+  }
+  return MRFP_ERR_BAD_SHAPE;
+}
+
+extern "C" int mrfp_debug_stage_op(const mrfp_hrfp_plan_t* P, const void* lut, int k, int op, int variant, const void* y,
+                                   const void* in2, void* out, const float* stats, const float* gamma, double* acc,
+                                   void* stream) {
+  if (!P || P->magic != kPlanMagic) return MRFP_ERR_BAD_PLAN;
+  if (k < 0 || k >= kHrfpStages) return MRFP_ERR_BAD_SHAPE;
+  if (!lut || !y || !stats) return MRFP_ERR_NULL_POINTER;
+  if (P->mode == MRFP_MATH_BF16)
+    return debug_stage_op<__nv_bfloat16>(P, (const int*)lut, k, op, variant, y, in2, out, stats, gamma, acc, (cudaStream_t)stream);
+  return debug_stage_op<float>(P, (const int*)lut, k, op, variant, y, in2, out, stats, gamma, acc, (cudaStream_t)stream);
+}
+
+// fp32 NCHW (C planes) -> NHWC with CD stored channels in bf16 (esize 2) or fp32 (esize 4); variant 1 allows the stmatrix
+// kernel (bf16, C == CD, C % 64 == 0, HW % 4 == 0); psum (N*C doubles, zeroed by the caller) receives the plane totals
+extern "C" int mrfp_debug_nchw_to_nhwc(const float* src, void* dst, int N, int C, int CD, int HW, int esize, int variant,
+                                       double* psum, void* stream) {
+  if (!src || !dst) return MRFP_ERR_NULL_POINTER;
+  if (N <= 0 || C <= 0 || CD < C || (CD & 7) || HW <= 0) return MRFP_ERR_BAD_SHAPE;
+  if (esize == 2) run_nchw_to_nhwc<__nv_bfloat16>(src, (__nv_bfloat16*)dst, N, C, CD, HW, false, psum, variant != 0, (cudaStream_t)stream);
+  else if (esize == 4) run_nchw_to_nhwc<float>(src, (float*)dst, N, C, CD, HW, false, psum, false, (cudaStream_t)stream);
+  else return MRFP_ERR_UNSUPPORTED;
   MRFP_CUDA_TRY(cudaGetLastError());
   return MRFP_OK;
 }

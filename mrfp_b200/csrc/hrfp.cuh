@@ -1,7 +1,9 @@
-// Internal declarations shared by hrfp.cu (plan, element-wise kernels, orchestration) and conv_tc.cu
-// (tcgen05 implicit-GEMM convolution).
+// Internal declarations shared by hrfp.cu (plan, element-wise kernels, orchestration), bn_ring.cu (bulk-copy row
+// passes) and conv_tc.cu (tcgen05 implicit-GEMM convolution).
 #pragma once
 #include "common.cuh"
+#include <cuda.h>
+#include <mutex>
 #include <vector>
 
 namespace mrfp {
@@ -12,7 +14,8 @@ constexpr int kTileH = 8;    // tcgen05 conv output tile: 8 rows x 16 cols = 128
 constexpr int kTileW = 16;
 
 struct HrfpStage {
-  int cin, cout, dil;
+  int cin, cout, dil;       // channel counts as stored (padded to the tensor-core granule for a narrow stem)
+  int cin_real, cout_real;  // channel counts of the module's conv (== cin, cout unless padded)
   int ch, cw;      // conv resolution (input and output of the 3x3 conv)
   int oh, ow;      // resolution after the nearest resample
   int max_rep;     // largest replication count of a source row / column
@@ -28,23 +31,20 @@ struct HrfpStage {
   size_t wb_off;          // packed dgrad weights in `saved` (bytes)
 };
 
-// bulk-copy forward element-wise pass (bn_ring.cu): A_next = ReLU(scale * gather(Y) + shift); MRFP_ERR_UNSUPPORTED -> LDG kernel
-int bn_relu_resample_bulk(const __nv_bfloat16* y, __nv_bfloat16* a, const int* idx_h, const int* idx_w, const int* host_idx_w,
-                          const float* scale, const float* shift, int N, int C, int IH, int IW, int OH, int OW, bool reverse,
-                          cudaStream_t stream);
-// bulk-copy BN-backward apply pass (bn_ring.cu): dY = P*mask*sum(replicas of dA) - cnt*(Q + R*y); MRFP_ERR_UNSUPPORTED -> LDG kernel
-int bn_bwd_apply_bulk(const __nv_bfloat16* dA, const __nv_bfloat16* y, __nv_bfloat16* dY, const int* lo_h, const int* lo_w,
-                      const int* host_lo_h, const int* host_lo_w, const float* stats, const float* gamma, const double* acc,
-                      int N, int C, int IH, int IW, int OH, int OW, double count, bool reverse, cudaStream_t stream);
-// the same with several single-buffered CTAs per SM (bn_ring.cu)
-int bn_bwd_reduce_bulk(const __nv_bfloat16* dA, const __nv_bfloat16* y, const int* idx_h, const int* idx_w,
-                       const int* host_idx_w, const float* stats, double* acc, int N, int C, int IH, int IW, int OH, int OW,
-                       bool reverse, cudaStream_t stream);
+// the three TMA descriptors of one convolution launch; a plan keeps one per (stage, direction) and re-encodes only
+// when a buffer address changes
+struct ConvMaps {
+  CUtensorMap in, w, out;
+  const void* key[3];
+  int valid;
+};
+
 }  // namespace mrfp
 
 struct mrfp_hrfp_plan {
   uint32_t magic;
   int N, cin, xh, xw, h, w, mode, esize;
+  int cin_pad;                     // stem channels as stored inside the chain
   mrfp::HrfpStage st[mrfp::kHrfpStages];
   std::vector<int> lut;
   size_t ws_bytes, saved_bytes;
@@ -52,51 +52,39 @@ struct mrfp_hrfp_plan {
   size_t acc_fwd_off, acc_bwd_off, bufs_off, buf_a_bytes, buf_g_bytes, buf_dy_bytes;
   // saved layout
   size_t stats_off;   // 8 x 4 x kMaxC floats: mean, invstd, scale, shift
+  // launch-side cache (not part of the geometry): tensor maps per (direction, stage)
+  mutable std::mutex mu;
+  mutable mrfp::ConvMaps maps[2][mrfp::kHrfpStages];
 };
 
 namespace mrfp {
 constexpr uint32_t kPlanMagic = 0x4d524650u;   // 'MRFP'
 
-// tcgen05 implicit-GEMM 3x3 convolution, bf16 NHWC in/out, fp32 accumulation in TMEM (conv_tc.cu).
+// tcgen05 implicit-GEMM 3x3 convolution, NHWC in/out, fp32 accumulation in TMEM (conv_tc.cu).
+//   esize 2: bf16 operands (kind::f16);  esize 4: fp32 storage, tf32 operands (kind::tf32)
 //   in  [N][H][W][cin], wpack [9][cout][cin] (tap-major, K contiguous), out [N][H][W][cout]
 //   cnt_h / cnt_w: zero-padded replication counts (device) -> per-channel weighted sum / sum of squares of the
-//   stored (bf16) conv output are added to stat_acc[0..cout) / stat_acc[kMaxC..kMaxC+cout); pass nullptr to skip.
-//   bwd_stats (dgrad use): the conv output is the gradient dA of the PREVIOUS chain stage's output; its epilogue then
-//   also accumulates that stage's BN-backward sums  U1 = sum mask*dA, U2 = sum mask*dA*y  into stat_acc, where y is
-//   the stage's saved conv output gathered through its nearest-neighbour tables and mask = [scale*y + shift > 0].
-struct ConvBwdStats {
-  const __nv_bfloat16* y;     // [N][IH][IW][cout]
-  const int* idx_h;           // [H] output row -> row of y
-  const int* idx_w;           // [W]
-  const float* scale;         // [cout] BN scale / shift of that stage (ReLU mask)
-  const float* shift;
-  int IH, IW;
-  int H, W;                   // filled in by conv3x3_tc_bf16
-};
+//   stored conv output are added to stat_acc[0..cout) / stat_acc[kMaxC..kMaxC+cout); pass nullptr to skip.
 //   add_src (dgrad use): a tensor of the output's shape that is added to the accumulators in fp32 before the single
-//   rounding to bf16 (the gradient of OCout_dec joining dA_3).
+//   rounding to the storage type (the gradient of OCout_dec joining dA_3).
 //   finalize (forward use, with stat_acc): the LAST CTA to add its partial statistics turns them into the BN
 //   mean / invstd / scale / shift table and updates the running statistics — no separate finalisation launch.
 struct ConvBnFinalize {
-  const float* gamma;         // [cout]
-  const float* beta;          // [cout] or null
-  float* running_mean;        // [cout] or null
+  const float* gamma;         // [cout_real]
+  const float* beta;          // [cout_real] or null
+  float* running_mean;        // [cout_real] or null
   float* running_var;
   float* stats;               // [4][kMaxC]: mean, invstd, scale, shift
   unsigned int* counter;      // zero before the launch
   double count;               // elements per channel of the resampled tensor
   float momentum, eps;
+  int cout_real;              // channels of the module's conv; stored channels beyond it get scale = shift = 0
 };
-int conv3x3_tc_bf16(const __nv_bfloat16* in, const __nv_bfloat16* wpack, __nv_bfloat16* out, int N, int H, int W,
-                    int cin, int cout, int dil, const int* cnt_h, const int* cnt_w, double* stat_acc,
-                    cudaStream_t stream, const ConvBwdStats* bwd_stats = nullptr, bool reverse_tiles = false,
-                    const ConvBnFinalize* finalize = nullptr, const __nv_bfloat16* add_src = nullptr);
-bool conv3x3_tc_supported(int cin, int cout);
+int conv3x3_tc(const void* in, const void* wpack, void* out, int esize, int N, int H, int W, int cin, int cout, int dil,
+               const int* cnt_h, const int* cnt_w, double* stat_acc, cudaStream_t stream, bool reverse_tiles = false,
+               const ConvBnFinalize* finalize = nullptr, const void* add_src = nullptr, ConvMaps* cache = nullptr);
+bool conv3x3_tc_supported(int cin, int cout, int esize);
 
-// TMA-fed BN-backward reduction (bn_ring.cu); MRFP_ERR_UNSUPPORTED -> use the LDG kernel
-int bn_bwd_reduce_ring(const __nv_bfloat16* dA, const __nv_bfloat16* y, const int* idx_h, const int* idx_w,
-                       const int* host_idx_w, float scale_w, const float* stats, double* acc, int N, int C, int IH, int IW,
-                       int OH, int OW, bool reverse, cudaStream_t stream);
 // bulk-copy forward element-wise pass (bn_ring.cu): A_next = ReLU(scale * gather(Y) + shift); MRFP_ERR_UNSUPPORTED -> LDG kernel
 int bn_relu_resample_bulk(const __nv_bfloat16* y, __nv_bfloat16* a, const int* idx_h, const int* idx_w, const int* host_idx_w,
                           const float* scale, const float* shift, int N, int C, int IH, int IW, int OH, int OW, bool reverse,
@@ -104,8 +92,8 @@ int bn_relu_resample_bulk(const __nv_bfloat16* y, __nv_bfloat16* a, const int* i
 // bulk-copy BN-backward apply pass (bn_ring.cu): dY = P*mask*sum(replicas of dA) - cnt*(Q + R*y); MRFP_ERR_UNSUPPORTED -> LDG kernel
 int bn_bwd_apply_bulk(const __nv_bfloat16* dA, const __nv_bfloat16* y, __nv_bfloat16* dY, const int* lo_h, const int* lo_w,
                       const int* host_lo_h, const int* host_lo_w, const float* stats, const float* gamma, const double* acc,
-                      int N, int C, int IH, int IW, int OH, int OW, double count, bool reverse, cudaStream_t stream);
-// the same with several single-buffered CTAs per SM (bn_ring.cu)
+                      int N, int C, int IH, int IW, int OH, int OW, double count, bool reverse, cudaStream_t stream, int c_real = 0);
+// bulk-copy BN-backward reduction (bn_ring.cu): U1 = sum mask*dA, U2 = sum mask*dA*y; MRFP_ERR_UNSUPPORTED -> LDG kernel
 int bn_bwd_reduce_bulk(const __nv_bfloat16* dA, const __nv_bfloat16* y, const int* idx_h, const int* idx_w,
                        const int* host_idx_w, const float* stats, double* acc, int N, int C, int IH, int IW, int OH, int OW,
                        bool reverse, cudaStream_t stream);

@@ -358,7 +358,7 @@ instnorm_bwd_kernel(const float* __restrict__ gy, const float* __restrict__ x, c
 // fits `cap`, else non-resident (slices are still spread over an 8-CTA cluster so one plane keeps 8 SMs busy)
 struct Geo { int cs, slice; bool resident; size_t smem; };
 Geo pick_geo(int HW, int nbuf, int max_smem_optin) {
-  static const int want_kb = getenv("MRFP_IN_SLICE_KB") ? atoi(getenv("MRFP_IN_SLICE_KB")) : 72;
+  constexpr int want_kb = 72;      // three CTAs per SM; 48 KB and 144-200 KB slices measured slower (profiles/README.md)
   const size_t want = (size_t)(want_kb > 0 ? want_kb : 72) << 10;
   const size_t cap = (size_t)max_smem_optin - 2048;              // static shared memory of the kernels
   Geo g{};

@@ -188,7 +188,8 @@ extern "C" int mrfp_npplus_fwd_presummed_f32(const float* x, const double* psum,
   if (smem > (size_t)di.max_smem_optin - 1024) return MRFP_ERR_UNSUPPORTED;
   cudaStream_t s = (cudaStream_t)stream;
   float2* coef = reinterpret_cast<float2*>(ws);
-  MRFP_CUDA_TRY(cudaFuncSetAttribute(np_coef_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  if (smem > (48u << 10))      // beyond the default limit only for C > 6144
+    MRFP_CUDA_TRY(cudaFuncSetAttribute(np_coef_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   launch_k(np_coef_kernel, dim3(1), dim3(256), smem, s, psum, alpha, eps, coef, mean, beta, N, C, HW);
   const int nchunk = (HW + kChunk - 1) / kChunk;
   const long long items = (long long)N * C * nchunk;

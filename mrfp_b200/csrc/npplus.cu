@@ -274,10 +274,13 @@ __device__ __forceinline__ void bulk_load(void* smem_dst, const void* gsrc, uint
 //   phase B   the resident tail first (no re-read), then units [0, u_dyn) in DESCENDING order from counterB —
 //             the most recently read data first, so the re-read is served from L2 while it lasts.
 // A fill of ring slot s carries its unit index (and, in phase B, the plane's (a, b) pair) in shared memory next to
-// the slot.  The counters are (re)initialised by CTA 0 of each launch and published with a per-launch nonce, so
-// the workspace needs no host-side clearing.
+// the slot.  Both counters are zero when a launch begins: the control block is zero-filled ONCE by the owner of the
+// workspace (mrfp_npplus_ws_init, or an allocation that zero-fills), and every launch re-arms it for the next one — CTA 0 clears
+// counter_b at kernel entry (it is first read behind the second grid barrier) and counter_a right behind the first grid
+// barrier (its last use precedes that barrier).  No per-launch host value enters the kernel, so a launch captured in a
+// CUDA graph replays correctly.
 struct NpCtrl {
-  unsigned long long nonce;
+  unsigned long long reserved;
   unsigned int counter_a;
   unsigned int counter_b;
   unsigned int pad[12];
@@ -307,8 +310,7 @@ template <bool BWD>
 __global__ void __launch_bounds__(kConsumers + 32, 1)
 npplus_ring_kernel(const float* __restrict__ x, const float* __restrict__ alpha, const float* __restrict__ eps,
                    const float* __restrict__ mean_in, float* __restrict__ out, float* __restrict__ mean_out,
-                   float* __restrict__ beta_out, unsigned char* ws, const NpGeom g, unsigned long long nonce,
-                   unsigned long long* trace) {
+                   float* __restrict__ beta_out, unsigned char* ws, const NpGeom g, unsigned long long* trace) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   // resident units of this CTA: a static HEAD of T units parked in TMEM at the very start (their imbalance is absorbed
   // by the dynamic queue that follows) and a static TAIL of S units that stays in the ring
@@ -351,12 +353,7 @@ npplus_ring_kernel(const float* __restrict__ x, const float* __restrict__ alpha,
   if (tid == 0) {
     for (int s = 0; s < S; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], kWarps); slot_cnt[s] = 0; }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    if (blockIdx.x == 0) {                               // open this launch's queues: the first batches are static
-      ctrl->counter_a = gridDim.x * g.grab;
-      ctrl->counter_b = 0;
-      __threadfence();
-      *reinterpret_cast<volatile unsigned long long*>(&ctrl->nonce) = nonce;
-    }
+    if (blockIdx.x == 0) ctrl->counter_b = 0;            // read behind the second grid barrier only
   }
   if (is_producer && T > RG) {                           // the whole TMEM (one CTA per SM, no MMA in this kernel)
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(&tmem_base_s)) : "memory");
@@ -396,15 +393,10 @@ npplus_ring_kernel(const float* __restrict__ x, const float* __restrict__ alpha,
       for (int j = 0; j < T; ++j) issue(head0 + j, pol_stream);
       // the last g.keep_units of the dynamic range are the first ones re-read in phase B: ask L2 to keep them
       const int keep_lo = u_dyn - g.keep_units, mid_lo = keep_lo - g.mid_units;
-      unsigned base = blockIdx.x * g.grab;
-      bool open = blockIdx.x == 0;
+      unsigned base = blockIdx.x * g.grab;               // the first batch of every CTA is static, the queue starts behind them
+      const unsigned q0 = gridDim.x * (unsigned)g.grab;
       while (base < (unsigned)u_dyn) {
-        if (!open) {
-          while (*reinterpret_cast<volatile unsigned long long*>(&ctrl->nonce) != nonce) {}
-          __threadfence();
-          open = true;
-        }
-        const unsigned nbase = atomicAdd(&ctrl->counter_a, (unsigned)g.grab);   // in flight while this batch is issued
+        const unsigned nbase = q0 + atomicAdd(&ctrl->counter_a, (unsigned)g.grab);   // in flight while this batch is issued
         for (int q = 0; q < g.grab && base + q < (unsigned)u_dyn; ++q) {
           const int u = (int)base + q;
           issue(dyn0 + u, u >= keep_lo ? pol_keep : (u >= mid_lo ? pol_mid : pol_stream));
@@ -465,6 +457,7 @@ npplus_ring_kernel(const float* __restrict__ x, const float* __restrict__ alpha,
   __threadfence();
   cg::this_grid().sync();
   stamp(2);
+  if (blockIdx.x == 0 && tid == 0) ctrl->counter_a = 0;  // every phase-A grab precedes the barrier: ready for the next launch
 
   // ---------------- statistics ----------------
   np_stage1<BWD>(ps, mean_in, eps, g, pm, chan, blockIdx.x * (kWarps + 1) + warp, gridDim.x * (kWarps + 1));
@@ -699,9 +692,9 @@ void plan_launch(int N, int C, int HW, bool ring, const DeviceInfo& di, NpLaunch
   const size_t slack = 1024;                                     // static smem + alignment
   if (ring) {
     long long grab = upc / 8;
-    static const long long grab_a = getenv("MRFP_NPPLUS_GRAB_A") ? atoll(getenv("MRFP_NPPLUS_GRAB_A")) : 2;   // measured: 2 beats 1 (queue-bound) and 4, 8
+    constexpr long long grab_a = 2;                              // measured: 2 beats 1 (queue-bound) and 4, 8
     g.grab = (int)(grab < 1 ? 1 : (grab > grab_a ? grab_a : grab));
-    static const int grab_b = getenv("MRFP_NPPLUS_GRAB_B") ? atoi(getenv("MRFP_NPPLUS_GRAB_B")) : 2;
+    constexpr int grab_b = 2;
     g.grab_b = g.grab < grab_b ? g.grab : grab_b;
     // per slot: the unit, two mbarriers, 16 warp partials, (a, b), unit index, fold counter
     const size_t per_slot = (size_t)kUnitVecs * 16 + 16 + kWarps * 8 + 8 + 4 + 4;
@@ -710,22 +703,14 @@ void plan_launch(int N, int C, int HW, bool ring, const DeviceInfo& di, NpLaunch
     if (s > min_upc) s = min_upc;                                // every CTA owns a full static tail
     if (s < 1) s = 1;
     g.slots = (int)s;
-    static const long long tmem_max = getenv("MRFP_NPPLUS_TMEM_UNITS") ? atoll(getenv("MRFP_NPPLUS_TMEM_UNITS")) : kTmemUnits;
     long long t = min_upc - s;
-    if (t > tmem_max) t = tmem_max;
     if (t > kTmemUnits) t = kTmemUnits;
     g.tmem_units = (int)(t < 0 ? 0 : t);
-    static const bool reg_park = !(getenv("MRFP_NPPLUS_REG_UNITS") && atoi(getenv("MRFP_NPPLUS_REG_UNITS")) == 0);
-    g.reg_units = (reg_park && min_upc - s - g.tmem_units >= kRegUnits) ? kRegUnits : 0;
+    g.reg_units = (min_upc - s - g.tmem_units >= kRegUnits) ? kRegUnits : 0;
     g.u_dyn = (int)(g.U - (long long)L->grid * (g.slots + g.tmem_units + g.reg_units));
     L->smem = align_up((size_t)g.slots * per_slot, 16);
-    // L2 share reserved for phase-B re-reads (MRFP_NPPLUS_KEEP_MB overrides; default 64 MiB)
-    static const long long keep_mb = getenv("MRFP_NPPLUS_KEEP_MB") ? atoll(getenv("MRFP_NPPLUS_KEEP_MB")) : 64;
-    g.keep_units = (int)((keep_mb << 20) / ((long long)kUnitVecs * 16));
-    static const long long mid_mb = getenv("MRFP_NPPLUS_MID_MB") ? atoll(getenv("MRFP_NPPLUS_MID_MB")) : 0;
-    g.mid_units = (int)((mid_mb << 20) / ((long long)kUnitVecs * 16));
-    static const int heads_last = getenv("MRFP_NPPLUS_HEADS_LAST") ? atoi(getenv("MRFP_NPPLUS_HEADS_LAST")) : 0;
-    g.heads_last = heads_last;
+    // L2 share asked to keep the last-read units for the phase-B re-read (0-100 MiB measured the same DRAM traffic)
+    g.keep_units = (int)((64LL << 20) / ((long long)kUnitVecs * 16));
   } else {
     const size_t coef_bytes = align_up((size_t)g.max_local_planes * sizeof(float2), 16);
     const size_t unit_bytes = (size_t)g.Q * 4;
@@ -734,11 +719,6 @@ void plan_launch(int N, int C, int HW, bool ring, const DeviceInfo& di, NpLaunch
     g.slots = (int)s;
     L->smem = align_up((size_t)g.slots * unit_bytes, 16) + coef_bytes;
   }
-}
-
-unsigned long long next_nonce() {
-  static std::atomic<unsigned long long> counter{0x9E3779B97F4A7C15ull};
-  return counter.fetch_add(0x9E3779B97F4A7C15ull) | 1ull;       // never 0, never repeats within a process
 }
 
 template <bool BWD>
@@ -762,18 +742,17 @@ int run(const float* x, const float* alpha, const float* eps, const float* mean_
   if (want_trace && ws_bytes >= base + (size_t)L.grid * 64) trace = (unsigned long long*)((char*)ws + base);
   if (ring) {
     unsigned char* wsb = (unsigned char*)ws;
-    unsigned long long nonce = next_nonce();
     void* args[] = {(void*)&x, (void*)&alpha, (void*)&eps, (void*)&mean_in, (void*)&out, (void*)&mean_out,
-                    (void*)&beta_out, (void*)&wsb, (void*)&g, (void*)&nonce, (void*)&trace};
+                    (void*)&beta_out, (void*)&wsb, (void*)&g, (void*)&trace};
     void* kern = (void*)npplus_ring_kernel<BWD>;
-    MRFP_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.smem));
+    MRFP_SMEM_OPT_IN(kern, di.max_smem_optin - 1024, di.device);   // once per device: the ring takes what the SM has (minus the static part)
     MRFP_CUDA_TRY(cudaLaunchCooperativeKernel(kern, dim3(L.grid), dim3(kConsumers + 32), args, L.smem, (cudaStream_t)stream));
   } else {
     double* ps = (double*)((char*)ws + sizeof(NpCtrl));
     void* args[] = {(void*)&x, (void*)&alpha, (void*)&eps, (void*)&mean_in, (void*)&out,
                     (void*)&mean_out, (void*)&beta_out, (void*)&ps, (void*)&g, (void*)&trace};
     void* kern = (void*)npplus_scalar_kernel<BWD>;
-    MRFP_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.smem));
+    MRFP_SMEM_OPT_IN(kern, di.max_smem_optin - 1024, di.device);
     MRFP_CUDA_TRY(cudaLaunchCooperativeKernel(kern, dim3(L.grid), dim3(kConsumers), args, L.smem, (cudaStream_t)stream));
   }
   return MRFP_OK;
@@ -781,6 +760,13 @@ int run(const float* x, const float* alpha, const float* eps, const float* mean_
 
 }  // namespace
 }  // namespace mrfp
+
+extern "C" int mrfp_npplus_ws_init(void* ws, size_t ws_bytes, void* stream) {
+  if (!ws) return MRFP_ERR_NULL_POINTER;
+  if (ws_bytes < sizeof(mrfp::NpCtrl) || ((uintptr_t)ws & 15)) return MRFP_ERR_WORKSPACE;
+  MRFP_CUDA_TRY(cudaMemsetAsync(ws, 0, sizeof(mrfp::NpCtrl), (cudaStream_t)stream));
+  return MRFP_OK;
+}
 
 extern "C" size_t mrfp_npplus_ws_bytes(int N, int C, int HW) {
   if (N <= 0 || C <= 0 || HW <= 0) return 0;

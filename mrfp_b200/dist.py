@@ -4,6 +4,9 @@ The path shards by batch with NO collective (every NP+ / HRFP-BN statistic is lo
 as under the reference's nn.DataParallel scatter, main.py:824); the only cross-rank operations here are the
 ones a benchmark or a trainer needs around it.
 """
+import random
+
+import numpy as np
 import torch
 import torch.distributed as dist
 
@@ -22,11 +25,15 @@ def shard_bounds(global_batch: int, world: int, rank: int):
 
 
 def seed_rank_streams(base_seed: int, rank: int):
-    """The reference re-seeds every module to 0 at import (deepv3.py:39-44), which would make all ranks draw
-    identical alpha / eps / HRFP weights; give every rank its own torch stream instead."""
-    torch.manual_seed(base_seed + 1000003 * rank)
+    """The reference re-seeds every module to 0 at import (deepv3.py:39-44: random, numpy, torch), which would make all
+    ranks draw identical gates / alpha / eps / HRFP weights; give every rank its own streams instead.  The three MRFP
+    gates p, p2, p3 come from Python's `random.random()` (deepv3.py:281-283), so that generator is seeded too."""
+    seed = base_seed + 1000003 * rank
+    random.seed(seed)
+    np.random.seed(seed % (2 ** 32))
+    torch.manual_seed(seed)
     if torch.cuda.is_available():
-        torch.cuda.manual_seed(base_seed + 1000003 * rank)
+        torch.cuda.manual_seed(seed)
 
 
 def max_over_ranks(value: float, device="cpu") -> float:

@@ -5,8 +5,10 @@ ordinary `nn.Conv2d` / `nn.BatchNorm2d` modules owned by the caller (same names 
 as the reference); this file only plans the geometry, owns the workspaces and exposes the chain as
 one `torch.autograd.Function` (input gradient only — the weights are frozen, deepv3.py:221-237).
 """
+import collections
 import ctypes
 import math
+import threading
 from typing import Optional, Sequence
 
 import numpy as np
@@ -14,8 +16,9 @@ import torch
 
 from . import _lib
 
-MATH_FP32 = 0
-MATH_BF16 = 2
+MATH_FP32 = 0      # CUDA-core fp32 convolutions (tight parity mode)
+MATH_TF32 = 1      # tcgen05 kind::tf32, fp32 storage: the arithmetic of the reference's cuDNN convolutions (TF32 default)
+MATH_BF16 = 2      # tcgen05 kind::f16 on bf16 operands and bf16 storage, fp32 accumulation (default: half the HBM traffic)
 DEFAULT_WIDTHS = (64, 64, 128, 256)
 
 
@@ -55,12 +58,10 @@ class HrfpPlan:
             out = (ctypes.c_int * 7)()
             _lib.check(lib.mrfp_hrfp_plan_stage(handle, k, out), "mrfp_hrfp_plan_stage")
             self.stages.append(tuple(out))
-        self._ws = None
 
     def workspace(self) -> torch.Tensor:
-        if self._ws is None:
-            self._ws = torch.empty(self.ws_bytes, dtype=torch.uint8, device=self.device)
-        return self._ws
+        """Scratch for one forward or backward call: the grow-only per-(device, stream) buffer every plan shares."""
+        return _lib.scratch(self.device, self.ws_bytes, "hrfp")
 
     @property
     def dec_shape(self):
@@ -76,15 +77,23 @@ class HrfpPlan:
             pass
 
 
-_PLAN_CACHE = {}
+_PLAN_CACHE = collections.OrderedDict()      # LRU: a plan is host geometry + a small LUT tensor; scratch is shared (_lib.scratch)
+_PLAN_CACHE_CAP = 16
+_PLAN_LOCK = threading.Lock()                 # nn.DataParallel runs replicas in host threads
 
 
 def get_plan(n, cin, xh, xw, h, w, device, math_mode=MATH_BF16, widths=DEFAULT_WIDTHS) -> HrfpPlan:
     key = (n, cin, xh, xw, h, w, math_mode, tuple(widths), str(device))
-    p = _PLAN_CACHE.get(key)
-    if p is None:
-        p = HrfpPlan(n, cin, xh, xw, h, w, device, math_mode, widths)
+    with _PLAN_LOCK:
+        p = _PLAN_CACHE.get(key)
+        if p is not None:
+            _PLAN_CACHE.move_to_end(key)
+            return p
+    p = HrfpPlan(n, cin, xh, xw, h, w, device, math_mode, widths)
+    with _PLAN_LOCK:
         _PLAN_CACHE[key] = p
+        while len(_PLAN_CACHE) > _PLAN_CACHE_CAP:      # an evicted plan is destroyed when its last user (a ctx) lets go
+            _PLAN_CACHE.popitem(last=False)
     return p
 
 
@@ -131,7 +140,7 @@ class _HrfpFn(torch.autograd.Function):
             np_alpha = np_draws[0].reshape(n, c).to(torch.float32).contiguous()
             np_eps = np_draws[1].reshape(n, c).to(torch.float32).contiguous()
             np_mean = torch.empty((n, c), dtype=torch.float32, device=dev)
-            np_ws = torch.empty(lib.mrfp_hrfp_np_ws_bytes(n, c), dtype=torch.uint8, device=dev)
+            np_ws = _lib.scratch(dev, lib.mrfp_hrfp_np_ws_bytes(n, c), "hrfp_np")      # per-call scratch (both directions)
             with torch.cuda.device(dev):
                 rc = lib.mrfp_hrfp_fwd_np(plan.handle, xp_c.data_ptr(), wa, ga, ba, rma, rva, momentum, eps,
                                           np_alpha.data_ptr(), np_eps.data_ptr(), np_mean.data_ptr(), None,
@@ -139,7 +148,7 @@ class _HrfpFn(torch.autograd.Function):
                                           None if ocdec is None else ocdec.data_ptr(),
                                           plan.lut.data_ptr(), saved.data_ptr(), ws.data_ptr(), _stream_ptr(dev))
             _lib.check(rc, "mrfp_hrfp_fwd_np")
-            ctx.np = (np_alpha, np_eps, np_mean, np_ws)
+            ctx.np = (np_alpha, np_eps, np_mean)
         else:
             with torch.cuda.device(dev):
                 rc = lib.mrfp_hrfp_fwd(plan.handle, xp_c.data_ptr(), wa, ga, ba, rma, rva, momentum, eps,
@@ -150,7 +159,8 @@ class _HrfpFn(torch.autograd.Function):
             _lib.check(rc, "mrfp_hrfp_fwd")
         ctx.plan = plan
         ctx.saved_buf = saved
-        ctx.gammas = [g for g in gammas]       # keep alive; gamma is read again in backward
+        ctx.gammas = [g for g in gammas]       # gamma is read again in backward: it must still be the forward's
+        ctx.gamma_versions = [g._version for g in gammas]
         ctx.has_add = x_add is not None
         ctx.want_out, ctx.want_dec = want_out, want_dec
         ctx.mail = None
@@ -171,6 +181,12 @@ class _HrfpFn(torch.autograd.Function):
     def backward(ctx, *grads):
         lib = _lib.load()
         plan = ctx.plan
+        if ctx.saved_buf is None:
+            raise _lib.MrfpError("HRFP backward called a second time: the chain's saved state is freed after the first "
+                                 "backward (retain_graph is not supported)")
+        if any(g._version != v for g, v in zip(ctx.gammas, ctx.gamma_versions)):
+            raise _lib.MrfpError("an HRFP BatchNorm weight was modified in place between forward and backward "
+                                 "(e.g. reinit_hrfp() ran in between): the gradient would mix old and new parameters")
         gi = iter(grads)
         g_out = next(gi) if ctx.want_out else None
         g_dec = next(gi) if ctx.want_dec else None
@@ -187,7 +203,8 @@ class _HrfpFn(torch.autograd.Function):
             ws = plan.workspace()
             with torch.cuda.device(dev):
                 if ctx.np is not None:      # gradient through NP+(xp) joins in the chain's last pass
-                    a_, e_, m_, w_ = ctx.np
+                    a_, e_, m_ = ctx.np
+                    w_ = _lib.scratch(dev, lib.mrfp_hrfp_np_ws_bytes(plan.n, plan.cin), "hrfp_np")
                     rc = lib.mrfp_hrfp_bwd_np(plan.handle, None if g_out_c is None else g_out_c.data_ptr(),
                                               None if g_dec_c is None else g_dec_c.data_ptr(), ga, a_.data_ptr(),
                                               e_.data_ptr(), m_.data_ptr(), w_.data_ptr(), plan.lut.data_ptr(),
@@ -214,6 +231,10 @@ def hrfp_chain(xp, convs, bns, h, w, x_add=None, want_out=True, want_dec=True, m
     value is an `HrfpDec` handle for `hrfp_plus_add` instead of a materialised tensor."""
     n, cin, xh, xw = xp.shape
     widths = tuple(c.out_channels for c in convs[:4])
+    if (xh, xw) != (math.ceil(h / 4), math.ceil(w / 4)):
+        # deepv3.py:327 resamples to (ceil(h/4), ceil(w/4)) and :330 adds xp: torch.add would raise on a mismatch
+        raise _lib.MrfpError(f"HRFP chain: xp is {xh}x{xw} but the chain ends at {math.ceil(h / 4)}x{math.ceil(w / 4)} "
+                             f"for a {h}x{w} image (deepv3.py:327, :330)")
     plan = get_plan(n, cin, xh, xw, h, w, xp.device, math_mode, widths)
     weights = [c.weight for c in convs]
     gammas = [b.weight for b in bns]

@@ -266,8 +266,11 @@ class MRFPPlus(nn.Module, MRFPMixin):
             return mods[-1](_instnorm.module_instance_norm_relu(mods[-3], x, True))
         return self.layer0(x)
 
-    def forward(self, x, gts=None, training=True):
-        p, p2, p3 = random.random(), random.random(), random.random()       # deepv3.py:281-283
+    def forward(self, x, gts=None, training=True, gates=None):
+        """deepv3.py:280-367.  `gates` (extension): the three Bernoulli draws (p, p2, p3) made by the caller with the
+        reference's `random.random()` calls instead of here — a CUDA-graph trainer has to know the branch before it
+        picks the graph to replay (mrfp_b200/train_step.py)."""
+        p, p2, p3 = gates if gates is not None else (random.random(), random.random(), random.random())   # deepv3.py:281-283
         h, w = x.shape[2:]
         if training and p < 0.5:
             self.reinit_hrfp()                                              # deepv3.py:290-306

@@ -29,7 +29,7 @@ class _NPPlusFn(torch.autograd.Function):
         mean = torch.empty((n, c), device=x.device, dtype=torch.float32)
         beta = torch.empty((n, c), device=x.device, dtype=torch.float32)
         ws_bytes = lib.mrfp_npplus_ws_bytes(n, c, h * w)
-        ws = torch.empty(ws_bytes, device=x.device, dtype=torch.uint8)
+        ws = _lib.scratch(x.device, ws_bytes, "npplus")
         with torch.cuda.device(x.device):
             rc = lib.mrfp_npplus_fwd_f32(x.data_ptr(), alpha.data_ptr(), eps.data_ptr(), out.data_ptr(),
                                          mean.data_ptr(), beta.data_ptr(), ws.data_ptr(), ws_bytes,
@@ -47,7 +47,7 @@ class _NPPlusFn(torch.autograd.Function):
         g = gout.contiguous()
         gin = torch.empty_like(g)
         ws_bytes = lib.mrfp_npplus_ws_bytes(n, c, h * w)
-        ws = torch.empty(ws_bytes, device=g.device, dtype=torch.uint8)
+        ws = _lib.scratch(g.device, ws_bytes, "npplus")
         with torch.cuda.device(g.device):
             rc = lib.mrfp_npplus_bwd_f32(g.data_ptr(), alpha.data_ptr(), eps.data_ptr(), mean.data_ptr(),
                                          gin.data_ptr(), ws.data_ptr(), ws_bytes, n, c, h * w, _stream_ptr(g))
@@ -99,7 +99,7 @@ class _NPPlusPresummedFn(torch.autograd.Function):
         out = torch.empty_like(x)
         mean = torch.empty((n, c), device=x.device, dtype=torch.float32)
         ws_bytes = lib.mrfp_npplus_presummed_ws_bytes(n, c)
-        ws = torch.empty(ws_bytes, device=x.device, dtype=torch.uint8)
+        ws = _lib.scratch(x.device, ws_bytes, "npplus_pre")
         with torch.cuda.device(x.device):
             rc = lib.mrfp_npplus_fwd_presummed_f32(x.data_ptr(), psum.data_ptr(), alpha.data_ptr(), eps.data_ptr(),
                                                    out.data_ptr(), mean.data_ptr(), None, ws.data_ptr(), ws_bytes,

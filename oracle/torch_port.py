@@ -41,15 +41,65 @@ def make_layers(weights=None, gammas=None):
     return convs, bns
 
 
-def hrfp_chain(convs, bns, xp, h, w):
-    o = F.relu(bns[0](F.interpolate(convs[0](xp), scale_factor=(1.205, 1.205))))
-    o = F.relu(bns[1](F.interpolate(convs[1](o), scale_factor=(1.2, 1.2))))
-    o = F.relu(bns[2](F.interpolate(convs[2](o), scale_factor=(1.2, 1.2))))
-    dec = F.relu(bns[3](F.interpolate(convs[3](o), size=(int(h / 2), int(w / 2)))))
-    o = F.relu(bns[4](F.interpolate(convs[4](dec), size=(int(h / 2), int(w / 2)))))
-    o = F.relu(bns[5](F.interpolate(convs[5](o), scale_factor=(0.838, 0.838))))
-    o = F.relu(bns[6](F.interpolate(convs[6](o), scale_factor=(0.798, 0.798))))
-    o = F.relu(bns[7](F.interpolate(convs[7](o), size=(math.ceil(h / 4), math.ceil(w / 4)))))
+class _NearestExactAdjoint(torch.autograd.Function):
+    """F.interpolate(mode='nearest') with ATen's forward index rule and the EXACT adjoint as backward.
+
+    Needed on CUDA only: ATen's CUDA `upsample_nearest2d_backward` is not the adjoint of its own forward for
+    scale_factor=1.2 (the two x1.2 stages of deepv3.py:321-322).  The forward picks src = floorf(dst * float(1/1.2)); the
+    backward re-derives the replica range of a source pixel as [ceilf(src * 1.2f), ceilf((src+1) * 1.2f)) and the two
+    float roundings disagree at every fifth pixel: <L x, v> and <x, L^T v> differ by 20-40 % (tools/adjoint_nearest.py on
+    the B200 box, torch 2.11; scale factors 1.205 / 0.838 / 0.798 and the size= calls are consistent, and so is the CPU
+    kernel for every case).  The reference's CPU autograd, the fixtures under tests/golden/ and this repo's kernels all
+    implement the adjoint of the forward."""
+
+    @staticmethod
+    def forward(ctx, x, idx_h, idx_w):
+        ctx.save_for_backward(idx_h, idx_w)
+        ctx.in_hw = (x.shape[2], x.shape[3])
+        return x.index_select(2, idx_h).index_select(3, idx_w)
+
+    @staticmethod
+    def backward(ctx, g):
+        idx_h, idx_w = ctx.saved_tensors
+        ih, iw = ctx.in_hw
+        t = g.new_zeros(g.shape[0], g.shape[1], ih, g.shape[3]).index_add_(2, idx_h, g)
+        return g.new_zeros(g.shape[0], g.shape[1], ih, iw).index_add_(3, idx_w, t), None, None
+
+
+def _nearest_index(in_size, out_size, scale_factor, device):
+    """ATen's forward rule (upsample_nearest2d): src = min(floorf(dst * scale), in - 1), scale a float32."""
+    scale = torch.tensor(1.0 / scale_factor if scale_factor else in_size / out_size, dtype=torch.float64).to(torch.float32)
+    if not scale_factor:
+        scale = torch.tensor(in_size, dtype=torch.float32) / torch.tensor(out_size, dtype=torch.float32)
+    dst = torch.arange(out_size, dtype=torch.float32)
+    return torch.clamp(torch.floor(dst * scale).to(torch.int64), max=in_size - 1).to(device)
+
+
+def nearest(x, scale_factor=None, size=None, exact_adjoint=False):
+    """The reference's F.interpolate call (default mode='nearest'); exact_adjoint: see _NearestExactAdjoint."""
+    if not exact_adjoint:
+        return F.interpolate(x, scale_factor=scale_factor, size=size)
+    ih, iw = x.shape[2], x.shape[3]
+    if scale_factor is not None:
+        oh, ow = int(math.floor(ih * scale_factor[0])), int(math.floor(iw * scale_factor[1]))
+        idx_h, idx_w = _nearest_index(ih, oh, scale_factor[0], x.device), _nearest_index(iw, ow, scale_factor[1], x.device)
+    else:
+        oh, ow = size
+        idx_h, idx_w = _nearest_index(ih, oh, None, x.device), _nearest_index(iw, ow, None, x.device)
+    return _NearestExactAdjoint.apply(x, idx_h, idx_w)
+
+
+def hrfp_chain(convs, bns, xp, h, w, exact_adjoint=False):
+    """deepv3.py:320-327.  exact_adjoint=True replaces only the BACKWARD of the nearest resamples (CUDA runs)."""
+    ea = exact_adjoint
+    o = F.relu(bns[0](nearest(convs[0](xp), scale_factor=(1.205, 1.205), exact_adjoint=ea)))
+    o = F.relu(bns[1](nearest(convs[1](o), scale_factor=(1.2, 1.2), exact_adjoint=ea)))
+    o = F.relu(bns[2](nearest(convs[2](o), scale_factor=(1.2, 1.2), exact_adjoint=ea)))
+    dec = F.relu(bns[3](nearest(convs[3](o), size=(int(h / 2), int(w / 2)), exact_adjoint=ea)))
+    o = F.relu(bns[4](nearest(convs[4](dec), size=(int(h / 2), int(w / 2)), exact_adjoint=ea)))
+    o = F.relu(bns[5](nearest(convs[5](o), scale_factor=(0.838, 0.838), exact_adjoint=ea)))
+    o = F.relu(bns[6](nearest(convs[6](o), scale_factor=(0.798, 0.798), exact_adjoint=ea)))
+    o = F.relu(bns[7](nearest(convs[7](o), size=(math.ceil(h / 4), math.ceil(w / 4)), exact_adjoint=ea)))
     return o, dec
 
 

@@ -108,9 +108,12 @@ def test_full_size_properties():
 
 
 @pytest.mark.parametrize("shape", [(8, 64, 96, 96), (4, 24, 33, 31), (8, 256, 192, 192)])
-def test_workspace_needs_no_initialisation_and_results_are_deterministic(shape):
-    """The workspace may hold anything (the queues are opened per launch with a nonce): zeros, 0xFF and random bytes
-    give bit-identical outputs, forward and backward, launch after launch."""
+def test_workspace_protocol_and_determinism(shape):
+    """Beyond its 64-byte control block the workspace may hold anything; the control block is zeroed once
+    (mrfp_npplus_ws_init) and every launch leaves the phase-A queue counter zero (the phase-B counter is cleared at
+    kernel entry), so one buffer serves launch after launch.  Zeros, 0xFF and
+    random bytes give bit-identical outputs, forward and backward; a second pair of launches on the SAME buffer (no
+    re-initialisation) does too."""
     from mrfp_b200 import _lib
     lib = _lib.load()
     n, c, h, w = shape
@@ -128,16 +131,57 @@ def test_workspace_needs_no_initialisation_and_results_are_deterministic(shape):
             ws.fill_(255)
         elif fill == "rand":
             ws.random_(0, 256)
-        out = torch.empty_like(x); gin = torch.empty_like(x)
-        mean = torch.empty(n, c, device="cuda"); beta = torch.empty(n, c, device="cuda")
-        assert lib.mrfp_npplus_fwd_f32(x.data_ptr(), alpha.data_ptr(), eps.data_ptr(), out.data_ptr(), mean.data_ptr(),
-                                       beta.data_ptr(), ws.data_ptr(), wsb, n, c, h * w, st) == 0
-        assert lib.mrfp_npplus_bwd_f32(g.data_ptr(), alpha.data_ptr(), eps.data_ptr(), mean.data_ptr(), gin.data_ptr(),
-                                       ws.data_ptr(), wsb, n, c, h * w, st) == 0
-        torch.cuda.synchronize()
-        outs.append((out, gin, mean))
+        assert lib.mrfp_npplus_ws_init(ws.data_ptr(), wsb, st) == 0
+        for rep in range(2):
+            out = torch.empty_like(x); gin = torch.empty_like(x)
+            mean = torch.empty(n, c, device="cuda"); beta = torch.empty(n, c, device="cuda")
+            assert lib.mrfp_npplus_fwd_f32(x.data_ptr(), alpha.data_ptr(), eps.data_ptr(), out.data_ptr(), mean.data_ptr(),
+                                           beta.data_ptr(), ws.data_ptr(), wsb, n, c, h * w, st) == 0
+            assert lib.mrfp_npplus_bwd_f32(g.data_ptr(), alpha.data_ptr(), eps.data_ptr(), mean.data_ptr(), gin.data_ptr(),
+                                           ws.data_ptr(), wsb, n, c, h * w, st) == 0
+            torch.cuda.synchronize()
+            assert int(ws[8:12].max()) == 0              # counter_a is zero again
+            outs.append((out, gin, mean))
     for o, gi, m in outs[1:]:
         assert torch.equal(o, outs[0][0]) and torch.equal(gi, outs[0][1]) and torch.equal(m, outs[0][2])
+    assert lib.mrfp_npplus_ws_init(None, wsb, st) == -1
+    assert lib.mrfp_npplus_ws_init(ws.data_ptr(), 8, st) == -3
+
+
+@pytest.mark.parametrize("shape", [(4, 64, 96, 96), (3, 24, 33, 31)])
+def test_cuda_graph_replay_of_forward_and_backward(shape):
+    """NP+ forward + backward captured into a CUDA graph and replayed on new inputs equals the eager calls (the ring
+    kernel's queue counters are restored by the kernel itself, nothing per-launch comes from the host)."""
+    from mrfp_b200.npplus import np_plus_with_draws
+    n, c, h, w = shape
+    torch.manual_seed(11)
+    xs = torch.relu(torch.randn(n, c, h, w, device="cuda"))
+    gs = torch.randn(n, c, h, w, device="cuda")
+    a = 1 + 0.75 * torch.randn(n, c, device="cuda")
+    e = 0.75 * torch.randn(n, c, device="cuda")
+
+    def run(x_, g_):
+        xr = x_.detach().requires_grad_(True)
+        y = np_plus_with_draws(xr, a, e)
+        (gx,) = torch.autograd.grad(y, xr, g_)
+        return y, gx
+
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        for _ in range(2):                               # warm-up on the capture stream: scratch buffers, attributes
+            run(xs, gs)
+    torch.cuda.current_stream().wait_stream(side)
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph, stream=side):
+        y_g, gx_g = run(xs, gs)
+    for it in range(3):
+        xs.copy_(torch.relu(torch.randn(n, c, h, w, device="cuda")))
+        gs.copy_(torch.randn(n, c, h, w, device="cuda"))
+        graph.replay()
+        torch.cuda.synchronize()
+        y_e, gx_e = run(xs, gs)
+        assert torch.equal(y_g, y_e) and torch.equal(gx_g, gx_e), it
 
 
 @pytest.mark.parametrize("shape", [(2, 256, 192, 192), (3, 24, 33, 31), (4, 116, 96, 96), (8, 64, 48, 48)])

@@ -16,7 +16,7 @@ def bench(n, c, h, w, iters=20):
     mean = torch.empty(n, c, device="cuda")
     beta = torch.empty(n, c, device="cuda")
     wsb = lib.mrfp_npplus_ws_bytes(n, c, h * w)
-    ws = torch.empty(wsb, dtype=torch.uint8, device="cuda")
+    ws = torch.zeros(wsb, dtype=torch.uint8, device="cuda")
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
     st = torch.cuda.current_stream().cuda_stream
     res = {}
