@@ -48,8 +48,10 @@ def parse():
 # ----------------------------------------------------------------------------------------------------------
 # reference arm / cpu_baseline: the reference's CPU implementation of the path (oracle/torch_port.py)
 # ----------------------------------------------------------------------------------------------------------
-def cpu_reference_run(steps, warmup, batch=2):
-    """Bounded sample: the same step at BASELINE config[0] size (batch 2), all host threads."""
+def cpu_reference_run(steps, warmup, batch=N_PER_GPU, budget_s=150.0):
+    """The reference's CPU implementation of the step (oracle/torch_port.py: the reference's own torch operators) at the
+    SAME per-GPU batch and shapes as the GPU arm, all host threads.  Bounded: at most `steps` timed passes and no more
+    than fit into `budget_s` seconds (never fewer than 3); the line reports the passes actually timed."""
     import torch
     from oracle import torch_port as T
     torch.set_num_threads(os.cpu_count() or 1)
@@ -62,31 +64,57 @@ def cpu_reference_run(steps, warmup, batch=2):
     grads = (torch.randn(batch, 64, XH, XW, generator=g), torch.randn(batch, 256, H_IMG // 2, W_IMG // 2, generator=g),
              torch.randn(batch, 256, XH, XW, generator=g))
     d1 = torch.randn(batch, 256, XH, XW, generator=g)                   # decoder feature before the Upsample of deepv3.py:356
-    for _ in range(warmup):
+    t_w = time.perf_counter()
+    for _ in range(max(1, warmup)):
         T.mrfp_step(convs, bns, xp, f2, d1, draws, grads, H_IMG, W_IMG)
+    per = (time.perf_counter() - t_w) / max(1, warmup)
+    steps = max(3, min(steps, int(budget_s / max(per, 1e-3))))
     t0 = time.perf_counter()
     for _ in range(steps):
         T.mrfp_step(convs, bns, xp, f2, d1, draws, grads, H_IMG, W_IMG)
     dt = time.perf_counter() - t0
-    return dict(value=batch * steps / dt, unit=UNIT, cores=torch.get_num_threads(), kind="port",
-                sample=f"same step at batch {batch} (BASELINE config[0] shapes), {steps} timed + {warmup} warm-up passes of "
-                       "oracle/torch_port.py (the reference's torch operators on the host cores); the reference itself is a "
-                       "Python package under /root/reference that does not exist on the GPU box"), dt / steps * 1e3
+    return dict(value=batch * steps / dt, unit=UNIT, cores=torch.get_num_threads(), kind="port", batch=batch, timed_passes=steps,
+                sample=f"the same step at the same per-GPU batch ({batch}) and shapes, {steps} timed + {max(1, warmup)} warm-up passes "
+                       "of oracle/torch_port.py (the reference's torch operators on all host cores; its throughput is the "
+                       "host's, whatever the number of GPUs in the other arm); the reference itself is a Python package "
+                       "under /root/reference that does not exist on the GPU box"), dt / steps * 1e3, steps
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    steps = max(1, min(args.steps, 3))
-    warm = 1 if args.warmup > 0 else 0
-    base, ms = cpu_reference_run(steps, warm)
+    warm = max(1, min(args.warmup, 2))
+    base, ms, steps = cpu_reference_run(args.steps, warm)
     line = {"impl": "reference", "metric": METRIC, "value": base["value"], "unit": UNIT, "n_gpus": args.gpus,
             "steps": steps, "warmup": warm, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": CONFIG, "cpu_baseline": base,
             "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line))
+
+
+def traffic_from_profiles(kernel_substr, file_hints=("",), prefixes=("R2_", "r9_", "r5_", "r3_")):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one launch of the kernel, read from the newest committed
+    `ncu --set full` export under profiles/ (`ncu -i ... --page raw --csv`: header row, unit row, one value row)."""
+    import csv
+    import glob
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
+    for pre in prefixes:
+        for path in sorted(glob.glob(os.path.join(ROOT, "profiles", pre + "*_raw.csv")), reverse=True):
+            try:
+                rows = list(csv.reader(open(path)))
+                h, u, v = rows[0], rows[1], rows[2]
+                if kernel_substr not in v[h.index("Kernel Name")] or not any(fh in os.path.basename(path) for fh in file_hints):
+                    continue
+                tot = 0.0
+                for key in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+                    i = h.index(key)
+                    tot += float(v[i].replace(",", "")) * scale[u[i]]
+                return int(tot), os.path.relpath(path, ROOT)
+            except Exception:          # noqa: BLE001  (a file of another layout: skip it)
+                continue
+    return None, None
 
 
 # ----------------------------------------------------------------------------------------------------------
@@ -470,9 +498,9 @@ def run_ours(args):
     big = np_rows["npplus_256ch"]
     roof_np = {"kernel": "npplus_ring_kernel<fwd> on (8,256,192,192)", "bound": "hbm", "achieved": big["fwd_gbs"], "peak": hbm_peak,
                "unit": "GB/s", "frac": big["fwd_gbs"] / hbm_peak,
-               "traffic": 498743808 + 247726848,     # dram__bytes_read.sum + dram__bytes_write.sum per launch
-               "traffic_source": "profiles/r3_np256_raw.csv (ncu --set full, one launch of this kernel); "
-                                 "algorithmic bytes per launch = 603979776",
+               "traffic": traffic_from_profiles("npplus_ring_kernel")[0],   # dram__bytes_read.sum + dram__bytes_write.sum per launch
+               "traffic_source": "%s (ncu --set full, one launch of this kernel); algorithmic bytes per launch = 603979776"
+                                 % traffic_from_profiles("npplus_ring_kernel")[1],
                "peak_source": peak_src,
                "all_four_np_kernels_gbs": np_bytes / np_time / 1e9, "per_call": np_rows}
 
@@ -546,8 +574,9 @@ def run_ours(args):
     top = max(conv_rows, key=lambda r: r["us"])
     roofline = {"kernel": f"conv3x3_tc_kernel<{top['cout']}> stage {top['stage']} ({top['cin']}->{top['cout']} @{top['hw'][0]}x{top['hw'][1]})",
                 "bound": "tensor", "achieved": top["tflops"], "peak": tf_peak, "unit": "TFLOP/s", "frac": top["tflops"] / tf_peak,
-                "traffic": (604724480 + 272979456) if top["stage"] == 4 else None,   # dram read + write bytes per launch
-                "traffic_source": "profiles/r3_conv_d1_raw.csv (ncu --set full, stage 4 forward): A 604 MB read once, Y 302 MB written",
+                "traffic": traffic_from_profiles("conv3x3_tc_kernel", ("conv_s4", "conv_d1"))[0] if top["stage"] == 4 else None,   # dram read + write bytes per launch
+                "traffic_source": "%s (ncu --set full, stage 4 forward: A 604 MB read once, Y 302 MB written)"
+                                  % traffic_from_profiles("conv3x3_tc_kernel", ("conv_s4", "conv_d1"))[1],
                 "peak_source": peak_src, "peak_sustained": tf_sustained,
                 "all_conv_fwd_tflops": conv_flop / conv_time / 1e9, "per_stage": conv_rows}
 
@@ -571,11 +600,19 @@ def run_ours(args):
         o, d = H.hrfp_chain(xr, convs, bns, H_IMG, W_IMG, math_mode=H.MATH_BF16, lazy_dec=True)
         torch.autograd.backward([o, H.hrfp_plus_add_upsampled(dec1_up, d)], [g_x, g_dec])
     t_chain_fb = t_api(chain_fb)
-    hrfp = {"fwd_ms": t_chain_f, "fwd_bwd_ms": t_chain_fb,
+    def chain_fb_tf32():
+        xr.grad = None
+        o, d = H.hrfp_chain(xr, convs, bns, H_IMG, W_IMG, math_mode=H.MATH_TF32, lazy_dec=True)
+        torch.autograd.backward([o, H.hrfp_plus_add_upsampled(dec1_up, d)], [g_x, g_dec])
+    try:
+        t_chain_fb_tf32 = t_api(chain_fb_tf32, 3)
+    except Exception as e_:          # noqa: BLE001
+        t_chain_fb_tf32 = repr(e_)[:200]
+    hrfp = {"fwd_ms": t_chain_f, "fwd_bwd_ms": t_chain_fb, "fwd_bwd_ms_tf32_mode": t_chain_fb_tf32,
             "fwd_tflops_needed_only": HRFP_FLOP_FWD_PER_SAMPLE * n / t_chain_f / 1e9,
             "fwd_bwd_tflops_needed_only": 2 * HRFP_FLOP_FWD_PER_SAMPLE * n / t_chain_fb / 1e9}
 
-    base, _ = cpu_reference_run(1, 1) if world == 1 else (None, None)
+    base = cpu_reference_run(3, 1, budget_s=30.0)[0] if world == 1 else None
 
     # kernels launched per step (ours; memsets excluded): NP+ call 2 fwd + bwd (call 1 is folded into the chain: +1 coefficient block each way); HRFP fwd 1 weight pack + 1 NCHW->NHWC +
     # 8 conv (BN finalised by the last CTA) + 7 BN/ReLU/resample + 1 NHWC->NCHW epilogue (OCout + x); 1 fused HRFP+ add;

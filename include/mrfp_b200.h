@@ -161,6 +161,16 @@ int mrfp_hrfp_plus_add(const mrfp_hrfp_plan_t* plan, const void* saved, const vo
 int mrfp_hrfp_plus_add_bilinear(const mrfp_hrfp_plan_t* plan, const void* saved, const void* lut, const float* dec1,
                                 int lh, int lw, float* out, void* stream);
 
+/* Backward of the reference's Upsample (network/mynn.py:114-119, bilinear, align_corners=True) at the up-sampling sites of
+ * the tail (deepv3.py:356, :362), as a gather instead of ATen's atomicAdd scatter:
+ *   gl (planes, LH, LW) = adjoint of the up-sampling applied to g (planes, OH, OW), OH >= LH, OW >= LW.
+ * The per-axis gather tables are built on the host with ATen's float arithmetic (mrfp_bilinear_bwd_write_table fills
+ * mrfp_bilinear_bwd_table_bytes(L, O) bytes; word [1] of a table is the `span_w` argument); the caller uploads them once. */
+size_t mrfp_bilinear_bwd_table_bytes(int L, int O);
+int    mrfp_bilinear_bwd_write_table(int L, int O, void* host_dst, size_t bytes);
+int    mrfp_bilinear_up_bwd_f32(const float* g, float* gl, long long planes, int LH, int LW, int OH, int OW,
+                                const void* tab_h, const void* tab_w, int span_w, void* stream);
+
 /* Plain variant of the same add for a materialised OCout_dec: out = a + b (n elements). */
 int mrfp_add_f32(const float* a, const float* b, float* out, size_t n, void* stream);
 

@@ -55,6 +55,10 @@ SIGNATURES = {
     "mrfp_hrfp_plus_add_bilinear": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, c_float_p, ctypes.c_int,
                                                    ctypes.c_int, c_float_p, ctypes.c_void_p]),
     "mrfp_add_f32": (ctypes.c_int, [c_float_p, c_float_p, c_float_p, ctypes.c_size_t, ctypes.c_void_p]),
+    "mrfp_bilinear_bwd_table_bytes": (ctypes.c_size_t, [ctypes.c_int, ctypes.c_int]),
+    "mrfp_bilinear_bwd_write_table": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_size_t]),
+    "mrfp_bilinear_up_bwd_f32": (ctypes.c_int, [c_float_p, c_float_p, ctypes.c_longlong, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                                ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]),
     "mrfp_instnorm_fwd_f32": (ctypes.c_int, [c_float_p, c_float_p, c_float_p, c_float_p, c_float_p, c_float_p, ctypes.c_void_p,
                                              ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_float, ctypes.c_int,
                                              ctypes.c_void_p]),

@@ -292,7 +292,7 @@ class _PlusAddFusedFn(torch.autograd.Function):
 def hrfp_plus_add_upsampled(dec1: torch.Tensor, ocout_dec: "HrfpDec") -> torch.Tensor:
     """deepv3.py:356-357 in one kernel: Upsample(dec1) (bilinear, align_corners=True, mynn.py:114-119) + OCout_dec, from
     the low-resolution `dec1` and the `HrfpDec` handle of `hrfp_chain(lazy_dec=True)`.  Neither the upsampled dec1 nor
-    OCout_dec is materialised.  Autograd: bilinear-transpose of the gradient to dec1 (ATen), identity to the chain."""
+    OCout_dec is materialised.  Autograd: bilinear-transpose of the gradient to dec1 (gather kernel), identity to the chain."""
     return _PlusAddUpFn.apply(dec1, ocout_dec.token, ocout_dec)
 
 
@@ -319,7 +319,8 @@ class _PlusAddUpFn(torch.autograd.Function):
         ctx.mail["g"] = g if ctx.mail["g"] is None else ctx.mail["g"] + g
         g_lo = None
         if ctx.needs_input_grad[0]:
-            g_lo = torch.ops.aten.upsample_bilinear2d_backward(g.contiguous(), list(g.shape[2:]), list(ctx.lo_shape), True, None, None)
+            from .bilinear import bilinear_up_backward          # gather form of ATen's scatter (csrc/bilinear.cu)
+            g_lo = bilinear_up_backward(g, ctx.lo_shape[2:])
         return g_lo, torch.zeros(1, dtype=torch.float32, device=g.device), None
 
 

@@ -23,6 +23,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
+from . import bilinear as _bilinear
 from . import hrfp as _hrfp
 from . import instnorm as _instnorm
 from . import npplus as _npplus
@@ -37,8 +38,8 @@ HRFP_BNS = ("OC1_bn", "OC2_bn", "OC3_bn", "OC4_bn", "OC1_decbn", "OC2_decbn", "O
 
 
 def upsample_bilinear(x, size):
-    """network/mynn.py:114-119."""
-    return F.interpolate(x, size=size, mode="bilinear", align_corners=True)
+    """network/mynn.py:114-119 (CUDA fp32: ATen forward, gather-form backward from csrc/bilinear.cu)."""
+    return _bilinear.upsample_bilinear(x, size)
 
 
 def init_hrfp_module(module: nn.Module):

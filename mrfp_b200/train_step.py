@@ -89,7 +89,9 @@ class GraphedTrainStep:
                 entry = self.graphs[combo] = (g, static_loss)
             if entry is not None:
                 entry[0].replay()
-                loss = entry[1]
+                # the graphs share one memory pool: a later replay of ANOTHER graph may use this graph's static output
+                # as scratch, so the loss leaves the pool right behind the replay (stream-ordered)
+                loss = entry[1].clone()
             else:
                 loss = self._fwd_bwd(fixed)
                 self.seen[combo] = self.seen.get(combo, 0) + 1
