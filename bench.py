@@ -24,13 +24,16 @@ sys.path.insert(0, ROOT)
 
 N_PER_GPU, H_IMG, W_IMG = 8, 768, 768
 XH = XW = 192
+N_CLASSES = 19
 HRFP_FLOP_FWD_PER_SAMPLE = 192.70e9        # needed-only MACs x2; dgrad the same
 METRIC = "mrfp_fwd_bwd_throughput"
 UNIT = "img/s"
 CONFIG = {
     "workload": "mrfp_fwd_bwd: NP+ on (8,64,192,192) and (8,256,192,192) + HRFP/HRFP+ chain 64ch@192^2 -> 256ch@384^2 -> "
-                "64ch@192^2 incl. the bilinear Upsample of the decoder feature in front of the HRFP+ add (deepv3.py:356-357, fused into the add kernel), "
-                "fwd + input-gradient bwd, per-GPU batch 8 (BASELINE config[1], 768x768 crop)",
+                "64ch@192^2, the HRFP+ tail THROUGH the classifier (deepv3.py:356-361: bilinear Upsample of the decoder feature, "
+                "HRFP+ add, final2 = Conv2d(256, 19, 1)), fwd + bwd (gradients to xp, the layer1 feature, dec1, W2, b2), per-GPU "
+                "batch 8 (BASELINE config[1], 768x768 crop).  Round 1 timed the step up to the HRFP+ sum; this step does "
+                "strictly more work (step_r1_definition carries the old one)",
     "per_gpu_batch": N_PER_GPU, "crop": [H_IMG, W_IMG], "hrfp_math": "bf16 tcgen05 (fp32 accumulate)", "np_plus_math": "fp32",
     "cache": "inputs larger than L2 (302 MB / 1.2 GB tensors per step); the per-kernel roofline launches flush L2 first",
 }
@@ -64,14 +67,18 @@ def cpu_reference_run(steps, warmup, batch=N_PER_GPU, budget_s=150.0):
     grads = (torch.randn(batch, 64, XH, XW, generator=g), torch.randn(batch, 256, H_IMG // 2, W_IMG // 2, generator=g),
              torch.randn(batch, 256, XH, XW, generator=g))
     d1 = torch.randn(batch, 256, XH, XW, generator=g)                   # decoder feature before the Upsample of deepv3.py:356
+    final2 = torch.nn.Conv2d(256, N_CLASSES, 1, bias=True)              # deepv3.py:219-220
+    grads = (grads[0], torch.randn(batch, N_CLASSES, H_IMG // 2, W_IMG // 2, generator=g), grads[2])
     t_w = time.perf_counter()
     for _ in range(max(1, warmup)):
-        T.mrfp_step(convs, bns, xp, f2, d1, draws, grads, H_IMG, W_IMG)
+        final2.zero_grad(set_to_none=True)
+        T.mrfp_step(convs, bns, xp, f2, d1, draws, grads, H_IMG, W_IMG, final2)
     per = (time.perf_counter() - t_w) / max(1, warmup)
     steps = max(3, min(steps, int(budget_s / max(per, 1e-3))))
     t0 = time.perf_counter()
     for _ in range(steps):
-        T.mrfp_step(convs, bns, xp, f2, d1, draws, grads, H_IMG, W_IMG)
+        final2.zero_grad(set_to_none=True)
+        T.mrfp_step(convs, bns, xp, f2, d1, draws, grads, H_IMG, W_IMG, final2)
     dt = time.perf_counter() - t0
     return dict(value=batch * steps / dt, unit=UNIT, cores=torch.get_num_threads(), kind="port", batch=batch, timed_passes=steps,
                 sample=f"the same step at the same per-GPU batch ({batch}) and shapes, {steps} timed + {max(1, warmup)} warm-up passes "
@@ -324,18 +331,32 @@ def run_ours(args):
     f2 = torch.relu(torch.randn(n, 256, XH, XW, device=dev) * sig + mu)
     draws = [(1 + 0.75 * torch.randn(n, c, 1, 1, device=dev), 0.75 * torch.randn(n, c, 1, 1, device=dev)) for c in (64, 256)]
     g_x = torch.randn(n, 64, XH, XW, device=dev)
-    g_dec = torch.randn(n, 256, H_IMG // 2, W_IMG // 2, device=dev)     # gradient wrt dec1 after the HRFP+ add
+    g_dec = torch.randn(n, N_CLASSES, H_IMG // 2, W_IMG // 2, device=dev)     # gradient wrt dec2 = final2(HRFP+ sum)
+    g_dec_r1 = torch.randn(n, 256, H_IMG // 2, W_IMG // 2, device=dev)        # (round-1 step: gradient wrt the HRFP+ sum)
     g_f2 = torch.randn(n, 256, XH, XW, device=dev)
     dec1_up = torch.randn(n, 256, XH, XW, device=dev)   # the decoder feature BEFORE the reference's bilinear Upsample (deepv3.py:356)
+    final2 = torch.nn.Conv2d(256, N_CLASSES, 1, bias=True).to(dev)            # deepv3.py:219-220
 
     def step(xp_, f2_, d1_, gx_, gdec_, gf2_):
         """Public API path: autograd Functions over the C ABI (the same calls MRFPPlus.forward makes)."""
         a = xp_.detach().requires_grad_(True)
         b = f2_.detach().requires_grad_(True)
+        d = d1_.detach().requires_grad_(True)
+        final2.weight.grad = None; final2.bias.grad = None
         # deepv3.py:316-330: x = OCout + NP+(xp); NP+ call 1 rides on the chain's passes (SURVEY.md 8f-1)
         x, dec = H.hrfp_chain(a, convs, bns, H_IMG, W_IMG, np_draws=draws[0], math_mode=H.MATH_BF16, lazy_dec=True)
         y2 = NP.np_plus_with_draws(b, *draws[1])                                       # :335
-        d1 = H.hrfp_plus_add_upsampled(d1_, dec)                                       # :356-357 (Upsample + add, one kernel)
+        d2 = H.hrfp_plus_final2(d, final2, dec)                                        # :356-361 (Upsample + add + classifier)
+        torch.autograd.backward([x, d2, y2], [gx_, gdec_, gf2_])
+        return x, d2, y2, a.grad, b.grad, d.grad
+
+    def step_r1(xp_, f2_, d1_, gx_, gdec_, gf2_):
+        """Round 1's step definition (up to the HRFP+ sum, no gradient to dec1), kept for comparison."""
+        a = xp_.detach().requires_grad_(True)
+        b = f2_.detach().requires_grad_(True)
+        x, dec = H.hrfp_chain(a, convs, bns, H_IMG, W_IMG, np_draws=draws[0], math_mode=H.MATH_BF16, lazy_dec=True)
+        y2 = NP.np_plus_with_draws(b, *draws[1])
+        d1 = H.hrfp_plus_add_upsampled(d1_, dec)
         torch.autograd.backward([x, d1, y2], [gx_, gdec_, gf2_])
         return x, d1, y2, a.grad, b.grad
 
@@ -365,6 +386,20 @@ def run_ours(args):
         sampler.join(timeout=2)
     total_ms = float(ms.item())
     value = world * n * args.steps / (total_ms * 1e-3)
+    # round 1's step definition, same timing rules
+    for _ in range(3):
+        step_r1(xp, f2, dec1_up, g_x, g_dec_r1, g_f2)
+    sync_all()
+    e0.record()
+    for _ in range(args.steps):
+        step_r1(xp, f2, dec1_up, g_x, g_dec_r1, g_f2)
+    e1.record()
+    sync_all()
+    ms_r1 = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms_r1, op=dist.ReduceOp.MAX)
+    step_r1_ms = float(ms_r1.item()) / args.steps
+    del g_dec_r1
 
     # ---- e2e: same step through the same API with HOST (pinned) buffers, copies inside the timed region ----
     # Every step copies ITS inputs host->device and ITS five results device->host.  The copies run on their own
@@ -593,17 +628,18 @@ def run_ours(args):
         return a.elapsed_time(b) / iters
 
     xr = xp.detach().requires_grad_(True)
-    t_chain_f = t_api(lambda: H.hrfp_plus_add_upsampled(dec1_up, H.hrfp_chain(xr, convs, bns, H_IMG, W_IMG, math_mode=H.MATH_BF16, lazy_dec=True)[1]))
+    with torch.no_grad():
+        t_chain_f = t_api(lambda: H.hrfp_plus_final2(dec1_up, final2, H.hrfp_chain(xr, convs, bns, H_IMG, W_IMG, math_mode=H.MATH_BF16, lazy_dec=True)[1]))
 
     def chain_fb():
         xr.grad = None
         o, d = H.hrfp_chain(xr, convs, bns, H_IMG, W_IMG, math_mode=H.MATH_BF16, lazy_dec=True)
-        torch.autograd.backward([o, H.hrfp_plus_add_upsampled(dec1_up, d)], [g_x, g_dec])
+        torch.autograd.backward([o, H.hrfp_plus_final2(dec1_up, final2, d)], [g_x, g_dec])
     t_chain_fb = t_api(chain_fb)
     def chain_fb_tf32():
         xr.grad = None
         o, d = H.hrfp_chain(xr, convs, bns, H_IMG, W_IMG, math_mode=H.MATH_TF32, lazy_dec=True)
-        torch.autograd.backward([o, H.hrfp_plus_add_upsampled(dec1_up, d)], [g_x, g_dec])
+        torch.autograd.backward([o, final2(H.hrfp_plus_add_upsampled(dec1_up, d))], [g_x, g_dec])
     try:
         t_chain_fb_tf32 = t_api(chain_fb_tf32, 3)
     except Exception as e_:          # noqa: BLE001
@@ -614,16 +650,20 @@ def run_ours(args):
 
     base = cpu_reference_run(3, 1, budget_s=30.0)[0] if world == 1 else None
 
-    # kernels launched per step (ours; memsets excluded): NP+ call 2 fwd + bwd (call 1 is folded into the chain: +1 coefficient block each way); HRFP fwd 1 weight pack + 1 NCHW->NHWC +
-    # 8 conv (BN finalised by the last CTA) + 7 BN/ReLU/resample + 1 NHWC->NCHW epilogue (OCout + x); 1 fused HRFP+ add;
-    # HRFP bwd 2 NCHW->NHWC + 8 x (2 BN-bwd + conv) + 1 NHWC->NCHW
-    launches_per_step = 2 + (1 + 1 + 1 + 8 + 7 + 1) + 1 + (2 + 1 + 24 + 1)
+    # kernels launched per step (ours; memsets and the host's two library GEMMs W2 . dec1 / its backward excluded):
+    # NP+ call 2 fwd + bwd (call 1 is folded into the chain: +1 coefficient block each way); HRFP fwd 1 weight pack + 1
+    # NCHW->NHWC + 8 conv (BN finalised by the last CTA) + 7 BN/ReLU/resample + 1 NHWC->NCHW epilogue (OCout + x); tail
+    # through the classifier 1 fwd + 1 bwd + 1 bilinear-transpose gather; HRFP bwd 1 NCHW->NHWC + 8 x (2 BN-bwd + conv) +
+    # 1 NHWC->NCHW
+    launches_per_step = 2 + (1 + 1 + 1 + 8 + 7 + 1) + 3 + (1 + 1 + 24 + 1)
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16 (HRFP tensor-core operands, fp32 accumulate) / f32 (NP+)", "data": "synthetic", "config": CONFIG,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
                     "pipeline": "H2D / kernels / D2H on three streams, double-buffered; every step moves its own inputs and results"},
             "gpu_launches": launches_per_step * args.steps,
+            "step_r1_definition": {"ms_per_step": step_r1_ms, "value": world * n / (step_r1_ms * 1e-3), "unit": UNIT,
+                                   "what": "round 1's step (tail up to the HRFP+ sum, (N,256,384,384) fp32 output and gradient, no gradient to dec1)"},
             "roofline": roofline, "roofline_npplus": roof_np, "roofline_instnorm": roof_in, "hrfp_chain": hrfp, "train": train,
             "clocks": sampler.summary() if sampler else None}
     if base is not None:

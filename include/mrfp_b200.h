@@ -161,6 +161,25 @@ int mrfp_hrfp_plus_add(const mrfp_hrfp_plan_t* plan, const void* saved, const vo
 int mrfp_hrfp_plus_add_bilinear(const mrfp_hrfp_plan_t* plan, const void* saved, const void* lut, const float* dec1,
                                 int lh, int lw, float* out, void* stream);
 
+/* HRFP+ tail fused THROUGH the classifier (bf16 plans, widths[3] == 256, K <= 24 classes) — replaces
+ * deepv3.py:356-361: dec1 = Upsample(dec1); dec1 = OCout_dec + dec1; dec2 = final2(dec1), final2 = Conv2d(256, K, 1, bias).
+ * A 1x1 convolution commutes with the bilinear interpolation:  dec2 = b2 + Upsample(W2 . dec1) + W2 . OCout_dec.
+ *   t_lo (N, K, lh, lw) fp32 = W2 . dec1 at LOW resolution (a plain GEMM, computed by the caller; autograd of that GEMM
+ *        yields the gradient to dec1 and the low-resolution half of the gradient to W2);
+ *   w2 (K, 256), b2 (K) fp32;  out (N, K, h/2, w/2) fp32 NCHW.
+ * Neither OCout_dec, the up-sampled dec1 nor their sum (N, 256, h/2, w/2) is materialised.
+ * Backward, given g = dL/d out: g_dec_nhwc (N, h/2, w/2, 256) bf16 = W2^T g (feed it to mrfp_hrfp_bwd_nhwc),
+ * g_w2 (K, 256) = sum_pixels g . OCout_dec^T (the high-resolution half of the weight gradient), g_b2 (K) = sum g; the
+ * gradient to t_lo is mrfp_bilinear_up_bwd_f32(g).  MRFP_ERR_UNSUPPORTED: use mrfp_hrfp_plus_add_bilinear + a conv. */
+int mrfp_hrfp_tail_final2_fwd(const mrfp_hrfp_plan_t* plan, const void* saved, const void* lut, const float* t_lo,
+                              int lh, int lw, const float* w2, const float* b2, int K, float* out, void* stream);
+int mrfp_hrfp_tail_final2_bwd(const mrfp_hrfp_plan_t* plan, const void* saved, const void* lut, const float* g,
+                              const float* w2, int K, void* g_dec_nhwc, float* g_w2, float* g_b2, void* stream);
+/* mrfp_hrfp_bwd / mrfp_hrfp_bwd_np with the gradient of OCout_dec in the chain's own layout (np_* all NULL: no folded NP+). */
+int mrfp_hrfp_bwd_nhwc(const mrfp_hrfp_plan_t* plan, const float* g_ocout, const void* g_dec_nhwc,
+                       const float* const* gamma, const float* np_alpha, const float* np_eps, const float* np_mean,
+                       void* np_ws, const void* lut, const void* saved, float* g_xp, void* ws, void* stream);
+
 /* Backward of the reference's Upsample (network/mynn.py:114-119, bilinear, align_corners=True) at the up-sampling sites of
  * the tail (deepv3.py:356, :362), as a gather instead of ATen's atomicAdd scatter:
  *   gl (planes, LH, LW) = adjoint of the up-sampling applied to g (planes, OH, OW), OH >= LH, OW >= LW.

@@ -1263,7 +1263,9 @@ int hrfp_forward(const mrfp_hrfp_plan* P, const float* xp, const float* const* W
 template <typename T>
 int hrfp_backward(const mrfp_hrfp_plan* P, const float* g_ocout, const float* g_ocout_dec, const float* const* gamma,
                   const int* lut, const char* saved, float* g_xp, char* ws, cudaStream_t s, const DeviceInfo& di,
-                  const NpStem* np) {
+                  const NpStem* np, const void* g_dec_nhwc) {
+  // g_dec_nhwc: the gradient of OCout_dec already in the chain's layout (N, h/2, w/2, C) and element type — produced by
+  // the fused classifier tail (tail_final2.cu) — instead of the fp32 NCHW tensor g_ocout_dec
   double* acc = reinterpret_cast<double*>(ws + P->acc_bwd_off);
   if (np && !g_ocout) np = nullptr;                      // no gradient through `x`: NP+ contributes nothing
   if (np) MRFP_CUDA_TRY(cudaMemsetAsync(np->psum, 0, (size_t)P->N * P->cin * sizeof(double), s));
@@ -1280,6 +1282,11 @@ int hrfp_backward(const mrfp_hrfp_plan* P, const float* g_ocout, const float* g_
     const HrfpStage& st = P->st[k];
     const float* gin = (k == kHrfpStages - 1) ? g_ocout : (k == 3 ? g_ocout_dec : nullptr);
     if (k == 3 && dec_joined) gin = nullptr;               // already added by the dgrad of stage 4
+    if (k == 3 && g_dec_nhwc && !dec_joined) {             // encoder-only backward: the tail's gradient IS dA_3
+      const size_t bytes = (size_t)P->N * st.oh * st.ow * st.cout * sizeof(T);
+      MRFP_CUDA_TRY(cudaMemcpyAsync(g0, g_dec_nhwc, bytes, cudaMemcpyDeviceToDevice, s));
+      dA = g0; other = g1; at_end = true;
+    }
     if (gin) {
       const int HW = st.oh * st.ow;
       T* dst = dA ? dA : g0;
@@ -1307,7 +1314,10 @@ int hrfp_backward(const mrfp_hrfp_plan* P, const float* g_ocout, const float* g_
       // buffer apply(4) has just finished reading and let the conv epilogue add it in fp32 (one rounding, and the
       // read-modify-write pass over dA_3 disappears)
       const T* add_src = nullptr;
-      if (k == 4 && g_ocout_dec) {
+      if (k == 4 && g_dec_nhwc) {
+        add_src = static_cast<const T*>(g_dec_nhwc);
+        dec_joined = true;
+      } else if (k == 4 && g_ocout_dec) {
         const HrfpStage& pv = P->st[3];
         run_nchw_to_nhwc<T>(g_ocout_dec, dA, P->N, pv.cout, pv.cout, pv.oh * pv.ow, false, (double*)nullptr, true, s);
         add_src = dA;
@@ -1488,9 +1498,10 @@ static int hrfp_fwd_entry(const mrfp_hrfp_plan_t* P, const float* xp, const floa
 
 static int hrfp_bwd_entry(const mrfp_hrfp_plan_t* P, const float* g_ocout, const float* g_ocout_dec,
                           const float* const* gamma, const void* lut, const void* saved, float* g_xp, void* ws,
-                          void* stream, const NpStem* np) {
+                          void* stream, const NpStem* np, const void* g_dec_nhwc = nullptr) {
   if (!P || P->magic != kPlanMagic) return MRFP_ERR_BAD_PLAN;
   if (!gamma || !lut || !saved || !g_xp || !ws) return MRFP_ERR_NULL_POINTER;
+  if (g_dec_nhwc && (g_ocout_dec || P->mode == MRFP_MATH_FP32 || ((uintptr_t)g_dec_nhwc & 15))) return MRFP_ERR_UNSUPPORTED;
   if (((uintptr_t)saved | (uintptr_t)ws | (uintptr_t)lut) & 255) return MRFP_ERR_WORKSPACE;
   DeviceInfo di;
   int rc = get_device_info(&di);
@@ -1499,9 +1510,9 @@ static int hrfp_bwd_entry(const mrfp_hrfp_plan_t* P, const float* g_ocout, const
   std::lock_guard<std::mutex> lock(P->mu);
   if (P->mode == MRFP_MATH_BF16)
     return hrfp_backward<__nv_bfloat16>(P, g_ocout, g_ocout_dec, gamma, (const int*)lut, (const char*)saved, g_xp,
-                                        (char*)ws, s, di, np);
+                                        (char*)ws, s, di, np, g_dec_nhwc);
   return hrfp_backward<float>(P, g_ocout, g_ocout_dec, gamma, (const int*)lut, (const char*)saved, g_xp, (char*)ws, s, di,
-                              np);
+                              np, g_dec_nhwc);
 }
 
 extern "C" int mrfp_hrfp_fwd(const mrfp_hrfp_plan_t* P, const float* xp, const float* const* W,
@@ -1554,6 +1565,22 @@ extern "C" int mrfp_hrfp_bwd_np(const mrfp_hrfp_plan_t* P, const float* g_ocout,
   if (!np_stem_setup(P, np_alpha, np_eps, const_cast<float*>(np_mean), nullptr, np_ws, &np))
     return (P && P->magic == kPlanMagic) ? MRFP_ERR_NULL_POINTER : MRFP_ERR_BAD_PLAN;
   return hrfp_bwd_entry(P, g_ocout, g_ocout_dec, gamma, lut, saved, g_xp, ws, stream, &np);
+}
+
+// The same two backward entry points with the gradient of OCout_dec given in the chain's own layout and element type
+// (N, h/2, w/2, C) — what mrfp_hrfp_tail_final2_bwd leaves — instead of an fp32 NCHW tensor.  np_* may all be NULL.
+extern "C" int mrfp_hrfp_bwd_nhwc(const mrfp_hrfp_plan_t* P, const float* g_ocout, const void* g_dec_nhwc,
+                                  const float* const* gamma, const float* np_alpha, const float* np_eps,
+                                  const float* np_mean, void* np_ws, const void* lut, const void* saved, float* g_xp,
+                                  void* ws, void* stream) {
+  if (!g_dec_nhwc) return MRFP_ERR_NULL_POINTER;
+  if (np_alpha || np_eps || np_mean || np_ws) {
+    NpStem np;
+    if (!np_stem_setup(P, np_alpha, np_eps, const_cast<float*>(np_mean), nullptr, np_ws, &np))
+      return (P && P->magic == kPlanMagic) ? MRFP_ERR_NULL_POINTER : MRFP_ERR_BAD_PLAN;
+    return hrfp_bwd_entry(P, g_ocout, nullptr, gamma, lut, saved, g_xp, ws, stream, &np, g_dec_nhwc);
+  }
+  return hrfp_bwd_entry(P, g_ocout, nullptr, gamma, lut, saved, g_xp, ws, stream, nullptr, g_dec_nhwc);
 }
 
 template <typename T>

@@ -190,9 +190,13 @@ class _HrfpFn(torch.autograd.Function):
         gi = iter(grads)
         g_out = next(gi) if ctx.want_out else None
         g_dec = next(gi) if ctx.want_dec else None
-        if ctx.mail is not None:             # the real gradient was parked by _PlusAddFusedFn.backward
+        g_dec_nhwc = None
+        if ctx.mail is not None:             # the real gradient was parked by the tail's backward
             g_dec = ctx.mail["g"]
             ctx.mail["g"] = None
+            g_dec_nhwc = ctx.mail.pop("g_nhwc", None)      # fused classifier tail: already NHWC in the chain's element type
+            if g_dec_nhwc is not None and g_dec is not None:
+                raise _lib.MrfpError("OCout_dec was consumed both by the fused classifier tail and by a plain HRFP+ add")
         dev = plan.device
         g_out_c = g_out.contiguous() if g_out is not None else None
         g_dec_c = g_dec.contiguous() if g_dec is not None else None
@@ -202,7 +206,15 @@ class _HrfpFn(torch.autograd.Function):
             ga = _ptr_array(ctx.gammas)
             ws = plan.workspace()
             with torch.cuda.device(dev):
-                if ctx.np is not None:      # gradient through NP+(xp) joins in the chain's last pass
+                if g_dec_nhwc is not None:
+                    a_, e_, m_ = ctx.np if ctx.np is not None else (None, None, None)
+                    w_ = _lib.scratch(dev, lib.mrfp_hrfp_np_ws_bytes(plan.n, plan.cin), "hrfp_np") if ctx.np is not None else None
+                    rc = lib.mrfp_hrfp_bwd_nhwc(plan.handle, None if g_out_c is None else g_out_c.data_ptr(), g_dec_nhwc.data_ptr(),
+                                                ga, None if a_ is None else a_.data_ptr(), None if e_ is None else e_.data_ptr(),
+                                                None if m_ is None else m_.data_ptr(), None if w_ is None else w_.data_ptr(),
+                                                plan.lut.data_ptr(), ctx.saved_buf.data_ptr(), g_xp.data_ptr(), ws.data_ptr(),
+                                                _stream_ptr(dev))
+                elif ctx.np is not None:      # gradient through NP+(xp) joins in the chain's last pass
                     a_, e_, m_ = ctx.np
                     w_ = _lib.scratch(dev, lib.mrfp_hrfp_np_ws_bytes(plan.n, plan.cin), "hrfp_np")
                     rc = lib.mrfp_hrfp_bwd_np(plan.handle, None if g_out_c is None else g_out_c.data_ptr(),
@@ -338,3 +350,70 @@ class _AddFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g):
         return g, g
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# HRFP+ tail fused through the classifier: deepv3.py:356-361 in one kernel per direction
+# ----------------------------------------------------------------------------------------------------------------------
+def tail_final2_supported(dec1: torch.Tensor, conv: torch.nn.Conv2d, ocout_dec) -> bool:
+    """The fused tail exists for the bf16 path, 256 decoder channels, <= 24 classes, a 1x1 classifier and an Upsample by
+    >= 2 whose source rows are 16-byte aligned; anything else takes hrfp_plus_add_upsampled + the module's own conv."""
+    if not isinstance(ocout_dec, HrfpDec) or ocout_dec.plan.math_mode != MATH_BF16:
+        return False
+    n, c, oh, ow = ocout_dec.plan.dec_shape
+    return (c == 256 and conv.kernel_size == (1, 1) and conv.stride == (1, 1) and conv.padding == (0, 0) and conv.groups == 1
+            and conv.in_channels == 256 and conv.out_channels <= 24 and dec1.is_cuda and dec1.dtype == torch.float32
+            and dec1.shape[3] % 4 == 0 and ow > 1 and 2 * (dec1.shape[3] - 1) <= ow - 1 and dec1.shape[2] <= oh)
+
+
+class _TailFinal2Fn(torch.autograd.Function):
+    """(t_lo, W2, b2, token) -> dec2 = b2 + Upsample(t_lo) + W2 . OCout_dec, with t_lo = W2 . dec1 at low resolution."""
+
+    @staticmethod
+    def forward(ctx, t_lo, weight, bias, token, handle):
+        lib = _lib.load()
+        plan = handle.plan
+        n, c, oh, ow = plan.dec_shape
+        k = weight.shape[0]
+        t = t_lo.contiguous()
+        w2 = weight.detach().reshape(k, c).contiguous()
+        out = torch.empty((n, k, oh, ow), dtype=torch.float32, device=t.device)
+        with torch.cuda.device(t.device):
+            rc = lib.mrfp_hrfp_tail_final2_fwd(plan.handle, handle.saved.data_ptr(), plan.lut.data_ptr(), t.data_ptr(), t.shape[2],
+                                               t.shape[3], w2.data_ptr(), None if bias is None else bias.data_ptr(), k,
+                                               out.data_ptr(), _stream_ptr(t.device))
+        _lib.check(rc, "mrfp_hrfp_tail_final2_fwd")
+        ctx.handle, ctx.w2, ctx.lo, ctx.has_bias, ctx.wshape = handle, w2, (t.shape[2], t.shape[3]), bias is not None, weight.shape
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        from .bilinear import bilinear_up_backward
+        lib = _lib.load()
+        handle, plan = ctx.handle, ctx.handle.plan
+        n, c, oh, ow = plan.dec_shape
+        k = ctx.w2.shape[0]
+        gc = g.contiguous()
+        g_t = bilinear_up_backward(gc, ctx.lo) if ctx.needs_input_grad[0] else None
+        g_nhwc = torch.empty((n, oh, ow, c), dtype=torch.bfloat16, device=g.device)
+        g_w2 = torch.empty((k, c), dtype=torch.float32, device=g.device)
+        g_b2 = torch.empty((k,), dtype=torch.float32, device=g.device)
+        with torch.cuda.device(g.device):
+            rc = lib.mrfp_hrfp_tail_final2_bwd(plan.handle, handle.saved.data_ptr(), plan.lut.data_ptr(), gc.data_ptr(),
+                                               ctx.w2.data_ptr(), k, g_nhwc.data_ptr(), g_w2.data_ptr(), g_b2.data_ptr(),
+                                               _stream_ptr(g.device))
+        _lib.check(rc, "mrfp_hrfp_tail_final2_bwd")
+        if handle.mail.get("g_nhwc") is not None or handle.mail.get("g") is not None:
+            raise _lib.MrfpError("OCout_dec handle consumed twice")
+        handle.mail["g_nhwc"] = g_nhwc
+        return (g_t, g_w2.reshape(ctx.wshape) if ctx.needs_input_grad[1] else None,
+                g_b2 if (ctx.has_bias and ctx.needs_input_grad[2]) else None,
+                torch.zeros(1, dtype=torch.float32, device=g.device), None)
+
+
+def hrfp_plus_final2(dec1: torch.Tensor, conv: torch.nn.Conv2d, ocout_dec: "HrfpDec") -> torch.Tensor:
+    """deepv3.py:356-361: final2(Upsample(dec1) + OCout_dec) for final2 = Conv2d(256, K, 1) without materialising anything
+    at (N, 256, h/2, w/2).  The low-resolution product W2 . dec1 is a plain library GEMM (autograd gives the gradients to
+    dec1 and the low-resolution half of the weight gradient); everything at high resolution is csrc/tail_final2.cu."""
+    t_lo = torch.nn.functional.conv2d(dec1, conv.weight)
+    return _TailFinal2Fn.apply(t_lo, conv.weight, conv.bias, ocout_dec.token, ocout_dec)

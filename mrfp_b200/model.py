@@ -75,6 +75,8 @@ class MRFPMixin:
     fuse_layer1_np = os.environ.get("MRFP_FUSE_LAYER1_NP", "1") != "0"
     # HRFP+ tail: bilinear Upsample of dec1 evaluated inside the add kernel (no (N,256,h/2,w/2) intermediate); MRFP_FUSE_PLUS_TAIL=0: off
     fuse_plus_tail = os.environ.get("MRFP_FUSE_PLUS_TAIL", "1") != "0"
+    # ... and through the classifier: final2(Upsample(dec1) + OCout_dec) in one kernel per direction; MRFP_FUSE_FINAL2=0: off
+    fuse_final2 = os.environ.get("MRFP_FUSE_FINAL2", "1") != "0"
 
     def _build_hrfp(self, in_ch=64, widths=(64, 64, 128, 256)):
         chans = [in_ch, widths[0], widths[1], widths[2], widths[3], widths[2], widths[1], widths[0], in_ch]
@@ -293,6 +295,11 @@ class MRFPPlus(nn.Module, MRFPMixin):
         dec0_fine = self.bot_fine(low_level)
         dec0 = torch.cat([dec0_fine, upsample_bilinear(dec0_up, low_level.shape[2:])], 1)
         dec1 = self.final1(dec0)
+        if (training and p3 < 0.5 and self.fuse_plus_tail and self.fuse_final2
+                and _hrfp.tail_final2_supported(dec1, self.final2[0], ocout_dec)):
+            # deepv3.py:355-361 in one kernel: Upsample + HRFP+ add + the 1x1 classifier (nothing at (N,256,h/2,w/2))
+            main_out = upsample_bilinear(_hrfp.hrfp_plus_final2(dec1, self.final2[0], ocout_dec), (h, w))
+            return self.criterion(main_out, gts)
         if training and p3 < 0.5:                                           # deepv3.py:355-357
             if self.fuse_plus_tail and isinstance(ocout_dec, _hrfp.HrfpDec) and dec1.is_cuda:
                 dec1 = _hrfp.hrfp_plus_add_upsampled(dec1, ocout_dec)       # Upsample + add in one kernel

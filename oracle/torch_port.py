@@ -103,19 +103,23 @@ def hrfp_chain(convs, bns, xp, h, w, exact_adjoint=False):
     return o, dec
 
 
-def mrfp_step(convs, bns, xp, feat2, dec1, draws, grads, h, w):
-    """One forward+backward pass of the whole MRFP path: both NP+ calls, the HRFP chain, the HRFP and HRFP+ adds.
+def mrfp_step(convs, bns, xp, feat2, dec1, draws, grads, h, w, final2=None):
+    """One forward+backward pass of the whole MRFP path: both NP+ calls, the HRFP chain, the HRFP and HRFP+ adds and —
+    with `final2` (deepv3.py:219-220, :359) — the 1x1 classifier that consumes the HRFP+ sum.
     `dec1` is the decoder feature before the reference's Upsample (deepv3.py:356, mynn.py:114-119); a tensor that
-    already has the (h/2, w/2) size passes through the interpolation unchanged."""
+    already has the (h/2, w/2) size passes through the interpolation unchanged.  grads = (g_x, g_tail, g_feat2) with
+    g_tail the gradient of the last tensor of the tail (dec2 with final2, the HRFP+ sum without)."""
     (a1, e1), (a2, e2) = draws
     g_x, g_d1, g_f2 = grads
     xp = xp.detach().requires_grad_(True)
     feat2 = feat2.detach().requires_grad_(True)
+    dec1 = dec1.detach().requires_grad_(True)
     x = np_plus(xp, a1, e1)                                              # :318
     ocout, dec = hrfp_chain(convs, bns, xp, h, w)                        # :320-327
     x = ocout + x                                                        # :330
     y2 = np_plus(feat2, a2, e2)                                          # :335
     dec1_up = F.interpolate(dec1, size=(int(h / 2), int(w / 2)), mode="bilinear", align_corners=True)   # :356
     d1 = torch.add(dec, dec1_up)                                         # :357
-    torch.autograd.backward([x, d1, y2], [g_x, g_d1, g_f2])
-    return x.detach(), d1.detach(), y2.detach(), xp.grad, feat2.grad
+    tail = final2(d1) if final2 is not None else d1                      # :359
+    torch.autograd.backward([x, tail, y2], [g_x, g_d1, g_f2])
+    return x.detach(), tail.detach(), y2.detach(), xp.grad, feat2.grad, dec1.grad

@@ -22,13 +22,16 @@ def test_gather_backward_equals_aten_backward(case):
     x64 = torch.zeros(*shape, device="cuda", dtype=torch.float64, requires_grad=True)
     (g64,) = torch.autograd.grad(F.interpolate(x64, size=size, mode="bilinear", align_corners=True), x64, g.double())
     scale = float(g64.abs().max())
-    assert float((got.double() - g64).abs().max()) <= 2e-6 * scale
-    assert float((ref.double() - g64).abs().max()) <= 2e-5 * scale        # ATen's own distance (atomics, fp32)
+    # ATen's fp32 forward takes its interpolation weights from float arithmetic (src = o * float((L-1)/(O-1))): they sit
+    # up to ~1e-7 * o from the exact ones.  The gather uses the same float weights, so it is the adjoint of the fp32
+    # forward and equals ATen's own backward up to summation order, and both sit ~1e-5 from the fp64 transpose.
+    assert float((got.double() - ref.double()).abs().max()) <= 2e-6 * scale
+    assert float((got.double() - g64).abs().max()) <= 1e-4 * scale
     # through autograd: module-level Upsample with the gather backward
     y = upsample_bilinear(x, size)
     assert torch.equal(y, F.interpolate(x.detach(), size=size, mode="bilinear", align_corners=True))
     y.backward(g)
-    assert float((x.grad.double() - g64).abs().max()) <= 2e-6 * scale
+    assert float((x.grad.double() - ref.double()).abs().max()) <= 2e-6 * scale
 
 
 def test_bad_arguments():

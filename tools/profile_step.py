@@ -1,4 +1,7 @@
-"""Per-kernel GPU time of one bench step (torch profiler / CUPTI), plus event-timed step time."""
+"""Per-kernel GPU time of one bench step (torch profiler / CUPTI), plus event-timed step time.
+
+    python tools/profile_step.py [-v]        MRFP_PROFILE_N: per-GPU batch (default 8)
+The step is bench.py's: chain fwd with NP+ call 1 folded in, NP+ call 2, tail through the classifier, backward of all."""
 import os, sys, collections
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -13,17 +16,19 @@ convs = [torch.nn.Conv2d(chans[k], chans[k + 1], 3, padding=dils[k], dilation=di
 bns = [torch.nn.BatchNorm2d(chans[k + 1]).to(dev).requires_grad_(False) for k in range(8)]
 for c, b in zip(convs, bns):
     init_hrfp_module(c); init_hrfp_module(b)
+final2 = torch.nn.Conv2d(256, 19, 1).to(dev)
 xp = torch.relu(torch.randn(n, 64, 192, 192, device=dev))
 f2 = torch.relu(torch.randn(n, 256, 192, 192, device=dev))
 d1 = torch.randn(n, 256, 192, 192, device=dev)
 draws = [(1 + 0.75 * torch.randn(n, c, 1, 1, device=dev), 0.75 * torch.randn(n, c, 1, 1, device=dev)) for c in (64, 256)]
-g_x = torch.randn(n, 64, 192, 192, device=dev); g_d = torch.randn(n, 256, 384, 384, device=dev); g_f = torch.randn(n, 256, 192, 192, device=dev)
+g_x = torch.randn(n, 64, 192, 192, device=dev); g_d = torch.randn(n, 19, 384, 384, device=dev); g_f = torch.randn(n, 256, 192, 192, device=dev)
 
 def step():
-    a = xp.detach().requires_grad_(True); b = f2.detach().requires_grad_(True)
+    a = xp.detach().requires_grad_(True); b = f2.detach().requires_grad_(True); d = d1.detach().requires_grad_(True)
+    final2.weight.grad = None; final2.bias.grad = None
     x, dec = H.hrfp_chain(a, convs, bns, 768, 768, np_draws=draws[0], math_mode=H.MATH_BF16, lazy_dec=True)
     y2 = NP.np_plus_with_draws(b, *draws[1])
-    o = H.hrfp_plus_add_upsampled(d1, dec)
+    o = H.hrfp_plus_final2(d, final2, dec)
     torch.autograd.backward([x, o, y2], [g_x, g_d, g_f])
 
 for _ in range(3):
