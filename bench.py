@@ -273,7 +273,7 @@ def train_bench(world, rank, dev, steps=30, warmup=10, global_batch=16, referenc
     host_ms = (time.perf_counter() - t0) * 1e3 / steps
     torch.cuda.synchronize()
     ms = D.max_over_ranks(e0.elapsed_time(e1), dev)
-    out = {"metric": "deeplabv3plus_%s_mrfp_plus_train_throughput" % {"resnet-50": "r50", "resnet-101": "r101"}[trunk],
+    out = {"metric": "deeplabv3plus_%s_mrfp_plus_train_throughput" % {"resnet-50": "r50", "resnet-101": "r101", "mobilenetv2": "mobilenetv2", "shufflenetv2": "shufflenetv2"}[trunk],
            "mrfp_ops": "reference eager ATen/cuDNN" if reference_ops else "libmrfp_b200", "value": global_batch * steps / (ms * 1e-3), "unit": "img/s",
            "global_batch": global_batch, "per_gpu_batch": nb, "steps": steps, "warmup": warmup, "ms_per_step": ms / steps,
            "host_enqueue_ms_per_step": host_ms, "launch_mode": mode,
@@ -479,6 +479,11 @@ def run_ours(args):
                 # BASELINE config[3] per-GPU shard: ResNet-101 host, global batch 32 at 8 GPUs = 4 per GPU
                 r101 = train_bench(world, rank, dev, steps=30, warmup=10, global_batch=4 * world, trunk="resnet-101")
                 train["resnet101_config3_shard"] = {k: r101[k] for k in ("metric",) + keys}
+            if os.environ.get("MRFP_BENCH_TRAIN_MOBILE", "1") != "0":
+                # BASELINE config[4]: MRFP+ on the narrow-stem trunks (16 ch @ stride 2 / 24 ch @ stride 4), global batch 16
+                for tr in ("mobilenetv2", "shufflenetv2"):
+                    mb = train_bench(world, rank, dev, steps=20, warmup=5, trunk=tr)
+                    train[tr + "_config4"] = {k: mb[k] for k in ("metric",) + keys}
         except Exception as e:          # noqa: BLE001  (e.g. out of memory on a smaller GPU): report, do not hide
             import traceback
             train = dict(train or {}, error=repr(e)[:400], traceback=traceback.format_exc()[-800:])

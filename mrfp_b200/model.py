@@ -203,21 +203,60 @@ class ASPP(nn.Module):
         return torch.cat([img] + [f(x) for f in self.features], 1)
 
 
+class _ShuffleLayer0(nn.Module):
+    """network/deepv3.py:121-151 with iw == 0: conv1 (conv-bn-relu) + maxpool under the reference's attribute name."""
+
+    def __init__(self, conv1, maxpool):
+        super().__init__()
+        self.layer = nn.Sequential(conv1, maxpool)
+
+    def forward(self, x):
+        return self.layer(x)
+
+
+class _ShuffleLayer4(nn.Module):
+    """network/deepv3.py:153-179 with iw == 0: conv5 (conv-bn-relu)."""
+
+    def __init__(self, conv5):
+        super().__init__()
+        self.layer = conv5
+
+    def forward(self, x):
+        return self.layer(x)
+
+
+MOBILE_TRUNKS = ("mobilenetv2", "shufflenetv2")
+
+
 class MRFPPlus(nn.Module, MRFPMixin):
     """DeepLabV3+ / ResNet-50 (IN at the stem and at the end of layer1, layer2: wt_layer=[0,0,4,4,4,0,0]) with
-    MRFP+ applied while training.  trunk="resnet-101" (BASELINE config[3]) is this repo's extension: same insertion
-    points on the reference's deep-stem ResNet-101, HRFP on its 128 stem channels."""
+    MRFP+ applied while training.
+
+    Extensions of this repo (the reference's MRFPPlus raises for any trunk but resnet-50,
+    deepv3.py:177-178) — the same three insertion points on the other trunks of the reference's DeepV3Plus:
+      trunk="resnet-101" (BASELINE config[3]): deep-stem ResNet-101, HRFP on its 128 stem channels;
+      trunk="mobilenetv2" / "shufflenetv2" (BASELINE config[4]; network/deepv3.py:121-193, :259-283, forward :478-556,
+      wt_layer all zero as DeepV3Plus forces): hooks after layer0 (16 ch @ stride 2 / 24 ch @ stride 4), after layer1
+      (32 / 116 ch @ stride 8) and after final1.  The HRFP chain is sized RELATIVE TO xp (x1.205, x1.2, x1.2, 2x, 2x,
+      x0.838, x0.798, 1x of the xp size — what deepv3.py:320-327 amounts to on a stride-4 stem), so a stride-2 stem
+      peaks at the image size; its narrow stem is zero-padded to the kernels' channel granule inside the plan."""
 
     def __init__(self, num_classes, trunk="resnet-50", criterion=None, criterion_aux=None, variant="D16",
                  wt_layer=(0, 0, 4, 4, 4, 0, 0), use_wtloss=False, math_mode=_hrfp.MATH_BF16, strict_buffers=False):
         super().__init__()
-        if trunk not in ("resnet-50", "resnet-101"):
+        if trunk not in ("resnet-50", "resnet-101") + MOBILE_TRUNKS:
             raise ValueError("Not a valid network arch")                    # deepv3.py:177-178
-        if tuple(wt_layer) != (0, 0, 4, 4, 4, 0, 0):
+        if trunk in MOBILE_TRUNKS:
+            wt_layer = (0, 0, 0, 0, 0, 0, 0)                                # network/deepv3.py:120
+        elif tuple(wt_layer) != (0, 0, 4, 4, 4, 0, 0):
             raise ValueError("only the reference's wt_layer=[0,0,4,4,4,0,0] host is provided")
         self.criterion, self.criterion_aux = criterion, criterion_aux
         self.variant, self.wt_layer, self.use_wtloss, self.trunk = variant, list(wt_layer), use_wtloss, trunk
         self.math_mode, self.strict_buffers = math_mode, strict_buffers
+        self.hrfp_scale = 1                  # image size the chain is planned for = hrfp_scale x the real one (4 / stem stride)
+        if trunk in MOBILE_TRUNKS:
+            self._build_mobile(num_classes, trunk, variant)
+            return
 
         if trunk == "resnet-50":                                            # Resnet.py:519-560 (7x7 stem), [3,4,6,3]
             stem_ch, blocks = 64, (3, 4, 6, 3)
@@ -260,8 +299,46 @@ class MRFPPlus(nn.Module, MRFPMixin):
         self.whitening = False
         self.three_input_layer = False
 
+    def _build_mobile(self, num_classes, trunk, variant):
+        """network/deepv3.py:121-193 (ShuffleNetV2 x1.0) and :259-283 (MobileNetV2): torchvision's modules — the
+        reference's network/Mobilenet.py and Shufflenet.py are torchvision's files plus the (here unused) iw options —
+        sliced and named as the reference slices them, so its DeepV3Plus state_dict (minus the `dsn` head) loads."""
+        import torchvision
+        if trunk == "mobilenetv2":
+            f = torchvision.models.mobilenet_v2(weights=None).features
+            self.layer0 = nn.Sequential(f[0], f[1])
+            self.layer1 = nn.Sequential(*[f[i] for i in range(2, 7)])
+            self.layer2 = nn.Sequential(*[f[i] for i in range(7, 11)])
+            self.layer3 = nn.Sequential(*[f[i] for i in range(11, 18)])
+            self.layer4 = nn.Sequential(f[18])
+            stem_ch, low_ch, final_ch, self.hrfp_scale = 16, 32, 1280, 2
+        else:
+            m = torchvision.models.shufflenet_v2_x1_0(weights=None)
+            self.layer0 = _ShuffleLayer0(m.conv1, m.maxpool)
+            self.layer1, self.layer2, self.layer3 = m.stage2, m.stage3, m.stage4
+            self.layer4 = _ShuffleLayer4(m.conv5)
+            stem_ch, low_ch, final_ch, self.hrfp_scale = 24, 116, 1024, 1
+        if variant == "D16":                                                # network/deepv3.py:184-187 / :276-279
+            for m_ in self.layer3.modules():
+                if isinstance(m_, nn.Conv2d) and m_.stride == (2, 2):
+                    m_.dilation, m_.padding, m_.stride = (2, 2), (2, 2), (1, 1)
+        self.output_stride = 16
+        self.aspp = ASPP(final_ch, 256)
+        self.bot_fine = nn.Sequential(nn.Conv2d(low_ch, 48, 1, bias=False), nn.BatchNorm2d(48), nn.ReLU(inplace=True))
+        self.bot_aspp = nn.Sequential(nn.Conv2d(1280, 256, 1, bias=False), nn.BatchNorm2d(256), nn.ReLU(inplace=True))
+        self.final1 = nn.Sequential(nn.Conv2d(304, 256, 3, padding=1, bias=False), nn.BatchNorm2d(256), nn.ReLU(inplace=True),
+                                    nn.Conv2d(256, 256, 3, padding=1, bias=False), nn.BatchNorm2d(256), nn.ReLU(inplace=True))
+        self.final2 = nn.Sequential(nn.Conv2d(256, num_classes, 1, bias=True))
+        self._build_hrfp(stem_ch)
+        init_head(self.aspp, self.bot_aspp, self.bot_fine, self.final1, self.final2)
+        self.eps = 1e-5
+        self.whitening = False
+        self.three_input_layer = False
+
     def _stem(self, x):
         """layer0 = conv(s) -> ... -> InstanceNorm2d(affine) -> ReLU -> maxpool (Resnet.py:591-599; ResNet3X3: :476-494)."""
+        if self.trunk in MOBILE_TRUNKS:
+            return self.layer0(x)
         if FUSE_INSTNORM and x.is_cuda and x.dtype == torch.float32:
             mods = list(self.layer0)
             for m in mods[:-3]:
@@ -275,15 +352,18 @@ class MRFPPlus(nn.Module, MRFPMixin):
         picks the graph to replay (mrfp_b200/train_step.py)."""
         p, p2, p3 = gates if gates is not None else (random.random(), random.random(), random.random())   # deepv3.py:281-283
         h, w = x.shape[2:]
+        he, we = h * self.hrfp_scale, w * self.hrfp_scale                   # the chain is sized relative to xp (stride-2 stems: 2x)
         if training and p < 0.5:
             self.reinit_hrfp()                                              # deepv3.py:290-306
         xp = self._stem(x)                                                  # deepv3.py:309-316
-        x, ocout_dec = self.mrfp_stem(xp, h, w, training, p, p2, p3)        # deepv3.py:317-330
+        x, ocout_dec = self.mrfp_stem(xp, he, we, training, p, p2, p3)      # deepv3.py:317-330
         last = self.layer1[-1]
-        last.emit_plane_sums = bool(training and p2 < 0.5 and self.fuse_layer1_np)
+        fused_sums = isinstance(last, Bottleneck)                           # ResNet hosts: layer1's last ReLU leaves the plane sums
+        if fused_sums:
+            last.emit_plane_sums = bool(training and p2 < 0.5 and self.fuse_layer1_np)
         x = self.layer1(x)                                                  # deepv3.py:332
         if training and p2 < 0.5:                                           # deepv3.py:334-335
-            if last.plane_sums is not None:      # statistics came with layer1's last ReLU: NP+ is one streaming pass
+            if fused_sums and last.plane_sums is not None:      # statistics came with layer1's last ReLU: NP+ is one streaming pass
                 alpha, eps = _npplus.draw_np_plus_factors(x)
                 x = _npplus.np_plus_presummed(x, last.plane_sums, alpha, eps)
                 last.plane_sums = None
@@ -304,7 +384,7 @@ class MRFPPlus(nn.Module, MRFPMixin):
             if self.fuse_plus_tail and isinstance(ocout_dec, _hrfp.HrfpDec) and dec1.is_cuda:
                 dec1 = _hrfp.hrfp_plus_add_upsampled(dec1, ocout_dec)       # Upsample + add in one kernel
             else:
-                dec1 = upsample_bilinear(dec1, (int(h / 2), int(w / 2)))
+                dec1 = upsample_bilinear(dec1, (int(he / 2), int(we / 2)))
                 dec1 = self._plus_add(dec1, ocout_dec)
         main_out = upsample_bilinear(self.final2(dec1), (h, w))
         if training:

@@ -233,3 +233,88 @@ def test_resnet101_training_step_runs_all_branches():
     for name in ("layer0.0.weight", "layer0.7.weight", "layer1.2.instance_norm_layer.weight", "final2.0.weight"):
         g = dict(m.named_parameters())[name].grad
         assert g is not None and torch.isfinite(g).all() and float(g.abs().sum()) > 0, name
+
+
+# ---- trunk="mobilenetv2" / "shufflenetv2" (BASELINE config[4]) ----
+@pytest.mark.refonly
+@pytest.mark.parametrize("trunk", ["mobilenetv2", "shufflenetv2"])
+def test_mobile_hosts_load_the_reference_state_dict_and_match_its_eval_forward_on_cpu(trunk):
+    """The host is state_dict-compatible with the reference's DeepV3Plus(trunk) (network/deepv3.py:103-556; its `dsn`
+    auxiliary head aside) and evaluates to the same logits — eval mode has no MRFP, so this pins the trunk wiring."""
+    import importlib
+    from oracle.ref_shim import load_reference
+    from mrfp_b200.model import MRFPPlus, HRFP_CONVS, HRFP_BNS
+    load_reference()
+    nd = importlib.import_module("network.deepv3")
+    ref = nd.DeepV3Plus(19, trunk=trunk, criterion=None, variant="D16", args=None).eval()
+    mine = MRFPPlus(19, trunk=trunk, criterion=_criterion()).eval()
+    fill_state_dict(ref, 9)
+    sd = {k: v for k, v in ref.state_dict().items() if not k.startswith("dsn.")}
+    mk = {k for k in mine.state_dict() if k.split(".")[0] not in HRFP_CONVS + HRFP_BNS}
+    assert mk == set(sd)
+    mine.load_state_dict(sd, strict=False)
+    x = torch.rand(2, 3, 96, 160) * 255
+    with torch.no_grad():
+        a, b = ref(x), mine(x, training=False)
+    assert torch.allclose(a, b, rtol=1e-5, atol=1e-5 * a.abs().max().item())
+    stem = {"mobilenetv2": 16, "shufflenetv2": 24}[trunk]
+    assert mine.OClayer1.in_channels == stem and mine.OCdeclayer4.out_channels == stem
+    assert mine.hrfp_scale == {"mobilenetv2": 2, "shufflenetv2": 1}[trunk]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("math_mode", [0, 2])
+@pytest.mark.parametrize("trunk", ["mobilenetv2", "shufflenetv2"])
+def test_mobile_hosts_training_step_matches_the_eager_reference_ops(trunk, math_mode):
+    """All three MRFP branches on a narrow-stem host (16 ch @ stride 2 / 24 ch @ stride 4; NP+ call 2 on 32 / 116 ch @
+    stride 8): the loss through the kernels equals the loss through the reference's own op sequence (deepv3.py:268-277,
+    :320-330, :356-357 written with torch operators, chain sized relative to xp) evaluated eagerly on the same model
+    with the same random draws; gradients reach the stem and every MRFP-adjacent layer."""
+    import torch.nn.functional as F
+    from oracle import torch_port as TP
+    from mrfp_b200.model import MRFPPlus
+    h, w = 96, 128
+    torch.manual_seed(0)
+    m = MRFPPlus(19, trunk=trunk, criterion=_criterion(), math_mode=math_mode).cuda().train()
+    x = torch.rand(2, 3, h, w, device="cuda") * 255
+    gts = torch.randint(0, 19, (2, h, w), device="cuda")
+    gates = (0.25, 0.25, 0.25)
+
+    def run(eager):
+        for mod in m.modules():                                  # same BN running buffers at the start of both runs
+            if isinstance(mod, torch.nn.BatchNorm2d):
+                mod.reset_running_stats()
+        m.zero_grad(set_to_none=True)
+        torch.manual_seed(5)
+        if not eager:
+            loss = m(x, gts, training=True, gates=gates)
+        else:                                                    # the reference's expressions on the host's modules
+            he, we = h * m.hrfp_scale, w * m.hrfp_scale
+            m.reinit_hrfp()
+            xp = m._stem(x)
+            a1, e1 = torch.empty_like(xp[:, :, :1, :1]).normal_(1.0, 0.75), torch.empty_like(xp[:, :, :1, :1]).normal_(0.0, 0.75)
+            convs, bns = m.hrfp_modules()
+            oc, dec = TP.hrfp_chain(convs, bns, xp, he, we, exact_adjoint=True)
+            f = m.layer1(oc + TP.np_plus(xp, a1, e1))
+            a2, e2 = torch.empty_like(f[:, :, :1, :1]).normal_(1.0, 0.75), torch.empty_like(f[:, :, :1, :1]).normal_(0.0, 0.75)
+            low = TP.np_plus(f, a2, e2)
+            top = m.layer4(m.layer3(m.layer2(low)))
+            d0 = torch.cat([m.bot_fine(low), F.interpolate(m.bot_aspp(m.aspp(top)), size=low.shape[2:], mode="bilinear", align_corners=True)], 1)
+            d1 = F.interpolate(m.final1(d0), size=(he // 2, we // 2), mode="bilinear", align_corners=True) + dec
+            loss = m.criterion(F.interpolate(m.final2(d1), size=(h, w), mode="bilinear", align_corners=True), gts)
+        loss.backward()
+        grads = {k: p.grad.detach().clone() for k, p in m.named_parameters() if p.grad is not None}
+        return float(loss), grads
+
+    l_k, g_k = run(False)
+    l_e, g_e = run(True)
+    tol = 1e-3 if math_mode == 0 else 5e-2
+    assert abs(l_k - l_e) <= tol * abs(l_e), (l_k, l_e)
+    assert set(g_k) == set(g_e)
+    for key in ("final2.0.weight", "final2.0.bias"):             # well-conditioned gradients: checked against the eager run
+        rel = float((g_k[key] - g_e[key]).norm() / g_e[key].norm())
+        assert rel <= (5e-3 if math_mode == 0 else 1e-1), (key, rel)
+    first = next(k for k in g_k if k.startswith("layer0") and k.endswith("weight"))
+    for key in (first, "bot_fine.0.weight", "final1.0.weight"):
+        assert torch.isfinite(g_k[key]).all() and float(g_k[key].abs().sum()) > 0, key
+    assert int(m.OC1_bn.num_batches_tracked) >= 1
