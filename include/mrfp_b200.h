@@ -213,6 +213,16 @@ int mrfp_instnorm_bwd_f32(const float* gy, const float* x, const float* gamma, c
                           const float* invstd, float* gx, float* dgamma_part, float* dbeta_part, int N, int C, int HW,
                           int relu, void* stream);
 
+/* Backward of NP+(ReLU(InstanceNorm(x))) — NP+ call 2 (deepv3.py:334-335) folded into the backward of its producer
+ * (Resnet.py:218-225), SURVEY.md 8f-1: g is the gradient of the NP+ OUTPUT; its plane totals (1R), the NP+ backward
+ * coefficients (np_alpha, np_eps: the forward's draws; np_mean: the plane means of the NP+ input saved by
+ * mrfp_npplus_fwd_presummed_f32) and the InstanceNorm backward with gy = a'*g + b' applied on load (2R + 1W) replace
+ * mrfp_npplus_bwd_f32 followed by mrfp_instnorm_bwd_f32 ((2R+1W) + (2R+1W)).  ws: >= N*C*16 bytes, 16-byte aligned; C <= 256. */
+int mrfp_instnorm_bwd_np_f32(const float* g, const float* x, const float* gamma, const float* beta, const float* mean,
+                             const float* invstd, const float* np_alpha, const float* np_eps, const float* np_mean,
+                             void* ws, size_t ws_bytes, float* gx, float* dgamma_part, float* dbeta_part, int N, int C, int HW,
+                             int relu, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -72,6 +72,8 @@ SIGNATURES = {
     "mrfp_instnorm_bwd_f32": (ctypes.c_int, [c_float_p, c_float_p, c_float_p, c_float_p, c_float_p, c_float_p, c_float_p,
                                              c_float_p, c_float_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                              ctypes.c_void_p]),
+    "mrfp_instnorm_bwd_np_f32": (ctypes.c_int, [c_float_p] * 9 + [ctypes.c_void_p, ctypes.c_size_t, c_float_p, c_float_p, c_float_p,
+                                                ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]),
 }
 
 # test / bench hooks exported by the library but not declared in the public header (single kernels on caller buffers)

@@ -1350,6 +1350,19 @@ int hrfp_backward(const mrfp_hrfp_plan* P, const float* g_ocout, const float* g_
 }
 
 }  // namespace
+
+int np_coef_launch(bool backward, const double* psum, const float* alpha, const float* eps, const float* mean_in, float2* coef,
+                   float* mean_out, float* beta_out, int N, int C, int HW, cudaStream_t stream) {
+  if (C > kMaxC) return MRFP_ERR_UNSUPPORTED;
+  if (backward)
+    launch_k(np_stem_coef_kernel<true>, dim3(1), dim3(256), 0, stream, psum, alpha, eps, mean_in, coef, (float*)nullptr,
+             (float*)nullptr, N, C, HW);
+  else
+    launch_k(np_stem_coef_kernel<false>, dim3(1), dim3(256), 0, stream, psum, alpha, eps, (const float*)nullptr, coef, mean_out,
+             beta_out, N, C, HW);
+  MRFP_CUDA_TRY(cudaGetLastError());
+  return MRFP_OK;
+}
 }  // namespace mrfp
 
 using namespace mrfp;

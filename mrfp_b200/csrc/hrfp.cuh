@@ -85,6 +85,14 @@ int conv3x3_tc(const void* in, const void* wpack, void* out, int esize, int N, i
                const ConvBnFinalize* finalize = nullptr, const void* add_src = nullptr, ConvMaps* cache = nullptr);
 bool conv3x3_tc_supported(int cin, int cout, int esize);
 
+// NP+ per-plane coefficients from plane totals (hrfp.cu; one block, C <= kMaxC).  forward: psum = sum_hw x -> coef = (a, b)
+// with out = a*x + b, mean_out / beta_out side arrays;  backward: psum = sum_hw g, mean_in = the forward's plane means ->
+// coef = (a', b') with gin = a'*g + b' (deepv3.py:268-277)
+int np_coef_launch(bool backward, const double* psum, const float* alpha, const float* eps, const float* mean_in, float2* coef,
+                   float* mean_out, float* beta_out, int N, int C, int HW, cudaStream_t stream);
+// psum[plane] = sum_hw g[plane][:] (np_fused.cu; zeroes psum first)
+int plane_sums(const float* g, double* psum, long long planes, int HW, cudaStream_t stream);
+
 // bulk-copy forward element-wise pass (bn_ring.cu): A_next = ReLU(scale * gather(Y) + shift); MRFP_ERR_UNSUPPORTED -> LDG kernel
 int bn_relu_resample_bulk(const __nv_bfloat16* y, __nv_bfloat16* a, const int* idx_h, const int* idx_w, const int* host_idx_w,
                           const float* scale, const float* shift, int N, int C, int IH, int IW, int OH, int OW, bool reverse,

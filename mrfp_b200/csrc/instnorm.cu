@@ -11,7 +11,7 @@
 //   backward  2R + 1W   (gy and x once each; ATen: ReLU backward + batch-norm backward = 5R + 2W)
 // Statistics are two-pass over the resident copy (mean first, then centred squares; double across lanes) — the same
 // biased variance F.instance_norm uses.  Planes too large for an 8-CTA cluster fall back to re-reading global memory.
-#include "common.cuh"
+#include "hrfp.cuh"
 #include "tma.cuh"
 #include <cooperative_groups.h>
 #include <math.h>
@@ -238,7 +238,9 @@ __global__ void __launch_bounds__(kThreads)
 instnorm_bwd_kernel(const float* __restrict__ gy, const float* __restrict__ x, const float* __restrict__ gamma,
                     const float* __restrict__ beta, const float* __restrict__ mean_in, const float* __restrict__ invstd_in,
                     float* __restrict__ gx, float* __restrict__ dgamma_part, float* __restrict__ dbeta_part, int C, int HW,
-                    int relu, int slice) {
+                    int relu, int slice, const float2* __restrict__ np_coef) {
+  // np_coef: the incoming tensor is the gradient of NP+(y), not of y; NP+'s own backward
+  // gy = a'[plane] * g + b'[plane] is applied as the elements are consumed, so gy is never written or re-read
   cg::cluster_group cluster = cg::this_cluster();
   const unsigned cs = cluster.num_blocks(), cr = cluster.block_rank();
   const long long plane = blockIdx.x / cs;
@@ -281,6 +283,7 @@ instnorm_bwd_kernel(const float* __restrict__ gy, const float* __restrict__ x, c
   const float mean = mean_in[plane], invstd = invstd_in[plane];
   const float gm = gamma ? gamma[c] : 1.f;
   const float a = gm * invstd, b = beta ? beta[c] : 0.f;
+  const float2 npc = np_coef ? np_coef[plane] : make_float2(1.f, 0.f);
   const float* px = RESIDENT ? bx : x + off;
   const float* pg = RESIDENT ? bg : gy + off;
 
@@ -289,7 +292,7 @@ instnorm_bwd_kernel(const float* __restrict__ gy, const float* __restrict__ x, c
   auto one = [&](float xv, float gv, float& xh, float& gp) {
     const float d = xv - mean;
     xh = d * invstd;
-    gp = (relu && !(fmaf(d, a, b) > 0.f)) ? 0.f : gv;
+    gp = (relu && !(fmaf(d, a, b) > 0.f)) ? 0.f : fmaf(npc.x, gv, npc.y);
     s1 += gp;
     s2 = fmaf(gp, xh, s2);
   };
@@ -683,9 +686,9 @@ extern "C" int mrfp_instnorm_fwd_f32(const float* x, const float* gamma, const f
   return MRFP_OK;
 }
 
-extern "C" int mrfp_instnorm_bwd_f32(const float* gy, const float* x, const float* gamma, const float* beta,
-                                     const float* mean, const float* invstd, float* gx, float* dgamma_part,
-                                     float* dbeta_part, int N, int C, int HW, int relu, void* stream) {
+static int instnorm_bwd_impl(const float* gy, const float* x, const float* gamma, const float* beta, const float* mean,
+                             const float* invstd, float* gx, float* dgamma_part, float* dbeta_part, int N, int C, int HW,
+                             int relu, void* stream, const float2* np_coef) {
   if (!gy || !x || !mean || !invstd || !gx || !dgamma_part || !dbeta_part) return MRFP_ERR_NULL_POINTER;
   if (N <= 0 || C <= 0 || HW <= 0 || (long long)N * C > (1ll << 28)) return MRFP_ERR_BAD_SHAPE;
   DeviceInfo di;
@@ -696,18 +699,45 @@ extern "C" int mrfp_instnorm_bwd_f32(const float* gy, const float* x, const floa
   const long long planes = (long long)N * C;
   cudaError_t e;
   const Geo g = pick_geo(HW, 2, di.max_smem_optin);
-  if (const int rcs = vec ? ring_cluster_size(HW, 2, g.resident ? g.smem : 0) : 0) {
+  if (const int rcs = (vec && !np_coef) ? ring_cluster_size(HW, 2, g.resident ? g.smem : 0) : 0) {
     RingArgs a = {x, gy, gamma, beta, gx, const_cast<float*>(mean), const_cast<float*>(invstd), nullptr, dgamma_part, dbeta_part,
                   C, HW, relu, 0, (int)planes, 0.f};
     MRFP_CUDA_TRY(launch_ring<true>(a, rcs, di.sm_count, s));
     return MRFP_OK;
   }
   if (g.resident)
-    e = vec ? launch_cluster(instnorm_bwd_kernel<true, true>, planes, g, s, gy, x, gamma, beta, mean, invstd, gx, dgamma_part, dbeta_part, C, HW, relu, g.slice)
-            : launch_cluster(instnorm_bwd_kernel<false, true>, planes, g, s, gy, x, gamma, beta, mean, invstd, gx, dgamma_part, dbeta_part, C, HW, relu, g.slice);
+    e = vec ? launch_cluster(instnorm_bwd_kernel<true, true>, planes, g, s, gy, x, gamma, beta, mean, invstd, gx, dgamma_part, dbeta_part, C, HW, relu, g.slice, np_coef)
+            : launch_cluster(instnorm_bwd_kernel<false, true>, planes, g, s, gy, x, gamma, beta, mean, invstd, gx, dgamma_part, dbeta_part, C, HW, relu, g.slice, np_coef);
   else
-    e = vec ? launch_cluster(instnorm_bwd_kernel<true, false>, planes, g, s, gy, x, gamma, beta, mean, invstd, gx, dgamma_part, dbeta_part, C, HW, relu, g.slice)
-            : launch_cluster(instnorm_bwd_kernel<false, false>, planes, g, s, gy, x, gamma, beta, mean, invstd, gx, dgamma_part, dbeta_part, C, HW, relu, g.slice);
+    e = vec ? launch_cluster(instnorm_bwd_kernel<true, false>, planes, g, s, gy, x, gamma, beta, mean, invstd, gx, dgamma_part, dbeta_part, C, HW, relu, g.slice, np_coef)
+            : launch_cluster(instnorm_bwd_kernel<false, false>, planes, g, s, gy, x, gamma, beta, mean, invstd, gx, dgamma_part, dbeta_part, C, HW, relu, g.slice, np_coef);
   MRFP_CUDA_TRY(e);
   return MRFP_OK;
+}
+
+extern "C" int mrfp_instnorm_bwd_f32(const float* gy, const float* x, const float* gamma, const float* beta,
+                                     const float* mean, const float* invstd, float* gx, float* dgamma_part,
+                                     float* dbeta_part, int N, int C, int HW, int relu, void* stream) {
+  return instnorm_bwd_impl(gy, x, gamma, beta, mean, invstd, gx, dgamma_part, dbeta_part, N, C, HW, relu, stream, nullptr);
+}
+
+// Backward of  NP+(ReLU(InstanceNorm(x)))  in one chain of passes (NP+ call 2, deepv3.py:334-335, folded
+// into its producer's backward, Resnet.py:218-225): plane totals of g (1R) -> NP+ backward coefficients (one block) ->
+// the InstanceNorm backward with gy = a'*g + b' applied on load (2R + 1W).  The gradient of the NP+ input is never
+// written: 3R + 1W instead of (2R + 1W) + (2R + 1W).  ws: >= N*C*16 bytes, 16-byte aligned.
+extern "C" int mrfp_instnorm_bwd_np_f32(const float* g, const float* x, const float* gamma, const float* beta,
+                                        const float* mean, const float* invstd, const float* np_alpha, const float* np_eps,
+                                        const float* np_mean, void* ws, size_t ws_bytes, float* gx, float* dgamma_part,
+                                        float* dbeta_part, int N, int C, int HW, int relu, void* stream) {
+  if (!g || !np_alpha || !np_eps || !np_mean || !ws) return MRFP_ERR_NULL_POINTER;
+  if (N <= 0 || C <= 0 || HW <= 0) return MRFP_ERR_BAD_SHAPE;
+  if (ws_bytes < (size_t)N * C * 16 || ((uintptr_t)ws & 15)) return MRFP_ERR_WORKSPACE;
+  double* psum = reinterpret_cast<double*>(ws);
+  float2* coef = reinterpret_cast<float2*>(psum + (size_t)N * C);
+  cudaStream_t s = (cudaStream_t)stream;
+  int rc = plane_sums(g, psum, (long long)N * C, HW, s);
+  if (rc) return rc;
+  rc = np_coef_launch(true, psum, np_alpha, np_eps, np_mean, coef, nullptr, nullptr, N, C, HW, s);
+  if (rc) return rc;
+  return instnorm_bwd_impl(g, x, gamma, beta, mean, invstd, gx, dgamma_part, dbeta_part, N, C, HW, relu, stream, coef);
 }

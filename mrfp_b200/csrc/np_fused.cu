@@ -7,7 +7,7 @@
 //   mrfp_npplus_fwd_presummed_f32 out = a[n,c]*y + b[n,c] from psum              (coefficient block + 1R+1W stream)
 // The backward of NP+ still needs the plane sums of the incoming gradient and stays on the ring kernel
 // (mrfp_npplus_bwd_f32).  Same formulas, in double, as npplus.cu (deepv3.py:268-277).
-#include "common.cuh"
+#include "hrfp.cuh"
 #include <math.h>
 
 namespace mrfp {
@@ -50,6 +50,44 @@ relu_psum_kernel(const float* __restrict__ x, float* __restrict__ y, double* __r
         acc += v;
         dst[i] = v;
       }
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) s_part[warp] = acc;
+    __syncthreads();
+    if (tid == 0) {
+      double t = 0;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) t += (double)s_part[i];
+      atomicAdd(psum + plane, t);
+    }
+    __syncthreads();
+  }
+}
+
+// read-only sibling: psum[plane] += sum of the chunk (the plane totals of an incoming gradient, NP+ backward)
+__global__ void __launch_bounds__(256)
+plane_psum_kernel(const float* __restrict__ x, double* __restrict__ psum, int HW, int nchunk, long long items) {
+  pdl_sync();
+  __shared__ float s_part[8];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const bool vec = (HW & 3) == 0 && ((uintptr_t)x & 15) == 0;
+  for (long long it = blockIdx.x; it < items; it += gridDim.x) {
+    const long long plane = it / nchunk;
+    const int ck = (int)(it - plane * nchunk);
+    const int base = ck * kChunk, len = min(kChunk, HW - base);
+    const float* src = x + plane * (long long)HW + base;
+    float acc = 0.f;
+    if (vec) {
+      float4 v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int i = (tid + u * 256) * 4;
+        v[u] = i < len ? __ldg(reinterpret_cast<const float4*>(src + i)) : make_float4(0.f, 0.f, 0.f, 0.f);   // (kept in L2: re-read next)
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) acc += (v[u].x + v[u].y) + (v[u].z + v[u].w);
+    } else {
+      for (int i = tid; i < len; i += 256) acc += src[i];
     }
     acc = warp_sum(acc);
     if (lane == 0) s_part[warp] = acc;
@@ -149,6 +187,18 @@ np_apply_kernel(const float* __restrict__ x, float* __restrict__ out, const floa
 }
 
 }  // namespace
+
+int plane_sums(const float* g, double* psum, long long planes, int HW, cudaStream_t stream) {
+  DeviceInfo di;
+  int rc = get_device_info(&di);
+  if (rc) return rc;
+  MRFP_CUDA_TRY(cudaMemsetAsync(psum, 0, (size_t)planes * sizeof(double), stream));
+  const int nchunk = (HW + kChunk - 1) / kChunk;
+  const long long items = planes * nchunk, cap = (long long)di.sm_count * 16;
+  launch_k(plane_psum_kernel, dim3((unsigned)(items < cap ? items : cap)), dim3(256), 0, stream, g, psum, HW, nchunk, items);
+  MRFP_CUDA_TRY(cudaGetLastError());
+  return MRFP_OK;
+}
 }  // namespace mrfp
 
 using namespace mrfp;

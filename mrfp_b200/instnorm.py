@@ -76,3 +76,75 @@ def module_instance_norm_relu(module: torch.nn.InstanceNorm2d, x, relu=True, wan
     if module.track_running_stats:
         raise _lib.MrfpError("instance_norm_relu: track_running_stats=True is not supported")
     return instance_norm_relu(x, module.weight, module.bias, module.eps, relu, want_plane_sums)
+
+
+class _InstNormReluNpFn(torch.autograd.Function):
+    """out = NP+(ReLU(InstanceNorm(x))) with injected NP+ draws (NP+ call 2, deepv3.py:334-335, and its
+    producer, Resnet.py:218-225, as one autograd node).  Forward: the IN + ReLU kernel also leaves the plane sums of its
+    output, NP+ is one streaming pass over it.  Backward: the plane totals of the incoming gradient, the NP+ backward
+    coefficients, and the InstanceNorm backward that applies them on load — the gradient of the NP+ input is never
+    materialised, and the normalised tensor is not kept for backward (the ReLU mask is recomputed from x)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, eps, alpha, eps_draw):
+        lib = _lib.load()
+        if not x.is_cuda or x.dtype != torch.float32:
+            raise _lib.MrfpError("instance_norm_relu_np_plus needs a CUDA fp32 tensor (no CPU fallback)")
+        n, c, h, w = x.shape
+        xc = x.contiguous()
+        wt = None if weight is None else weight.detach().to(torch.float32).contiguous()
+        bs = None if bias is None else bias.detach().to(torch.float32).contiguous()
+        al = alpha.reshape(n, c).to(torch.float32).contiguous()
+        ed = eps_draw.reshape(n, c).to(torch.float32).contiguous()
+        y = torch.empty_like(xc)
+        out = torch.empty_like(xc)
+        mean = torch.empty((n, c), device=x.device, dtype=torch.float32)
+        invstd = torch.empty((n, c), device=x.device, dtype=torch.float32)
+        np_mean = torch.empty((n, c), device=x.device, dtype=torch.float32)
+        psum = torch.empty((n, c), device=x.device, dtype=torch.float64)
+        ws_bytes = lib.mrfp_npplus_presummed_ws_bytes(n, c)
+        ws = _lib.scratch(x.device, ws_bytes, "npplus_pre")
+        st = _stream_ptr(xc)
+        with torch.cuda.device(x.device):
+            rc = lib.mrfp_instnorm_fwd_f32(xc.data_ptr(), None if wt is None else wt.data_ptr(), None if bs is None else bs.data_ptr(),
+                                           y.data_ptr(), mean.data_ptr(), invstd.data_ptr(), psum.data_ptr(), n, c, h * w,
+                                           float(eps), 1, st)
+            _lib.check(rc, "mrfp_instnorm_fwd_f32")
+            rc = lib.mrfp_npplus_fwd_presummed_f32(y.data_ptr(), psum.data_ptr(), al.data_ptr(), ed.data_ptr(), out.data_ptr(),
+                                                   np_mean.data_ptr(), None, ws.data_ptr(), ws_bytes, n, c, h * w, st)
+            _lib.check(rc, "mrfp_npplus_fwd_presummed_f32")
+        ctx.save_for_backward(xc, wt, bs, mean, invstd, al, ed, np_mean)
+        ctx.has_affine = (weight is not None, bias is not None)
+        return out
+
+    @staticmethod
+    def backward(ctx, g_out):
+        lib = _lib.load()
+        x, wt, bs, mean, invstd, al, ed, np_mean = ctx.saved_tensors
+        n, c, h, w = x.shape
+        g = g_out.contiguous()
+        gx = torch.empty_like(x)
+        dg = torch.empty((n, c), device=x.device, dtype=torch.float32)
+        db = torch.empty((n, c), device=x.device, dtype=torch.float32)
+        ws = _lib.scratch(x.device, n * c * 16, "in_np_bwd")
+        with torch.cuda.device(x.device):
+            rc = lib.mrfp_instnorm_bwd_np_f32(g.data_ptr(), x.data_ptr(), None if wt is None else wt.data_ptr(),
+                                              None if bs is None else bs.data_ptr(), mean.data_ptr(), invstd.data_ptr(),
+                                              al.data_ptr(), ed.data_ptr(), np_mean.data_ptr(), ws.data_ptr(), n * c * 16,
+                                              gx.data_ptr(), dg.data_ptr(), db.data_ptr(), n, c, h * w, 1, _stream_ptr(x))
+        _lib.check(rc, "mrfp_instnorm_bwd_np_f32")
+        gw = dg.sum(0) if ctx.has_affine[0] and ctx.needs_input_grad[1] else None
+        gb = db.sum(0) if ctx.has_affine[1] and ctx.needs_input_grad[2] else None
+        return gx, gw, gb, None, None, None
+
+
+def instance_norm_relu_np_plus(x, weight, bias, eps, alpha, eps_draw):
+    """NP+(relu(F.instance_norm(x, weight=weight, bias=bias, eps=eps))) with the two NP+ draws injected
+    (alpha ~ N(1, .75), eps_draw ~ N(0, .75), shape (N, C[, 1, 1]))."""
+    return _InstNormReluNpFn.apply(x, weight, bias, eps, alpha, eps_draw)
+
+
+def module_instance_norm_relu_np_plus(module: torch.nn.InstanceNorm2d, x, alpha, eps_draw):
+    if module.track_running_stats:
+        raise _lib.MrfpError("instance_norm_relu: track_running_stats=True is not supported")
+    return instance_norm_relu_np_plus(x, module.weight, module.bias, module.eps, alpha, eps_draw)

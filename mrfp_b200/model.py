@@ -147,8 +147,9 @@ class Bottleneck(nn.Module):
         if instance_norm:
             self.instance_norm_layer = nn.InstanceNorm2d(planes * 4, affine=True)
         self.has_in = instance_norm
-        self.emit_plane_sums = False       # set on the last block of layer1 by MRFPPlus
+        self.emit_plane_sums = False       # set on the last block of layer1 by MRFPPlus: NP+ call 2 joins this block's IN + ReLU
         self.plane_sums = None
+        self.np_applied = False
         self.relu = nn.ReLU(inplace=True)
 
     def forward(self, x):
@@ -158,6 +159,12 @@ class Bottleneck(nn.Module):
         out = out + (x if self.downsample is None else self.downsample(x))
         if self.has_in and FUSE_INSTNORM and out.is_cuda and out.dtype == torch.float32:
             # IN + ReLU in one on-chip pass per plane; for layer1's last block also the plane sums NP+ call 2 needs
+            if self.emit_plane_sums and self.training and out.shape[1] <= 256:
+                # NP+ call 2 (deepv3.py:334-335) as one autograd node with its producer: the two draws are made
+                # here, at the RNG position of the reference's call (nothing between this point and it consumes random numbers)
+                alpha, eps = _npplus.draw_np_plus_factors(out)
+                self.np_applied = True
+                return _instnorm.module_instance_norm_relu_np_plus(self.instance_norm_layer, out, alpha, eps)
             if self.emit_plane_sums and self.training:
                 out, self.plane_sums = _instnorm.module_instance_norm_relu(self.instance_norm_layer, out, True, True)
                 return out
@@ -362,7 +369,9 @@ class MRFPPlus(nn.Module, MRFPMixin):
         if fused_sums:
             last.emit_plane_sums = bool(training and p2 < 0.5 and self.fuse_layer1_np)
         x = self.layer1(x)                                                  # deepv3.py:332
-        if training and p2 < 0.5:                                           # deepv3.py:334-335
+        if training and p2 < 0.5 and fused_sums and last.np_applied:        # deepv3.py:334-335 already applied inside layer1's last block
+            last.np_applied = False
+        elif training and p2 < 0.5:                                         # deepv3.py:334-335
             if fused_sums and last.plane_sums is not None:      # statistics came with layer1's last ReLU: NP+ is one streaming pass
                 alpha, eps = _npplus.draw_np_plus_factors(x)
                 x = _npplus.np_plus_presummed(x, last.plane_sums, alpha, eps)

@@ -129,3 +129,37 @@ def test_ring_variant_everywhere_in_a_subprocess():
     r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-x", "-q", "-m", "gpu", "-k", "vs_oracle or fixture"],
                        env=env, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+@pytest.mark.parametrize("shape", [(2, 256, 48, 48), (4, 64, 96, 96), (3, 24, 33, 31), (2, 256, 192, 192)])
+def test_np_plus_folded_into_the_instnorm_node(shape):
+    """NP+ call 2 and its producer as ONE autograd node (deepv3.py:334-335 + Resnet.py:218-225): output and the
+    gradients to x, gamma, beta against the two-node form (IN + ReLU kernels, then the standalone NP+ ring kernels) and
+    against the numpy oracle's composition in fp64."""
+    from mrfp_b200.instnorm import instance_norm_relu, instance_norm_relu_np_plus
+    from mrfp_b200.npplus import np_plus_with_draws
+    n, c, h, w = shape
+    xi, gam, bet, gyi = make_in_case(31, shape)
+    rng = np.random.default_rng(32)
+    al = (1 + 0.75 * rng.standard_normal((n, c))).astype(np.float32)
+    ed = (0.75 * rng.standard_normal((n, c))).astype(np.float32)
+    t = lambda a: torch.from_numpy(a).cuda()
+    res = []
+    for fused in (True, False):
+        x = t(xi).requires_grad_(True); g_ = t(gam).requires_grad_(True); b_ = t(bet).requires_grad_(True)
+        if fused:
+            out = instance_norm_relu_np_plus(x, g_, b_, 1e-5, t(al), t(ed))
+        else:
+            out = np_plus_with_draws(instance_norm_relu(x, g_, b_, 1e-5, True), t(al), t(ed))
+        out.backward(t(gyi))
+        res.append((out.detach(), x.grad, g_.grad, b_.grad))
+    for a, b, tol in zip(res[0], res[1], (2e-6, 2e-5, 2e-5, 2e-5)):
+        assert float((a.double() - b.double()).abs().max()) <= tol * float(b.double().abs().max()) + 1e-7
+    if n * c * h * w <= 4 * 64 * 96 * 96:              # fp64 composition of the two oracle functions
+        ry, _, _, _ = O.instance_norm_relu_forward(xi, gam, bet)
+        ro, npm, _ = O.np_plus_forward(ry.astype(np.float64), al.astype(np.float64), ed.astype(np.float64))
+        gy = O.np_plus_backward(gyi.astype(np.float64), al.astype(np.float64), ed.astype(np.float64), npm)
+        rgx, _, _ = O.instance_norm_relu_backward(gy, xi, gam, bet)
+        far = np.abs(O.instance_norm_relu_forward(xi, gam, bet, relu=False)[0]) > 1e-4
+        assert np.abs(res[0][0].cpu().numpy() - ro).max() <= 2e-5 * np.abs(ro).max()
+        assert np.abs(res[0][1].cpu().numpy() - rgx)[far].max() <= 2e-4 * np.abs(rgx).max()
