@@ -153,7 +153,7 @@ def test_np_plus_folded_into_the_instnorm_node(shape):
             out = np_plus_with_draws(instance_norm_relu(x, g_, b_, 1e-5, True), t(al), t(ed))
         out.backward(t(gyi))
         res.append((out.detach(), x.grad, g_.grad, b_.grad))
-    for a, b, tol in zip(res[0], res[1], (2e-6, 2e-5, 2e-5, 2e-5)):
+    for a, b, tol in zip(res[0], res[1], (2e-6, 2e-5, 2e-4, 2e-4)):      # (d_gamma / d_beta: fp32 sums over N*HW elements)
         assert float((a.double() - b.double()).abs().max()) <= tol * float(b.double().abs().max()) + 1e-7
     if n * c * h * w <= 4 * 64 * 96 * 96:              # fp64 composition of the two oracle functions
         ry, _, _, _ = O.instance_norm_relu_forward(xi, gam, bet)

@@ -26,6 +26,15 @@ def _data(rank):
     return img, lab
 
 
+def _pin_host_arithmetic():
+    """The host trunk on deterministic fp32 cuDNN algorithms: at this tiny size (4x4 maps at layer4, BN over 32 values)
+    the trunk amplifies TF32 / algorithm-choice noise to 1e-3 of the loss, which would mask what these tests compare."""
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.deterministic = True
+    torch.backends.cudnn.benchmark = False
+
+
 def _build(rank, math_mode, init_state=None):
     """Model + optimiser of one rank, RNG streams as bench.py's train leg: torch per rank, gates shared."""
     from mrfp_b200 import dist as D
@@ -101,7 +110,7 @@ def _worker(rank, world, port, init_path, out_path, use_graphs):
     from mrfp_b200.train_step import GraphedTrainStep
     torch.cuda.set_device(0)
     dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
-    torch.backends.cudnn.benchmark = False
+    _pin_host_arithmetic()
     model, opt = _build(rank, 0, torch.load(init_path))
     img, lab = _data(rank)
     step = GraphedTrainStep(model, opt, img, lab, eager_steps=1, use_graphs=use_graphs)
@@ -118,7 +127,16 @@ def _worker(rank, world, port, init_path, out_path, use_graphs):
 def test_two_rank_step_equals_single_process_on_the_same_shards(use_graphs):
     import torch.multiprocessing as mp
     from mrfp_b200.train_step import GraphedTrainStep
-    torch.backends.cudnn.benchmark = False
+    old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.deterministic)
+    _pin_host_arithmetic()
+    try:
+        _two_rank_body(use_graphs)
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.deterministic = old
+
+
+def _two_rank_body(use_graphs):
+    import torch.multiprocessing as mp
     world = 2
     tmp = tempfile.mkdtemp()
     init_path, out_path = os.path.join(tmp, "init.pt"), os.path.join(tmp, "out.pt")
