@@ -50,10 +50,11 @@ template <int COUT> struct Cfg {
   static constexpr int kMT = COUT == 256 ? 1 : 2;
   static constexpr int kAStageBytes = kMT * kATileBytes;
   static constexpr int kBTileBytes = COUT * 128;
-  static constexpr int kStages = COUT == 64 ? 5 : 4;
+  static constexpr int kStages = 4;
+  static constexpr int kOutBufs = 2;                                // staging tiles: chunk i+1 is packed while chunk i drains
   static constexpr int kTmemCols = 2 * kMT * COUT;                  // 256 / 512 / 512: powers of two
-  static constexpr int kSmemBytes = kStages * (kAStageBytes + kBTileBytes) + kStageOutBytes +
-                                    2 * COUT * 4 + 512 /* row weights */ + 256 /* barriers */ + 1024 /* alignment slack */;
+  static constexpr int kSmemBytes = kStages * (kAStageBytes + kBTileBytes) + kOutBufs * kStageOutBytes +
+                                    512 /* row weights */ + 256 /* barriers */ + 1024 /* alignment slack */;
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -129,6 +130,7 @@ __device__ __forceinline__ bool elect_one() {
   asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
   return pred != 0;
 }
+__device__ int g_conv_dbg = 0;   // TEMP ablation flags
 __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
 
 template <int COUT, typename T>
@@ -148,8 +150,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_cons
   unsigned char* sA = smem;
   unsigned char* sB = sA + C::kStages * C::kAStageBytes;
   unsigned char* sOut = sB + C::kStages * C::kBTileBytes;
-  float* s_stats = reinterpret_cast<float*>(sOut + kStageOutBytes);
-  float* s_wgt = s_stats + 2 * COUT;                                    // [128] replication count of each tile row's pixel
+  float* s_wgt = reinterpret_cast<float*>(sOut + C::kOutBufs * kStageOutBytes);   // [128] replication count of each tile row's pixel
   uint64_t* full = reinterpret_cast<uint64_t*>(s_wgt + 128);
   uint64_t* empty = full + C::kStages;
   uint64_t* tmem_full = empty + C::kStages;
@@ -167,7 +168,6 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_cons
     for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 4); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  for (int i = threadIdx.x; i < 2 * COUT; i += kThreads) s_stats[i] = 0.f;
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)), "n"(C::kTmemCols) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -177,6 +177,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_cons
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_ptr;
   pdl_sync();                                 // set-up above overlaps the previous kernel's tail
+  const int dbg = g_conv_dbg;
 
   if (warp == 0) {
     // ===================== TMA producer (whole warp walks, one elected lane issues) =====================
@@ -190,9 +191,9 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_cons
         for (int kc = 0; kc < CIN / kBlockK; ++kc) {
           mbar_wait(&empty[stage], phase ^ 1);
           if (elect_one()) {
-            mbar_expect_tx(&full[stage], C::kAStageBytes + C::kBTileBytes);
-            tma_load_4d(sA + stage * C::kAStageBytes, &tmap_in, &full[stage], kc * kBlockK, w0 + dx, h0 + dy, n);
-            tma_load_2d(sB + stage * C::kBTileBytes, &tmap_w, &full[stage], kc * kBlockK, tap * COUT);
+            mbar_expect_tx(&full[stage], ((dbg & 8) ? 0 : C::kAStageBytes) + ((dbg & 16) ? 0 : C::kBTileBytes));
+            if (!(dbg & 8)) tma_load_4d(sA + stage * C::kAStageBytes, &tmap_in, &full[stage], kc * kBlockK, w0 + dx, h0 + dy, n);
+            if (!(dbg & 16)) tma_load_2d(sB + stage * C::kBTileBytes, &tmap_w, &full[stage], kc * kBlockK, tap * COUT);
           }
           __syncwarp();
           if (++stage == C::kStages) { stage = 0; phase ^= 1; }
@@ -222,6 +223,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_cons
         if (elect_one()) {
           const uint64_t da = make_desc_sw128(sA_u + stage * C::kAStageBytes);
           const uint64_t db = make_desc_sw128(sB_u + stage * C::kBTileBytes);
+          if (!(dbg & 4))
 #pragma unroll
           for (int k = 0; k < 4; ++k)                  // one UMMA_K = 32 bytes of the swizzle row (16 bf16 / 8 tf32)
 #pragma unroll
@@ -247,7 +249,9 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_cons
     // stored and later normalised), weighted by the replication count of each row's pixel; a word is a channel pair
     // (bf16) or one channel (fp32)
     const int cp = et & 31, pg = et >> 5;
-    float a1x = 0.f, a1y = 0.f, a2x = 0.f, a2y = 0.f;
+    float a1x[kChunks], a1y[kChunks], a2x[kChunks], a2y[kChunks];      // per 128-byte chunk of the output row (static indices)
+#pragma unroll
+    for (int j = 0; j < kChunks; ++j) a1x[j] = a1y[j] = a2x[j] = a2y[j] = 0.f;
     // add_src: this thread's 128 bytes of its pixel, fetched ONE CHUNK AHEAD so the loads overlap the previous chunk
     uint4 ad_nxt[8], ad_cur[8];
     bool ad_nxt_ok = false, ad_ok = false;
@@ -274,7 +278,13 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_cons
       const int acc = it & 1;
       mbar_wait(&tmem_full[acc], (it >> 1) & 1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-#pragma unroll 1
+      if (dbg & 2) {
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+        continue;
+      }
+#pragma unroll
       for (int jj = 0; jj < C::kMT * kChunks; ++jj) {
         const int mt = jj / kChunks, j = jj % kChunks;
         if (add_src != nullptr) {                // rotate the prefetch: this chunk's data, then start the next chunk's loads
@@ -283,9 +293,9 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_cons
           ad_ok = ad_nxt_ok;
           if (jj + 1 < C::kMT * kChunks) add_fetch(t0, jj + 1); else add_fetch(t0 + gridDim.x, 0);
         }
-        unsigned char* ob = sOut;
-        // the TMA store that last read the staging buffer must have drained
-        if (leader) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        unsigned char* ob = sOut + ((C::kMT * kChunks) % 2 == 0 ? (jj & 1) : ((it * C::kMT * kChunks + jj) & 1)) * kStageOutBytes;
+        // the TMA store that last read this staging buffer (two chunks ago) must have drained
+        if (leader) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
         epi_bar_sync();
         if (stat_acc) s_wgt[r] = (float)(cnt_h[h0 + mt * kTileH + hl] * cnt_w[w0 + wl]);   // 0 outside the image (zero-padded tables)
         const uint32_t tcol = (uint32_t)((acc * C::kMT + mt) * COUT + j * kChunkC);
@@ -367,29 +377,31 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_cons
               s2x = fmaf(t0, y0, s2x);
             }
           }
-          if constexpr (kBf16) {
-            if (kChunks == 1) { a1x += s1x; a1y += s1y; a2x += s2x; a2y += s2y; }   // one channel set: keep in registers
-            else {
-              atomicAdd(&s_stats[j * 64 + 2 * cp], s1x); atomicAdd(&s_stats[j * 64 + 2 * cp + 1], s1y);
-              atomicAdd(&s_stats[COUT + j * 64 + 2 * cp], s2x); atomicAdd(&s_stats[COUT + j * 64 + 2 * cp + 1], s2y);
-            }
-          } else {
-            atomicAdd(&s_stats[j * 32 + cp], s1x);
-            atomicAdd(&s_stats[COUT + j * 32 + cp], s2x);
-          }
+          a1x[j] += s1x; a2x[j] += s2x;
+          if constexpr (kBf16) { a1y[j] += s1y; a2y[j] += s2y; }
         }
       }
     }
     if (leader) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
-    if (stat_acc && kBf16 && kChunks == 1) {
-      atomicAdd(&s_stats[2 * cp], a1x); atomicAdd(&s_stats[2 * cp + 1], a1y);
-      atomicAdd(&s_stats[COUT + 2 * cp], a2x); atomicAdd(&s_stats[COUT + 2 * cp + 1], a2y);
-    }
-    epi_bar_sync();
     if (stat_acc) {
-      for (int c = et; c < COUT; c += 128) {
-        atomicAdd(stat_acc + c, (double)s_stats[c]);
-        atomicAdd(stat_acc + kMaxC + c, (double)s_stats[COUT + c]);
+      // the four row groups meet once per kernel, in the first pipeline slot: every load of this CTA has been consumed and
+      // every MMA has retired (the last tmem_full), so the operand ring is idle
+      float* part = reinterpret_cast<float*>(sA) + pg * 2 * COUT;
+#pragma unroll
+      for (int j = 0; j < kChunks; ++j) {
+        if constexpr (kBf16) {
+          part[j * 64 + 2 * cp] = a1x[j]; part[j * 64 + 2 * cp + 1] = a1y[j];
+          part[COUT + j * 64 + 2 * cp] = a2x[j]; part[COUT + j * 64 + 2 * cp + 1] = a2y[j];
+        } else {
+          part[j * 32 + cp] = a1x[j];
+          part[COUT + j * 32 + cp] = a2x[j];
+        }
+      }
+      epi_bar_sync();
+      const float* all = reinterpret_cast<const float*>(sA);
+      for (int c = et; c < 2 * COUT; c += 128) {
+        const float sum = (all[c] + all[2 * COUT + c]) + (all[4 * COUT + c] + all[6 * COUT + c]);
+        atomicAdd(stat_acc + (c < COUT ? c : kMaxC + c - COUT), (double)sum);
       }
     }
     if (stat_acc && fin.stats) {
@@ -564,6 +576,7 @@ extern "C" int mrfp_debug_conv3x3_bf16(const void* in, const void* wpack, void* 
   return mrfp::conv3x3_tc(in, wpack, out, 2, N, H, W, cin, cout, dil, cnt_h, cnt_w, stat_acc, (cudaStream_t)stream, false,
                           nullptr, nullptr, nullptr);
 }
+extern "C" int mrfp_debug_conv_set(int v) { return (int)cudaMemcpyToSymbol(mrfp::g_conv_dbg, &v, sizeof(int)); }
 extern "C" int mrfp_debug_conv3x3_tf32(const void* in, const void* wpack, void* out, int N, int H, int W, int cin,
                                        int cout, int dil, const int* cnt_h, const int* cnt_w, double* stat_acc,
                                        void* stream) {
