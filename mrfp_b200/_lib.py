@@ -37,6 +37,7 @@ SIGNATURES = {
     "mrfp_hrfp_plan_lut_bytes": (ctypes.c_size_t, [ctypes.c_void_p]),
     "mrfp_hrfp_plan_write_luts": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t]),
     "mrfp_hrfp_plan_stage": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.POINTER(ctypes.c_int)]),
+    "mrfp_hrfp_plan_set_fusion": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
     "mrfp_hrfp_fwd": (ctypes.c_int, [ctypes.c_void_p, c_float_p, c_void_pp, c_void_pp, c_void_pp, c_void_pp,
                                      c_void_pp, ctypes.c_float, ctypes.c_float, c_float_p, c_float_p, c_float_p,
                                      ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),

@@ -1,0 +1,425 @@
+// tcgen05 implicit-GEMM 3x3 convolution whose A operand is BUILT ON CHIP from the previous stage's conv output (sm_100a,
+// bf16 operands, fp32 accumulation in TMEM).  Replaces, per stage k >= 1 of /root/reference/deepv3.py:320-327,
+//     F.interpolate(nearest) -> BatchNorm2d (batch statistics) -> ReLU -> Conv2d
+// without the resampled / normalised / rectified activation A_k ever existing in HBM: it is produced straight into the
+// shared-memory operand tile from Y_{k-1} (bf16 NHWC at the previous conv's resolution) and that BatchNorm's
+// scale / shift table.
+//
+// Tile: 16 rows x (8 * MT) columns of output pixels; each 16 x 8 sub-tile is one UMMA M = 128 accumulator.  Per
+// 64-channel chunk ONE halo tile is built: the (16 + 2d) x (8 MT + 2d) input neighbourhood, a pixel per 128-byte row,
+// rows of the box contiguous, 16-byte pieces XOR-swizzled with bits 7..9 of their own shared-memory address (the
+// 128-byte swizzle is a function of the absolute address, so ANY 128-byte-aligned start is a valid view).  The 9 taps
+// are 9 start addresses into that tile: an eight-row group of the M tile is 8 consecutive pixels of one image row,
+// consecutive groups are one box row (boxw * 128 B) apart = the descriptor's stride-byte-offset.  The element-wise work
+// therefore runs ONCE per input element (not once per tap), and the L2->SM operand stream drops to the weights (one
+// {64, COUT} TMA box per (chunk, tap), own ring) plus ~1.3-1.9x the input (halo overlap).
+//
+// Warp roles (448 threads, persistent over tiles): warp 0 = weight TMA producer, warp 1 = TMEM allocator + MMA issuer,
+// warps 2-5 = epilogue (conv_common.cuh: TMEM -> staging tile -> TMA store, BN statistics, BN finalisation),
+// warps 6-13 = operand producers: cp.async.cg copies (L2 -> shared memory, no registers, no L1 allocation) put the raw
+// bf16 values at their final swizzled place nA - 1 stages ahead; the thread that copied a piece rewrites it in place
+// as ReLU(scale * y + shift) once it has landed.
+#include "conv_common.cuh"
+#include <atomic>
+
+namespace mrfp {
+namespace {
+using namespace convk;
+
+constexpr int kGThreads = 448;
+constexpr int kGTileH = 16, kGSubW = 8;        // M sub-tile: 16 rows x 8 columns
+constexpr int kProducers = 256;                // warps 6..13
+constexpr int kPxLanes = kProducers / 8;       // box pixels handled per pass (8 threads = the 8 16-byte pieces of a pixel)
+constexpr int kMaxAStages = 4;
+constexpr int kSmemLimit = 232448;             // 227 KB opt-in maximum per CTA
+
+template <int COUT> struct GCfg {
+  static constexpr int kMT = COUT == 256 ? 1 : 2;
+  static constexpr int kBTileBytes = COUT * 128;
+  static constexpr int kBStages = COUT == 256 ? 4 : (COUT == 128 ? 4 : 6);
+  static constexpr int kTmemCols = 2 * kMT * COUT;
+  // weight ring, staging tiles, row weights, barriers — rounded so that the halo stages stay 1024-aligned
+  static constexpr int kFixedBytes = (kBStages * kBTileBytes + 2 * kStageOutBytes + 512 +
+                                      8 * (2 * kMaxAStages + 2 * kBStages + 4) + 16 + 1023) / 1024 * 1024;
+};
+
+// what the producers gather from
+struct GatherArgs {
+  const __nv_bfloat16* y;      // Y_{k-1} [N][SH][SW][CIN]
+  const int* idx_h;            // [H] dst -> src row of the nearest resample
+  const int* idx_w;            // [W]
+  const float* stats;          // [4][kMaxC] mean, invstd, scale, shift of BatchNorm k-1
+  int SH, SW;                  // resolution of Y_{k-1}
+};
+
+__device__ int g_gather_dbg = 0;   // TEMP ablation: 1 = producers idle, 2 = no MMAs, 8 = no transform, 16 = no copies
+__device__ __forceinline__ void prod_bar_sync() { asm volatile("bar.sync 2, 256;" ::: "memory"); }
+// explicit shared-space accesses by 32-bit address (see conv_common.cuh)
+__device__ __forceinline__ int lds32(uint32_t a) { int v; asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+__device__ __forceinline__ uint4 lds128(uint32_t a) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ void unpack8(const uint4& v, float (&f)[8]) {
+  const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { f[2 * i] = __uint_as_float(w[i] << 16); f[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u); }
+}
+__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
+  uint32_t p[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const __nv_bfloat162 h2 = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+    p[i] = *reinterpret_cast<const uint32_t*>(&h2);
+  }
+  return make_uint4(p[0], p[1], p[2], p[3]);
+}
+__device__ __forceinline__ void ld8s(uint32_t a, float (&v)[8]) {
+  const uint4 x = lds128(a), y = lds128(a + 16);
+  v[0] = __uint_as_float(x.x); v[1] = __uint_as_float(x.y); v[2] = __uint_as_float(x.z); v[3] = __uint_as_float(x.w);
+  v[4] = __uint_as_float(y.x); v[5] = __uint_as_float(y.y); v[6] = __uint_as_float(y.z); v[7] = __uint_as_float(y.w);
+}
+
+// in[h][w][c] = ReLU(scale[c] * Y_prev[idx_h[h]][idx_w[w]][c] + shift[c]) inside the image, 0 in the padding
+template <int COUT>
+__global__ void __launch_bounds__(kGThreads, 1)
+conv3x3_gather_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_out,
+                      const GatherArgs ga, int CIN, int dil, int boxw, int tiles_h, int tiles_w, int num_tiles,
+                      const int* __restrict__ cnt_h, const int* __restrict__ cnt_w, double* __restrict__ stat_acc, int rev,
+                      const ConvBnFinalize fin, int H, int W, int nA, int a_stage_bytes, int tab_bytes) {
+  using C = GCfg<COUT>;
+  using T = __nv_bfloat16;
+  constexpr int kBlockK = 64;
+  constexpr int MT = C::kMT;
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  // what the epilogue touches sits at compile-time offsets; the halo stages, gather tables and per-channel constants
+  // follow at run-time offsets and are addressed explicitly
+  unsigned char* sB = smem;
+  unsigned char* sOut = sB + C::kBStages * C::kBTileBytes;
+  float* s_wgt = reinterpret_cast<float*>(sOut + 2 * kStageOutBytes);          // [128]
+  uint64_t* full_a = reinterpret_cast<uint64_t*>(s_wgt + 128);
+  uint64_t* empty_a = full_a + kMaxAStages;
+  uint64_t* full_b = empty_a + kMaxAStages;
+  uint64_t* empty_b = full_b + C::kBStages;
+  uint64_t* tmem_full = empty_b + C::kBStages;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  unsigned char* sA = smem + C::kFixedBytes;                                   // nA stages of a_stage_bytes (1024-aligned)
+  unsigned char* s_tab = sA + nA * a_stage_bytes;                              // nA gather tables
+  float* s_const = reinterpret_cast<float*>(s_tab + tab_bytes);                // scale [CIN], shift [CIN]
+
+  const int warp = threadIdx.x >> 5;
+  const int nchunks = CIN / kBlockK;
+  const int boxh = kGTileH + 2 * dil;
+  const int npix = boxh * boxw;
+
+  if (threadIdx.x == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap_w)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap_out)) : "memory");
+    for (int i = 0; i < nA; ++i) { mbar_init(&full_a[i], kProducers); mbar_init(&empty_a[i], 1); }
+    for (int i = 0; i < C::kBStages; ++i) { mbar_init(&full_b[i], 1); mbar_init(&empty_b[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)), "n"(C::kTmemCols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_ptr;
+  pdl_sync();                                 // set-up above overlaps the previous kernel's tail
+  const int dbg = g_gather_dbg;
+
+  if (warp == 0) {
+    // ===================== weight TMA producer (whole warp walks, one elected lane issues) =====================
+    int bs = 0; uint32_t bph = 0;
+    for (int t0 = blockIdx.x; t0 < num_tiles; t0 += gridDim.x) {
+      for (int kc = 0; kc < nchunks; ++kc) {
+        for (int tap = 0; tap < 9; ++tap) {
+          mbar_wait(&empty_b[bs], bph ^ 1);
+          if (elect_one()) {
+            mbar_expect_tx(&full_b[bs], C::kBTileBytes);
+            tma_load_2d(sB + bs * C::kBTileBytes, &tmap_w, &full_b[bs], kc * kBlockK, tap * COUT);
+          }
+          __syncwarp();
+          if (++bs == C::kBStages) { bs = 0; bph ^= 1; }
+        }
+      }
+    }
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  } else if (warp == 1) {
+    // ===================== MMA issuer (whole warp walks with warp-uniform values, one elected lane issues) ==========
+    constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(COUT >> 3) << 17) | ((128u >> 4) << 24);
+    const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
+    const uint32_t sA_u = smem_u32(sA), sB_u = smem_u32(sB);
+    // K-major, 128-byte swizzle, eight-row groups one box row apart (descriptor fields: LBO = 1, SBO, version 1, SW128)
+    const uint64_t desc_hi = (1ull << 16) | ((uint64_t)((uint32_t)boxw * 8u) << 32) | (1ull << 46) | (2ull << 61);
+    int as = 0, bs = 0; uint32_t aph = 0, bph = 0;
+    int it = 0;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+      const int acc = it & 1;
+      mbar_wait(&tmem_empty[acc], ((it >> 1) & 1) ^ 1);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t d_tmem = tmem_u + (uint32_t)(acc * MT * COUT);
+      for (int kc = 0; kc < nchunks; ++kc) {
+        mbar_wait(&full_a[as], aph);
+        const uint64_t da_stage = desc_hi | (uint64_t)(((sA_u + (uint32_t)(as * a_stage_bytes)) >> 4) & 0x3FFFu);
+#pragma unroll 3
+        for (int tap = 0; tap < 9; ++tap) {
+          mbar_wait(&full_b[bs], bph);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          if (elect_one()) {
+            // the tap's view starts (ty * d * boxw + tx * d) box pixels into the halo tile; descriptors advance in 16-byte units
+            const uint64_t da = da_stage + (uint64_t)(((tap / 3) * dil * boxw + (tap % 3) * dil) * 8);
+            const uint64_t db = make_desc_sw128(sB_u + bs * C::kBTileBytes);
+            if (!(dbg & 2))
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+#pragma unroll
+              for (int mt = 0; mt < MT; ++mt)
+                umma<T>(d_tmem + (uint32_t)(mt * COUT), da + (uint64_t)(mt * kGSubW * 8 + k * 2), db + (uint64_t)(k * 2), idesc,
+                        (kc | tap | k) != 0);
+            umma_commit(&empty_b[bs]);
+            if (tap == 8) umma_commit(&empty_a[as]);     // the halo tile is free once all 9 taps have read it
+          }
+          __syncwarp();
+          if (++bs == C::kBStages) { bs = 0; bph ^= 1; }
+        }
+        if (++as == nA) { as = 0; aph ^= 1; }
+      }
+      if (elect_one()) umma_commit(&tmem_full[acc]);     // accumulator complete
+      __syncwarp();
+    }
+  } else if (warp < 6) {
+    // ===================== epilogue (warps 2..5): conv_common.cuh =====================
+    EpiSmem es;
+    es.sOut = sOut; es.s_wgt = s_wgt; es.scratch = reinterpret_cast<float*>(sA); es.tmem_full = tmem_full; es.tmem_empty = tmem_empty;
+    conv_epilogue<COUT, T, kGTileH, kGSubW, MT, true, false>(es, tmem_base, tmap_out, tiles_h, tiles_w, num_tiles, cnt_h, cnt_w,
+                                                             stat_acc, rev, fin, nullptr, H, W);
+  } else {
+    // ===================== operand producers (warps 6..13) =====================
+    const int pt = threadIdx.x - 192;            // 0..255
+    const int piece = pt & 7;                    // 16-byte piece (8 channels) of a pixel's 128-byte chunk
+    const int pl = pt >> 3;                      // pixel lane: box pixels pl, pl + 32, ...
+    const uint32_t tab_u = smem_u32(s_tab), sA_u = smem_u32(sA), const_u = smem_u32(s_const);
+    for (int j = pt; j < CIN; j += kProducers) { s_const[j] = ga.stats[2 * kMaxC + j]; s_const[CIN + j] = ga.stats[3 * kMaxC + j]; }
+    // gather table of a tile (shared by its channel chunks): source pixel of each box pixel, -1 in the zero padding;
+    // nA buffers, because the copies run up to nA - 1 chunks — possibly tiles — ahead of the transform
+    const int tab_stride = tab_bytes / nA;
+    auto build_table = [&](int seq) {
+      const int t0 = blockIdx.x + seq * gridDim.x;
+      const int t = rev ? num_tiles - 1 - t0 : t0;
+      const int tw = t % tiles_w, th = (t / tiles_w) % tiles_h, n = t / (tiles_w * tiles_h);
+      const int h0 = th * kGTileH - dil, w0 = tw * kGSubW * MT - dil;      // image coordinates of box pixel (0, 0)
+      const uint32_t tab = tab_u + (uint32_t)((seq % nA) * tab_stride);
+      prod_bar_sync();                           // every producer is done with the tile that owned this buffer (first: the constants)
+      for (int p = pt; p < npix; p += kProducers) {
+        const int row = p / boxw, col = p - row * boxw;
+        const int h = h0 + row, w = w0 + col;
+        const bool in = (unsigned)h < (unsigned)H && (unsigned)w < (unsigned)W;
+        const int off = in ? (n * ga.SH + ga.idx_h[h]) * ga.SW + ga.idx_w[w] : -1;
+        asm volatile("st.shared.b32 [%0], %1;" ::"r"(tab + 4u * (uint32_t)p), "r"(off) : "memory");
+      }
+      prod_bar_sync();
+    };
+    const int my_tiles = (num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+    const int nitems = my_tiles * nchunks;       // an item = one 64-channel chunk of one tile = one halo stage
+    constexpr int U = MT == 2 ? 13 : 8;          // box pixels per thread: ceil(20 * 20 / 32), ceil(20 * 12 / 32)
+    // a stage is 1024-byte aligned and a thread's pixels are 32 apart: the swizzle phase of its rows is the constant pl & 7
+    const uint32_t my_off = (uint32_t)pl * 128u + (uint32_t)((piece ^ (pl & 7)) << 4);
+    const int LA = nA - 1;
+    int i_item = 0, i_seq = -1, i_kc = 0, i_as = 0; uint32_t i_ph = 0;
+    // issues the copies of the next item; returns the validity mask of this thread's pixels (bit u: inside the image)
+    auto issue_next = [&]() -> uint32_t {
+      uint32_t valid = 0;
+      if (i_item < nitems) {
+        if (i_kc == 0) build_table(++i_seq);
+        const uint32_t tab = tab_u + (uint32_t)((i_seq % nA) * tab_stride) + 4u * (uint32_t)pl;
+        mbar_wait(&empty_a[i_as], i_ph ^ 1);
+        const uint32_t dst0 = sA_u + (uint32_t)(i_as * a_stage_bytes) + my_off;
+        const __nv_bfloat16* yb = ga.y + i_kc * kBlockK + piece * 8;
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          if (pl + kPxLanes * u < npix && !(dbg & 17)) {
+            const int off = lds32(tab + (uint32_t)(4 * kPxLanes * u));
+            const __nv_bfloat16* src = off >= 0 ? yb + (size_t)off * CIN : ga.y;
+            // a pixel of the zero padding: source size 0 zero-fills the 16 bytes
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;"
+                         ::"r"(dst0 + (uint32_t)(kPxLanes * 128 * u)), "l"(src), "r"(off >= 0 ? 16 : 0) : "memory");
+            valid |= (off >= 0 ? 1u : 0u) << u;
+          }
+        }
+        if (++i_kc == nchunks) i_kc = 0;
+        if (++i_as == nA) { i_as = 0; i_ph ^= 1; }
+        ++i_item;
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");     // one group per call, empty or not: uniform accounting
+      return valid;
+    };
+    uint32_t vq0 = 0, vq1 = 0, vq2 = 0;          // validity masks of the items in flight, oldest first
+    if (LA >= 1) vq0 = issue_next();
+    if (LA >= 2) vq1 = issue_next();
+    if (LA >= 3) vq2 = issue_next();
+    int j_kc = 0, j_as = 0;
+    for (int j = 0; j < nitems; ++j) {
+      // item j is the oldest of the LA groups in flight
+      if (LA == 1) asm volatile("cp.async.wait_group 0;" ::: "memory");
+      else if (LA == 2) asm volatile("cp.async.wait_group 1;" ::: "memory");
+      else asm volatile("cp.async.wait_group 2;" ::: "memory");
+      const uint32_t dst0 = sA_u + (uint32_t)(j_as * a_stage_bytes) + my_off;
+      float sc[8], sh[8];
+      ld8s(const_u + 4u * (uint32_t)(j_kc * kBlockK + piece * 8), sc);
+      ld8s(const_u + 4u * (uint32_t)(CIN + j_kc * kBlockK + piece * 8), sh);
+      const uint32_t valid = vq0;
+      if (!(dbg & 9))
+#pragma unroll
+      for (int u0 = 0; u0 < U; u0 += 5) {          // up to five pixels per batch: their shared-memory reads overlap
+        uint4 v[5];
+#pragma unroll
+        for (int i = 0; i < 5; ++i) {
+          v[i] = make_uint4(0u, 0u, 0u, 0u);
+          if (u0 + i < U && pl + kPxLanes * (u0 + i) < npix) v[i] = lds128(dst0 + (uint32_t)(kPxLanes * 128 * (u0 + i)));
+        }
+#pragma unroll
+        for (int i = 0; i < 5; ++i) {
+          if (u0 + i < U) {
+            float f[8];
+            unpack8(v[i], f);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) f[q] = fmaxf(fmaf(sc[q], f[q], sh[q]), 0.f);
+            uint4 o = pack8(f);
+            if (!((valid >> (u0 + i)) & 1u)) o = make_uint4(0u, 0u, 0u, 0u);     // the convolution's zero padding stays zero
+            if (pl + kPxLanes * (u0 + i) < npix)
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};"
+                           ::"r"(dst0 + (uint32_t)(kPxLanes * 128 * (u0 + i))), "r"(o.x), "r"(o.y), "r"(o.z), "r"(o.w) : "memory");
+          }
+        }
+      }
+      // generic-proxy writes -> visible to the tensor core's (async-proxy) reads, then one arrival per producer thread
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      mbar_arrive(&full_a[j_as]);
+      if (++j_kc == nchunks) j_kc = 0;
+      if (++j_as == nA) j_as = 0;
+      vq0 = vq1; vq1 = vq2;
+      const uint32_t vn = issue_next();          // item j + LA: its stage is free once the MMAs of item j - 1 have retired
+      if (LA == 1) vq0 = vn; else if (LA == 2) vq1 = vn; else vq2 = vn;
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(C::kTmemCols) : "memory");
+  }
+}
+
+// shared-memory carve-up of one launch: as many halo stages as fit next to the weight ring, the staging tiles, the
+// gather tables and the per-channel constants
+struct SmemPlan { int boxw, a_stage, tab_bytes, nA, smem; };
+SmemPlan smem_plan(int cout, int cin, int dil) {
+  const int mt = cout == 256 ? 1 : 2;
+  SmemPlan p;
+  p.boxw = kGSubW * mt + 2 * dil;
+  const int boxh = kGTileH + 2 * dil;
+  p.a_stage = (int)align_up((size_t)p.boxw * boxh * 128, 1024);
+  const int tab1 = (int)align_up((size_t)p.boxw * boxh * 4, 16);          // one table buffer per halo stage
+  const int fixed = (cout == 256 ? GCfg<256>::kFixedBytes : (cout == 128 ? GCfg<128>::kFixedBytes : GCfg<64>::kFixedBytes)) +
+                    2 * cin * 4 + 1024 /* alignment slack */;
+  p.nA = (kSmemLimit - fixed) / (p.a_stage + tab1);
+  if (p.nA > kMaxAStages) p.nA = kMaxAStages;
+  p.tab_bytes = p.nA * tab1;
+  p.smem = fixed + p.nA * (p.a_stage + tab1);
+  return p;
+}
+
+template <int COUT>
+int launch(const GatherArgs& ga, const void* wpack, void* out, int N, int H, int W, int cin, int dil, const int* cnt_h,
+           const int* cnt_w, double* stat_acc, int rev, const ConvBnFinalize& fin, ConvMaps* cache, cudaStream_t stream) {
+  using C = GCfg<COUT>;
+  ConvMaps local;
+  local.valid = 0;
+  ConvMaps* m = cache ? cache : &local;
+  if (!m->valid || m->key[0] != nullptr || m->key[1] != wpack || m->key[2] != out) {
+    m->valid = 0;
+    {
+      const cuuint64_t dims[2] = {(cuuint64_t)cin, (cuuint64_t)9 * COUT};
+      const cuuint64_t strides[1] = {(cuuint64_t)cin * 2};
+      const cuuint32_t box[2] = {64, COUT};
+      int rc = conv_make_map(&m->w, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, wpack, 2, dims, strides, box);
+      if (rc) return rc;
+    }
+    {
+      const cuuint64_t dims[4] = {(cuuint64_t)COUT, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+      const cuuint64_t strides[3] = {(cuuint64_t)COUT * 2, (cuuint64_t)W * COUT * 2, (cuuint64_t)H * W * COUT * 2};
+      const cuuint32_t box[4] = {64, kGSubW, kGTileH, 1};
+      int rc = conv_make_map(&m->out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, out, 4, dims, strides, box);
+      if (rc) return rc;
+    }
+    m->key[0] = nullptr; m->key[1] = wpack; m->key[2] = out;
+    m->valid = 1;
+  }
+  DeviceInfo di;
+  int rc = get_device_info(&di);
+  if (rc) return rc;
+  const SmemPlan sp = smem_plan(COUT, cin, dil);
+  if (sp.nA < 2) return MRFP_ERR_UNSUPPORTED;
+  const int tile_w = kGSubW * C::kMT;
+  const int tiles_h = (H + kGTileH - 1) / kGTileH, tiles_w = (W + tile_w - 1) / tile_w;
+  const int num_tiles = N * tiles_h * tiles_w;
+  const int grid = num_tiles < di.sm_count ? num_tiles : di.sm_count;
+  auto kern = conv3x3_gather_kernel<COUT>;
+  MRFP_SMEM_OPT_IN(kern, kSmemLimit, di.device);
+  launch_k(kern, dim3(grid), dim3(kGThreads), (size_t)sp.smem, stream, m->w, m->out, ga, cin, dil, sp.boxw, tiles_h, tiles_w,
+           num_tiles, cnt_h, cnt_w, stat_acc, rev, fin, H, W, sp.nA, sp.a_stage, sp.tab_bytes);
+  MRFP_CUDA_TRY(cudaGetLastError());
+  return MRFP_OK;
+}
+
+}  // namespace
+
+bool conv3x3_gather_supported(int N, int H, int W, int SH, int SW, int cin, int cout, int dil) {
+  if (cin % 64 != 0 || cin > kMaxC || (cout != 64 && cout != 128 && cout != 256)) return false;
+  if (dil != 1 && dil != 2) return false;
+  if (smem_plan(cout, cin, dil).nA < 2) return false;
+  // pixel indices are kept as 32-bit ints in the gather table
+  return (long long)N * H * W < (1ll << 31) && (long long)N * SH * SW < (1ll << 31);
+}
+
+int conv3x3_gather_fwd(const void* y_prev, int SH, int SW, const int* idx_h, const int* idx_w, const float* stats_prev,
+                       const void* wpack, void* out, int N, int H, int W, int cin, int cout, int dil, const int* cnt_h,
+                       const int* cnt_w, double* stat_acc, cudaStream_t stream, bool reverse_tiles,
+                       const ConvBnFinalize* finalize, ConvMaps* cache) {
+  if (!conv3x3_gather_supported(N, H, W, SH, SW, cin, cout, dil)) return MRFP_ERR_UNSUPPORTED;
+  if (((uintptr_t)y_prev | (uintptr_t)wpack | (uintptr_t)out) & 15) return MRFP_ERR_WORKSPACE;
+  ConvBnFinalize fin = {};
+  if (finalize) {
+    if (!stat_acc || !finalize->gamma || !finalize->stats || !finalize->counter) return MRFP_ERR_NULL_POINTER;
+    fin = *finalize;
+    if (fin.cout_real <= 0 || fin.cout_real > cout) fin.cout_real = cout;
+  }
+  GatherArgs ga = {};
+  ga.y = static_cast<const __nv_bfloat16*>(y_prev);
+  ga.idx_h = idx_h; ga.idx_w = idx_w; ga.stats = stats_prev; ga.SH = SH; ga.SW = SW;
+  const int rev = reverse_tiles ? 1 : 0;
+  switch (cout) {
+    case 64: return launch<64>(ga, wpack, out, N, H, W, cin, dil, cnt_h, cnt_w, stat_acc, rev, fin, cache, stream);
+    case 128: return launch<128>(ga, wpack, out, N, H, W, cin, dil, cnt_h, cnt_w, stat_acc, rev, fin, cache, stream);
+    case 256: return launch<256>(ga, wpack, out, N, H, W, cin, dil, cnt_h, cnt_w, stat_acc, rev, fin, cache, stream);
+  }
+  return MRFP_ERR_UNSUPPORTED;
+}
+
+}  // namespace mrfp
+
+// test / bench hooks (not part of the public header): one gathered forward convolution on caller-provided buffers
+extern "C" int mrfp_debug_conv3x3_gather_fwd(const void* y_prev, int SH, int SW, const int* idx_h, const int* idx_w,
+                                             const float* stats_prev, const void* wpack, void* out, int N, int H, int W, int cin,
+                                             int cout, int dil, void* stream) {
+  return mrfp::conv3x3_gather_fwd(y_prev, SH, SW, idx_h, idx_w, stats_prev, wpack, out, N, H, W, cin, cout, dil, nullptr, nullptr,
+                                  nullptr, (cudaStream_t)stream, false, nullptr, nullptr);
+}
+extern "C" int mrfp_debug_gather_set(int v) { return (int)cudaMemcpyToSymbol(mrfp::g_gather_dbg, &v, sizeof(int)); }

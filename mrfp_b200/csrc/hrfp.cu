@@ -1220,6 +1220,15 @@ int hrfp_forward(const mrfp_hrfp_plan* P, const float* xp, const float* const* W
     double* a = acc + (size_t)k * 2 * kMaxC;
     float* stats = reinterpret_cast<float*>(saved + P->stats_off) + (size_t)k * 4 * kMaxC;
     const double count = (double)P->N * st.oh * st.ow;
+    // operand of this conv built on chip from Y_{k-1} (conv_gather.cu) instead of read from a materialised A_k
+    const bool gathered = tc && k > 0 && (P->fuse & 1) && sizeof(T) == 2 &&
+                          conv3x3_gather_supported(P->N, st.ch, st.cw, P->st[k - 1].ch, P->st[k - 1].cw, st.cin, st.cout, st.dil);
+    if (k > 0 && !gathered) {     // A_k = ReLU(BN(nearest(Y_{k-1}))) as a tensor in HBM
+      const HrfpStage& pv = P->st[k - 1];
+      int rf = run_resample<T>(P, k - 1, lut, reinterpret_cast<const T*>(saved + pv.y_off), nxt, stats - 4 * kMaxC, true, true, di, s);
+      if (rf) return rf;
+      T* t = cur; cur = nxt; nxt = t;
+    }
     if (tc) {
       ConvBnFinalize fin = {};
       fin.gamma = gamma[k]; fin.beta = beta ? beta[k] : nullptr;
@@ -1227,8 +1236,16 @@ int hrfp_forward(const mrfp_hrfp_plan* P, const float* xp, const float* const* W
       fin.stats = stats;
       fin.counter = fin_counters + k;
       fin.count = count; fin.momentum = momentum; fin.eps = eps; fin.cout_real = st.cout_real;
-      int rc = conv3x3_tc(cur, ws + st.wf_off, Y, P->esize, P->N, st.ch, st.cw, st.cin, st.cout, st.dil, lut + st.cnt_h,
-                          lut + st.cnt_w, a, s, false, &fin, nullptr, &P->maps[0][k]);
+      int rc;
+      if (gathered) {
+        const HrfpStage& pv = P->st[k - 1];
+        rc = conv3x3_gather_fwd(saved + pv.y_off, pv.ch, pv.cw, lut + pv.idx_h, lut + pv.idx_w, stats - 4 * kMaxC, ws + st.wf_off, Y,
+                                P->N, st.ch, st.cw, st.cin, st.cout, st.dil, lut + st.cnt_h, lut + st.cnt_w, a, s, false, &fin,
+                                &P->maps_g[k]);
+      } else {
+        rc = conv3x3_tc(cur, ws + st.wf_off, Y, P->esize, P->N, st.ch, st.cw, st.cin, st.cout, st.dil, lut + st.cnt_h,
+                        lut + st.cnt_w, a, s, false, &fin, nullptr, &P->maps[0][k]);
+      }
       if (rc) return rc;
     } else {
       int rc = launch_direct_conv<T>(cur, ws + st.wf_off, Y, P->N, st.ch, st.cw, st.cin, st.cout, st.dil, lut + st.cnt_h,
@@ -1250,10 +1267,6 @@ int hrfp_forward(const mrfp_hrfp_plan* P, const float* xp, const float* const* W
       launch_k(nhwc_to_nchw_kernel<T, false>, dim3(g), dim3(256), 0, s, (const T*)Y, ocout, np ? xp : x_add, lut + st.idx_h,
                lut + st.idx_w, (const float*)(stats + 2 * kMaxC), (const float*)(stats + 3 * kMaxC), st.cout_real, st.cout,
                st.ch, st.cw, st.oh, st.ow, np ? (const float2*)np->coef : (const float2*)nullptr, (const float*)nullptr, 0, 0);
-    } else if (k + 1 < last) {
-      int rf = run_resample<T>(P, k, lut, Y, nxt, stats, true, true, di, s);
-      if (rf) return rf;
-      T* t = cur; cur = nxt; nxt = t;
     }
   }
   MRFP_CUDA_TRY(cudaGetLastError());
@@ -1388,7 +1401,8 @@ extern "C" int mrfp_hrfp_plan_create(mrfp_hrfp_plan_t** out, int N, int cin, int
   P->esize = math_mode == MRFP_MATH_BF16 ? 2 : 4;
   P->cin_pad = stem_pad(cin, math_mode);
   for (int d = 0; d < 2; ++d)
-    for (int k = 0; k < kHrfpStages; ++k) P->maps[d][k].valid = 0;
+    for (int k = 0; k < kHrfpStages; ++k) P->maps[d][k].valid = P->maps_g[k].valid = 0;
+  P->fuse = math_mode == MRFP_MATH_BF16 ? 1 : 0;    // mrfp_hrfp_plan_set_fusion
   // layer table of deepv3.py:221-237, parametrised by the encoder widths and the (padded) stem width
   const int chans[9] = {P->cin_pad, wd[0], wd[1], wd[2], wd[3], wd[2], wd[1], wd[0], P->cin_pad};
   const int dils[8] = {1, 1, 2, 2, 1, 1, 2, 2};
@@ -1477,6 +1491,12 @@ extern "C" int mrfp_hrfp_plan_write_luts(const mrfp_hrfp_plan_t* P, void* host_d
   if (bytes < P->lut.size() * sizeof(int)) return MRFP_ERR_WORKSPACE;
   memcpy(host_dst, P->lut.data(), P->lut.size() * sizeof(int));
   return MRFP_OK;
+}
+extern "C" int mrfp_hrfp_plan_set_fusion(mrfp_hrfp_plan_t* P, int bits) {
+  if (!P || P->magic != kPlanMagic) return MRFP_ERR_BAD_PLAN;
+  std::lock_guard<std::mutex> g(P->mu);
+  P->fuse = P->mode == MRFP_MATH_BF16 ? (bits & 1) : 0;
+  return P->fuse;
 }
 extern "C" int mrfp_hrfp_plan_stage(const mrfp_hrfp_plan_t* P, int k, int* out7) {
   if (!P || P->magic != kPlanMagic) return MRFP_ERR_BAD_PLAN;

@@ -55,6 +55,8 @@ struct mrfp_hrfp_plan {
   // launch-side cache (not part of the geometry): tensor maps per (direction, stage)
   mutable std::mutex mu;
   mutable mrfp::ConvMaps maps[2][mrfp::kHrfpStages];
+  mutable mrfp::ConvMaps maps_g[mrfp::kHrfpStages];      // the operand-fused forward variant (conv_gather.cu)
+  int fuse;                        // 1: forward convs build their operand from Y_{k-1} on chip (bf16 mode only)
 };
 
 namespace mrfp {
@@ -84,6 +86,17 @@ int conv3x3_tc(const void* in, const void* wpack, void* out, int esize, int N, i
                const int* cnt_h, const int* cnt_w, double* stat_acc, cudaStream_t stream, bool reverse_tiles = false,
                const ConvBnFinalize* finalize = nullptr, const void* add_src = nullptr, ConvMaps* cache = nullptr);
 bool conv3x3_tc_supported(int cin, int cout, int esize);
+int conv_make_map(CUtensorMap* m, CUtensorMapDataType dt, const void* base, int rank, const cuuint64_t* dims,
+                  const cuuint64_t* strides, const cuuint32_t* box);
+
+// The same forward convolution with its A operand built on chip from the previous stage's conv output (conv_gather.cu,
+// bf16 only):  in[h][w][c] = ReLU(scale[c] * y_prev[idx_h[h]][idx_w[w]][c] + shift[c])  — BatchNorm (stats_prev: [4][kMaxC]) +
+// ReLU + nearest resample of Y_{k-1}, never written to HBM; everything else as conv3x3_tc.
+bool conv3x3_gather_supported(int N, int H, int W, int SH, int SW, int cin, int cout, int dil);
+int conv3x3_gather_fwd(const void* y_prev, int SH, int SW, const int* idx_h, const int* idx_w, const float* stats_prev,
+                       const void* wpack, void* out, int N, int H, int W, int cin, int cout, int dil, const int* cnt_h,
+                       const int* cnt_w, double* stat_acc, cudaStream_t stream, bool reverse_tiles,
+                       const ConvBnFinalize* finalize, ConvMaps* cache);
 
 // NP+ per-plane coefficients from plane totals (hrfp.cu; one block, C <= kMaxC).  forward: psum = sum_hw x -> coef = (a, b)
 // with out = a*x + b, mean_out / beta_out side arrays;  backward: psum = sum_hw g, mean_in = the forward's plane means ->

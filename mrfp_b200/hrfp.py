@@ -8,6 +8,7 @@ one `torch.autograd.Function` (input gradient only — the weights are frozen, d
 import collections
 import ctypes
 import math
+import os
 import threading
 from typing import Optional, Sequence
 
@@ -36,15 +37,24 @@ def _ptr_array(tensors: Sequence[Optional[torch.Tensor]]):
 class HrfpPlan:
     """Geometry + launch plan for one (N, cin, xh, xw, h, w, math_mode); owns LUTs and workspace."""
 
-    def __init__(self, n, cin, xh, xw, h, w, device, math_mode=MATH_BF16, widths=DEFAULT_WIDTHS):
+    def __init__(self, n, cin, xh, xw, h, w, device, math_mode=MATH_BF16, widths=DEFAULT_WIDTHS, fuse=None):
         lib = _lib.load()
-        self.key = (n, cin, xh, xw, h, w, math_mode, tuple(widths), str(device))
+        self.key = (n, cin, xh, xw, h, w, math_mode, tuple(widths), str(device), fuse)
         self.device = torch.device(device)
         handle = ctypes.c_void_p()
         warr = (ctypes.c_int * 4)(*widths)
         _lib.check(lib.mrfp_hrfp_plan_create(ctypes.byref(handle), n, cin, xh, xw, h, w, warr, math_mode),
                    "mrfp_hrfp_plan_create")
         self.handle = handle
+        # operand fusion of the bf16 chain (include/mrfp_b200.h: mrfp_hrfp_plan_set_fusion); None = the library default (on)
+        if fuse is None and os.environ.get("MRFP_FUSED_GATHER"):
+            fuse = int(os.environ["MRFP_FUSED_GATHER"])
+        if fuse is not None:
+            self.fuse = lib.mrfp_hrfp_plan_set_fusion(handle, int(fuse))
+            if self.fuse < 0:
+                _lib.check(self.fuse, "mrfp_hrfp_plan_set_fusion")
+        else:
+            self.fuse = 1 if math_mode == MATH_BF16 else 0
         self.n, self.cin, self.xh, self.xw, self.h, self.w = n, cin, xh, xw, h, w
         self.math_mode = math_mode
         self.ws_bytes = lib.mrfp_hrfp_plan_ws_bytes(handle)
@@ -82,14 +92,14 @@ _PLAN_CACHE_CAP = 16
 _PLAN_LOCK = threading.Lock()                 # nn.DataParallel runs replicas in host threads
 
 
-def get_plan(n, cin, xh, xw, h, w, device, math_mode=MATH_BF16, widths=DEFAULT_WIDTHS) -> HrfpPlan:
-    key = (n, cin, xh, xw, h, w, math_mode, tuple(widths), str(device))
+def get_plan(n, cin, xh, xw, h, w, device, math_mode=MATH_BF16, widths=DEFAULT_WIDTHS, fuse=None) -> HrfpPlan:
+    key = (n, cin, xh, xw, h, w, math_mode, tuple(widths), str(device), fuse)
     with _PLAN_LOCK:
         p = _PLAN_CACHE.get(key)
         if p is not None:
             _PLAN_CACHE.move_to_end(key)
             return p
-    p = HrfpPlan(n, cin, xh, xw, h, w, device, math_mode, widths)
+    p = HrfpPlan(n, cin, xh, xw, h, w, device, math_mode, widths, fuse)
     with _PLAN_LOCK:
         _PLAN_CACHE[key] = p
         while len(_PLAN_CACHE) > _PLAN_CACHE_CAP:      # an evicted plan is destroyed when its last user (a ctx) lets go
@@ -233,21 +243,23 @@ class _HrfpFn(torch.autograd.Function):
 
 
 def hrfp_chain(xp, convs, bns, h, w, x_add=None, want_out=True, want_dec=True, math_mode=MATH_BF16,
-               update_running_stats=True, lazy_dec=False, np_draws=None):
+               update_running_stats=True, lazy_dec=False, np_draws=None, fuse=None):
     """Runs the chain of deepv3.py:320-327 on `xp` with the caller's 8 conv / 8 BN modules.
 
     `np_draws=(alpha, eps)` (the two draws of deepv3.py:274-275) makes the first output OCout + NP+(xp) — NP+ call 1
     (deepv3.py:316-318) rides on the chain's own passes and NP+(xp) is never materialised.
 
     Returns (OCout [+ x_add], OCout_dec) restricted to the requested outputs.  With `lazy_dec=True` the second
-    value is an `HrfpDec` handle for `hrfp_plus_add` instead of a materialised tensor."""
+    value is an `HrfpDec` handle for `hrfp_plus_add` instead of a materialised tensor.
+    `fuse` (bf16 mode; None = on): 1 folds the forward resample + BatchNorm + ReLU between two convolutions into the next
+    convolution's operand producer (mrfp_hrfp_plan_set_fusion); 0 runs it as a separate pass."""
     n, cin, xh, xw = xp.shape
     widths = tuple(c.out_channels for c in convs[:4])
     if (xh, xw) != (math.ceil(h / 4), math.ceil(w / 4)):
         # deepv3.py:327 resamples to (ceil(h/4), ceil(w/4)) and :330 adds xp: torch.add would raise on a mismatch
         raise _lib.MrfpError(f"HRFP chain: xp is {xh}x{xw} but the chain ends at {math.ceil(h / 4)}x{math.ceil(w / 4)} "
                              f"for a {h}x{w} image (deepv3.py:327, :330)")
-    plan = get_plan(n, cin, xh, xw, h, w, xp.device, math_mode, widths)
+    plan = get_plan(n, cin, xh, xw, h, w, xp.device, math_mode, widths, fuse)
     weights = [c.weight for c in convs]
     gammas = [b.weight for b in bns]
     betas = [b.bias for b in bns]
