@@ -114,10 +114,13 @@ size_t mrfp_hrfp_plan_lut_bytes(const mrfp_hrfp_plan_t* plan);    /* nearest-ind
 int    mrfp_hrfp_plan_write_luts(const mrfp_hrfp_plan_t* plan, void* host_dst, size_t bytes);
 /* per stage k (0..7): out[0..5] = cin, cout, dilation, conv_h, conv_w, out_h; out[6] = out_w */
 int    mrfp_hrfp_plan_stage(const mrfp_hrfp_plan_t* plan, int k, int* out7);
-/* Operand fusion of the bf16 chain (default on; ignored by the other math modes).  bits & 1: the forward
- * F.interpolate -> BatchNorm2d -> ReLU between two convs of deepv3.py:320-327 is computed inside the next conv's operand
- * producer, so the intermediate activation never reaches HBM; 0 keeps it as a separate pass (A/B measurements, tests).
- * Returns the bits in effect, or a negative MRFP_ERR_* code. */
+/* Operand fusion of the bf16 chain (default: all bits; ignored by the other math modes).
+ *   bit 0: the forward F.interpolate -> BatchNorm2d -> ReLU between two convs of deepv3.py:320-327 is computed inside the next
+ *          conv's operand producer: the intermediate activation never reaches HBM;
+ *   bit 1: ReLU' -> BatchNorm2d backward -> nearest adjoint in front of a dgrad is computed inside that dgrad's operand
+ *          producer, for the stages whose resample never replicates a pixel (the identity and the down-sampling stages).
+ * 0 keeps every element-wise step as a separate pass (A/B measurements, tests).  Returns the bits in effect, or a negative
+ * MRFP_ERR_* code.  Not to be changed between a forward and its backward. */
 int    mrfp_hrfp_plan_set_fusion(mrfp_hrfp_plan_t* plan, int bits);
 
 /* Forward.  W[k]: (cout,cin,3,3); gamma/beta[k]: (cout); running_mean/var[k]: (cout) updated in

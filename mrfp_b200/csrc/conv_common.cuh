@@ -135,8 +135,9 @@ struct EpiSmem {
 };
 
 // Runs on warps 2..5 of the CTA (128 threads).  The tile walk (blockIdx.x, += gridDim.x, optional reversal) must match the
-// producer and MMA warps of the calling kernel.  ADD = false compiles the add_src path (and its 64 prefetch registers) out.
-template <int COUT, typename T, int TH, int TW, int MT, bool HMT, bool ADD>
+// producer and MMA warps of the calling kernel.  ADD: 0 compiles the add_src path out; 1 fetches a chunk's 128 bytes of add_src
+// one chunk ahead into a second register set (64 registers); 2 keeps one set and fetches behind the chunk's packing (32).
+template <int COUT, typename T, int TH, int TW, int MT, bool HMT, int ADD>
 __device__ __forceinline__ void conv_epilogue(const EpiSmem& sm, uint32_t tmem_base, const CUtensorMap& tmap_out, int tiles_h,
                                               int tiles_w, int num_tiles, const int* __restrict__ cnt_h,
                                               const int* __restrict__ cnt_w, double* __restrict__ stat_acc, int rev,
@@ -168,6 +169,7 @@ __device__ __forceinline__ void conv_epilogue(const EpiSmem& sm, uint32_t tmem_b
   for (int j = 0; j < kChunks; ++j) a1x[j] = a1y[j] = a2x[j] = a2y[j] = 0.f;
   // add_src: this thread's 128 bytes of its pixel, fetched ONE CHUNK AHEAD so the loads overlap the previous chunk
   uint4 ad_nxt[8], ad_cur[8];
+  uint4 (&ad_use)[8] = *(ADD == 2 ? &ad_nxt : &ad_cur);
   bool ad_nxt_ok = false, ad_ok = false;
   auto add_fetch = [&](int t0_, int jj_) {
     ad_nxt_ok = false;
@@ -195,12 +197,13 @@ __device__ __forceinline__ void conv_epilogue(const EpiSmem& sm, uint32_t tmem_b
 #pragma unroll
     for (int jj = 0; jj < MT * kChunks; ++jj) {
       const int mt = jj / kChunks, j = jj % kChunks;
-      if (ADD && add_src != nullptr) {         // rotate the prefetch: this chunk's data, then start the next chunk's loads
+      if (ADD == 1 && add_src != nullptr) {    // rotate the prefetch: this chunk's data, then start the next chunk's loads
 #pragma unroll
         for (int c = 0; c < 8; ++c) ad_cur[c] = ad_nxt[c];
         ad_ok = ad_nxt_ok;
         if (jj + 1 < MT * kChunks) add_fetch(t0, jj + 1); else add_fetch(t0 + gridDim.x, 0);
       }
+      if (ADD == 2) ad_ok = ad_nxt_ok;
       unsigned char* ob = sOut + ((MT * kChunks) % 2 == 0 ? (jj & 1) : ((it * MT * kChunks + jj) & 1)) * kStageOutBytes;
       const uint32_t ob_u = smem_u32(ob);
       // the TMA store that last read this staging buffer (two chunks ago) must have drained
@@ -216,7 +219,7 @@ __device__ __forceinline__ void conv_epilogue(const EpiSmem& sm, uint32_t tmem_b
           if (ad_ok) {                           // summed in fp32, rounded once
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
-              const uint4 a4 = ad_cur[half * 4 + c];
+              const uint4 a4 = ad_use[half * 4 + c];
               const uint32_t w4[4] = {a4.x, a4.y, a4.z, a4.w};
 #pragma unroll
               for (int i = 0; i < 4; ++i) {
@@ -244,7 +247,7 @@ __device__ __forceinline__ void conv_epilogue(const EpiSmem& sm, uint32_t tmem_b
         for (int c = 0; c < 8; ++c) {            // eight 16-byte chunks (4 channels each)
           uint4 o = make_uint4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
           if (ad_ok) {
-            const uint4 a4 = ad_cur[c];
+            const uint4 a4 = ad_use[c];
             o.x = __float_as_uint(__uint_as_float(o.x) + __uint_as_float(a4.x));
             o.y = __float_as_uint(__uint_as_float(o.y) + __uint_as_float(a4.y));
             o.z = __float_as_uint(__uint_as_float(o.z) + __uint_as_float(a4.z));
@@ -252,6 +255,9 @@ __device__ __forceinline__ void conv_epilogue(const EpiSmem& sm, uint32_t tmem_b
           }
           sts_v4(ob_u + (uint32_t)(r * 128 + ((c ^ (r & 7)) << 4)), o.x, o.y, o.z, o.w);
         }
+      }
+      if (ADD == 2 && add_src != nullptr) {    // the single register set is free again: the next chunk's loads
+        if (jj + 1 < MT * kChunks) add_fetch(t0, jj + 1); else add_fetch(t0 + gridDim.x, 0);
       }
       if (jj == MT * kChunks - 1) {       // all TMEM reads of this accumulator are done
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");

@@ -1,9 +1,11 @@
-// tcgen05 implicit-GEMM 3x3 convolution whose A operand is BUILT ON CHIP from the previous stage's conv output (sm_100a,
-// bf16 operands, fp32 accumulation in TMEM).  Replaces, per stage k >= 1 of /root/reference/deepv3.py:320-327,
-//     F.interpolate(nearest) -> BatchNorm2d (batch statistics) -> ReLU -> Conv2d
-// without the resampled / normalised / rectified activation A_k ever existing in HBM: it is produced straight into the
-// shared-memory operand tile from Y_{k-1} (bf16 NHWC at the previous conv's resolution) and that BatchNorm's
-// scale / shift table.
+// tcgen05 implicit-GEMM 3x3 convolution whose A operand is BUILT ON CHIP from the neighbouring tensors of the chain
+// (sm_100a, bf16 operands, fp32 accumulation in TMEM).  Per stage of /root/reference/deepv3.py:320-327 it replaces
+//   kGatherFwd    F.interpolate(nearest) -> BatchNorm2d (batch statistics) -> ReLU -> Conv2d         (stage k >= 1)
+//                 the activation A_k is produced straight into the operand tile from Y_{k-1} and that BatchNorm's table
+//   kGatherBwd    ReLU' -> BatchNorm2d backward -> adjoint of the nearest resample -> Conv2d dgrad   (stages whose resample
+//                 never replicates a pixel: the identity and the down-sampling stages) — dY_k is produced from dA_{k+1},
+//                 Y_k and the BN-backward sums
+// so that A_k (forward) and dY_k (backward) never exist in HBM.
 //
 // Tile: 16 rows x (8 * MT) columns of output pixels; each 16 x 8 sub-tile is one UMMA M = 128 accumulator.  Per
 // 64-channel chunk ONE halo tile is built: the (16 + 2d) x (8 MT + 2d) input neighbourhood, a pixel per 128-byte row,
@@ -18,7 +20,8 @@
 // warps 2-5 = epilogue (conv_common.cuh: TMEM -> staging tile -> TMA store, BN statistics, BN finalisation),
 // warps 6-13 = operand producers: cp.async.cg copies (L2 -> shared memory, no registers, no L1 allocation) put the raw
 // bf16 values at their final swizzled place nA - 1 stages ahead; the thread that copied a piece rewrites it in place
-// as ReLU(scale * y + shift) once it has landed.
+// (forward: ReLU(scale * y + shift); backward: the BN-backward apply of y and the gradient piece that the same thread
+// copied into a side stage) once it has landed.
 #include "conv_common.cuh"
 #include <atomic>
 
@@ -33,23 +36,30 @@ constexpr int kPxLanes = kProducers / 8;       // box pixels handled per pass (8
 constexpr int kMaxAStages = 4;
 constexpr int kSmemLimit = 232448;             // 227 KB opt-in maximum per CTA
 
+constexpr int kMaxBStages = 6;
+constexpr int kGatherFwd = 0, kGatherBwd = 1;
+// staging tiles, row weights, barriers at compile-time offsets; rounded so that everything behind stays 1024-aligned
+constexpr int kFixedBytes = (2 * kStageOutBytes + 512 + 8 * (2 * kMaxAStages + 2 * kMaxBStages + 4) + 16 + 1023) / 1024 * 1024;
+
 template <int COUT> struct GCfg {
   static constexpr int kMT = COUT == 256 ? 1 : 2;
   static constexpr int kBTileBytes = COUT * 128;
-  static constexpr int kBStages = COUT == 256 ? 4 : (COUT == 128 ? 4 : 6);
+  static constexpr int kBStages = COUT == 256 ? 4 : (COUT == 128 ? 4 : 6);     // preferred depth of the weight ring
   static constexpr int kTmemCols = 2 * kMT * COUT;
-  // weight ring, staging tiles, row weights, barriers — rounded so that the halo stages stay 1024-aligned
-  static constexpr int kFixedBytes = (kBStages * kBTileBytes + 2 * kStageOutBytes + 512 +
-                                      8 * (2 * kMaxAStages + 2 * kBStages + 4) + 16 + 1023) / 1024 * 1024;
 };
 
 // what the producers gather from
 struct GatherArgs {
-  const __nv_bfloat16* y;      // Y_{k-1} [N][SH][SW][CIN]
-  const int* idx_h;            // [H] dst -> src row of the nearest resample
-  const int* idx_w;            // [W]
-  const float* stats;          // [4][kMaxC] mean, invstd, scale, shift of BatchNorm k-1
-  int SH, SW;                  // resolution of Y_{k-1}
+  const __nv_bfloat16* y;      // fwd: Y_{k-1} [N][SH][SW][CIN];  bwd: Y_k [N][H][W][CIN]
+  const __nv_bfloat16* g;      // bwd: dA_{k+1} [N][SH][SW][CIN]
+  const int* tab_h;            // fwd: idx_h [H] (dst -> src row);  bwd: lo_h [H + 1] (first replica of each source row)
+  const int* tab_w;
+  const float* stats;          // [4][kMaxC] mean, invstd, scale, shift of the BatchNorm in question
+  const float* gamma;          // bwd
+  const double* acc;           // bwd: [2][kMaxC] sum mask*dA, sum mask*dA*y (bn_bwd_reduce)
+  double count;                // bwd: elements per channel of the resampled tensor
+  int SH, SW;                  // fwd: resolution of Y_{k-1};  bwd: of dA_{k+1}
+  int c_real;                  // bwd: channels of the module's BatchNorm (stored channels beyond it: dY = 0)
 };
 
 __device__ int g_gather_dbg = 0;   // TEMP ablation: 1 = producers idle, 2 = no MMAs, 8 = no transform, 16 = no copies
@@ -81,34 +91,39 @@ __device__ __forceinline__ void ld8s(uint32_t a, float (&v)[8]) {
   v[4] = __uint_as_float(y.x); v[5] = __uint_as_float(y.y); v[6] = __uint_as_float(y.z); v[7] = __uint_as_float(y.w);
 }
 
-// in[h][w][c] = ReLU(scale[c] * Y_prev[idx_h[h]][idx_w[w]][c] + shift[c]) inside the image, 0 in the padding
-template <int COUT>
+// kGatherFwd:   in[h][w][c] = ReLU(scale[c] * y[idx_h[h]][idx_w[w]][c] + shift[c])
+// kGatherBwd:   in[h][w][c] = P[c] * [scale[c]*y+shift[c] > 0] * g[replica of (h,w)][c] - (R[c]*y[h][w][c] + Q[c])  where (h,w) has a
+//               replica, 0 where it has none (a pixel the down-sampling skipped receives no gradient)
+// each inside the image, 0 in the convolution's zero padding
+template <int COUT, int MODE, bool ADD>
 __global__ void __launch_bounds__(kGThreads, 1)
 conv3x3_gather_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_out,
                       const GatherArgs ga, int CIN, int dil, int boxw, int tiles_h, int tiles_w, int num_tiles,
                       const int* __restrict__ cnt_h, const int* __restrict__ cnt_w, double* __restrict__ stat_acc, int rev,
-                      const ConvBnFinalize fin, int H, int W, int nA, int a_stage_bytes, int tab_bytes) {
+                      const ConvBnFinalize fin, const __nv_bfloat16* __restrict__ add_src, int H, int W, int nA, int nB,
+                      int a_stage_bytes, int tab_bytes) {
   using C = GCfg<COUT>;
   using T = __nv_bfloat16;
   constexpr int kBlockK = 64;
   constexpr int MT = C::kMT;
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  // what the epilogue touches sits at compile-time offsets; the halo stages, gather tables and per-channel constants
-  // follow at run-time offsets and are addressed explicitly
-  unsigned char* sB = smem;
-  unsigned char* sOut = sB + C::kBStages * C::kBTileBytes;
+  // what the epilogue touches sits at compile-time offsets; the weight ring, the halo stages, the gradient side stage
+  // (kGatherBwd), the gather tables and the per-channel constants follow at run-time offsets and are addressed explicitly
+  unsigned char* sOut = smem;
   float* s_wgt = reinterpret_cast<float*>(sOut + 2 * kStageOutBytes);          // [128]
   uint64_t* full_a = reinterpret_cast<uint64_t*>(s_wgt + 128);
   uint64_t* empty_a = full_a + kMaxAStages;
   uint64_t* full_b = empty_a + kMaxAStages;
-  uint64_t* empty_b = full_b + C::kBStages;
-  uint64_t* tmem_full = empty_b + C::kBStages;
+  uint64_t* empty_b = full_b + kMaxBStages;
+  uint64_t* tmem_full = empty_b + kMaxBStages;
   uint64_t* tmem_empty = tmem_full + 2;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
-  unsigned char* sA = smem + C::kFixedBytes;                                   // nA stages of a_stage_bytes (1024-aligned)
-  unsigned char* s_tab = sA + nA * a_stage_bytes;                              // nA gather tables
-  float* s_const = reinterpret_cast<float*>(s_tab + tab_bytes);                // scale [CIN], shift [CIN]
+  unsigned char* sB = smem + kFixedBytes;                                      // nB weight tiles
+  unsigned char* sA = sB + nB * C::kBTileBytes;                                // nA stages of a_stage_bytes (1024-aligned)
+  unsigned char* sG = sA + nA * a_stage_bytes;                                 // kGatherBwd: one stage of gradient pieces
+  unsigned char* s_tab = sG + (MODE == kGatherBwd ? a_stage_bytes : 0);        // gather tables
+  float* s_const = reinterpret_cast<float*>(s_tab + tab_bytes);                // fwd: scale, shift [CIN]; bwd: + P, Q, R
 
   const int warp = threadIdx.x >> 5;
   const int nchunks = CIN / kBlockK;
@@ -119,7 +134,7 @@ conv3x3_gather_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_c
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap_w)) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap_out)) : "memory");
     for (int i = 0; i < nA; ++i) { mbar_init(&full_a[i], kProducers); mbar_init(&empty_a[i], 1); }
-    for (int i = 0; i < C::kBStages; ++i) { mbar_init(&full_b[i], 1); mbar_init(&empty_b[i], 1); }
+    for (int i = 0; i < nB; ++i) { mbar_init(&full_b[i], 1); mbar_init(&empty_b[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 4); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -146,7 +161,7 @@ conv3x3_gather_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_c
             tma_load_2d(sB + bs * C::kBTileBytes, &tmap_w, &full_b[bs], kc * kBlockK, tap * COUT);
           }
           __syncwarp();
-          if (++bs == C::kBStages) { bs = 0; bph ^= 1; }
+          if (++bs == nB) { bs = 0; bph ^= 1; }
         }
       }
     }
@@ -187,7 +202,7 @@ conv3x3_gather_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_c
             if (tap == 8) umma_commit(&empty_a[as]);     // the halo tile is free once all 9 taps have read it
           }
           __syncwarp();
-          if (++bs == C::kBStages) { bs = 0; bph ^= 1; }
+          if (++bs == nB) { bs = 0; bph ^= 1; }
         }
         if (++as == nA) { as = 0; aph ^= 1; }
       }
@@ -198,31 +213,55 @@ conv3x3_gather_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_c
     // ===================== epilogue (warps 2..5): conv_common.cuh =====================
     EpiSmem es;
     es.sOut = sOut; es.s_wgt = s_wgt; es.scratch = reinterpret_cast<float*>(sA); es.tmem_full = tmem_full; es.tmem_empty = tmem_empty;
-    conv_epilogue<COUT, T, kGTileH, kGSubW, MT, true, false>(es, tmem_base, tmap_out, tiles_h, tiles_w, num_tiles, cnt_h, cnt_w,
-                                                             stat_acc, rev, fin, nullptr, H, W);
+    conv_epilogue<COUT, T, kGTileH, kGSubW, MT, true, ADD ? 2 : 0>(es, tmem_base, tmap_out, tiles_h, tiles_w, num_tiles, cnt_h, cnt_w,
+                                                           stat_acc, rev, fin, add_src, H, W);
   } else {
     // ===================== operand producers (warps 6..13) =====================
     const int pt = threadIdx.x - 192;            // 0..255
     const int piece = pt & 7;                    // 16-byte piece (8 channels) of a pixel's 128-byte chunk
     const int pl = pt >> 3;                      // pixel lane: box pixels pl, pl + 32, ...
-    const uint32_t tab_u = smem_u32(s_tab), sA_u = smem_u32(sA), const_u = smem_u32(s_const);
-    for (int j = pt; j < CIN; j += kProducers) { s_const[j] = ga.stats[2 * kMaxC + j]; s_const[CIN + j] = ga.stats[3 * kMaxC + j]; }
-    // gather table of a tile (shared by its channel chunks): source pixel of each box pixel, -1 in the zero padding;
-    // nA buffers, because the copies run up to nA - 1 chunks — possibly tiles — ahead of the transform
-    const int tab_stride = tab_bytes / nA;
+    const uint32_t tab_u = smem_u32(s_tab), sA_u = smem_u32(sA), sG_u = smem_u32(sG), const_u = smem_u32(s_const);
+    {
+      for (int j = pt; j < CIN; j += kProducers) {
+        s_const[j] = ga.stats[2 * kMaxC + j]; s_const[CIN + j] = ga.stats[3 * kMaxC + j];
+        if constexpr (MODE == kGatherBwd) {      // BN-backward constants from the reduced sums (as bn_bwd_apply, hrfp.cu)
+          const double mean = ga.stats[j], invstd = ga.stats[kMaxC + j], gm = j < ga.c_real ? ga.gamma[j] : 0.f;
+          const double S1 = ga.acc[j], S2 = invstd * (ga.acc[kMaxC + j] - mean * S1);
+          const double M1 = gm * S1 / ga.count, M2 = gm * S2 / ga.count;
+          const double r = invstd * invstd * M2;
+          s_const[2 * CIN + j] = (float)(invstd * gm); s_const[3 * CIN + j] = (float)(invstd * M1 - mean * r);
+          s_const[4 * CIN + j] = (float)r;
+        }
+      }
+    }
+    // gather table of a tile (shared by its channel chunks): source pixel of each box pixel, -1 where the operand is zero
+    // (the convolution's padding; backward: also a pixel without replica); nT buffers, because the copies run up to
+    // nA - 1 chunks — possibly tiles — ahead of the transform
+    constexpr int kEnt = MODE == kGatherBwd ? 8 : 4;       // bytes per table entry
+    const int nT = MODE == kGatherBwd ? 1 : nA;
+    const int tab_stride = tab_bytes / nT;
     auto build_table = [&](int seq) {
       const int t0 = blockIdx.x + seq * gridDim.x;
       const int t = rev ? num_tiles - 1 - t0 : t0;
       const int tw = t % tiles_w, th = (t / tiles_w) % tiles_h, n = t / (tiles_w * tiles_h);
       const int h0 = th * kGTileH - dil, w0 = tw * kGSubW * MT - dil;      // image coordinates of box pixel (0, 0)
-      const uint32_t tab = tab_u + (uint32_t)((seq % nA) * tab_stride);
+      const uint32_t tab = tab_u + (uint32_t)((seq % nT) * tab_stride);
       prod_bar_sync();                           // every producer is done with the tile that owned this buffer (first: the constants)
       for (int p = pt; p < npix; p += kProducers) {
         const int row = p / boxw, col = p - row * boxw;
         const int h = h0 + row, w = w0 + col;
         const bool in = (unsigned)h < (unsigned)H && (unsigned)w < (unsigned)W;
-        const int off = in ? (n * ga.SH + ga.idx_h[h]) * ga.SW + ga.idx_w[w] : -1;
-        asm volatile("st.shared.b32 [%0], %1;" ::"r"(tab + 4u * (uint32_t)p), "r"(off) : "memory");
+        if constexpr (MODE == kGatherFwd) {
+          const int off = in ? (n * ga.SH + ga.tab_h[h]) * ga.SW + ga.tab_w[w] : -1;
+          asm volatile("st.shared.b32 [%0], %1;" ::"r"(tab + 4u * (uint32_t)p), "r"(off) : "memory");
+        } else {
+          int oy = -1, og = 0;
+          if (in) {
+            const int dh = ga.tab_h[h], dw = ga.tab_w[w];
+            if (ga.tab_h[h + 1] > dh && ga.tab_w[w + 1] > dw) { oy = (n * H + h) * W + w; og = (n * ga.SH + dh) * ga.SW + dw; }
+          }
+          asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(tab + 8u * (uint32_t)p), "r"(oy), "r"(og) : "memory");
+        }
       }
       prod_bar_sync();
     };
@@ -231,25 +270,33 @@ conv3x3_gather_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_c
     constexpr int U = MT == 2 ? 13 : 8;          // box pixels per thread: ceil(20 * 20 / 32), ceil(20 * 12 / 32)
     // a stage is 1024-byte aligned and a thread's pixels are 32 apart: the swizzle phase of its rows is the constant pl & 7
     const uint32_t my_off = (uint32_t)pl * 128u + (uint32_t)((piece ^ (pl & 7)) << 4);
-    const int LA = nA - 1;
+    // backward: the gradient side stage is single, so the copies run one item ahead of the MMAs but never ahead of the transform
+    const int LA = MODE == kGatherBwd ? 0 : nA - 1;
     int i_item = 0, i_seq = -1, i_kc = 0, i_as = 0; uint32_t i_ph = 0;
-    // issues the copies of the next item; returns the validity mask of this thread's pixels (bit u: inside the image)
+    // issues the copies of the next item; returns the mask of this thread's live pixels (bit u: operand not identically zero)
     auto issue_next = [&]() -> uint32_t {
       uint32_t valid = 0;
       if (i_item < nitems) {
         if (i_kc == 0) build_table(++i_seq);
-        const uint32_t tab = tab_u + (uint32_t)((i_seq % nA) * tab_stride) + 4u * (uint32_t)pl;
+        const uint32_t tab = tab_u + (uint32_t)((i_seq % nT) * tab_stride) + (uint32_t)(kEnt * pl);
         mbar_wait(&empty_a[i_as], i_ph ^ 1);
         const uint32_t dst0 = sA_u + (uint32_t)(i_as * a_stage_bytes) + my_off;
-        const __nv_bfloat16* yb = ga.y + i_kc * kBlockK + piece * 8;
+        const int c0 = i_kc * kBlockK + piece * 8;
 #pragma unroll
         for (int u = 0; u < U; ++u) {
           if (pl + kPxLanes * u < npix && !(dbg & 17)) {
-            const int off = lds32(tab + (uint32_t)(4 * kPxLanes * u));
-            const __nv_bfloat16* src = off >= 0 ? yb + (size_t)off * CIN : ga.y;
-            // a pixel of the zero padding: source size 0 zero-fills the 16 bytes
+            const int off = lds32(tab + (uint32_t)(kEnt * kPxLanes * u));
+            const __nv_bfloat16* src = off >= 0 ? ga.y + (size_t)off * CIN + c0 : ga.y;
+            // an identically-zero pixel: source size 0 zero-fills the 16 bytes
             asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;"
                          ::"r"(dst0 + (uint32_t)(kPxLanes * 128 * u)), "l"(src), "r"(off >= 0 ? 16 : 0) : "memory");
+            if constexpr (MODE == kGatherBwd) {
+              if (off >= 0) {
+                const int og = lds32(tab + (uint32_t)(kEnt * kPxLanes * u) + 4u);
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;"
+                             ::"r"(sG_u + my_off + (uint32_t)(kPxLanes * 128 * u)), "l"(ga.g + (size_t)og * CIN + c0) : "memory");
+              }
+            }
             valid |= (off >= 0 ? 1u : 0u) << u;
           }
         }
@@ -260,42 +307,79 @@ conv3x3_gather_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_c
       asm volatile("cp.async.commit_group;" ::: "memory");     // one group per call, empty or not: uniform accounting
       return valid;
     };
-    uint32_t vq0 = 0, vq1 = 0, vq2 = 0;          // validity masks of the items in flight, oldest first
+    uint32_t vq0 = 0, vq1 = 0, vq2 = 0;          // live-pixel masks of the items in flight, oldest first
     if (LA >= 1) vq0 = issue_next();
     if (LA >= 2) vq1 = issue_next();
     if (LA >= 3) vq2 = issue_next();
     int j_kc = 0, j_as = 0;
     for (int j = 0; j < nitems; ++j) {
-      // item j is the oldest of the LA groups in flight
-      if (LA == 1) asm volatile("cp.async.wait_group 0;" ::: "memory");
+      if (LA == 0) vq0 = issue_next();           // backward: copy, wait, transform — the MMAs of item j - 1 run meanwhile
+      // item j is the oldest of the groups in flight
+      if (LA <= 1) asm volatile("cp.async.wait_group 0;" ::: "memory");
       else if (LA == 2) asm volatile("cp.async.wait_group 1;" ::: "memory");
       else asm volatile("cp.async.wait_group 2;" ::: "memory");
       const uint32_t dst0 = sA_u + (uint32_t)(j_as * a_stage_bytes) + my_off;
-      float sc[8], sh[8];
-      ld8s(const_u + 4u * (uint32_t)(j_kc * kBlockK + piece * 8), sc);
-      ld8s(const_u + 4u * (uint32_t)(CIN + j_kc * kBlockK + piece * 8), sh);
       const uint32_t valid = vq0;
-      if (!(dbg & 9))
+      if constexpr (MODE == kGatherFwd) {
+        float sc[8], sh[8];
+        ld8s(const_u + 4u * (uint32_t)(j_kc * kBlockK + piece * 8), sc);
+        ld8s(const_u + 4u * (uint32_t)(CIN + j_kc * kBlockK + piece * 8), sh);
+        if (!(dbg & 9))
 #pragma unroll
-      for (int u0 = 0; u0 < U; u0 += 5) {          // up to five pixels per batch: their shared-memory reads overlap
-        uint4 v[5];
+        for (int u0 = 0; u0 < U; u0 += 5) {        // up to five pixels per batch: their shared-memory reads overlap
+          uint4 v[5];
 #pragma unroll
-        for (int i = 0; i < 5; ++i) {
-          v[i] = make_uint4(0u, 0u, 0u, 0u);
-          if (u0 + i < U && pl + kPxLanes * (u0 + i) < npix) v[i] = lds128(dst0 + (uint32_t)(kPxLanes * 128 * (u0 + i)));
+          for (int i = 0; i < 5; ++i) {
+            v[i] = make_uint4(0u, 0u, 0u, 0u);
+            if (u0 + i < U && pl + kPxLanes * (u0 + i) < npix) v[i] = lds128(dst0 + (uint32_t)(kPxLanes * 128 * (u0 + i)));
+          }
+#pragma unroll
+          for (int i = 0; i < 5; ++i) {
+            if (u0 + i < U) {
+              float f[8];
+              unpack8(v[i], f);
+#pragma unroll
+              for (int q = 0; q < 8; ++q) f[q] = fmaxf(fmaf(sc[q], f[q], sh[q]), 0.f);
+              uint4 o = pack8(f);
+              if (!((valid >> (u0 + i)) & 1u)) o = make_uint4(0u, 0u, 0u, 0u);   // the convolution's zero padding stays zero
+              if (pl + kPxLanes * (u0 + i) < npix)
+                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};"
+                             ::"r"(dst0 + (uint32_t)(kPxLanes * 128 * (u0 + i))), "r"(o.x), "r"(o.y), "r"(o.z), "r"(o.w) : "memory");
+            }
+          }
         }
+      } else {
+        const uint32_t cb = const_u + 4u * (uint32_t)(j_kc * kBlockK + piece * 8);
+        float sc[8], sh[8], cP[8], cQ[8], cR[8];
+        ld8s(cb, sc); ld8s(cb + 4u * (uint32_t)CIN, sh); ld8s(cb + 8u * (uint32_t)CIN, cP); ld8s(cb + 12u * (uint32_t)CIN, cQ);
+        ld8s(cb + 16u * (uint32_t)CIN, cR);
+        const uint32_t g0 = sG_u + my_off;
+        if (!(dbg & 9))
 #pragma unroll
-        for (int i = 0; i < 5; ++i) {
-          if (u0 + i < U) {
-            float f[8];
-            unpack8(v[i], f);
+        for (int u0 = 0; u0 < U; u0 += 3) {        // three pixels per batch (six shared-memory reads in flight)
+          uint4 vy[3], vg[3];
 #pragma unroll
-            for (int q = 0; q < 8; ++q) f[q] = fmaxf(fmaf(sc[q], f[q], sh[q]), 0.f);
-            uint4 o = pack8(f);
-            if (!((valid >> (u0 + i)) & 1u)) o = make_uint4(0u, 0u, 0u, 0u);     // the convolution's zero padding stays zero
-            if (pl + kPxLanes * (u0 + i) < npix)
+          for (int i = 0; i < 3; ++i) {
+            vy[i] = vg[i] = make_uint4(0u, 0u, 0u, 0u);
+            if (u0 + i < U && ((valid >> (u0 + i)) & 1u)) {
+              vy[i] = lds128(dst0 + (uint32_t)(kPxLanes * 128 * (u0 + i)));
+              vg[i] = lds128(g0 + (uint32_t)(kPxLanes * 128 * (u0 + i)));
+            }
+          }
+#pragma unroll
+          for (int i = 0; i < 3; ++i) {
+            if (u0 + i < U && ((valid >> (u0 + i)) & 1u)) {      // a dead pixel keeps the zeros its copy filled in
+              float y[8], g[8];
+              unpack8(vy[i], y); unpack8(vg[i], g);
+#pragma unroll
+              for (int q = 0; q < 8; ++q) {
+                const float t = fmaf(sc[q], y[q], sh[q]) > 0.f ? g[q] : 0.f;
+                y[q] = cP[q] * t - fmaf(cR[q], y[q], cQ[q]);
+              }
+              const uint4 o = pack8(y);
               asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};"
                            ::"r"(dst0 + (uint32_t)(kPxLanes * 128 * (u0 + i))), "r"(o.x), "r"(o.y), "r"(o.z), "r"(o.w) : "memory");
+            }
           }
         }
       }
@@ -304,9 +388,11 @@ conv3x3_gather_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_c
       mbar_arrive(&full_a[j_as]);
       if (++j_kc == nchunks) j_kc = 0;
       if (++j_as == nA) j_as = 0;
-      vq0 = vq1; vq1 = vq2;
-      const uint32_t vn = issue_next();          // item j + LA: its stage is free once the MMAs of item j - 1 have retired
-      if (LA == 1) vq0 = vn; else if (LA == 2) vq1 = vn; else vq2 = vn;
+      if (LA >= 1) {
+        vq0 = vq1; vq1 = vq2;
+        const uint32_t vn = issue_next();        // item j + LA: its stage is free once the MMAs of item j - 1 have retired
+        if (LA == 1) vq0 = vn; else if (LA == 2) vq1 = vn; else vq2 = vn;
+      }
     }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -317,28 +403,43 @@ conv3x3_gather_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_c
   }
 }
 
-// shared-memory carve-up of one launch: as many halo stages as fit next to the weight ring, the staging tiles, the
-// gather tables and the per-channel constants
-struct SmemPlan { int boxw, a_stage, tab_bytes, nA, smem; };
-SmemPlan smem_plan(int cout, int cin, int dil) {
+// shared-memory carve-up of one launch: weight ring, halo stages (+ the gradient side stage), gather tables, per-channel
+// constants behind the fixed part.  Forward: as many halo stages as fit (the copies run nA - 1 stages ahead), a
+// shallower weight ring if that buys the third stage.  Backward: two halo stages + the side stage.
+struct SmemPlan { int boxw, a_stage, tab_bytes, nA, nB, smem; };
+SmemPlan smem_plan(int mode, int cout, int cin, int dil) {
   const int mt = cout == 256 ? 1 : 2;
-  SmemPlan p;
+  const int b_pref = cout == 256 ? GCfg<256>::kBStages : (cout == 128 ? GCfg<128>::kBStages : GCfg<64>::kBStages);
+  const int b_tile = cout * 128;
+  SmemPlan p = {};
   p.boxw = kGSubW * mt + 2 * dil;
-  const int boxh = kGTileH + 2 * dil;
-  p.a_stage = (int)align_up((size_t)p.boxw * boxh * 128, 1024);
-  const int tab1 = (int)align_up((size_t)p.boxw * boxh * 4, 16);          // one table buffer per halo stage
-  const int fixed = (cout == 256 ? GCfg<256>::kFixedBytes : (cout == 128 ? GCfg<128>::kFixedBytes : GCfg<64>::kFixedBytes)) +
-                    2 * cin * 4 + 1024 /* alignment slack */;
-  p.nA = (kSmemLimit - fixed) / (p.a_stage + tab1);
-  if (p.nA > kMaxAStages) p.nA = kMaxAStages;
-  p.tab_bytes = p.nA * tab1;
-  p.smem = fixed + p.nA * (p.a_stage + tab1);
+  const int npix = p.boxw * (kGTileH + 2 * dil);
+  p.a_stage = (int)align_up((size_t)npix * 128, 1024);
+  const int tab1 = (int)align_up((size_t)npix * (mode == kGatherBwd ? 8 : 4), 16);
+  const int consts = (mode == kGatherFwd ? 2 : 5) * cin * 4;
+  const int base = kFixedBytes + consts + 1024 /* alignment slack */;
+  auto stages_for = [&](int nb) {                    // halo stages that fit next to nb weight tiles
+    const int left = kSmemLimit - base - nb * b_tile;
+    if (mode == kGatherBwd) return left >= 3 * p.a_stage + tab1 ? 2 : 0;
+    int n = left / (p.a_stage + tab1);
+    return n > kMaxAStages ? kMaxAStages : n;
+  };
+  const int want = mode == kGatherBwd ? 2 : 3;
+  p.nB = b_pref;
+  p.nA = stages_for(p.nB);
+  for (int nb = b_pref - 1; nb >= 3 && p.nA < want; --nb)      // the deepest weight ring that still leaves the wanted stages
+    if (stages_for(nb) > p.nA) { p.nB = nb; p.nA = stages_for(nb); }
+  if (p.nA < 2) { p.nA = 0; return p; }
+  const int ntab = mode == kGatherBwd ? 1 : p.nA;
+  p.tab_bytes = ntab * tab1;
+  p.smem = base + p.nB * b_tile + (p.nA + (mode == kGatherBwd ? 1 : 0)) * p.a_stage + p.tab_bytes;
   return p;
 }
 
-template <int COUT>
+template <int COUT, int MODE, bool ADD>
 int launch(const GatherArgs& ga, const void* wpack, void* out, int N, int H, int W, int cin, int dil, const int* cnt_h,
-           const int* cnt_w, double* stat_acc, int rev, const ConvBnFinalize& fin, ConvMaps* cache, cudaStream_t stream) {
+           const int* cnt_w, double* stat_acc, int rev, const ConvBnFinalize& fin, const void* add_src, ConvMaps* cache,
+           cudaStream_t stream) {
   using C = GCfg<COUT>;
   ConvMaps local;
   local.valid = 0;
@@ -365,35 +466,52 @@ int launch(const GatherArgs& ga, const void* wpack, void* out, int N, int H, int
   DeviceInfo di;
   int rc = get_device_info(&di);
   if (rc) return rc;
-  const SmemPlan sp = smem_plan(COUT, cin, dil);
+  const SmemPlan sp = smem_plan(MODE, COUT, cin, dil);
   if (sp.nA < 2) return MRFP_ERR_UNSUPPORTED;
   const int tile_w = kGSubW * C::kMT;
   const int tiles_h = (H + kGTileH - 1) / kGTileH, tiles_w = (W + tile_w - 1) / tile_w;
   const int num_tiles = N * tiles_h * tiles_w;
   const int grid = num_tiles < di.sm_count ? num_tiles : di.sm_count;
-  auto kern = conv3x3_gather_kernel<COUT>;
+  auto kern = conv3x3_gather_kernel<COUT, MODE, ADD>;
   MRFP_SMEM_OPT_IN(kern, kSmemLimit, di.device);
   launch_k(kern, dim3(grid), dim3(kGThreads), (size_t)sp.smem, stream, m->w, m->out, ga, cin, dil, sp.boxw, tiles_h, tiles_w,
-           num_tiles, cnt_h, cnt_w, stat_acc, rev, fin, H, W, sp.nA, sp.a_stage, sp.tab_bytes);
+           num_tiles, cnt_h, cnt_w, stat_acc, rev, fin, static_cast<const __nv_bfloat16*>(add_src), H, W, sp.nA, sp.nB, sp.a_stage,
+           sp.tab_bytes);
   MRFP_CUDA_TRY(cudaGetLastError());
   return MRFP_OK;
 }
 
-}  // namespace
+template <int MODE, bool ADD>
+int dispatch(const GatherArgs& ga, const void* wpack, void* out, int N, int H, int W, int cin, int cout, int dil,
+             const int* cnt_h, const int* cnt_w, double* stat_acc, int rev, const ConvBnFinalize& fin, const void* add_src,
+             ConvMaps* cache, cudaStream_t stream) {
+  switch (cout) {
+    case 64: return launch<64, MODE, ADD>(ga, wpack, out, N, H, W, cin, dil, cnt_h, cnt_w, stat_acc, rev, fin, add_src, cache, stream);
+    case 128: return launch<128, MODE, ADD>(ga, wpack, out, N, H, W, cin, dil, cnt_h, cnt_w, stat_acc, rev, fin, add_src, cache, stream);
+    case 256: return launch<256, MODE, ADD>(ga, wpack, out, N, H, W, cin, dil, cnt_h, cnt_w, stat_acc, rev, fin, add_src, cache, stream);
+  }
+  return MRFP_ERR_UNSUPPORTED;
+}
 
-bool conv3x3_gather_supported(int N, int H, int W, int SH, int SW, int cin, int cout, int dil) {
+bool supported(int mode, int N, int H, int W, int SH, int SW, int cin, int cout, int dil) {
   if (cin % 64 != 0 || cin > kMaxC || (cout != 64 && cout != 128 && cout != 256)) return false;
   if (dil != 1 && dil != 2) return false;
-  if (smem_plan(cout, cin, dil).nA < 2) return false;
+  if (smem_plan(mode, cout, cin, dil).nA < 2) return false;
   // pixel indices are kept as 32-bit ints in the gather table
   return (long long)N * H * W < (1ll << 31) && (long long)N * SH * SW < (1ll << 31);
+}
+
+}  // namespace
+
+bool conv3x3_gather_supported(int mode, int N, int H, int W, int SH, int SW, int cin, int cout, int dil) {
+  return supported(mode, N, H, W, SH, SW, cin, cout, dil);
 }
 
 int conv3x3_gather_fwd(const void* y_prev, int SH, int SW, const int* idx_h, const int* idx_w, const float* stats_prev,
                        const void* wpack, void* out, int N, int H, int W, int cin, int cout, int dil, const int* cnt_h,
                        const int* cnt_w, double* stat_acc, cudaStream_t stream, bool reverse_tiles,
                        const ConvBnFinalize* finalize, ConvMaps* cache) {
-  if (!conv3x3_gather_supported(N, H, W, SH, SW, cin, cout, dil)) return MRFP_ERR_UNSUPPORTED;
+  if (!supported(kGatherFwd, N, H, W, SH, SW, cin, cout, dil)) return MRFP_ERR_UNSUPPORTED;
   if (((uintptr_t)y_prev | (uintptr_t)wpack | (uintptr_t)out) & 15) return MRFP_ERR_WORKSPACE;
   ConvBnFinalize fin = {};
   if (finalize) {
@@ -403,23 +521,35 @@ int conv3x3_gather_fwd(const void* y_prev, int SH, int SW, const int* idx_h, con
   }
   GatherArgs ga = {};
   ga.y = static_cast<const __nv_bfloat16*>(y_prev);
-  ga.idx_h = idx_h; ga.idx_w = idx_w; ga.stats = stats_prev; ga.SH = SH; ga.SW = SW;
+  ga.tab_h = idx_h; ga.tab_w = idx_w; ga.stats = stats_prev; ga.SH = SH; ga.SW = SW;
+  return dispatch<kGatherFwd, false>(ga, wpack, out, N, H, W, cin, cout, dil, cnt_h, cnt_w, stat_acc, reverse_tiles ? 1 : 0, fin,
+                                     nullptr, cache, stream);
+}
+
+int conv3x3_gather_bwd(const void* y, const void* dA, int OH, int OW, const int* lo_h, const int* lo_w, const float* stats,
+                       const float* gamma, const double* acc, double count, int c_real, const void* wpack, void* out, int N,
+                       int H, int W, int cin, int cout, int dil, cudaStream_t stream, bool reverse_tiles, const void* add_src,
+                       ConvMaps* cache) {
+  if (!supported(kGatherBwd, N, H, W, OH, OW, cin, cout, dil)) return MRFP_ERR_UNSUPPORTED;
+  if (((uintptr_t)y | (uintptr_t)dA | (uintptr_t)wpack | (uintptr_t)out | (uintptr_t)add_src) & 15) return MRFP_ERR_WORKSPACE;
+  GatherArgs ga = {};
+  ga.y = static_cast<const __nv_bfloat16*>(y); ga.g = static_cast<const __nv_bfloat16*>(dA);
+  ga.tab_h = lo_h; ga.tab_w = lo_w; ga.stats = stats; ga.gamma = gamma; ga.acc = acc; ga.count = count;
+  ga.SH = OH; ga.SW = OW; ga.c_real = c_real;
+  const ConvBnFinalize fin = {};
   const int rev = reverse_tiles ? 1 : 0;
-  switch (cout) {
-    case 64: return launch<64>(ga, wpack, out, N, H, W, cin, dil, cnt_h, cnt_w, stat_acc, rev, fin, cache, stream);
-    case 128: return launch<128>(ga, wpack, out, N, H, W, cin, dil, cnt_h, cnt_w, stat_acc, rev, fin, cache, stream);
-    case 256: return launch<256>(ga, wpack, out, N, H, W, cin, dil, cnt_h, cnt_w, stat_acc, rev, fin, cache, stream);
-  }
-  return MRFP_ERR_UNSUPPORTED;
+  if (add_src)
+    return dispatch<kGatherBwd, true>(ga, wpack, out, N, H, W, cin, cout, dil, nullptr, nullptr, nullptr, rev, fin, add_src, cache, stream);
+  return dispatch<kGatherBwd, false>(ga, wpack, out, N, H, W, cin, cout, dil, nullptr, nullptr, nullptr, rev, fin, nullptr, cache, stream);
 }
 
 }  // namespace mrfp
 
-// test / bench hooks (not part of the public header): one gathered forward convolution on caller-provided buffers
+// test / bench hooks (not part of the public header): single convolutions on caller-provided buffers
 extern "C" int mrfp_debug_conv3x3_gather_fwd(const void* y_prev, int SH, int SW, const int* idx_h, const int* idx_w,
                                              const float* stats_prev, const void* wpack, void* out, int N, int H, int W, int cin,
-                                             int cout, int dil, void* stream) {
-  return mrfp::conv3x3_gather_fwd(y_prev, SH, SW, idx_h, idx_w, stats_prev, wpack, out, N, H, W, cin, cout, dil, nullptr, nullptr,
-                                  nullptr, (cudaStream_t)stream, false, nullptr, nullptr);
+                                             int cout, int dil, const int* cnt_h, const int* cnt_w, double* stat_acc, void* stream) {
+  return mrfp::conv3x3_gather_fwd(y_prev, SH, SW, idx_h, idx_w, stats_prev, wpack, out, N, H, W, cin, cout, dil, cnt_h, cnt_w,
+                                  stat_acc, (cudaStream_t)stream, false, nullptr, nullptr);
 }
 extern "C" int mrfp_debug_gather_set(int v) { return (int)cudaMemcpyToSymbol(mrfp::g_gather_dbg, &v, sizeof(int)); }

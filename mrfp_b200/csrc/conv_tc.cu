@@ -146,7 +146,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_cons
     // ===================== epilogue (warps 2..5): conv_common.cuh =====================
     EpiSmem es;
     es.sOut = sOut; es.s_wgt = s_wgt; es.scratch = reinterpret_cast<float*>(sA); es.tmem_full = tmem_full; es.tmem_empty = tmem_empty;
-    conv_epilogue<COUT, T, kTileH, kTileW, C::kMT, false, true>(es, tmem_base, tmap_out, tiles_h, tiles_w, num_tiles, cnt_h, cnt_w,
+    conv_epilogue<COUT, T, kTileH, kTileW, C::kMT, false, 1>(es, tmem_base, tmap_out, tiles_h, tiles_w, num_tiles, cnt_h, cnt_w,
                                                                 stat_acc, rev, fin, add_src, H, W);
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");

@@ -1222,7 +1222,7 @@ int hrfp_forward(const mrfp_hrfp_plan* P, const float* xp, const float* const* W
     const double count = (double)P->N * st.oh * st.ow;
     // operand of this conv built on chip from Y_{k-1} (conv_gather.cu) instead of read from a materialised A_k
     const bool gathered = tc && k > 0 && (P->fuse & 1) && sizeof(T) == 2 &&
-                          conv3x3_gather_supported(P->N, st.ch, st.cw, P->st[k - 1].ch, P->st[k - 1].cw, st.cin, st.cout, st.dil);
+                          conv3x3_gather_supported(0, P->N, st.ch, st.cw, P->st[k - 1].ch, P->st[k - 1].cw, st.cin, st.cout, st.dil);
     if (k > 0 && !gathered) {     // A_k = ReLU(BN(nearest(Y_{k-1}))) as a tensor in HBM
       const HrfpStage& pv = P->st[k - 1];
       int rf = run_resample<T>(P, k - 1, lut, reinterpret_cast<const T*>(saved + pv.y_off), nxt, stats - 4 * kMaxC, true, true, di, s);
@@ -1241,7 +1241,7 @@ int hrfp_forward(const mrfp_hrfp_plan* P, const float* xp, const float* const* W
         const HrfpStage& pv = P->st[k - 1];
         rc = conv3x3_gather_fwd(saved + pv.y_off, pv.ch, pv.cw, lut + pv.idx_h, lut + pv.idx_w, stats - 4 * kMaxC, ws + st.wf_off, Y,
                                 P->N, st.ch, st.cw, st.cin, st.cout, st.dil, lut + st.cnt_h, lut + st.cnt_w, a, s, false, &fin,
-                                &P->maps_g[k]);
+                                &P->maps_g[0][k]);
       } else {
         rc = conv3x3_tc(cur, ws + st.wf_off, Y, P->esize, P->N, st.ch, st.cw, st.cin, st.cout, st.dil, lut + st.cnt_h,
                         lut + st.cnt_w, a, s, false, &fin, nullptr, &P->maps[0][k]);
@@ -1318,9 +1318,16 @@ int hrfp_backward(const mrfp_hrfp_plan* P, const float* g_ocout, const float* g_
     int rr = run_bwd_reduce<T>(P, k, lut, dA, Y, stats, a, at_end, true, di, s);
     if (rr) return rr;
     at_end = !at_end;
-    int ra = run_bwd_apply<T>(P, k, lut, dA, Y, dY, stats, gamma[k], a, at_end, true, di, s);
-    if (ra) return ra;
-    at_end = !at_end;
+    // a stage whose resample never replicates a pixel (identity, down-sampling): dY_k is built inside the dgrad's operand
+    // producers from dA_{k+1}, Y_k and the sums (conv_gather.cu) instead of a pass over HBM.  (The fp32 OCout_dec gradient
+    // of the unfused tail is staged in the dA buffer, which the gathered dgrad still reads: that case keeps the pass.)
+    const bool gathered = tc && (P->fuse & 2) && sizeof(T) == 2 && st.max_rep <= 1 && !(k == 4 && g_ocout_dec && !g_dec_nhwc) &&
+                          conv3x3_gather_supported(1, P->N, st.ch, st.cw, st.oh, st.ow, st.cout, st.cin, st.dil);
+    if (!gathered) {
+      int ra = run_bwd_apply<T>(P, k, lut, dA, Y, dY, stats, gamma[k], a, at_end, true, di, s);
+      if (ra) return ra;
+      at_end = !at_end;
+    }
     // dgrad: conv of dY (cout channels) with the rotated / transposed kernel -> dA_prev (cin channels)
     if (tc) {
       // stage 4's dgrad produces dA_3, which the gradient of OCout_dec has to join: convert that gradient into the
@@ -1337,8 +1344,14 @@ int hrfp_backward(const mrfp_hrfp_plan* P, const float* g_ocout, const float* g_
         dec_joined = true;
         at_end = true;
       }
-      int rc = conv3x3_tc(dY, saved + st.wb_off, other, P->esize, P->N, st.ch, st.cw, st.cout, st.cin, st.dil, nullptr, nullptr,
-                          nullptr, s, at_end, nullptr, add_src, &P->maps[1][k]);
+      int rc;
+      if (gathered)
+        rc = conv3x3_gather_bwd(Y, dA, st.oh, st.ow, lut + st.lo_h, lut + st.lo_w, stats, gamma[k], a, (double)P->N * st.oh * st.ow,
+                                st.cout_real, saved + st.wb_off, other, P->N, st.ch, st.cw, st.cout, st.cin, st.dil, s, at_end,
+                                add_src, &P->maps_g[1][k]);
+      else
+        rc = conv3x3_tc(dY, saved + st.wb_off, other, P->esize, P->N, st.ch, st.cw, st.cout, st.cin, st.dil, nullptr, nullptr,
+                        nullptr, s, at_end, nullptr, add_src, &P->maps[1][k]);
       if (rc) return rc;
       at_end = !at_end;
     } else {
@@ -1401,8 +1414,8 @@ extern "C" int mrfp_hrfp_plan_create(mrfp_hrfp_plan_t** out, int N, int cin, int
   P->esize = math_mode == MRFP_MATH_BF16 ? 2 : 4;
   P->cin_pad = stem_pad(cin, math_mode);
   for (int d = 0; d < 2; ++d)
-    for (int k = 0; k < kHrfpStages; ++k) P->maps[d][k].valid = P->maps_g[k].valid = 0;
-  P->fuse = math_mode == MRFP_MATH_BF16 ? 1 : 0;    // mrfp_hrfp_plan_set_fusion
+    for (int k = 0; k < kHrfpStages; ++k) P->maps[d][k].valid = P->maps_g[d][k].valid = 0;
+  P->fuse = math_mode == MRFP_MATH_BF16 ? 3 : 0;    // mrfp_hrfp_plan_set_fusion
   // layer table of deepv3.py:221-237, parametrised by the encoder widths and the (padded) stem width
   const int chans[9] = {P->cin_pad, wd[0], wd[1], wd[2], wd[3], wd[2], wd[1], wd[0], P->cin_pad};
   const int dils[8] = {1, 1, 2, 2, 1, 1, 2, 2};
@@ -1495,7 +1508,7 @@ extern "C" int mrfp_hrfp_plan_write_luts(const mrfp_hrfp_plan_t* P, void* host_d
 extern "C" int mrfp_hrfp_plan_set_fusion(mrfp_hrfp_plan_t* P, int bits) {
   if (!P || P->magic != kPlanMagic) return MRFP_ERR_BAD_PLAN;
   std::lock_guard<std::mutex> g(P->mu);
-  P->fuse = P->mode == MRFP_MATH_BF16 ? (bits & 1) : 0;
+  P->fuse = P->mode == MRFP_MATH_BF16 ? (bits & 3) : 0;
   return P->fuse;
 }
 extern "C" int mrfp_hrfp_plan_stage(const mrfp_hrfp_plan_t* P, int k, int* out7) {

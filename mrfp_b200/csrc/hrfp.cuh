@@ -55,8 +55,9 @@ struct mrfp_hrfp_plan {
   // launch-side cache (not part of the geometry): tensor maps per (direction, stage)
   mutable std::mutex mu;
   mutable mrfp::ConvMaps maps[2][mrfp::kHrfpStages];
-  mutable mrfp::ConvMaps maps_g[mrfp::kHrfpStages];      // the operand-fused forward variant (conv_gather.cu)
-  int fuse;                        // 1: forward convs build their operand from Y_{k-1} on chip (bf16 mode only)
+  mutable mrfp::ConvMaps maps_g[2][mrfp::kHrfpStages];   // the halo-tile variants (conv_gather.cu)
+  int fuse;                        // bf16 mode: bit 0 forward convs build their operand from Y_{k-1} on chip, bit 1 dgrads of
+                                   // non-replicating stages build dY_k on chip
 };
 
 namespace mrfp {
@@ -89,14 +90,22 @@ bool conv3x3_tc_supported(int cin, int cout, int esize);
 int conv_make_map(CUtensorMap* m, CUtensorMapDataType dt, const void* base, int rank, const cuuint64_t* dims,
                   const cuuint64_t* strides, const cuuint32_t* box);
 
-// The same forward convolution with its A operand built on chip from the previous stage's conv output (conv_gather.cu,
-// bf16 only):  in[h][w][c] = ReLU(scale[c] * y_prev[idx_h[h]][idx_w[w]][c] + shift[c])  — BatchNorm (stats_prev: [4][kMaxC]) +
-// ReLU + nearest resample of Y_{k-1}, never written to HBM; everything else as conv3x3_tc.
-bool conv3x3_gather_supported(int N, int H, int W, int SH, int SW, int cin, int cout, int dil);
+// The same convolution on a halo-tile pipeline whose A operand is built on chip (conv_gather.cu, bf16 only):
+//   fwd:   in[h][w][c] = ReLU(scale[c] * y_prev[idx_h[h]][idx_w[w]][c] + shift[c]) — BatchNorm (stats_prev: [4][kMaxC]) + ReLU +
+//          nearest resample of Y_{k-1}, never written to HBM; everything else as conv3x3_tc
+//   bwd:   in = dY_k = BN-backward apply of (dA_{k+1}, Y_k) with the nearest adjoint, for a stage whose resample never
+//          replicates a pixel (lo_h / lo_w: first replica of each source row / column, [H + 1] / [W + 1]); acc = the sums of
+//          bn_bwd_reduce; out = dA_k; add_src as conv3x3_tc
+// mode: 0 fwd, 1 bwd.  MRFP_ERR_UNSUPPORTED -> the caller runs the separate element-wise pass and conv3x3_tc.
+bool conv3x3_gather_supported(int mode, int N, int H, int W, int SH, int SW, int cin, int cout, int dil);
 int conv3x3_gather_fwd(const void* y_prev, int SH, int SW, const int* idx_h, const int* idx_w, const float* stats_prev,
                        const void* wpack, void* out, int N, int H, int W, int cin, int cout, int dil, const int* cnt_h,
                        const int* cnt_w, double* stat_acc, cudaStream_t stream, bool reverse_tiles,
                        const ConvBnFinalize* finalize, ConvMaps* cache);
+int conv3x3_gather_bwd(const void* y, const void* dA, int OH, int OW, const int* lo_h, const int* lo_w, const float* stats,
+                       const float* gamma, const double* acc, double count, int c_real, const void* wpack, void* out, int N,
+                       int H, int W, int cin, int cout, int dil, cudaStream_t stream, bool reverse_tiles, const void* add_src,
+                       ConvMaps* cache);
 
 // NP+ per-plane coefficients from plane totals (hrfp.cu; one block, C <= kMaxC).  forward: psum = sum_hw x -> coef = (a, b)
 // with out = a*x + b, mean_out / beta_out side arrays;  backward: psum = sum_hw g, mean_in = the forward's plane means ->

@@ -54,7 +54,7 @@ class HrfpPlan:
             if self.fuse < 0:
                 _lib.check(self.fuse, "mrfp_hrfp_plan_set_fusion")
         else:
-            self.fuse = 1 if math_mode == MATH_BF16 else 0
+            self.fuse = 3 if math_mode == MATH_BF16 else 0
         self.n, self.cin, self.xh, self.xw, self.h, self.w = n, cin, xh, xw, h, w
         self.math_mode = math_mode
         self.ws_bytes = lib.mrfp_hrfp_plan_ws_bytes(handle)
@@ -251,8 +251,9 @@ def hrfp_chain(xp, convs, bns, h, w, x_add=None, want_out=True, want_dec=True, m
 
     Returns (OCout [+ x_add], OCout_dec) restricted to the requested outputs.  With `lazy_dec=True` the second
     value is an `HrfpDec` handle for `hrfp_plus_add` instead of a materialised tensor.
-    `fuse` (bf16 mode; None = on): 1 folds the forward resample + BatchNorm + ReLU between two convolutions into the next
-    convolution's operand producer (mrfp_hrfp_plan_set_fusion); 0 runs it as a separate pass."""
+    `fuse` (bf16 mode; None = all on): bit 0 folds the forward resample + BatchNorm + ReLU between two convolutions into
+    the next convolution's operand producer, bit 1 the BatchNorm backward in front of the dgrads of the non-replicating
+    stages (mrfp_hrfp_plan_set_fusion); 0: separate passes."""
     n, cin, xh, xw = xp.shape
     widths = tuple(c.out_channels for c in convs[:4])
     if (xh, xw) != (math.ceil(h / 4), math.ceil(w / 4)):

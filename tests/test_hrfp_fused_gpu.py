@@ -1,11 +1,12 @@
 """Operand-fused bf16 chain (csrc/conv_gather.cu) vs the same chain with the element-wise passes as separate kernels.
 
-Both compute the same arithmetic on the same bf16-rounded operands — A_k = ReLU(BN(nearest(Y_{k-1}))) is rounded to bf16
-once in either path, into shared memory in one and into HBM in the other — so they may differ only by the fp32
+Both compute the same arithmetic on the same bf16-rounded operands — A_k = ReLU(BN(nearest(Y_{k-1}))) (forward, fusion bit 0)
+and dY_k = BN-backward apply of (dA_{k+1}, Y_k) (backward of the non-replicating stages, bit 1) are rounded to bf16 once
+in either path, into shared memory in one and into HBM in the other — so the paths may differ only by the fp32
 accumulation order of the convolution (tap-major vs chunk-major), i.e. by isolated bf16 rounding flips that the later
-stages carry along.  The unfused path is the one
-pinned kernel by kernel in tests/test_hrfp_stage_gpu.py and tests/test_conv_tc_gpu.py; the fused path is also the
-default of every other chain test (oracle, reference fixtures, full size)."""
+stages carry along.  The unfused path is the one pinned
+kernel by kernel in tests/test_hrfp_stage_gpu.py and tests/test_conv_tc_gpu.py; the fused path (both bits) is the default
+of every other chain test (oracle, reference fixtures, full size)."""
 import math
 
 import numpy as np
@@ -39,9 +40,9 @@ def _l2(a, b):
 GEOMS = [(2, 48, 48), (3, 40, 56), (2, 60, 44), (2, 96, 80), (2, 200, 184)]
 
 
+@pytest.mark.parametrize("fuse", [1, 2, 3])
 @pytest.mark.parametrize("geom", GEOMS)
-def test_fused_equals_unfused(geom):
-    fuse = 1
+def test_fused_equals_unfused(geom, fuse):
     n, h, w = geom
     xh, xw = math.ceil(h / 4), math.ceil(w / 4)
     ws, gs = make_hrfp_params(11 + h)
@@ -61,13 +62,13 @@ def test_fused_equals_unfused(geom):
 
 def test_fusion_bits_are_reported_and_ignored_outside_bf16():
     from mrfp_b200.hrfp import HrfpPlan, MATH_BF16, MATH_TF32
-    assert HrfpPlan(2, 64, 12, 12, 48, 48, "cuda", MATH_BF16).fuse == 1
+    assert HrfpPlan(2, 64, 12, 12, 48, 48, "cuda", MATH_BF16).fuse == 3
     assert HrfpPlan(2, 64, 12, 12, 48, 48, "cuda", MATH_BF16, fuse=1).fuse == 1
     assert HrfpPlan(2, 64, 12, 12, 48, 48, "cuda", MATH_BF16, fuse=0).fuse == 0
-    assert HrfpPlan(2, 64, 12, 12, 48, 48, "cuda", MATH_TF32, fuse=1).fuse == 0
+    assert HrfpPlan(2, 64, 12, 12, 48, 48, "cuda", MATH_TF32, fuse=3).fuse == 0
 
 
-@pytest.mark.parametrize("fuse", [0, 1])
+@pytest.mark.parametrize("fuse", [0, 3])
 def test_vs_oracle_small(fuse):
     """Both paths against the numpy oracle (fp64 arithmetic) at the bf16 mode's stated tolerance."""
     n, h, w = 2, 48, 48

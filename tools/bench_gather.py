@@ -14,7 +14,7 @@ tap.restype = ctypes.c_int
 tap.argtypes = [ctypes.c_void_p] * 3 + [ctypes.c_int] * 6 + [ctypes.c_void_p] * 4
 gat = lib.mrfp_debug_conv3x3_gather_fwd
 gat.restype = ctypes.c_int
-gat.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int] + [ctypes.c_void_p] * 5 + [ctypes.c_int] * 6 + [ctypes.c_void_p]
+gat.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int] + [ctypes.c_void_p] * 5 + [ctypes.c_int] * 6 + [ctypes.c_void_p] * 4
 dbg_set = lib.mrfp_debug_gather_set
 dbg_set.restype = ctypes.c_int
 dbg_set.argtypes = [ctypes.c_int]
@@ -54,13 +54,20 @@ for k, (ci, co, dil, hw, shw) in enumerate(stages, start=1):
     out_g = torch.empty(n, hw, hw, co, device="cuda", dtype=torch.bfloat16)
     out_t = torch.empty_like(out_g)
     a = torch.relu(y.float().index_select(1, idx).index_select(2, idx) * stats[2, :ci] + stats[3, :ci]).to(torch.bfloat16).contiguous()
+    cnt = torch.zeros(hw + 64, dtype=torch.int32, device="cuda"); cnt[:hw] = 1
+    acc = torch.zeros(2 * 256, dtype=torch.float64, device="cuda")
     t_tap = timed(lambda: tap(a.data_ptr(), w.data_ptr(), out_t.data_ptr(), n, hw, hw, ci, co, dil, None, None, None, st))
-    line = f"stage {k}: {ci:3d}->{co:3d} d{dil} @{hw} <- {shw}: tap {t_tap:7.1f} us"
+    t_tap_s = timed(lambda: tap(a.data_ptr(), w.data_ptr(), out_t.data_ptr(), n, hw, hw, ci, co, dil, cnt.data_ptr(), cnt.data_ptr(),
+                                acc.data_ptr(), st))
+    line = f"stage {k}: {ci:3d}->{co:3d} d{dil} @{hw} <- {shw}: tap {t_tap:7.1f} / with stats {t_tap_s:7.1f} us"
     for f in flags:
         dbg_set(f)
         t = timed(lambda: gat(y.data_ptr(), shw, shw, idx32.data_ptr(), idx32.data_ptr(), stats.data_ptr(), w.data_ptr(),
-                              out_g.data_ptr(), n, hw, hw, ci, co, dil, st))
-        line += f" | dbg{f} {t:7.1f} us"
+                              out_g.data_ptr(), n, hw, hw, ci, co, dil, None, None, None, st))
+        acc.zero_()
+        ts = timed(lambda: gat(y.data_ptr(), shw, shw, idx32.data_ptr(), idx32.data_ptr(), stats.data_ptr(), w.data_ptr(),
+                               out_g.data_ptr(), n, hw, hw, ci, co, dil, cnt.data_ptr(), cnt.data_ptr(), acc.data_ptr(), st))
+        line += f" | dbg{f} {t:7.1f} / {ts:7.1f} us"
         if f == 0:
             err = float((out_g.float() - out_t.float()).norm() / out_t.float().norm())
             line += f" (rel l2 vs tap {err:.2e})"
