@@ -127,6 +127,7 @@ template <int TH, int TW, int MT, bool HMT> struct TileGeom {
 };
 
 struct EpiSmem {
+  uint64_t* add_full;         // [2] (ADD == 3 only, initialised with count 1): the add tile has landed in staging buffer b
   unsigned char* sOut;        // 2 staging tiles of kStageOutBytes, 1024-byte aligned
   float* s_wgt;               // [128]
   float* scratch;             // >= 8 * COUT floats, idle once every MMA of the CTA has retired (the operand ring)
@@ -136,12 +137,15 @@ struct EpiSmem {
 
 // Runs on warps 2..5 of the CTA (128 threads).  The tile walk (blockIdx.x, += gridDim.x, optional reversal) must match the
 // producer and MMA warps of the calling kernel.  ADD: 0 compiles the add_src path out; 1 fetches a chunk's 128 bytes of add_src
-// one chunk ahead into a second register set (64 registers); 2 keeps one set and fetches behind the chunk's packing (32).
+// one chunk ahead into a second register set (64 registers); 2 keeps one set and fetches behind the chunk's packing (32);
+// 3 brings the chunk's add tile by TMA into the very staging buffer the result will be packed into, one chunk ahead (no
+// registers, no exposed latency): each thread reads the 128 bytes of its own row and overwrites them with the sum.
 template <int COUT, typename T, int TH, int TW, int MT, bool HMT, int ADD>
 __device__ __forceinline__ void conv_epilogue(const EpiSmem& sm, uint32_t tmem_base, const CUtensorMap& tmap_out, int tiles_h,
                                               int tiles_w, int num_tiles, const int* __restrict__ cnt_h,
                                               const int* __restrict__ cnt_w, double* __restrict__ stat_acc, int rev,
-                                              const ConvBnFinalize& fin, const T* __restrict__ add_src, int H, int W) {
+                                              const ConvBnFinalize& fin, const T* __restrict__ add_src, int H, int W,
+                                              const CUtensorMap* tmap_add = nullptr) {
   using E = Elem<T>;
   using G = TileGeom<TH, TW, MT, HMT>;
   constexpr int kChunkC = 128 / (int)sizeof(T);                // channels of one 128-byte output chunk
@@ -173,7 +177,7 @@ __device__ __forceinline__ void conv_epilogue(const EpiSmem& sm, uint32_t tmem_b
   bool ad_nxt_ok = false, ad_ok = false;
   auto add_fetch = [&](int t0_, int jj_) {
     ad_nxt_ok = false;
-    if (!ADD || add_src == nullptr || t0_ >= num_tiles) return;
+    if (!ADD || ADD == 3 || add_src == nullptr || t0_ >= num_tiles) return;
     const int t_ = rev ? num_tiles - 1 - t0_ : t0_;
     const int tw_ = t_ % tiles_w, th_ = (t_ / tiles_w) % tiles_h, n_ = t_ / (tiles_w * tiles_h);
     const int mt_ = jj_ / kChunks, j_ = jj_ % kChunks;
@@ -186,6 +190,16 @@ __device__ __forceinline__ void conv_epilogue(const EpiSmem& sm, uint32_t tmem_b
     }
   };
   add_fetch(blockIdx.x, 0);
+  // ADD == 3: the leader loads chunk (t0_, jj_)'s tile of add_src into staging buffer `buf` (TMA zero-fills beyond the image)
+  auto add_issue = [&](int t0_, int jj_, int buf) {
+    if (t0_ >= num_tiles) return;
+    const int t_ = rev ? num_tiles - 1 - t0_ : t0_;
+    const int tw_ = t_ % tiles_w, th_ = (t_ / tiles_w) % tiles_h, n_ = t_ / (tiles_w * tiles_h);
+    const int mt_ = jj_ / kChunks, j_ = jj_ % kChunks;
+    mbar_expect_tx(&sm.add_full[buf], kStageOutBytes);
+    tma_load_4d(sOut + buf * kStageOutBytes, tmap_add, &sm.add_full[buf], j_ * kChunkC, G::w0(tw_) + G::dw(mt_), G::h0(th_) + G::dh(mt_), n_);
+  };
+  if (ADD == 3 && leader) add_issue(blockIdx.x, 0, 0);
   int it = 0;
   for (int t0 = blockIdx.x; t0 < num_tiles; t0 += gridDim.x, ++it) {
     const int t = rev ? num_tiles - 1 - t0 : t0;
@@ -204,10 +218,19 @@ __device__ __forceinline__ void conv_epilogue(const EpiSmem& sm, uint32_t tmem_b
         if (jj + 1 < MT * kChunks) add_fetch(t0, jj + 1); else add_fetch(t0 + gridDim.x, 0);
       }
       if (ADD == 2) ad_ok = ad_nxt_ok;
-      unsigned char* ob = sOut + ((MT * kChunks) % 2 == 0 ? (jj & 1) : ((it * MT * kChunks + jj) & 1)) * kStageOutBytes;
+      const int bsel = (MT * kChunks) % 2 == 0 ? (jj & 1) : ((it * MT * kChunks + jj) & 1);
+      unsigned char* ob = sOut + bsel * kStageOutBytes;
       const uint32_t ob_u = smem_u32(ob);
-      // the TMA store that last read this staging buffer (two chunks ago) must have drained
-      if (leader) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+      if (ADD == 3) {
+        // the store of the previous chunk must have read the OTHER buffer before the next chunk's add tile lands in it
+        if (leader) {
+          asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+          if (jj + 1 < MT * kChunks) add_issue(t0, jj + 1, bsel ^ 1); else add_issue(t0 + gridDim.x, 0, bsel ^ 1);
+        }
+      } else {
+        // the TMA store that last read this staging buffer (two chunks ago) must have drained
+        if (leader) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+      }
       epi_bar_sync();
       if (stat_acc) sts_f32(s_wgt_u + 4u * (uint32_t)r, (float)(cnt_h[h0 + G::dh(mt) + hl] * cnt_w[w0 + G::dw(mt) + wl]));   // 0 outside the image (zero-padded tables)
       const uint32_t tcol = (uint32_t)((acc * MT + mt) * COUT + j * kChunkC);
@@ -216,7 +239,22 @@ __device__ __forceinline__ void conv_epilogue(const EpiSmem& sm, uint32_t tmem_b
         for (int half = 0; half < 2; ++half) {
           uint32_t v[32];
           tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + tcol + (uint32_t)(half * 32), v);
-          if (ad_ok) {                           // summed in fp32, rounded once
+          if (ADD == 3) {                        // this row's half of the add tile, from the buffer the sum goes back into
+            if (half == 0) mbar_wait(&sm.add_full[bsel], (uint32_t)(((it * MT * kChunks + jj) >> 1) & 1));
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              const int chunk = half * 4 + c;
+              uint32_t w4[4];
+              asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                           : "=r"(w4[0]), "=r"(w4[1]), "=r"(w4[2]), "=r"(w4[3]) : "r"(ob_u + (uint32_t)(r * 128 + ((chunk ^ (r & 7)) << 4))));
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                v[c * 8 + 2 * i] = __float_as_uint(__uint_as_float(v[c * 8 + 2 * i]) + __uint_as_float(w4[i] << 16));
+                v[c * 8 + 2 * i + 1] = __float_as_uint(__uint_as_float(v[c * 8 + 2 * i + 1]) + __uint_as_float(w4[i] & 0xffff0000u));
+              }
+            }
+          }
+          if (ADD != 3 && ad_ok) {               // summed in fp32, rounded once
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
               const uint4 a4 = ad_use[half * 4 + c];

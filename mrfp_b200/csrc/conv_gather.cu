@@ -39,7 +39,7 @@ constexpr int kSmemLimit = 232448;             // 227 KB opt-in maximum per CTA
 constexpr int kMaxBStages = 6;
 constexpr int kGatherFwd = 0, kGatherBwd = 1;
 // staging tiles, row weights, barriers at compile-time offsets; rounded so that everything behind stays 1024-aligned
-constexpr int kFixedBytes = (2 * kStageOutBytes + 512 + 8 * (2 * kMaxAStages + 2 * kMaxBStages + 4) + 16 + 1023) / 1024 * 1024;
+constexpr int kFixedBytes = (2 * kStageOutBytes + 512 + 8 * (2 * kMaxAStages + 2 * kMaxBStages + 6) + 16 + 1023) / 1024 * 1024;
 
 template <int COUT> struct GCfg {
   static constexpr int kMT = COUT == 256 ? 1 : 2;
@@ -98,7 +98,7 @@ __device__ __forceinline__ void ld8s(uint32_t a, float (&v)[8]) {
 template <int COUT, int MODE, bool ADD>
 __global__ void __launch_bounds__(kGThreads, 1)
 conv3x3_gather_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_out,
-                      const GatherArgs ga, int CIN, int dil, int boxw, int tiles_h, int tiles_w, int num_tiles,
+                      const __grid_constant__ CUtensorMap tmap_add, const GatherArgs ga, int CIN, int dil, int boxw, int tiles_h, int tiles_w, int num_tiles,
                       const int* __restrict__ cnt_h, const int* __restrict__ cnt_w, double* __restrict__ stat_acc, int rev,
                       const ConvBnFinalize fin, const __nv_bfloat16* __restrict__ add_src, int H, int W, int nA, int nB,
                       int a_stage_bytes, int tab_bytes) {
@@ -118,7 +118,8 @@ conv3x3_gather_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_c
   uint64_t* empty_b = full_b + kMaxBStages;
   uint64_t* tmem_full = empty_b + kMaxBStages;
   uint64_t* tmem_empty = tmem_full + 2;
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  uint64_t* add_full = tmem_empty + 2;                                         // ADD: the epilogue's add tile has landed
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(add_full + 2);
   unsigned char* sB = smem + kFixedBytes;                                      // nB weight tiles
   unsigned char* sA = sB + nB * C::kBTileBytes;                                // nA stages of a_stage_bytes (1024-aligned)
   unsigned char* sG = sA + nA * a_stage_bytes;                                 // kGatherBwd: one stage of gradient pieces
@@ -133,9 +134,10 @@ conv3x3_gather_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_c
   if (threadIdx.x == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap_w)) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap_out)) : "memory");
+    if (ADD) asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap_add)) : "memory");
     for (int i = 0; i < nA; ++i) { mbar_init(&full_a[i], kProducers); mbar_init(&empty_a[i], 1); }
     for (int i = 0; i < nB; ++i) { mbar_init(&full_b[i], 1); mbar_init(&empty_b[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 4); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 4); mbar_init(&add_full[i], 1); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -213,8 +215,9 @@ conv3x3_gather_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_c
     // ===================== epilogue (warps 2..5): conv_common.cuh =====================
     EpiSmem es;
     es.sOut = sOut; es.s_wgt = s_wgt; es.scratch = reinterpret_cast<float*>(sA); es.tmem_full = tmem_full; es.tmem_empty = tmem_empty;
-    conv_epilogue<COUT, T, kGTileH, kGSubW, MT, true, ADD ? 2 : 0>(es, tmem_base, tmap_out, tiles_h, tiles_w, num_tiles, cnt_h, cnt_w,
-                                                           stat_acc, rev, fin, add_src, H, W);
+    es.add_full = add_full;
+    conv_epilogue<COUT, T, kGTileH, kGSubW, MT, true, ADD ? 3 : 0>(es, tmem_base, tmap_out, tiles_h, tiles_w, num_tiles, cnt_h, cnt_w,
+                                                                   stat_acc, rev, fin, add_src, H, W, &tmap_add);
   } else {
     // ===================== operand producers (warps 6..13) =====================
     const int pt = threadIdx.x - 192;            // 0..255
@@ -444,7 +447,7 @@ int launch(const GatherArgs& ga, const void* wpack, void* out, int N, int H, int
   ConvMaps local;
   local.valid = 0;
   ConvMaps* m = cache ? cache : &local;
-  if (!m->valid || m->key[0] != nullptr || m->key[1] != wpack || m->key[2] != out) {
+  if (!m->valid || m->key[0] != add_src || m->key[1] != wpack || m->key[2] != out) {
     m->valid = 0;
     {
       const cuuint64_t dims[2] = {(cuuint64_t)cin, (cuuint64_t)9 * COUT};
@@ -460,7 +463,16 @@ int launch(const GatherArgs& ga, const void* wpack, void* out, int N, int H, int
       int rc = conv_make_map(&m->out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, out, 4, dims, strides, box);
       if (rc) return rc;
     }
-    m->key[0] = nullptr; m->key[1] = wpack; m->key[2] = out;
+    if (add_src) {       // the tile of add_src that an output chunk is summed with: same geometry as the output (kept in m->in)
+      const cuuint64_t dims[4] = {(cuuint64_t)COUT, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+      const cuuint64_t strides[3] = {(cuuint64_t)COUT * 2, (cuuint64_t)W * COUT * 2, (cuuint64_t)H * W * COUT * 2};
+      const cuuint32_t box[4] = {64, kGSubW, kGTileH, 1};
+      int rc = conv_make_map(&m->in, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, add_src, 4, dims, strides, box);
+      if (rc) return rc;
+    } else {
+      m->in = m->out;
+    }
+    m->key[0] = add_src; m->key[1] = wpack; m->key[2] = out;
     m->valid = 1;
   }
   DeviceInfo di;
@@ -474,7 +486,7 @@ int launch(const GatherArgs& ga, const void* wpack, void* out, int N, int H, int
   const int grid = num_tiles < di.sm_count ? num_tiles : di.sm_count;
   auto kern = conv3x3_gather_kernel<COUT, MODE, ADD>;
   MRFP_SMEM_OPT_IN(kern, kSmemLimit, di.device);
-  launch_k(kern, dim3(grid), dim3(kGThreads), (size_t)sp.smem, stream, m->w, m->out, ga, cin, dil, sp.boxw, tiles_h, tiles_w,
+  launch_k(kern, dim3(grid), dim3(kGThreads), (size_t)sp.smem, stream, m->w, m->out, m->in, ga, cin, dil, sp.boxw, tiles_h, tiles_w,
            num_tiles, cnt_h, cnt_w, stat_acc, rev, fin, static_cast<const __nv_bfloat16*>(add_src), H, W, sp.nA, sp.nB, sp.a_stage,
            sp.tab_bytes);
   MRFP_CUDA_TRY(cudaGetLastError());
