@@ -101,7 +101,7 @@ def run_reference(args):
     print(json.dumps(line))
 
 
-def traffic_from_profiles(kernel_substr, file_hints=("",), prefixes=("R2_", "r9_", "r5_", "r3_")):
+def traffic_from_profiles(kernel_substr, file_hints=("",), prefixes=("R2b_", "R2_", "r9_", "r5_", "r3_")):
     """dram__bytes_read.sum + dram__bytes_write.sum of one launch of the kernel, read from the newest committed
     `ncu --set full` export under profiles/ (`ncu -i ... --page raw --csv`: header row, unit row, one value row)."""
     import csv
@@ -595,30 +595,94 @@ def run_ours(args):
     except Exception as e_:          # noqa: BLE001
         roof_in = {"error": repr(e_)[:200]}
 
-    # tcgen05 conv kernels of the chain, forward shapes (debug hook = the same kernel the chain launches)
+    # tcgen05 conv kernels of the chain at the step's shapes, each through the debug hook of the kernel the chain launches
+    # for it: forward stage 0 = conv3x3_tc_kernel on the stem feature; forward stages 1-7 = conv3x3_gather_kernel<fwd> (the
+    # resample + BN + ReLU of the previous stage built into the operand, BN statistics in the epilogue); dgrads of the
+    # up-sampling stages 0-3 = conv3x3_tc_kernel on dY; dgrads of stages 4-7 = conv3x3_gather_kernel<bwd> (BN-backward apply
+    # built into the operand; stage 4 also adds the OCout_dec gradient)
     import ctypes
     fn = lib.mrfp_debug_conv3x3_bf16
     fn.restype = ctypes.c_int
     fn.argtypes = [ctypes.c_void_p] * 3 + [ctypes.c_int] * 6 + [ctypes.c_void_p] * 4
+    gfn = lib.mrfp_debug_conv3x3_gather_fwd
+    gfn.restype = ctypes.c_int
+    gfn.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int] + [ctypes.c_void_p] * 5 + [ctypes.c_int] * 6 + [ctypes.c_void_p] * 4
+    bfn = lib.mrfp_debug_conv3x3_gather_bwd
+    bfn.restype = ctypes.c_int
+    bfn.argtypes = ([ctypes.c_void_p] * 2 + [ctypes.c_int] * 2 + [ctypes.c_void_p] * 5 + [ctypes.c_double] + [ctypes.c_void_p] * 2 +
+                    [ctypes.c_int] * 6 + [ctypes.c_void_p] * 2)
     plan = H.get_plan(n, 64, XH, XW, H_IMG, W_IMG, dev, H.MATH_BF16)
-    conv_rows, conv_time, conv_flop = [], 0.0, 0.0
+
+    def nearest_idx(src, dst):          # ATen's rule in float32 (size= form; the tables only shape the access pattern here)
+        sc = torch.tensor(src / dst, dtype=torch.float32)
+        return torch.clamp(torch.floor(torch.arange(dst, dtype=torch.float32) * sc).to(torch.int64), max=src - 1)
+
+    def padded_ones(size):
+        c = torch.zeros((size + 15) // 16 * 16 + 16, dtype=torch.int32, device=dev)
+        c[:size] = 1
+        return c
+
+    def ok(rc):
+        assert rc == 0, f"conv debug hook returned {rc}"
+
+    conv_rows, dgrad_rows, conv_time, conv_flop = [], [], 0.0, 0.0
+    stats_t = torch.zeros(4, 256, device=dev)
+    stats_t[1] = 1.0; stats_t[2] = 0.5 + torch.rand(256, device=dev); stats_t[3] = 0.2 * torch.randn(256, device=dev)
+    gamma_t = torch.ones(256, device=dev)
     for k, (cin, cout, dil, ch, cw, oh, ow) in enumerate(plan.stages):
-        a_in = torch.randn(n, ch, cw, cin, device=dev).to(torch.bfloat16)
+        fl = 2.0 * n * ch * cw * cout * 9 * cin
         wp = (torch.randn(9, cout, cin, device=dev) * (2.0 / (9 * cin)) ** 0.5).to(torch.bfloat16)
         y = torch.empty(n, ch, cw, cout, device=dev, dtype=torch.bfloat16)
-        t = time_launch(lambda: fn(a_in.data_ptr(), wp.data_ptr(), y.data_ptr(), n, ch, cw, cin, cout, dil, None, None, None, st), 5)
-        fl = 2.0 * n * ch * cw * cout * 9 * cin
-        conv_rows.append({"stage": k, "cin": cin, "cout": cout, "hw": [ch, cw], "us": t * 1e3, "tflops": fl / t / 1e9})
+        cnth, cntw = padded_ones(ch), padded_ones(cw)
+        acc_t = torch.zeros(2 * 256, dtype=torch.float64, device=dev)
+        if k == 0:
+            a_in = torch.randn(n, ch, cw, cin, device=dev).to(torch.bfloat16)
+            t = time_launch(lambda: ok(fn(a_in.data_ptr(), wp.data_ptr(), y.data_ptr(), n, ch, cw, cin, cout, dil, cnth.data_ptr(),
+                                          cntw.data_ptr(), acc_t.data_ptr(), st)), 5)
+            kern = f"conv3x3_tc_kernel<{cout}>"
+        else:
+            sh, sw = plan.stages[k - 1][3], plan.stages[k - 1][4]
+            a_in = torch.randn(n, sh, sw, cin, device=dev).to(torch.bfloat16)
+            ih, iw = nearest_idx(sh, ch).to(torch.int32).to(dev), nearest_idx(sw, cw).to(torch.int32).to(dev)
+            t = time_launch(lambda: ok(gfn(a_in.data_ptr(), sh, sw, ih.data_ptr(), iw.data_ptr(), stats_t.data_ptr(), wp.data_ptr(),
+                                           y.data_ptr(), n, ch, cw, cin, cout, dil, cnth.data_ptr(), cntw.data_ptr(), acc_t.data_ptr(), st)), 5)
+            kern = f"conv3x3_gather_kernel<{cout}, fwd>"
+        conv_rows.append({"stage": k, "kernel": kern, "cin": cin, "cout": cout, "hw": [ch, cw], "us": t * 1e3, "tflops": fl / t / 1e9})
         conv_time += t; conv_flop += fl
-        del a_in, wp, y
-    top = max(conv_rows, key=lambda r: r["us"])
-    roofline = {"kernel": f"conv3x3_tc_kernel<{top['cout']}> stage {top['stage']} ({top['cin']}->{top['cout']} @{top['hw'][0]}x{top['hw'][1]})",
+        del a_in, y
+        # dgrad of the stage: cout channels in, cin channels out, same resolution and FLOPs
+        wpb = (torch.randn(9, cin, cout, device=dev) * (2.0 / (9 * cout)) ** 0.5).to(torch.bfloat16)
+        gout = torch.empty(n, ch, cw, cin, device=dev, dtype=torch.bfloat16)
+        if k <= 3:
+            dy = torch.randn(n, ch, cw, cout, device=dev).to(torch.bfloat16)
+            t = time_launch(lambda: ok(fn(dy.data_ptr(), wpb.data_ptr(), gout.data_ptr(), n, ch, cw, cout, cin, dil, None, None, None, st)), 5)
+            kern = f"conv3x3_tc_kernel<{cin}>"
+            del dy
+        else:
+            yk = torch.randn(n, ch, cw, cout, device=dev).to(torch.bfloat16)
+            da = torch.randn(n, oh, ow, cout, device=dev).to(torch.bfloat16)
+            ih, iw = nearest_idx(ch, oh), nearest_idx(cw, ow)
+            loh = torch.searchsorted(ih, torch.arange(ch + 1)).to(torch.int32).to(dev)
+            low = torch.searchsorted(iw, torch.arange(cw + 1)).to(torch.int32).to(dev)
+            add = torch.randn(n, ch, cw, cin, device=dev).to(torch.bfloat16) if k == 4 else None
+            t = time_launch(lambda: ok(bfn(yk.data_ptr(), da.data_ptr(), oh, ow, loh.data_ptr(), low.data_ptr(), stats_t.data_ptr(),
+                                        gamma_t.data_ptr(), acc_t.data_ptr(), float(n * oh * ow), wpb.data_ptr(), gout.data_ptr(), n, ch, cw,
+                                        cout, cin, dil, None if add is None else add.data_ptr(), st)), 5)
+            kern = f"conv3x3_gather_kernel<{cin}, bwd{', add' if k == 4 else ''}>"
+            del yk, da, add
+        dgrad_rows.append({"stage": k, "kernel": kern, "cin": cout, "cout": cin, "hw": [ch, cw], "us": t * 1e3, "tflops": fl / t / 1e9})
+        del wp, wpb, gout
+    top = max(conv_rows + dgrad_rows, key=lambda r: r["us"])
+    is_dgrad = top in dgrad_rows
+    hint = ("gather_d4",) if is_dgrad else ("gather_s4",)
+    roofline = {"kernel": f"{top['kernel']} stage {top['stage']} {'dgrad' if is_dgrad else 'forward'} "
+                          f"({top['cin']}->{top['cout']} @{top['hw'][0]}x{top['hw'][1]}) — the longest single launch of the step",
                 "bound": "tensor", "achieved": top["tflops"], "peak": tf_peak, "unit": "TFLOP/s", "frac": top["tflops"] / tf_peak,
-                "traffic": traffic_from_profiles("conv3x3_tc_kernel", ("conv_s4", "conv_d1"))[0] if top["stage"] == 4 else None,   # dram read + write bytes per launch
-                "traffic_source": "%s (ncu --set full, stage 4 forward: A 604 MB read once, Y 302 MB written)"
-                                  % traffic_from_profiles("conv3x3_tc_kernel", ("conv_s4", "conv_d1"))[1],
+                "traffic": traffic_from_profiles("conv3x3_gather_kernel", hint)[0],   # dram read + write bytes per launch
+                "traffic_source": "%s (ncu --set full, one launch of this kernel inside the step)"
+                                  % traffic_from_profiles("conv3x3_gather_kernel", hint)[1],
                 "peak_source": peak_src, "peak_sustained": tf_sustained,
-                "all_conv_fwd_tflops": conv_flop / conv_time / 1e9, "per_stage": conv_rows}
+                "all_conv_fwd_tflops": conv_flop / conv_time / 1e9, "per_stage": conv_rows, "per_stage_dgrad": dgrad_rows}
 
     # chain-level numbers through the public API
     def t_api(fn_, iters=5):
@@ -657,10 +721,11 @@ def run_ours(args):
 
     # kernels launched per step (ours; memsets and the host's two library GEMMs W2 . dec1 / its backward excluded):
     # NP+ call 2 fwd + bwd (call 1 is folded into the chain: +1 coefficient block each way); HRFP fwd 1 weight pack + 1
-    # NCHW->NHWC + 8 conv (BN finalised by the last CTA) + 7 BN/ReLU/resample + 1 NHWC->NCHW epilogue (OCout + x); tail
-    # through the classifier 1 fwd + 1 bwd + 1 bilinear-transpose gather; HRFP bwd 1 NCHW->NHWC + 8 x (2 BN-bwd + conv) +
-    # 1 NHWC->NCHW
-    launches_per_step = 2 + (1 + 1 + 1 + 8 + 7 + 1) + 3 + (1 + 1 + 24 + 1)
+    # NCHW->NHWC + 8 conv (stages 1-7 build their operand from the previous conv output, BN finalised by the last CTA) + 1
+    # NHWC->NCHW epilogue (OCout + x); tail through the classifier 1 fwd + 1 bwd + 1 bilinear-transpose gather; HRFP bwd
+    # 1 NCHW->NHWC + 8 BN-bwd reductions + 4 BN-bwd apply passes (stages 0-3; stages 4-7 build dY inside the dgrad) + 8 dgrad
+    # + 1 NHWC->NCHW
+    launches_per_step = 2 + (1 + 1 + 1 + 8 + 1) + 3 + (1 + 1 + 8 + 4 + 8 + 1)
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16 (HRFP tensor-core operands, fp32 accumulate) / f32 (NP+)", "data": "synthetic", "config": CONFIG,

@@ -62,7 +62,6 @@ struct GatherArgs {
   int c_real;                  // bwd: channels of the module's BatchNorm (stored channels beyond it: dY = 0)
 };
 
-__device__ int g_gather_dbg = 0;   // TEMP ablation: 1 = producers idle, 2 = no MMAs, 8 = no transform, 16 = no copies
 __device__ __forceinline__ void prod_bar_sync() { asm volatile("bar.sync 2, 256;" ::: "memory"); }
 // explicit shared-space accesses by 32-bit address (see conv_common.cuh)
 __device__ __forceinline__ int lds32(uint32_t a) { int v; asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
@@ -149,7 +148,6 @@ conv3x3_gather_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_c
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_ptr;
   pdl_sync();                                 // set-up above overlaps the previous kernel's tail
-  const int dbg = g_gather_dbg;
 
   if (warp == 0) {
     // ===================== weight TMA producer (whole warp walks, one elected lane issues) =====================
@@ -193,7 +191,6 @@ conv3x3_gather_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_c
             // the tap's view starts (ty * d * boxw + tx * d) box pixels into the halo tile; descriptors advance in 16-byte units
             const uint64_t da = da_stage + (uint64_t)(((tap / 3) * dil * boxw + (tap % 3) * dil) * 8);
             const uint64_t db = make_desc_sw128(sB_u + bs * C::kBTileBytes);
-            if (!(dbg & 2))
 #pragma unroll
             for (int k = 0; k < 4; ++k)
 #pragma unroll
@@ -287,7 +284,7 @@ conv3x3_gather_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_c
         const int c0 = i_kc * kBlockK + piece * 8;
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-          if (pl + kPxLanes * u < npix && !(dbg & 17)) {
+          if (pl + kPxLanes * u < npix) {
             const int off = lds32(tab + (uint32_t)(kEnt * kPxLanes * u));
             const __nv_bfloat16* src = off >= 0 ? ga.y + (size_t)off * CIN + c0 : ga.y;
             // an identically-zero pixel: source size 0 zero-fills the 16 bytes
@@ -327,7 +324,6 @@ conv3x3_gather_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_c
         float sc[8], sh[8];
         ld8s(const_u + 4u * (uint32_t)(j_kc * kBlockK + piece * 8), sc);
         ld8s(const_u + 4u * (uint32_t)(CIN + j_kc * kBlockK + piece * 8), sh);
-        if (!(dbg & 9))
 #pragma unroll
         for (int u0 = 0; u0 < U; u0 += 5) {        // up to five pixels per batch: their shared-memory reads overlap
           uint4 v[5];
@@ -357,7 +353,6 @@ conv3x3_gather_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_c
         ld8s(cb, sc); ld8s(cb + 4u * (uint32_t)CIN, sh); ld8s(cb + 8u * (uint32_t)CIN, cP); ld8s(cb + 12u * (uint32_t)CIN, cQ);
         ld8s(cb + 16u * (uint32_t)CIN, cR);
         const uint32_t g0 = sG_u + my_off;
-        if (!(dbg & 9))
 #pragma unroll
         for (int u0 = 0; u0 < U; u0 += 3) {        // three pixels per batch (six shared-memory reads in flight)
           uint4 vy[3], vg[3];
@@ -557,11 +552,18 @@ int conv3x3_gather_bwd(const void* y, const void* dA, int OH, int OW, const int*
 
 }  // namespace mrfp
 
-// test / bench hooks (not part of the public header): single convolutions on caller-provided buffers
+// test / bench hooks (not part of the public header): single convolutions on caller-provided buffers — the same kernels
+// the chain launches
 extern "C" int mrfp_debug_conv3x3_gather_fwd(const void* y_prev, int SH, int SW, const int* idx_h, const int* idx_w,
                                              const float* stats_prev, const void* wpack, void* out, int N, int H, int W, int cin,
                                              int cout, int dil, const int* cnt_h, const int* cnt_w, double* stat_acc, void* stream) {
   return mrfp::conv3x3_gather_fwd(y_prev, SH, SW, idx_h, idx_w, stats_prev, wpack, out, N, H, W, cin, cout, dil, cnt_h, cnt_w,
                                   stat_acc, (cudaStream_t)stream, false, nullptr, nullptr);
 }
-extern "C" int mrfp_debug_gather_set(int v) { return (int)cudaMemcpyToSymbol(mrfp::g_gather_dbg, &v, sizeof(int)); }
+extern "C" int mrfp_debug_conv3x3_gather_bwd(const void* y, const void* dA, int OH, int OW, const int* lo_h, const int* lo_w,
+                                             const float* stats, const float* gamma, const double* acc, double count, const void* wpack,
+                                             void* out, int N, int H, int W, int cin, int cout, int dil, const void* add_src,
+                                             void* stream) {
+  return mrfp::conv3x3_gather_bwd(y, dA, OH, OW, lo_h, lo_w, stats, gamma, acc, count, cin, wpack, out, N, H, W, cin, cout, dil,
+                                  (cudaStream_t)stream, false, add_src, nullptr);
+}

@@ -67,3 +67,53 @@ def test_conv_without_stats_full_size_linearity():
     torch.backends.cudnn.allow_tf32 = False
     ref = F.conv2d(xb, wb, padding=1)
     assert (got - ref).abs().max().item() <= 2 ** -8 * ref.abs().max().item() + 1e-5
+
+
+def _nearest_idx(src, dst):
+    scale = torch.tensor(src / dst, dtype=torch.float32)
+    return torch.clamp(torch.floor(torch.arange(dst, dtype=torch.float32) * scale).to(torch.int64), max=src - 1).cuda()
+
+
+@pytest.mark.parametrize("cin,cout,dil", [(64, 64, 1), (64, 64, 2), (64, 128, 2), (128, 256, 2), (256, 128, 1), (128, 64, 1)])
+@pytest.mark.parametrize("geom", [(2, 16, 16, 16, 16), (2, 20, 37, 17, 31), (1, 50, 61, 60, 75), (2, 33, 24, 28, 20)])
+def test_gathered_conv_matches_torch(cin, cout, dil, geom):
+    """conv3x3_gather_kernel alone (csrc/conv_gather.cu): Conv2d(ReLU(scale * nearest(Y_prev) + shift)) with the operand
+    built on chip, against torch on the same bf16 operand (rounded once, like the materialised A_k of the unfused path):
+    up-sampling, down-sampling and identity resamples, ragged tiles, and the BN statistics of the stored output."""
+    import ctypes as C
+    from mrfp_b200 import _lib
+    n, h, w, sh, sw = geom
+    torch.manual_seed(cin + cout + dil + h + sh)
+    fn = _lib.load().mrfp_debug_conv3x3_gather_fwd
+    fn.restype = C.c_int
+    fn.argtypes = [C.c_void_p, C.c_int, C.c_int] + [C.c_void_p] * 5 + [C.c_int] * 6 + [C.c_void_p] * 4
+    y = torch.randn(n, sh, sw, cin, device="cuda").to(torch.bfloat16)
+    wt = torch.randn(cout, cin, 3, 3, device="cuda") * (2.0 / (9 * cin)) ** 0.5
+    wp = wt.permute(2, 3, 0, 1).reshape(9, cout, cin).contiguous().to(torch.bfloat16)
+    stats = torch.zeros(4, 256, device="cuda")
+    stats[2, :cin] = 0.5 + torch.rand(cin, device="cuda"); stats[3, :cin] = 0.3 * torch.randn(cin, device="cuda")
+    ih, iw = _nearest_idx(sh, h), _nearest_idx(sw, w)
+    ih32, iw32 = ih.to(torch.int32).contiguous(), iw.to(torch.int32).contiguous()
+    cnt_h = torch.zeros(((h + 15) // 16 + 1) * 16, dtype=torch.int32, device="cuda")
+    cnt_w = torch.zeros(((w + 15) // 16 + 1) * 16, dtype=torch.int32, device="cuda")
+    cnt_h[:h] = torch.randint(0, 3, (h,), device="cuda", dtype=torch.int32)
+    cnt_w[:w] = torch.randint(0, 3, (w,), device="cuda", dtype=torch.int32)
+    acc = torch.zeros(2, 256, device="cuda", dtype=torch.float64)
+    out = torch.full((n, h, w, cout), float("nan"), device="cuda", dtype=torch.bfloat16)
+    rc = fn(y.data_ptr(), sh, sw, ih32.data_ptr(), iw32.data_ptr(), stats.data_ptr(), wp.data_ptr(), out.data_ptr(), n, h, w, cin,
+            cout, dil, cnt_h.data_ptr(), cnt_w.data_ptr(), acc.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    assert rc == 0, rc
+    torch.cuda.synchronize()
+    a = torch.relu(torch.addcmul(stats[3, :cin], y.float().index_select(1, ih).index_select(2, iw), stats[2, :cin]))
+    a = a.to(torch.bfloat16).permute(0, 3, 1, 2).double()                    # fmaf(scale, y, shift) -> one bf16 rounding
+    wb = wp.reshape(3, 3, cout, cin).permute(2, 3, 0, 1).double()
+    ref = F.conv2d(a, wb, padding=dil, dilation=dil)
+    got = out.permute(0, 3, 1, 2).double()
+    assert not torch.isnan(got).any()
+    # bf16 output rounding (2^-9 relative) + the rare operand that rounds the other way (fma vs mul-add of the reference)
+    assert (got - ref).abs().max().item() <= 2 ** -7 * ref.abs().max().item() + 1e-6
+    assert float((got - ref).norm() / ref.norm()) <= 3e-3
+    wgt = (cnt_h[:h].double()[:, None] * cnt_w[:w].double()[None, :])[None, None]
+    s1 = (got * wgt).sum((0, 2, 3)); s2 = (got * got * wgt).sum((0, 2, 3))
+    assert torch.allclose(acc[0, :cout], s1, rtol=1e-4, atol=1e-4 * s1.abs().max().item())
+    assert torch.allclose(acc[1, :cout], s2, rtol=1e-4, atol=1e-4 * s2.abs().max().item())

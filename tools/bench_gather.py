@@ -1,7 +1,7 @@
-"""Gathered forward convolutions (csrc/conv_gather.cu) of the 7 fused stages at batch 8, alone: time, parity against
-`tap conv(ReLU(BN(nearest(Y))))` computed with torch + the tap kernel, and the producer / MMA ablations.
+"""Gathered forward convolutions (csrc/conv_gather.cu) of the 7 fused stages at batch 8, alone: time without / with the BN
+statistics in the epilogue, next to the tap kernel on the materialised operand, and parity between the two.
 
-    python tools/bench_gather.py [dbg ...]      dbg: 0 = full kernel, 1 = producers idle, 2 = no MMAs
+    python tools/bench_gather.py
 """
 import ctypes, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -15,9 +15,6 @@ tap.argtypes = [ctypes.c_void_p] * 3 + [ctypes.c_int] * 6 + [ctypes.c_void_p] * 
 gat = lib.mrfp_debug_conv3x3_gather_fwd
 gat.restype = ctypes.c_int
 gat.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int] + [ctypes.c_void_p] * 5 + [ctypes.c_int] * 6 + [ctypes.c_void_p] * 4
-dbg_set = lib.mrfp_debug_gather_set
-dbg_set.restype = ctypes.c_int
-dbg_set.argtypes = [ctypes.c_int]
 
 n = int(os.environ.get("MRFP_PROFILE_N", "8"))
 # (cin, cout, dil, conv resolution, source resolution): stages 1..7 of deepv3.py:320-327 at a 768^2 crop
@@ -25,7 +22,6 @@ stages = [(64, 64, 1, 231, 192), (64, 128, 2, 277, 231), (128, 256, 2, 332, 277)
           (64, 64, 2, 321, 384), (64, 64, 2, 256, 321)]
 flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 st = torch.cuda.current_stream().cuda_stream
-flags = [int(a) for a in sys.argv[1:]] or [0]
 
 
 def timed(fn):
@@ -60,17 +56,13 @@ for k, (ci, co, dil, hw, shw) in enumerate(stages, start=1):
     t_tap_s = timed(lambda: tap(a.data_ptr(), w.data_ptr(), out_t.data_ptr(), n, hw, hw, ci, co, dil, cnt.data_ptr(), cnt.data_ptr(),
                                 acc.data_ptr(), st))
     line = f"stage {k}: {ci:3d}->{co:3d} d{dil} @{hw} <- {shw}: tap {t_tap:7.1f} / with stats {t_tap_s:7.1f} us"
-    for f in flags:
-        dbg_set(f)
+    if True:
         t = timed(lambda: gat(y.data_ptr(), shw, shw, idx32.data_ptr(), idx32.data_ptr(), stats.data_ptr(), w.data_ptr(),
                               out_g.data_ptr(), n, hw, hw, ci, co, dil, None, None, None, st))
         acc.zero_()
         ts = timed(lambda: gat(y.data_ptr(), shw, shw, idx32.data_ptr(), idx32.data_ptr(), stats.data_ptr(), w.data_ptr(),
                                out_g.data_ptr(), n, hw, hw, ci, co, dil, cnt.data_ptr(), cnt.data_ptr(), acc.data_ptr(), st))
-        line += f" | dbg{f} {t:7.1f} / {ts:7.1f} us"
-        if f == 0:
-            err = float((out_g.float() - out_t.float()).norm() / out_t.float().norm())
-            line += f" (rel l2 vs tap {err:.2e})"
-    dbg_set(0)
+        err = float((out_g.float() - out_t.float()).norm() / out_t.float().norm())
+        line += f" | gathered {t:7.1f} / {ts:7.1f} us (rel l2 vs tap {err:.2e})"
     print(line, flush=True)
     del y, w, a, out_g, out_t

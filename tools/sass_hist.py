@@ -33,7 +33,7 @@ def main():
         if m:
             cur = kernels.setdefault(m.group(1), collections.Counter())
             continue
-        m = re.match(r"\s*/\*[0-9a-f]{4}\*/\s+(?:@!?U?P\d+\s+)?([A-Z][A-Z0-9_]*)", line)
+        m = re.match(r"\s*/\*[0-9a-f]{4,6}\*/\s+(?:@!?U?P\d+\s+)?([A-Z][A-Z0-9_]*)", line)
         if m and cur is not None:
             cur[m.group(1)] += 1
     dm = demangle(list(kernels))
