@@ -598,8 +598,8 @@ def run_ours(args):
     # tcgen05 conv kernels of the chain at the step's shapes, each through the debug hook of the kernel the chain launches
     # for it: forward stage 0 = conv3x3_tc_kernel on the stem feature; forward stages 1-7 = conv3x3_gather_kernel<fwd> (the
     # resample + BN + ReLU of the previous stage built into the operand, BN statistics in the epilogue); dgrads of the
-    # up-sampling stages 0-3 = conv3x3_tc_kernel on dY; dgrads of stages 4-7 = conv3x3_gather_kernel<bwd> (BN-backward apply
-    # built into the operand; stage 4 also adds the OCout_dec gradient)
+    # wide up-sampling stages 2-3 = conv3x3_tc_kernel on dY; the other dgrads = conv3x3_gather_kernel<bwd | bwd-rep> (BN-backward
+    # apply built into the operand; stage 4 also adds the OCout_dec gradient)
     import ctypes
     fn = lib.mrfp_debug_conv3x3_bf16
     fn.restype = ctypes.c_int
@@ -609,8 +609,8 @@ def run_ours(args):
     gfn.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int] + [ctypes.c_void_p] * 5 + [ctypes.c_int] * 6 + [ctypes.c_void_p] * 4
     bfn = lib.mrfp_debug_conv3x3_gather_bwd
     bfn.restype = ctypes.c_int
-    bfn.argtypes = ([ctypes.c_void_p] * 2 + [ctypes.c_int] * 2 + [ctypes.c_void_p] * 5 + [ctypes.c_double] + [ctypes.c_void_p] * 2 +
-                    [ctypes.c_int] * 6 + [ctypes.c_void_p] * 2)
+    bfn.argtypes = ([ctypes.c_void_p] * 2 + [ctypes.c_int] * 2 + [ctypes.c_void_p] * 4 + [ctypes.c_int] + [ctypes.c_void_p] * 3 +
+                    [ctypes.c_double] + [ctypes.c_void_p] * 2 + [ctypes.c_int] * 6 + [ctypes.c_void_p] * 2)
     plan = H.get_plan(n, 64, XH, XW, H_IMG, W_IMG, dev, H.MATH_BF16)
 
     def nearest_idx(src, dst):          # ATen's rule in float32 (size= form; the tables only shape the access pattern here)
@@ -653,7 +653,7 @@ def run_ours(args):
         # dgrad of the stage: cout channels in, cin channels out, same resolution and FLOPs
         wpb = (torch.randn(9, cin, cout, device=dev) * (2.0 / (9 * cout)) ** 0.5).to(torch.bfloat16)
         gout = torch.empty(n, ch, cw, cin, device=dev, dtype=torch.bfloat16)
-        if k <= 3:
+        if k in (2, 3):
             dy = torch.randn(n, ch, cw, cout, device=dev).to(torch.bfloat16)
             t = time_launch(lambda: ok(fn(dy.data_ptr(), wpb.data_ptr(), gout.data_ptr(), n, ch, cw, cout, cin, dil, None, None, None, st)), 5)
             kern = f"conv3x3_tc_kernel<{cin}>"
@@ -662,13 +662,16 @@ def run_ours(args):
             yk = torch.randn(n, ch, cw, cout, device=dev).to(torch.bfloat16)
             da = torch.randn(n, oh, ow, cout, device=dev).to(torch.bfloat16)
             ih, iw = nearest_idx(ch, oh), nearest_idx(cw, ow)
-            loh = torch.searchsorted(ih, torch.arange(ch + 1)).to(torch.int32).to(dev)
-            low = torch.searchsorted(iw, torch.arange(cw + 1)).to(torch.int32).to(dev)
+            loh_c = torch.searchsorted(ih, torch.arange(ch + 1)).to(torch.int32).contiguous()     # host copies size the extras stage
+            low_c = torch.searchsorted(iw, torch.arange(cw + 1)).to(torch.int32).contiguous()
+            loh, low = loh_c.to(dev), low_c.to(dev)
+            rep = 2 if k < 4 else 1                     # up-sampling stages: up to 2 x 2 replicas of a source pixel
             add = torch.randn(n, ch, cw, cin, device=dev).to(torch.bfloat16) if k == 4 else None
-            t = time_launch(lambda: ok(bfn(yk.data_ptr(), da.data_ptr(), oh, ow, loh.data_ptr(), low.data_ptr(), stats_t.data_ptr(),
-                                        gamma_t.data_ptr(), acc_t.data_ptr(), float(n * oh * ow), wpb.data_ptr(), gout.data_ptr(), n, ch, cw,
-                                        cout, cin, dil, None if add is None else add.data_ptr(), st)), 5)
-            kern = f"conv3x3_gather_kernel<{cin}, bwd{', add' if k == 4 else ''}>"
+            t = time_launch(lambda: ok(bfn(yk.data_ptr(), da.data_ptr(), oh, ow, loh.data_ptr(), low.data_ptr(), loh_c.data_ptr(),
+                                           low_c.data_ptr(), rep, stats_t.data_ptr(), gamma_t.data_ptr(), acc_t.data_ptr(),
+                                           float(n * oh * ow), wpb.data_ptr(), gout.data_ptr(), n, ch, cw, cout, cin, dil,
+                                           None if add is None else add.data_ptr(), st)), 5)
+            kern = f"conv3x3_gather_kernel<{cin}, {'bwd-rep' if k < 4 else 'bwd'}{', add' if k == 4 else ''}>"
             del yk, da, add
         dgrad_rows.append({"stage": k, "kernel": kern, "cin": cout, "cout": cin, "hw": [ch, cw], "us": t * 1e3, "tflops": fl / t / 1e9})
         del wp, wpb, gout
@@ -723,9 +726,9 @@ def run_ours(args):
     # NP+ call 2 fwd + bwd (call 1 is folded into the chain: +1 coefficient block each way); HRFP fwd 1 weight pack + 1
     # NCHW->NHWC + 8 conv (stages 1-7 build their operand from the previous conv output, BN finalised by the last CTA) + 1
     # NHWC->NCHW epilogue (OCout + x); tail through the classifier 1 fwd + 1 bwd + 1 bilinear-transpose gather; HRFP bwd
-    # 1 NCHW->NHWC + 8 BN-bwd reductions + 4 BN-bwd apply passes (stages 0-3; stages 4-7 build dY inside the dgrad) + 8 dgrad
+    # 1 NCHW->NHWC + 8 BN-bwd reductions + 2 BN-bwd apply passes (stages 2-3; the others build dY inside the dgrad) + 8 dgrad
     # + 1 NHWC->NCHW
-    launches_per_step = 2 + (1 + 1 + 1 + 8 + 1) + 3 + (1 + 1 + 8 + 4 + 8 + 1)
+    launches_per_step = 2 + (1 + 1 + 1 + 8 + 1) + 3 + (1 + 1 + 8 + 2 + 8 + 1)
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16 (HRFP tensor-core operands, fp32 accumulate) / f32 (NP+)", "data": "synthetic", "config": CONFIG,

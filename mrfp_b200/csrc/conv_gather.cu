@@ -5,6 +5,8 @@
 //   kGatherBwd    ReLU' -> BatchNorm2d backward -> adjoint of the nearest resample -> Conv2d dgrad   (stages whose resample
 //                 never replicates a pixel: the identity and the down-sampling stages) — dY_k is produced from dA_{k+1},
 //                 Y_k and the BN-backward sums
+//   kGatherBwdRep the same for an up-sampling stage (a source pixel has up to 2 x 2 replicas in dA_{k+1}): the first replica
+//                 goes to the gradient side stage, the others to a compacted "extras" stage
 // so that A_k (forward) and dY_k (backward) never exist in HBM.
 //
 // Tile: 16 rows x (8 * MT) columns of output pixels; each 16 x 8 sub-tile is one UMMA M = 128 accumulator.  Per
@@ -23,7 +25,9 @@
 // (forward: ReLU(scale * y + shift); backward: the BN-backward apply of y and the gradient piece that the same thread
 // copied into a side stage) once it has landed.
 #include "conv_common.cuh"
+#include <algorithm>
 #include <atomic>
+#include <vector>
 
 namespace mrfp {
 namespace {
@@ -37,15 +41,13 @@ constexpr int kMaxAStages = 4;
 constexpr int kSmemLimit = 232448;             // 227 KB opt-in maximum per CTA
 
 constexpr int kMaxBStages = 6;
-constexpr int kGatherFwd = 0, kGatherBwd = 1;
+constexpr int kGatherFwd = 0, kGatherBwd = 1, kGatherBwdRep = 2;
 // staging tiles, row weights, barriers at compile-time offsets; rounded so that everything behind stays 1024-aligned
 constexpr int kFixedBytes = (2 * kStageOutBytes + 512 + 8 * (2 * kMaxAStages + 2 * kMaxBStages + 6) + 16 + 1023) / 1024 * 1024;
 
 template <int COUT> struct GCfg {
-  static constexpr int kMT = COUT == 256 ? 1 : 2;
   static constexpr int kBTileBytes = COUT * 128;
   static constexpr int kBStages = COUT == 256 ? 4 : (COUT == 128 ? 4 : 6);     // preferred depth of the weight ring
-  static constexpr int kTmemCols = 2 * kMT * COUT;
 };
 
 // what the producers gather from
@@ -94,17 +96,18 @@ __device__ __forceinline__ void ld8s(uint32_t a, float (&v)[8]) {
 // kGatherBwd:   in[h][w][c] = P[c] * [scale[c]*y+shift[c] > 0] * g[replica of (h,w)][c] - (R[c]*y[h][w][c] + Q[c])  where (h,w) has a
 //               replica, 0 where it has none (a pixel the down-sampling skipped receives no gradient)
 // each inside the image, 0 in the convolution's zero padding
-template <int COUT, int MODE, bool ADD>
+template <int COUT, int MODE, bool ADD, int MT>
 __global__ void __launch_bounds__(kGThreads, 1)
 conv3x3_gather_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_out,
                       const __grid_constant__ CUtensorMap tmap_add, const GatherArgs ga, int CIN, int dil, int boxw, int tiles_h, int tiles_w, int num_tiles,
                       const int* __restrict__ cnt_h, const int* __restrict__ cnt_w, double* __restrict__ stat_acc, int rev,
                       const ConvBnFinalize fin, const __nv_bfloat16* __restrict__ add_src, int H, int W, int nA, int nB,
-                      int a_stage_bytes, int tab_bytes) {
+                      int a_stage_bytes, int tab_bytes, int e_bytes) {
   using C = GCfg<COUT>;
   using T = __nv_bfloat16;
   constexpr int kBlockK = 64;
-  constexpr int MT = C::kMT;
+  constexpr bool kBwd = MODE != kGatherFwd;
+  constexpr int kTmemCols = 2 * MT * COUT;
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   // what the epilogue touches sits at compile-time offsets; the weight ring, the halo stages, the gradient side stage
@@ -121,8 +124,9 @@ conv3x3_gather_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_c
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(add_full + 2);
   unsigned char* sB = smem + kFixedBytes;                                      // nB weight tiles
   unsigned char* sA = sB + nB * C::kBTileBytes;                                // nA stages of a_stage_bytes (1024-aligned)
-  unsigned char* sG = sA + nA * a_stage_bytes;                                 // kGatherBwd: one stage of gradient pieces
-  unsigned char* s_tab = sG + (MODE == kGatherBwd ? a_stage_bytes : 0);        // gather tables
+  unsigned char* sG = sA + nA * a_stage_bytes;                                 // backward: one stage of gradient pieces
+  unsigned char* sE = sG + (kBwd ? a_stage_bytes : 0);                         // kGatherBwdRep: replicas 2..4, one 128-byte row each
+  unsigned char* s_tab = sE + e_bytes;                                         // gather tables
   float* s_const = reinterpret_cast<float*>(s_tab + tab_bytes);                // fwd: scale, shift [CIN]; bwd: + P, Q, R
 
   const int warp = threadIdx.x >> 5;
@@ -140,7 +144,7 @@ conv3x3_gather_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_c
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)), "n"(C::kTmemCols) : "memory");
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)), "n"(kTmemCols) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -220,11 +224,11 @@ conv3x3_gather_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_c
     const int pt = threadIdx.x - 192;            // 0..255
     const int piece = pt & 7;                    // 16-byte piece (8 channels) of a pixel's 128-byte chunk
     const int pl = pt >> 3;                      // pixel lane: box pixels pl, pl + 32, ...
-    const uint32_t tab_u = smem_u32(s_tab), sA_u = smem_u32(sA), sG_u = smem_u32(sG), const_u = smem_u32(s_const);
+    const uint32_t tab_u = smem_u32(s_tab), sA_u = smem_u32(sA), sG_u = smem_u32(sG), sE_u = smem_u32(sE), const_u = smem_u32(s_const);
     {
       for (int j = pt; j < CIN; j += kProducers) {
         s_const[j] = ga.stats[2 * kMaxC + j]; s_const[CIN + j] = ga.stats[3 * kMaxC + j];
-        if constexpr (MODE == kGatherBwd) {      // BN-backward constants from the reduced sums (as bn_bwd_apply, hrfp.cu)
+        if constexpr (kBwd) {                    // BN-backward constants from the reduced sums (as bn_bwd_apply, hrfp.cu)
           const double mean = ga.stats[j], invstd = ga.stats[kMaxC + j], gm = j < ga.c_real ? ga.gamma[j] : 0.f;
           const double S1 = ga.acc[j], S2 = invstd * (ga.acc[kMaxC + j] - mean * S1);
           const double M1 = gm * S1 / ga.count, M2 = gm * S2 / ga.count;
@@ -237,8 +241,8 @@ conv3x3_gather_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_c
     // gather table of a tile (shared by its channel chunks): source pixel of each box pixel, -1 where the operand is zero
     // (the convolution's padding; backward: also a pixel without replica); nT buffers, because the copies run up to
     // nA - 1 chunks — possibly tiles — ahead of the transform
-    constexpr int kEnt = MODE == kGatherBwd ? 8 : 4;       // bytes per table entry
-    const int nT = MODE == kGatherBwd ? 1 : nA;
+    constexpr int kEnt = MODE == kGatherFwd ? 4 : (MODE == kGatherBwd ? 8 : 16);       // bytes per table entry
+    const int nT = kBwd ? 1 : nA;
     const int tab_stride = tab_bytes / nT;
     auto build_table = [&](int seq) {
       const int t0 = blockIdx.x + seq * gridDim.x;
@@ -247,6 +251,47 @@ conv3x3_gather_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_c
       const int h0 = th * kGTileH - dil, w0 = tw * kGSubW * MT - dil;      // image coordinates of box pixel (0, 0)
       const uint32_t tab = tab_u + (uint32_t)((seq % nT) * tab_stride);
       prod_bar_sync();                           // every producer is done with the tile that owned this buffer (first: the constants)
+      if constexpr (MODE == kGatherBwdRep) {
+        // entry = (y pixel | -1, first replica's pixel in g, slot of the other replicas in the extras stage, nh | nw << 8);
+        // the slots are an exclusive prefix sum of (nh * nw - 1) over the box pixels: warp scans + warp totals in shared memory
+        const uint32_t scan_u = tab + 16u * (uint32_t)npix;                 // [8] warp totals
+        const int lane_ = pt & 31, wid = pt >> 5;
+        int carry = 0;
+        for (int base = 0; base < npix; base += kProducers) {
+          const int p = base + pt;
+          int oy = -1, og = 0, nh = 0, nw = 0;
+          if (p < npix) {
+            const int row = p / boxw, col = p - row * boxw;
+            const int h = h0 + row, w = w0 + col;
+            if ((unsigned)h < (unsigned)H && (unsigned)w < (unsigned)W) {
+              const int dh = ga.tab_h[h], dw = ga.tab_w[w];
+              nh = ga.tab_h[h + 1] - dh; nw = ga.tab_w[w + 1] - dw;
+              if (nh > 0 && nw > 0) { oy = (n * H + h) * W + w; og = (n * ga.SH + dh) * ga.SW + dw; }
+            }
+          }
+          const int e = oy >= 0 ? nh * nw - 1 : 0;
+          int x = e;
+#pragma unroll
+          for (int o = 1; o < 32; o <<= 1) {
+            const int v = __shfl_up_sync(0xffffffffu, x, o);
+            if (lane_ >= o) x += v;
+          }
+          if (lane_ == 31) asm volatile("st.shared.b32 [%0], %1;" ::"r"(scan_u + 4u * (uint32_t)wid), "r"(x) : "memory");
+          prod_bar_sync();
+          int before = carry, total = carry;
+#pragma unroll
+          for (int i = 0; i < kProducers / 32; ++i) {
+            const int v = lds32(scan_u + 4u * (uint32_t)i);
+            if (i < wid) before += v;
+            total += v;
+          }
+          if (p < npix)
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};"
+                         ::"r"(tab + 16u * (uint32_t)p), "r"(oy), "r"(og), "r"(before + x - e), "r"(nh | (nw << 8)) : "memory");
+          carry = total;
+          prod_bar_sync();                       // the warp totals are reused by the next pass
+        }
+      } else {
       for (int p = pt; p < npix; p += kProducers) {
         const int row = p / boxw, col = p - row * boxw;
         const int h = h0 + row, w = w0 + col;
@@ -264,6 +309,7 @@ conv3x3_gather_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_c
         }
       }
       prod_bar_sync();
+      }
     };
     const int my_tiles = (num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
     const int nitems = my_tiles * nchunks;       // an item = one 64-channel chunk of one tile = one halo stage
@@ -271,7 +317,7 @@ conv3x3_gather_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_c
     // a stage is 1024-byte aligned and a thread's pixels are 32 apart: the swizzle phase of its rows is the constant pl & 7
     const uint32_t my_off = (uint32_t)pl * 128u + (uint32_t)((piece ^ (pl & 7)) << 4);
     // backward: the gradient side stage is single, so the copies run one item ahead of the MMAs but never ahead of the transform
-    const int LA = MODE == kGatherBwd ? 0 : nA - 1;
+    const int LA = kBwd ? 0 : nA - 1;
     int i_item = 0, i_seq = -1, i_kc = 0, i_as = 0; uint32_t i_ph = 0;
     // issues the copies of the next item; returns the mask of this thread's live pixels (bit u: operand not identically zero)
     auto issue_next = [&]() -> uint32_t {
@@ -290,11 +336,28 @@ conv3x3_gather_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_c
             // an identically-zero pixel: source size 0 zero-fills the 16 bytes
             asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;"
                          ::"r"(dst0 + (uint32_t)(kPxLanes * 128 * u)), "l"(src), "r"(off >= 0 ? 16 : 0) : "memory");
-            if constexpr (MODE == kGatherBwd) {
+            if constexpr (kBwd) {
               if (off >= 0) {
                 const int og = lds32(tab + (uint32_t)(kEnt * kPxLanes * u) + 4u);
+                const __nv_bfloat16* gp = ga.g + (size_t)og * CIN + c0;
                 asm volatile("cp.async.cg.shared.global [%0], [%1], 16;"
-                             ::"r"(sG_u + my_off + (uint32_t)(kPxLanes * 128 * u)), "l"(ga.g + (size_t)og * CIN + c0) : "memory");
+                             ::"r"(sG_u + my_off + (uint32_t)(kPxLanes * 128 * u)), "l"(gp) : "memory");
+                if constexpr (MODE == kGatherBwdRep) {     // replicas (0,1), (1,0), (1,1) -> consecutive rows of the extras stage
+                  const int rep = lds32(tab + (uint32_t)(kEnt * kPxLanes * u) + 12u);
+                  if (rep != (1 | (1 << 8))) {
+                    const int nh = rep & 0xff, nw = rep >> 8;
+                    uint32_t ed = sE_u + (uint32_t)lds32(tab + (uint32_t)(kEnt * kPxLanes * u) + 8u) * 128u + (uint32_t)(piece << 4);
+                    if (nw > 1) {
+                      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(ed), "l"(gp + CIN) : "memory");
+                      ed += 128u;
+                    }
+                    if (nh > 1) {
+                      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(ed), "l"(gp + (size_t)ga.SW * CIN) : "memory");
+                      if (nw > 1)
+                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(ed + 128u), "l"(gp + (size_t)ga.SW * CIN + CIN) : "memory");
+                    }
+                  }
+                }
               }
             }
             valid |= (off >= 0 ? 1u : 0u) << u;
@@ -369,10 +432,27 @@ conv3x3_gather_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_c
             if (u0 + i < U && ((valid >> (u0 + i)) & 1u)) {      // a dead pixel keeps the zeros its copy filled in
               float y[8], g[8];
               unpack8(vy[i], y); unpack8(vg[i], g);
+              float cnt = 1.f;
+              if constexpr (MODE == kGatherBwdRep) {             // the other replicas, in the order (0,1), (1,0), (1,1)
+                const uint32_t te = tab_u + (uint32_t)(16 * (pl + kPxLanes * (u0 + i)));
+                const int rep = lds32(te + 12u);
+                const int nx = (rep & 0xff) * (rep >> 8) - 1;
+                if (nx > 0) {
+                  const uint32_t ea = sE_u + (uint32_t)lds32(te + 8u) * 128u + (uint32_t)(piece << 4);
+                  for (int x = 0; x < nx; ++x) {
+                    float e8[8];
+                    unpack8(lds128(ea + 128u * (uint32_t)x), e8);
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) g[q] += e8[q];
+                  }
+                  cnt = (float)(nx + 1);
+                }
+              }
 #pragma unroll
               for (int q = 0; q < 8; ++q) {
                 const float t = fmaf(sc[q], y[q], sh[q]) > 0.f ? g[q] : 0.f;
-                y[q] = cP[q] * t - fmaf(cR[q], y[q], cQ[q]);
+                if constexpr (MODE == kGatherBwdRep) y[q] = cP[q] * t - cnt * fmaf(cR[q], y[q], cQ[q]);
+                else y[q] = cP[q] * t - fmaf(cR[q], y[q], cQ[q]);
               }
               const uint4 o = pack8(y);
               asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};"
@@ -397,48 +477,81 @@ conv3x3_gather_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_c
   __syncthreads();
   if (warp == 1) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(C::kTmemCols) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(kTmemCols) : "memory");
   }
 }
 
-// shared-memory carve-up of one launch: weight ring, halo stages (+ the gradient side stage), gather tables, per-channel
-// constants behind the fixed part.  Forward: as many halo stages as fit (the copies run nA - 1 stages ahead), a
-// shallower weight ring if that buys the third stage.  Backward: two halo stages + the side stage.
-struct SmemPlan { int boxw, a_stage, tab_bytes, nA, nB, smem; };
-SmemPlan smem_plan(int mode, int cout, int cin, int dil) {
-  const int mt = cout == 256 ? 1 : 2;
+// shared-memory carve-up of one launch: weight ring, halo stages (+ the gradient side stage, + the extras stage), gather
+// tables, per-channel constants behind the fixed part.  Forward: as many halo stages as fit (the copies run nA - 1 stages
+// ahead), a shallower weight ring if that buys the third stage.  Backward: two halo stages + the side stage(s).
+struct SmemPlan { int mt, boxw, a_stage, tab_bytes, e_bytes, nA, nB, smem; };
+SmemPlan smem_plan_mt(int mode, int cout, int cin, int dil, int mt, int e_rows) {
   const int b_pref = cout == 256 ? GCfg<256>::kBStages : (cout == 128 ? GCfg<128>::kBStages : GCfg<64>::kBStages);
   const int b_tile = cout * 128;
   SmemPlan p = {};
+  p.mt = mt;
   p.boxw = kGSubW * mt + 2 * dil;
   const int npix = p.boxw * (kGTileH + 2 * dil);
   p.a_stage = (int)align_up((size_t)npix * 128, 1024);
-  const int tab1 = (int)align_up((size_t)npix * (mode == kGatherBwd ? 8 : 4), 16);
+  p.e_bytes = mode == kGatherBwdRep ? (int)align_up((size_t)e_rows * 128, 1024) : 0;
+  const int ent = mode == kGatherFwd ? 4 : (mode == kGatherBwd ? 8 : 16);
+  const int tab1 = (int)align_up((size_t)npix * ent + (mode == kGatherBwdRep ? 64 : 0), 16);
   const int consts = (mode == kGatherFwd ? 2 : 5) * cin * 4;
   const int base = kFixedBytes + consts + 1024 /* alignment slack */;
   auto stages_for = [&](int nb) {                    // halo stages that fit next to nb weight tiles
-    const int left = kSmemLimit - base - nb * b_tile;
-    if (mode == kGatherBwd) return left >= 3 * p.a_stage + tab1 ? 2 : 0;
+    const int left = kSmemLimit - base - nb * b_tile - p.e_bytes;
+    if (mode != kGatherFwd) return left >= 3 * p.a_stage + tab1 ? 2 : 0;
     int n = left / (p.a_stage + tab1);
     return n > kMaxAStages ? kMaxAStages : n;
   };
-  const int want = mode == kGatherBwd ? 2 : 3;
+  const int want = mode == kGatherFwd ? 3 : 2;
   p.nB = b_pref;
   p.nA = stages_for(p.nB);
   for (int nb = b_pref - 1; nb >= 3 && p.nA < want; --nb)      // the deepest weight ring that still leaves the wanted stages
     if (stages_for(nb) > p.nA) { p.nB = nb; p.nA = stages_for(nb); }
   if (p.nA < 2) { p.nA = 0; return p; }
-  const int ntab = mode == kGatherBwd ? 1 : p.nA;
-  p.tab_bytes = ntab * tab1;
-  p.smem = base + p.nB * b_tile + (p.nA + (mode == kGatherBwd ? 1 : 0)) * p.a_stage + p.tab_bytes;
+  p.tab_bytes = (mode == kGatherFwd ? p.nA : 1) * tab1;
+  p.smem = base + p.nB * b_tile + (p.nA + (mode == kGatherFwd ? 0 : 1)) * p.a_stage + p.e_bytes + p.tab_bytes;
   return p;
 }
 
-template <int COUT, int MODE, bool ADD>
-int launch(const GatherArgs& ga, const void* wpack, void* out, int N, int H, int W, int cin, int dil, const int* cnt_h,
-           const int* cnt_w, double* stat_acc, int rev, const ConvBnFinalize& fin, const void* add_src, ConvMaps* cache,
-           cudaStream_t stream) {
-  using C = GCfg<COUT>;
+// rows of the extras stage a tile can need: max over tiles of sum over live box pixels of (nh * nw - 1) — separable in the
+// row / column replica counts (lo tables on the host: first replica of each source row / column)
+int extras_rows(const int* lo_h, const int* lo_w, int H, int W, int dil, int mt) {
+  const int boxh = kGTileH + 2 * dil, boxw = kGSubW * mt + 2 * dil, tile_w = kGSubW * mt;
+  auto axis = [&](const int* lo, int size, int tile, int box, std::vector<std::pair<int, int>>& out) {
+    for (int t0 = 0; t0 < size; t0 += tile) {
+      int reps = 0, live = 0;
+      for (int i = t0 - dil; i < t0 - dil + box; ++i)
+        if (i >= 0 && i < size) { const int c = lo[i + 1] - lo[i]; reps += c; live += c > 0; }
+      out.emplace_back(reps, live);
+    }
+  };
+  std::vector<std::pair<int, int>> rh, rw;
+  axis(lo_h, H, kGTileH, boxh, rh);
+  axis(lo_w, W, tile_w, boxw, rw);
+  int best = 0;
+  for (const auto& a : rh)
+    for (const auto& b : rw) best = std::max(best, a.first * b.first - a.second * b.second);
+  return best;
+}
+
+// the plan of a launch.  The replica form needs 3 + ~0.7 halo-stage equivalents of staging: it fits for the 64-wide
+// dilation-1 stages; on the smaller 16 x 8 tile it would fit everywhere, but there the copies — which cannot run ahead of the
+// transform for lack of a second side stage — leave the 128-wide dgrad 4x producer-bound (measured 918 us against 371 + 291 us
+// for the separate pass + tap kernel), so that fallback is not taken.
+SmemPlan smem_plan(int mode, int cout, int cin, int dil, const int* host_lo_h = nullptr, const int* host_lo_w = nullptr, int H = 0,
+                   int W = 0) {
+  const int mt0 = cout == 256 ? 1 : 2;
+  if (mode != kGatherBwdRep) return smem_plan_mt(mode, cout, cin, dil, mt0, 0);
+  if (!host_lo_h || !host_lo_w || cout == 256) return SmemPlan{};
+  return smem_plan_mt(mode, cout, cin, dil, mt0, extras_rows(host_lo_h, host_lo_w, H, W, dil, mt0));
+}
+
+template <int COUT, int MODE, bool ADD, int MT>
+int launch(const SmemPlan& sp, const GatherArgs& ga, const void* wpack, void* out, int N, int H, int W, int cin, int dil,
+           const int* cnt_h, const int* cnt_w, double* stat_acc, int rev, const ConvBnFinalize& fin, const void* add_src,
+           ConvMaps* cache, cudaStream_t stream) {
   ConvMaps local;
   local.valid = 0;
   ConvMaps* m = cache ? cache : &local;
@@ -473,45 +586,47 @@ int launch(const GatherArgs& ga, const void* wpack, void* out, int N, int H, int
   DeviceInfo di;
   int rc = get_device_info(&di);
   if (rc) return rc;
-  const SmemPlan sp = smem_plan(MODE, COUT, cin, dil);
-  if (sp.nA < 2) return MRFP_ERR_UNSUPPORTED;
-  const int tile_w = kGSubW * C::kMT;
+  const int tile_w = kGSubW * MT;
   const int tiles_h = (H + kGTileH - 1) / kGTileH, tiles_w = (W + tile_w - 1) / tile_w;
   const int num_tiles = N * tiles_h * tiles_w;
   const int grid = num_tiles < di.sm_count ? num_tiles : di.sm_count;
-  auto kern = conv3x3_gather_kernel<COUT, MODE, ADD>;
+  auto kern = conv3x3_gather_kernel<COUT, MODE, ADD, MT>;
   MRFP_SMEM_OPT_IN(kern, kSmemLimit, di.device);
   launch_k(kern, dim3(grid), dim3(kGThreads), (size_t)sp.smem, stream, m->w, m->out, m->in, ga, cin, dil, sp.boxw, tiles_h, tiles_w,
            num_tiles, cnt_h, cnt_w, stat_acc, rev, fin, static_cast<const __nv_bfloat16*>(add_src), H, W, sp.nA, sp.nB, sp.a_stage,
-           sp.tab_bytes);
+           sp.tab_bytes, sp.e_bytes);
   MRFP_CUDA_TRY(cudaGetLastError());
   return MRFP_OK;
 }
 
 template <int MODE, bool ADD>
-int dispatch(const GatherArgs& ga, const void* wpack, void* out, int N, int H, int W, int cin, int cout, int dil,
+int dispatch(const SmemPlan& sp, const GatherArgs& ga, const void* wpack, void* out, int N, int H, int W, int cin, int cout, int dil,
              const int* cnt_h, const int* cnt_w, double* stat_acc, int rev, const ConvBnFinalize& fin, const void* add_src,
              ConvMaps* cache, cudaStream_t stream) {
-  switch (cout) {
-    case 64: return launch<64, MODE, ADD>(ga, wpack, out, N, H, W, cin, dil, cnt_h, cnt_w, stat_acc, rev, fin, add_src, cache, stream);
-    case 128: return launch<128, MODE, ADD>(ga, wpack, out, N, H, W, cin, dil, cnt_h, cnt_w, stat_acc, rev, fin, add_src, cache, stream);
-    case 256: return launch<256, MODE, ADD>(ga, wpack, out, N, H, W, cin, dil, cnt_h, cnt_w, stat_acc, rev, fin, add_src, cache, stream);
-  }
+  if (sp.nA < 2) return MRFP_ERR_UNSUPPORTED;
+#define MRFP_GATHER_CASE(CO, MTV) \
+  return launch<CO, MODE, ADD, MTV>(sp, ga, wpack, out, N, H, W, cin, dil, cnt_h, cnt_w, stat_acc, rev, fin, add_src, cache, stream)
+  if (cout == 256 && sp.mt == 1) { if constexpr (MODE != kGatherBwdRep) MRFP_GATHER_CASE(256, 1); }
+  if (cout == 128 && sp.mt == 2) MRFP_GATHER_CASE(128, 2);
+  if (cout == 64 && sp.mt == 2) MRFP_GATHER_CASE(64, 2);
+#undef MRFP_GATHER_CASE
   return MRFP_ERR_UNSUPPORTED;
 }
 
-bool supported(int mode, int N, int H, int W, int SH, int SW, int cin, int cout, int dil) {
+bool supported(int mode, int N, int H, int W, int SH, int SW, int cin, int cout, int dil, const int* host_lo_h = nullptr,
+               const int* host_lo_w = nullptr) {
   if (cin % 64 != 0 || cin > kMaxC || (cout != 64 && cout != 128 && cout != 256)) return false;
   if (dil != 1 && dil != 2) return false;
-  if (smem_plan(mode, cout, cin, dil).nA < 2) return false;
+  if (smem_plan(mode, cout, cin, dil, host_lo_h, host_lo_w, H, W).nA < 2) return false;
   // pixel indices are kept as 32-bit ints in the gather table
   return (long long)N * H * W < (1ll << 31) && (long long)N * SH * SW < (1ll << 31);
 }
 
 }  // namespace
 
-bool conv3x3_gather_supported(int mode, int N, int H, int W, int SH, int SW, int cin, int cout, int dil) {
-  return supported(mode, N, H, W, SH, SW, cin, cout, dil);
+bool conv3x3_gather_supported(int mode, int N, int H, int W, int SH, int SW, int cin, int cout, int dil, const int* host_lo_h,
+                              const int* host_lo_w) {
+  return supported(mode, N, H, W, SH, SW, cin, cout, dil, host_lo_h, host_lo_w);
 }
 
 int conv3x3_gather_fwd(const void* y_prev, int SH, int SW, const int* idx_h, const int* idx_w, const float* stats_prev,
@@ -529,15 +644,17 @@ int conv3x3_gather_fwd(const void* y_prev, int SH, int SW, const int* idx_h, con
   GatherArgs ga = {};
   ga.y = static_cast<const __nv_bfloat16*>(y_prev);
   ga.tab_h = idx_h; ga.tab_w = idx_w; ga.stats = stats_prev; ga.SH = SH; ga.SW = SW;
-  return dispatch<kGatherFwd, false>(ga, wpack, out, N, H, W, cin, cout, dil, cnt_h, cnt_w, stat_acc, reverse_tiles ? 1 : 0, fin,
-                                     nullptr, cache, stream);
+  return dispatch<kGatherFwd, false>(smem_plan(kGatherFwd, cout, cin, dil), ga, wpack, out, N, H, W, cin, cout, dil, cnt_h, cnt_w,
+                                     stat_acc, reverse_tiles ? 1 : 0, fin, nullptr, cache, stream);
 }
 
-int conv3x3_gather_bwd(const void* y, const void* dA, int OH, int OW, const int* lo_h, const int* lo_w, const float* stats,
-                       const float* gamma, const double* acc, double count, int c_real, const void* wpack, void* out, int N,
-                       int H, int W, int cin, int cout, int dil, cudaStream_t stream, bool reverse_tiles, const void* add_src,
-                       ConvMaps* cache) {
-  if (!supported(kGatherBwd, N, H, W, OH, OW, cin, cout, dil)) return MRFP_ERR_UNSUPPORTED;
+int conv3x3_gather_bwd(const void* y, const void* dA, int OH, int OW, const int* lo_h, const int* lo_w, const int* host_lo_h,
+                       const int* host_lo_w, int max_rep, const float* stats, const float* gamma, const double* acc, double count,
+                       int c_real, const void* wpack, void* out, int N, int H, int W, int cin, int cout, int dil,
+                       cudaStream_t stream, bool reverse_tiles, const void* add_src, ConvMaps* cache) {
+  const int mode = max_rep <= 1 ? kGatherBwd : kGatherBwdRep;
+  if (max_rep > 2 || (mode == kGatherBwdRep && add_src)) return MRFP_ERR_UNSUPPORTED;
+  if (!supported(mode, N, H, W, OH, OW, cin, cout, dil, host_lo_h, host_lo_w)) return MRFP_ERR_UNSUPPORTED;
   if (((uintptr_t)y | (uintptr_t)dA | (uintptr_t)wpack | (uintptr_t)out | (uintptr_t)add_src) & 15) return MRFP_ERR_WORKSPACE;
   GatherArgs ga = {};
   ga.y = static_cast<const __nv_bfloat16*>(y); ga.g = static_cast<const __nv_bfloat16*>(dA);
@@ -545,9 +662,12 @@ int conv3x3_gather_bwd(const void* y, const void* dA, int OH, int OW, const int*
   ga.SH = OH; ga.SW = OW; ga.c_real = c_real;
   const ConvBnFinalize fin = {};
   const int rev = reverse_tiles ? 1 : 0;
+  const SmemPlan sp = smem_plan(mode, cout, cin, dil, host_lo_h, host_lo_w, H, W);
+  if (mode == kGatherBwdRep)
+    return dispatch<kGatherBwdRep, false>(sp, ga, wpack, out, N, H, W, cin, cout, dil, nullptr, nullptr, nullptr, rev, fin, nullptr, cache, stream);
   if (add_src)
-    return dispatch<kGatherBwd, true>(ga, wpack, out, N, H, W, cin, cout, dil, nullptr, nullptr, nullptr, rev, fin, add_src, cache, stream);
-  return dispatch<kGatherBwd, false>(ga, wpack, out, N, H, W, cin, cout, dil, nullptr, nullptr, nullptr, rev, fin, nullptr, cache, stream);
+    return dispatch<kGatherBwd, true>(sp, ga, wpack, out, N, H, W, cin, cout, dil, nullptr, nullptr, nullptr, rev, fin, add_src, cache, stream);
+  return dispatch<kGatherBwd, false>(sp, ga, wpack, out, N, H, W, cin, cout, dil, nullptr, nullptr, nullptr, rev, fin, nullptr, cache, stream);
 }
 
 }  // namespace mrfp
@@ -561,9 +681,9 @@ extern "C" int mrfp_debug_conv3x3_gather_fwd(const void* y_prev, int SH, int SW,
                                   stat_acc, (cudaStream_t)stream, false, nullptr, nullptr);
 }
 extern "C" int mrfp_debug_conv3x3_gather_bwd(const void* y, const void* dA, int OH, int OW, const int* lo_h, const int* lo_w,
-                                             const float* stats, const float* gamma, const double* acc, double count, const void* wpack,
-                                             void* out, int N, int H, int W, int cin, int cout, int dil, const void* add_src,
-                                             void* stream) {
-  return mrfp::conv3x3_gather_bwd(y, dA, OH, OW, lo_h, lo_w, stats, gamma, acc, count, cin, wpack, out, N, H, W, cin, cout, dil,
-                                  (cudaStream_t)stream, false, add_src, nullptr);
+                                             const int* host_lo_h, const int* host_lo_w, int max_rep, const float* stats,
+                                             const float* gamma, const double* acc, double count, const void* wpack, void* out, int N,
+                                             int H, int W, int cin, int cout, int dil, const void* add_src, void* stream) {
+  return mrfp::conv3x3_gather_bwd(y, dA, OH, OW, lo_h, lo_w, host_lo_h, host_lo_w, max_rep, stats, gamma, acc, count, cin, wpack, out, N,
+                                  H, W, cin, cout, dil, (cudaStream_t)stream, false, add_src, nullptr);
 }

@@ -1318,11 +1318,14 @@ int hrfp_backward(const mrfp_hrfp_plan* P, const float* g_ocout, const float* g_
     int rr = run_bwd_reduce<T>(P, k, lut, dA, Y, stats, a, at_end, true, di, s);
     if (rr) return rr;
     at_end = !at_end;
-    // a stage whose resample never replicates a pixel (identity, down-sampling): dY_k is built inside the dgrad's operand
-    // producers from dA_{k+1}, Y_k and the sums (conv_gather.cu) instead of a pass over HBM.  (The fp32 OCout_dec gradient
-    // of the unfused tail is staged in the dA buffer, which the gathered dgrad still reads: that case keeps the pass.)
-    const bool gathered = tc && (P->fuse & 2) && sizeof(T) == 2 && st.max_rep <= 1 && !(k == 4 && g_ocout_dec && !g_dec_nhwc) &&
-                          conv3x3_gather_supported(1, P->N, st.ch, st.cw, st.oh, st.ow, st.cout, st.cin, st.dil);
+    // dY_k is built inside the dgrad's operand producers from dA_{k+1}, Y_k and the sums (conv_gather.cu) instead of a pass
+    // over HBM: identity / down-sampling stages directly, up-sampling stages (up to 2 x 2 replicas per pixel) through an
+    // extras stage.  (The fp32 OCout_dec gradient of the unfused tail is staged in the dA buffer, which the gathered dgrad
+    // still reads: that case keeps the pass.)
+    const bool gathered = tc && (P->fuse & 2) && sizeof(T) == 2 && st.max_rep <= 2 && !(k == 4 && g_ocout_dec && !g_dec_nhwc) &&
+                          !(st.max_rep > 1 && k == 4) &&
+                          conv3x3_gather_supported(st.max_rep <= 1 ? 1 : 2, P->N, st.ch, st.cw, st.oh, st.ow, st.cout, st.cin, st.dil,
+                                                   P->lut.data() + st.lo_h, P->lut.data() + st.lo_w);
     if (!gathered) {
       int ra = run_bwd_apply<T>(P, k, lut, dA, Y, dY, stats, gamma[k], a, at_end, true, di, s);
       if (ra) return ra;
@@ -1346,9 +1349,9 @@ int hrfp_backward(const mrfp_hrfp_plan* P, const float* g_ocout, const float* g_
       }
       int rc;
       if (gathered)
-        rc = conv3x3_gather_bwd(Y, dA, st.oh, st.ow, lut + st.lo_h, lut + st.lo_w, stats, gamma[k], a, (double)P->N * st.oh * st.ow,
-                                st.cout_real, saved + st.wb_off, other, P->N, st.ch, st.cw, st.cout, st.cin, st.dil, s, at_end,
-                                add_src, &P->maps_g[1][k]);
+        rc = conv3x3_gather_bwd(Y, dA, st.oh, st.ow, lut + st.lo_h, lut + st.lo_w, P->lut.data() + st.lo_h, P->lut.data() + st.lo_w,
+                                st.max_rep, stats, gamma[k], a, (double)P->N * st.oh * st.ow, st.cout_real, saved + st.wb_off, other,
+                                P->N, st.ch, st.cw, st.cout, st.cin, st.dil, s, at_end, add_src, &P->maps_g[1][k]);
       else
         rc = conv3x3_tc(dY, saved + st.wb_off, other, P->esize, P->N, st.ch, st.cw, st.cout, st.cin, st.dil, nullptr, nullptr,
                         nullptr, s, at_end, nullptr, add_src, &P->maps[1][k]);

@@ -93,19 +93,21 @@ int conv_make_map(CUtensorMap* m, CUtensorMapDataType dt, const void* base, int 
 // The same convolution on a halo-tile pipeline whose A operand is built on chip (conv_gather.cu, bf16 only):
 //   fwd:   in[h][w][c] = ReLU(scale[c] * y_prev[idx_h[h]][idx_w[w]][c] + shift[c]) — BatchNorm (stats_prev: [4][kMaxC]) + ReLU +
 //          nearest resample of Y_{k-1}, never written to HBM; everything else as conv3x3_tc
-//   bwd:   in = dY_k = BN-backward apply of (dA_{k+1}, Y_k) with the nearest adjoint, for a stage whose resample never
-//          replicates a pixel (lo_h / lo_w: first replica of each source row / column, [H + 1] / [W + 1]); acc = the sums of
-//          bn_bwd_reduce; out = dA_k; add_src as conv3x3_tc
-// mode: 0 fwd, 1 bwd.  MRFP_ERR_UNSUPPORTED -> the caller runs the separate element-wise pass and conv3x3_tc.
-bool conv3x3_gather_supported(int mode, int N, int H, int W, int SH, int SW, int cin, int cout, int dil);
+//   bwd:   in = dY_k = BN-backward apply of (dA_{k+1}, Y_k) with the nearest adjoint (lo_h / lo_w: first replica of each source
+//          row / column, [H + 1] / [W + 1], on the device and — for max_rep = 2, an up-sampling stage with up to 2 x 2 replicas
+//          per pixel — also on the host, where the capacity of the extras stage is derived); acc = the sums of bn_bwd_reduce;
+//          out = dA_k; add_src as conv3x3_tc (non-replicating stages only)
+// mode: 0 fwd, 1 bwd without replicas, 2 bwd with replicas.  MRFP_ERR_UNSUPPORTED -> the caller runs the separate element-wise pass and conv3x3_tc.
+bool conv3x3_gather_supported(int mode, int N, int H, int W, int SH, int SW, int cin, int cout, int dil,
+                              const int* host_lo_h = nullptr, const int* host_lo_w = nullptr);
 int conv3x3_gather_fwd(const void* y_prev, int SH, int SW, const int* idx_h, const int* idx_w, const float* stats_prev,
                        const void* wpack, void* out, int N, int H, int W, int cin, int cout, int dil, const int* cnt_h,
                        const int* cnt_w, double* stat_acc, cudaStream_t stream, bool reverse_tiles,
                        const ConvBnFinalize* finalize, ConvMaps* cache);
-int conv3x3_gather_bwd(const void* y, const void* dA, int OH, int OW, const int* lo_h, const int* lo_w, const float* stats,
-                       const float* gamma, const double* acc, double count, int c_real, const void* wpack, void* out, int N,
-                       int H, int W, int cin, int cout, int dil, cudaStream_t stream, bool reverse_tiles, const void* add_src,
-                       ConvMaps* cache);
+int conv3x3_gather_bwd(const void* y, const void* dA, int OH, int OW, const int* lo_h, const int* lo_w, const int* host_lo_h,
+                       const int* host_lo_w, int max_rep, const float* stats, const float* gamma, const double* acc, double count,
+                       int c_real, const void* wpack, void* out, int N, int H, int W, int cin, int cout, int dil,
+                       cudaStream_t stream, bool reverse_tiles, const void* add_src, ConvMaps* cache);
 
 // NP+ per-plane coefficients from plane totals (hrfp.cu; one block, C <= kMaxC).  forward: psum = sum_hw x -> coef = (a, b)
 // with out = a*x + b, mean_out / beta_out side arrays;  backward: psum = sum_hw g, mean_in = the forward's plane means ->
