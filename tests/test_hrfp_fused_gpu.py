@@ -36,8 +36,8 @@ def _l2(a, b):
 
 
 # (n, h, w): odd sizes exercise ragged tile edges (16 x 16 and 16 x 8 tiles), 40 x 56 a non-square image, 200 x 184
-# several tiles per image row and column
-GEOMS = [(2, 48, 48), (3, 40, 56), (2, 60, 44), (2, 96, 80), (2, 200, 184)]
+# several tiles per image row and column, 16 x 20 an image smaller than one halo tile
+GEOMS = [(2, 48, 48), (3, 40, 56), (2, 60, 44), (2, 96, 80), (2, 200, 184), (2, 16, 20)]
 
 
 @pytest.mark.parametrize("fuse", [1, 2, 3])
