@@ -505,9 +505,11 @@ SmemPlan smem_plan_mt(int mode, int cout, int cin, int dil, int mt, int e_rows) 
     return n > kMaxAStages ? kMaxAStages : n;
   };
   const int want = mode == kGatherFwd ? 3 : 2;
+  const int nb_min = mode == kGatherFwd ? 4 : 3;      // forward: a third halo stage is not worth a weight ring below 4 (measured
+                                                        // on the 256-wide stage: 2 stages + 4 tiles 345 us, 3 + 3 373 us)
   p.nB = b_pref;
   p.nA = stages_for(p.nB);
-  for (int nb = b_pref - 1; nb >= 3 && p.nA < want; --nb)      // the deepest weight ring that still leaves the wanted stages
+  for (int nb = b_pref - 1; nb >= nb_min && p.nA < want; --nb) // the deepest weight ring that still leaves the wanted stages
     if (stages_for(nb) > p.nA) { p.nB = nb; p.nA = stages_for(nb); }
   if (p.nA < 2) { p.nA = 0; return p; }
   p.tab_bytes = (mode == kGatherFwd ? p.nA : 1) * tab1;
