@@ -139,7 +139,9 @@ struct EpiSmem {
 // producer and MMA warps of the calling kernel.  ADD: 0 compiles the add_src path out; 1 fetches a chunk's 128 bytes of add_src
 // one chunk ahead into a second register set (64 registers); 2 keeps one set and fetches behind the chunk's packing (32);
 // 3 brings the chunk's add tile by TMA into the very staging buffer the result will be packed into, one chunk ahead (no
-// registers, no exposed latency): each thread reads the 128 bytes of its own row and overwrites them with the sum.
+// registers, no exposed latency): each thread reads the 128 bytes of its own row and overwrites them with the sum.  (Mode 3
+// is for launches without BN statistics — the dgrads: the statistics loop of chunk i would still be reading the buffer that
+// the leader refills for chunk i + 1.)
 template <int COUT, typename T, int TH, int TW, int MT, bool HMT, int ADD>
 __device__ __forceinline__ void conv_epilogue(const EpiSmem& sm, uint32_t tmem_base, const CUtensorMap& tmap_out, int tiles_h,
                                               int tiles_w, int num_tiles, const int* __restrict__ cnt_h,
