@@ -674,6 +674,16 @@ int conv3x3_gather_bwd(const void* y, const void* dA, int OH, int OW, const int*
 
 }  // namespace mrfp
 
+// test hook (host only, no device call): the shared-memory plan of a launch — out[0..5] = M sub-tiles, halo stages (0: the
+// kernel refuses this geometry), weight-ring slots, dynamic shared memory bytes, bytes of the extras stage, box width
+extern "C" int mrfp_debug_gather_plan(int mode, int cout, int cin, int dil, const int* host_lo_h, const int* host_lo_w, int H, int W,
+                                      int* out6) {
+  if (!out6 || mode < 0 || mode > 2) return MRFP_ERR_NULL_POINTER;
+  const mrfp::SmemPlan p = mrfp::smem_plan(mode, cout, cin, dil, host_lo_h, host_lo_w, H, W);
+  out6[0] = p.mt; out6[1] = p.nA; out6[2] = p.nB; out6[3] = p.smem; out6[4] = p.e_bytes; out6[5] = p.boxw;
+  return MRFP_OK;
+}
+
 // test / bench hooks (not part of the public header): single convolutions on caller-provided buffers — the same kernels
 // the chain launches
 extern "C" int mrfp_debug_conv3x3_gather_fwd(const void* y_prev, int SH, int SW, const int* idx_h, const int* idx_w,
