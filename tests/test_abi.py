@@ -55,3 +55,17 @@ def test_instnorm_argument_errors_without_gpu():
     assert lib.mrfp_instnorm_fwd_f32(None, None, None, None, None, None, None, 1, 1, 1, 1e-5, 1, None) == -1
     assert lib.mrfp_instnorm_bwd_f32(None, None, None, None, None, None, None, None, None, 1, 1, 1, 1, None) == -1
     assert lib.mrfp_instnorm_fwd_f32(8, None, None, 8, 8, 8, None, 0, 1, 1, 1e-5, 1, None) == -2
+
+
+def test_plan_fusion_bits_without_gpu():
+    """mrfp_hrfp_plan_set_fusion is host-only state: bits 0-1 for a bf16 plan, always 0 for the other math modes."""
+    import ctypes
+    from mrfp_b200 import _lib
+    lib = _lib.load()
+    for mode, expect in ((2, (3, 1, 2, 0, 3)), (1, (0, 0, 0, 0, 0)), (0, (0, 0, 0, 0, 0))):
+        h = ctypes.c_void_p()
+        assert lib.mrfp_hrfp_plan_create(ctypes.byref(h), 2, 64, 12, 12, 48, 48, None, mode) == 0
+        got = tuple(lib.mrfp_hrfp_plan_set_fusion(h, bits) for bits in (7, 1, 2, 0, 3))
+        assert got == expect, (mode, got)
+        lib.mrfp_hrfp_plan_destroy(h)
+    assert lib.mrfp_hrfp_plan_set_fusion(None, 1) == -5
