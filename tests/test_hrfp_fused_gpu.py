@@ -83,3 +83,23 @@ def test_vs_oracle_small(fuse):
     assert _l2(out.cpu(), torch.from_numpy(ro)) <= 3e-2
     assert _l2(dec.cpu(), torch.from_numpy(rd)) <= 3e-2
     assert _l2(gx.cpu(), torch.from_numpy(rg)) <= 3e-1
+
+
+def test_fused_equals_unfused_on_a_sweep_of_geometries():
+    """A deterministic sweep of odd image sizes (ragged tiles on every side, single-tile images, tall and wide images,
+    batch 1): the operand-fused chain against the separate passes."""
+    rng = np.random.default_rng(2024)
+    geoms = [(int(rng.integers(1, 4)), int(rng.integers(16, 150)), int(rng.integers(16, 150))) for _ in range(10)]
+    geoms += [(1, 17, 131), (2, 129, 18)]
+    for n, h, w in geoms:
+        xh, xw = math.ceil(h / 4), math.ceil(w / 4)
+        ws, gs = make_hrfp_params(h + 3 * w)
+        xp = make_feat(h * 7 + w, (n, 64, xh, xw))
+        gen = torch.Generator(device="cuda").manual_seed(h + w)
+        g1 = torch.randn((n, 64, xh, xw), device="cuda", generator=gen)
+        g2 = torch.randn((n, 256, h // 2, w // 2), device="cuda", generator=gen)
+        ref = _chain(xp, ws, gs, h, w, 0, g1, g2)
+        got = _chain(xp, ws, gs, h, w, 3, g1, g2)
+        for name, a, b, tol in zip(("OCout", "OCout_dec", "g_xp"), got, ref, (1e-2, 1e-2, 8e-2)):
+            assert torch.isfinite(a).all(), (name, n, h, w)
+            assert _l2(a, b) <= tol, (name, (n, h, w), _l2(a, b))
