@@ -178,12 +178,12 @@ EncodeTiledFn get_encode_fn() {
 }
 
 int make_map(CUtensorMap* m, CUtensorMapDataType dt, const void* base, int rank, const cuuint64_t* dims,
-             const cuuint64_t* strides, const cuuint32_t* box) {
+             const cuuint64_t* strides, const cuuint32_t* box, bool swizzle128 = true) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) return MRFP_ERR_DRIVER;
   const cuuint32_t ones[4] = {1, 1, 1, 1};
   CUresult r = fn(m, dt, (cuuint32_t)rank, const_cast<void*>(base), dims, strides, box, ones, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                  swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? MRFP_OK : MRFP_ERR_DRIVER;
 }
 
@@ -261,8 +261,8 @@ int dispatch(const void* in, const void* wpack, void* out, int N, int H, int W, 
 }  // namespace
 
 int conv_make_map(CUtensorMap* m, CUtensorMapDataType dt, const void* base, int rank, const cuuint64_t* dims,
-                  const cuuint64_t* strides, const cuuint32_t* box) {
-  return make_map(m, dt, base, rank, dims, strides, box);
+                  const cuuint64_t* strides, const cuuint32_t* box, bool swizzle128) {
+  return make_map(m, dt, base, rank, dims, strides, box, swizzle128);
 }
 
 bool conv3x3_tc_supported(int cin, int cout, int esize) {

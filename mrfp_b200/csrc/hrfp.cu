@@ -1416,8 +1416,10 @@ extern "C" int mrfp_hrfp_plan_create(mrfp_hrfp_plan_t** out, int N, int cin, int
   P->N = N; P->cin = cin; P->xh = xh; P->xw = xw; P->h = h; P->w = w; P->mode = math_mode;
   P->esize = math_mode == MRFP_MATH_BF16 ? 2 : 4;
   P->cin_pad = stem_pad(cin, math_mode);
-  for (int d = 0; d < 2; ++d)
+  for (int d = 0; d < 2; ++d) {
     for (int k = 0; k < kHrfpStages; ++k) P->maps[d][k].valid = P->maps_g[d][k].valid = 0;
+    P->maps_tail[d].valid = 0;
+  }
   P->fuse = math_mode == MRFP_MATH_BF16 ? 3 : 0;    // mrfp_hrfp_plan_set_fusion
   // layer table of deepv3.py:221-237, parametrised by the encoder widths and the (padded) stem width
   const int chans[9] = {P->cin_pad, wd[0], wd[1], wd[2], wd[3], wd[2], wd[1], wd[0], P->cin_pad};

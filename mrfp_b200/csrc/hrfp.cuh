@@ -38,6 +38,14 @@ struct ConvMaps {
   const void* key[3];
   int valid;
 };
+// the two descriptors of one classifier-tail launch (tail_final2.cu): Y_3 as [pixel][256 ch], and the fp32 side input
+// (forward: the low-resolution product, backward: the incoming gradient) as [plane][row][col]
+struct TailMaps {
+  CUtensorMap y, aux;
+  const void* key[2];
+  int k, d0, d1;
+  int valid;
+};
 
 }  // namespace mrfp
 
@@ -56,6 +64,7 @@ struct mrfp_hrfp_plan {
   mutable std::mutex mu;
   mutable mrfp::ConvMaps maps[2][mrfp::kHrfpStages];
   mutable mrfp::ConvMaps maps_g[2][mrfp::kHrfpStages];   // the halo-tile variants (conv_gather.cu)
+  mutable mrfp::TailMaps maps_tail[2];                   // classifier tail, forward / backward
   int fuse;                        // bf16 mode: bit 0 forward convs build their operand from Y_{k-1} on chip, bit 1 dgrads of
                                    // non-replicating stages build dY_k on chip
 };
@@ -88,7 +97,7 @@ int conv3x3_tc(const void* in, const void* wpack, void* out, int esize, int N, i
                const ConvBnFinalize* finalize = nullptr, const void* add_src = nullptr, ConvMaps* cache = nullptr);
 bool conv3x3_tc_supported(int cin, int cout, int esize);
 int conv_make_map(CUtensorMap* m, CUtensorMapDataType dt, const void* base, int rank, const cuuint64_t* dims,
-                  const cuuint64_t* strides, const cuuint32_t* box);
+                  const cuuint64_t* strides, const cuuint32_t* box, bool swizzle128 = true);
 
 // The same convolution on a halo-tile pipeline whose A operand is built on chip (conv_gather.cu, bf16 only):
 //   fwd:   in[h][w][c] = ReLU(scale[c] * y_prev[idx_h[h]][idx_w[w]][c] + shift[c]) — BatchNorm (stats_prev: [4][kMaxC]) + ReLU +
