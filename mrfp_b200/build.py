@@ -14,7 +14,7 @@ LIBDIR = os.path.join(PKG, "lib")
 LIB = os.path.join(LIBDIR, "libmrfp_b200.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-         "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-Xptxas", "-v"]
+         "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-Xptxas", "-v"] + os.environ.get("MRFP_EXTRA_NVCC_FLAGS", "").split()
 
 
 def _sources():
@@ -27,6 +27,7 @@ def _stamp():
             [os.path.join(PKG, "..", "include", "mrfp_b200.h"), os.path.abspath(__file__)]:
         with open(f, "rb") as fh:
             h.update(fh.read())
+    h.update(" ".join(FLAGS).encode())
     return h.hexdigest()
 
 

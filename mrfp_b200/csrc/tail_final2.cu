@@ -5,22 +5,37 @@
 // A 1x1 convolution commutes with the (linear) bilinear interpolation, so
 //     dec2 = b2 + Upsample(W2 . dec1) + W2 . OCout_dec
 // The first product is a (N, K, h/4, w/4) tensor the host computes with a plain GEMM at LOW resolution; this file
-// evaluates the rest per 128-pixel tile of an output row: the span of the stored conv output Y_3 the tile gathers from
-// arrives in shared memory as bf16 NHWC (16-byte cp.async, XOR-swizzled), `ldmatrix` hands it to the warps as
-// m16n8k16 A fragments whose per-lane row addresses perform the nearest-neighbour gather, BatchNorm + ReLU are applied to
-// the fragments in registers, and `mma.sync` contracts the 256 channels against W2 (bf16, K <= 24 classes).  Neither
-// OCout_dec nor the up-sampled dec1 nor their sum (1.2 GB fp32 at batch 8) ever exists; the forward writes 90 MB.
+// evaluates the rest per 64-pixel tile of an output row, in persistent CTAs (two per SM) whose inputs arrive by TMA one
+// tile ahead (double-buffered, issued by one thread, completion on an mbarrier):
+//   * the span of the stored conv output Y_3 the tile gathers from — ONE 3-D box of a tensor map that views Y_3 as
+//     [4 groups of 64 channels][pixel][64 channels], landing as four SWIZZLE_128B tiles [64 px][128 bytes];
+//   * forward: the two low-resolution rows of every class ([K][2][44] fp32 box; columns beyond the row end and the row
+//     below the last one arrive as zeros); backward: the tile's g ([K][64] fp32 box, zeros beyond the row end).
+// `ldmatrix` hands the span to the warps as m16n8k16 fragments whose per-lane row addresses perform the nearest-neighbour
+// gather (relative source indices of every tile staged once per CTA), BatchNorm + ReLU are applied to the fragments in
+// registers (one packed fp32x2 FMA, one rounding to bf16x2, max on the pair), and `mma.sync` contracts against W2 (bf16,
+// K <= 24 classes).  Everything that does not change from tile to tile lives in REGISTERS of the persistent CTA: the
+// classifier fragments and the BN constants of the warp's channels (forward: warp = one quarter of the channels x 32
+// pixels, the four quarter sums meet in the epilogue; backward: warp = 32 channels x all pixels in both products).
+// Neither OCout_dec nor the up-sampled dec1 nor their sum (1.2 GB fp32 at batch 8) ever exists; the forward writes 90 MB.
 //   Tensor-core choice: the A operand needs a register-side transform (BN/ReLU of gathered rows) and the contraction is
 //   11.5 GFLOP per launch against ~0.6 GB of HBM traffic — 5 % of the tensor peak keeps up with the memory system, so
 //   warp-level mma.sync on register fragments (no shared-memory round trip for the transformed operand) is the better
 //   fit than a tcgen05 pipeline here.
 // Backward (one pass over g = dL/d dec2, (N, K, h/2, w/2) fp32):
-//     dA3[p][c]   = sum_k g[k][p] W2[k][c]        -> bf16 NHWC, joins the chain as the gradient of OCout_dec (rank K)
+//     dA3[p][c]   = sum_k g[k][p] W2[k][c]        -> bf16 NHWC, joins the chain as the gradient of OCout_dec (rank K);
+//                                                   A fragments by ldmatrix.trans from the bf16 [class][pixel] copy of g,
+//                                                   results transposed inside each lane quad and stored from registers
 //     gW2[k][c]  += sum_p g[k][p] OCout_dec[c][p]  (OCout_dec regenerated from Y_3 in registers; accumulators stay in
 //                                                   registers across the tiles of a persistent CTA)
 //     gb2[k]     += sum_p g[k][p]
 // The low-resolution half (gradient of W2 . dec1 through the Upsample) is the gather kernel of bilinear.cu plus the
 // host's GEMM autograd.
+// What was measured on the way (tools/trace_tail.py, profiles/README.md "R2c"): the first form (128-pixel tiles, per-thread
+// cp.async of the span, one bulk copy per low-resolution row, W2 fragments and the BN table re-read from shared memory
+// per k-block) ran 215 / 363 us at batch 8; per-thread cp.async and per-row bulk copies cost the issuing warps 2400-4300
+// cycles per 64-pixel tile, a lane-indexed register pick compiles to divergent branches, a proxy fence per issue and
+// global index look-ups sit on the critical path of every barrier.  This form: 133 / 210 us.
 #include "hrfp.cuh"
 #include "tma.cuh"
 #include <mutex>
@@ -30,13 +45,9 @@ namespace {
 
 using namespace tma;
 
-constexpr int kPx = 128;             // output pixels per tile (a segment of one output row)
-constexpr int kSpan = 120;           // source pixels a tile may gather from (128 * 332/384 + 2 = 113 in the reference geometry)
 constexpr int kC = 256;              // channels of OCout_dec (widths[3])
 constexpr int kCls = 24;             // classes, padded to three n-blocks of 8 (forward) / 32 (backward k-blocks)
-constexpr int kSeg = 76;             // staged low-resolution row pitch (floats)
 constexpr int kThreads = 256;
-constexpr int kOutPitch = 132;       // floats; 132 mod 32 = 4: the accumulator scatter is bank-conflict free
 
 __device__ __forceinline__ void ldsm_x4(uint32_t addr, uint32_t (&r)[4]) {
   asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
@@ -59,19 +70,6 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
   const __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<const uint32_t*>(&h);
 }
-// two bf16 values of CONSECUTIVE CHANNELS (c, c+1): BN + ReLU with (scale_c, shift_c, scale_c1, shift_c1)
-__device__ __forceinline__ uint32_t bn_relu_pair_ch(uint32_t v, const float4 s) {
-  const float y0 = fmaxf(fmaf(s.x, __uint_as_float(v << 16), s.y), 0.f);
-  const float y1 = fmaxf(fmaf(s.z, __uint_as_float(v & 0xffff0000u), s.w), 0.f);
-  return pack_bf16(y0, y1);
-}
-// two bf16 values of ONE channel (two pixels): BN + ReLU with (scale, shift)
-__device__ __forceinline__ uint32_t bn_relu_pair_px(uint32_t v, const float2 s) {
-  const float y0 = fmaxf(fmaf(s.x, __uint_as_float(v << 16), s.y), 0.f);
-  const float y1 = fmaxf(fmaf(s.x, __uint_as_float(v & 0xffff0000u), s.y), 0.f);
-  return pack_bf16(y0, y1);
-}
-
 struct TailArgs {
   const __nv_bfloat16* y;          // Y_3 (N, IH, IW, 256) bf16 NHWC
   const int* idx_h; const int* idx_w;
@@ -80,327 +78,24 @@ struct TailArgs {
   const float* w2;                 // (K, 256) fp32
 };
 
-// the tile's source span of Y_3 -> shared memory [pixel][256 ch] (512-byte rows, 16-byte chunks XOR-swizzled by pixel & 7)
-__device__ __forceinline__ void gather_span(unsigned char* ysm, const TailArgs& a, int n, int oh, int w0, int w_last, int* s0_out) {
-  const int s0 = a.idx_w[w0], nsp = a.idx_w[w_last] - s0 + 1;
-  const __nv_bfloat16* yrow = a.y + (((size_t)n * a.IH + a.idx_h[oh]) * a.IW + s0) * kC;
-  for (int e = threadIdx.x; e < nsp * 32; e += kThreads) {
-    const int p = e >> 5, ch = e & 31;
-    const uint32_t dst = smem_u32(ysm + p * 512 + ((ch ^ (p & 7)) << 4));
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(yrow + (size_t)p * kC + ch * 8) : "memory");
-  }
-  asm volatile("cp.async.commit_group;" ::: "memory");
-  *s0_out = s0;
-}
 
-// ======================================================================================================
-// forward: out (N, K, OH, OW) = b2 + bilinear(T, align_corners) + W2 . ReLU(BN(gather(Y_3)))
-// ======================================================================================================
-constexpr size_t kFwdSmem = (size_t)kSpan * 512 + (size_t)kCls * 512 + kC * sizeof(float2) + (size_t)2 * kCls * kSeg * 4 +
-                            (size_t)kCls * kOutPitch * 4 + kPx * sizeof(float4) + kPx * sizeof(int);
-
-__global__ void __launch_bounds__(kThreads, 2)
-tail_final2_fwd_kernel(const TailArgs a, const float* __restrict__ tlo, int LH, int LW, const float* __restrict__ b2,
-                       float* __restrict__ out, int wtiles, int num_tiles) {
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  unsigned char* ysm = smem_raw;                                                        // [span px][256 ch bf16]
-  unsigned char* w2sm = ysm + (size_t)kSpan * 512;                                      // [24 classes][256 ch bf16]
-  float2* ss = reinterpret_cast<float2*>(w2sm + (size_t)kCls * 512);                    // (scale, shift) per channel
-  float* trow = reinterpret_cast<float*>(ss + kC);                                      // [row 0/1][class][kSeg]
-  float* outst = trow + 2 * kCls * kSeg;                                                // [class][kOutPitch]
-  float4* pix = reinterpret_cast<float4*>(outst + kCls * kOutPitch);                    // per pixel: o0, o1, wl0, wl1
-  int* spx = reinterpret_cast<int*>(pix + kPx);                                         // per pixel: source pixel - s0
-  __shared__ __align__(8) uint64_t bar;
-  const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
-  const int K = a.K;
-  if (t == 0) { mbar_init(&bar, 1); mbar_fence_init(); }
-  pdl_sync();
-  // classifier weights -> bf16 [class][channel], rows swizzled like the activations; BN table
-  for (int e = t; e < kCls * kC; e += kThreads) {
-    const int k = e >> 8, c = e & 255;
-    const float v = k < K ? a.w2[k * kC + c] : 0.f;
-    *reinterpret_cast<__nv_bfloat16*>(w2sm + k * 512 + (((c >> 3) ^ (k & 7)) << 4) + (c & 7) * 2) = __float2bfloat16_rn(v);
-  }
-  for (int c = t; c < kC; c += kThreads) ss[c] = make_float2(a.scale[c], a.shift[c]);
-  __syncthreads();
-  const float rh = a.OH > 1 ? (float)(LH - 1) / (float)(a.OH - 1) : 0.f;               // ATen upsample_bilinear2d(align_corners=True)
-  const float rw = a.OW > 1 ? (float)(LW - 1) / (float)(a.OW - 1) : 0.f;
-  uint32_t phase = 0;
-  for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-    const int wt = tile % wtiles, orow = tile / wtiles;
-    const int n = orow / a.OH, oh = orow - n * a.OH, w0 = wt * kPx;
-    const int w_last = min(w0 + kPx - 1, a.OW - 1);
-    const float h1r = rh * (float)oh;
-    const int h1 = (int)h1r, h1p = h1 < LH - 1 ? 1 : 0;
-    const float hl1 = h1r - (float)h1, hl0 = 1.f - hl1;
-    const int ws = (int)(rw * (float)w0) & ~3;
-    const int w_hi = min(LW - 1, (int)(rw * (float)w_last) + 1);
-    const int cnt = min(kSeg, (w_hi - ws + 4) & ~3);
-    if (t == 0) mbar_expect_tx(&bar, (uint32_t)(2 * K * cnt) * 4u);
-    __syncthreads();                                   // previous tile's readers are done; expect_tx precedes the copies
-    if (t < 2 * K) {                                   // the two low-resolution rows of every class
-      const int k = t >> 1, r = t & 1;
-      const float* src = tlo + (((size_t)n * K + k) * LH + h1 + (r ? h1p : 0)) * LW + ws;
-      bulk_load(trow + (size_t)(r * kCls + k) * kSeg, src, (uint32_t)cnt * 4u, &bar);
-    }
-    int s0;
-    gather_span(ysm, a, n, oh, w0, w_last, &s0);
-    if (t < kPx) {
-      const int ow = min(w0 + t, a.OW - 1);
-      const float w1r = rw * (float)ow;
-      const int w1 = (int)w1r;
-      const float wl1 = w1r - (float)w1;
-      pix[t] = make_float4(__int_as_float(w1 - ws), __int_as_float(w1 - ws + (w1 < LW - 1 ? 1 : 0)), 1.f - wl1, wl1);
-      spx[t] = a.idx_w[ow] - s0;
-    }
-    asm volatile("cp.async.wait_group 0;" ::: "memory");
-    mbar_wait(&bar, phase);
-    phase ^= 1u;
-    __syncthreads();
-    // vertical blend of the staged rows, in place over row 0
-    for (int e = t; e < K * (cnt >> 2); e += kThreads) {
-      const int k = e / (cnt >> 2), q = e - k * (cnt >> 2);
-      float4* p0 = reinterpret_cast<float4*>(trow + (size_t)k * kSeg) + q;
-      const float4 u = *p0, v = *(reinterpret_cast<const float4*>(trow + (size_t)(kCls + k) * kSeg) + q);
-      *p0 = make_float4(fmaf(hl1, v.x, hl0 * u.x), fmaf(hl1, v.y, hl0 * u.y), fmaf(hl1, v.z, hl0 * u.z), fmaf(hl1, v.w, hl0 * u.w));
-    }
-    // ---- contraction over the 256 channels: warp = 16 pixels, 3 n-blocks of 8 classes ----
-    {
-      const int g = lane >> 2, tq = lane & 3;
-      const int amat = lane >> 3, arow = (amat & 1) * 8 + (lane & 7), akc = amat >> 1;
-      const int sidx = spx[16 * warp + arow];
-      const uint32_t abase = smem_u32(ysm) + (uint32_t)sidx * 512u;
-      const int asw = sidx & 7;
-      const int bn01 = (amat >> 1) * 8 + (lane & 7), bkc = amat & 1;
-      const uint32_t bbase01 = smem_u32(w2sm) + (uint32_t)bn01 * 512u;
-      const int bn2 = 16 + (lane & 7), bkc2 = (lane >> 3) & 1;
-      const uint32_t bbase2 = smem_u32(w2sm) + (uint32_t)bn2 * 512u;
-      float acc[3][4];
-#pragma unroll
-      for (int i = 0; i < 3; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-#pragma unroll 4
-      for (int kb = 0; kb < kC / 16; ++kb) {
-        uint32_t af[4], b01[4], b2r[2];
-        ldsm_x4(abase + (uint32_t)(((kb * 2 + akc) ^ asw) << 4), af);
-        ldsm_x4(bbase01 + (uint32_t)(((kb * 2 + bkc) ^ (bn01 & 7)) << 4), b01);
-        ldsm_x2(bbase2 + (uint32_t)(((kb * 2 + bkc2) ^ (bn2 & 7)) << 4), b2r);
-        const float4 s0v = *reinterpret_cast<const float4*>(ss + kb * 16 + 2 * tq);
-        const float4 s1v = *reinterpret_cast<const float4*>(ss + kb * 16 + 8 + 2 * tq);
-        af[0] = bn_relu_pair_ch(af[0], s0v); af[1] = bn_relu_pair_ch(af[1], s0v);
-        af[2] = bn_relu_pair_ch(af[2], s1v); af[3] = bn_relu_pair_ch(af[3], s1v);
-        mma_bf16(acc[0], af, b01[0], b01[1]);
-        mma_bf16(acc[1], af, b01[2], b01[3]);
-        mma_bf16(acc[2], af, b2r[0], b2r[1]);
-      }
-#pragma unroll
-      for (int nb = 0; nb < 3; ++nb) {                 // c0,c1: (pixel g, class 2tq, 2tq+1); c2,c3: pixel g + 8
-        float* o = outst + (nb * 8 + 2 * tq) * kOutPitch + 16 * warp + g;
-        o[0] = acc[nb][0]; o[kOutPitch] = acc[nb][1]; o[8] = acc[nb][2]; o[kOutPitch + 8] = acc[nb][3];
-      }
-    }
-    __syncthreads();
-    // ---- + bias + horizontal taps of the blended low-resolution row, fp32 NCHW rows of 128 pixels ----
-    const bool vec = (a.OW & 3) == 0;
-    for (int e = t; e < K * (kPx / 4); e += kThreads) {
-      const int k = e >> 5, q = e & 31, px = 4 * q, ow = w0 + px;
-      if (ow >= a.OW) continue;
-      const float* vb = trow + (size_t)k * kSeg;
-      const float bias = b2 ? b2[k] : 0.f;
-      float r[4];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const float4 tp = pix[px + i];
-        r[i] = outst[k * kOutPitch + px + i] + bias + fmaf(tp.z, vb[__float_as_int(tp.x)], tp.w * vb[__float_as_int(tp.y)]);
-      }
-      float* op = out + (((size_t)n * K + k) * a.OH + oh) * a.OW + ow;
-      if (vec && ow + 3 < a.OW) *reinterpret_cast<float4*>(op) = make_float4(r[0], r[1], r[2], r[3]);
-      else
-        for (int i = 0; i < 4 && ow + i < a.OW; ++i) op[i] = r[i];
-    }
-  }
-}
-
-// ======================================================================================================
-// backward: dA3 (N, OH, OW, 256) bf16 = W2^T g;  gW2 (K, 256) += g . OCout_dec^T;  gb2 (K) += sum g
-// ======================================================================================================
-constexpr size_t kBwdSmem = (size_t)kSpan * 512 + (size_t)kPx * 64 + (size_t)32 * 256 + (size_t)kC * 64 + (size_t)kPx * 128 +
-                            kC * sizeof(float2) + kPx * sizeof(int) + 32 * sizeof(float);
-
-__global__ void __launch_bounds__(kThreads, 2)
-tail_final2_bwd_kernel(const TailArgs a, const float* __restrict__ g, __nv_bfloat16* __restrict__ dA, float* __restrict__ gW2,
-                       float* __restrict__ gb2, int wtiles, int num_tiles) {
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  unsigned char* ysm = smem_raw;                                   // [span px][256 ch bf16]
-  unsigned char* gT = ysm + (size_t)kSpan * 512;                   // [128 px][32 classes bf16]   (64-byte rows)
-  unsigned char* gC = gT + (size_t)kPx * 64;                       // [32 classes][128 px bf16]   (256-byte rows)
-  unsigned char* w2t = gC + (size_t)32 * 256;                      // [256 ch][32 classes bf16]   (64-byte rows)
-  unsigned char* stg = w2t + (size_t)kC * 64;                      // [128 px][64 ch bf16] store staging (128-byte rows)
-  float2* ss = reinterpret_cast<float2*>(stg + (size_t)kPx * 128);
-  int* spx = reinterpret_cast<int*>(ss + kC);
-  float* s_gb = reinterpret_cast<float*>(spx + kPx);               // [32] class sums of g
-  const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
-  const int K = a.K;
-  const int g8 = lane >> 2, tq = lane & 3;
-  pdl_sync();
-  // W2^T -> bf16 [channel][class], 16-byte chunks swizzled by (channel >> 1) & 3
-  for (int e = t; e < kC * 32; e += kThreads) {
-    const int c = e >> 5, k = e & 31;
-    const float v = k < K ? a.w2[k * kC + c] : 0.f;
-    *reinterpret_cast<__nv_bfloat16*>(w2t + c * 64 + (((k >> 3) ^ ((c >> 1) & 3)) << 4) + (k & 7) * 2) = __float2bfloat16_rn(v);
-  }
-  if (t < 32) s_gb[t] = 0.f;
-  for (int c = t; c < kC; c += kThreads) ss[c] = make_float2(a.scale[c], a.shift[c]);
-  // weight-gradient accumulators of this CTA: warp = 32 channels (4 n-blocks) x 2 m-tiles of 16 classes
-  float wacc[2][4][4];
-#pragma unroll
-  for (int i = 0; i < 2; ++i)
-#pragma unroll
-    for (int j = 0; j < 4; ++j)
-#pragma unroll
-      for (int q = 0; q < 4; ++q) wacc[i][j][q] = 0.f;
-  __syncthreads();
-
-  for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-    const int wt = tile % wtiles, orow = tile / wtiles;
-    const int n = orow / a.OH, oh = orow - n * a.OH, w0 = wt * kPx;
-    const int w_last = min(w0 + kPx - 1, a.OW - 1);
-    __syncthreads();                                   // previous tile's readers are done
-    int s0;
-    gather_span(ysm, a, n, oh, w0, w_last, &s0);
-    if (t < kPx) spx[t] = a.idx_w[min(w0 + t, a.OW - 1)] - s0;
-    // g tile (32 classes x 128 pixels; zero beyond K and beyond the row end) -> bf16 in both orientations
-    for (int e = t; e < 32 * (kPx / 2); e += kThreads) {
-      const int k = e >> 6, pp = (e & 63) * 2, ow = w0 + pp;
-      float v0 = 0.f, v1 = 0.f;
-      if (k < K) {
-        const float* gp = g + (((size_t)n * K + k) * a.OH + oh) * a.OW + ow;
-        if (ow < a.OW) v0 = __ldg(gp);
-        if (ow + 1 < a.OW) v1 = __ldg(gp + 1);
-      }
-      // gC[k][pp..pp+1]: 256-byte rows, chunk (pp >> 3) swizzled by k & 7
-      *reinterpret_cast<uint32_t*>(gC + k * 256 + (((pp >> 3) ^ (k & 7)) << 4) + (pp & 7) * 2) = pack_bf16(v0, v1);
-      // gT[pp][k], gT[pp+1][k]: 64-byte rows, chunk (k >> 3) swizzled by (px >> 1) & 3
-      *reinterpret_cast<__nv_bfloat16*>(gT + pp * 64 + (((k >> 3) ^ ((pp >> 1) & 3)) << 4) + (k & 7) * 2) = __float2bfloat16_rn(v0);
-      *reinterpret_cast<__nv_bfloat16*>(gT + (pp + 1) * 64 + (((k >> 3) ^ (((pp + 1) >> 1) & 3)) << 4) + (k & 7) * 2) = __float2bfloat16_rn(v1);
-      if (k < K) {                                     // bias gradient: the 64 lanes of a class row reduce through shuffles
-        float sg = v0 + v1;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) sg += __shfl_xor_sync(0xffffffffu, sg, o);
-        if (lane == 0) atomicAdd(&s_gb[k], sg);
-      }
-    }
-    asm volatile("cp.async.wait_group 0;" ::: "memory");
-    __syncthreads();
-
-    // ---- (1) dA3[px][ch] = sum_k g[k][px] W2[k][ch]: warp = 16 pixels, four passes of 64 channels ----
-    {
-      const int amat = lane >> 3, arow = (amat & 1) * 8 + (lane & 7), akc = amat >> 1;
-      const int prow = 16 * warp + arow;
-      uint32_t af[2][4];
-#pragma unroll
-      for (int kb = 0; kb < 2; ++kb)
-        ldsm_x4(smem_u32(gT + prow * 64 + (((kb * 2 + akc) ^ ((prow >> 1) & 3)) << 4)), af[kb]);
-      const int bn = (amat >> 1) * 8 + (lane & 7), bkc = amat & 1;     // rows of the B matrices: channels
-#pragma unroll 1
-      for (int pass = 0; pass < 4; ++pass) {
-        float acc[8][4];
-#pragma unroll
-        for (int i = 0; i < 8; ++i)
-#pragma unroll
-          for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-#pragma unroll
-        for (int np = 0; np < 4; ++np) {               // pairs of n-blocks: 16 channels
-          const int ch = pass * 64 + np * 16 + bn;
-#pragma unroll
-          for (int kb = 0; kb < 2; ++kb) {
-            uint32_t bf[4];
-            ldsm_x4(smem_u32(w2t + ch * 64 + (((kb * 2 + bkc) ^ ((ch >> 1) & 3)) << 4)), bf);
-            mma_bf16(acc[2 * np], af[kb], bf[0], bf[1]);
-            mma_bf16(acc[2 * np + 1], af[kb], bf[2], bf[3]);
-          }
-        }
-        __syncthreads();                               // staging tile free (previous pass stored)
-#pragma unroll
-        for (int nb = 0; nb < 8; ++nb) {               // c0,c1: (pixel g8, channels nb*8 + 2tq, +1); c2,c3: pixel g8 + 8
-          const int p0 = 16 * warp + g8, p1 = p0 + 8;
-          *reinterpret_cast<uint32_t*>(stg + p0 * 128 + ((nb ^ (p0 & 7)) << 4) + tq * 4) = pack_bf16(acc[nb][0], acc[nb][1]);
-          *reinterpret_cast<uint32_t*>(stg + p1 * 128 + ((nb ^ (p1 & 7)) << 4) + tq * 4) = pack_bf16(acc[nb][2], acc[nb][3]);
-        }
-        __syncthreads();
-        __nv_bfloat16* drow = dA + (((size_t)n * a.OH + oh) * a.OW + w0) * kC + pass * 64;
-#pragma unroll
-        for (int q = 0; q < kPx * 8 / kThreads; ++q) {
-          const int e = t + q * kThreads, px = e >> 3, chunk = e & 7;
-          if (w0 + px < a.OW)
-            *reinterpret_cast<uint4*>(drow + (size_t)px * kC + chunk * 8) =
-                *reinterpret_cast<const uint4*>(stg + px * 128 + ((chunk ^ (px & 7)) << 4));
-        }
-      }
-    }
-
-    // ---- (2) gW2[k][ch] += sum_px g[k][px] ReLU(BN(Y_3[src(px)][ch])): warp = channels [32 warp, +32) ----
-    {
-      const int amat = lane >> 3, arow = (amat & 1) * 8 + (lane & 7), akc = amat >> 1;   // A = gC: rows = classes, k = pixels
-      const int tm = lane >> 3;                        // B (.trans): matrices (k 0-7 | k 8-15) x (n-block j | j + 1)
-      const int brow = (tm & 1) * 8 + (lane & 7);      // pixel within the k-block
-      const int bnb = tm >> 1;                         // n-block within the pair
-      float2 sc[4];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) sc[j] = ss[32 * warp + j * 8 + g8];
-#pragma unroll 2
-      for (int kb = 0; kb < kPx / 16; ++kb) {
-        uint32_t a0[4], a1[4];
-        ldsm_x4(smem_u32(gC + arow * 256 + (((kb * 2 + akc) ^ (arow & 7)) << 4)), a0);
-        ldsm_x4(smem_u32(gC + (16 + arow) * 256 + (((kb * 2 + akc) ^ ((16 + arow) & 7)) << 4)), a1);
-        const int sidx = spx[kb * 16 + brow];
-#pragma unroll
-        for (int jp = 0; jp < 2; ++jp) {               // n-block pairs: channels 32 warp + 16 jp + {0..7, 8..15}
-          const int chunk = 4 * warp + 2 * jp + bnb;   // 16-byte chunk (8 channels) of the 512-byte pixel row
-          uint32_t bf[4];
-          ldsm_x4_t(smem_u32(ysm) + (uint32_t)sidx * 512u + (uint32_t)((chunk ^ (sidx & 7)) << 4), bf);
-          bf[0] = bn_relu_pair_px(bf[0], sc[2 * jp]); bf[1] = bn_relu_pair_px(bf[1], sc[2 * jp]);
-          bf[2] = bn_relu_pair_px(bf[2], sc[2 * jp + 1]); bf[3] = bn_relu_pair_px(bf[3], sc[2 * jp + 1]);
-          mma_bf16(wacc[0][2 * jp], a0, bf[0], bf[1]);
-          mma_bf16(wacc[0][2 * jp + 1], a0, bf[2], bf[3]);
-          mma_bf16(wacc[1][2 * jp], a1, bf[0], bf[1]);
-          mma_bf16(wacc[1][2 * jp + 1], a1, bf[2], bf[3]);
-        }
-      }
-    }
-  }
-  // ---- publish the CTA's weight- and bias-gradient partials ----
-  __syncthreads();
-#pragma unroll
-  for (int mt = 0; mt < 2; ++mt)
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int ch = 32 * warp + j * 8 + 2 * tq;
-      const int k0 = mt * 16 + g8, k1 = k0 + 8;
-      if (k0 < K) { atomicAdd(gW2 + k0 * kC + ch, wacc[mt][j][0]); atomicAdd(gW2 + k0 * kC + ch + 1, wacc[mt][j][1]); }
-      if (k1 < K) { atomicAdd(gW2 + k1 * kC + ch, wacc[mt][j][2]); atomicAdd(gW2 + k1 * kC + ch + 1, wacc[mt][j][3]); }
-    }
-  if (t < K) atomicAdd(gb2 + t, s_gb[t]);
-}
-
-// ======================================================================================================
-// Second form of both kernels: 64-pixel tiles whose inputs are DOUBLE-BUFFERED TMA copies issued by one thread (the next
-// tile's span of Y_3 — four SWIZZLE_128B boxes of 64 channels — and its fp32 side rows are in flight while the current
-// tile is contracted), and every operand that does not change from tile to tile — the classifier fragments and the BN
-// constants — held in registers of the persistent CTA instead of being re-read from shared memory for every k-block.
-// What was measured on the way (tools/trace_tail.py, profiles/README.md): per-thread cp.async copies and per-row bulk
-// copies cost the issuing warps 2400-4300 cycles per tile; a lane-indexed register pick compiles to divergent branches.
-// ======================================================================================================
+// Phase timeline for tools/trace_tail.py (build with MRFP_EXTRA_NVCC_FLAGS=-DMRFP_TAIL_TRACE): clock64 sums of thread 0 of
+// every CTA per phase of the tile loop; compiled out otherwise.
+#ifdef MRFP_TAIL_TRACE
 __device__ unsigned long long g_tail_dbg[16];
 #define TR_DECL unsigned long long tr_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0}; long long tr_t = clock64();
 #define TR(k) do { if (threadIdx.x == 0) { const long long _n = clock64(); tr_acc[k] += (unsigned long long)(_n - tr_t); tr_t = _n; } } while (0)
 #define TR_END(off) do { if (threadIdx.x == 0) { for (int _k = 0; _k < 8; ++_k) atomicAdd(&g_tail_dbg[(off) + _k], tr_acc[_k]); } } while (0)
-constexpr int kPx2 = 64;             // output pixels per tile
-constexpr int kSpan2 = 64;           // source pixels a tile's box holds (64 * 332/384 + 2 = 58 needed in the reference geometry)
-constexpr int kSeg2 = 44;            // staged low-resolution row pitch (floats): an Upsample by >= 2 needs <= 40
-constexpr int kOutPitch2 = 68;       // floats; 68 mod 32 = 4: the accumulator scatter is bank-conflict free
-constexpr uint32_t kSpanBytes2 = kSpan2 * 512;
+#else
+#define TR_DECL
+#define TR(k) do { } while (0)
+#define TR_END(off) do { } while (0)
+#endif
+constexpr int kPx = 64;             // output pixels per tile
+constexpr int kSpan = 64;           // source pixels a tile's box holds (64 * 332/384 + 2 = 58 needed in the reference geometry)
+constexpr int kSeg = 44;            // staged low-resolution row pitch (floats): an Upsample by >= 2 needs <= 40
+constexpr int kOutPitch = 68;       // floats; 68 mod 32 = 4: the accumulator scatter is bank-conflict free
+constexpr uint32_t kSpanBytes = kSpan * 512;
 
 __device__ __forceinline__ void tma_2d(uint32_t dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
   asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
@@ -413,7 +108,7 @@ __device__ __forceinline__ void tma_3d(uint32_t dst, const CUtensorMap* map, uin
 // a span buffer is four boxes [64 px][64 ch] (128-byte rows, 16-byte chunks XOR-swizzled by pixel & 7): address of the
 // 16-byte chunk `chunk` (8 channels, 0..31) of source pixel `p`
 __device__ __forceinline__ uint32_t span_addr(uint32_t base, int p, int chunk) {
-  return base + (uint32_t)(chunk >> 3) * (uint32_t)(kSpan2 * 128) + (uint32_t)p * 128u + (uint32_t)(((chunk & 7) ^ (p & 7)) << 4);
+  return base + (uint32_t)(chunk >> 3) * (uint32_t)(kSpan * 128) + (uint32_t)p * 128u + (uint32_t)(((chunk & 7) ^ (p & 7)) << 4);
 }
 
 struct TileXY { int n, oh, w0, w_last; };
@@ -435,7 +130,7 @@ struct TileWalk {
   }
   __device__ __forceinline__ TileXY xy() const {
     TileXY c;
-    c.n = n; c.oh = oh; c.w0 = wt * kPx2; c.w_last = min(c.w0 + kPx2 - 1, OW - 1);
+    c.n = n; c.oh = oh; c.w0 = wt * kPx; c.w_last = min(c.w0 + kPx - 1, OW - 1);
     return c;
   }
 };
@@ -466,21 +161,22 @@ __device__ __forceinline__ unsigned char* smem_1k(unsigned char* raw) {
   return raw + (((a + 1023u) & ~1023u) - a);
 }
 
-constexpr size_t kFwd2Smem = 1024 + (size_t)2 * kSpanBytes2 + (size_t)4 * kCls * kOutPitch2 * 4 + (size_t)2 * 2 * kCls * kSeg2 * 4 +
-                             kPx2 * sizeof(float4) + kPx2 * sizeof(int) + 16;
+constexpr size_t kFwdSmem = 1024 + (size_t)2 * kSpanBytes + (size_t)4 * kCls * kOutPitch * 4 + (size_t)2 * 2 * kCls * kSeg * 4 +
+                             16;       // + the index tables: (wtiles * 65 + OH) ints
 
 // forward: warp = (channel quarter q, pixel-group pair u): 2 x 16 pixels x 64 channels x 24 classes; the four quarter
 // sums of a pixel meet in the epilogue
 __global__ void __launch_bounds__(kThreads, 2)
-tail_final2_fwd2_kernel(const __grid_constant__ CUtensorMap tm_y, const __grid_constant__ CUtensorMap tm_lo, const TailArgs a,
+tail_final2_fwd_kernel(const __grid_constant__ CUtensorMap tm_y, const __grid_constant__ CUtensorMap tm_lo, const TailArgs a,
                         int LH, int LW, const float* __restrict__ b2, float* __restrict__ out, int wtiles, int num_tiles) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   unsigned char* ysm = smem_1k(smem_raw);                                               // [2][4 boxes][64 px][64 ch bf16]
-  float* outst = reinterpret_cast<float*>(ysm + (size_t)2 * kSpanBytes2);               // [quarter][class][kOutPitch2]
-  float* trow = outst + 4 * kCls * kOutPitch2;                                          // [buffer][row 0/1][class][kSeg2]
-  float4* pix = reinterpret_cast<float4*>(trow + 2 * 2 * kCls * kSeg2);                 // per pixel: o0, o1, wl0, wl1
-  int* spx = reinterpret_cast<int*>(pix + kPx2);                                        // per pixel: source pixel - s0
-  uint64_t* bar = reinterpret_cast<uint64_t*>(spx + kPx2);                              // [2] full barriers
+  float* outst = reinterpret_cast<float*>(ysm + (size_t)2 * kSpanBytes);               // [quarter][class][kOutPitch]
+  float* trow = outst + 4 * kCls * kOutPitch;                                          // [buffer][class][row 0/1][kSeg]
+  uint64_t* bar = reinterpret_cast<uint64_t*>(trow + 2 * 2 * kCls * kSeg);             // [2] full barriers
+  int* rel = reinterpret_cast<int*>(bar + 2);                                           // [wtiles * 64]: source pixel - the tile's first
+  int* wstart = rel + wtiles * kPx;                                                    // [wtiles]: first source pixel of a tile
+  int* hsrc = wstart + wtiles;                                                          // [OH]: source row of an output row
   const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
   const int K = a.K;
   const int g = lane >> 2, tq = lane & 3;
@@ -498,6 +194,9 @@ tail_final2_fwd2_kernel(const __grid_constant__ CUtensorMap tm_y, const __grid_c
     const float v = k < K ? a.w2[k * kC + c] : 0.f;
     *reinterpret_cast<__nv_bfloat16*>(ysm + k * 512 + (((c >> 3) ^ (k & 7)) << 4) + (c & 7) * 2) = __float2bfloat16_rn(v);
   }
+  for (int e = t; e < wtiles * kPx; e += kThreads) rel[e] = a.idx_w[min(e, a.OW - 1)] - a.idx_w[e & ~(kPx - 1)];
+  for (int e = t; e < wtiles; e += kThreads) wstart[e] = a.idx_w[e * kPx];
+  for (int e = t; e < a.OH; e += kThreads) hsrc[e] = a.idx_h[e];
   __syncthreads();
   uint32_t bq[4][6];
   uint64_t sq[4][4];                                    // per k-block: (scale, scale), (shift, shift) of channels 2tq, +1 | 8 + 2tq, +1
@@ -520,19 +219,16 @@ tail_final2_fwd2_kernel(const __grid_constant__ CUtensorMap tm_y, const __grid_c
   __syncthreads();                                     // the staging region becomes span buffer 0
   const float rh = a.OH > 1 ? (float)(LH - 1) / (float)(a.OH - 1) : 0.f;               // ATen upsample_bilinear2d(align_corners=True)
   const float rw = a.OW > 1 ? (float)(LW - 1) / (float)(a.OW - 1) : 0.f;
-  // one thread: the tile's span of Y_3 (4 boxes) and the two low-resolution rows of every class (2 boxes of [K][kSeg2];
-  // columns beyond the row end arrive as zeros)
+  // one thread: the tile's span of Y_3 (one box: 64 px x 4 groups of 64 channels) and the two low-resolution rows of
+  // every class (one box [K][2][kSeg]; columns beyond the row end and the row below the last arrive as zeros)
+  // (no thread ever writes a TMA-target buffer after the prologue, so the issue needs no proxy fence)
   auto issue = [&](const TileXY& c, int b) {
-    const int h1 = (int)(rh * (float)c.oh), h1p = h1 < LH - 1 ? 1 : 0;
+    const int h1 = (int)(rh * (float)c.oh);
     const int ws = (int)(rw * (float)c.w0) & ~3;
-    const int pix0 = (c.n * a.IH + a.idx_h[c.oh]) * a.IW + a.idx_w[c.w0];
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    mbar_expect_tx(&bar[b], 4u * (uint32_t)(kSpan2 * 128) + 2u * (uint32_t)K * (uint32_t)(kSeg2 * 4));
-    const uint32_t yb = smem_u32(ysm) + (uint32_t)b * kSpanBytes2;
-#pragma unroll
-    for (int j = 0; j < 4; ++j) tma_2d(yb + (uint32_t)j * (uint32_t)(kSpan2 * 128), &tm_y, &bar[b], 64 * j, pix0);
-    tma_3d(smem_u32(trow + (size_t)(b * 2 + 0) * kCls * kSeg2), &tm_lo, &bar[b], ws, h1, c.n * K);
-    tma_3d(smem_u32(trow + (size_t)(b * 2 + 1) * kCls * kSeg2), &tm_lo, &bar[b], ws, h1 + h1p, c.n * K);
+    const int pix0 = (c.n * a.IH + hsrc[c.oh]) * a.IW + wstart[c.w0 / kPx];
+    mbar_expect_tx(&bar[b], kSpanBytes + 2u * (uint32_t)K * (uint32_t)(kSeg * 4));
+    tma_3d(smem_u32(ysm) + (uint32_t)b * kSpanBytes, &tm_y, &bar[b], 0, pix0, 0);
+    tma_3d(smem_u32(trow + (size_t)b * 2 * kCls * kSeg), &tm_lo, &bar[b], ws, h1, c.n * K);
   };
   TileWalk walk(a, blockIdx.x, gridDim.x, wtiles);
   if (t == 0) issue(walk.xy(), 0);
@@ -541,37 +237,20 @@ tail_final2_fwd2_kernel(const __grid_constant__ CUtensorMap tm_y, const __grid_c
   for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
     const int b = it & 1;
     const TileXY c = walk.xy();
-    walk.advance();
     __syncthreads();                                   // (A) the previous tile is consumed: the other buffers are free
     TR(0);
+    walk.advance();
     if (t == 0 && tile + (int)gridDim.x < num_tiles) issue(walk.xy(), b ^ 1);
     const float h1r = rh * (float)c.oh;
     const float hl1 = h1r - (float)(int)h1r, hl0 = 1.f - hl1;
     const int ws = (int)(rw * (float)c.w0) & ~3;
-    if (t < kPx2) {
-      const int ow = min(c.w0 + t, a.OW - 1);
-      const float w1r = rw * (float)ow;
-      const int w1 = (int)w1r;
-      const float wl1 = w1r - (float)w1;
-      pix[t] = make_float4(__int_as_float(w1 - ws), __int_as_float(w1 - ws + (w1 < LW - 1 ? 1 : 0)), 1.f - wl1, wl1);
-      spx[t] = a.idx_w[ow] - a.idx_w[c.w0];
-    }
     TR(1);
-    mbar_wait(&bar[b], (uint32_t)(it >> 1) & 1u);
+    mbar_wait(&bar[b], (uint32_t)(it >> 1) & 1u);      // the copies are visible through the barrier
     TR(2);
-    __syncthreads();                                   // (B) pix / spx are visible (the copies are, through the barrier)
-    TR(4);
-    float* tr = trow + (size_t)b * 2 * kCls * kSeg2;
-    for (int e = t; e < K * 16; e += kThreads) {       // vertical blend of the staged rows, in place over row 0
-      const int k = e >> 4, qd = e & 15;
-      if (qd >= kSeg2 / 4) continue;
-      float4* p0 = reinterpret_cast<float4*>(tr + (size_t)k * kSeg2) + qd;
-      const float4 x0 = *p0, x1 = *(reinterpret_cast<const float4*>(tr + (size_t)(kCls + k) * kSeg2) + qd);
-      *p0 = make_float4(fmaf(hl1, x1.x, hl0 * x0.x), fmaf(hl1, x1.y, hl0 * x0.y), fmaf(hl1, x1.z, hl0 * x0.z), fmaf(hl1, x1.w, hl0 * x0.w));
-    }
+    const float* tr = trow + (size_t)b * 2 * kCls * kSeg;
     {
-      const int sidx0 = spx[32 * u + arow], sidx1 = spx[32 * u + 16 + arow];
-      const uint32_t ybase = smem_u32(ysm) + (uint32_t)b * kSpanBytes2;
+      const int sidx0 = rel[c.w0 + 32 * u + arow], sidx1 = rel[c.w0 + 32 * u + 16 + arow];
+      const uint32_t ybase = smem_u32(ysm) + (uint32_t)b * kSpanBytes;
       float acc[2][3][4];
 #pragma unroll
       for (int i = 0; i < 2; ++i)
@@ -600,33 +279,34 @@ tail_final2_fwd2_kernel(const __grid_constant__ CUtensorMap tm_y, const __grid_c
       for (int i = 0; i < 2; ++i)
 #pragma unroll
         for (int nb = 0; nb < 3; ++nb) {               // c0,c1: (pixel g, class 2tq, 2tq+1); c2,c3: pixel g + 8
-          float* o = outst + (size_t)q * kCls * kOutPitch2 + (nb * 8 + 2 * tq) * kOutPitch2 + 32 * u + 16 * i + g;
-          o[0] = acc[i][nb][0]; o[kOutPitch2] = acc[i][nb][1]; o[8] = acc[i][nb][2]; o[kOutPitch2 + 8] = acc[i][nb][3];
+          float* o = outst + (size_t)q * kCls * kOutPitch + (nb * 8 + 2 * tq) * kOutPitch + 32 * u + 16 * i + g;
+          o[0] = acc[i][nb][0]; o[kOutPitch] = acc[i][nb][1]; o[8] = acc[i][nb][2]; o[kOutPitch + 8] = acc[i][nb][3];
         }
     }
     TR(5);
     __syncthreads();                                   // (C)
     TR(6);
-    // ---- quarter sums + bias + horizontal taps of the blended low-resolution row, fp32 NCHW rows of 64 pixels ----
-    const bool vec = (a.OW & 3) == 0;
-    for (int e = t; e < K * (kPx2 / 4); e += kThreads) {
-      const int k = e >> 4, qd = e & 15, px = 4 * qd, ow = c.w0 + px;
-      if (ow >= a.OW) continue;
-      const float* vb = tr + (size_t)k * kSeg2;
-      const float bias = b2 ? b2[k] : 0.f;
-      const float* op0 = outst + k * kOutPitch2 + px;
-      const float4 p0 = *reinterpret_cast<const float4*>(op0), p1 = *reinterpret_cast<const float4*>(op0 + kCls * kOutPitch2);
-      const float4 p2 = *reinterpret_cast<const float4*>(op0 + 2 * kCls * kOutPitch2), p3 = *reinterpret_cast<const float4*>(op0 + 3 * kCls * kOutPitch2);
-      float r[4] = {(p0.x + p1.x) + (p2.x + p3.x), (p0.y + p1.y) + (p2.y + p3.y), (p0.z + p1.z) + (p2.z + p3.z), (p0.w + p1.w) + (p2.w + p3.w)};
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const float4 tp = pix[px + i];
-        r[i] += bias + fmaf(tp.z, vb[__float_as_int(tp.x)], tp.w * vb[__float_as_int(tp.y)]);
+    // ---- quarter sums + bias + the four bilinear taps (ATen's order: rows outside, columns inside): thread = one pixel,
+    //      classes cg, cg + 4, ...; a warp writes 128 contiguous bytes of one fp32 NCHW row per class ----
+    {
+      const int px = t & (kPx - 1), cg = t >> 6, ow = c.w0 + px;
+      if (ow < a.OW) {
+        const float w1r = rw * (float)ow;
+        const int w1 = (int)w1r;
+        const float wl1 = w1r - (float)w1, wl0 = 1.f - wl1;
+        const int x0 = w1 - ws, x1 = x0 + (w1 < LW - 1 ? 1 : 0);
+        float* op = out + (((size_t)c.n * K + cg) * a.OH + c.oh) * a.OW + ow;
+        const size_t plane4 = (size_t)4 * a.OH * a.OW;
+#pragma unroll 2
+        for (int k = cg; k < K; k += 4, op += plane4) {
+          const float* v0 = tr + (size_t)k * 2 * kSeg;
+          const float* v1 = v0 + kSeg;
+          const float* o = outst + k * kOutPitch + px;
+          const float acc = (o[0] + o[kCls * kOutPitch]) + (o[2 * kCls * kOutPitch] + o[3 * kCls * kOutPitch]);
+          const float up = hl0 * fmaf(wl0, v0[x0], wl1 * v0[x1]) + hl1 * fmaf(wl0, v1[x0], wl1 * v1[x1]);
+          *op = acc + ((b2 ? b2[k] : 0.f) + up);
+        }
       }
-      float* op = out + (((size_t)c.n * K + k) * a.OH + c.oh) * a.OW + ow;
-      if (vec && ow + 3 < a.OW) *reinterpret_cast<float4*>(op) = make_float4(r[0], r[1], r[2], r[3]);
-      else
-        for (int i = 0; i < 4 && ow + i < a.OW; ++i) op[i] = r[i];
     }
     TR(7);
   }
@@ -647,20 +327,23 @@ __device__ __forceinline__ uint4 quad_transpose(const uint32_t (&r)[4], int tq) 
   return o;
 }
 
-constexpr size_t kBwd2Smem = 1024 + (size_t)2 * kSpanBytes2 + (size_t)32 * kPx2 * 2 + (size_t)2 * 32 * kPx2 * 4 + kPx2 * sizeof(int) + 16;
+constexpr size_t kBwdSmem = 1024 + (size_t)2 * kSpanBytes + (size_t)32 * kPx * 2 + (size_t)2 * 32 * kPx * 4 + 16;
+                             // + the index tables: (wtiles * 65 + OH) ints
 
 // backward: warp = channels [32 warp, +32) in both products.  g_tma: g arrives as one [K][64] box per tile; otherwise
 // (rows of g not 16-byte aligned) through plain loads
 __global__ void __launch_bounds__(kThreads, 2)
-tail_final2_bwd2_kernel(const __grid_constant__ CUtensorMap tm_y, const __grid_constant__ CUtensorMap tm_g, const TailArgs a,
+tail_final2_bwd_kernel(const __grid_constant__ CUtensorMap tm_y, const __grid_constant__ CUtensorMap tm_g, const TailArgs a,
                         const float* __restrict__ gsrc, int g_tma, __nv_bfloat16* __restrict__ dA, float* __restrict__ gW2,
                         float* __restrict__ gb2, int wtiles, int num_tiles) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   unsigned char* ysm = smem_1k(smem_raw);                          // [2][4 boxes][64 px][64 ch bf16]
-  unsigned char* gC = ysm + (size_t)2 * kSpanBytes2;               // [32 classes][64 px bf16]   (128-byte rows, swizzled)
-  float* gF = reinterpret_cast<float*>(gC + (size_t)32 * kPx2 * 2);   // [2][32 classes][64 px fp32]: g as it arrives
-  int* spx = reinterpret_cast<int*>(gF + 2 * 32 * kPx2);
-  uint64_t* bar = reinterpret_cast<uint64_t*>(spx + kPx2);         // [2] full barriers
+  unsigned char* gC = ysm + (size_t)2 * kSpanBytes;               // [32 classes][64 px bf16]   (128-byte rows, swizzled)
+  float* gF = reinterpret_cast<float*>(gC + (size_t)32 * kPx * 2);   // [2][32 classes][64 px fp32]: g as it arrives
+  uint64_t* bar = reinterpret_cast<uint64_t*>(gF + 2 * 32 * kPx);   // [2] full barriers
+  int* rel = reinterpret_cast<int*>(bar + 2);                      // [wtiles * 64]: source pixel - the tile's first
+  int* wstart = rel + wtiles * kPx;                               // [wtiles]: first source pixel of a tile
+  int* hsrc = wstart + wtiles;                                     // [OH]: source row of an output row
   const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
   const int K = a.K;
   const int g8 = lane >> 2, tq = lane & 3;
@@ -677,7 +360,10 @@ tail_final2_bwd2_kernel(const __grid_constant__ CUtensorMap tm_y, const __grid_c
     const float v = k < K ? a.w2[k * kC + c] : 0.f;
     *reinterpret_cast<__nv_bfloat16*>(ysm + c * 64 + (((k >> 3) ^ ((c >> 1) & 3)) << 4) + (k & 7) * 2) = __float2bfloat16_rn(v);
   }
-  for (int e = t; e < 2 * 32 * kPx2; e += kThreads) gF[e] = 0.f;    // rows of classes >= K stay zero from here on
+  for (int e = t; e < 2 * 32 * kPx; e += kThreads) gF[e] = 0.f;    // rows of classes >= K stay zero from here on
+  for (int e = t; e < wtiles * kPx; e += kThreads) rel[e] = a.idx_w[min(e, a.OW - 1)] - a.idx_w[e & ~(kPx - 1)];
+  for (int e = t; e < wtiles; e += kThreads) wstart[e] = a.idx_w[e * kPx];
+  for (int e = t; e < a.OH; e += kThreads) hsrc[e] = a.idx_h[e];
   __syncthreads();
   uint32_t w1b[2][2][4];                                // [16-channel pair np][class k-block][n-block 2np: b0 b1 | 2np + 1: b0 b1]
   {
@@ -707,21 +393,19 @@ tail_final2_bwd2_kernel(const __grid_constant__ CUtensorMap tm_y, const __grid_c
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // staging writes and the zero fill precede the TMA writes
   __syncthreads();                                      // the staging region becomes span buffer 0
 
-  // one thread: the tile's span of Y_3 (4 boxes) and its [K][64] box of g (pixels beyond the row end arrive as zeros)
+  // one thread: the tile's span of Y_3 (one box: 64 px x 4 groups of 64 channels) and its [K][64] box of g (pixels beyond the row end arrive as zeros)
+  // (no thread ever writes a TMA-target buffer after the prologue, so the issue needs no proxy fence)
   auto issue = [&](const TileXY& c, int b) {
-    const int pix0 = (c.n * a.IH + a.idx_h[c.oh]) * a.IW + a.idx_w[c.w0];
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    mbar_expect_tx(&bar[b], 4u * (uint32_t)(kSpan2 * 128) + (g_tma ? (uint32_t)K * (uint32_t)(kPx2 * 4) : 0u));
-    const uint32_t yb = smem_u32(ysm) + (uint32_t)b * kSpanBytes2;
-#pragma unroll
-    for (int j = 0; j < 4; ++j) tma_2d(yb + (uint32_t)j * (uint32_t)(kSpan2 * 128), &tm_y, &bar[b], 64 * j, pix0);
-    if (g_tma) tma_3d(smem_u32(gF + (size_t)b * 32 * kPx2), &tm_g, &bar[b], c.w0, c.oh, c.n * K);
+    const int pix0 = (c.n * a.IH + hsrc[c.oh]) * a.IW + wstart[c.w0 / kPx];
+    mbar_expect_tx(&bar[b], kSpanBytes + (g_tma ? (uint32_t)K * (uint32_t)(kPx * 4) : 0u));
+    tma_3d(smem_u32(ysm) + (uint32_t)b * kSpanBytes, &tm_y, &bar[b], 0, pix0, 0);
+    if (g_tma) tma_3d(smem_u32(gF + (size_t)b * 32 * kPx), &tm_g, &bar[b], c.w0, c.oh, c.n * K);
   };
   auto load_g_slow = [&](const TileXY& c, int b) {       // every thread: generic loads into the staging tile
-    float* dstb = gF + (size_t)b * 32 * kPx2;
-    for (int e = t; e < K * kPx2; e += kThreads) {
+    float* dstb = gF + (size_t)b * 32 * kPx;
+    for (int e = t; e < K * kPx; e += kThreads) {
       const int k = e >> 6, px = e & 63, ow = c.w0 + px;
-      dstb[k * kPx2 + px] = ow < a.OW ? __ldg(gsrc + (((size_t)c.n * K + k) * a.OH + c.oh) * a.OW + ow) : 0.f;
+      dstb[k * kPx + px] = ow < a.OW ? __ldg(gsrc + (((size_t)c.n * K + k) * a.OH + c.oh) * a.OW + ow) : 0.f;
     }
   };
   TileWalk walk(a, blockIdx.x, gridDim.x, wtiles);
@@ -732,36 +416,35 @@ tail_final2_bwd2_kernel(const __grid_constant__ CUtensorMap tm_y, const __grid_c
   for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
     const int b = it & 1;
     const TileXY c = walk.xy();
-    walk.advance();
     const bool more = tile + (int)gridDim.x < num_tiles;
     __syncthreads();                                   // (A) the previous tile is consumed
     TR(0);
+    walk.advance();
     if (more) {
       if (t == 0) issue(walk.xy(), b ^ 1);
       if (!g_tma) load_g_slow(walk.xy(), b ^ 1);
     }
     TR(1);
-    if (t < kPx2) spx[t] = a.idx_w[min(c.w0 + t, a.OW - 1)] - a.idx_w[c.w0];
     TR(2);
     mbar_wait(&bar[b], (uint32_t)(it >> 1) & 1u);
     TR(3);
     {
-      const float* gb = gF + (size_t)b * 32 * kPx2;
+      const float* gb = gF + (size_t)b * 32 * kPx;
 #pragma unroll
       for (int i = 0; i < 4; ++i) {                    // g tile -> bf16 [class][pixel]: a warp writes one whole 128-byte row
         const int k = warp + 8 * i;
-        const float2 v = *reinterpret_cast<const float2*>(gb + k * kPx2 + 2 * lane);
+        const float2 v = *reinterpret_cast<const float2*>(gb + k * kPx + 2 * lane);
         *reinterpret_cast<uint32_t*>(gC + k * 128 + (((lane >> 2) ^ (k & 7)) << 4) + (lane & 3) * 4) = pack_bf16(v.x, v.y);
         sg[i] += v.x + v.y;
       }
     }
-    __syncthreads();                                   // (B) gC and spx are visible
+    __syncthreads();                                   // (B) gC is visible
     TR(4);
-    const uint32_t ybase = smem_u32(ysm) + (uint32_t)b * kSpanBytes2;
+    const uint32_t ybase = smem_u32(ysm) + (uint32_t)b * kSpanBytes;
 
     // ---- (1) dA3[px][ch] = sum_k g[k][px] W2[k][ch]: A fragments by ldmatrix.trans from gC, results leave from registers ----
 #pragma unroll 2
-    for (int mt = 0; mt < kPx2 / 16; ++mt) {
+    for (int mt = 0; mt < kPx / 16; ++mt) {
       uint32_t af[2][4];
 #pragma unroll
       for (int kb = 0; kb < 2; ++kb) {                 // matrices: (px 0-7 | px 8-15) x (classes 16 kb + 0-7 | + 8-15)
@@ -797,11 +480,11 @@ tail_final2_bwd2_kernel(const __grid_constant__ CUtensorMap tm_y, const __grid_c
       const int brow = (tm & 1) * 8 + (lane & 7);      // pixel within the k-block
       const int bnb = tm >> 1;                         // n-block within the pair
 #pragma unroll 2
-      for (int kb = 0; kb < kPx2 / 16; ++kb) {
+      for (int kb = 0; kb < kPx / 16; ++kb) {
         uint32_t a0[4], a1[4];
         ldsm_x4(smem_u32(gC + arow * 128 + (((kb * 2 + akc) ^ (arow & 7)) << 4)), a0);
         ldsm_x4(smem_u32(gC + (16 + arow) * 128 + (((kb * 2 + akc) ^ ((16 + arow) & 7)) << 4)), a1);
-        const int sidx = spx[kb * 16 + brow];
+        const int sidx = rel[c.w0 + kb * 16 + brow];
 #pragma unroll
         for (int jp = 0; jp < 2; ++jp) {               // n-block pairs: channels 32 warp + 16 jp + {0..7, 8..15}
           const int chunk = 4 * warp + 2 * jp + bnb;   // 16-byte chunk (8 channels) of the pixel's 256 channels
@@ -836,15 +519,16 @@ tail_final2_bwd2_kernel(const __grid_constant__ CUtensorMap tm_y, const __grid_c
   }
 }
 
-int tail_args(const mrfp_hrfp_plan* P, const void* saved, const void* lut, const float* w2, int K, TailArgs* a, int px, int span) {
+int tail_args(const mrfp_hrfp_plan* P, const void* saved, const void* lut, const float* w2, int K, TailArgs* a) {
   if (P->mode != MRFP_MATH_BF16) return MRFP_ERR_UNSUPPORTED;
   const HrfpStage& st = P->st[3];
   if (st.cout != kC || K <= 0 || K > kCls) return MRFP_ERR_UNSUPPORTED;
   const int* hidx = P->lut.data() + st.idx_w;           // every tile's source span must fit the buffer
-  for (int w0 = 0; w0 < st.ow; w0 += px) {
-    const int w1 = (w0 + px < st.ow ? w0 + px : st.ow) - 1;
-    if (hidx[w1] - hidx[w0] + 1 > span) return MRFP_ERR_UNSUPPORTED;
+  for (int w0 = 0; w0 < st.ow; w0 += kPx) {
+    const int w1 = (w0 + kPx < st.ow ? w0 + kPx : st.ow) - 1;
+    if (hidx[w1] - hidx[w0] + 1 > kSpan) return MRFP_ERR_UNSUPPORTED;
   }
+  if ((long long)P->N * st.ch * st.cw > 0x7fffffffLL) return MRFP_ERR_BAD_SHAPE;   // pixel coordinate of the tensor map
   const float* stats = reinterpret_cast<const float*>((const char*)saved + P->stats_off) + (size_t)3 * 4 * kMaxC;
   a->y = reinterpret_cast<const __nv_bfloat16*>((const char*)saved + st.y_off);
   a->idx_h = (const int*)lut + st.idx_h; a->idx_w = (const int*)lut + st.idx_w;
@@ -855,23 +539,25 @@ int tail_args(const mrfp_hrfp_plan* P, const void* saved, const void* lut, const
 }
 
 // the launch's two descriptors, cached in the plan per direction and re-encoded when an address or a shape changes
-int tail_maps(const mrfp_hrfp_plan* P, int dir, const TailArgs& a, const float* aux, int d0, int d1, int box_w, bool want_aux,
-              TailMaps* out) {
+int tail_maps(const mrfp_hrfp_plan* P, int dir, const TailArgs& a, const float* aux, int d0, int d1, int box_w, int box_h,
+              bool want_aux, TailMaps* out) {
   std::lock_guard<std::mutex> lock(P->mu);
   TailMaps* m = &P->maps_tail[dir];
   if (!m->valid || m->key[0] != a.y || m->key[1] != aux || m->k != a.K || m->d0 != d0 || m->d1 != d1) {
     m->valid = 0;
     {
-      const cuuint64_t dims[2] = {(cuuint64_t)kC, (cuuint64_t)a.N * a.IH * a.IW};
-      const cuuint64_t strides[1] = {(cuuint64_t)kC * 2};
-      const cuuint32_t box[2] = {64, kSpan2};
-      int rc = conv_make_map(&m->y, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, a.y, 2, dims, strides, box, true);
+      // Y_3 as [4 groups of 64 channels][pixel][64 channels]: one box = 64 pixels x 4 groups, which lands as four
+      // SWIZZLE_128B tiles of [64 px][128 bytes]
+      const cuuint64_t dims[3] = {64, (cuuint64_t)a.N * a.IH * a.IW, 4};
+      const cuuint64_t strides[2] = {(cuuint64_t)kC * 2, 128};
+      const cuuint32_t box[3] = {64, kSpan, 4};
+      int rc = conv_make_map(&m->y, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, a.y, 3, dims, strides, box, true);
       if (rc) return rc;
     }
     if (want_aux) {                                      // fp32 (N * K, d0, d1): one box = box_w columns of one row of K planes
       const cuuint64_t dims[3] = {(cuuint64_t)d1, (cuuint64_t)d0, (cuuint64_t)a.N * a.K};
       const cuuint64_t strides[2] = {(cuuint64_t)d1 * 4, (cuuint64_t)d0 * d1 * 4};
-      const cuuint32_t box[3] = {(cuuint32_t)box_w, 1, (cuuint32_t)a.K};
+      const cuuint32_t box[3] = {(cuuint32_t)box_w, (cuuint32_t)box_h, (cuuint32_t)a.K};
       int rc = conv_make_map(&m->aux, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, aux, 3, dims, strides, box, false);
       if (rc) return rc;
     } else {
@@ -894,33 +580,26 @@ extern "C" int mrfp_hrfp_tail_final2_fwd(const mrfp_hrfp_plan_t* P, const void* 
   if (!P || P->magic != kPlanMagic) return MRFP_ERR_BAD_PLAN;
   if (!saved || !lut || !t_lo || !w2 || !out) return MRFP_ERR_NULL_POINTER;
   if (lh <= 0 || lw <= 0) return MRFP_ERR_BAD_SHAPE;
-  static const int v2 = getenv("MRFP_TAIL_V") ? atoi(getenv("MRFP_TAIL_V")) : 2;
   TailArgs a;
-  int rc = tail_args(P, saved, lut, w2, K, &a, v2 == 2 ? kPx2 : kPx, v2 == 2 ? kSpan2 : kSpan);
+  int rc = tail_args(P, saved, lut, w2, K, &a);
   if (rc) return rc;
-  // the staged low-resolution span: an Upsample by >= 2 (as the reference's), rows 16-byte aligned for the bulk copies
+  // the staged low-resolution span: an Upsample by >= 2 (as the reference's), rows 16-byte aligned for the tensor map
   if (lw > a.OW || lh > a.OH || !(a.OW > 1 && 2 * (lw - 1) <= a.OW - 1) || (lw & 3) || ((uintptr_t)t_lo & 15)) return MRFP_ERR_UNSUPPORTED;
   DeviceInfo di;
   rc = get_device_info(&di);
   if (rc) return rc;
-  const int px = v2 == 2 ? kPx2 : kPx;
-  const int wtiles = (a.OW + px - 1) / px;
+  const int wtiles = (a.OW + kPx - 1) / kPx;
   const long long tiles = (long long)a.N * a.OH * wtiles;
   if (tiles > 0x7fffffffLL) return MRFP_ERR_BAD_SHAPE;
   const int grid = (int)(tiles < 2LL * di.sm_count ? tiles : 2LL * di.sm_count);
-  if (v2 == 2) {
-    if ((long long)a.N * a.IH * a.IW > 0x7fffffffLL) return MRFP_ERR_BAD_SHAPE;
-    TailMaps tm;
-    rc = tail_maps(P, 0, a, t_lo, lh, lw, kSeg2, true, &tm);
-    if (rc) return rc;
-    MRFP_SMEM_OPT_IN(tail_final2_fwd2_kernel, kFwd2Smem, di.device);
-    launch_k(tail_final2_fwd2_kernel, dim3(grid), dim3(kThreads), kFwd2Smem, (cudaStream_t)stream, tm.y, tm.aux, a, lh, lw, b2, out,
-             wtiles, (int)tiles);
-  } else {
-    MRFP_SMEM_OPT_IN(tail_final2_fwd_kernel, kFwdSmem, di.device);
-    launch_k(tail_final2_fwd_kernel, dim3(grid), dim3(kThreads), kFwdSmem, (cudaStream_t)stream, a, t_lo, lh, lw, b2, out, wtiles,
-             (int)tiles);
-  }
+  TailMaps tm;
+  rc = tail_maps(P, 0, a, t_lo, lh, lw, kSeg, 2, true, &tm);
+  if (rc) return rc;
+  const size_t smem = kFwdSmem + ((size_t)wtiles * (kPx + 1) + a.OH) * sizeof(int);
+  if (smem > (size_t)di.max_smem_optin) return MRFP_ERR_UNSUPPORTED;
+  MRFP_SMEM_OPT_IN(tail_final2_fwd_kernel, di.max_smem_optin, di.device);
+  launch_k(tail_final2_fwd_kernel, dim3(grid), dim3(kThreads), smem, (cudaStream_t)stream, tm.y, tm.aux, a, lh, lw, b2, out, wtiles,
+           (int)tiles);
   MRFP_CUDA_TRY(cudaGetLastError());
   return MRFP_OK;
 }
@@ -930,9 +609,8 @@ extern "C" int mrfp_hrfp_tail_final2_bwd(const mrfp_hrfp_plan_t* P, const void* 
   if (!P || P->magic != kPlanMagic) return MRFP_ERR_BAD_PLAN;
   if (!saved || !lut || !g || !w2 || !g_dec_nhwc || !g_w2 || !g_b2) return MRFP_ERR_NULL_POINTER;
   if ((uintptr_t)g_dec_nhwc & 15) return MRFP_ERR_WORKSPACE;
-  static const int v2 = getenv("MRFP_TAIL_V") ? atoi(getenv("MRFP_TAIL_V")) : 2;
   TailArgs a;
-  int rc = tail_args(P, saved, lut, w2, K, &a, v2 == 2 ? kPx2 : kPx, v2 == 2 ? kSpan2 : kSpan);
+  int rc = tail_args(P, saved, lut, w2, K, &a);
   if (rc) return rc;
   DeviceInfo di;
   rc = get_device_info(&di);
@@ -940,31 +618,27 @@ extern "C" int mrfp_hrfp_tail_final2_bwd(const mrfp_hrfp_plan_t* P, const void* 
   cudaStream_t s = (cudaStream_t)stream;
   MRFP_CUDA_TRY(cudaMemsetAsync(g_w2, 0, (size_t)K * kC * sizeof(float), s));
   MRFP_CUDA_TRY(cudaMemsetAsync(g_b2, 0, (size_t)K * sizeof(float), s));
-  const int px = v2 == 2 ? kPx2 : kPx;
-  const int wtiles = (a.OW + px - 1) / px;
+  const int wtiles = (a.OW + kPx - 1) / kPx;
   const long long tiles = (long long)a.N * a.OH * wtiles;
   if (tiles > 0x7fffffffLL) return MRFP_ERR_BAD_SHAPE;
   const int grid = (int)(tiles < 2LL * di.sm_count ? tiles : 2LL * di.sm_count);
-  if (v2 == 2) {
-    if ((long long)a.N * a.IH * a.IW > 0x7fffffffLL) return MRFP_ERR_BAD_SHAPE;
-    const int g_tma = (a.OW & 3) == 0 && ((uintptr_t)g & 15) == 0;     // rows of g 16-byte aligned: one box per tile
-    TailMaps tm;
-    rc = tail_maps(P, 1, a, g, a.OH, a.OW, kPx2, g_tma != 0, &tm);
-    if (rc) return rc;
-    MRFP_SMEM_OPT_IN(tail_final2_bwd2_kernel, kBwd2Smem, di.device);
-    launch_k(tail_final2_bwd2_kernel, dim3(grid), dim3(kThreads), kBwd2Smem, s, tm.y, tm.aux, a, g, g_tma,
-             reinterpret_cast<__nv_bfloat16*>(g_dec_nhwc), g_w2, g_b2, wtiles, (int)tiles);
-  } else {
-    MRFP_SMEM_OPT_IN(tail_final2_bwd_kernel, kBwdSmem, di.device);
-    launch_k(tail_final2_bwd_kernel, dim3(grid), dim3(kThreads), kBwdSmem, s, a, g, reinterpret_cast<__nv_bfloat16*>(g_dec_nhwc), g_w2,
-             g_b2, wtiles, (int)tiles);
-  }
+  const int g_tma = (a.OW & 3) == 0 && ((uintptr_t)g & 15) == 0;     // rows of g 16-byte aligned: one box per tile
+  TailMaps tm;
+  rc = tail_maps(P, 1, a, g, a.OH, a.OW, kPx, 1, g_tma != 0, &tm);
+  if (rc) return rc;
+  const size_t smem = kBwdSmem + ((size_t)wtiles * (kPx + 1) + a.OH) * sizeof(int);
+  if (smem > (size_t)di.max_smem_optin) return MRFP_ERR_UNSUPPORTED;
+  MRFP_SMEM_OPT_IN(tail_final2_bwd_kernel, di.max_smem_optin, di.device);
+  launch_k(tail_final2_bwd_kernel, dim3(grid), dim3(kThreads), smem, s, tm.y, tm.aux, a, g, g_tma,
+           reinterpret_cast<__nv_bfloat16*>(g_dec_nhwc), g_w2, g_b2, wtiles, (int)tiles);
   MRFP_CUDA_TRY(cudaGetLastError());
   return MRFP_OK;
 }
 
+#ifdef MRFP_TAIL_TRACE
 extern "C" int mrfp_debug_tail_trace(unsigned long long* host16, int reset) {
   if (host16) MRFP_CUDA_TRY(cudaMemcpyFromSymbol(host16, mrfp::g_tail_dbg, sizeof(unsigned long long) * 16));
   if (reset) { unsigned long long z[16] = {0}; MRFP_CUDA_TRY(cudaMemcpyToSymbol(mrfp::g_tail_dbg, z, sizeof(z))); }
   return 0;
 }
+#endif

@@ -1,6 +1,7 @@
 """A/B of two builds / switches of the classifier tail at the benchmarked geometry (batch 2, 768^2).
 
-    MRFP_TAIL_V=1 python tools/ab_tail.py dump /tmp/t1.pt;  MRFP_TAIL_V=2 python tools/ab_tail.py dump /tmp/t2.pt
+    python tools/ab_tail.py dump /tmp/t1.pt          (build A)
+    python tools/ab_tail.py dump /tmp/t2.pt          (build B)
     python tools/ab_tail.py cmp /tmp/t1.pt /tmp/t2.pt
 `dump` also checks dec2 and the three classifier-side gradients against fp64 built from the materialised OCout_dec."""
 import os, sys

@@ -1,4 +1,7 @@
-"""Phase timeline of the tail kernels (temporary instrumentation: clock64 sums of thread 0 of every CTA)."""
+"""Phase timeline of the classifier-tail kernels: clock64 sums of thread 0 of every CTA per phase of the tile loop.
+
+    MRFP_EXTRA_NVCC_FLAGS=-DMRFP_TAIL_TRACE python -m mrfp_b200.build --force && python tools/trace_tail.py
+The instrumentation is compiled out of the default build (rebuild without the flag afterwards)."""
 import os, sys, ctypes
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -17,6 +20,7 @@ xp = torch.relu(torch.randn(n, 64, 192, 192, device=dev))
 d1 = torch.randn(n, 256, 192, 192, device=dev)
 g_d = torch.randn(n, 19, 384, 384, device=dev)
 lib = _lib.load()
+lib = ctypes.CDLL(_lib.LIB_PATH)
 lib.mrfp_debug_tail_trace.argtypes = [ctypes.c_void_p, ctypes.c_int]
 def step():
     a = xp.detach().requires_grad_(True); d = d1.detach().requires_grad_(True)
