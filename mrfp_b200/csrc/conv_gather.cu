@@ -387,6 +387,9 @@ conv3x3_gather_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_c
         float sc[8], sh[8];
         ld8s(const_u + 4u * (uint32_t)(j_kc * kBlockK + piece * 8), sc);
         ld8s(const_u + 4u * (uint32_t)(CIN + j_kc * kBlockK + piece * 8), sh);
+        uint64_t sc2[4], sh2[4];                   // channel pairs for the packed fp32x2 FMA (common.cuh: bn_relu_x2)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) { sc2[q] = pack_f32x2(sc[2 * q], sc[2 * q + 1]); sh2[q] = pack_f32x2(sh[2 * q], sh[2 * q + 1]); }
 #pragma unroll
         for (int u0 = 0; u0 < U; u0 += 5) {        // up to five pixels per batch: their shared-memory reads overlap
           uint4 v[5];
@@ -398,11 +401,8 @@ conv3x3_gather_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_c
 #pragma unroll
           for (int i = 0; i < 5; ++i) {
             if (u0 + i < U) {
-              float f[8];
-              unpack8(v[i], f);
-#pragma unroll
-              for (int q = 0; q < 8; ++q) f[q] = fmaxf(fmaf(sc[q], f[q], sh[q]), 0.f);
-              uint4 o = pack8(f);
+              uint4 o = make_uint4(bn_relu_x2(v[i].x, sc2[0], sh2[0]), bn_relu_x2(v[i].y, sc2[1], sh2[1]),
+                                   bn_relu_x2(v[i].z, sc2[2], sh2[2]), bn_relu_x2(v[i].w, sc2[3], sh2[3]));
               if (!((valid >> (u0 + i)) & 1u)) o = make_uint4(0u, 0u, 0u, 0u);   // the convolution's zero padding stays zero
               if (pl + kPxLanes * (u0 + i) < npix)
                 asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};"

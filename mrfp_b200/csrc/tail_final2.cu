@@ -135,25 +135,6 @@ struct TileWalk {
   }
 };
 
-// BatchNorm + ReLU of two bf16 values in one register: one packed fp32 FMA, one rounding to bf16x2, ReLU on the pair.
-// max(round(x), 0) == round(max(x, 0)): same results as the scalar form above, 5 instructions instead of 7.
-__device__ __forceinline__ uint64_t pack_f32x2(float lo, float hi) {
-  uint64_t r;
-  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
-  return r;
-}
-__device__ __forceinline__ uint32_t bn_relu_x2(uint32_t v, uint64_t scale2, uint64_t shift2) {
-  uint64_t x, y;
-  asm("mov.b64 %0, {%1, %2};" : "=l"(x) : "r"(v << 16), "r"(v & 0xffff0000u));
-  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(y) : "l"(x), "l"(scale2), "l"(shift2));
-  float lo, hi;
-  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(y));
-  uint32_t p;
-  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(p) : "f"(hi), "f"(lo));
-  asm("max.bf16x2 %0, %1, %2;" : "=r"(p) : "r"(p), "r"(0u));
-  return p;
-}
-
 // dynamic shared memory, rounded up to the 1024 bytes the swizzled boxes need (by pointer arithmetic, so that the
 // compiler keeps the shared address space)
 __device__ __forceinline__ unsigned char* smem_1k(unsigned char* raw) {
