@@ -178,7 +178,10 @@ int mrfp_hrfp_plus_add_bilinear(const mrfp_hrfp_plan_t* plan, const void* saved,
  * Neither OCout_dec, the up-sampled dec1 nor their sum (N, 256, h/2, w/2) is materialised.
  * Backward, given g = dL/d out: g_dec_nhwc (N, h/2, w/2, 256) bf16 = W2^T g (feed it to mrfp_hrfp_bwd_nhwc),
  * g_w2 (K, 256) = sum_pixels g . OCout_dec^T (the high-resolution half of the weight gradient), g_b2 (K) = sum g; the
- * gradient to t_lo is mrfp_bilinear_up_bwd_f32(g).  MRFP_ERR_UNSUPPORTED: use mrfp_hrfp_plus_add_bilinear + a conv. */
+ * gradient to t_lo is mrfp_bilinear_up_bwd_f32(g).  MRFP_ERR_UNSUPPORTED: use mrfp_hrfp_plus_add_bilinear + a conv.
+ * Inputs arrive through TMA tensor maps the plan caches per direction (re-encoded when an address or shape changes): t_lo
+ * must be 16-byte aligned with lw % 4 == 0 and describe an Upsample by >= 2 (else MRFP_ERR_UNSUPPORTED); g may have any
+ * alignment (rows that are not 16-byte aligned are read with plain loads). */
 int mrfp_hrfp_tail_final2_fwd(const mrfp_hrfp_plan_t* plan, const void* saved, const void* lut, const float* t_lo,
                               int lh, int lw, const float* w2, const float* b2, int K, float* out, void* stream);
 int mrfp_hrfp_tail_final2_bwd(const mrfp_hrfp_plan_t* plan, const void* saved, const void* lut, const float* g,

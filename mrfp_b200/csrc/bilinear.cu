@@ -18,7 +18,8 @@
 namespace mrfp {
 namespace {
 
-constexpr int kRows = 8, kCols = 64, kThreads = 256;
+constexpr int kRows = 8, kCols = 64, kThreads = 256;   // kRows == warps per CTA
+constexpr int kMaxRun = 6;                               // run lengths kept in registers (an Upsample by 2 has runs of 3-4)
 
 // table blob (4-byte words): [0] = T (run length), [1] = span_max (host use), [2 .. 2+L) = start[L], then w[L][T] floats
 struct AxisTable { int T; const int* start; const float* w; };
@@ -38,18 +39,47 @@ bilinear_up_bwd_kernel(const float* __restrict__ g, float* __restrict__ gl, int 
   const int ox0 = tw.start[x0];
   const int span = min(tw.start[x1] + tw.T, OW) - ox0;                 // output columns this tile gathers from
   const float* gp = g + plane * (size_t)OH * OW;
-  for (int idx = threadIdx.x; idx < kRows * span; idx += kThreads) {
-    const int r = idx / span, j = idx - r * span, y = y0 + r;
-    float acc = 0.f;
+  // vertical pass: warp = one low-resolution row (kRows == warps); its run of weights and (clamped) source rows sit in
+  // registers, so a lane's loads of one column are independent of each other and of the next column's
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (th.T <= kMaxRun) {
+    const int y = y0 + warp;
+    float* trow = t + warp * span_max;
     if (y < LH) {
       const int s = th.start[y];
-      const float* wv = th.w + (size_t)y * th.T;
-      for (int a = 0; a < th.T; ++a) {
-        const int oy = s + a;
-        if (oy < OH) acc = fmaf(wv[a], __ldg(gp + (size_t)oy * OW + ox0 + j), acc);
+      float wr[kMaxRun];
+      size_t off[kMaxRun];
+#pragma unroll
+      for (int a = 0; a < kMaxRun; ++a) {              // weights beyond the run are zero in the table; rows beyond OH are clamped
+        wr[a] = a < th.T ? th.w[(size_t)y * th.T + a] : 0.f;
+        off[a] = (size_t)min(s + a, OH - 1) * OW;
       }
+#pragma unroll 2
+      for (int j = lane; j < span; j += 32) {
+        const float* col = gp + ox0 + j;
+        float acc = 0.f;
+#pragma unroll
+        for (int a = 0; a < kMaxRun; ++a)
+          if (a < th.T) acc = fmaf(wr[a], __ldg(col + off[a]), acc);
+        trow[j] = acc;
+      }
+    } else {
+      for (int j = lane; j < span; j += 32) trow[j] = 0.f;
     }
-    t[r * span_max + j] = acc;
+  } else {
+    for (int idx = threadIdx.x; idx < kRows * span; idx += kThreads) {
+      const int r = idx / span, j = idx - r * span, y = y0 + r;
+      float acc = 0.f;
+      if (y < LH) {
+        const int s = th.start[y];
+        const float* wv = th.w + (size_t)y * th.T;
+        for (int a = 0; a < th.T; ++a) {
+          const int oy = s + a;
+          if (oy < OH) acc = fmaf(wv[a], __ldg(gp + (size_t)oy * OW + ox0 + j), acc);
+        }
+      }
+      t[r * span_max + j] = acc;
+    }
   }
   __syncthreads();
   float* op = gl + plane * (size_t)LH * LW;
