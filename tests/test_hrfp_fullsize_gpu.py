@@ -211,3 +211,49 @@ def test_fused_np_plus_and_tail_at_benchmarked_shape():
     for name in ("tf32", "bf16"):
         bx, bd, bg = rows[name]["bounds"]
         assert rows[name]["x"] <= bx and rows[name]["d1"] <= bd and rows[name]["gx"] <= bg, rows
+
+
+def test_classifier_tail_at_benchmarked_shape():
+    """deepv3.py:356-361 through the classifier (mrfp_hrfp_tail_final2_fwd / _bwd, csrc/tail_final2.cu) at config[0] size:
+    dec2 and the high-resolution gradients of final2 against fp64 built from the materialised OCout_dec of the same
+    chain (so the difference is the bf16 rounding of the classifier operands only), the gradient that joins the chain
+    against W2^T g rounded to bf16."""
+    import torch.nn.functional as F
+    from mrfp_b200.hrfp import hrfp_chain, hrfp_plus_add_upsampled, hrfp_plus_final2
+    n, k = 2, 19
+    ws, gs = make_hrfp_params(31)
+    gen = torch.Generator(device="cuda").manual_seed(32)
+    xp = torch.from_numpy(make_feat(33, (n, 64, XH, XW))).cuda()
+    d1 = torch.randn(n, 256, XH, XW, device="cuda", generator=gen)
+    g = torch.randn(n, k, H // 2, W // 2, device="cuda", generator=gen)
+    torch.manual_seed(34)
+    final2 = torch.nn.Conv2d(256, k, 1).cuda()
+
+    def chain():
+        convs, bns = TP.make_layers(ws, gs)
+        convs = [c.cuda() for c in convs]; bns = [b.cuda() for b in bns]
+        return hrfp_chain(xp, convs, bns, H, W, want_out=False, math_mode=2, lazy_dec=True, update_running_stats=False)[1]
+
+    da = d1.clone().requires_grad_(True)
+    dec = chain()
+    out = hrfp_plus_final2(da, final2, dec)
+    out.backward(g)
+    g_nhwc = dec.mail.get("g_nhwc")                                # (N, h/2, w/2, 256) bf16: the rank-K gradient of OCout_dec
+    full = hrfp_plus_add_upsampled(d1, chain()).double().requires_grad_(True)
+    w64 = final2.weight.detach().double().requires_grad_(True); b64 = final2.bias.detach().double().requires_grad_(True)
+    ref = F.conv2d(full, w64, b64)
+    ref.backward(g.double())
+    # W2^T g in fp64 with the classifier rounded to bf16 as the kernel sees it
+    w2b = final2.weight.detach().reshape(k, 256).bfloat16().double()
+    gd = torch.einsum("nkhw,kc->nhwc", g.bfloat16().double(), w2b)
+    # the gradient to dec1 goes through the low-resolution product: W2^T . (adjoint of the bilinear Upsample)(g)
+    d64 = d1.double().requires_grad_(True)
+    F.interpolate(F.conv2d(d64, w64.detach()), size=(H // 2, W // 2), mode="bilinear", align_corners=True).backward(g.double())
+    rows = dict(dec2=_l2(out, ref), g_w2=_l2(final2.weight.grad, w64.grad), g_b2=_l2(final2.bias.grad, b64.grad),
+                g_dec1=_l2(da.grad, d64.grad))
+    if g_nhwc is not None:
+        rows["g_dec_nhwc"] = _l2(g_nhwc, gd)
+    _record("classifier_tail_batch2_768x768", rows)
+    print(json.dumps(rows))
+    assert rows["dec2"] <= 5e-3 and rows["g_w2"] <= 5e-3 and rows["g_b2"] <= 1e-5 and rows["g_dec1"] <= 5e-3, rows
+    assert rows.get("g_dec_nhwc", 0.0) <= 5e-3, rows

@@ -401,8 +401,9 @@ def test_bad_plan_arguments():
 
 # the last geometry has output rows of 46 pixels: rows of g are not 16-byte aligned, so the backward takes plain loads
 # instead of the per-tile TMA box
+# ... and the one before it the widest classifier the kernels take (24 classes), without a bias
 @pytest.mark.parametrize("geom", [(2, 96, 80, (24, 20), 19), (1, 96, 544, (24, 136), 19), (2, 64, 48, (16, 12), 7),
-                                  (2, 92, 92, (23, 20), 19)])
+                                  (1, 128, 160, (32, 40), -24), (2, 92, 92, (23, 20), 19)])
 def test_tail_fused_through_the_classifier_equals_the_unfused_tail(geom):
     """deepv3.py:356-361: final2(Upsample(dec1) + OCout_dec) through mrfp_hrfp_tail_final2_* (one kernel per direction,
     nothing materialised at (N,256,h/2,w/2)) vs the Upsample+add kernel followed by the module's own 1x1 conv: output,
@@ -410,11 +411,12 @@ def test_tail_fused_through_the_classifier_equals_the_unfused_tail(geom):
     the classifier operands (activations and W2) and of the rank-K gradient that joins the chain."""
     from mrfp_b200.hrfp import hrfp_chain, hrfp_plus_add_upsampled, hrfp_plus_final2, tail_final2_supported
     n, h, w, lo, k = geom
+    has_bias, k = k > 0, abs(k)                      # a negative class count: no bias
     xh, xw = math.ceil(h / 4), math.ceil(w / 4)
     ws, gs = make_hrfp_params(71)
     convs, bns = _modules(ws, gs, "cuda")
     torch.manual_seed(72)
-    final2 = torch.nn.Conv2d(256, k, 1, bias=True).cuda()
+    final2 = torch.nn.Conv2d(256, k, 1, bias=has_bias).cuda()
     xp = torch.from_numpy(make_feat(73, (n, 64, xh, xw))).cuda()
     d_lo = torch.randn(n, 256, *lo, device="cuda")
     g = torch.randn(n, k, h // 2, w // 2, device="cuda")
@@ -429,7 +431,8 @@ def test_tail_fused_through_the_classifier_equals_the_unfused_tail(geom):
         else:
             out = final2(hrfp_plus_add_upsampled(da, dec))
         out.backward(g)
-        res.append([t.detach().clone() for t in (out, da.grad, final2.weight.grad, final2.bias.grad, xa.grad)])
+        gb = final2.bias.grad if has_bias else torch.ones(1, device="cuda")
+        res.append([t.detach().clone() for t in (out, da.grad, final2.weight.grad, gb, xa.grad)])
     names = ("dec2", "g_dec1", "g_W2", "g_b2", "g_xp")
     tols = (1e-2, 1e-2, 1e-2, 1e-5, TOL_VS_BF16_ORACLE["bwd"])
     for name, a, b, tol in zip(names, res[0], res[1], tols):
@@ -439,7 +442,7 @@ def test_tail_fused_through_the_classifier_equals_the_unfused_tail(geom):
     # linearity (zero classifier on the chain side is not expressible), check dec2 against fp64 directly
     _, dec = hrfp_chain(xp, convs, bns, h, w, want_out=False, math_mode=2, lazy_dec=True, update_running_stats=False)
     full = hrfp_plus_add_upsampled(d_lo, dec).double()
-    ref = torch.nn.functional.conv2d(full, final2.weight.double(), final2.bias.double())
+    ref = torch.nn.functional.conv2d(full, final2.weight.double(), final2.bias.double() if has_bias else None)
     _, dec = hrfp_chain(xp, convs, bns, h, w, want_out=False, math_mode=2, lazy_dec=True, update_running_stats=False)
     got = hrfp_plus_final2(d_lo, final2, dec)
     assert float((got.double() - ref).norm() / ref.norm()) <= 5e-3
