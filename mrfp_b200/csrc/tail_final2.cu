@@ -70,6 +70,7 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
   const __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<const uint32_t*>(&h);
 }
+// launch-constant arguments of both kernels
 struct TailArgs {
   const __nv_bfloat16* y;          // Y_3 (N, IH, IW, 256) bf16 NHWC
   const int* idx_h; const int* idx_w;
@@ -77,7 +78,6 @@ struct TailArgs {
   int N, IH, IW, OH, OW, K;
   const float* w2;                 // (K, 256) fp32
 };
-
 
 // Phase timeline for tools/trace_tail.py (build with MRFP_EXTRA_NVCC_FLAGS=-DMRFP_TAIL_TRACE): clock64 sums of thread 0 of
 // every CTA per phase of the tile loop; compiled out otherwise.
@@ -91,16 +91,13 @@ __device__ unsigned long long g_tail_dbg[16];
 #define TR(k) do { } while (0)
 #define TR_END(off) do { } while (0)
 #endif
+
 constexpr int kPx = 64;             // output pixels per tile
 constexpr int kSpan = 64;           // source pixels a tile's box holds (64 * 332/384 + 2 = 58 needed in the reference geometry)
 constexpr int kSeg = 44;            // staged low-resolution row pitch (floats): an Upsample by >= 2 needs <= 40
 constexpr int kOutPitch = 68;       // floats; 68 mod 32 = 4: the accumulator scatter is bank-conflict free
 constexpr uint32_t kSpanBytes = kSpan * 512;
 
-__device__ __forceinline__ void tma_2d(uint32_t dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
-  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-               ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
-}
 __device__ __forceinline__ void tma_3d(uint32_t dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
   asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
                ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
