@@ -1,4 +1,4 @@
-"""Times the tcgen05 conv kernel on the chain's forward and dgrad shapes (B=8, 768^2 crop); MRFP_CONV_MODE selects the kernel."""
+"""Times the tcgen05 conv kernel on the chain's forward and dgrad shapes (B=8, 768^2 crop) (the tap kernel conv3x3_tc_kernel through its debug hook)."""
 import ctypes, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
