@@ -191,6 +191,19 @@ int mrfp_hrfp_bwd_nhwc(const mrfp_hrfp_plan_t* plan, const float* g_ocout, const
                        const float* const* gamma, const float* np_alpha, const float* np_eps, const float* np_mean,
                        void* np_ws, const void* lut, const void* saved, float* g_xp, void* ws, void* stream);
 
+/* The RANK-K form of the same pair (the default of the Python host): the gradient of OCout_dec is W2^T g with K <= 24
+ * classes, so instead of leaving it as an (N, h/2, w/2, 256) tensor the tail's backward leaves its two factors —
+ *   g64 (N, h/2, w/2, 64) bf16: g per pixel, classes beyond K zero;   w2t64 (256, 64) bf16: W2 transposed, zero-padded —
+ * and mrfp_hrfp_bwd_rk lets the stage-4 dgrad accumulate g64 . w2t64^T as one more k-block on the tensor cores (fp32, one
+ * rounding together with the convolution's own sum).  The 604 MB tensor (batch 8, 768^2) is neither written nor read; when
+ * the stage-4 dgrad does not run as the operand-fused kernel, or the backward is encoder-only, the library expands the
+ * product itself.  Everything else as mrfp_hrfp_tail_final2_bwd / mrfp_hrfp_bwd_nhwc. */
+int mrfp_hrfp_tail_final2_bwd_rk(const mrfp_hrfp_plan_t* plan, const void* saved, const void* lut, const float* g,
+                                 const float* w2, int K, void* g64, void* w2t64, float* g_w2, float* g_b2, void* stream);
+int mrfp_hrfp_bwd_rk(const mrfp_hrfp_plan_t* plan, const float* g_ocout, const void* g64, const void* w2t64,
+                     const float* const* gamma, const float* np_alpha, const float* np_eps, const float* np_mean,
+                     void* np_ws, const void* lut, const void* saved, float* g_xp, void* ws, void* stream);
+
 /* Backward of the reference's Upsample (network/mynn.py:114-119, bilinear, align_corners=True) at the up-sampling sites of
  * the tail (deepv3.py:356, :362), as a gather instead of ATen's atomicAdd scatter:
  *   gl (planes, LH, LW) = adjoint of the up-sampling applied to g (planes, OH, OW), OH >= LH, OW >= LW.

@@ -62,6 +62,12 @@ SIGNATURES = {
     "mrfp_hrfp_bwd_nhwc": (ctypes.c_int, [ctypes.c_void_p, c_float_p, ctypes.c_void_p, c_void_pp, c_float_p, c_float_p,
                                           c_float_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, c_float_p,
                                           ctypes.c_void_p, ctypes.c_void_p]),
+    "mrfp_hrfp_tail_final2_bwd_rk": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, c_float_p, c_float_p,
+                                                    ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, c_float_p, c_float_p,
+                                                    ctypes.c_void_p]),
+    "mrfp_hrfp_bwd_rk": (ctypes.c_int, [ctypes.c_void_p, c_float_p, ctypes.c_void_p, ctypes.c_void_p, c_void_pp, c_float_p,
+                                        c_float_p, c_float_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, c_float_p,
+                                        ctypes.c_void_p, ctypes.c_void_p]),
     "mrfp_add_f32": (ctypes.c_int, [c_float_p, c_float_p, c_float_p, ctypes.c_size_t, ctypes.c_void_p]),
     "mrfp_bilinear_bwd_table_bytes": (ctypes.c_size_t, [ctypes.c_int, ctypes.c_int]),
     "mrfp_bilinear_bwd_write_table": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_size_t]),

@@ -96,10 +96,13 @@ __device__ __forceinline__ void ld8s(uint32_t a, float (&v)[8]) {
 // kGatherBwd:   in[h][w][c] = P[c] * [scale[c]*y+shift[c] > 0] * g[replica of (h,w)][c] - (R[c]*y[h][w][c] + Q[c])  where (h,w) has a
 //               replica, 0 where it has none (a pixel the down-sampling skipped receives no gradient)
 // each inside the image, 0 in the convolution's zero padding
-template <int COUT, int MODE, bool ADD, int MT>
+// ADD: 0 nothing joins the output; 1 a tensor of the output's shape is added in the epilogue (add tile by TMA); 2 a RANK-K
+// term joins as one more k-block of the accumulation: out += G[pixel][64] . W2T[cout][64]^T (the classifier tail's gradient,
+// tail_final2.cu) — its two operands travel through the weight ring: tmap_add describes G (N, H, W, 64), tmap_rkw W2T (cout, 64)
+template <int COUT, int MODE, int ADD, int MT>
 __global__ void __launch_bounds__(kGThreads, 1)
 conv3x3_gather_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_out,
-                      const __grid_constant__ CUtensorMap tmap_add, const GatherArgs ga, int CIN, int dil, int boxw, int tiles_h, int tiles_w, int num_tiles,
+                      const __grid_constant__ CUtensorMap tmap_add, const __grid_constant__ CUtensorMap tmap_rkw, const GatherArgs ga, int CIN, int dil, int boxw, int tiles_h, int tiles_w, int num_tiles,
                       const int* __restrict__ cnt_h, const int* __restrict__ cnt_w, double* __restrict__ stat_acc, int rev,
                       const ConvBnFinalize fin, const __nv_bfloat16* __restrict__ add_src, int H, int W, int nA, int nB,
                       int a_stage_bytes, int tab_bytes, int e_bytes) {
@@ -138,6 +141,7 @@ conv3x3_gather_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_c
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap_w)) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap_out)) : "memory");
     if (ADD) asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap_add)) : "memory");
+    if (ADD == 2) asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap_rkw)) : "memory");
     for (int i = 0; i < nA; ++i) { mbar_init(&full_a[i], kProducers); mbar_init(&empty_a[i], 1); }
     for (int i = 0; i < nB; ++i) { mbar_init(&full_b[i], 1); mbar_init(&empty_b[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 4); mbar_init(&add_full[i], 1); }
@@ -167,6 +171,24 @@ conv3x3_gather_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_c
           __syncwarp();
           if (++bs == nB) { bs = 0; bph ^= 1; }
         }
+      }
+      if constexpr (ADD == 2) {                  // the rank-K block's operands: the tile of G, then W2T
+        const int t = rev ? num_tiles - 1 - t0 : t0;
+        const int tw = t % tiles_w, th = (t / tiles_w) % tiles_h, n = t / (tiles_w * tiles_h);
+        mbar_wait(&empty_b[bs], bph ^ 1);
+        if (elect_one()) {
+          mbar_expect_tx(&full_b[bs], (uint32_t)(kGTileH * kGSubW * MT * 128));
+          tma_load_4d(sB + bs * C::kBTileBytes, &tmap_add, &full_b[bs], 0, tw * kGSubW * MT, th * kGTileH, n);
+        }
+        __syncwarp();
+        if (++bs == nB) { bs = 0; bph ^= 1; }
+        mbar_wait(&empty_b[bs], bph ^ 1);
+        if (elect_one()) {
+          mbar_expect_tx(&full_b[bs], C::kBTileBytes);
+          tma_load_2d(sB + bs * C::kBTileBytes, &tmap_rkw, &full_b[bs], 0, 0);
+        }
+        __syncwarp();
+        if (++bs == nB) { bs = 0; bph ^= 1; }
       }
     }
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
@@ -209,6 +231,27 @@ conv3x3_gather_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_c
         }
         if (++as == nA) { as = 0; aph ^= 1; }
       }
+      if constexpr (ADD == 2) {                  // + G[pixel][class] . W2T[cout][class]^T: two k-steps cover the <= 24 classes
+        static_assert(MT == 1, "the rank-K block is laid out for one M sub-tile");
+        const int gs = bs;
+        mbar_wait(&full_b[bs], bph);
+        if (++bs == nB) { bs = 0; bph ^= 1; }
+        const int ws_ = bs;
+        mbar_wait(&full_b[bs], bph);
+        if (++bs == nB) { bs = 0; bph ^= 1; }
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        if (elect_one()) {
+          // G tile as TMA wrote it: [16 rows][8 px][128 B], i.e. eight-pixel groups 1024 bytes apart (SBO = 64 x 16 bytes)
+          const uint64_t dg = (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61) |
+                              (uint64_t)(((sB_u + (uint32_t)(gs * C::kBTileBytes)) >> 4) & 0x3FFFu);
+          const uint64_t dw = make_desc_sw128(sB_u + ws_ * C::kBTileBytes);
+#pragma unroll
+          for (int k = 0; k < 2; ++k) umma<T>(d_tmem, dg + (uint64_t)(k * 2), dw + (uint64_t)(k * 2), idesc, true);
+          umma_commit(&empty_b[gs]);
+          umma_commit(&empty_b[ws_]);
+        }
+        __syncwarp();
+      }
       if (elect_one()) umma_commit(&tmem_full[acc]);     // accumulator complete
       __syncwarp();
     }
@@ -217,7 +260,7 @@ conv3x3_gather_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_c
     EpiSmem es;
     es.sOut = sOut; es.s_wgt = s_wgt; es.scratch = reinterpret_cast<float*>(sA); es.tmem_full = tmem_full; es.tmem_empty = tmem_empty;
     es.add_full = add_full;
-    conv_epilogue<COUT, T, kGTileH, kGSubW, MT, true, ADD ? 3 : 0>(es, tmem_base, tmap_out, tiles_h, tiles_w, num_tiles, cnt_h, cnt_w,
+    conv_epilogue<COUT, T, kGTileH, kGSubW, MT, true, ADD == 1 ? 3 : 0>(es, tmem_base, tmap_out, tiles_h, tiles_w, num_tiles, cnt_h, cnt_w,
                                                                    stat_acc, rev, fin, add_src, H, W, &tmap_add);
   } else {
     // ===================== operand producers (warps 6..13) =====================
@@ -550,14 +593,14 @@ SmemPlan smem_plan(int mode, int cout, int cin, int dil, const int* host_lo_h = 
   return smem_plan_mt(mode, cout, cin, dil, mt0, extras_rows(host_lo_h, host_lo_w, H, W, dil, mt0));
 }
 
-template <int COUT, int MODE, bool ADD, int MT>
+template <int COUT, int MODE, int ADD, int MT>
 int launch(const SmemPlan& sp, const GatherArgs& ga, const void* wpack, void* out, int N, int H, int W, int cin, int dil,
            const int* cnt_h, const int* cnt_w, double* stat_acc, int rev, const ConvBnFinalize& fin, const void* add_src,
-           ConvMaps* cache, cudaStream_t stream) {
+           const void* rk_w2t, ConvMaps* cache, cudaStream_t stream) {
   ConvMaps local;
   local.valid = 0;
   ConvMaps* m = cache ? cache : &local;
-  if (!m->valid || m->key[0] != add_src || m->key[1] != wpack || m->key[2] != out) {
+  if (!m->valid || m->key[0] != add_src || m->key[1] != wpack || m->key[2] != out || m->key_aux != rk_w2t) {
     m->valid = 0;
     {
       const cuuint64_t dims[2] = {(cuuint64_t)cin, (cuuint64_t)9 * COUT};
@@ -573,7 +616,18 @@ int launch(const SmemPlan& sp, const GatherArgs& ga, const void* wpack, void* ou
       int rc = conv_make_map(&m->out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, out, 4, dims, strides, box);
       if (rc) return rc;
     }
-    if (add_src) {       // the tile of add_src that an output chunk is summed with: same geometry as the output (kept in m->in)
+    if (ADD == 2) {      // rank-K term: add_src is G (N, H, W, 64) bf16, rk_w2t is W2T (COUT, 64) bf16
+      const cuuint64_t dims[4] = {64, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+      const cuuint64_t strides[3] = {128, (cuuint64_t)W * 128, (cuuint64_t)H * W * 128};
+      const cuuint32_t box[4] = {64, (cuuint32_t)(kGSubW * MT), kGTileH, 1};
+      int rc = conv_make_map(&m->in, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, add_src, 4, dims, strides, box);
+      if (rc) return rc;
+      const cuuint64_t dims2[2] = {64, (cuuint64_t)COUT};
+      const cuuint64_t strides2[1] = {128};
+      const cuuint32_t box2[2] = {64, COUT};
+      rc = conv_make_map(&m->aux, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rk_w2t, 2, dims2, strides2, box2);
+      if (rc) return rc;
+    } else if (add_src) {       // the tile of add_src that an output chunk is summed with: same geometry as the output (kept in m->in)
       const cuuint64_t dims[4] = {(cuuint64_t)COUT, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
       const cuuint64_t strides[3] = {(cuuint64_t)COUT * 2, (cuuint64_t)W * COUT * 2, (cuuint64_t)H * W * COUT * 2};
       const cuuint32_t box[4] = {64, kGSubW, kGTileH, 1};
@@ -582,7 +636,8 @@ int launch(const SmemPlan& sp, const GatherArgs& ga, const void* wpack, void* ou
     } else {
       m->in = m->out;
     }
-    m->key[0] = add_src; m->key[1] = wpack; m->key[2] = out;
+    if (ADD != 2) m->aux = m->w;
+    m->key[0] = add_src; m->key[1] = wpack; m->key[2] = out; m->key_aux = rk_w2t;
     m->valid = 1;
   }
   DeviceInfo di;
@@ -594,23 +649,25 @@ int launch(const SmemPlan& sp, const GatherArgs& ga, const void* wpack, void* ou
   const int grid = num_tiles < di.sm_count ? num_tiles : di.sm_count;
   auto kern = conv3x3_gather_kernel<COUT, MODE, ADD, MT>;
   MRFP_SMEM_OPT_IN(kern, kSmemLimit, di.device);
-  launch_k(kern, dim3(grid), dim3(kGThreads), (size_t)sp.smem, stream, m->w, m->out, m->in, ga, cin, dil, sp.boxw, tiles_h, tiles_w,
-           num_tiles, cnt_h, cnt_w, stat_acc, rev, fin, static_cast<const __nv_bfloat16*>(add_src), H, W, sp.nA, sp.nB, sp.a_stage,
+  launch_k(kern, dim3(grid), dim3(kGThreads), (size_t)sp.smem, stream, m->w, m->out, m->in, m->aux, ga, cin, dil, sp.boxw, tiles_h, tiles_w,
+           num_tiles, cnt_h, cnt_w, stat_acc, rev, fin, static_cast<const __nv_bfloat16*>(ADD == 1 ? add_src : nullptr), H, W, sp.nA, sp.nB, sp.a_stage,
            sp.tab_bytes, sp.e_bytes);
   MRFP_CUDA_TRY(cudaGetLastError());
   return MRFP_OK;
 }
 
-template <int MODE, bool ADD>
+template <int MODE, int ADD>
 int dispatch(const SmemPlan& sp, const GatherArgs& ga, const void* wpack, void* out, int N, int H, int W, int cin, int cout, int dil,
              const int* cnt_h, const int* cnt_w, double* stat_acc, int rev, const ConvBnFinalize& fin, const void* add_src,
-             ConvMaps* cache, cudaStream_t stream) {
+             const void* rk_w2t, ConvMaps* cache, cudaStream_t stream) {
   if (sp.nA < 2) return MRFP_ERR_UNSUPPORTED;
 #define MRFP_GATHER_CASE(CO, MTV) \
-  return launch<CO, MODE, ADD, MTV>(sp, ga, wpack, out, N, H, W, cin, dil, cnt_h, cnt_w, stat_acc, rev, fin, add_src, cache, stream)
+  return launch<CO, MODE, ADD, MTV>(sp, ga, wpack, out, N, H, W, cin, dil, cnt_h, cnt_w, stat_acc, rev, fin, add_src, rk_w2t, cache, stream)
   if (cout == 256 && sp.mt == 1) { if constexpr (MODE != kGatherBwdRep) MRFP_GATHER_CASE(256, 1); }
+  if constexpr (ADD != 2) {
   if (cout == 128 && sp.mt == 2) MRFP_GATHER_CASE(128, 2);
   if (cout == 64 && sp.mt == 2) MRFP_GATHER_CASE(64, 2);
+  }
 #undef MRFP_GATHER_CASE
   return MRFP_ERR_UNSUPPORTED;
 }
@@ -646,16 +703,18 @@ int conv3x3_gather_fwd(const void* y_prev, int SH, int SW, const int* idx_h, con
   GatherArgs ga = {};
   ga.y = static_cast<const __nv_bfloat16*>(y_prev);
   ga.tab_h = idx_h; ga.tab_w = idx_w; ga.stats = stats_prev; ga.SH = SH; ga.SW = SW;
-  return dispatch<kGatherFwd, false>(smem_plan(kGatherFwd, cout, cin, dil), ga, wpack, out, N, H, W, cin, cout, dil, cnt_h, cnt_w,
-                                     stat_acc, reverse_tiles ? 1 : 0, fin, nullptr, cache, stream);
+  return dispatch<kGatherFwd, 0>(smem_plan(kGatherFwd, cout, cin, dil), ga, wpack, out, N, H, W, cin, cout, dil, cnt_h, cnt_w,
+                                 stat_acc, reverse_tiles ? 1 : 0, fin, nullptr, nullptr, cache, stream);
 }
 
 int conv3x3_gather_bwd(const void* y, const void* dA, int OH, int OW, const int* lo_h, const int* lo_w, const int* host_lo_h,
                        const int* host_lo_w, int max_rep, const float* stats, const float* gamma, const double* acc, double count,
                        int c_real, const void* wpack, void* out, int N, int H, int W, int cin, int cout, int dil,
-                       cudaStream_t stream, bool reverse_tiles, const void* add_src, ConvMaps* cache) {
+                       cudaStream_t stream, bool reverse_tiles, const void* add_src, ConvMaps* cache, const void* rk_w2t) {
+  // rk_w2t != nullptr: add_src is the rank-K operand G (N, H, W, 64) and rk_w2t the matrix W2T (cout, 64), see the kernel
   const int mode = max_rep <= 1 ? kGatherBwd : kGatherBwdRep;
   if (max_rep > 2 || (mode == kGatherBwdRep && add_src)) return MRFP_ERR_UNSUPPORTED;
+  if (rk_w2t && (!add_src || cout != 256 || ((uintptr_t)rk_w2t & 15))) return MRFP_ERR_UNSUPPORTED;
   if (!supported(mode, N, H, W, OH, OW, cin, cout, dil, host_lo_h, host_lo_w)) return MRFP_ERR_UNSUPPORTED;
   if (((uintptr_t)y | (uintptr_t)dA | (uintptr_t)wpack | (uintptr_t)out | (uintptr_t)add_src) & 15) return MRFP_ERR_WORKSPACE;
   GatherArgs ga = {};
@@ -666,10 +725,12 @@ int conv3x3_gather_bwd(const void* y, const void* dA, int OH, int OW, const int*
   const int rev = reverse_tiles ? 1 : 0;
   const SmemPlan sp = smem_plan(mode, cout, cin, dil, host_lo_h, host_lo_w, H, W);
   if (mode == kGatherBwdRep)
-    return dispatch<kGatherBwdRep, false>(sp, ga, wpack, out, N, H, W, cin, cout, dil, nullptr, nullptr, nullptr, rev, fin, nullptr, cache, stream);
+    return dispatch<kGatherBwdRep, 0>(sp, ga, wpack, out, N, H, W, cin, cout, dil, nullptr, nullptr, nullptr, rev, fin, nullptr, nullptr, cache, stream);
+  if (rk_w2t)
+    return dispatch<kGatherBwd, 2>(sp, ga, wpack, out, N, H, W, cin, cout, dil, nullptr, nullptr, nullptr, rev, fin, add_src, rk_w2t, cache, stream);
   if (add_src)
-    return dispatch<kGatherBwd, true>(sp, ga, wpack, out, N, H, W, cin, cout, dil, nullptr, nullptr, nullptr, rev, fin, add_src, cache, stream);
-  return dispatch<kGatherBwd, false>(sp, ga, wpack, out, N, H, W, cin, cout, dil, nullptr, nullptr, nullptr, rev, fin, nullptr, cache, stream);
+    return dispatch<kGatherBwd, 1>(sp, ga, wpack, out, N, H, W, cin, cout, dil, nullptr, nullptr, nullptr, rev, fin, add_src, nullptr, cache, stream);
+  return dispatch<kGatherBwd, 0>(sp, ga, wpack, out, N, H, W, cin, cout, dil, nullptr, nullptr, nullptr, rev, fin, nullptr, nullptr, cache, stream);
 }
 
 }  // namespace mrfp
@@ -697,5 +758,5 @@ extern "C" int mrfp_debug_conv3x3_gather_bwd(const void* y, const void* dA, int 
                                              const float* gamma, const double* acc, double count, const void* wpack, void* out, int N,
                                              int H, int W, int cin, int cout, int dil, const void* add_src, void* stream) {
   return mrfp::conv3x3_gather_bwd(y, dA, OH, OW, lo_h, lo_w, host_lo_h, host_lo_w, max_rep, stats, gamma, acc, count, cin, wpack, out, N,
-                                  H, W, cin, cout, dil, (cudaStream_t)stream, false, add_src, nullptr);
+                                  H, W, cin, cout, dil, (cudaStream_t)stream, false, add_src, nullptr, nullptr);
 }

@@ -1273,10 +1273,65 @@ int hrfp_forward(const mrfp_hrfp_plan* P, const float* xp, const float* const* W
   return MRFP_OK;
 }
 
+// Fallback of the rank-K form of the classifier tail's gradient (G (pixels, 64) bf16, W2T (C, 64) bf16, classes beyond K
+// zero): dA[px][c] = sum_k G[px][k] W2T[c][k], for the launches that cannot take it as a k-block of the stage-4 dgrad
+// (encoder-only backward, fusion switched off).  Plain CUDA cores: 8 channels of one pixel per thread.
+__global__ void __launch_bounds__(256)
+rankk_expand_kernel(const __nv_bfloat16* __restrict__ G, const __nv_bfloat16* __restrict__ W2T, __nv_bfloat16* __restrict__ dA,
+                    long long npix, int C) {
+  extern __shared__ float s_w[];                         // [C][32] fp32 (<= 24 classes are non-zero)
+  pdl_sync();
+  for (int e = threadIdx.x; e < C * 32; e += 256) s_w[e] = __bfloat162float(W2T[(size_t)(e >> 5) * 64 + (e & 31)]);
+  __syncthreads();
+  const int cg = C >> 3;
+  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < npix * cg; i += (long long)gridDim.x * 256) {
+    const long long px = i / cg;
+    const int c0 = (int)(i - px * cg) * 8;
+    float g[32];
+    const uint4* gp = reinterpret_cast<const uint4*>(G + px * 64);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const uint4 v = __ldg(gp + q);
+      const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { g[8 * q + 2 * j] = __uint_as_float(w[j] << 16); g[8 * q + 2 * j + 1] = __uint_as_float(w[j] & 0xffff0000u); }
+    }
+    float o[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float a = 0.f;
+#pragma unroll
+      for (int k = 0; k < 32; ++k) a = fmaf(g[k], s_w[(c0 + j) * 32 + k], a);
+      o[j] = a;
+    }
+    uint32_t pk[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const __nv_bfloat162 h2 = __floats2bfloat162_rn(o[2 * j], o[2 * j + 1]);
+      pk[j] = *reinterpret_cast<const uint32_t*>(&h2);
+    }
+    *reinterpret_cast<uint4*>(dA + px * C + c0) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+  }
+}
+
+template <typename T>
+int rankk_expand(const void* g64, const void* w2t, T* dA, long long npix, int C, const DeviceInfo& di, cudaStream_t s) {
+  if constexpr (sizeof(T) != 2) {
+    return MRFP_ERR_UNSUPPORTED;
+  } else {
+    launch_k(rankk_expand_kernel, dim3((unsigned)(di.sm_count * 8)), dim3(256), (size_t)C * 32 * sizeof(float), s,
+             static_cast<const __nv_bfloat16*>(g64), static_cast<const __nv_bfloat16*>(w2t), reinterpret_cast<__nv_bfloat16*>(dA), npix, C);
+    MRFP_CUDA_TRY(cudaGetLastError());
+    return MRFP_OK;
+  }
+}
+
 template <typename T>
 int hrfp_backward(const mrfp_hrfp_plan* P, const float* g_ocout, const float* g_ocout_dec, const float* const* gamma,
                   const int* lut, const char* saved, float* g_xp, char* ws, cudaStream_t s, const DeviceInfo& di,
-                  const NpStem* np, const void* g_dec_nhwc) {
+                  const NpStem* np, const void* g_dec_nhwc, const void* rk_w2t = nullptr) {
+  // rk_w2t != nullptr: g_dec_nhwc is the RANK-K form of that gradient, G (N, h/2, w/2, 64) bf16 with W2T (C, 64) bf16 — it
+  // joins as one more k-block of the stage-4 dgrad and the (N, h/2, w/2, C) tensor never exists
   // g_dec_nhwc: the gradient of OCout_dec already in the chain's layout (N, h/2, w/2, C) and element type — produced by
   // the fused classifier tail (tail_final2.cu) — instead of the fp32 NCHW tensor g_ocout_dec
   double* acc = reinterpret_cast<double*>(ws + P->acc_bwd_off);
@@ -1296,8 +1351,13 @@ int hrfp_backward(const mrfp_hrfp_plan* P, const float* g_ocout, const float* g_
     const float* gin = (k == kHrfpStages - 1) ? g_ocout : (k == 3 ? g_ocout_dec : nullptr);
     if (k == 3 && dec_joined) gin = nullptr;               // already added by the dgrad of stage 4
     if (k == 3 && g_dec_nhwc && !dec_joined) {             // encoder-only backward: the tail's gradient IS dA_3
-      const size_t bytes = (size_t)P->N * st.oh * st.ow * st.cout * sizeof(T);
-      MRFP_CUDA_TRY(cudaMemcpyAsync(g0, g_dec_nhwc, bytes, cudaMemcpyDeviceToDevice, s));
+      if (rk_w2t) {
+        int re = rankk_expand<T>(g_dec_nhwc, rk_w2t, g0, (long long)P->N * st.oh * st.ow, st.cout, di, s);
+        if (re) return re;
+      } else {
+        const size_t bytes = (size_t)P->N * st.oh * st.ow * st.cout * sizeof(T);
+        MRFP_CUDA_TRY(cudaMemcpyAsync(g0, g_dec_nhwc, bytes, cudaMemcpyDeviceToDevice, s));
+      }
       dA = g0; other = g1; at_end = true;
     }
     if (gin) {
@@ -1337,7 +1397,19 @@ int hrfp_backward(const mrfp_hrfp_plan* P, const float* g_ocout, const float* g_
       // buffer apply(4) has just finished reading and let the conv epilogue add it in fp32 (one rounding, and the
       // read-modify-write pass over dA_3 disappears)
       const T* add_src = nullptr;
-      if (k == 4 && g_dec_nhwc) {
+      const void* rk = nullptr;
+      if (k == 4 && g_dec_nhwc && rk_w2t && gathered) {      // rank-K: G and W2T travel through the dgrad's weight ring
+        add_src = static_cast<const T*>(g_dec_nhwc);
+        rk = rk_w2t;
+        dec_joined = true;
+      } else if (k == 4 && g_dec_nhwc && rk_w2t) {           // ... unless the dgrad is the tap kernel: expand into the buffer
+        const HrfpStage& pv = P->st[3];                      // apply(4) has just finished reading
+        int re = rankk_expand<T>(g_dec_nhwc, rk_w2t, dA, (long long)P->N * pv.oh * pv.ow, pv.cout, di, s);
+        if (re) return re;
+        add_src = dA;
+        dec_joined = true;
+        at_end = true;
+      } else if (k == 4 && g_dec_nhwc) {
         add_src = static_cast<const T*>(g_dec_nhwc);
         dec_joined = true;
       } else if (k == 4 && g_ocout_dec) {
@@ -1351,7 +1423,7 @@ int hrfp_backward(const mrfp_hrfp_plan* P, const float* g_ocout, const float* g_
       if (gathered)
         rc = conv3x3_gather_bwd(Y, dA, st.oh, st.ow, lut + st.lo_h, lut + st.lo_w, P->lut.data() + st.lo_h, P->lut.data() + st.lo_w,
                                 st.max_rep, stats, gamma[k], a, (double)P->N * st.oh * st.ow, st.cout_real, saved + st.wb_off, other,
-                                P->N, st.ch, st.cw, st.cout, st.cin, st.dil, s, at_end, add_src, &P->maps_g[1][k]);
+                                P->N, st.ch, st.cw, st.cout, st.cin, st.dil, s, at_end, add_src, &P->maps_g[1][k], rk);
       else
         rc = conv3x3_tc(dY, saved + st.wb_off, other, P->esize, P->N, st.ch, st.cw, st.cout, st.cin, st.dil, nullptr, nullptr,
                         nullptr, s, at_end, nullptr, add_src, &P->maps[1][k]);
@@ -1549,10 +1621,11 @@ static int hrfp_fwd_entry(const mrfp_hrfp_plan_t* P, const float* xp, const floa
 
 static int hrfp_bwd_entry(const mrfp_hrfp_plan_t* P, const float* g_ocout, const float* g_ocout_dec,
                           const float* const* gamma, const void* lut, const void* saved, float* g_xp, void* ws,
-                          void* stream, const NpStem* np, const void* g_dec_nhwc = nullptr) {
+                          void* stream, const NpStem* np, const void* g_dec_nhwc = nullptr, const void* rk_w2t = nullptr) {
   if (!P || P->magic != kPlanMagic) return MRFP_ERR_BAD_PLAN;
   if (!gamma || !lut || !saved || !g_xp || !ws) return MRFP_ERR_NULL_POINTER;
   if (g_dec_nhwc && (g_ocout_dec || P->mode == MRFP_MATH_FP32 || ((uintptr_t)g_dec_nhwc & 15))) return MRFP_ERR_UNSUPPORTED;
+  if (rk_w2t && (!g_dec_nhwc || P->mode != MRFP_MATH_BF16 || ((uintptr_t)rk_w2t & 15))) return MRFP_ERR_UNSUPPORTED;
   if (((uintptr_t)saved | (uintptr_t)ws | (uintptr_t)lut) & 255) return MRFP_ERR_WORKSPACE;
   DeviceInfo di;
   int rc = get_device_info(&di);
@@ -1561,7 +1634,7 @@ static int hrfp_bwd_entry(const mrfp_hrfp_plan_t* P, const float* g_ocout, const
   std::lock_guard<std::mutex> lock(P->mu);
   if (P->mode == MRFP_MATH_BF16)
     return hrfp_backward<__nv_bfloat16>(P, g_ocout, g_ocout_dec, gamma, (const int*)lut, (const char*)saved, g_xp,
-                                        (char*)ws, s, di, np, g_dec_nhwc);
+                                        (char*)ws, s, di, np, g_dec_nhwc, rk_w2t);
   return hrfp_backward<float>(P, g_ocout, g_ocout_dec, gamma, (const int*)lut, (const char*)saved, g_xp, (char*)ws, s, di,
                               np, g_dec_nhwc);
 }
@@ -1632,6 +1705,21 @@ extern "C" int mrfp_hrfp_bwd_nhwc(const mrfp_hrfp_plan_t* P, const float* g_ocou
     return hrfp_bwd_entry(P, g_ocout, nullptr, gamma, lut, saved, g_xp, ws, stream, &np, g_dec_nhwc);
   }
   return hrfp_bwd_entry(P, g_ocout, nullptr, gamma, lut, saved, g_xp, ws, stream, nullptr, g_dec_nhwc);
+}
+
+// ... and with that gradient in its RANK-K form (mrfp_hrfp_tail_final2_bwd_rk): g64 (N, h/2, w/2, 64) bf16 = the classifier's
+// incoming gradient per pixel, w2t (C, 64) bf16 = the classifier transposed; classes beyond K are zero in both.
+extern "C" int mrfp_hrfp_bwd_rk(const mrfp_hrfp_plan_t* P, const float* g_ocout, const void* g64, const void* w2t,
+                                const float* const* gamma, const float* np_alpha, const float* np_eps, const float* np_mean,
+                                void* np_ws, const void* lut, const void* saved, float* g_xp, void* ws, void* stream) {
+  if (!g64 || !w2t) return MRFP_ERR_NULL_POINTER;
+  if (np_alpha || np_eps || np_mean || np_ws) {
+    NpStem np;
+    if (!np_stem_setup(P, np_alpha, np_eps, const_cast<float*>(np_mean), nullptr, np_ws, &np))
+      return (P && P->magic == kPlanMagic) ? MRFP_ERR_NULL_POINTER : MRFP_ERR_BAD_PLAN;
+    return hrfp_bwd_entry(P, g_ocout, nullptr, gamma, lut, saved, g_xp, ws, stream, &np, g64, w2t);
+  }
+  return hrfp_bwd_entry(P, g_ocout, nullptr, gamma, lut, saved, g_xp, ws, stream, nullptr, g64, w2t);
 }
 
 template <typename T>

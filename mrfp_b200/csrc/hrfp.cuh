@@ -34,8 +34,9 @@ struct HrfpStage {
 // the three TMA descriptors of one convolution launch; a plan keeps one per (stage, direction) and re-encodes only
 // when a buffer address changes
 struct ConvMaps {
-  CUtensorMap in, w, out;
+  CUtensorMap in, w, out, aux;   // aux: the second operand of a rank-K term (conv_gather.cu)
   const void* key[3];
+  const void* key_aux;
   int valid;
 };
 // the two descriptors of one classifier-tail launch (tail_final2.cu): Y_3 as [pixel][256 ch], and the fp32 side input
@@ -116,7 +117,8 @@ int conv3x3_gather_fwd(const void* y_prev, int SH, int SW, const int* idx_h, con
 int conv3x3_gather_bwd(const void* y, const void* dA, int OH, int OW, const int* lo_h, const int* lo_w, const int* host_lo_h,
                        const int* host_lo_w, int max_rep, const float* stats, const float* gamma, const double* acc, double count,
                        int c_real, const void* wpack, void* out, int N, int H, int W, int cin, int cout, int dil,
-                       cudaStream_t stream, bool reverse_tiles, const void* add_src, ConvMaps* cache);
+                       cudaStream_t stream, bool reverse_tiles, const void* add_src, ConvMaps* cache,
+                       const void* rk_w2t = nullptr);
 
 // NP+ per-plane coefficients from plane totals (hrfp.cu; one block, C <= kMaxC).  forward: psum = sum_hw x -> coef = (a, b)
 // with out = a*x + b, mean_out / beta_out side arrays;  backward: psum = sum_hw g, mean_in = the forward's plane means ->

@@ -309,11 +309,14 @@ constexpr size_t kBwdSmem = 1024 + (size_t)2 * kSpanBytes + (size_t)32 * kPx * 2
                              // + the index tables: (wtiles * 65 + OH) ints
 
 // backward: warp = channels [32 warp, +32) in both products.  g_tma: g arrives as one [K][64] box per tile; otherwise
-// (rows of g not 16-byte aligned) through plain loads
+// (rows of g not 16-byte aligned) through plain loads.  g64 != nullptr: the RANK-K form — instead of dA = W2^T g the kernel
+// leaves g itself as bf16 (N, OH, OW, 64) (classes beyond K zero) and W2T (256, 64) bf16 in w2t64; the stage-4 dgrad takes
+// the product as one more k-block of its accumulation (conv_gather.cu, ADD == 2) and dA never exists
 __global__ void __launch_bounds__(kThreads, 2)
 tail_final2_bwd_kernel(const __grid_constant__ CUtensorMap tm_y, const __grid_constant__ CUtensorMap tm_g, const TailArgs a,
                         const float* __restrict__ gsrc, int g_tma, __nv_bfloat16* __restrict__ dA, float* __restrict__ gW2,
-                        float* __restrict__ gb2, int wtiles, int num_tiles) {
+                        float* __restrict__ gb2, int wtiles, int num_tiles, __nv_bfloat16* __restrict__ g64,
+                        __nv_bfloat16* __restrict__ w2t64) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   unsigned char* ysm = smem_1k(smem_raw);                          // [2][4 boxes][64 px][64 ch bf16]
   unsigned char* gC = ysm + (size_t)2 * kSpanBytes;               // [32 classes][64 px bf16]   (128-byte rows, swizzled)
@@ -339,6 +342,11 @@ tail_final2_bwd_kernel(const __grid_constant__ CUtensorMap tm_y, const __grid_co
     *reinterpret_cast<__nv_bfloat16*>(ysm + c * 64 + (((k >> 3) ^ ((c >> 1) & 3)) << 4) + (k & 7) * 2) = __float2bfloat16_rn(v);
   }
   for (int e = t; e < 2 * 32 * kPx; e += kThreads) gF[e] = 0.f;    // rows of classes >= K stay zero from here on
+  if (g64 != nullptr && blockIdx.x == 0)                            // rank-K form: the classifier transposed, (256, 64) bf16
+    for (int e = t; e < kC * 64; e += kThreads) {
+      const int c = e >> 6, k = e & 63;
+      w2t64[e] = __float2bfloat16_rn(k < K ? a.w2[k * kC + c] : 0.f);
+    }
   for (int e = t; e < wtiles * kPx; e += kThreads) rel[e] = a.idx_w[min(e, a.OW - 1)] - a.idx_w[e & ~(kPx - 1)];
   for (int e = t; e < wtiles; e += kThreads) wstart[e] = a.idx_w[e * kPx];
   for (int e = t; e < a.OH; e += kThreads) hsrc[e] = a.idx_h[e];
@@ -420,35 +428,51 @@ tail_final2_bwd_kernel(const __grid_constant__ CUtensorMap tm_y, const __grid_co
     TR(4);
     const uint32_t ybase = smem_u32(ysm) + (uint32_t)b * kSpanBytes;
 
-    // ---- (1) dA3[px][ch] = sum_k g[k][px] W2[k][ch]: A fragments by ldmatrix.trans from gC, results leave from registers ----
-#pragma unroll 2
-    for (int mt = 0; mt < kPx / 16; ++mt) {
-      uint32_t af[2][4];
+    if (g64 != nullptr) {
+      // ---- (1') rank-K form: the tile of g as bf16 [pixel][64 classes]; 8 pixels x 128 contiguous bytes per warp store ----
+      const float* gb = gF + (size_t)b * 32 * kPx;
+      const int px = t >> 2, quarter = t & 3;          // 16 classes = 32 bytes per thread
+      if (c.w0 + px < a.OW) {
+        uint32_t pk[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+        if (quarter < 2) {
 #pragma unroll
-      for (int kb = 0; kb < 2; ++kb) {                 // matrices: (px 0-7 | px 8-15) x (classes 16 kb + 0-7 | + 8-15)
-        const int cls = 16 * kb + (amat >> 1) * 8 + (lane & 7), chunk = 2 * mt + (amat & 1);
-        ldsm_x4_t(smem_u32(gC + cls * 128 + ((chunk ^ (cls & 7)) << 4)), af[kb]);
-      }
-      float acc[4][4];
-#pragma unroll
-      for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-#pragma unroll
-      for (int np = 0; np < 2; ++np)
-#pragma unroll
-        for (int kb = 0; kb < 2; ++kb) {
-          mma_bf16(acc[2 * np], af[kb], w1b[np][kb][0], w1b[np][kb][1]);
-          mma_bf16(acc[2 * np + 1], af[kb], w1b[np][kb][2], w1b[np][kb][3]);
+          for (int j = 0; j < 8; ++j) pk[j] = pack_bf16(gb[(16 * quarter + 2 * j) * kPx + px], gb[(16 * quarter + 2 * j + 1) * kPx + px]);
         }
-      uint32_t r0[4], r1[4];
+        uint4* dst = reinterpret_cast<uint4*>(g64 + (((size_t)c.n * a.OH + c.oh) * a.OW + c.w0 + px) * 64 + 16 * quarter);
+        dst[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        dst[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+      }
+    } else {
+      // ---- (1) dA3[px][ch] = sum_k g[k][px] W2[k][ch]: A fragments by ldmatrix.trans from gC, results leave from registers ----
+#pragma unroll 2
+      for (int mt = 0; mt < kPx / 16; ++mt) {
+        uint32_t af[2][4];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) { r0[j] = pack_bf16(acc[j][0], acc[j][1]); r1[j] = pack_bf16(acc[j][2], acc[j][3]); }
-      const uint4 o0 = quad_transpose(r0, tq), o1 = quad_transpose(r1, tq);     // channels 32 warp + 8 tq + 0..7
-      const int p0 = 16 * mt + g8, p1 = p0 + 8;
-      __nv_bfloat16* drow = dA + (((size_t)c.n * a.OH + c.oh) * a.OW + c.w0) * kC + 32 * warp + 8 * tq;
-      if (c.w0 + p0 < a.OW) *reinterpret_cast<uint4*>(drow + (size_t)p0 * kC) = o0;
-      if (c.w0 + p1 < a.OW) *reinterpret_cast<uint4*>(drow + (size_t)p1 * kC) = o1;
+        for (int kb = 0; kb < 2; ++kb) {                 // matrices: (px 0-7 | px 8-15) x (classes 16 kb + 0-7 | + 8-15)
+          const int cls = 16 * kb + (amat >> 1) * 8 + (lane & 7), chunk = 2 * mt + (amat & 1);
+          ldsm_x4_t(smem_u32(gC + cls * 128 + ((chunk ^ (cls & 7)) << 4)), af[kb]);
+        }
+        float acc[4][4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+#pragma unroll
+        for (int np = 0; np < 2; ++np)
+#pragma unroll
+          for (int kb = 0; kb < 2; ++kb) {
+            mma_bf16(acc[2 * np], af[kb], w1b[np][kb][0], w1b[np][kb][1]);
+            mma_bf16(acc[2 * np + 1], af[kb], w1b[np][kb][2], w1b[np][kb][3]);
+          }
+        uint32_t r0[4], r1[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { r0[j] = pack_bf16(acc[j][0], acc[j][1]); r1[j] = pack_bf16(acc[j][2], acc[j][3]); }
+        const uint4 o0 = quad_transpose(r0, tq), o1 = quad_transpose(r1, tq);     // channels 32 warp + 8 tq + 0..7
+        const int p0 = 16 * mt + g8, p1 = p0 + 8;
+        __nv_bfloat16* drow = dA + (((size_t)c.n * a.OH + c.oh) * a.OW + c.w0) * kC + 32 * warp + 8 * tq;
+        if (c.w0 + p0 < a.OW) *reinterpret_cast<uint4*>(drow + (size_t)p0 * kC) = o0;
+        if (c.w0 + p1 < a.OW) *reinterpret_cast<uint4*>(drow + (size_t)p1 * kC) = o1;
+      }
     }
 
     TR(5);
@@ -582,11 +606,11 @@ extern "C" int mrfp_hrfp_tail_final2_fwd(const mrfp_hrfp_plan_t* P, const void* 
   return MRFP_OK;
 }
 
-extern "C" int mrfp_hrfp_tail_final2_bwd(const mrfp_hrfp_plan_t* P, const void* saved, const void* lut, const float* g,
-                                         const float* w2, int K, void* g_dec_nhwc, float* g_w2, float* g_b2, void* stream) {
+static int tail_bwd_launch(const mrfp_hrfp_plan_t* P, const void* saved, const void* lut, const float* g, const float* w2, int K,
+                           void* g_dec_nhwc, void* g64, void* w2t64, float* g_w2, float* g_b2, void* stream) {
   if (!P || P->magic != kPlanMagic) return MRFP_ERR_BAD_PLAN;
-  if (!saved || !lut || !g || !w2 || !g_dec_nhwc || !g_w2 || !g_b2) return MRFP_ERR_NULL_POINTER;
-  if ((uintptr_t)g_dec_nhwc & 15) return MRFP_ERR_WORKSPACE;
+  if (!saved || !lut || !g || !w2 || !g_w2 || !g_b2 || (!g_dec_nhwc && !(g64 && w2t64))) return MRFP_ERR_NULL_POINTER;
+  if (((uintptr_t)g_dec_nhwc | (uintptr_t)g64 | (uintptr_t)w2t64) & 15) return MRFP_ERR_WORKSPACE;
   TailArgs a;
   int rc = tail_args(P, saved, lut, w2, K, &a);
   if (rc) return rc;
@@ -608,9 +632,23 @@ extern "C" int mrfp_hrfp_tail_final2_bwd(const mrfp_hrfp_plan_t* P, const void* 
   if (smem > (size_t)di.max_smem_optin) return MRFP_ERR_UNSUPPORTED;
   MRFP_SMEM_OPT_IN(tail_final2_bwd_kernel, di.max_smem_optin, di.device);
   launch_k(tail_final2_bwd_kernel, dim3(grid), dim3(kThreads), smem, s, tm.y, tm.aux, a, g, g_tma,
-           reinterpret_cast<__nv_bfloat16*>(g_dec_nhwc), g_w2, g_b2, wtiles, (int)tiles);
+           reinterpret_cast<__nv_bfloat16*>(g_dec_nhwc), g_w2, g_b2, wtiles, (int)tiles, reinterpret_cast<__nv_bfloat16*>(g64),
+           reinterpret_cast<__nv_bfloat16*>(w2t64));
   MRFP_CUDA_TRY(cudaGetLastError());
   return MRFP_OK;
+}
+
+extern "C" int mrfp_hrfp_tail_final2_bwd(const mrfp_hrfp_plan_t* P, const void* saved, const void* lut, const float* g,
+                                         const float* w2, int K, void* g_dec_nhwc, float* g_w2, float* g_b2, void* stream) {
+  if (!g_dec_nhwc) return MRFP_ERR_NULL_POINTER;
+  return tail_bwd_launch(P, saved, lut, g, w2, K, g_dec_nhwc, nullptr, nullptr, g_w2, g_b2, stream);
+}
+
+extern "C" int mrfp_hrfp_tail_final2_bwd_rk(const mrfp_hrfp_plan_t* P, const void* saved, const void* lut, const float* g,
+                                            const float* w2, int K, void* g64, void* w2t64, float* g_w2, float* g_b2,
+                                            void* stream) {
+  if (!g64 || !w2t64) return MRFP_ERR_NULL_POINTER;
+  return tail_bwd_launch(P, saved, lut, g, w2, K, nullptr, g64, w2t64, g_w2, g_b2, stream);
 }
 
 #ifdef MRFP_TAIL_TRACE

@@ -201,11 +201,13 @@ class _HrfpFn(torch.autograd.Function):
         g_out = next(gi) if ctx.want_out else None
         g_dec = next(gi) if ctx.want_dec else None
         g_dec_nhwc = None
+        g_rk = None
         if ctx.mail is not None:             # the real gradient was parked by the tail's backward
             g_dec = ctx.mail["g"]
             ctx.mail["g"] = None
             g_dec_nhwc = ctx.mail.pop("g_nhwc", None)      # fused classifier tail: already NHWC in the chain's element type
-            if g_dec_nhwc is not None and g_dec is not None:
+            g_rk = ctx.mail.pop("g_rk", None)              # ... or its rank-K form (g64, w2t64)
+            if (g_dec_nhwc is not None or g_rk is not None) and g_dec is not None:
                 raise _lib.MrfpError("OCout_dec was consumed both by the fused classifier tail and by a plain HRFP+ add")
         dev = plan.device
         g_out_c = g_out.contiguous() if g_out is not None else None
@@ -216,7 +218,15 @@ class _HrfpFn(torch.autograd.Function):
             ga = _ptr_array(ctx.gammas)
             ws = plan.workspace()
             with torch.cuda.device(dev):
-                if g_dec_nhwc is not None:
+                if g_rk is not None:
+                    a_, e_, m_ = ctx.np if ctx.np is not None else (None, None, None)
+                    w_ = _lib.scratch(dev, lib.mrfp_hrfp_np_ws_bytes(plan.n, plan.cin), "hrfp_np") if ctx.np is not None else None
+                    rc = lib.mrfp_hrfp_bwd_rk(plan.handle, None if g_out_c is None else g_out_c.data_ptr(), g_rk[0].data_ptr(),
+                                              g_rk[1].data_ptr(), ga, None if a_ is None else a_.data_ptr(),
+                                              None if e_ is None else e_.data_ptr(), None if m_ is None else m_.data_ptr(),
+                                              None if w_ is None else w_.data_ptr(), plan.lut.data_ptr(), ctx.saved_buf.data_ptr(),
+                                              g_xp.data_ptr(), ws.data_ptr(), _stream_ptr(dev))
+                elif g_dec_nhwc is not None:
                     a_, e_, m_ = ctx.np if ctx.np is not None else (None, None, None)
                     w_ = _lib.scratch(dev, lib.mrfp_hrfp_np_ws_bytes(plan.n, plan.cin), "hrfp_np") if ctx.np is not None else None
                     rc = lib.mrfp_hrfp_bwd_nhwc(plan.handle, None if g_out_c is None else g_out_c.data_ptr(), g_dec_nhwc.data_ptr(),
@@ -408,17 +418,28 @@ class _TailFinal2Fn(torch.autograd.Function):
         k = ctx.w2.shape[0]
         gc = g.contiguous()
         g_t = bilinear_up_backward(gc, ctx.lo) if ctx.needs_input_grad[0] else None
-        g_nhwc = torch.empty((n, oh, ow, c), dtype=torch.bfloat16, device=g.device)
         g_w2 = torch.empty((k, c), dtype=torch.float32, device=g.device)
         g_b2 = torch.empty((k,), dtype=torch.float32, device=g.device)
-        with torch.cuda.device(g.device):
-            rc = lib.mrfp_hrfp_tail_final2_bwd(plan.handle, handle.saved.data_ptr(), plan.lut.data_ptr(), gc.data_ptr(),
-                                               ctx.w2.data_ptr(), k, g_nhwc.data_ptr(), g_w2.data_ptr(), g_b2.data_ptr(),
-                                               _stream_ptr(g.device))
-        _lib.check(rc, "mrfp_hrfp_tail_final2_bwd")
-        if handle.mail.get("g_nhwc") is not None or handle.mail.get("g") is not None:
+        if handle.mail.get("g_nhwc") is not None or handle.mail.get("g_rk") is not None or handle.mail.get("g") is not None:
             raise _lib.MrfpError("OCout_dec handle consumed twice")
-        handle.mail["g_nhwc"] = g_nhwc
+        if os.environ.get("MRFP_TAIL_RANKK", "1") != "0":
+            # rank-K form: W2^T g joins the chain as its two factors (include/mrfp_b200.h: mrfp_hrfp_bwd_rk)
+            g64 = torch.empty((n, oh, ow, 64), dtype=torch.bfloat16, device=g.device)
+            w2t = torch.empty((c, 64), dtype=torch.bfloat16, device=g.device)
+            with torch.cuda.device(g.device):
+                rc = lib.mrfp_hrfp_tail_final2_bwd_rk(plan.handle, handle.saved.data_ptr(), plan.lut.data_ptr(), gc.data_ptr(),
+                                                      ctx.w2.data_ptr(), k, g64.data_ptr(), w2t.data_ptr(), g_w2.data_ptr(),
+                                                      g_b2.data_ptr(), _stream_ptr(g.device))
+            _lib.check(rc, "mrfp_hrfp_tail_final2_bwd_rk")
+            handle.mail["g_rk"] = (g64, w2t)
+        else:
+            g_nhwc = torch.empty((n, oh, ow, c), dtype=torch.bfloat16, device=g.device)
+            with torch.cuda.device(g.device):
+                rc = lib.mrfp_hrfp_tail_final2_bwd(plan.handle, handle.saved.data_ptr(), plan.lut.data_ptr(), gc.data_ptr(),
+                                                   ctx.w2.data_ptr(), k, g_nhwc.data_ptr(), g_w2.data_ptr(), g_b2.data_ptr(),
+                                                   _stream_ptr(g.device))
+            _lib.check(rc, "mrfp_hrfp_tail_final2_bwd")
+            handle.mail["g_nhwc"] = g_nhwc
         return (g_t, g_w2.reshape(ctx.wshape) if ctx.needs_input_grad[1] else None,
                 g_b2 if (ctx.has_bias and ctx.needs_input_grad[2]) else None,
                 torch.zeros(1, dtype=torch.float32, device=g.device), None)

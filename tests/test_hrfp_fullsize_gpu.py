@@ -239,6 +239,11 @@ def test_classifier_tail_at_benchmarked_shape():
     out = hrfp_plus_final2(da, final2, dec)
     out.backward(g)
     g_nhwc = dec.mail.get("g_nhwc")                                # (N, h/2, w/2, 256) bf16: the rank-K gradient of OCout_dec
+    if g_nhwc is None and dec.mail.get("g_rk") is not None:        # ... left as its two factors (mrfp_hrfp_tail_final2_bwd_rk)
+        g64, w2t = dec.mail["g_rk"]
+        assert float(g64[..., k:].abs().max()) == 0.0 and float(w2t[:, k:].abs().max()) == 0.0
+        assert torch.equal(g64[..., :k], g.bfloat16().permute(0, 2, 3, 1)) and torch.equal(w2t[:, :k], final2.weight.detach().reshape(k, 256).bfloat16().t())
+        g_nhwc = g64.double() @ w2t.double().t()
     full = hrfp_plus_add_upsampled(d1, chain()).double().requires_grad_(True)
     w64 = final2.weight.detach().double().requires_grad_(True); b64 = final2.bias.detach().double().requires_grad_(True)
     ref = F.conv2d(full, w64, b64)

@@ -446,3 +446,37 @@ def test_tail_fused_through_the_classifier_equals_the_unfused_tail(geom):
     _, dec = hrfp_chain(xp, convs, bns, h, w, want_out=False, math_mode=2, lazy_dec=True, update_running_stats=False)
     got = hrfp_plus_final2(d_lo, final2, dec)
     assert float((got.double() - ref).norm() / ref.norm()) <= 5e-3
+
+
+@pytest.mark.parametrize("geom", [(2, 96, 80, (24, 20), 19), (1, 96, 544, (24, 136), 7)])
+def test_rank_k_form_of_the_tail_gradient_in_the_full_chain(geom, monkeypatch):
+    """The gradient of OCout_dec out of the fused classifier tail is W2^T g (rank K): by default it joins the chain as its two
+    factors and the stage-4 dgrad accumulates their product as one more k-block (mrfp_hrfp_tail_final2_bwd_rk + mrfp_hrfp_bwd_rk,
+    conv_gather.cu ADD == 2) — against the materialised (N, h/2, w/2, 256) bf16 tensor added in that dgrad's epilogue
+    (MRFP_TAIL_RANKK=0) and against the unfused tail; full chain, so that the stage-4 dgrad runs."""
+    from mrfp_b200.hrfp import hrfp_chain, hrfp_plus_add_upsampled, hrfp_plus_final2
+    n, h, w, lo, k = geom
+    xh, xw = math.ceil(h / 4), math.ceil(w / 4)
+    ws, gs = make_hrfp_params(81)
+    convs, bns = _modules(ws, gs, "cuda")
+    torch.manual_seed(82)
+    final2 = torch.nn.Conv2d(256, k, 1, bias=True).cuda()
+    xp = torch.from_numpy(make_feat(83, (n, 64, xh, xw))).cuda()
+    d_lo = torch.randn(n, 256, *lo, device="cuda")
+    g = torch.randn(n, k, h // 2, w // 2, device="cuda")
+    gx = torch.randn(n, 64, xh, xw, device="cuda")
+    res = {}
+    for name in ("rank_k", "materialised", "unfused"):
+        monkeypatch.setenv("MRFP_TAIL_RANKK", "0" if name == "materialised" else "1")
+        final2.zero_grad(set_to_none=True)
+        xa = xp.clone().requires_grad_(True); da = d_lo.clone().requires_grad_(True)
+        x, dec = hrfp_chain(xa, convs, bns, h, w, math_mode=2, lazy_dec=True, update_running_stats=False)
+        out = hrfp_plus_final2(da, final2, dec) if name != "unfused" else final2(hrfp_plus_add_upsampled(da, dec))
+        torch.autograd.backward([x, out], [gx, g])
+        res[name] = [t.detach().clone() for t in (out, da.grad, final2.weight.grad, xa.grad)]
+    rel = lambda a, b: float((a.double() - b.double()).norm() / b.double().norm())
+    for i, nm in enumerate(("dec2", "g_dec1", "g_W2")):
+        assert rel(res["rank_k"][i], res["materialised"][i]) <= 1e-5, nm      # the same kernels up to the atomics' order
+    assert rel(res["rank_k"][3], res["materialised"][3]) <= 2e-2              # one rounding instead of two on the way into dA_3
+    assert rel(res["rank_k"][3], res["unfused"][3]) <= TOL_VS_BF16_ORACLE["bwd"]
+    assert rel(res["materialised"][3], res["unfused"][3]) <= TOL_VS_BF16_ORACLE["bwd"]

@@ -24,10 +24,15 @@ def dump(path):
     xp = torch.relu(torch.randn(n, 64, 192, 192, device=dev))
     d1 = torch.randn(n, 256, 192, 192, device=dev)
     g = torch.randn(n, 19, 384, 384, device=dev)
+    g_x = torch.randn(n, 64, 192, 192, device=dev)
     xa = xp.clone().requires_grad_(True); da = d1.clone().requires_grad_(True)
-    _, dec = H.hrfp_chain(xa, convs, bns, h, w, want_out=False, math_mode=H.MATH_BF16, lazy_dec=True, update_running_stats=False)
+    full = os.environ.get("AB_TAIL_ENCODER_ONLY", "0") == "0"      # full chain: the tail's gradient joins in the stage-4 dgrad
+    x, dec = H.hrfp_chain(xa, convs, bns, h, w, want_out=full, math_mode=H.MATH_BF16, lazy_dec=True, update_running_stats=False)
     out = H.hrfp_plus_final2(da, final2, dec)
-    out.backward(g)
+    if full:
+        torch.autograd.backward([x, out], [g_x, g])
+    else:
+        out.backward(g)
     res = dict(out=out.detach(), g_d1=da.grad, g_w2=final2.weight.grad.clone(), g_b2=final2.bias.grad.clone(), g_xp=xa.grad)
     # fp64 from the materialised decoder feature of the same chain
     _, dec = H.hrfp_chain(xp, convs, bns, h, w, want_out=False, math_mode=H.MATH_BF16, lazy_dec=True, update_running_stats=False)
