@@ -101,7 +101,7 @@ def run_reference(args):
     print(json.dumps(line))
 
 
-def traffic_from_profiles(kernel_substr, file_hints=("",), prefixes=("R2b_", "R2_", "r9_", "r5_", "r3_")):
+def traffic_from_profiles(kernel_substr, file_hints=("",), prefixes=("R2c_", "R2b_", "R2_", "r9_", "r5_", "r3_")):
     """dram__bytes_read.sum + dram__bytes_write.sum of one launch of the kernel, read from the newest committed
     `ncu --set full` export under profiles/ (`ncu -i ... --page raw --csv`: header row, unit row, one value row)."""
     import csv
@@ -599,7 +599,7 @@ def run_ours(args):
     # for it: forward stage 0 = conv3x3_tc_kernel on the stem feature; forward stages 1-7 = conv3x3_gather_kernel<fwd> (the
     # resample + BN + ReLU of the previous stage built into the operand, BN statistics in the epilogue); dgrads of the
     # wide up-sampling stages 2-3 = conv3x3_tc_kernel on dY; the other dgrads = conv3x3_gather_kernel<bwd | bwd-rep> (BN-backward
-    # apply built into the operand; stage 4 also adds the OCout_dec gradient)
+    # apply built into the operand; stage 4 also takes the classifier tail's gradient as a rank-K k-block)
     import ctypes
     fn = lib.mrfp_debug_conv3x3_bf16
     fn.restype = ctypes.c_int
@@ -611,6 +611,10 @@ def run_ours(args):
     bfn.restype = ctypes.c_int
     bfn.argtypes = ([ctypes.c_void_p] * 2 + [ctypes.c_int] * 2 + [ctypes.c_void_p] * 4 + [ctypes.c_int] + [ctypes.c_void_p] * 3 +
                     [ctypes.c_double] + [ctypes.c_void_p] * 2 + [ctypes.c_int] * 6 + [ctypes.c_void_p] * 2)
+    rfn = lib.mrfp_debug_conv3x3_gather_bwd_rk     # stage 4: the classifier tail's gradient joins as a rank-K k-block
+    rfn.restype = ctypes.c_int
+    rfn.argtypes = ([ctypes.c_void_p] * 2 + [ctypes.c_int] * 2 + [ctypes.c_void_p] * 7 + [ctypes.c_double] + [ctypes.c_void_p] * 2 +
+                    [ctypes.c_int] * 6 + [ctypes.c_void_p] * 3)
     plan = H.get_plan(n, 64, XH, XW, H_IMG, W_IMG, dev, H.MATH_BF16)
 
     def nearest_idx(src, dst):          # ATen's rule in float32 (size= form; the tables only shape the access pattern here)
@@ -666,13 +670,23 @@ def run_ours(args):
             low_c = torch.searchsorted(iw, torch.arange(cw + 1)).to(torch.int32).contiguous()
             loh, low = loh_c.to(dev), low_c.to(dev)
             rep = 2 if k < 4 else 1                     # up-sampling stages: up to 2 x 2 replicas of a source pixel
-            add = torch.randn(n, ch, cw, cin, device=dev).to(torch.bfloat16) if k == 4 else None
-            t = time_launch(lambda: ok(bfn(yk.data_ptr(), da.data_ptr(), oh, ow, loh.data_ptr(), low.data_ptr(), loh_c.data_ptr(),
-                                           low_c.data_ptr(), rep, stats_t.data_ptr(), gamma_t.data_ptr(), acc_t.data_ptr(),
-                                           float(n * oh * ow), wpb.data_ptr(), gout.data_ptr(), n, ch, cw, cout, cin, dil,
-                                           None if add is None else add.data_ptr(), st)), 5)
-            kern = f"conv3x3_gather_kernel<{cin}, {'bwd-rep' if k < 4 else 'bwd'}{', add' if k == 4 else ''}>"
-            del yk, da, add
+            if k == 4:      # as the chain launches it: + G (pixels, 64) . W2T (256, 64)^T, the classifier tail's gradient
+                g64 = torch.zeros(n, ch, cw, 64, device=dev, dtype=torch.bfloat16)
+                g64[..., :N_CLASSES] = torch.randn(n, ch, cw, N_CLASSES, device=dev).to(torch.bfloat16)
+                w2t = torch.zeros(cin, 64, device=dev, dtype=torch.bfloat16)
+                w2t[:, :N_CLASSES] = (0.05 * torch.randn(cin, N_CLASSES, device=dev)).to(torch.bfloat16)
+                t = time_launch(lambda: ok(rfn(yk.data_ptr(), da.data_ptr(), oh, ow, loh.data_ptr(), low.data_ptr(), loh_c.data_ptr(),
+                                               low_c.data_ptr(), stats_t.data_ptr(), gamma_t.data_ptr(), acc_t.data_ptr(),
+                                               float(n * oh * ow), wpb.data_ptr(), gout.data_ptr(), n, ch, cw, cout, cin, dil,
+                                               g64.data_ptr(), w2t.data_ptr(), st)), 5)
+                del g64, w2t
+            else:
+                t = time_launch(lambda: ok(bfn(yk.data_ptr(), da.data_ptr(), oh, ow, loh.data_ptr(), low.data_ptr(), loh_c.data_ptr(),
+                                               low_c.data_ptr(), rep, stats_t.data_ptr(), gamma_t.data_ptr(), acc_t.data_ptr(),
+                                               float(n * oh * ow), wpb.data_ptr(), gout.data_ptr(), n, ch, cw, cout, cin, dil,
+                                               None, st)), 5)
+            kern = f"conv3x3_gather_kernel<{cin}, {'bwd-rep' if k < 4 else 'bwd'}{', rank-K' if k == 4 else ''}>"
+            del yk, da
         dgrad_rows.append({"stage": k, "kernel": kern, "cin": cout, "cout": cin, "hw": [ch, cw], "us": t * 1e3, "tflops": fl / t / 1e9})
         del wp, wpb, gout
     top = max(conv_rows + dgrad_rows, key=lambda r: r["us"])

@@ -760,3 +760,11 @@ extern "C" int mrfp_debug_conv3x3_gather_bwd(const void* y, const void* dA, int 
   return mrfp::conv3x3_gather_bwd(y, dA, OH, OW, lo_h, lo_w, host_lo_h, host_lo_w, max_rep, stats, gamma, acc, count, cin, wpack, out, N,
                                   H, W, cin, cout, dil, (cudaStream_t)stream, false, add_src, nullptr, nullptr);
 }
+// ... the stage-4 form with the rank-K term: g64 (N, H, W, 64) bf16 and w2t (cout, 64) bf16 (see conv3x3_gather_kernel, ADD == 2)
+extern "C" int mrfp_debug_conv3x3_gather_bwd_rk(const void* y, const void* dA, int OH, int OW, const int* lo_h, const int* lo_w,
+                                                const int* host_lo_h, const int* host_lo_w, const float* stats, const float* gamma,
+                                                const double* acc, double count, const void* wpack, void* out, int N, int H, int W,
+                                                int cin, int cout, int dil, const void* g64, const void* w2t, void* stream) {
+  return mrfp::conv3x3_gather_bwd(y, dA, OH, OW, lo_h, lo_w, host_lo_h, host_lo_w, 1, stats, gamma, acc, count, cin, wpack, out, N, H, W,
+                                  cin, cout, dil, (cudaStream_t)stream, false, g64, nullptr, w2t);
+}
